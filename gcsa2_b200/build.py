@@ -1,0 +1,40 @@
+"""Builds gcsa2_b200/libgcsa2_b200.so in-tree: nvcc for sm_100a (engine.cu) + g++ (builder.cpp).
+
+The shared library is self-contained (static cudart), so it travels to the GPU box with the
+snapshot and loads on a CPU-only machine too (symbol checks in the CPU test-suite)."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libgcsa2_b200.so")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include", "gcsa2_b200.h")
+
+NVCC = os.environ.get("GCSA_B200_NVCC", "nvcc")
+CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC,-fopenmp", "-Wno-deprecated-gpu-targets"]
+CXX_FLAGS = ["-O2", "-march=x86-64-v2", "-std=c++17", "-fopenmp", "-fPIC", "-Wall", "-Wextra"]
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build(force=False, verbose=False):
+    engine_cu, builder_cpp = os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "builder.cpp")
+    engine_o, builder_o = os.path.join(CSRC, "engine.o"), os.path.join(CSRC, "builder.o")
+    if not force and not _stale(LIB, [engine_cu, builder_cpp, INCLUDE]):
+        return LIB
+    run = lambda cmd: subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL)
+    run([NVCC] + NVCC_FLAGS + ["-c", engine_cu, "-o", engine_o])
+    run([CXX] + CXX_FLAGS + ["-c", builder_cpp, "-o", builder_o])
+    run([NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB, engine_o, builder_o, "-Xcompiler", "-fopenmp", "-lgomp"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -1,0 +1,116 @@
+"""Host-side index construction: graph -> kmers -> FlatGCSA / FlatLCP.
+
+Thin wrapper over the C++ builder (gcsa2_b200/csrc/builder.cpp) through the C ABI.  Stands in
+for build_gcsa / GCSA::GCSA(InputGraph&, ...) of the reference (src/gcsa.cpp:447-724) for
+in-memory inputs; construction stays on the CPU.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+from .flat import FlatGCSA, FlatLCP, SIGMA, words_for
+
+
+@dataclass
+class CharGraph:
+    """A graph of single-character nodes in CSR form (struct gcsa_b200_graph)."""
+    comp: np.ndarray            # uint8[n]
+    value: np.ndarray           # uint64[n] node_type
+    succ_offsets: np.ndarray    # uint64[n + 1]
+    succ: np.ndarray            # uint64[edges]
+    sink: int
+    sources: np.ndarray         # uint64[], nodes that get predecessor '$' (technical edge sink -> source)
+
+    @property
+    def nodes(self):
+        return int(self.comp.size)
+
+    @staticmethod
+    def from_lists(comps, values, succ, sources, sink):
+        offsets = np.zeros(len(comps) + 1, dtype=np.uint64)
+        offsets[1:] = np.cumsum([len(s) for s in succ])
+        flat = np.array([w for s in succ for w in s], dtype=np.uint64)
+        return CharGraph(comp=np.array(comps, dtype=np.uint8), value=np.array(values, dtype=np.uint64),
+                         succ_offsets=offsets, succ=flat, sink=int(sink), sources=np.array(sources, dtype=np.uint64))
+
+
+@dataclass
+class KMers:
+    """KMer records of the reference (include/gcsa/support.h:475-497): key = label << 16 |
+    predecessor mask << 8 | successor mask; one record per (kmer, successor position)."""
+    key: np.ndarray
+    from_: np.ndarray
+    to: np.ndarray
+    k: int
+
+    def labels(self):
+        """Decoded labels (comp tuples), for tests."""
+        lab = self.key >> np.uint64(16)
+        return [tuple(int((x >> np.uint64(3 * (self.k - 1 - i))) & np.uint64(7)) for i in range(self.k)) for x in lab]
+
+    def write_binary(self, path):
+        """Binary .graph format of the reference: 24-byte GraphFileHeader {flags, kmer_count,
+        kmer_length} followed by 24-byte KMer {key, from, to} records (include/gcsa/files.h:40-52,
+        src/files.cpp:127-187)."""
+        with open(path, "wb") as f:
+            np.array([0, self.key.size, self.k], dtype=np.uint64).tofile(f)
+            rec = np.empty((self.key.size, 3), dtype=np.uint64)
+            rec[:, 0], rec[:, 1], rec[:, 2] = self.key, self.from_, self.to
+            rec.tofile(f)
+
+
+def enumerate_kmers(graph, k):
+    g = capi.Graph()
+    comp = np.ascontiguousarray(graph.comp, dtype=np.uint8)
+    value = capi.as_u64(graph.value); offs = capi.as_u64(graph.succ_offsets)
+    succ = capi.as_u64(graph.succ); sources = capi.as_u64(graph.sources)
+    g.nodes, g.comp, g.value = graph.nodes, comp.ctypes.data, value.ctypes.data
+    g.succ_offsets, g.succ, g.sink = offs.ctypes.data, succ.ctypes.data, int(graph.sink)
+    g.n_sources, g.sources = int(np.asarray(graph.sources).size), sources.ctypes.data
+    out = capi.Kmers()
+    capi.check(capi.lib().gcsa_b200_enumerate_kmers(C.byref(g), int(k), C.byref(out)))
+    n = int(out.n)
+    def take(p):
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(max(n, 1),))[:n].copy()
+    res = KMers(key=take(out.key), from_=take(out.from_), to=take(out.to), k=int(k))
+    capi.lib().gcsa_b200_kmers_free(C.byref(out))
+    return res
+
+
+def build_from_kmers(kmers, doubling_steps, sample_period=64, lcp_branching=64, allow_inconsistent=False):
+    """-> (FlatGCSA, FlatLCP).  Raises GCSAError(ERR_INCONSISTENT) if the kmers do not describe a
+    graph whose order-K pruned de Bruijn graph satisfies the GCSA invariants."""
+    key, frm, to = capi.as_u64(kmers.key), capi.as_u64(kmers.from_), capi.as_u64(kmers.to)
+    built = capi.Built()
+    rc = capi.lib().gcsa_b200_build_from_kmers(key.ctypes.data, frm.ctypes.data, to.ctypes.data, int(kmers.key.size),
+                                               int(kmers.k), int(doubling_steps), int(sample_period), C.byref(built))
+    capi.check(rc, allow=(capi.ERR_INCONSISTENT,) if allow_inconsistent else ())
+    f = built.index
+    def bits(p, n_bits):
+        n = words_for(n_bits) + 1
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(n,)).copy()
+    N = int(f.path_nodes)
+    flat = FlatGCSA(
+        path_nodes=N, edge_count=int(f.edge_count), order=int(f.order),
+        C=np.array([f.C[i] for i in range(SIGMA + 1)], dtype=np.uint64),
+        bwt=[bits(f.bwt[c], N) for c in range(SIGMA)],
+        edges=bits(f.edges, f.edge_count), sampled_paths=bits(f.sampled_paths, N),
+        sample_count=int(f.sample_count),
+        stored_samples=np.ctypeslib.as_array(C.cast(f.stored_samples, C.POINTER(C.c_uint64)),
+                                             shape=(max(1, int(f.sample_count)),))[:int(f.sample_count)].copy(),
+        samples=bits(f.samples, f.sample_count), extra_filter=bits(f.extra_filter, N),
+        extra_values_len=int(f.extra_values_len), extra_values=bits(f.extra_values, f.extra_values_len),
+        redundant_len=int(f.redundant_len), redundant=bits(f.redundant, f.redundant_len))
+    lcp = np.ctypeslib.as_array(C.cast(built.lcp, C.POINTER(C.c_uint8)), shape=(max(1, int(built.lcp_size)),))[:int(built.lcp_size)].copy()
+    capi.lib().gcsa_b200_built_free(C.byref(built))
+    flat.consistent = (rc == 0)
+    return flat, FlatLCP.from_values(lcp, branching=lcp_branching)
+
+
+def build_index(graph, k, doubling_steps, sample_period=64, lcp_branching=64, allow_inconsistent=False):
+    """graph -> order k * 2^steps index; returns (FlatGCSA, FlatLCP, KMers)."""
+    kmers = enumerate_kmers(graph, k)
+    flat, lcp = build_from_kmers(kmers, doubling_steps, sample_period, lcp_branching, allow_inconsistent)
+    return flat, lcp, kmers

@@ -1,0 +1,1686 @@
+/*
+  engine.cu -- B200 (sm_100a) batched backward-search engine behind the C ABI of
+  include/gcsa2_b200.h.  Hand-written CUDA; no tensor cores (integer rank/select work).
+
+  Device layout (DESIGN.md "Data layout in HBM"):
+
+  * FUSED BWT BLOCKS.  The four fast characters (A,C,G,T; fast_bwt[1..4] of
+    include/gcsa/gcsa.h:217-219) are interleaved: block b covers path nodes [87b, 87b+87) and is
+    one 128-byte line of four 32-byte sectors, one per character c:
+        w0 = (C[c] + rank(B_c, 87b))            [40 bits] | B_c bits 64..86   [23 bits] << 40
+        w1 = B_c bits 0..63 of the block
+        w2 = rank(edges, P - 1)                 [40 bits] | window bits 64..87 [24 bits] << 40
+        w3 = window bits 0..63,   window bit t = edges[P - 1 + t],  P = C[c] + rank(B_c, 87b)
+    so that one endpoint of GCSA::LF(range, c) (include/gcsa/gcsa.h:155-162, 253-274) -- the B_c
+    rank AND the dependent rank on `edges` -- is ONE 32-byte sector read (LDG.E.256) instead of
+    two cache-line probes in two vectors, and GCSA::LF(node) (gcsa.h:165-183) is one 128-byte line.
+  * RANK VECTORS (edges, sampled_paths, SadaSparse::filter): 32-byte sectors {cumulative count,
+    192 data bits}; a rank probe or bit access is one sector.
+  * SELECT VECTORS (SadaSparse::values, SadaCount::data): rank vector + one hint per 512 ones.
+  * samples/select (gcsa.h:235-236) is replaced by an explicit start-offset array per sampled node.
+  * sparse characters ($, N, #; sparse_bwt of gcsa.h:221-223) are sorted position lists.
+  * optional k-mer table: find() results of all 4^k ACGT strings of length k (16 bytes each).
+*/
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <random>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+#include "../../include/gcsa2_b200.h"
+
+typedef uint64_t u64;
+typedef unsigned long long ull;
+typedef unsigned int u32;
+typedef unsigned char u8;
+
+#define BWT_W 87u
+#define RV_W 192u
+#define SEL_HINT 512u
+#define M40 ((1ull << 40) - 1)
+
+//------------------------------------------------------------------------------
+// Errors
+//------------------------------------------------------------------------------
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+
+#define CUDA_TRY(expr) do { cudaError_t e_ = (expr); if(e_ != cudaSuccess) { \
+  return fail(GCSA_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } } while(0)
+
+//------------------------------------------------------------------------------
+// Device views
+//------------------------------------------------------------------------------
+
+struct RankVecDev { const ulonglong4* sec; u64 n_bits; u64 n_sec; };
+struct SelVecDev  { RankVecDev rv; const u32* hints; u64 ones; };
+
+struct DevView
+{
+  u64 path_nodes, edge_count;
+  u64 C[GCSA_B200_SIGMA + 1];
+  u64 char_sp[GCSA_B200_SIGMA], char_ep[GCSA_B200_SIGMA];
+  const ulonglong4* bwt;
+  RankVecDev edges, sampled, extra_filter;
+  SelVecDev extra_values, redundant;
+  const u64* sparse_pos[3]; u64 sparse_n[3];       // comps 0, 5, 6
+  const u64* stored_samples; const u64* sample_start; u64 sample_count;
+  const ulonglong2* table; int table_k;
+  u8 char2comp[256];
+};
+
+struct LcpView
+{
+  u64 size, branching, levels, values;
+  u64 offsets[16];
+  const u8* data;
+};
+
+//------------------------------------------------------------------------------
+// Device primitives
+//------------------------------------------------------------------------------
+
+__device__ __forceinline__ ulonglong4 ld256(const ulonglong4* p)
+{
+  ulonglong4 r;
+  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.x), "=l"(r.y), "=l"(r.z), "=l"(r.w) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ bool range_empty(u64 sp, u64 ep) { return (sp + 1 > ep + 1); }   // utils.h:93-101
+
+// ones among the low k bits of w, 0 <= k <= 64
+__device__ __forceinline__ u32 popc_low(u64 w, u32 k)
+{
+  u64 m = (k >= 64 ? ~0ull : ((1ull << k) - 1));
+  return (u32)__popcll(w & m);
+}
+
+// ones among the low k bits of the (up to) 88-bit string hi:lo, 0 <= k <= 88
+__device__ __forceinline__ u32 popc_low88(u64 lo, u32 hi, u32 k)
+{
+  u32 klo = (k < 64 ? k : 64), khi = k - klo;
+  return popc_low(lo, klo) + (u32)__popc(hi & ((1u << khi) - 1));
+}
+
+__device__ __forceinline__ u64 rv_rank(const RankVecDev& v, u64 i)
+{
+  u64 s = i / RV_W; u32 off = (u32)(i - s * RV_W);
+  ulonglong4 q = ld256(v.sec + s);
+  u32 w = off >> 6, r = off & 63;
+  u64 res = q.x;
+  if(w > 0) { res += __popcll(q.y); }
+  if(w > 1) { res += __popcll(q.z); }
+  u64 word = (w == 0 ? q.y : (w == 1 ? q.z : q.w));
+  return res + popc_low(word, r);
+}
+
+// bit i and rank(i) from one sector
+__device__ __forceinline__ bool rv_get_rank(const RankVecDev& v, u64 i, u64& rank)
+{
+  u64 s = i / RV_W; u32 off = (u32)(i - s * RV_W);
+  ulonglong4 q = ld256(v.sec + s);
+  u32 w = off >> 6, r = off & 63;
+  u64 res = q.x;
+  if(w > 0) { res += __popcll(q.y); }
+  if(w > 1) { res += __popcll(q.z); }
+  u64 word = (w == 0 ? q.y : (w == 1 ? q.z : q.w));
+  rank = res + popc_low(word, r);
+  return (word >> r) & 1;
+}
+
+// position of the j-th (1-based) set bit of w; w has at least j set bits
+__device__ __forceinline__ u32 select_in_word(u64 w, u32 j)
+{
+  u32 lo = (u32)w, c = __popc(lo);
+  if(j <= c) { return __fns(lo, 0, j); }
+  return 32 + __fns((u32)(w >> 32), 0, j - c);
+}
+
+// select1(k), k >= 1 (SadaCount / SadaSparse selects, support.h:253, 324)
+__device__ __forceinline__ u64 sv_select(const SelVecDev& v, u64 k)
+{
+  u64 h = (k - 1) / SEL_HINT;
+  u64 lo = v.hints[h], hi = v.hints[h + 1];
+  // last sector in [lo, hi] whose cumulative count is < k
+  while(lo < hi)
+  {
+    u64 mid = lo + (hi - lo + 1) / 2;
+    u64 cum = __ldg(&(v.rv.sec[mid].x));
+    if(cum < k) { lo = mid; } else { hi = mid - 1; }
+  }
+  ulonglong4 q = ld256(v.rv.sec + lo);
+  u32 need = (u32)(k - q.x);
+  u32 c0 = __popcll(q.y), c1 = __popcll(q.z);
+  u64 base = lo * RV_W;
+  if(need <= c0) { return base + select_in_word(q.y, need); }
+  need -= c0;
+  if(need <= c1) { return base + 64 + select_in_word(q.z, need); }
+  need -= c1;
+  return base + 128 + select_in_word(q.w, need);
+}
+
+// number of list entries < i
+__device__ __forceinline__ u64 sparse_rank(const u64* pos, u64 n, u64 i)
+{
+  u64 lo = 0, hi = n;
+  while(lo < hi)
+  {
+    u64 mid = (lo + hi) >> 1;
+    if(__ldg(pos + mid) < i) { lo = mid + 1; } else { hi = mid; }
+  }
+  return lo;
+}
+
+__device__ __forceinline__ int sparse_slot(u32 c) { return (c == 0 ? 0 : (int)c - 4); }   // 0,5,6 -> 0,1,2
+
+/*
+  GCSA::LF(range, comp), include/gcsa/gcsa.h:155-162 with 262-274 and pathNodeRange 253-258.
+  Fast characters: one fused sector per endpoint.  Sparse characters: list rank + edges rank.
+*/
+__device__ __forceinline__ void lf_range(const DevView& v, u64 sp, u64 ep, u32 c, u64& osp, u64& oep, u32* sectors = nullptr)
+{
+  if(c >= 1 && c <= GCSA_B200_FAST_CHARS)
+  {
+    u64 e1 = ep + 1;
+    u64 bs = sp / BWT_W, be = e1 / BWT_W;
+    u32 os = (u32)(sp - bs * BWT_W), oe = (u32)(e1 - be * BWT_W);
+    ulonglong4 a = ld256(v.bwt + bs * 4 + (c - 1));
+    ulonglong4 b = a;
+    if(be != bs) { b = ld256(v.bwt + be * 4 + (c - 1)); }
+    if(sectors) { *sectors += (be != bs ? 2 : 1); }
+    u32 js = popc_low88(a.y, (u32)(a.x >> 40), os);
+    u32 je = popc_low88(b.y, (u32)(b.x >> 40), oe);
+    u64 f = (a.x & M40) + js;
+    u64 s = (b.x & M40) + je - 1;
+    if(range_empty(f, s)) { osp = f; oep = s; return; }
+    osp = (a.z & M40) + popc_low88(a.w, (u32)(a.z >> 40), js + 1);
+    oep = (b.z & M40) + popc_low88(b.w, (u32)(b.z >> 40), je);
+  }
+  else if(c < GCSA_B200_SIGMA)
+  {
+    int slot = sparse_slot(c);
+    u64 f = v.C[c] + sparse_rank(v.sparse_pos[slot], v.sparse_n[slot], sp);
+    u64 s = v.C[c] + sparse_rank(v.sparse_pos[slot], v.sparse_n[slot], ep + 1) - 1;
+    if(range_empty(f, s)) { osp = f; oep = s; return; }
+    osp = rv_rank(v.edges, f);
+    oep = rv_rank(v.edges, s);
+    if(sectors) { *sectors += 2; }
+  }
+  else { osp = 1; oep = 0; }    // not a comp value: Range::empty_range()
+}
+
+/*
+  GCSA::LF(path_node), include/gcsa/gcsa.h:165-183: first predecessor, fast characters first.
+  One 128-byte line holds the four fast sectors of the node's block.
+*/
+__device__ __forceinline__ u64 lf_node(const DevView& v, u64 i)
+{
+  u64 b = i / BWT_W; u32 off = (u32)(i - b * BWT_W);
+  const ulonglong4* line = v.bwt + b * 4;
+  ulonglong4 q[4];
+  #pragma unroll
+  for(int c = 0; c < 4; c++) { q[c] = ld256(line + c); }
+  #pragma unroll
+  for(int c = 0; c < 4; c++)
+  {
+    bool bit = (off < 64 ? (q[c].y >> off) & 1 : ((q[c].x >> 40) >> (off - 64)) & 1);
+    if(bit)
+    {
+      u32 j = popc_low88(q[c].y, (u32)(q[c].x >> 40), off);
+      return (q[c].z & M40) + popc_low88(q[c].w, (u32)(q[c].z >> 40), j + 1);
+    }
+  }
+  for(u32 c = GCSA_B200_FAST_CHARS + 1; c < GCSA_B200_SIGMA; c++)
+  {
+    int slot = sparse_slot(c);
+    u64 r = sparse_rank(v.sparse_pos[slot], v.sparse_n[slot], i);
+    if(r < v.sparse_n[slot] && v.sparse_pos[slot][r] == i) { return rv_rank(v.edges, v.C[c] + r); }
+  }
+  return rv_rank(v.edges, v.C[0] + sparse_rank(v.sparse_pos[0], v.sparse_n[0], i));
+}
+
+// bit B_c[i] for any comp (used by LF_fast / LF_all single-node shortcut, src/gcsa.cpp:748-756)
+__device__ __forceinline__ bool bwt_bit(const DevView& v, u64 i, u32 c)
+{
+  if(c >= 1 && c <= GCSA_B200_FAST_CHARS)
+  {
+    u64 b = i / BWT_W; u32 off = (u32)(i - b * BWT_W);
+    ulonglong4 q = ld256(v.bwt + b * 4 + (c - 1));
+    return (off < 64 ? (q.y >> off) & 1 : ((q.x >> 40) >> (off - 64)) & 1);
+  }
+  int slot = sparse_slot(c);
+  u64 r = sparse_rank(v.sparse_pos[slot], v.sparse_n[slot], i);
+  return (r < v.sparse_n[slot] && v.sparse_pos[slot][r] == i);
+}
+
+//------------------------------------------------------------------------------
+// Kernels: find
+//------------------------------------------------------------------------------
+
+struct FindStatsDev { u64 found, total_length, lf_steps, sector_probes, table_hits; };
+
+/*
+  GCSA::find(begin, end), include/gcsa/gcsa.h:96-110.  One query per lane; the LF loop advances
+  one character per warp-step.  Queries are pulled from a contiguous per-warp slice; a lane whose
+  range became empty (or whose pattern is exhausted) is refilled on the next step, the
+  assignment being computed with one ballot + popc (no atomics, no shared memory).
+*/
+template<bool STATS>
+__global__ void __launch_bounds__(256)
+find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict__ offsets, u64 char_base,
+            u64 n, u64* __restrict__ sp_out, u64* __restrict__ ep_out, FindStatsDev* stats)
+{
+  __shared__ u8 c2c[256];
+  for(int i = threadIdx.x; i < 256; i += blockDim.x) { c2c[i] = v.char2comp[i]; }
+  __syncthreads();
+
+  const u32 lane = threadIdx.x & 31;
+  const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+  // contiguous slice of queries for this warp
+  const u64 per = (n + n_warps - 1) / n_warps;
+  u64 next = warp * per;
+  const u64 slice_end = (next + per < n ? next + per : n);
+  if(next >= n) { return; }
+
+  u64 q = ~0ull, sp = 0, ep = 0, pos = 0, begin = 0;
+  bool live = false;
+  u64 st_found = 0, st_len = 0, st_steps = 0, st_sectors = 0, st_hits = 0;
+
+  while(true)
+  {
+    // refill dead lanes
+    u32 dead = __ballot_sync(0xFFFFFFFFu, !live);
+    if(dead)
+    {
+      u32 my = __popc(dead & ((1u << lane) - 1));
+      if(!live)
+      {
+        u64 cand = next + my;
+        if(cand < slice_end)
+        {
+          q = cand;
+          u64 b = offsets[q] - char_base, e = offsets[q + 1] - char_base;
+          begin = b; live = true;
+          if(e == b || v.path_nodes == 0) { sp = 0; ep = v.path_nodes - 1; pos = b; }
+          else
+          {
+            pos = e - 1;
+            bool used_table = false;
+            if(v.table_k > 0 && e - b >= (u64)v.table_k)
+            {
+              u64 idx = 0; bool ok = true;
+              for(int t = 0; t < v.table_k; t++)
+              {
+                u32 c = c2c[chars[e - 1 - t]];
+                ok = ok && (c >= 1 && c <= 4);
+                idx |= (u64)((c - 1) & 3) << (2 * t);
+              }
+              if(ok)
+              {
+                ulonglong2 r = __ldg(v.table + idx);
+                sp = r.x; ep = r.y; pos = e - v.table_k; used_table = true;
+                if(STATS) { st_hits++; }
+              }
+            }
+            if(!used_table)
+            {
+              u32 c = c2c[chars[pos]];
+              sp = v.char_sp[c]; ep = v.char_ep[c];
+            }
+          }
+        }
+      }
+      next += __popc(dead);
+      if(next > slice_end) { next = slice_end; }
+    }
+    if(__ballot_sync(0xFFFFFFFFu, live) == 0) { break; }
+
+    if(live)
+    {
+      if(range_empty(sp, ep) || pos == begin)
+      {
+        sp_out[q] = sp; ep_out[q] = ep;
+        if(STATS && !range_empty(sp, ep)) { st_found++; st_len += ep + 1 - sp; }
+        live = false;
+      }
+      else
+      {
+        pos--;
+        u32 c = c2c[chars[pos]];
+        u32 sectors = 0;
+        lf_range(v, sp, ep, c, sp, ep, STATS ? &sectors : nullptr);
+        if(STATS) { st_steps++; st_sectors += sectors; }
+      }
+    }
+  }
+
+  if(STATS)
+  {
+    atomicAdd((ull*)&stats->found, (ull)st_found); atomicAdd((ull*)&stats->total_length, (ull)st_len);
+    atomicAdd((ull*)&stats->lf_steps, (ull)st_steps); atomicAdd((ull*)&stats->sector_probes, (ull)st_sectors);
+    atomicAdd((ull*)&stats->table_hits, (ull)st_hits);
+  }
+}
+
+// Fills the k-mer table: entry idx = find() of the string whose t-th character from the END is
+// comp ((idx >> 2t) & 3) + 1.  Early exit exactly as find() does, so empty entries carry the
+// same uncanonicalised pair the full search would return.
+__global__ void __launch_bounds__(256)
+table_kernel(const DevView v, int k, ulonglong2* table)
+{
+  u64 total = 1ull << (2 * k);
+  for(u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x)
+  {
+    u32 c = (u32)(idx & 3) + 1;
+    u64 sp = v.char_sp[c], ep = v.char_ep[c];
+    for(int t = 1; t < k && !range_empty(sp, ep); t++)
+    {
+      c = (u32)((idx >> (2 * t)) & 3) + 1;
+      lf_range(v, sp, ep, c, sp, ep);
+    }
+    table[idx] = make_ulonglong2(sp, ep);
+  }
+}
+
+//------------------------------------------------------------------------------
+// Kernels: LF, count
+//------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+lf_kernel(const DevView v, const u64* __restrict__ sp, const u64* __restrict__ ep, const u8* __restrict__ comp,
+          u64 n, u64* __restrict__ osp, u64* __restrict__ oep)
+{
+  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+  {
+    u64 a, b;
+    lf_range(v, sp[i], ep[i], comp[i], a, b);
+    osp[i] = a; oep[i] = b;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+lf_node_kernel(const DevView v, const u64* __restrict__ nodes, u64 n, u64* __restrict__ out)
+{
+  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+  {
+    out[i] = lf_node(v, nodes[i]);
+  }
+}
+
+// GCSA::LF_fast / LF_all, src/gcsa.cpp:742-798.  One thread per (range, comp).
+__global__ void __launch_bounds__(256)
+lf_multi_kernel(const DevView v, const u64* __restrict__ sp, const u64* __restrict__ ep, u64 n, int all_chars,
+                u64* __restrict__ out)
+{
+  u64 total = n * GCSA_B200_SIGMA;
+  for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x)
+  {
+    u64 i = t / GCSA_B200_SIGMA; u32 c = (u32)(t - i * GCSA_B200_SIGMA);
+    u64 a = 1, b = 0;                                        // Range::empty_range()
+    u32 last = (all_chars ? GCSA_B200_SIGMA - 2 : GCSA_B200_FAST_CHARS);
+    u64 s = sp[i], e = ep[i];
+    if(c >= 1 && c <= last && !range_empty(s, e))
+    {
+      if(s == e)                                             // single path node: follow set bits only
+      {
+        if(bwt_bit(v, s, c)) { lf_range(v, s, e, c, a, b); }
+      }
+      else { lf_range(v, s, e, c, a, b); }
+    }
+    out[t * 2] = a; out[t * 2 + 1] = b;
+  }
+}
+
+// SadaSparse::count, support.h:329-335
+__device__ __forceinline__ u64 sada_sparse_count(const DevView& v, u64 sp, u64 ep)
+{
+  u64 a = rv_rank(v.extra_filter, sp), b = rv_rank(v.extra_filter, ep + 1);
+  if(b <= a) { return 0; }
+  return (sv_select(v.extra_values, b) + 1) - (a > 0 ? sv_select(v.extra_values, a) + 1 : 0);
+}
+
+// SadaCount::count, support.h:255-258
+__device__ __forceinline__ u64 sada_count(const DevView& v, u64 sp, u64 ep)
+{
+  return (sv_select(v.redundant, ep + 1) - ep) - (sp > 0 ? sv_select(v.redundant, sp) + 1 - sp : 0);
+}
+
+// GCSA::count, src/gcsa.cpp:802-809
+__device__ __forceinline__ u64 count_range(const DevView& v, u64 sp, u64 ep)
+{
+  if(range_empty(sp, ep) || ep >= v.path_nodes) { return 0; }
+  u64 res = sada_sparse_count(v, sp, ep) + (ep + 1 - sp);
+  if(ep > sp) { res -= sada_count(v, sp, ep - 1); }
+  return res;
+}
+
+__global__ void __launch_bounds__(256)
+count_kernel(const DevView v, const u64* __restrict__ sp, const u64* __restrict__ ep, u64 n, u64* __restrict__ out)
+{
+  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+  {
+    out[i] = count_range(v, sp[i], ep[i]);
+  }
+}
+
+//------------------------------------------------------------------------------
+// Kernels: locate (src/gcsa.cpp:827-842, 880-896)
+//------------------------------------------------------------------------------
+
+// number of path nodes each range contributes (0 for empty / out-of-range ranges, gcsa.cpp:831)
+__global__ void __launch_bounds__(256)
+locate_lengths_kernel(u64 path_nodes, const u64* __restrict__ sp, const u64* __restrict__ ep, u64 n, u64* __restrict__ len)
+{
+  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+  {
+    u64 s = sp[i], e = ep[i];
+    len[i] = ((range_empty(s, e) || e >= path_nodes) ? 0 : e + 1 - s);
+  }
+}
+
+/*
+  One thread per (range, node): walk LF until a sampled node (locateInternal, gcsa.cpp:882-887),
+  remember (first sample, steps) and how many values the node stores (firstSample, gcsa.h:202-206;
+  the select on `samples` is an explicit offset array here).
+*/
+__global__ void __launch_bounds__(256)
+locate_walk_kernel(const DevView v, const u64* __restrict__ sp, const u64* __restrict__ node_off, u64 n, u64 items,
+                   u64* __restrict__ first, u32* __restrict__ steps_out, u64* __restrict__ cnt)
+{
+  for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < items; t += (u64)gridDim.x * blockDim.x)
+  {
+    // range owning item t: last r with node_off[r] <= t
+    u64 lo = 0, hi = n - 1;
+    while(lo < hi)
+    {
+      u64 mid = lo + (hi - lo + 1) / 2;
+      if(node_off[mid] <= t) { lo = mid; } else { hi = mid - 1; }
+    }
+    u64 node = sp[lo] + (t - node_off[lo]);
+    u32 steps = 0;
+    u64 r;
+    while(!rv_get_rank(v.sampled, node, r)) { node = lf_node(v, node); steps++; }
+    u64 s0 = v.sample_start[r], s1 = v.sample_start[r + 1];
+    first[t] = s0; steps_out[t] = steps; cnt[t] = s1 - s0;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+locate_fill_kernel(const DevView v, u64 items, const u64* __restrict__ first, const u32* __restrict__ steps,
+                   const u64* __restrict__ val_off, u64* __restrict__ raw)
+{
+  for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < items; t += (u64)gridDim.x * blockDim.x)
+  {
+    u64 s0 = first[t], o0 = val_off[t], c = val_off[t + 1] - o0;
+    for(u64 j = 0; j < c; j++) { raw[o0 + j] = v.stored_samples[s0 + j] + steps[t]; }   // gcsa.cpp:893
+  }
+}
+
+// segment boundaries of the raw values, per range: seg[r] = val_off[node_off[r]]
+__global__ void __launch_bounds__(256)
+locate_segments_kernel(const u64* __restrict__ node_off, const u64* __restrict__ val_off, u64 n, u64* __restrict__ seg)
+{
+  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (u64)gridDim.x * blockDim.x)
+  {
+    seg[i] = val_off[node_off[i]];
+  }
+}
+
+// removeDuplicates (utils.h:350-357) after the segmented sort: flag the first copy of each value
+__global__ void __launch_bounds__(256)
+locate_flag_kernel(const u64* __restrict__ sorted, const u64* __restrict__ seg, u64 n, u64 total, u64* __restrict__ flag)
+{
+  for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x)
+  {
+    // segment of t: last r with seg[r] <= t
+    u64 lo = 0, hi = n;
+    while(lo < hi)
+    {
+      u64 mid = lo + (hi - lo + 1) / 2;
+      if(seg[mid] <= t) { lo = mid; } else { hi = mid - 1; }
+    }
+    flag[t] = (t == seg[lo] || sorted[t] != sorted[t - 1]) ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+locate_compact_kernel(const u64* __restrict__ sorted, const u64* __restrict__ flag, const u64* __restrict__ flag_scan,
+                      u64 total, u64* __restrict__ values, u64 capacity)
+{
+  for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x)
+  {
+    if(flag[t] && flag_scan[t] < capacity) { values[flag_scan[t]] = sorted[t]; }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+locate_offsets_kernel(const u64* __restrict__ seg, const u64* __restrict__ flag_scan, u64 n, u64 total, u64 distinct,
+                      u64* __restrict__ out_offsets)
+{
+  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (u64)gridDim.x * blockDim.x)
+  {
+    u64 s = seg[i];
+    out_offsets[i] = (s >= total ? distinct : flag_scan[s]);
+  }
+}
+
+//------------------------------------------------------------------------------
+// Kernels: LCP (src/lcp.cpp:152-200, 276-519)
+//------------------------------------------------------------------------------
+
+struct Pair64 { u64 first, second; };
+
+__device__ __forceinline__ u64 rmt_parent(const LcpView& l, u64 node, u64 level) { return l.offsets[level + 1] + (node - l.offsets[level]) / l.branching; }
+__device__ __forceinline__ u64 rmt_first_sibling(const LcpView& l, u64 node, u64 level) { return node - (node - l.offsets[level]) % l.branching; }
+__device__ __forceinline__ u64 rmt_last_sibling(const LcpView& l, u64 first_child, u64 level)
+{ u64 a = l.offsets[level + 1], b = first_child + l.branching; return (a < b ? a : b) - 1; }
+__device__ __forceinline__ u64 rmt_first_child(const LcpView& l, u64 node, u64 level) { return l.offsets[level - 1] + (node - l.offsets[level]) * l.branching; }
+__device__ __forceinline__ u64 rmt_last_child(const LcpView& l, u64 node, u64 level) { return rmt_last_sibling(l, rmt_first_child(l, node, level), level - 1); }
+__device__ __forceinline__ u64 rmt_level(const LcpView& l, u64 node) { u64 level = 0; while(l.offsets[level + 1] <= node) { level++; } return level; }
+
+template<bool OR_EQUAL> __device__ __forceinline__ bool sv_less(u64 a, u64 b) { return (OR_EQUAL ? a <= b : a < b); }
+
+// lcp.cpp:333-370
+template<bool OR_EQUAL>
+__device__ Pair64 lcp_psv(const LcpView& l, u64 to)
+{
+  Pair64 nf = { l.values, l.values };
+  if(to == 0 || to >= l.size) { return nf; }
+  u64 level = 0, val = l.data[to];
+  Pair64 res = nf;
+  while(to != l.values - 1)
+  {
+    u64 from = rmt_first_sibling(l, to, level), i = to;
+    res = nf;
+    while(i > from) { i--; u64 x = l.data[i]; if(sv_less<OR_EQUAL>(x, val)) { res.first = i; res.second = x; break; } }
+    if(res.first < l.values) { break; }
+    to = rmt_parent(l, to, level); level++;
+  }
+  if(res.first >= l.values) { return res; }
+  while(level > 0)
+  {
+    u64 from = rmt_first_child(l, res.first, level); level--;
+    u64 i = rmt_last_sibling(l, from, level) + 1;
+    res = nf;
+    while(i > from) { i--; u64 x = l.data[i]; if(sv_less<OR_EQUAL>(x, val)) { res.first = i; res.second = x; break; } }
+  }
+  return res;
+}
+
+// lcp.cpp:389-426
+template<bool OR_EQUAL>
+__device__ Pair64 lcp_nsv(const LcpView& l, u64 from)
+{
+  Pair64 nf = { l.values, l.values };
+  if(from + 1 >= l.size) { return nf; }
+  u64 level = 0, val = l.data[from];
+  Pair64 res = nf;
+  while(from != l.values - 1)
+  {
+    u64 to = rmt_last_sibling(l, from, level);
+    res = nf;
+    for(u64 i = from + 1; i <= to; i++) { u64 x = l.data[i]; if(sv_less<OR_EQUAL>(x, val)) { res.first = i; res.second = x; break; } }
+    if(res.first < l.values) { break; }
+    from = rmt_parent(l, from, level); level++;
+  }
+  if(res.first >= l.values) { return res; }
+  while(level > 0)
+  {
+    from = rmt_first_child(l, res.first, level); level--;
+    u64 to = rmt_last_sibling(l, from, level);
+    res = nf;
+    for(u64 i = from; i <= to; i++) { u64 x = l.data[i]; if(sv_less<OR_EQUAL>(x, val)) { res.first = i; res.second = x; break; } }
+  }
+  return res;
+}
+
+/*
+  lcp.cpp:448-513 rmq(sp, ep): leftmost minimum.  The reference collects the right-hand partial
+  sibling groups on a stack and pops them afterwards so that positions are visited left to right;
+  here the right-hand side keeps its own running minimum with "<=" (a later, more-left group wins
+  ties), which yields the same leftmost minimum without a stack.
+*/
+__device__ Pair64 lcp_rmq(const LcpView& l, u64 sp, u64 ep)
+{
+  Pair64 nf = { l.values, l.values };
+  if(sp > ep || ep >= l.size) { return nf; }
+  if(sp == ep) { Pair64 r = { sp, l.data[sp] }; return r; }
+
+  Pair64 res = { l.values, l.size };
+  Pair64 tail = { l.values, ~0ull };
+  u64 level = 0, left = sp, right = ep;
+  while(true)
+  {
+    u64 left_par = rmt_parent(l, left, level), right_par = rmt_parent(l, right, level);
+    if(left_par == right_par)
+    {
+      for(u64 i = left; i <= right; i++) { u64 x = l.data[i]; if(x < res.second) { res.first = i; res.second = x; } }
+      break;
+    }
+    u64 left_child = rmt_first_child(l, left_par, level + 1);
+    if(left != left_child)
+    {
+      u64 last_child = rmt_last_sibling(l, left_child, level);
+      for(u64 i = left; i <= last_child; i++) { u64 x = l.data[i]; if(x < res.second) { res.first = i; res.second = x; } }
+      left_par++;
+    }
+    u64 right_child = rmt_last_child(l, right_par, level + 1);
+    if(right != right_child)
+    {
+      u64 first_child = rmt_first_sibling(l, right_child, level);
+      // this group lies to the LEFT of everything already in tail: it wins ties; inside the group
+      // the leftmost minimum wins.
+      Pair64 grp = { l.values, ~0ull };
+      for(u64 i = first_child; i <= right; i++) { u64 x = l.data[i]; if(x < grp.second) { grp.first = i; grp.second = x; } }
+      if(grp.second <= tail.second) { tail = grp; }
+      right_par--;
+    }
+    if(left_par >= right_par)
+    {
+      if(left_par == right_par) { u64 x = l.data[left_par]; if(x < res.second) { res.first = left_par; res.second = x; } }
+      break;
+    }
+    left = left_par; right = right_par; level++;
+  }
+  if(tail.first < l.values && tail.second < res.second) { res = tail; }
+  if(res.first >= l.values) { return res; }
+
+  level = rmt_level(l, res.first);
+  while(level > 0)
+  {
+    res.first = rmt_first_child(l, res.first, level); level--;
+    while(l.data[res.first] != res.second) { res.first++; }
+  }
+  return res;
+}
+
+// LCPArray::parent(range), lcp.cpp:276-301 with nodeFor (lcp.h:163-175) and root (lcp.h:137)
+__device__ gcsa_b200_stnode lcp_parent(const LcpView& l, u64 sp, u64 ep)
+{
+  gcsa_b200_stnode out;
+  if(sp == 0 && ep == l.size - 1) { out.sp = 0; out.ep = l.size - 1; out.left_lcp = 0; out.right_lcp = 0; out.node_lcp = 0; return out; }
+  u64 left_lcp = l.data[sp];
+  u64 right_lcp = (ep + 1 < l.size ? l.data[ep + 1] : 0);
+  u64 node_lcp = (left_lcp > right_lcp ? left_lcp : right_lcp);
+  Pair64 left = { sp, left_lcp }, right = { ep + 1, right_lcp };
+  if(left_lcp == node_lcp)
+  {
+    left = lcp_psv<false>(l, sp);
+    if(left.first == l.values && left.second == l.values) { left.first = 0; left.second = 0; }
+  }
+  if(right_lcp == node_lcp)
+  {
+    right = lcp_nsv<false>(l, ep + 1);
+    if(right.first == l.values && right.second == l.values) { right.first = l.size; right.second = 0; }
+  }
+  out.sp = left.first; out.ep = right.first - 1; out.left_lcp = left.second; out.right_lcp = right.second; out.node_lcp = node_lcp;
+  return out;
+}
+
+__global__ void __launch_bounds__(256)
+parent_kernel(const LcpView l, const u64* __restrict__ sp, const u64* __restrict__ ep, u64 n, gcsa_b200_stnode* __restrict__ out)
+{
+  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+  {
+    out[i] = lcp_parent(l, sp[i], ep[i]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+depth_kernel(const LcpView l, const u64* __restrict__ sp, const u64* __restrict__ ep, u64 n, u64* __restrict__ out)
+{
+  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+  {
+    u64 s = sp[i], e = ep[i];
+    u64 res = GCSA_B200_UNKNOWN;
+    if(e + 1 - s > 1)                                                  // lcp.cpp:321
+    {
+      Pair64 r = lcp_rmq(l, s + 1, e);
+      if(!(r.first == l.values && r.second == l.values)) { res = r.second; }
+    }
+    out[i] = res;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+lcp_sv_kernel(const LcpView l, int which, const u64* __restrict__ pos, u64 n, u64* __restrict__ opos, u64* __restrict__ oval)
+{
+  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+  {
+    Pair64 r;
+    if(which == 0) { r = lcp_psv<false>(l, pos[i]); }
+    else if(which == 1) { r = lcp_psv<true>(l, pos[i]); }
+    else if(which == 2) { r = lcp_nsv<false>(l, pos[i]); }
+    else { r = lcp_nsv<true>(l, pos[i]); }
+    opos[i] = r.first; oval[i] = r.second;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+lcp_rmq_kernel(const LcpView l, const u64* __restrict__ sp, const u64* __restrict__ ep, u64 n, u64* __restrict__ opos, u64* __restrict__ oval)
+{
+  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+  {
+    Pair64 r = lcp_rmq(l, sp[i], ep[i]);
+    opos[i] = r.first; oval[i] = r.second;
+  }
+}
+
+//------------------------------------------------------------------------------
+// Host side: handles
+//------------------------------------------------------------------------------
+
+struct gcsa_b200_index
+{
+  int device = 0;
+  int sm_count = 148;
+  DevView view;
+  std::vector<void*> allocations;
+  u64 device_bytes = 0;
+  gcsa_flat_index header;            // scalars only (pointers nulled)
+};
+
+struct gcsa_b200_lcp
+{
+  int device = 0;
+  int sm_count = 148;
+  LcpView view;
+  void* data = nullptr;
+};
+
+namespace {
+
+struct HostBits
+{
+  const uint64_t* words; u64 n_bits;
+  inline u64 word(u64 w) const
+  {
+    u64 n_words = (n_bits + 63) / 64;
+    if(words == nullptr || w >= n_words) { return 0; }
+    u64 x = words[w];
+    u64 rem = n_bits - w * 64;
+    if(rem < 64) { x &= ((1ull << rem) - 1); }
+    return x;
+  }
+  // up to 64 bits starting at bit `start` (bits past the end read as 0)
+  inline u64 get(u64 start, u32 len) const
+  {
+    if(len == 0) { return 0; }
+    u64 w = start >> 6; u32 off = start & 63;
+    u64 x = word(w) >> off;
+    if(off && off + len > 64) { x |= word(w + 1) << (64 - off); }
+    if(len < 64) { x &= ((1ull << len) - 1); }
+    return x;
+  }
+};
+
+// ones before each word; cum[n_words] = total
+std::vector<u64> wordCum(const HostBits& b)
+{
+  u64 n_words = (b.n_bits + 63) / 64;
+  std::vector<u64> cum(n_words + 2, 0);
+  for(u64 w = 0; w < n_words; w++) { cum[w + 1] = cum[w] + __builtin_popcountll(b.word(w)); }
+  cum[n_words + 1] = cum[n_words];
+  return cum;
+}
+
+inline u64 hostRank(const HostBits& b, const std::vector<u64>& cum, u64 i)
+{
+  if(i >= b.n_bits) { return cum[(b.n_bits + 63) / 64]; }
+  u64 w = i >> 6; u32 r = i & 63;
+  return cum[w] + (r ? __builtin_popcountll(b.word(w) & ((1ull << r) - 1)) : 0);
+}
+
+int upload(gcsa_b200_index* idx, const void* host, size_t bytes, const void** dev)
+{
+  void* p = nullptr;
+  size_t alloc = std::max<size_t>(bytes, 256);
+  CUDA_TRY(cudaMalloc(&p, alloc));
+  idx->allocations.push_back(p);
+  idx->device_bytes += alloc;
+  if(bytes) { CUDA_TRY(cudaMemcpy(p, host, bytes, cudaMemcpyHostToDevice)); }
+  *dev = p;
+  return 0;
+}
+
+int buildRankVec(gcsa_b200_index* idx, const HostBits& b, RankVecDev* out, std::vector<ulonglong4>* keep = nullptr)
+{
+  u64 n_sec = b.n_bits / RV_W + 1;
+  std::vector<ulonglong4> sec(n_sec);
+  u64 cum = 0;
+  for(u64 s = 0; s < n_sec; s++)
+  {
+    ulonglong4 q;
+    q.x = cum; q.y = b.word(3 * s); q.z = b.word(3 * s + 1); q.w = b.word(3 * s + 2);
+    cum += __builtin_popcountll(q.y) + __builtin_popcountll(q.z) + __builtin_popcountll(q.w);
+    sec[s] = q;
+  }
+  const void* d = nullptr;
+  int rc = upload(idx, sec.data(), sec.size() * sizeof(ulonglong4), &d);
+  if(rc) { return rc; }
+  out->sec = (const ulonglong4*)d; out->n_bits = b.n_bits; out->n_sec = n_sec;
+  if(keep) { keep->swap(sec); }
+  return 0;
+}
+
+int buildSelVec(gcsa_b200_index* idx, const HostBits& b, SelVecDev* out)
+{
+  std::vector<ulonglong4> sec;
+  int rc = buildRankVec(idx, b, &out->rv, &sec);
+  if(rc) { return rc; }
+  u64 ones = 0;
+  if(!sec.empty())
+  {
+    const ulonglong4& q = sec.back();
+    ones = q.x + __builtin_popcountll(q.y) + __builtin_popcountll(q.z) + __builtin_popcountll(q.w);
+  }
+  u64 n_hints = ones / SEL_HINT + 2;
+  std::vector<u32> hints(n_hints, (u32)(sec.size() - 1));
+  u64 h = 0;
+  for(u64 s = 0; s < sec.size() && h < n_hints; s++)
+  {
+    const ulonglong4& q = sec[s];
+    u64 end = q.x + __builtin_popcountll(q.y) + __builtin_popcountll(q.z) + __builtin_popcountll(q.w);
+    while(h < n_hints && h * SEL_HINT + 1 <= end) { if(h * SEL_HINT + 1 > q.x) { hints[h] = (u32)s; } h++; }
+  }
+  const void* d = nullptr;
+  rc = upload(idx, hints.data(), hints.size() * sizeof(u32), &d);
+  if(rc) { return rc; }
+  out->hints = (const u32*)d; out->ones = ones;
+  return 0;
+}
+
+inline int gridFor(u64 n, int sm_count, int per_sm = 8)
+{
+  u64 blocks = (n + 255) / 256;
+  u64 cap = (u64)sm_count * per_sm;
+  return (int)std::max<u64>(1, std::min(blocks, cap));
+}
+
+struct DeviceGuard
+{
+  int prev = 0; bool ok = false;
+  explicit DeviceGuard(int device) { ok = (cudaGetDevice(&prev) == cudaSuccess) && (cudaSetDevice(device) == cudaSuccess); }
+  ~DeviceGuard() { if(ok) { cudaSetDevice(prev); } }
+};
+
+} // namespace
+
+//------------------------------------------------------------------------------
+// C ABI
+//------------------------------------------------------------------------------
+
+const char* gcsa_b200_last_error(void) { return g_last_error.c_str(); }
+const char* gcsa_b200_version(void) { return "gcsa2_b200 0.1 (sm_100a; GCSA v3 / LCP v1 semantics of gcsa2 1.3.0)"; }
+
+int gcsa_b200_device_count(void)
+{
+  int n = 0;
+  if(cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+void gcsa_b200_free(void* p) { std::free(p); }
+
+int gcsa_b200_index_create(const gcsa_flat_index* host, int device, const gcsa_b200_options* options, gcsa_b200_index** out)
+{
+  if(host == nullptr || out == nullptr) { return fail(GCSA_B200_ERR_INVALID, "index_create: null argument"); }
+  *out = nullptr;
+  if(host->sigma != GCSA_B200_SIGMA || host->fast_chars != GCSA_B200_FAST_CHARS)
+  {
+    return fail(GCSA_B200_ERR_INVALID, "index_create: only the default alphabet (sigma 7, 4 fast characters) is supported");
+  }
+  if(host->path_nodes >= (1ull << 40) || host->edge_count >= (1ull << 40))
+  {
+    return fail(GCSA_B200_ERR_INVALID, "index_create: more than 2^40 path nodes or edges");
+  }
+  int n_dev = gcsa_b200_device_count();
+  if(n_dev <= 0) { return fail(GCSA_B200_ERR_CUDA, "index_create: no CUDA device available (this engine has no CPU fallback)"); }
+  if(device < 0 || device >= n_dev) { return fail(GCSA_B200_ERR_INVALID, "index_create: bad device ordinal"); }
+  DeviceGuard guard(device);
+  if(!guard.ok) { return fail(GCSA_B200_ERR_CUDA, "index_create: cudaSetDevice failed"); }
+
+  {
+    cudaMemPool_t pool;
+    if(cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+    {
+      uint64_t keep = ~0ull;      // do not hand stream-ordered allocations back to the OS between calls
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
+  gcsa_b200_index* idx = new gcsa_b200_index();
+  idx->device = device;
+  cudaDeviceGetAttribute(&idx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  idx->header = *host;
+  for(int c = 0; c < GCSA_B200_SIGMA; c++) { idx->header.bwt[c] = nullptr; }
+  idx->header.edges = idx->header.sampled_paths = idx->header.stored_samples = idx->header.samples = nullptr;
+  idx->header.extra_filter = idx->header.extra_values = idx->header.redundant = nullptr;
+
+  DevView& v = idx->view;
+  std::memset(&v, 0, sizeof(v));
+  const u64 N = host->path_nodes;
+  v.path_nodes = N; v.edge_count = host->edge_count;
+  for(int c = 0; c <= GCSA_B200_SIGMA; c++) { v.C[c] = host->C[c]; }
+  std::memcpy(v.char2comp, host->char2comp, 256);
+  for(int i = 0; i < 256; i++) { if(v.char2comp[i] >= GCSA_B200_SIGMA) { delete idx; return fail(GCSA_B200_ERR_INVALID, "index_create: char2comp value out of range"); } }
+
+  int rc = 0;
+  #define TRY_RC(expr) do { rc = (expr); if(rc) { gcsa_b200_index_destroy(idx); return rc; } } while(0)
+
+  HostBits edges = { host->edges, host->edge_count };
+  std::vector<u64> edge_cum = wordCum(edges);
+  TRY_RC(buildRankVec(idx, edges, &v.edges));
+
+  // charRange(comp) = pathNodeRange(C[comp], C[comp+1] - 1), gcsa.h:150-153; C[comp+1] == 0 -> (0, ~0)
+  for(int c = 0; c < GCSA_B200_SIGMA; c++)
+  {
+    if(host->C[c + 1] == 0) { v.char_sp[c] = 0; v.char_ep[c] = ~0ull; }
+    else { v.char_sp[c] = hostRank(edges, edge_cum, host->C[c]); v.char_ep[c] = hostRank(edges, edge_cum, host->C[c + 1] - 1); }
+  }
+
+  // fused BWT blocks
+  {
+    u64 n_blocks = N / BWT_W + 1;
+    std::vector<ulonglong4> blocks(n_blocks * 4);
+    for(int c = 1; c <= GCSA_B200_FAST_CHARS; c++)
+    {
+      HostBits B = { host->bwt[c], N };
+      std::vector<u64> cum = wordCum(B);
+      const u64 Cc = host->C[c];
+      #pragma omp parallel for schedule(static)
+      for(long long bb = 0; bb < (long long)n_blocks; bb++)
+      {
+        u64 b = (u64)bb, start = b * BWT_W;
+        u64 cnt = hostRank(B, cum, start);
+        u64 P = Cc + cnt;
+        u64 blo = B.get(start, 64), bhi = B.get(start + 64, BWT_W - 64);
+        u64 e0, wlo, whi;
+        if(P == 0) { e0 = 0; wlo = edges.get(0, 63) << 1; whi = edges.get(63, 24); }
+        else { e0 = hostRank(edges, edge_cum, P - 1); wlo = edges.get(P - 1, 64); whi = edges.get(P - 1 + 64, 24); }
+        ulonglong4 q;
+        q.x = (P & M40) | (bhi << 40); q.y = blo;
+        q.z = (e0 & M40) | (whi << 40); q.w = wlo;
+        blocks[b * 4 + (c - 1)] = q;
+      }
+    }
+    const void* d = nullptr;
+    TRY_RC(upload(idx, blocks.data(), blocks.size() * sizeof(ulonglong4), &d));
+    v.bwt = (const ulonglong4*)d;
+  }
+
+  // sparse characters
+  {
+    const int comps[3] = { 0, 5, 6 };
+    for(int s = 0; s < 3; s++)
+    {
+      HostBits B = { host->bwt[comps[s]], N };
+      std::vector<u64> pos;
+      u64 n_words = (N + 63) / 64;
+      for(u64 w = 0; w < n_words; w++)
+      {
+        u64 x = B.word(w);
+        while(x) { pos.push_back(w * 64 + __builtin_ctzll(x)); x &= x - 1; }
+      }
+      const void* d = nullptr;
+      TRY_RC(upload(idx, pos.data(), pos.size() * sizeof(u64), &d));
+      v.sparse_pos[s] = (const u64*)d; v.sparse_n[s] = pos.size();
+    }
+  }
+
+  // samples
+  {
+    HostBits sampled = { host->sampled_paths, N };
+    TRY_RC(buildRankVec(idx, sampled, &v.sampled));
+    HostBits last = { host->samples, host->sample_count };
+    std::vector<u64> start; start.push_back(0);
+    u64 n_words = (host->sample_count + 63) / 64;
+    for(u64 w = 0; w < n_words; w++)
+    {
+      u64 x = last.word(w);
+      while(x) { start.push_back(w * 64 + __builtin_ctzll(x) + 1); x &= x - 1; }
+    }
+    start.push_back(host->sample_count);   // guard entry
+    const void* d = nullptr;
+    TRY_RC(upload(idx, start.data(), start.size() * sizeof(u64), &d));
+    v.sample_start = (const u64*)d;
+    TRY_RC(upload(idx, host->stored_samples, host->sample_count * sizeof(u64), &d));
+    v.stored_samples = (const u64*)d; v.sample_count = host->sample_count;
+  }
+
+  // counting structures
+  {
+    HostBits filter = { host->extra_filter, N };
+    TRY_RC(buildRankVec(idx, filter, &v.extra_filter));
+    HostBits values = { host->extra_values, host->extra_values_len };
+    TRY_RC(buildSelVec(idx, values, &v.extra_values));
+    HostBits red = { host->redundant, host->redundant_len };
+    TRY_RC(buildSelVec(idx, red, &v.redundant));
+  }
+
+  // k-mer table
+  int k = (options ? options->kmer_table_k : 0);
+  if(k < 0) { k = 0; }
+  if(k > 15) { k = 15; }
+  if(k > 0 && N > 0)
+  {
+    u64 entries = 1ull << (2 * k);
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, entries * sizeof(ulonglong2));
+    if(e != cudaSuccess) { gcsa_b200_index_destroy(idx); return fail(GCSA_B200_ERR_NOMEM, "index_create: k-mer table allocation failed"); }
+    idx->allocations.push_back(p); idx->device_bytes += entries * sizeof(ulonglong2);
+    table_kernel<<<gridFor(entries, idx->sm_count, 8), 256>>>(v, k, (ulonglong2*)p);
+    e = cudaDeviceSynchronize();
+    if(e != cudaSuccess) { gcsa_b200_index_destroy(idx); return fail(GCSA_B200_ERR_CUDA, std::string("table_kernel: ") + cudaGetErrorString(e)); }
+    v.table = (const ulonglong2*)p; v.table_k = k;
+  }
+  #undef TRY_RC
+
+  *out = idx;
+  return 0;
+}
+
+void gcsa_b200_index_destroy(gcsa_b200_index* index)
+{
+  if(index == nullptr) { return; }
+  DeviceGuard guard(index->device);
+  for(void* p : index->allocations) { cudaFree(p); }
+  delete index;
+}
+
+int gcsa_b200_index_info(const gcsa_b200_index* index, gcsa_b200_info* info)
+{
+  if(index == nullptr || info == nullptr) { return fail(GCSA_B200_ERR_INVALID, "index_info: null argument"); }
+  std::memset(info, 0, sizeof(*info));
+  info->path_nodes = index->header.path_nodes; info->edge_count = index->header.edge_count;
+  info->order = index->header.order; info->sample_count = index->header.sample_count;
+  info->device_bytes = index->device_bytes; info->kmer_table_k = index->view.table_k;
+  info->device = index->device; info->sm_count = index->sm_count;
+  return 0;
+}
+
+int gcsa_b200_char_range(const gcsa_b200_index* index, uint64_t comp, uint64_t* sp, uint64_t* ep)
+{
+  if(index == nullptr || sp == nullptr || ep == nullptr) { return fail(GCSA_B200_ERR_INVALID, "char_range: null argument"); }
+  if(comp >= GCSA_B200_SIGMA) { *sp = 0; *ep = ~0ull; return 0; }
+  *sp = index->view.char_sp[comp]; *ep = index->view.char_ep[comp];
+  return 0;
+}
+
+//------------------------------------------------------------------------------
+// find
+//------------------------------------------------------------------------------
+
+static int launchFind(const gcsa_b200_index* index, const u8* d_chars, const u64* d_offsets, u64 char_base, u64 n,
+                      u64* d_sp, u64* d_ep, FindStatsDev* d_stats, cudaStream_t stream)
+{
+  if(n == 0) { return 0; }
+  // persistent grid: 8 CTAs of 256 threads per SM (2048 resident threads), slices per warp
+  int grid = gridFor(n, index->sm_count, 8);
+  if(d_stats) { find_kernel<true><<<grid, 256, 0, stream>>>(index->view, d_chars, d_offsets, char_base, n, d_sp, d_ep, d_stats); }
+  else { find_kernel<false><<<grid, 256, 0, stream>>>(index->view, d_chars, d_offsets, char_base, n, d_sp, d_ep, nullptr); }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int gcsa_b200_find_batch(const gcsa_b200_index* index, const uint8_t* d_chars, const uint64_t* d_offsets,
+                         uint64_t n, uint64_t* d_sp, uint64_t* d_ep, void* stream)
+{
+  if(index == nullptr || (n > 0 && (d_chars == nullptr || d_offsets == nullptr || d_sp == nullptr || d_ep == nullptr)))
+  {
+    return fail(GCSA_B200_ERR_INVALID, "find_batch: null argument");
+  }
+  DeviceGuard guard(index->device);
+  return launchFind(index, d_chars, (const u64*)d_offsets, 0, n, (u64*)d_sp, (u64*)d_ep, nullptr, (cudaStream_t)stream);
+}
+
+/*
+  Host-buffer find: the batch is cut into chunks that are pipelined over three streams
+  (H2D of chunk i+1 overlaps the kernel of chunk i and the D2H of chunk i-1).
+*/
+static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const uint64_t* offsets, uint64_t n,
+                    uint64_t* sp, uint64_t* ep, gcsa_b200_find_stats* stats)
+{
+  if(index == nullptr || (n > 0 && (chars == nullptr || offsets == nullptr || sp == nullptr || ep == nullptr)))
+  {
+    return fail(GCSA_B200_ERR_INVALID, "find_host: null argument");
+  }
+  if(stats) { std::memset(stats, 0, sizeof(*stats)); stats->queries = n; }
+  if(n == 0) { return 0; }
+  DeviceGuard guard(index->device);
+
+  const int STREAMS = 3;
+  const u64 CHUNK = 1ull << 20;
+  cudaStream_t streams[STREAMS];
+  for(int s = 0; s < STREAMS; s++) { CUDA_TRY(cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking)); }
+  FindStatsDev* d_stats = nullptr;
+  if(stats) { CUDA_TRY(cudaMalloc(&d_stats, sizeof(FindStatsDev))); CUDA_TRY(cudaMemset(d_stats, 0, sizeof(FindStatsDev))); }
+
+  int rc = 0;
+  u64 n_chunks = (n + CHUNK - 1) / CHUNK;
+  for(u64 c = 0; c < n_chunks && rc == 0; c++)
+  {
+    cudaStream_t st = streams[c % STREAMS];
+    u64 q0 = c * CHUNK, q1 = std::min(n, q0 + CHUNK), m = q1 - q0;
+    u64 c0 = offsets[q0], c1 = offsets[q1], bytes = c1 - c0;
+    u8* d_chars = nullptr; u64* d_off = nullptr; u64* d_res = nullptr;
+    cudaError_t e;
+    if((e = cudaMallocAsync(&d_chars, bytes + 16, st)) != cudaSuccess ||
+       (e = cudaMallocAsync(&d_off, (m + 1) * sizeof(u64), st)) != cudaSuccess ||
+       (e = cudaMallocAsync(&d_res, 2 * m * sizeof(u64), st)) != cudaSuccess)
+    { rc = fail(GCSA_B200_ERR_NOMEM, std::string("find_host: ") + cudaGetErrorString(e)); break; }
+    if(bytes) { cudaMemcpyAsync(d_chars, chars + c0, bytes, cudaMemcpyHostToDevice, st); }
+    cudaMemcpyAsync(d_off, offsets + q0, (m + 1) * sizeof(u64), cudaMemcpyHostToDevice, st);
+    rc = launchFind(index, d_chars, d_off, c0, m, d_res, d_res + m, d_stats, st);
+    cudaMemcpyAsync(sp + q0, d_res, m * sizeof(u64), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(ep + q0, d_res + m, m * sizeof(u64), cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(d_chars, st); cudaFreeAsync(d_off, st); cudaFreeAsync(d_res, st);
+  }
+  cudaError_t err = cudaSuccess;
+  for(int s = 0; s < STREAMS; s++)
+  {
+    cudaError_t e = cudaStreamSynchronize(streams[s]);
+    if(e != cudaSuccess) { err = e; }
+  }
+  if(stats && err == cudaSuccess && rc == 0)
+  {
+    FindStatsDev h;
+    err = cudaMemcpy(&h, d_stats, sizeof(h), cudaMemcpyDeviceToHost);
+    stats->found = h.found; stats->total_length = h.total_length; stats->lf_steps = h.lf_steps;
+    stats->sector_probes = h.sector_probes; stats->table_hits = h.table_hits;
+  }
+  if(d_stats) { cudaFree(d_stats); }
+  for(int s = 0; s < STREAMS; s++) { cudaStreamDestroy(streams[s]); }
+  if(rc) { return rc; }
+  if(err != cudaSuccess) { return fail(GCSA_B200_ERR_CUDA, std::string("find_host: ") + cudaGetErrorString(err)); }
+  return 0;
+}
+
+int gcsa_b200_find_host(const gcsa_b200_index* index, const uint8_t* chars, const uint64_t* offsets,
+                        uint64_t n, uint64_t* sp, uint64_t* ep)
+{
+  return findHost(index, chars, offsets, n, sp, ep, nullptr);
+}
+
+int gcsa_b200_find_stats_host(const gcsa_b200_index* index, const uint8_t* chars, const uint64_t* offsets,
+                              uint64_t n, uint64_t* sp, uint64_t* ep, gcsa_b200_find_stats* stats)
+{
+  if(stats == nullptr) { return fail(GCSA_B200_ERR_INVALID, "find_stats_host: null stats"); }
+  return findHost(index, chars, offsets, n, sp, ep, stats);
+}
+
+//------------------------------------------------------------------------------
+// Generic host wrapper: copy inputs, run, copy outputs
+//------------------------------------------------------------------------------
+
+namespace {
+
+struct Scratch
+{
+  cudaStream_t stream = nullptr;
+  std::vector<void*> ptrs;
+  int init() { return (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) == cudaSuccess ? 0 : -1); }
+  template<class T> T* alloc(u64 count)
+  {
+    void* p = nullptr;
+    if(cudaMallocAsync(&p, std::max<u64>(count, 1) * sizeof(T), stream) != cudaSuccess) { return nullptr; }
+    ptrs.push_back(p);
+    return (T*)p;
+  }
+  template<class T> T* in(const T* host, u64 count)
+  {
+    T* p = alloc<T>(count);
+    if(p && count) { cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, stream); }
+    return p;
+  }
+  template<class T> void out(T* host, const T* dev, u64 count)
+  {
+    if(count) { cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, stream); }
+  }
+  cudaError_t finish()
+  {
+    for(void* p : ptrs) { cudaFreeAsync(p, stream); }
+    ptrs.clear();
+    cudaError_t e = cudaStreamSynchronize(stream);
+    cudaStreamDestroy(stream); stream = nullptr;
+    return e;
+  }
+};
+
+} // namespace
+
+#define HOST_PROLOGUE(name, handle) \
+  if((handle) == nullptr) { return fail(GCSA_B200_ERR_INVALID, name ": null handle"); } \
+  DeviceGuard guard((handle)->device); \
+  Scratch sc; if(sc.init()) { return fail(GCSA_B200_ERR_CUDA, name ": cannot create stream"); }
+
+#define HOST_EPILOGUE(name, rc) \
+  { cudaError_t e_ = sc.finish(); if((rc) != 0) { return (rc); } \
+    if(e_ != cudaSuccess) { return fail(GCSA_B200_ERR_CUDA, std::string(name ": ") + cudaGetErrorString(e_)); } return 0; }
+
+int gcsa_b200_lf_batch(const gcsa_b200_index* index, const uint64_t* d_sp, const uint64_t* d_ep,
+                       const uint8_t* d_comp, uint64_t n, uint64_t* d_sp_out, uint64_t* d_ep_out, void* stream)
+{
+  if(index == nullptr) { return fail(GCSA_B200_ERR_INVALID, "lf_batch: null handle"); }
+  if(n == 0) { return 0; }
+  DeviceGuard guard(index->device);
+  lf_kernel<<<gridFor(n, index->sm_count), 256, 0, (cudaStream_t)stream>>>(index->view, (const u64*)d_sp, (const u64*)d_ep, d_comp, n, (u64*)d_sp_out, (u64*)d_ep_out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int gcsa_b200_lf_host(const gcsa_b200_index* index, const uint64_t* sp, const uint64_t* ep,
+                      const uint8_t* comp, uint64_t n, uint64_t* sp_out, uint64_t* ep_out)
+{
+  HOST_PROLOGUE("lf_host", index);
+  u64* a = sc.in((const u64*)sp, n); u64* b = sc.in((const u64*)ep, n); u8* c = sc.in(comp, n);
+  u64* oa = sc.alloc<u64>(n); u64* ob = sc.alloc<u64>(n);
+  int rc = gcsa_b200_lf_batch(index, a, b, c, n, oa, ob, sc.stream);
+  sc.out((u64*)sp_out, oa, n); sc.out((u64*)ep_out, ob, n);
+  HOST_EPILOGUE("lf_host", rc);
+}
+
+int gcsa_b200_lf_node_batch(const gcsa_b200_index* index, const uint64_t* d_nodes, uint64_t n, uint64_t* d_out, void* stream)
+{
+  if(index == nullptr) { return fail(GCSA_B200_ERR_INVALID, "lf_node_batch: null handle"); }
+  if(n == 0) { return 0; }
+  DeviceGuard guard(index->device);
+  lf_node_kernel<<<gridFor(n, index->sm_count), 256, 0, (cudaStream_t)stream>>>(index->view, (const u64*)d_nodes, n, (u64*)d_out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int gcsa_b200_lf_node_host(const gcsa_b200_index* index, const uint64_t* nodes, uint64_t n, uint64_t* out)
+{
+  HOST_PROLOGUE("lf_node_host", index);
+  u64* a = sc.in((const u64*)nodes, n); u64* o = sc.alloc<u64>(n);
+  int rc = gcsa_b200_lf_node_batch(index, a, n, o, sc.stream);
+  sc.out((u64*)out, o, n);
+  HOST_EPILOGUE("lf_node_host", rc);
+}
+
+int gcsa_b200_lf_multi_batch(const gcsa_b200_index* index, const uint64_t* d_sp, const uint64_t* d_ep,
+                             uint64_t n, int all_chars, uint64_t* d_out, void* stream)
+{
+  if(index == nullptr) { return fail(GCSA_B200_ERR_INVALID, "lf_multi_batch: null handle"); }
+  if(n == 0) { return 0; }
+  DeviceGuard guard(index->device);
+  lf_multi_kernel<<<gridFor(n * GCSA_B200_SIGMA, index->sm_count), 256, 0, (cudaStream_t)stream>>>(index->view, (const u64*)d_sp, (const u64*)d_ep, n, all_chars, (u64*)d_out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int gcsa_b200_lf_multi_host(const gcsa_b200_index* index, const uint64_t* sp, const uint64_t* ep,
+                            uint64_t n, int all_chars, uint64_t* out)
+{
+  HOST_PROLOGUE("lf_multi_host", index);
+  u64* a = sc.in((const u64*)sp, n); u64* b = sc.in((const u64*)ep, n);
+  u64* o = sc.alloc<u64>(n * GCSA_B200_SIGMA * 2);
+  int rc = gcsa_b200_lf_multi_batch(index, a, b, n, all_chars, o, sc.stream);
+  sc.out((u64*)out, o, n * GCSA_B200_SIGMA * 2);
+  HOST_EPILOGUE("lf_multi_host", rc);
+}
+
+int gcsa_b200_count_batch(const gcsa_b200_index* index, const uint64_t* d_sp, const uint64_t* d_ep,
+                          uint64_t n, uint64_t* d_out, void* stream)
+{
+  if(index == nullptr) { return fail(GCSA_B200_ERR_INVALID, "count_batch: null handle"); }
+  if(n == 0) { return 0; }
+  DeviceGuard guard(index->device);
+  count_kernel<<<gridFor(n, index->sm_count), 256, 0, (cudaStream_t)stream>>>(index->view, (const u64*)d_sp, (const u64*)d_ep, n, (u64*)d_out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int gcsa_b200_count_host(const gcsa_b200_index* index, const uint64_t* sp, const uint64_t* ep, uint64_t n, uint64_t* out)
+{
+  HOST_PROLOGUE("count_host", index);
+  u64* a = sc.in((const u64*)sp, n); u64* b = sc.in((const u64*)ep, n); u64* o = sc.alloc<u64>(n);
+  int rc = gcsa_b200_count_batch(index, a, b, n, o, sc.stream);
+  sc.out((u64*)out, o, n);
+  HOST_EPILOGUE("count_host", rc);
+}
+
+//------------------------------------------------------------------------------
+// locate
+//------------------------------------------------------------------------------
+
+namespace {
+
+template<class T> int scanExclusive(const T* in, T* out, u64 count, cudaStream_t st)
+{
+  size_t bytes = 0;
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, count, st));
+  void* tmp = nullptr;
+  CUDA_TRY(cudaMallocAsync(&tmp, std::max<size_t>(bytes, 16), st));
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, count, st);
+  cudaFreeAsync(tmp, st);
+  CUDA_TRY(e);
+  return 0;
+}
+
+/*
+  The whole locate pipeline on device buffers.  Outputs: d_out_offsets (n + 1).  If d_values is
+  null or capacity is too small, only the sizes are computed and *needed is set.
+  Temporaries are stream-ordered allocations.
+*/
+int locateDevice(const gcsa_b200_index* index, const u64* d_sp, const u64* d_ep, u64 n,
+                 u64* d_out_offsets, u64* d_values, u64 capacity, u64* needed, cudaStream_t st,
+                 u64** d_values_alloc = nullptr)
+{
+  const DevView& v = index->view;
+  const int sm = index->sm_count;
+  std::vector<void*> tmp;
+  auto alloc = [&](u64 bytes) -> void* { void* p = nullptr; if(cudaMallocAsync(&p, std::max<u64>(bytes, 16), st) != cudaSuccess) { return nullptr; } tmp.push_back(p); return p; };
+  auto cleanup = [&]() { for(void* p : tmp) { cudaFreeAsync(p, st); } tmp.clear(); };
+  #define LOC_TRY(expr) do { cudaError_t e_ = (expr); if(e_ != cudaSuccess) { cleanup(); \
+    return fail(GCSA_B200_ERR_CUDA, std::string("locate: " #expr ": ") + cudaGetErrorString(e_)); } } while(0)
+  #define LOC_RC(expr) do { int rc_ = (expr); if(rc_) { cleanup(); return rc_; } } while(0)
+
+  // 1. nodes per range, exclusive scan
+  u64* len = (u64*)alloc((n + 1) * sizeof(u64));
+  u64* node_off = (u64*)alloc((n + 1) * sizeof(u64));
+  if(!len || !node_off) { cleanup(); return fail(GCSA_B200_ERR_NOMEM, "locate: out of device memory"); }
+  LOC_TRY(cudaMemsetAsync(len, 0, (n + 1) * sizeof(u64), st));
+  locate_lengths_kernel<<<gridFor(n, sm), 256, 0, st>>>(v.path_nodes, d_sp, d_ep, n, len);
+  LOC_RC(scanExclusive(len, node_off, n + 1, st));
+  u64 items = 0;
+  LOC_TRY(cudaMemcpyAsync(&items, node_off + n, sizeof(u64), cudaMemcpyDeviceToHost, st));
+  LOC_TRY(cudaStreamSynchronize(st));
+
+  if(items == 0)
+  {
+    LOC_TRY(cudaMemsetAsync(d_out_offsets, 0, (n + 1) * sizeof(u64), st));
+    if(needed) { *needed = 0; }
+    cleanup();
+    return 0;
+  }
+
+  // 2. walk every node to its sample
+  u64* first = (u64*)alloc(items * sizeof(u64));
+  u32* steps = (u32*)alloc(items * sizeof(u32));
+  u64* cnt = (u64*)alloc((items + 1) * sizeof(u64));
+  u64* val_off = (u64*)alloc((items + 1) * sizeof(u64));
+  if(!first || !steps || !cnt || !val_off) { cleanup(); return fail(GCSA_B200_ERR_NOMEM, "locate: out of device memory"); }
+  LOC_TRY(cudaMemsetAsync(cnt + items, 0, sizeof(u64), st));
+  locate_walk_kernel<<<gridFor(items, sm), 256, 0, st>>>(v, d_sp, node_off, n, items, first, steps, cnt);
+  LOC_RC(scanExclusive(cnt, val_off, items + 1, st));
+  u64 total = 0;
+  LOC_TRY(cudaMemcpyAsync(&total, val_off + items, sizeof(u64), cudaMemcpyDeviceToHost, st));
+  LOC_TRY(cudaStreamSynchronize(st));
+
+  // 3. fill, segmented sort, unique
+  u64* raw = (u64*)alloc(total * sizeof(u64));
+  u64* sorted = (u64*)alloc(total * sizeof(u64));
+  u64* seg = (u64*)alloc((n + 1) * sizeof(u64));
+  u64* flag = (u64*)alloc((total + 1) * sizeof(u64));
+  u64* flag_scan = (u64*)alloc((total + 1) * sizeof(u64));
+  if(!raw || !sorted || !seg || !flag || !flag_scan) { cleanup(); return fail(GCSA_B200_ERR_NOMEM, "locate: out of device memory"); }
+  locate_fill_kernel<<<gridFor(items, sm), 256, 0, st>>>(v, items, first, steps, val_off, raw);
+  locate_segments_kernel<<<gridFor(n + 1, sm), 256, 0, st>>>(node_off, val_off, n, seg);
+  {
+    size_t bytes = 0;
+    LOC_TRY(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, raw, sorted, (long long)total, (long long)n, seg, seg + 1, st));
+    void* t = alloc(bytes);
+    if(!t) { cleanup(); return fail(GCSA_B200_ERR_NOMEM, "locate: out of device memory"); }
+    LOC_TRY(cub::DeviceSegmentedSort::SortKeys(t, bytes, raw, sorted, (long long)total, (long long)n, seg, seg + 1, st));
+  }
+  LOC_TRY(cudaMemsetAsync(flag + total, 0, sizeof(u64), st));
+  locate_flag_kernel<<<gridFor(total, sm), 256, 0, st>>>(sorted, seg, n, total, flag);
+  LOC_RC(scanExclusive(flag, flag_scan, total + 1, st));
+  u64 distinct = 0;
+  LOC_TRY(cudaMemcpyAsync(&distinct, flag_scan + total, sizeof(u64), cudaMemcpyDeviceToHost, st));
+  LOC_TRY(cudaStreamSynchronize(st));
+  if(needed) { *needed = distinct; }
+  locate_offsets_kernel<<<gridFor(n + 1, sm), 256, 0, st>>>(seg, flag_scan, n, total, distinct, d_out_offsets);
+  int rc = 0;
+  if(d_values_alloc != nullptr)
+  {
+    void* p = nullptr;
+    LOC_TRY(cudaMallocAsync(&p, std::max<u64>(distinct, 1) * sizeof(u64), st));
+    *d_values_alloc = (u64*)p; d_values = (u64*)p; capacity = distinct;
+  }
+  if(d_values == nullptr || capacity < distinct) { rc = GCSA_B200_ERR_CAPACITY; g_last_error = "locate: output capacity too small"; }
+  else { locate_compact_kernel<<<gridFor(total, sm), 256, 0, st>>>(sorted, flag, flag_scan, total, d_values, capacity); }
+  LOC_TRY(cudaGetLastError());
+  cleanup();
+  #undef LOC_TRY
+  #undef LOC_RC
+  return rc;
+}
+
+} // namespace
+
+int gcsa_b200_locate_batch(const gcsa_b200_index* index, const uint64_t* d_sp, const uint64_t* d_ep, uint64_t n,
+                           uint64_t* d_out_offsets, uint64_t* d_values, uint64_t capacity, uint64_t* needed, void* stream)
+{
+  if(index == nullptr || d_out_offsets == nullptr) { return fail(GCSA_B200_ERR_INVALID, "locate_batch: null argument"); }
+  DeviceGuard guard(index->device);
+  if(n == 0)
+  {
+    CUDA_TRY(cudaMemsetAsync(d_out_offsets, 0, sizeof(u64), (cudaStream_t)stream));
+    if(needed) { *needed = 0; }
+    return 0;
+  }
+  return locateDevice(index, (const u64*)d_sp, (const u64*)d_ep, n, (u64*)d_out_offsets, (u64*)d_values, capacity, (u64*)needed, (cudaStream_t)stream);
+}
+
+int gcsa_b200_locate_host(const gcsa_b200_index* index, const uint64_t* sp, const uint64_t* ep, uint64_t n,
+                          uint64_t* out_offsets, uint64_t** values)
+{
+  if(out_offsets == nullptr || values == nullptr) { return fail(GCSA_B200_ERR_INVALID, "locate_host: null argument"); }
+  *values = nullptr;
+  HOST_PROLOGUE("locate_host", index);
+  u64* a = sc.in((const u64*)sp, n); u64* b = sc.in((const u64*)ep, n);
+  u64* offs = sc.alloc<u64>(n + 1);
+  u64 needed = 0;
+  u64* d_vals = nullptr;
+  int rc = 0;
+  if(n == 0) { out_offsets[0] = 0; }
+  else
+  {
+    rc = locateDevice(index, a, b, n, offs, nullptr, 0, &needed, sc.stream, &d_vals);
+    if(rc == 0)
+    {
+      u64* vals = (u64*)std::malloc(std::max<u64>(needed, 1) * sizeof(u64));
+      if(d_vals != nullptr) { sc.out(vals, d_vals, needed); sc.ptrs.push_back(d_vals); }
+      sc.out((u64*)out_offsets, offs, n + 1);
+      *values = (uint64_t*)vals;
+    }
+  }
+  HOST_EPILOGUE("locate_host", rc);
+}
+
+/*
+  GCSA::locate(range, max_positions, results), src/gcsa.cpp:844-878, batched.  count() runs on the
+  device; ranges with max >= total/2 are located in full on the device; the others draw positions
+  with std::mt19937_64(sp ^ ep) exactly like the reference, one draw per unfinished range per
+  round, and each round's nodes are located as one device batch.
+*/
+int gcsa_b200_locate_max_host(const gcsa_b200_index* index, const uint64_t* sp, const uint64_t* ep, uint64_t n,
+                              uint64_t max_positions, uint64_t* out_offsets, uint64_t** values)
+{
+  if(index == nullptr || out_offsets == nullptr || values == nullptr) { return fail(GCSA_B200_ERR_INVALID, "locate_max_host: null argument"); }
+  *values = nullptr;
+  std::vector<u64> totals(n);
+  int rc = gcsa_b200_count_host(index, sp, ep, n, (uint64_t*)totals.data());
+  if(rc) { return rc; }
+
+  std::vector<std::vector<u64>> results(n);
+  std::vector<std::mt19937_64> rngs; rngs.reserve(n);
+  std::vector<u64> maxes(n);
+  std::vector<u64> full_sp, full_ep, full_id;
+  std::vector<u64> rnd_id;
+  std::vector<std::unordered_set<u64>> found(n);
+  for(u64 i = 0; i < n; i++)
+  {
+    rngs.emplace_back(sp[i] ^ ep[i]);
+    maxes[i] = std::min<u64>(max_positions, totals[i]);
+    if(totals[i] == 0) { continue; }
+    if(maxes[i] >= totals[i] / 2) { full_sp.push_back(sp[i]); full_ep.push_back(ep[i]); full_id.push_back(i); }
+    else { rnd_id.push_back(i); }
+  }
+  if(!full_id.empty())
+  {
+    std::vector<u64> offs(full_id.size() + 1); uint64_t* vals = nullptr;
+    rc = gcsa_b200_locate_host(index, (const uint64_t*)full_sp.data(), (const uint64_t*)full_ep.data(), full_id.size(), (uint64_t*)offs.data(), &vals);
+    if(rc) { return rc; }
+    for(u64 t = 0; t < full_id.size(); t++) { results[full_id[t]].assign(vals + offs[t], vals + offs[t + 1]); }
+    std::free(vals);
+  }
+  while(!rnd_id.empty())
+  {
+    std::vector<u64> nodes(rnd_id.size());
+    for(u64 t = 0; t < rnd_id.size(); t++)
+    {
+      u64 i = rnd_id[t];
+      nodes[t] = sp[i] + rngs[i]() % (ep[i] + 1 - sp[i]);
+    }
+    std::vector<u64> offs(rnd_id.size() + 1); uint64_t* vals = nullptr;
+    rc = gcsa_b200_locate_host(index, (const uint64_t*)nodes.data(), (const uint64_t*)nodes.data(), rnd_id.size(), (uint64_t*)offs.data(), &vals);
+    if(rc) { return rc; }
+    std::vector<u64> still;
+    for(u64 t = 0; t < rnd_id.size(); t++)
+    {
+      u64 i = rnd_id[t];
+      for(u64 j = offs[t]; j < offs[t + 1]; j++) { found[i].insert(vals[j]); }
+      if(found[i].size() < maxes[i]) { still.push_back(i); }
+      else { results[i].assign(found[i].begin(), found[i].end()); }
+    }
+    std::free(vals);
+    rnd_id.swap(still);
+  }
+  out_offsets[0] = 0;
+  for(u64 i = 0; i < n; i++)
+  {
+    std::vector<u64>& r = results[i];
+    if(r.size() > maxes[i])
+    {
+      std::sort(r.begin(), r.end());                        // deterministicShuffle, utils.h:359-370
+      for(u64 j = r.size(); j > 0; j--) { std::swap(r[j - 1], r[rngs[i]() % j]); }
+      r.resize(maxes[i]);
+    }
+    std::sort(r.begin(), r.end());
+    out_offsets[i + 1] = out_offsets[i] + r.size();
+  }
+  u64* vals = (u64*)std::malloc(std::max<u64>(out_offsets[n], 1) * sizeof(u64));
+  for(u64 i = 0; i < n; i++) { std::copy(results[i].begin(), results[i].end(), vals + out_offsets[i]); }
+  *values = (uint64_t*)vals;
+  return 0;
+}
+
+//------------------------------------------------------------------------------
+// LCP
+//------------------------------------------------------------------------------
+
+int gcsa_b200_lcp_create(const gcsa_flat_lcp* host, int device, gcsa_b200_lcp** out)
+{
+  if(host == nullptr || out == nullptr) { return fail(GCSA_B200_ERR_INVALID, "lcp_create: null argument"); }
+  *out = nullptr;
+  if(host->levels + 1 > 16 || host->levels == 0 || host->branching < 2) { return fail(GCSA_B200_ERR_INVALID, "lcp_create: bad tree shape"); }
+  int n_dev = gcsa_b200_device_count();
+  if(n_dev <= 0) { return fail(GCSA_B200_ERR_CUDA, "lcp_create: no CUDA device available (this engine has no CPU fallback)"); }
+  if(device < 0 || device >= n_dev) { return fail(GCSA_B200_ERR_INVALID, "lcp_create: bad device ordinal"); }
+  DeviceGuard guard(device);
+  gcsa_b200_lcp* l = new gcsa_b200_lcp();
+  l->device = device;
+  cudaDeviceGetAttribute(&l->sm_count, cudaDevAttrMultiProcessorCount, device);
+  LcpView& v = l->view;
+  std::memset(&v, 0, sizeof(v));
+  v.size = host->size; v.branching = host->branching; v.levels = host->levels;
+  for(u64 i = 0; i <= host->levels; i++) { v.offsets[i] = host->offsets[i]; }
+  for(u64 i = host->levels + 1; i < 16; i++) { v.offsets[i] = ~0ull; }
+  v.values = host->offsets[host->levels];
+  cudaError_t e = cudaMalloc(&l->data, std::max<u64>(v.values, 16));
+  if(e == cudaSuccess && v.values) { e = cudaMemcpy(l->data, host->data, v.values, cudaMemcpyHostToDevice); }
+  if(e != cudaSuccess) { if(l->data) { cudaFree(l->data); } delete l; return fail(GCSA_B200_ERR_CUDA, std::string("lcp_create: ") + cudaGetErrorString(e)); }
+  v.data = (const u8*)l->data;
+  *out = l;
+  return 0;
+}
+
+void gcsa_b200_lcp_destroy(gcsa_b200_lcp* lcp)
+{
+  if(lcp == nullptr) { return; }
+  DeviceGuard guard(lcp->device);
+  cudaFree(lcp->data);
+  delete lcp;
+}
+
+int gcsa_b200_parent_batch(const gcsa_b200_lcp* lcp, const uint64_t* d_sp, const uint64_t* d_ep, uint64_t n,
+                           gcsa_b200_stnode* d_out, void* stream)
+{
+  if(lcp == nullptr) { return fail(GCSA_B200_ERR_INVALID, "parent_batch: null handle"); }
+  if(n == 0) { return 0; }
+  DeviceGuard guard(lcp->device);
+  parent_kernel<<<gridFor(n, lcp->sm_count), 256, 0, (cudaStream_t)stream>>>(lcp->view, (const u64*)d_sp, (const u64*)d_ep, n, d_out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int gcsa_b200_parent_host(const gcsa_b200_lcp* lcp, const uint64_t* sp, const uint64_t* ep, uint64_t n, gcsa_b200_stnode* out)
+{
+  HOST_PROLOGUE("parent_host", lcp);
+  u64* a = sc.in((const u64*)sp, n); u64* b = sc.in((const u64*)ep, n);
+  gcsa_b200_stnode* o = sc.alloc<gcsa_b200_stnode>(n);
+  int rc = gcsa_b200_parent_batch(lcp, a, b, n, o, sc.stream);
+  sc.out(out, o, n);
+  HOST_EPILOGUE("parent_host", rc);
+}
+
+int gcsa_b200_depth_batch(const gcsa_b200_lcp* lcp, const uint64_t* d_sp, const uint64_t* d_ep, uint64_t n,
+                          uint64_t* d_out, void* stream)
+{
+  if(lcp == nullptr) { return fail(GCSA_B200_ERR_INVALID, "depth_batch: null handle"); }
+  if(n == 0) { return 0; }
+  DeviceGuard guard(lcp->device);
+  depth_kernel<<<gridFor(n, lcp->sm_count), 256, 0, (cudaStream_t)stream>>>(lcp->view, (const u64*)d_sp, (const u64*)d_ep, n, (u64*)d_out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int gcsa_b200_depth_host(const gcsa_b200_lcp* lcp, const uint64_t* sp, const uint64_t* ep, uint64_t n, uint64_t* out)
+{
+  HOST_PROLOGUE("depth_host", lcp);
+  u64* a = sc.in((const u64*)sp, n); u64* b = sc.in((const u64*)ep, n); u64* o = sc.alloc<u64>(n);
+  int rc = gcsa_b200_depth_batch(lcp, a, b, n, o, sc.stream);
+  sc.out((u64*)out, o, n);
+  HOST_EPILOGUE("depth_host", rc);
+}
+
+int gcsa_b200_lcp_sv_host(const gcsa_b200_lcp* lcp, int which, const uint64_t* pos, uint64_t n,
+                          uint64_t* out_pos, uint64_t* out_val)
+{
+  if(which < 0 || which > 3) { return fail(GCSA_B200_ERR_INVALID, "lcp_sv_host: which must be 0..3"); }
+  HOST_PROLOGUE("lcp_sv_host", lcp);
+  u64* a = sc.in((const u64*)pos, n); u64* op = sc.alloc<u64>(n); u64* ov = sc.alloc<u64>(n);
+  int rc = 0;
+  if(n) { lcp_sv_kernel<<<gridFor(n, lcp->sm_count), 256, 0, sc.stream>>>(lcp->view, which, a, n, op, ov); }
+  sc.out((u64*)out_pos, op, n); sc.out((u64*)out_val, ov, n);
+  HOST_EPILOGUE("lcp_sv_host", rc);
+}
+
+int gcsa_b200_lcp_rmq_host(const gcsa_b200_lcp* lcp, const uint64_t* sp, const uint64_t* ep, uint64_t n,
+                           uint64_t* out_pos, uint64_t* out_val)
+{
+  HOST_PROLOGUE("lcp_rmq_host", lcp);
+  u64* a = sc.in((const u64*)sp, n); u64* b = sc.in((const u64*)ep, n);
+  u64* op = sc.alloc<u64>(n); u64* ov = sc.alloc<u64>(n);
+  int rc = 0;
+  if(n) { lcp_rmq_kernel<<<gridFor(n, lcp->sm_count), 256, 0, sc.stream>>>(lcp->view, a, b, n, op, ov); }
+  sc.out((u64*)out_pos, op, n); sc.out((u64*)out_val, ov, n);
+  HOST_EPILOGUE("lcp_rmq_host", rc);
+}
+
+

@@ -1,0 +1,278 @@
+"""Host-side mirror of the reference's query interface over the C ABI.
+
+GCSA     <-> gcsa::GCSA      (reference include/gcsa/gcsa.h:40-275): find, charRange, LF,
+                              LF_fast, LF_all, count, locate and the size accessors, with the
+                              reference's names, argument meaning and error behaviour (queries
+                              never raise for odd ranges; count/locate treat ranges past the
+                              index as empty, src/gcsa.cpp:805, 817, 831), plus *_batch forms.
+LCPArray <-> gcsa::LCPArray  (include/gcsa/lcp.h:90-194): parent, depth, psv/psev/nsv/nsev, rmq.
+
+Everything here is plumbing: the work happens in libgcsa2_b200.so (CUDA, sm_100a).  There is no
+CPU implementation behind these classes; constructing one without a CUDA device raises.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .flat import FlatGCSA, FlatLCP, SIGMA
+
+UNKNOWN = (1 << 64) - 1
+
+
+def pack_patterns(patterns):
+    """list of str/bytes -> (chars uint8[], offsets uint64[n + 1])"""
+    bs = [p.encode() if isinstance(p, str) else bytes(p) for p in patterns]
+    offsets = np.zeros(len(bs) + 1, dtype=np.uint64)
+    if bs:
+        offsets[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
+    chars = np.frombuffer(b"".join(bs), dtype=np.uint8).copy()
+    if chars.size == 0:
+        chars = np.zeros(1, dtype=np.uint8)
+    return chars, offsets
+
+
+def range_empty(rng):
+    """Range::empty, include/gcsa/utils.h:93-101."""
+    return ((int(rng[0]) + 1) & UNKNOWN) > ((int(rng[1]) + 1) & UNKNOWN)
+
+
+def range_length(rng):
+    return (int(rng[1]) + 1 - int(rng[0])) & UNKNOWN
+
+
+class GCSA:
+    def __init__(self, flat, device=0, kmer_table_k=0):
+        self._h = None
+        L = capi.lib()
+        keep = []
+        f = capi.flat_struct(flat, keep)
+        opt = capi.Options(); opt.kmer_table_k = int(kmer_table_k)
+        h = C.c_void_p()
+        capi.check(L.gcsa_b200_index_create(C.byref(f), int(device), C.byref(opt), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self.char2comp = np.array(flat.char2comp, dtype=np.uint8)
+        self.C = np.array(flat.C, dtype=np.uint64)
+        info = capi.Info()
+        capi.check(L.gcsa_b200_index_info(self._h, C.byref(info)))
+        self._info = info
+
+    def close(self):
+        if self._h is not None:
+            capi.lib().gcsa_b200_index_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- accessors (gcsa.h:137-148) ----
+    def size(self): return int(self._info.path_nodes)
+    def empty(self): return self.size() == 0
+    def edgeCount(self): return int(self._info.edge_count)
+    def order(self): return int(self._info.order)
+    def sampleCount(self): return int(self._info.sample_count)
+    def deviceBytes(self): return int(self._info.device_bytes)
+    def kmerTableK(self): return int(self._info.kmer_table_k)
+    def smCount(self): return int(self._info.sm_count)
+    @property
+    def handle(self): return self._h
+
+    # ---- find (gcsa.h:96-122) ----
+    def find(self, pattern):
+        sp, ep = self.find_batch([pattern])
+        return (int(sp[0]), int(ep[0]))
+
+    def find_batch(self, patterns, offsets=None, stats=False):
+        """patterns: list of str/bytes, or a uint8 array together with `offsets` (n + 1)."""
+        if offsets is None:
+            chars, offsets = pack_patterns(patterns)
+        else:
+            chars = np.ascontiguousarray(patterns, dtype=np.uint8)
+            offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        sp = np.zeros(max(n, 1), dtype=np.uint64); ep = np.zeros(max(n, 1), dtype=np.uint64)
+        if stats:
+            st = capi.FindStats()
+            capi.check(capi.lib().gcsa_b200_find_stats_host(self._h, chars.ctypes.data, offsets.ctypes.data, n,
+                                                            sp.ctypes.data, ep.ctypes.data, C.byref(st)))
+            return sp[:n], ep[:n], {k: int(getattr(st, k)) for k, _ in capi.FindStats._fields_}
+        capi.check(capi.lib().gcsa_b200_find_host(self._h, chars.ctypes.data, offsets.ctypes.data, n,
+                                                  sp.ctypes.data, ep.ctypes.data))
+        return sp[:n], ep[:n]
+
+    def find_host_raw(self, chars_ptr, offsets_ptr, n, sp_ptr, ep_ptr):
+        """Host pointers (e.g. pinned torch tensors' data_ptr()); the C ABI call a user makes."""
+        capi.check(capi.lib().gcsa_b200_find_host(self._h, chars_ptr, offsets_ptr, int(n), sp_ptr, ep_ptr))
+
+    def find_device(self, d_chars, d_offsets, n, d_sp, d_ep, stream=0):
+        """Device pointers / tensors, stream-ordered, no synchronisation."""
+        capi.check(capi.lib().gcsa_b200_find_batch(self._h, capi.ptr(d_chars), capi.ptr(d_offsets), int(n),
+                                                   capi.ptr(d_sp), capi.ptr(d_ep), stream or None))
+
+    # ---- low-level interface (gcsa.h:150-183, gcsa.cpp:742-798) ----
+    def charRange(self, comp):
+        sp, ep = C.c_uint64(), C.c_uint64()
+        capi.check(capi.lib().gcsa_b200_char_range(self._h, int(comp), C.byref(sp), C.byref(ep)))
+        return (sp.value, ep.value)
+
+    def LF(self, range_or_node, comp=None):
+        if comp is None:
+            return int(self.lf_node_batch([range_or_node])[0])
+        sp, ep = self.lf_batch([range_or_node[0]], [range_or_node[1]], [comp])
+        return (int(sp[0]), int(ep[0]))
+
+    def lf_batch(self, sp, ep, comp):
+        sp, ep = capi.as_u64(sp), capi.as_u64(ep)
+        comp = np.ascontiguousarray(comp, dtype=np.uint8)
+        n = int(comp.size)
+        osp = np.zeros(max(n, 1), dtype=np.uint64); oep = np.zeros(max(n, 1), dtype=np.uint64)
+        capi.check(capi.lib().gcsa_b200_lf_host(self._h, sp.ctypes.data, ep.ctypes.data, comp.ctypes.data, n,
+                                                osp.ctypes.data, oep.ctypes.data))
+        return osp[:n], oep[:n]
+
+    def lf_node_batch(self, nodes):
+        n = len(nodes)
+        nodes = capi.as_u64(nodes)
+        out = np.zeros(max(n, 1), dtype=np.uint64)
+        capi.check(capi.lib().gcsa_b200_lf_node_host(self._h, nodes.ctypes.data, n, out.ctypes.data))
+        return out[:n]
+
+    def lf_multi_batch(self, sp, ep, all_chars):
+        n = len(sp)
+        sp, ep = capi.as_u64(sp), capi.as_u64(ep)
+        out = np.zeros((max(n, 1), SIGMA, 2), dtype=np.uint64)
+        capi.check(capi.lib().gcsa_b200_lf_multi_host(self._h, sp.ctypes.data, ep.ctypes.data, n, int(all_chars), out.ctypes.data))
+        return out[:n]
+
+    def LF_fast(self, rng):
+        """results[comp] for 1 <= comp <= fast_chars (gcsa.cpp:742-767); other slots are (1, 0)."""
+        out = self.lf_multi_batch([rng[0]], [rng[1]], 0)[0]
+        return [(int(a), int(b)) for a, b in out]
+
+    def LF_all(self, rng):
+        out = self.lf_multi_batch([rng[0]], [rng[1]], 1)[0]
+        return [(int(a), int(b)) for a, b in out]
+
+    # ---- count / locate (gcsa.cpp:802-878) ----
+    def count(self, rng):
+        return int(self.count_batch([rng[0]], [rng[1]])[0])
+
+    def count_batch(self, sp, ep):
+        n = len(sp)
+        sp, ep = capi.as_u64(sp), capi.as_u64(ep)
+        out = np.zeros(max(n, 1), dtype=np.uint64)
+        capi.check(capi.lib().gcsa_b200_count_host(self._h, sp.ctypes.data, ep.ctypes.data, n, out.ctypes.data))
+        return out[:n]
+
+    def locate(self, range_or_node, max_positions=None):
+        """locate(path_node) / locate(range) / locate(range, max_positions): sorted distinct values."""
+        if isinstance(range_or_node, tuple):
+            sp, ep = [range_or_node[0]], [range_or_node[1]]
+        else:
+            node = int(range_or_node)
+            if node >= self.size():                       # gcsa.cpp:817
+                return []
+            sp, ep = [node], [node]
+        offs, vals = self.locate_batch(sp, ep, max_positions=max_positions)
+        return [int(x) for x in vals[int(offs[0]):int(offs[1])]]
+
+    def locate_batch(self, sp, ep, max_positions=None):
+        """CSR result: values[offsets[i]:offsets[i+1]] are the sorted distinct positions of range i."""
+        n = len(sp)
+        sp, ep = capi.as_u64(sp), capi.as_u64(ep)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        p = C.c_void_p()
+        if max_positions is None:
+            capi.check(capi.lib().gcsa_b200_locate_host(self._h, sp.ctypes.data, ep.ctypes.data, n, offs.ctypes.data, C.byref(p)))
+        else:
+            capi.check(capi.lib().gcsa_b200_locate_max_host(self._h, sp.ctypes.data, ep.ctypes.data, n, int(max_positions),
+                                                            offs.ctypes.data, C.byref(p)))
+        total = int(offs[n])
+        vals = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(max(total, 1),))[:total].copy()
+        capi.lib().gcsa_b200_free(p)
+        return offs, vals
+
+
+class LCPArray:
+    def __init__(self, flat_lcp, device=0):
+        self._h = None
+        self._offsets = capi.as_u64(flat_lcp.offsets)
+        data = np.ascontiguousarray(flat_lcp.data, dtype=np.uint8)
+        if data.size == 0:
+            data = np.zeros(1, dtype=np.uint8)
+        f = capi.FlatLcp()
+        f.size, f.branching, f.levels = int(flat_lcp.size), int(flat_lcp.branching), int(flat_lcp.levels)
+        f.offsets, f.data = self._offsets.ctypes.data, data.ctypes.data
+        h = C.c_void_p()
+        capi.check(capi.lib().gcsa_b200_lcp_create(C.byref(f), int(device), C.byref(h)))
+        self._h = h
+        self._size, self._values = int(flat_lcp.size), int(self._offsets[int(flat_lcp.levels)])
+        self._branching, self._levels = int(flat_lcp.branching), int(flat_lcp.levels)
+
+    def close(self):
+        if self._h is not None:
+            capi.lib().gcsa_b200_lcp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self): return self._size
+    def values(self): return self._values
+    def levels(self): return self._levels
+    def branching(self): return self._branching
+    def root(self): return (0, self._size - 1, 0, 0, 0)            # lcp.h:137
+    def notFound(self): return (self._values, self._values)        # lcp.h:178
+    @property
+    def handle(self): return self._h
+
+    def parent(self, rng):
+        return tuple(int(x) for x in self.parent_batch([rng[0]], [rng[1]])[0])
+
+    def parent_batch(self, sp, ep):
+        n = len(sp)
+        sp, ep = capi.as_u64(sp), capi.as_u64(ep)
+        out = np.zeros((max(n, 1), 5), dtype=np.uint64)
+        capi.check(capi.lib().gcsa_b200_parent_host(self._h, sp.ctypes.data, ep.ctypes.data, n, out.ctypes.data))
+        return out[:n]
+
+    def depth(self, rng):
+        return int(self.depth_batch([rng[0]], [rng[1]])[0])
+
+    def depth_batch(self, sp, ep):
+        n = len(sp)
+        sp, ep = capi.as_u64(sp), capi.as_u64(ep)
+        out = np.zeros(max(n, 1), dtype=np.uint64)
+        capi.check(capi.lib().gcsa_b200_depth_host(self._h, sp.ctypes.data, ep.ctypes.data, n, out.ctypes.data))
+        return out[:n]
+
+    def _sv(self, which, pos):
+        n = len(pos)
+        pos = capi.as_u64(pos)
+        a = np.zeros(max(n, 1), dtype=np.uint64); b = np.zeros(max(n, 1), dtype=np.uint64)
+        capi.check(capi.lib().gcsa_b200_lcp_sv_host(self._h, which, pos.ctypes.data, n, a.ctypes.data, b.ctypes.data))
+        return a[:n], b[:n]
+
+    def psv(self, pos): a, b = self._sv(0, [pos]); return (int(a[0]), int(b[0]))
+    def psev(self, pos): a, b = self._sv(1, [pos]); return (int(a[0]), int(b[0]))
+    def nsv(self, pos): a, b = self._sv(2, [pos]); return (int(a[0]), int(b[0]))
+    def nsev(self, pos): a, b = self._sv(3, [pos]); return (int(a[0]), int(b[0]))
+    def sv_batch(self, which, pos): return self._sv({"psv": 0, "psev": 1, "nsv": 2, "nsev": 3}[which], pos)
+
+    def rmq(self, sp, ep):
+        a, b = self.rmq_batch([sp], [ep])
+        return (int(a[0]), int(b[0]))
+
+    def rmq_batch(self, sp, ep):
+        n = len(sp)
+        sp, ep = capi.as_u64(sp), capi.as_u64(ep)
+        a = np.zeros(max(n, 1), dtype=np.uint64); b = np.zeros(max(n, 1), dtype=np.uint64)
+        capi.check(capi.lib().gcsa_b200_lcp_rmq_host(self._h, sp.ctypes.data, ep.ctypes.data, n, a.ctypes.data, b.ctypes.data))
+        return a[:n], b[:n]

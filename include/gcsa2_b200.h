@@ -1,0 +1,233 @@
+/*
+  gcsa2_b200.h -- C ABI of the B200 batched backward-search engine for GCSA2 indexes.
+
+  This is the drop-in boundary.  The reference (jltsiren/gcsa2) exposes the query path as the
+  C++ class gcsa::GCSA / gcsa::LCPArray with header-inline methods; a foreign-function binding
+  of that path would bind exactly the operations below, one batch entry point per method.  Each
+  entry point cites the reference interface it replaces (file:line in the reference tree).
+
+  Conventions
+    * plain pointers and sizes, no C++ or torch types; status return: 0 = ok, < 0 = GCSA_B200_ERR_*;
+      no exceptions cross the boundary; gcsa_b200_last_error() gives the message of the calling
+      thread's last failure.
+    * "*_batch" entry points take DEVICE pointers and are stream-ordered on `stream`
+      (a cudaStream_t passed as void*; NULL = the legacy default stream).  They never synchronise.
+    * "*_host" entry points take HOST pointers; they copy in, run the same kernels, copy out and
+      return when the results are in the caller's buffers.
+    * ranges are closed [sp, ep] pairs of path-node ranks, empty iff sp + 1 > ep + 1
+      (include/gcsa/utils.h:84-117); empty results of find()/LF() are returned uncanonicalised
+      exactly as the reference returns them (include/gcsa/gcsa.h:160).
+    * handles are immutable after creation; any number of host threads may issue queries on one
+      handle concurrently (the reference's query methods are const, src/algorithms.cpp:113).
+    * the library fails loudly (GCSA_B200_ERR_CUDA) when there is no usable CUDA device; there is
+      no CPU fallback.
+*/
+#ifndef GCSA2_B200_H
+#define GCSA2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCSA_B200_SIGMA 7              /* $ A C G T N #  (src/support.cpp:92) */
+#define GCSA_B200_FAST_CHARS 4         /* comps 1..4 (include/gcsa/support.h:108) */
+#define GCSA_B200_UNKNOWN (~(uint64_t)0)   /* STNode::UNKNOWN, include/gcsa/lcp.h:46 */
+
+#define GCSA_B200_OK 0
+#define GCSA_B200_ERR_INVALID      (-1)   /* bad argument */
+#define GCSA_B200_ERR_CUDA         (-2)   /* CUDA runtime failure / no device */
+#define GCSA_B200_ERR_NOMEM        (-3)
+#define GCSA_B200_ERR_CAPACITY     (-4)   /* output buffer too small (locate) */
+#define GCSA_B200_ERR_INCONSISTENT (-5)   /* builder: input violates the GCSA invariants */
+
+/* ---------------------------------------------------------------------------------------------
+   The index as plain host arrays (members of gcsa::GCSA, include/gcsa/gcsa.h:214-240).
+   Every bit vector is little-endian 64-bit words: bit i = (words[i >> 6] >> (i & 63)) & 1.
+   --------------------------------------------------------------------------------------------- */
+typedef struct gcsa_flat_index {
+  uint64_t path_nodes;                 /* GCSAHeader::path_nodes, include/gcsa/files.h:135-156 */
+  uint64_t edge_count;                 /* GCSAHeader::edges */
+  uint64_t order;                      /* GCSAHeader::order */
+  uint64_t sigma, fast_chars;          /* Alphabet::sigma, fast_chars (support.h:149-151) */
+  uint64_t C[GCSA_B200_SIGMA + 1];     /* Alphabet::C */
+  uint8_t  char2comp[256];             /* Alphabet::char2comp */
+  const uint64_t* bwt[GCSA_B200_SIGMA];/* fast_bwt[1..4], sparse_bwt[0,5,6]: path_nodes bits each */
+  const uint64_t* edges;               /* edge_count bits, 1 = last outgoing edge of a node */
+  const uint64_t* sampled_paths;       /* path_nodes bits */
+  uint64_t sample_count;
+  const uint64_t* stored_samples;      /* sample_count values (int_vector<0> unpacked) */
+  const uint64_t* samples;             /* sample_count bits, 1 = last sample of a node */
+  const uint64_t* extra_filter;        /* SadaSparse::filter, path_nodes bits (support.h:319) */
+  uint64_t extra_values_len;
+  const uint64_t* extra_values;        /* SadaSparse::values (support.h:323) */
+  uint64_t redundant_len;
+  const uint64_t* redundant;           /* SadaCount::data (support.h:252) */
+} gcsa_flat_index;
+
+/* gcsa::LCPArray members (include/gcsa/lcp.h:182-190): levels of a k-ary range-minimum tree,
+   level 0 = the LCP array, concatenated; one byte per value (values are <= 255). */
+typedef struct gcsa_flat_lcp {
+  uint64_t size, branching, levels;
+  const uint64_t* offsets;             /* levels + 1 */
+  const uint8_t*  data;                /* offsets[levels] */
+} gcsa_flat_lcp;
+
+/* STNode, include/gcsa/lcp.h:40-79 */
+typedef struct gcsa_b200_stnode { uint64_t sp, ep, left_lcp, right_lcp, node_lcp; } gcsa_b200_stnode;
+
+typedef struct gcsa_b200_options {
+  int      kmer_table_k;   /* 0 = none; else a lookup table of find() results for all ACGT strings of
+                              this length is built at creation (4^k * 16 bytes) and used to skip the
+                              first k backward steps.  -1 = engine default. */
+  int      reserved[7];
+} gcsa_b200_options;
+
+typedef struct gcsa_b200_info {
+  uint64_t path_nodes, edge_count, order, sample_count;
+  uint64_t device_bytes;               /* HBM used by the index */
+  int      kmer_table_k;
+  int      device;
+  int      sm_count;
+  int      reserved;
+} gcsa_b200_info;
+
+/* Per-batch statistics of find(): filled by gcsa_b200_find_stats_host (measurement only). */
+typedef struct gcsa_b200_find_stats {
+  uint64_t queries, found, total_length, lf_steps, sector_probes, table_hits;
+} gcsa_b200_find_stats;
+
+typedef struct gcsa_b200_index gcsa_b200_index;
+typedef struct gcsa_b200_lcp   gcsa_b200_lcp;
+
+const char* gcsa_b200_last_error(void);
+const char* gcsa_b200_version(void);
+int gcsa_b200_device_count(void);
+
+/* Replaces GCSA::load() + the SDSL rank/select supports (src/gcsa.cpp:140-216, 726-738):
+   uploads the arrays and builds the device rank dictionary.  options may be NULL. */
+int  gcsa_b200_index_create(const gcsa_flat_index* host, int device, const gcsa_b200_options* options,
+                            gcsa_b200_index** out);
+void gcsa_b200_index_destroy(gcsa_b200_index* index);
+int  gcsa_b200_index_info(const gcsa_b200_index* index, gcsa_b200_info* info);
+
+/* GCSA::find(begin, end) / find(Container) / find(Element*, length), include/gcsa/gcsa.h:96-122.
+   Pattern i is chars[offsets[i] .. offsets[i+1]); characters are raw bytes mapped through
+   char2comp like the reference does (gcsa.h:102,106). */
+int gcsa_b200_find_batch(const gcsa_b200_index* index, const uint8_t* d_chars, const uint64_t* d_offsets,
+                         uint64_t n, uint64_t* d_sp, uint64_t* d_ep, void* stream);
+int gcsa_b200_find_host(const gcsa_b200_index* index, const uint8_t* chars, const uint64_t* offsets,
+                        uint64_t n, uint64_t* sp, uint64_t* ep);
+/* Same answers plus executed-work counters (slower; for the roofline accounting only). */
+int gcsa_b200_find_stats_host(const gcsa_b200_index* index, const uint8_t* chars, const uint64_t* offsets,
+                              uint64_t n, uint64_t* sp, uint64_t* ep, gcsa_b200_find_stats* stats);
+
+/* GCSA::charRange(comp), include/gcsa/gcsa.h:150-153 (host-side, O(1), no device work). */
+int gcsa_b200_char_range(const gcsa_b200_index* index, uint64_t comp, uint64_t* sp, uint64_t* ep);
+
+/* GCSA::LF(range_type, comp_type), include/gcsa/gcsa.h:155-162. */
+int gcsa_b200_lf_batch(const gcsa_b200_index* index, const uint64_t* d_sp, const uint64_t* d_ep,
+                       const uint8_t* d_comp, uint64_t n, uint64_t* d_sp_out, uint64_t* d_ep_out, void* stream);
+int gcsa_b200_lf_host(const gcsa_b200_index* index, const uint64_t* sp, const uint64_t* ep,
+                      const uint8_t* comp, uint64_t n, uint64_t* sp_out, uint64_t* ep_out);
+
+/* GCSA::LF(size_type path_node), include/gcsa/gcsa.h:165-183. */
+int gcsa_b200_lf_node_batch(const gcsa_b200_index* index, const uint64_t* d_nodes, uint64_t n,
+                            uint64_t* d_out, void* stream);
+int gcsa_b200_lf_node_host(const gcsa_b200_index* index, const uint64_t* nodes, uint64_t n, uint64_t* out);
+
+/* GCSA::LF_fast / LF_all, src/gcsa.cpp:742-798.  out holds sigma (sp, ep) pairs per input range,
+   indexed by comp: out[(i * sigma + comp) * 2 + {0,1}]; slots the reference does not write are
+   (1, 0) = Range::empty_range().  all_chars = 0: LF_fast (comps 1..fast_chars);
+   all_chars = 1: LF_all (comps 1..sigma-2). */
+int gcsa_b200_lf_multi_batch(const gcsa_b200_index* index, const uint64_t* d_sp, const uint64_t* d_ep,
+                             uint64_t n, int all_chars, uint64_t* d_out, void* stream);
+int gcsa_b200_lf_multi_host(const gcsa_b200_index* index, const uint64_t* sp, const uint64_t* ep,
+                            uint64_t n, int all_chars, uint64_t* out);
+
+/* GCSA::count(range_type), src/gcsa.cpp:802-809. */
+int gcsa_b200_count_batch(const gcsa_b200_index* index, const uint64_t* d_sp, const uint64_t* d_ep,
+                          uint64_t n, uint64_t* d_out, void* stream);
+int gcsa_b200_count_host(const gcsa_b200_index* index, const uint64_t* sp, const uint64_t* ep,
+                         uint64_t n, uint64_t* out);
+
+/* GCSA::locate(range_type, results, append = false, sort = true), src/gcsa.cpp:827-842, as a CSR:
+   the sorted distinct node_type values of range i are values[out_offsets[i] .. out_offsets[i+1]).
+   *_host allocates *values with malloc (release with gcsa_b200_free).
+   *_batch writes into caller-owned device buffers; if capacity is too small it returns
+   GCSA_B200_ERR_CAPACITY after writing the needed size to *needed (a host pointer); the call
+   synchronises `stream` once to learn the sizes. */
+int gcsa_b200_locate_host(const gcsa_b200_index* index, const uint64_t* sp, const uint64_t* ep, uint64_t n,
+                          uint64_t* out_offsets, uint64_t** values);
+int gcsa_b200_locate_batch(const gcsa_b200_index* index, const uint64_t* d_sp, const uint64_t* d_ep, uint64_t n,
+                           uint64_t* d_out_offsets, uint64_t* d_values, uint64_t capacity, uint64_t* needed,
+                           void* stream);
+/* GCSA::locate(range_type, max_positions, results), src/gcsa.cpp:844-878 (host buffers). */
+int gcsa_b200_locate_max_host(const gcsa_b200_index* index, const uint64_t* sp, const uint64_t* ep, uint64_t n,
+                              uint64_t max_positions, uint64_t* out_offsets, uint64_t** values);
+void gcsa_b200_free(void* p);
+
+/* LCPArray, include/gcsa/lcp.h:90-194; load() at src/lcp.cpp:116-143. */
+int  gcsa_b200_lcp_create(const gcsa_flat_lcp* host, int device, gcsa_b200_lcp** out);
+void gcsa_b200_lcp_destroy(gcsa_b200_lcp* lcp);
+/* LCPArray::parent(range_type), src/lcp.cpp:276-301. */
+int gcsa_b200_parent_batch(const gcsa_b200_lcp* lcp, const uint64_t* d_sp, const uint64_t* d_ep, uint64_t n,
+                           gcsa_b200_stnode* d_out, void* stream);
+int gcsa_b200_parent_host(const gcsa_b200_lcp* lcp, const uint64_t* sp, const uint64_t* ep, uint64_t n,
+                          gcsa_b200_stnode* out);
+/* LCPArray::depth(range_type), src/lcp.cpp:319-325. */
+int gcsa_b200_depth_batch(const gcsa_b200_lcp* lcp, const uint64_t* d_sp, const uint64_t* d_ep, uint64_t n,
+                          uint64_t* d_out, void* stream);
+int gcsa_b200_depth_host(const gcsa_b200_lcp* lcp, const uint64_t* sp, const uint64_t* ep, uint64_t n,
+                         uint64_t* out);
+/* LCPArray::psv / psev / nsv / nsev, src/lcp.cpp:372-438: which = 0 psv, 1 psev, 2 nsv, 3 nsev.
+   out_pos / out_val = the (res, LCP[res]) pair, or notFound() = (values, values). */
+int gcsa_b200_lcp_sv_host(const gcsa_b200_lcp* lcp, int which, const uint64_t* pos, uint64_t n,
+                          uint64_t* out_pos, uint64_t* out_val);
+/* LCPArray::rmq(sp, ep), src/lcp.cpp:448-513. */
+int gcsa_b200_lcp_rmq_host(const gcsa_b200_lcp* lcp, const uint64_t* sp, const uint64_t* ep, uint64_t n,
+                           uint64_t* out_pos, uint64_t* out_val);
+
+/* ---------------------------------------------------------------------------------------------
+   Host-side construction (CPU; gcsa2_b200/csrc/builder.cpp).  Replaces, for in-memory inputs,
+   GCSA::GCSA(InputGraph&, ConstructionParameters) (src/gcsa.cpp:447-724) and
+   LCPArray::LCPArray(InputGraph&) level 0 (src/lcp.cpp:204-272).
+   --------------------------------------------------------------------------------------------- */
+typedef struct gcsa_b200_built {
+  gcsa_flat_index index;               /* arrays owned by the library: gcsa_b200_built_free */
+  uint64_t lcp_size;
+  uint8_t* lcp;                        /* LCP of adjacent path-node labels, in characters */
+} gcsa_b200_built;
+
+/* keys / from / to: the KMer records of the reference (include/gcsa/support.h:475-497):
+   key = label (3 bits per character, first character most significant) << 16 | predecessor
+   comp mask << 8 | successor comp mask; from / to = node_type; to = ~0 for kmers that are not
+   extended.  Returns 0, or GCSA_B200_ERR_INCONSISTENT (arrays still returned) / other error. */
+int  gcsa_b200_build_from_kmers(const uint64_t* keys, const uint64_t* from, const uint64_t* to, uint64_t n,
+                                int kmer_length, int doubling_steps, uint64_t sample_period,
+                                gcsa_b200_built* result);
+void gcsa_b200_built_free(gcsa_b200_built* result);
+
+/* A graph of single-character nodes in CSR form, for the synthetic inputs of the benchmarks. */
+typedef struct gcsa_b200_graph {
+  uint64_t nodes;
+  const uint8_t*  comp;                /* comp value of each node's character */
+  const uint64_t* value;               /* node_type of each node (include/gcsa/support.h:443-471) */
+  const uint64_t* succ_offsets;        /* nodes + 1 */
+  const uint64_t* succ;                /* successor node indexes */
+  uint64_t sink;                       /* index of the '$' node */
+  uint64_t n_sources;
+  const uint64_t* sources;             /* nodes that follow the sink through the technical edge */
+} gcsa_b200_graph;
+
+typedef struct gcsa_b200_kmers { uint64_t n; uint64_t* key; uint64_t* from; uint64_t* to; } gcsa_b200_kmers;
+
+int  gcsa_b200_enumerate_kmers(const gcsa_b200_graph* graph, int kmer_length, gcsa_b200_kmers* result);
+void gcsa_b200_kmers_free(gcsa_b200_kmers* result);
+void gcsa_b200_default_char2comp(uint8_t* table256);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCSA2_B200_H */
