@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- k-mer find() throughput of the B200 engine on BASELINE.json configs[1]:
+10 M 32-mers sampled from a 100 Mbp synthetic linear reference, order-128 index, per GPU.
+
+  python bench.py --gpus N --steps K --warmup W            (torchrun launches N ranks for N > 1)
+  python bench.py --impl reference ...                     (the CPU path on the host cores)
+
+A "step" is one pass of find() over the rank's whole batch.  `value` is measured with the batch
+resident in HBM (CUDA events on the launching stream); `e2e` through the C-ABI host entry point
+gcsa_b200_find_host with pinned host buffers (H2D and D2H inside the timed region).
+Weak scaling: every rank searches its own batch of the same size against its own replica of the
+index; the only collective is the all-reduce of the result counters and of the step time (max).
+
+Only the cpu_baseline leg and --impl reference execute oracle/ (as the thing timed on the CPU,
+never on the product path).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "kmer_find_queries_per_sec"
+UNIT = "queries/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-mbp", type=float, default=100.0, help="length of the synthetic linear reference (Mbp)")
+    ap.add_argument("--queries", type=int, default=10_000_000, help="patterns per GPU")
+    ap.add_argument("--pattern-length", type=int, default=32)
+    ap.add_argument("--kmer-table-k", type=int, default=12)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="queries of the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--locate", action="store_true", help="also report locate() positions/s on a 1 M sample")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def workload_name(args):
+    return "cfg2: %d x %d-mers sampled from a %g Mbp synthetic linear reference (seed 2), order-128 index (k=16, 3 doubling steps)" % (
+        args.queries, args.pattern_length, args.ref_mbp)
+
+
+def build_or_load_index(args, rank, world, barrier):
+    """Rank 0 builds the index on the host (CPU, untimed) and shares it through /dev/shm."""
+    from gcsa2_b200 import synth
+    from gcsa2_b200.builder import build_index
+    from gcsa2_b200.flat import FlatGCSA
+    L = int(args.ref_mbp * 1_000_000)
+    seq = synth.random_sequence(L, seed=2)
+    shared = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir(),
+                          "gcsa2_b200_bench_%d_%d.npz" % (L, os.getppid() if world > 1 else os.getpid()))
+    flat = None
+    t0 = time.time()
+    if rank == 0:
+        flat, _, _ = build_index(synth.linear_graph(seq, node_len=32), 16, 3)
+        if world > 1:
+            flat.save(shared)
+    barrier()
+    if rank != 0:
+        flat = FlatGCSA.load(shared)
+    barrier()
+    if rank == 0 and world > 1 and os.path.exists(shared):
+        os.remove(shared)
+    return seq, flat, time.time() - t0
+
+
+def make_patterns(seq, n, length, seed):
+    from gcsa2_b200 import synth
+    chars = np.empty(n * length, dtype=np.uint8)
+    step = 1_000_000
+    for i, q0 in enumerate(range(0, n, step)):
+        m = min(step, n - q0)
+        c, _ = synth.patterns_from_sequence(seq, m, length, seed=seed * 1000 + i)
+        chars[q0 * length:(q0 + m) * length] = c
+    offsets = np.arange(n + 1, dtype=np.uint64) * np.uint64(length)
+    return chars, offsets
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(flat, chars, offsets, length, sample, threads=None):
+    """The CPU restatement (oracle/) timed on the host cores: benchmark/query_gcsa.cpp:88-103's loop,
+    OpenMP over queries like src/algorithms.cpp:113."""
+    from oracle import oracle as orc
+    ora = orc.OracleGCSA(flat)
+    threads = threads or orc.lib().oracle_max_threads()
+    n = min(sample, len(offsets) - 1)
+    c, o = chars[:n * length], offsets[:n + 1]
+    ora.find_batch(c[:length * min(n, 20000)], o[:min(n, 20000) + 1], threads=threads)       # warm the caches
+    best = None
+    for _ in range(2):
+        _, _, secs = ora.find_batch(c, o, threads=threads)
+        best = secs if best is None else min(best, secs)
+    return ora, {"value": n / best, "unit": UNIT, "cores": threads, "kind": "port",
+                 "sample": "%d of the same %d-mers, best of 2, %d OpenMP threads (schedule dynamic,4096)" % (n, length, threads),
+                 "seconds": best}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (restated in oracle/; the reference itself cannot be
+    built here because sdsl-lite is absent), all host threads, a bounded sample per step."""
+    if rank != 0:
+        return
+    seq, flat, build_s = build_or_load_index(args, 0, 1, lambda: None)
+    from oracle import oracle as orc
+    threads = orc.lib().oracle_max_threads()
+    sample = args.cpu_sample or min(args.queries, 200_000 * threads)
+    chars, offsets = make_patterns(seq, sample, args.pattern_length, seed=11)
+    ora = orc.OracleGCSA(flat)
+    times = []
+    for i in range(args.warmup + args.steps):
+        _, _, secs = ora.find_batch(chars, offsets, threads=threads)
+        if i >= args.warmup:
+            times.append(secs)
+    ms = 1000.0 * float(np.mean(times))
+    value = sample / (ms / 1000.0)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "step": "bounded sample of %d queries per step" % sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "%d queries per step, %d OpenMP threads" % (sample, threads)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "index_build_s": build_s}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank, world, local = dist_env()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier(device_ids=[local])
+
+    from gcsa2_b200 import GCSA
+    seq, flat, build_s = build_or_load_index(args, rank, world, barrier)
+    n, length = args.queries, args.pattern_length
+    chars, offsets = make_patterns(seq, n, length, seed=100 + rank)
+
+    t0 = time.time()
+    index = GCSA(flat, device=local, kmer_table_k=args.kmer_table_k)
+    create_s = time.time() - t0
+
+    # ---- device-resident leg ----
+    d_chars = torch.from_numpy(chars).cuda()
+    d_off = torch.from_numpy(offsets.view(np.int64)).cuda()
+    d_sp = torch.empty(n, dtype=torch.int64, device="cuda"); d_ep = torch.empty_like(d_sp)
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        index.find_device(d_chars, d_off, n, d_sp, d_ep, stream.cuda_stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize(); barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    ev1.record(stream)
+    torch.cuda.synchronize(); barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+
+    # results of the last step: counters
+    sp = d_sp.cpu().numpy().view(np.uint64); ep = d_ep.cpu().numpy().view(np.uint64)
+    found = int(np.count_nonzero((sp + np.uint64(1)) <= (ep + np.uint64(1))))
+
+    # ---- end-to-end leg: pinned host buffers through gcsa_b200_find_host ----
+    h_chars = torch.from_numpy(chars).pin_memory(); h_off = torch.from_numpy(offsets.view(np.int64)).pin_memory()
+    h_sp = torch.empty(n, dtype=torch.int64).pin_memory(); h_ep = torch.empty(n, dtype=torch.int64).pin_memory()
+
+    def step_e2e():
+        index.find_host_raw(h_chars.data_ptr(), h_off.data_ptr(), n, h_sp.data_ptr(), h_ep.data_ptr())
+
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
+    torch.cuda.synchronize(); barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_ms = 1000.0 * (time.perf_counter() - t0) / args.steps
+    barrier()
+    e2e_same = bool((h_sp.numpy().view(np.uint64) == sp).all() and (h_ep.numpy().view(np.uint64) == ep).all())
+
+    # ---- work counters for the roofline (untimed; a 1 M sample through the stats kernel) ----
+    m = min(n, 1_000_000)
+    _, _, st = index.find_batch(chars[:m * length], offsets[:m + 1], stats=True)
+    scale = n / m
+    engine_bytes = scale * (32.0 * st["sector_probes"] + 16.0 * st["table_hits"]) + float(n) * (length + 8 + 16)
+
+    # ---- max over ranks, totals ----
+    if dist is not None:
+        t = torch.tensor([ms_step, e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, e2e_ms = float(t[0]), float(t[1])
+        c = torch.tensor([n, found], dtype=torch.int64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)                       # NCCL: gather of the result counters
+        total_q, total_found = int(c[0]), int(c[1])
+    else:
+        total_q, total_found = n, found
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        achieved = engine_bytes / (ms_total / args.steps / 1000.0) / 1e9
+        line = {
+            "metric": METRIC, "value": total_q / (ms_step / 1000.0), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "queries_per_gpu": n, "pattern_length": length,
+                       "index": {"path_nodes": index.size(), "edges": index.edgeCount(), "order": index.order(),
+                                 "device_bytes": index.deviceBytes(), "kmer_table_k": index.kmerTableK()},
+                       "parallelism": "queries sharded across %d GPU(s), index replicated" % world,
+                       "l2": "no explicit flush: every step streams %.0f MB of patterns/offsets/results, more than the 126 MB L2" % (
+                           n * (length + 8 + 16) / 1e6)},
+            "found": total_found, "queries": total_q,
+            "e2e": {"value": total_q / (e2e_ms / 1000.0), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(n * length + (n + 1) * 8), "d2h_bytes_per_step": int(n * 16),
+                    "api": "gcsa_b200_find_host (pinned host buffers, chunked H2D/kernel/D2H pipeline)",
+                    "matches_device_leg": e2e_same},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "find_kernel<false>", "peak_source": peak_src,
+                         "bytes_per_launch": engine_bytes,
+                         "accounting": "32 B per distinct fused-sector probe + 16 B per k-mer table entry + |P| + 8 + 16 B I/O per query",
+                         "lf_steps_per_query": st["lf_steps"] / m, "sector_probes_per_query": st["sector_probes"] / m},
+            "clocks": clocks,
+            "setup": {"index_build_s": build_s, "index_create_s": create_s},
+        }
+        if not args.no_cpu_baseline:
+            threads = None
+            sample = args.cpu_sample
+            from oracle import oracle as orc
+            threads = orc.lib().oracle_max_threads()
+            sample = sample or min(n, 200_000 * threads)
+            ora, cb = cpu_baseline(flat, chars, offsets, length, sample, threads)
+            osp, oep, _, steps_ref, probes_ref = ora.find_batch(chars[:m * length], offsets[:m + 1], threads=threads, stats=True)
+            cb["parity_on_sample"] = bool((osp == sp[:m]).all() and (oep == ep[:m]).all())
+            line["cpu_baseline"] = cb
+            ref_bytes = scale * 64.0 * probes_ref + float(n) * (length + 16)
+            line["roofline"]["reference_accounting"] = {
+                "bytes_per_launch": ref_bytes, "achieved": ref_bytes / (ms_total / args.steps / 1000.0) / 1e9,
+                "note": "SURVEY.md 8(d): 64 B per distinct rank probe of the reference algorithm + |P| + 16 B; exceeds what the fused layout moves"}
+        print(json.dumps(line), flush=True)
+
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

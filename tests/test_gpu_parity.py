@@ -1,0 +1,214 @@
+"""Parity of the CUDA engine with the CPU oracle, through the C ABI (needs a GPU).
+
+Bit-exact comparison of every operation of SURVEY.md section 8(a): find, charRange, LF(range),
+LF(node), LF_fast/LF_all, count, locate (x3), parent, depth, psv/psev/nsv/nsev, rmq."""
+import numpy as np
+import pytest
+
+from brute import random_graph
+from helpers import kat1_flat, load_kat1
+from verify import kmer_table, verify_index
+from gcsa2_b200 import GCSA, LCPArray, synth
+from gcsa2_b200.builder import CharGraph, build_index
+from gcsa2_b200.flat import FlatLCP
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+M64 = (1 << 64) - 1
+
+
+def empty(sp, ep):
+    return ((int(sp) + 1) & M64) > ((int(ep) + 1) & M64)
+
+
+def both(flat, table_k=0):
+    return GCSA(flat, kmer_table_k=table_k), orc.OracleGCSA(flat)
+
+
+def assert_find_equal(gpu, ora, chars, offsets, threads=4):
+    sp, ep = gpu.find_batch(chars, offsets)
+    osp, oep, _ = ora.find_batch(chars, offsets, threads=threads)
+    bad = np.flatnonzero((sp != osp) | (ep != oep))
+    assert bad.size == 0, (bad[:5], sp[bad[:5]], ep[bad[:5]], osp[bad[:5]], oep[bad[:5]])
+    return sp, ep
+
+
+def random_ranges(rng, n_nodes, n):
+    """Valid, empty, singleton, full and out-of-range ranges."""
+    a = rng.integers(0, n_nodes, size=n).astype(np.uint64)
+    ln = np.minimum(rng.geometric(0.3, size=n), n_nodes).astype(np.uint64)
+    b = np.minimum(a + ln - np.uint64(1), np.uint64(n_nodes - 1))
+    sp = np.concatenate([a, [0, 0, 1, 5, n_nodes - 1, 3]]).astype(np.uint64)
+    ep = np.concatenate([b, [n_nodes - 1, M64, 0, 4, n_nodes + 3, 3]]).astype(np.uint64)
+    return sp, ep
+
+
+# ---------------------------------------------------------------------------------------------
+
+def test_kat1_golden_vectors():
+    kat = load_kat1()
+    flat, lcp = kat1_flat(kat)
+    for table_k in (0, 1, 2, 3):
+        gpu = GCSA(flat, kmer_table_k=table_k)
+        for pattern, expected in kat["find"].items():
+            got = gpu.find(pattern)
+            if expected is None:
+                assert empty(*got), (pattern, got)
+            else:
+                assert list(got) == expected, (pattern, got, table_k)
+        assert gpu.find("ATT") == (5, 4)
+        comp = {"$": 0, "A": 1, "C": 2, "G": 3, "T": 4, "N": 5, "#": 6}
+        for case in kat["lf"]:
+            assert list(gpu.LF(tuple(case["range"]), comp[case["char"]])) == case["result"]
+        for pattern, expected in kat["locate"].items():
+            rng = gpu.find(pattern)
+            assert gpu.locate(rng) == sorted(expected) and gpu.count(rng) == len(expected)
+        for i, vals in enumerate(kat["values"]):
+            assert gpu.locate(i) == sorted(vals)
+        assert gpu.locate(99) == [] and gpu.locate((3, 99)) == [] and gpu.count((5, 4)) == 0
+        assert [gpu.charRange(c) for c in range(7)] == [orc.OracleGCSA(flat).char_range(c) for c in range(7)]
+    glcp = LCPArray(FlatLCP.from_values(np.array(lcp, dtype=np.uint8), branching=4))
+    assert glcp.parent((2, 4)) == (1, 4, 0, 0, 1) and glcp.depth((2, 4)) == 2
+    assert glcp.parent((0, 15)) == (0, 15, 0, 0, 0)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_all_operations_random_graphs(seed):
+    rng = np.random.default_rng(100 + seed)
+    g = random_graph(rng, int(rng.integers(200, 1500)), 8, snp_rate=0.1, node_len=4,
+                     alphabet=[(1, 2, 3, 4), (1, 2)][seed % 2])
+    cg = CharGraph.from_lists(g.comps, g.values, g.succ, g.sources, g.sink)
+    flat, flcp, kmers = build_index(cg, 2, 2, sample_period=[4, 64][seed % 2], lcp_branching=[2, 4, 64, 3][seed])
+    gpu, ora = both(flat, table_k=[0, 2, 3, 5][seed])
+    N = flat.path_nodes
+
+    # find: patterns of every kind (ragged lengths, empty, with $, #, N, lower case, garbage bytes)
+    alphabet = np.frombuffer(b"ACGTACGTACGTacgtN$#x\0", dtype=np.uint8)
+    lengths = rng.integers(0, 14, size=4000)
+    offsets = np.zeros(lengths.size + 1, dtype=np.uint64); offsets[1:] = np.cumsum(lengths)
+    chars = alphabet[rng.integers(0, alphabet.size, size=int(offsets[-1]) + 1)]
+    assert_find_equal(gpu, ora, chars, offsets)
+    table = kmer_table(kmers)
+    chars2, offsets2 = orc.pack_patterns([s for s, _ in table])
+    sp, ep = assert_find_equal(gpu, ora, chars2, offsets2)
+    assert not any(empty(a, b) for a, b in zip(sp, ep))
+
+    # LF(range, comp) for all comps (incl. invalid range shapes), LF(node), LF_fast / LF_all
+    rsp, rep = random_ranges(rng, N, 3000)
+    comps = rng.integers(0, 7, size=rsp.size).astype(np.uint8)
+    valid = ~np.array([empty(a, b) or b >= N for a, b in zip(rsp, rep)])
+    gsp, gep = gpu.lf_batch(rsp[valid], rep[valid], comps[valid])
+    for i, (a, b, c) in enumerate(zip(rsp[valid], rep[valid], comps[valid])):
+        assert (int(gsp[i]), int(gep[i])) == ora.LF((int(a), int(b)), int(c))
+    nodes = np.arange(N, dtype=np.uint64)
+    assert list(gpu.lf_node_batch(nodes)) == [ora.LF(int(i)) for i in nodes]
+    multi_sp, multi_ep = rsp[valid][:500], rep[valid][:500]
+    for all_chars in (0, 1):
+        out = gpu.lf_multi_batch(multi_sp, multi_ep, all_chars)
+        last = 5 if all_chars else 4
+        for i, (a, b) in enumerate(zip(multi_sp, multi_ep)):
+            exp = (ora.LF_all if all_chars else ora.LF_fast)((int(a), int(b)))
+            for c in range(1, last + 1):
+                assert (int(out[i, c, 0]), int(out[i, c, 1])) == exp[c], (a, b, c)
+
+    # count / locate on arbitrary ranges, including empty and out-of-range ones
+    cnt = gpu.count_batch(rsp, rep)
+    assert list(cnt) == [ora.count((int(a), int(b))) for a, b in zip(rsp, rep)]
+    offs, vals = gpu.locate_batch(rsp, rep)
+    ooffs, ovals, _ = ora.locate_batch(rsp, rep, threads=2)
+    assert (offs == ooffs).all() and (vals == ovals).all()
+    assert (np.diff(offs) == cnt).all()                                   # query_gcsa.cpp:171-179
+    for m in (1, 3, 10):
+        moffs, mvals = gpu.locate_batch(rsp[:300], rep[:300], max_positions=m)
+        for i in range(300):
+            assert list(mvals[int(moffs[i]):int(moffs[i + 1])]) == ora.locate((int(rsp[i]), int(rep[i])), m)
+
+    # LCP operations
+    glcp, olcp = LCPArray(flcp), orc.OracleLCP(flcp)
+    psp, pep = rsp[valid], rep[valid]
+    par = glcp.parent_batch(psp, pep)
+    opar, _ = olcp.parent_batch(psp, pep)
+    assert (par == opar).all()
+    assert list(glcp.depth_batch(psp, pep)) == [olcp.depth((int(a), int(b))) for a, b in zip(psp, pep)]
+    pos = np.concatenate([np.arange(N), [N, N + 5]]).astype(np.uint64)
+    for which in ("psv", "psev", "nsv", "nsev"):
+        a, b = glcp.sv_batch(which, pos)
+        assert [(int(x), int(y)) for x, y in zip(a, b)] == [getattr(olcp, which)(int(p)) for p in pos], which
+    qa, qb = rng.integers(0, N, size=2000), rng.integers(0, N + 2, size=2000)
+    a, b = glcp.rmq_batch(qa, qb)
+    assert [(int(x), int(y)) for x, y in zip(a, b)] == [olcp.rmq(int(s), int(e)) for s, e in zip(qa, qb)]
+
+    # the reference's own predicates, evaluated through the engine
+    assert verify_index(gpu, glcp, table, limit=150, seed=seed) == []
+
+
+def test_linear_reference_order128_kmer_table_invariance():
+    """1 Mbp linear reference, order 128: 32-mers sampled from it and uniform random 32-mers;
+    identical answers with and without the k-mer table."""
+    seq = synth.random_sequence(1_000_000, seed=2)
+    flat, flcp, _ = build_index(synth.linear_graph(seq), 16, 3)
+    ora = orc.OracleGCSA(flat)
+    chars, offsets = synth.patterns_from_sequence(seq, 200_000, 32, seed=5)
+    rchars, roffsets = synth.random_patterns(200_000, 32, seed=6)
+    ref = None
+    for table_k in (0, 4, 10):
+        gpu = GCSA(flat, kmer_table_k=table_k)
+        sp, ep = assert_find_equal(gpu, ora, chars, offsets)
+        assert not np.any(sp > ep)                       # all sampled patterns occur
+        rsp, rep = assert_find_equal(gpu, ora, rchars, roffsets)
+        if ref is None:
+            ref = (sp, ep, rsp, rep)
+        else:
+            assert all((a == b).all() for a, b in zip(ref, (sp, ep, rsp, rep)))
+        # round trip: locate(find(P)) contains the position P was cut from
+        starts = np.random.default_rng(5).integers(0, seq.size - 32 + 1, size=200_000)
+        offs, vals = gpu.locate_batch(sp[:5000], ep[:5000])
+        graph_values = synth.linear_graph(seq).value
+        for i in range(5000):
+            assert graph_values[1 + starts[i]] in vals[int(offs[i]):int(offs[i + 1])]
+        stats = gpu.find_batch(chars[:3200], offsets[:101], stats=True)[2]
+        assert stats["queries"] == 100 and stats["found"] == 100
+        assert stats["lf_steps"] == 100 * (31 if table_k == 0 else 32 - table_k)
+        gpu.close()
+
+
+def test_snp_graph_find_locate_parent():
+    seq = synth.random_sequence(300_000, seed=3)
+    graph, sites, alt = synth.snp_graph(seq, seed=3, snp_rate=0.01)
+    flat, flcp, kmers = build_index(graph, 16, 3)
+    gpu, ora = both(flat, table_k=8)
+    glcp, olcp = LCPArray(flcp), orc.OracleLCP(flcp)
+    chars, offsets = synth.patterns_from_snp_graph(seq, sites, alt, 50_000, 64, seed=7)
+    sp, ep = assert_find_equal(gpu, ora, chars, offsets)
+    assert not np.any(sp > ep)
+    offs, vals = gpu.locate_batch(sp, ep)
+    ooffs, ovals, _ = ora.locate_batch(sp, ep, threads=4)
+    assert (offs == ooffs).all() and (vals == ovals).all()
+    assert (gpu.count_batch(sp, ep) == np.diff(offs)).all()
+    par = glcp.parent_batch(sp, ep)
+    opar, _ = olcp.parent_batch(sp, ep, threads=4)
+    assert (par == opar).all()
+    mchars, moffsets = synth.mixed_length_patterns(seq, sites, alt, 20_000, 16, 256, seed=8)
+    assert_find_equal(gpu, ora, mchars, moffsets)
+    assert verify_index(gpu, glcp, kmer_table(kmers), limit=100) == []
+
+
+def test_device_pointer_entry_point_and_empty_batches():
+    import torch
+    seq = synth.random_sequence(50_000, seed=4)
+    flat, _, _ = build_index(synth.linear_graph(seq), 16, 1)
+    gpu, ora = both(flat)
+    chars, offsets = synth.patterns_from_sequence(seq, 10_000, 24, seed=1)
+    d_chars = torch.from_numpy(chars).cuda(); d_off = torch.from_numpy(offsets.view(np.int64)).cuda()
+    d_sp = torch.empty(10_000, dtype=torch.int64, device="cuda"); d_ep = torch.empty_like(d_sp)
+    stream = torch.cuda.current_stream().cuda_stream
+    gpu.find_device(d_chars, d_off, 10_000, d_sp, d_ep, stream)
+    torch.cuda.synchronize()
+    osp, oep, _ = ora.find_batch(chars, offsets)
+    assert (d_sp.cpu().numpy().view(np.uint64) == osp).all() and (d_ep.cpu().numpy().view(np.uint64) == oep).all()
+    sp, ep = gpu.find_batch([])
+    assert sp.size == 0 and ep.size == 0
+    assert gpu.count_batch([], []).size == 0
+    offs, vals = gpu.locate_batch([], [])
+    assert list(offs) == [0] and vals.size == 0
+    assert gpu.find("") == (0, flat.path_nodes - 1)
