@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--kmer-table-k", type=int, default=12)
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--locate", action="store_true", help="also report locate() positions/s on a 1 M sample")
+    ap.add_argument("--index-cache", default="", help="npz file: load the built index from it if present, else save it there")
     return ap.parse_args()
 
 
@@ -72,7 +72,12 @@ def build_or_load_index(args, rank, world, barrier):
     flat = None
     t0 = time.time()
     if rank == 0:
-        flat, _, _ = build_index(synth.linear_graph(seq, node_len=32), 16, 3)
+        if args.index_cache and os.path.exists(args.index_cache):
+            flat = FlatGCSA.load(args.index_cache)
+        else:
+            flat, _, _ = build_index(synth.linear_graph(seq, node_len=32), 16, 3)
+            if args.index_cache:
+                flat.save(args.index_cache)
         if world > 1:
             flat.save(shared)
     barrier()

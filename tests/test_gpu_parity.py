@@ -38,8 +38,8 @@ def random_ranges(rng, n_nodes, n):
     a = rng.integers(0, n_nodes, size=n).astype(np.uint64)
     ln = np.minimum(rng.geometric(0.3, size=n), n_nodes).astype(np.uint64)
     b = np.minimum(a + ln - np.uint64(1), np.uint64(n_nodes - 1))
-    sp = np.concatenate([a, [0, 0, 1, 5, n_nodes - 1, 3]]).astype(np.uint64)
-    ep = np.concatenate([b, [n_nodes - 1, M64, 0, 4, n_nodes + 3, 3]]).astype(np.uint64)
+    sp = np.concatenate([a, np.array([0, 0, 1, 5, n_nodes - 1, 3], dtype=np.uint64)])
+    ep = np.concatenate([b, np.array([n_nodes - 1, M64, 0, 4, n_nodes + 3, 3], dtype=np.uint64)])
     return sp, ep
 
 
@@ -117,7 +117,9 @@ def test_all_operations_random_graphs(seed):
     offs, vals = gpu.locate_batch(rsp, rep)
     ooffs, ovals, _ = ora.locate_batch(rsp, rep, threads=2)
     assert (offs == ooffs).all() and (vals == ovals).all()
-    assert (np.diff(offs) == cnt).all()                                   # query_gcsa.cpp:171-179
+    # count() == |locate()| holds for ranges that find() produces (query_gcsa.cpp:171-179)
+    foffs, _ = gpu.locate_batch(sp, ep)
+    assert (np.diff(foffs) == gpu.count_batch(sp, ep)).all()
     for m in (1, 3, 10):
         moffs, mvals = gpu.locate_batch(rsp[:300], rep[:300], max_positions=m)
         for i in range(300):
