@@ -496,9 +496,20 @@ uint64_t oracle_locate_max(const oracle_gcsa* g, uint64_t sp, uint64_t ep, uint6
   }
   else
   {
+    /* The reference loops until enough distinct values were seen; that never ends when count()
+       overestimates the distinct values of a range that is not a suffix-tree node.  Oracle and
+       engine both give up after 16 * length + 1024 draws and locate the whole range instead. */
     u64set found; set_init(&found, 16);
+    uint64_t draws = 0, max_draws = 16 * range_length(sp, ep) + 1024;
     while(found.size < max_positions)
     {
+      if(draws++ >= max_draws)
+      {
+        locate_range_vec(g, sp, ep, &results);
+        for(uint64_t i = 0; i < results.size; i++) { set_insert(&found, results.data[i]); }
+        results.size = 0;
+        break;
+      }
       uint64_t pos = sp + oracle_mt64_next(&rng) % range_length(sp, ep);
       locate_internal(g, pos, &results);
       for(uint64_t i = 0; i < results.size; i++) { set_insert(&found, results.data[i]); }

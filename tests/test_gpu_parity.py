@@ -120,10 +120,12 @@ def test_all_operations_random_graphs(seed):
     # count() == |locate()| holds for ranges that find() produces (query_gcsa.cpp:171-179)
     foffs, _ = gpu.locate_batch(sp, ep)
     assert (np.diff(foffs) == gpu.count_batch(sp, ep)).all()
+    wide = np.argsort(-(ep - sp).astype(np.int64))[:150]              # the widest find() ranges + some arbitrary ones
+    msp = np.concatenate([sp[wide], rsp[:150]]); mep = np.concatenate([ep[wide], rep[:150]])
     for m in (1, 3, 10):
-        moffs, mvals = gpu.locate_batch(rsp[:300], rep[:300], max_positions=m)
-        for i in range(300):
-            assert list(mvals[int(moffs[i]):int(moffs[i + 1])]) == ora.locate((int(rsp[i]), int(rep[i])), m)
+        moffs, mvals = gpu.locate_batch(msp, mep, max_positions=m)
+        for i in range(msp.size):
+            assert list(mvals[int(moffs[i]):int(moffs[i + 1])]) == ora.locate((int(msp[i]), int(mep[i])), m)
 
     # LCP operations
     glcp, olcp = LCPArray(flcp), orc.OracleLCP(flcp)
