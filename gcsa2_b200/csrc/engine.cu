@@ -1487,7 +1487,7 @@ int gcsa_b200_locate_host(const gcsa_b200_index* index, const uint64_t* sp, cons
   u64 needed = 0;
   u64* d_vals = nullptr;
   int rc = 0;
-  if(n == 0) { out_offsets[0] = 0; }
+  if(n == 0) { out_offsets[0] = 0; *values = (uint64_t*)std::malloc(sizeof(u64)); }
   else
   {
     rc = locateDevice(index, a, b, n, offs, nullptr, 0, &needed, sc.stream, &d_vals);

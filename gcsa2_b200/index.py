@@ -192,6 +192,8 @@ class GCSA:
             capi.check(capi.lib().gcsa_b200_locate_max_host(self._h, sp.ctypes.data, ep.ctypes.data, n, int(max_positions),
                                                             offs.ctypes.data, C.byref(p)))
         total = int(offs[n])
+        if not p.value:
+            return offs, np.zeros(0, dtype=np.uint64)
         vals = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(max(total, 1),))[:total].copy()
         capi.lib().gcsa_b200_free(p)
         return offs, vals
