@@ -19,7 +19,8 @@
   * SELECT VECTORS (SadaSparse::values, SadaCount::data): rank vector + one hint per 512 ones.
   * samples/select (gcsa.h:235-236) is replaced by an explicit start-offset array per sampled node.
   * sparse characters ($, N, #; sparse_bwt of gcsa.h:221-223) are sorted position lists.
-  * optional k-mer table: find() results of all 4^k ACGT strings of length k (16 bytes each).
+  * optional k-mer table: find() results of all 4^k ACGT strings of length k, 8 bytes each
+    (sp in 40 bits, range length in 24 bits; an empty result always has ep = sp - 1).
 */
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
@@ -46,6 +47,7 @@ typedef unsigned char u8;
 #define RV_W 192u
 #define SEL_HINT 512u
 #define M40 ((1ull << 40) - 1)
+#define TABLE_ESCAPE 0xFFFFFFull
 
 //------------------------------------------------------------------------------
 // Errors
@@ -75,7 +77,7 @@ struct DevView
   SelVecDev extra_values, redundant;
   const u64* sparse_pos[3]; u64 sparse_n[3];       // comps 0, 5, 6
   const u64* stored_samples; const u64* sample_start; u64 sample_count;
-  const ulonglong2* table; int table_k;
+  const u64* table; int table_k;      // entry = sp | length << 40; length 0xFFFFFF = not tabulated
   u8 char2comp[256];
 };
 
@@ -276,8 +278,8 @@ struct FindStatsDev { u64 found, total_length, lf_steps, sector_probes, table_hi
   range became empty (or whose pattern is exhausted) is refilled on the next step, the
   assignment being computed with one ballot + popc (no atomics, no shared memory).
 */
-template<bool STATS>
-__global__ void __launch_bounds__(256)
+template<bool STATS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(256, MIN_BLOCKS)
 find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict__ offsets, u64 char_base,
             u64 n, u64* __restrict__ sp_out, u64* __restrict__ ep_out, FindStatsDev* stats)
 {
@@ -329,9 +331,13 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
               }
               if(ok)
               {
-                ulonglong2 r = __ldg(v.table + idx);
-                sp = r.x; ep = r.y; pos = e - v.table_k; used_table = true;
-                if(STATS) { st_hits++; }
+                u64 r = __ldg(v.table + idx);
+                u64 len = r >> 40;
+                if(len != TABLE_ESCAPE)
+                {
+                  sp = r & M40; ep = sp + len - 1; pos = e - v.table_k; used_table = true;
+                  if(STATS) { st_hits++; }
+                }
               }
             }
             if(!used_table)
@@ -374,23 +380,54 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
   }
 }
 
-// Fills the k-mer table: entry idx = find() of the string whose t-th character from the END is
-// comp ((idx >> 2t) & 3) + 1.  Early exit exactly as find() does, so empty entries carry the
-// same uncanonicalised pair the full search would return.
+/*
+  k-mer table.  Entry idx describes the string whose t-th character from the END is comp
+  ((idx >> 2t) & 3) + 1 and holds exactly what find() returns for it, early exit included: an
+  empty result keeps the uncanonicalised pair of the step where the search died, and such a pair
+  always has ep = sp - 1 (rank is monotone), so (sp, length) loses nothing.
+  The table is grown one character at a time: level j+1 is one LF step away from level j.
+*/
 __global__ void __launch_bounds__(256)
-table_kernel(const DevView v, int k, ulonglong2* table)
+table_init_kernel(const DevView v, ulonglong2* tmp)
 {
-  u64 total = 1ull << (2 * k);
+  u32 idx = threadIdx.x;
+  if(idx < 4) { tmp[idx] = make_ulonglong2(v.char_sp[idx + 1], v.char_ep[idx + 1]); }
+}
+
+// level j (4^j entries in tmp[0, 4^j)) -> level j + 1 in place: slot idx | c << 2j
+__global__ void __launch_bounds__(256)
+table_extend_kernel(const DevView v, int j, ulonglong2* tmp)
+{
+  u64 total = 1ull << (2 * j);
   for(u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x)
   {
-    u32 c = (u32)(idx & 3) + 1;
-    u64 sp = v.char_sp[c], ep = v.char_ep[c];
-    for(int t = 1; t < k && !range_empty(sp, ep); t++)
+    ulonglong2 r = tmp[idx];
+    #pragma unroll
+    for(u32 c = 4; c-- > 0; )
     {
-      c = (u32)((idx >> (2 * t)) & 3) + 1;
-      lf_range(v, sp, ep, c, sp, ep);
+      u64 sp = r.x, ep = r.y;
+      if(!range_empty(sp, ep)) { lf_range(v, sp, ep, c + 1, sp, ep); }
+      tmp[idx | ((u64)c << (2 * j))] = make_ulonglong2(sp, ep);
     }
-    table[idx] = make_ulonglong2(sp, ep);
+  }
+}
+
+// last level: level k - 1 in tmp -> packed level k in table (k >= 2); for k == 1 pack tmp itself
+__global__ void __launch_bounds__(256)
+table_final_kernel(const DevView v, int k, const ulonglong2* tmp, u64* table)
+{
+  u64 total = (k == 1 ? 4 : 1ull << (2 * (k - 1)));
+  for(u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x)
+  {
+    ulonglong2 r = tmp[idx];
+    for(u32 c = 0; c < (k == 1 ? 1u : 4u); c++)
+    {
+      u64 sp = r.x, ep = r.y;
+      if(k > 1 && !range_empty(sp, ep)) { lf_range(v, sp, ep, c + 1, sp, ep); }
+      u64 len = ep + 1 - sp;
+      u64 entry = (len >= TABLE_ESCAPE || sp > M40) ? (TABLE_ESCAPE << 40) : (sp | (len << 40));
+      table[k == 1 ? idx : (idx | ((u64)c << (2 * (k - 1))))] = entry;
+    }
   }
 }
 
@@ -960,6 +997,12 @@ int gcsa_b200_index_create(const gcsa_flat_index* host, int device, const gcsa_b
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
   }
+  if(const char* g = std::getenv("GCSA_B200_L2_FETCH"))
+  {
+    // Random 32-byte sector probes: ask the L2 not to over-fetch neighbouring sectors from HBM.
+    size_t bytes = (size_t)std::atoi(g);
+    if(bytes == 32 || bytes == 64 || bytes == 128) { cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, bytes); }
+  }
   gcsa_b200_index* idx = new gcsa_b200_index();
   idx->device = device;
   cudaDeviceGetAttribute(&idx->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -1072,18 +1115,28 @@ int gcsa_b200_index_create(const gcsa_flat_index* host, int device, const gcsa_b
   // k-mer table
   int k = (options ? options->kmer_table_k : 0);
   if(k < 0) { k = 0; }
-  if(k > 15) { k = 15; }
+  if(k > 16) { k = 16; }
   if(k > 0 && N > 0)
   {
     u64 entries = 1ull << (2 * k);
-    void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, entries * sizeof(ulonglong2));
-    if(e != cudaSuccess) { gcsa_b200_index_destroy(idx); return fail(GCSA_B200_ERR_NOMEM, "index_create: k-mer table allocation failed"); }
-    idx->allocations.push_back(p); idx->device_bytes += entries * sizeof(ulonglong2);
-    table_kernel<<<gridFor(entries, idx->sm_count, 8), 256>>>(v, k, (ulonglong2*)p);
+    u64 tmp_entries = (k == 1 ? 4 : 1ull << (2 * (k - 1)));
+    void* p = nullptr; void* tmp = nullptr;
+    cudaError_t e = cudaMalloc(&p, entries * sizeof(u64));
+    if(e == cudaSuccess) { e = cudaMalloc(&tmp, tmp_entries * sizeof(ulonglong2)); }
+    if(e != cudaSuccess)
+    {
+      if(p) { cudaFree(p); }
+      gcsa_b200_index_destroy(idx);
+      return fail(GCSA_B200_ERR_NOMEM, "index_create: k-mer table allocation failed");
+    }
+    idx->allocations.push_back(p); idx->device_bytes += entries * sizeof(u64);
+    table_init_kernel<<<1, 256>>>(v, (ulonglong2*)tmp);
+    for(int j = 1; j + 1 < k; j++) { table_extend_kernel<<<gridFor(1ull << (2 * j), idx->sm_count, 8), 256>>>(v, j, (ulonglong2*)tmp); }
+    table_final_kernel<<<gridFor(tmp_entries, idx->sm_count, 8), 256>>>(v, k, (const ulonglong2*)tmp, (u64*)p);
     e = cudaDeviceSynchronize();
-    if(e != cudaSuccess) { gcsa_b200_index_destroy(idx); return fail(GCSA_B200_ERR_CUDA, std::string("table_kernel: ") + cudaGetErrorString(e)); }
-    v.table = (const ulonglong2*)p; v.table_k = k;
+    cudaFree(tmp);
+    if(e != cudaSuccess) { gcsa_b200_index_destroy(idx); return fail(GCSA_B200_ERR_CUDA, std::string("k-mer table kernels: ") + cudaGetErrorString(e)); }
+    v.table = (const u64*)p; v.table_k = k;
   }
   #undef TRY_RC
 
@@ -1127,9 +1180,11 @@ static int launchFind(const gcsa_b200_index* index, const u8* d_chars, const u64
 {
   if(n == 0) { return 0; }
   // persistent grid: 8 CTAs of 256 threads per SM (2048 resident threads), slices per warp
-  int grid = gridFor(n, index->sm_count, 8);
-  if(d_stats) { find_kernel<true><<<grid, 256, 0, stream>>>(index->view, d_chars, d_offsets, char_base, n, d_sp, d_ep, d_stats); }
-  else { find_kernel<false><<<grid, 256, 0, stream>>>(index->view, d_chars, d_offsets, char_base, n, d_sp, d_ep, nullptr); }
+  static const int min_blocks = []() { const char* e = std::getenv("GCSA_B200_FIND_MINBLOCKS"); return (e ? std::atoi(e) : 6); }();
+  int grid = gridFor(n, index->sm_count, min_blocks >= 8 ? 8 : 6);
+  if(d_stats) { find_kernel<true, 1><<<grid, 256, 0, stream>>>(index->view, d_chars, d_offsets, char_base, n, d_sp, d_ep, d_stats); }
+  else if(min_blocks >= 8) { find_kernel<false, 8><<<grid, 256, 0, stream>>>(index->view, d_chars, d_offsets, char_base, n, d_sp, d_ep, nullptr); }
+  else { find_kernel<false, 6><<<grid, 256, 0, stream>>>(index->view, d_chars, d_offsets, char_base, n, d_sp, d_ep, nullptr); }
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
