@@ -232,12 +232,11 @@ def main():
 
     # ---- device-resident leg ----
     d_chars = torch.from_numpy(chars).cuda()
-    d_off = torch.from_numpy(offsets.view(np.int64)).cuda()
     d_sp = torch.empty(n, dtype=torch.int64, device="cuda"); d_ep = torch.empty_like(d_sp)
     stream = torch.cuda.current_stream()
 
     def step_device():
-        index.find_device(d_chars, d_off, n, d_sp, d_ep, stream.cuda_stream)
+        index.find_fixed_device(d_chars, length, n, d_sp, d_ep, stream.cuda_stream)
 
     for _ in range(max(args.warmup, 3)):
         step_device()
@@ -261,11 +260,11 @@ def main():
     found = int(np.count_nonzero((sp + np.uint64(1)) <= (ep + np.uint64(1))))
 
     # ---- end-to-end leg: pinned host buffers through gcsa_b200_find_host ----
-    h_chars = torch.from_numpy(chars).pin_memory(); h_off = torch.from_numpy(offsets.view(np.int64)).pin_memory()
+    h_chars = torch.from_numpy(chars).pin_memory()
     h_sp = torch.empty(n, dtype=torch.int64).pin_memory(); h_ep = torch.empty(n, dtype=torch.int64).pin_memory()
 
     def step_e2e():
-        index.find_host_raw(h_chars.data_ptr(), h_off.data_ptr(), n, h_sp.data_ptr(), h_ep.data_ptr())
+        index.find_fixed_host_raw(h_chars.data_ptr(), length, n, h_sp.data_ptr(), h_ep.data_ptr())
 
     for _ in range(max(args.warmup, 3)):
         step_e2e()
@@ -282,7 +281,10 @@ def main():
     m = min(n, 1_000_000)
     _, _, st = index.find_batch(chars[:m * length], offsets[:m + 1], stats=True)
     scale = n / m
-    engine_bytes = scale * (32.0 * st["sector_probes"] + 16.0 * st["table_hits"]) + float(n) * (length + 8 + 16)
+    # 64 B per distinct rank probe (the HBM access granule: a missed 32-byte sector
+    # costs one 64-byte fetch), here one probe = one fused sector; 8 B per k-mer table entry read;
+    # |P| + 16 B of I/O per query.
+    engine_bytes = scale * (64.0 * st["sector_probes"] + 8.0 * st["table_hits"]) + float(n) * (length + 16)
 
     # ---- max over ranks, totals ----
     if dist is not None:
@@ -307,17 +309,17 @@ def main():
                                  "device_bytes": index.deviceBytes(), "kmer_table_k": index.kmerTableK()},
                        "parallelism": "queries sharded across %d GPU(s), index replicated" % world,
                        "l2": "no explicit flush: every step streams %.0f MB of patterns/offsets/results, more than the 126 MB L2" % (
-                           n * (length + 8 + 16) / 1e6)},
+                           n * (length + 16) / 1e6)},
             "found": total_found, "queries": total_q,
             "e2e": {"value": total_q / (e2e_ms / 1000.0), "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(n * length + (n + 1) * 8), "d2h_bytes_per_step": int(n * 16),
-                    "api": "gcsa_b200_find_host (pinned host buffers, chunked H2D/kernel/D2H pipeline)",
+                    "h2d_bytes_per_step": int(n * length), "d2h_bytes_per_step": int(n * 16),
+                    "api": "gcsa_b200_find_fixed_host (pinned host buffers, chunked H2D/kernel/D2H pipeline)",
                     "matches_device_leg": e2e_same},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "find_kernel<false>", "peak_source": peak_src,
+                         "traffic": None, "kernel": "find_kernel<false,6>", "peak_source": peak_src,
                          "bytes_per_launch": engine_bytes,
-                         "accounting": "32 B per distinct fused-sector probe + 16 B per k-mer table entry + |P| + 8 + 16 B I/O per query",
+                         "accounting": "64 B per distinct fused-sector probe executed + 8 B per k-mer table entry + |P| + 16 B I/O per query (SURVEY.md 8(d) units)",
                          "lf_steps_per_query": st["lf_steps"] / m, "sector_probes_per_query": st["sector_probes"] / m},
             "clocks": clocks,
             "setup": {"index_build_s": build_s, "index_create_s": create_s},
@@ -335,7 +337,7 @@ def main():
             ref_bytes = scale * 64.0 * probes_ref + float(n) * (length + 16)
             line["roofline"]["reference_accounting"] = {
                 "bytes_per_launch": ref_bytes, "achieved": ref_bytes / (ms_total / args.steps / 1000.0) / 1e9,
-                "note": "SURVEY.md 8(d): 64 B per distinct rank probe of the reference algorithm + |P| + 16 B; exceeds what the fused layout moves"}
+                "note": "64 B per distinct rank probe the REFERENCE algorithm issues (4 per LF step, no k-mer table) + |P| + 16 B; the fused layout and the table avoid most of them"}
         print(json.dumps(line), flush=True)
 
     if dist is not None:

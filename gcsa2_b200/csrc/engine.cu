@@ -281,7 +281,7 @@ struct FindStatsDev { u64 found, total_length, lf_steps, sector_probes, table_hi
 template<bool STATS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(256, MIN_BLOCKS)
 find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict__ offsets, u64 char_base,
-            u64 n, u64* __restrict__ sp_out, u64* __restrict__ ep_out, FindStatsDev* stats)
+            u64 fixed_length, u64 n, u64* __restrict__ sp_out, u64* __restrict__ ep_out, FindStatsDev* stats)
 {
   __shared__ u8 c2c[256];
   for(int i = threadIdx.x; i < 256; i += blockDim.x) { c2c[i] = v.char2comp[i]; }
@@ -313,7 +313,9 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
         if(cand < slice_end)
         {
           q = cand;
-          u64 b = offsets[q] - char_base, e = offsets[q + 1] - char_base;
+          u64 b, e;
+          if(offsets != nullptr) { b = offsets[q] - char_base; e = offsets[q + 1] - char_base; }
+          else { b = q * fixed_length; e = b + fixed_length; }
           begin = b; live = true;
           if(e == b || v.path_nodes == 0) { sp = 0; ep = v.path_nodes - 1; pos = b; }
           else
@@ -1175,16 +1177,16 @@ int gcsa_b200_char_range(const gcsa_b200_index* index, uint64_t comp, uint64_t* 
 // find
 //------------------------------------------------------------------------------
 
-static int launchFind(const gcsa_b200_index* index, const u8* d_chars, const u64* d_offsets, u64 char_base, u64 n,
-                      u64* d_sp, u64* d_ep, FindStatsDev* d_stats, cudaStream_t stream)
+static int launchFind(const gcsa_b200_index* index, const u8* d_chars, const u64* d_offsets, u64 char_base, u64 fixed_length,
+                      u64 n, u64* d_sp, u64* d_ep, FindStatsDev* d_stats, cudaStream_t stream)
 {
   if(n == 0) { return 0; }
   // persistent grid: 8 CTAs of 256 threads per SM (2048 resident threads), slices per warp
   static const int min_blocks = []() { const char* e = std::getenv("GCSA_B200_FIND_MINBLOCKS"); return (e ? std::atoi(e) : 6); }();
   int grid = gridFor(n, index->sm_count, min_blocks >= 8 ? 8 : 6);
-  if(d_stats) { find_kernel<true, 1><<<grid, 256, 0, stream>>>(index->view, d_chars, d_offsets, char_base, n, d_sp, d_ep, d_stats); }
-  else if(min_blocks >= 8) { find_kernel<false, 8><<<grid, 256, 0, stream>>>(index->view, d_chars, d_offsets, char_base, n, d_sp, d_ep, nullptr); }
-  else { find_kernel<false, 6><<<grid, 256, 0, stream>>>(index->view, d_chars, d_offsets, char_base, n, d_sp, d_ep, nullptr); }
+  if(d_stats) { find_kernel<true, 1><<<grid, 256, 0, stream>>>(index->view, d_chars, d_offsets, char_base, fixed_length, n, d_sp, d_ep, d_stats); }
+  else if(min_blocks >= 8) { find_kernel<false, 8><<<grid, 256, 0, stream>>>(index->view, d_chars, d_offsets, char_base, fixed_length, n, d_sp, d_ep, nullptr); }
+  else { find_kernel<false, 6><<<grid, 256, 0, stream>>>(index->view, d_chars, d_offsets, char_base, fixed_length, n, d_sp, d_ep, nullptr); }
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -1197,17 +1199,28 @@ int gcsa_b200_find_batch(const gcsa_b200_index* index, const uint8_t* d_chars, c
     return fail(GCSA_B200_ERR_INVALID, "find_batch: null argument");
   }
   DeviceGuard guard(index->device);
-  return launchFind(index, d_chars, (const u64*)d_offsets, 0, n, (u64*)d_sp, (u64*)d_ep, nullptr, (cudaStream_t)stream);
+  return launchFind(index, d_chars, (const u64*)d_offsets, 0, 0, n, (u64*)d_sp, (u64*)d_ep, nullptr, (cudaStream_t)stream);
+}
+
+int gcsa_b200_find_fixed_batch(const gcsa_b200_index* index, const uint8_t* d_chars, uint64_t pattern_length,
+                               uint64_t n, uint64_t* d_sp, uint64_t* d_ep, void* stream)
+{
+  if(index == nullptr || (n > 0 && (d_chars == nullptr || d_sp == nullptr || d_ep == nullptr)))
+  {
+    return fail(GCSA_B200_ERR_INVALID, "find_fixed_batch: null argument");
+  }
+  DeviceGuard guard(index->device);
+  return launchFind(index, d_chars, nullptr, 0, pattern_length, n, (u64*)d_sp, (u64*)d_ep, nullptr, (cudaStream_t)stream);
 }
 
 /*
   Host-buffer find: the batch is cut into chunks that are pipelined over three streams
   (H2D of chunk i+1 overlaps the kernel of chunk i and the D2H of chunk i-1).
 */
-static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const uint64_t* offsets, uint64_t n,
-                    uint64_t* sp, uint64_t* ep, gcsa_b200_find_stats* stats)
+static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const uint64_t* offsets, uint64_t fixed_length,
+                    uint64_t n, uint64_t* sp, uint64_t* ep, gcsa_b200_find_stats* stats)
 {
-  if(index == nullptr || (n > 0 && (chars == nullptr || offsets == nullptr || sp == nullptr || ep == nullptr)))
+  if(index == nullptr || (n > 0 && (chars == nullptr || sp == nullptr || ep == nullptr)))
   {
     return fail(GCSA_B200_ERR_INVALID, "find_host: null argument");
   }
@@ -1215,8 +1228,10 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
   if(n == 0) { return 0; }
   DeviceGuard guard(index->device);
 
+  // Chunks of >= 1 M queries, at most ~8 per batch: large enough for PCIe to reach its streaming
+  // rate, enough of them for the copy engines and the SMs to overlap.
   const int STREAMS = 3;
-  const u64 CHUNK = 1ull << 20;
+  const u64 CHUNK = std::max<u64>(1ull << 20, (n + 7) / 8);
   cudaStream_t streams[STREAMS];
   for(int s = 0; s < STREAMS; s++) { CUDA_TRY(cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking)); }
   FindStatsDev* d_stats = nullptr;
@@ -1228,19 +1243,19 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
   {
     cudaStream_t st = streams[c % STREAMS];
     u64 q0 = c * CHUNK, q1 = std::min(n, q0 + CHUNK), m = q1 - q0;
-    u64 c0 = offsets[q0], c1 = offsets[q1], bytes = c1 - c0;
+    u64 c0 = (offsets ? offsets[q0] : q0 * fixed_length), c1 = (offsets ? offsets[q1] : q1 * fixed_length), bytes = c1 - c0;
     u8* d_chars = nullptr; u64* d_off = nullptr; u64* d_res = nullptr;
     cudaError_t e;
     if((e = cudaMallocAsync(&d_chars, bytes + 16, st)) != cudaSuccess ||
-       (e = cudaMallocAsync(&d_off, (m + 1) * sizeof(u64), st)) != cudaSuccess ||
+       (offsets && (e = cudaMallocAsync(&d_off, (m + 1) * sizeof(u64), st)) != cudaSuccess) ||
        (e = cudaMallocAsync(&d_res, 2 * m * sizeof(u64), st)) != cudaSuccess)
     { rc = fail(GCSA_B200_ERR_NOMEM, std::string("find_host: ") + cudaGetErrorString(e)); break; }
     if(bytes) { cudaMemcpyAsync(d_chars, chars + c0, bytes, cudaMemcpyHostToDevice, st); }
-    cudaMemcpyAsync(d_off, offsets + q0, (m + 1) * sizeof(u64), cudaMemcpyHostToDevice, st);
-    rc = launchFind(index, d_chars, d_off, c0, m, d_res, d_res + m, d_stats, st);
+    if(offsets) { cudaMemcpyAsync(d_off, offsets + q0, (m + 1) * sizeof(u64), cudaMemcpyHostToDevice, st); }
+    rc = launchFind(index, d_chars, d_off, c0, fixed_length, m, d_res, d_res + m, d_stats, st);
     cudaMemcpyAsync(sp + q0, d_res, m * sizeof(u64), cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(ep + q0, d_res + m, m * sizeof(u64), cudaMemcpyDeviceToHost, st);
-    cudaFreeAsync(d_chars, st); cudaFreeAsync(d_off, st); cudaFreeAsync(d_res, st);
+    cudaFreeAsync(d_chars, st); if(d_off) { cudaFreeAsync(d_off, st); } cudaFreeAsync(d_res, st);
   }
   cudaError_t err = cudaSuccess;
   for(int s = 0; s < STREAMS; s++)
@@ -1265,14 +1280,22 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
 int gcsa_b200_find_host(const gcsa_b200_index* index, const uint8_t* chars, const uint64_t* offsets,
                         uint64_t n, uint64_t* sp, uint64_t* ep)
 {
-  return findHost(index, chars, offsets, n, sp, ep, nullptr);
+  if(n > 0 && offsets == nullptr) { return fail(GCSA_B200_ERR_INVALID, "find_host: null offsets"); }
+  return findHost(index, chars, offsets, 0, n, sp, ep, nullptr);
+}
+
+int gcsa_b200_find_fixed_host(const gcsa_b200_index* index, const uint8_t* chars, uint64_t pattern_length,
+                              uint64_t n, uint64_t* sp, uint64_t* ep)
+{
+  return findHost(index, chars, nullptr, pattern_length, n, sp, ep, nullptr);
 }
 
 int gcsa_b200_find_stats_host(const gcsa_b200_index* index, const uint8_t* chars, const uint64_t* offsets,
                               uint64_t n, uint64_t* sp, uint64_t* ep, gcsa_b200_find_stats* stats)
 {
   if(stats == nullptr) { return fail(GCSA_B200_ERR_INVALID, "find_stats_host: null stats"); }
-  return findHost(index, chars, offsets, n, sp, ep, stats);
+  if(n > 0 && offsets == nullptr) { return fail(GCSA_B200_ERR_INVALID, "find_stats_host: null offsets"); }
+  return findHost(index, chars, offsets, 0, n, sp, ep, stats);
 }
 
 //------------------------------------------------------------------------------

@@ -108,6 +108,21 @@ class GCSA:
         """Host pointers (e.g. pinned torch tensors' data_ptr()); the C ABI call a user makes."""
         capi.check(capi.lib().gcsa_b200_find_host(self._h, chars_ptr, offsets_ptr, int(n), sp_ptr, ep_ptr))
 
+    def find_fixed_host_raw(self, chars_ptr, pattern_length, n, sp_ptr, ep_ptr):
+        """k-mer form: n patterns of one length back to back, host pointers."""
+        capi.check(capi.lib().gcsa_b200_find_fixed_host(self._h, chars_ptr, int(pattern_length), int(n), sp_ptr, ep_ptr))
+
+    def find_fixed_batch(self, chars, pattern_length):
+        chars = np.ascontiguousarray(chars, dtype=np.uint8)
+        n = chars.size // int(pattern_length) if pattern_length else 0
+        sp = np.zeros(max(n, 1), dtype=np.uint64); ep = np.zeros(max(n, 1), dtype=np.uint64)
+        self.find_fixed_host_raw(chars.ctypes.data, pattern_length, n, sp.ctypes.data, ep.ctypes.data)
+        return sp[:n], ep[:n]
+
+    def find_fixed_device(self, d_chars, pattern_length, n, d_sp, d_ep, stream=0):
+        capi.check(capi.lib().gcsa_b200_find_fixed_batch(self._h, capi.ptr(d_chars), int(pattern_length), int(n),
+                                                         capi.ptr(d_sp), capi.ptr(d_ep), stream or None))
+
     def find_device(self, d_chars, d_offsets, n, d_sp, d_ep, stream=0):
         """Device pointers / tensors, stream-ordered, no synchronisation."""
         capi.check(capi.lib().gcsa_b200_find_batch(self._h, capi.ptr(d_chars), capi.ptr(d_offsets), int(n),

@@ -79,7 +79,7 @@ typedef struct gcsa_b200_stnode { uint64_t sp, ep, left_lcp, right_lcp, node_lcp
 
 typedef struct gcsa_b200_options {
   int      kmer_table_k;   /* 0 = none; else a lookup table of find() results for all ACGT strings of
-                              this length is built at creation (4^k * 16 bytes) and used to skip the
+                              this length is built at creation (4^k * 8 bytes) and used to skip the
                               first k backward steps.  -1 = engine default. */
   int      reserved[7];
 } gcsa_b200_options;
@@ -119,6 +119,12 @@ int gcsa_b200_find_batch(const gcsa_b200_index* index, const uint8_t* d_chars, c
                          uint64_t n, uint64_t* d_sp, uint64_t* d_ep, void* stream);
 int gcsa_b200_find_host(const gcsa_b200_index* index, const uint8_t* chars, const uint64_t* offsets,
                         uint64_t n, uint64_t* sp, uint64_t* ep);
+/* The k-mer form of the same call: n patterns of one length stored back to back (pattern i is
+   chars[i * pattern_length .. (i + 1) * pattern_length)), no offsets array to move. */
+int gcsa_b200_find_fixed_batch(const gcsa_b200_index* index, const uint8_t* d_chars, uint64_t pattern_length,
+                               uint64_t n, uint64_t* d_sp, uint64_t* d_ep, void* stream);
+int gcsa_b200_find_fixed_host(const gcsa_b200_index* index, const uint8_t* chars, uint64_t pattern_length,
+                              uint64_t n, uint64_t* sp, uint64_t* ep);
 /* Same answers plus executed-work counters (slower; for the roofline accounting only). */
 int gcsa_b200_find_stats_host(const gcsa_b200_index* index, const uint8_t* chars, const uint64_t* offsets,
                               uint64_t n, uint64_t* sp, uint64_t* ep, gcsa_b200_find_stats* stats);

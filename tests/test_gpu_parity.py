@@ -160,6 +160,8 @@ def test_linear_reference_order128_kmer_table_invariance():
         sp, ep = assert_find_equal(gpu, ora, chars, offsets)
         assert not np.any(sp > ep)                       # all sampled patterns occur
         rsp, rep = assert_find_equal(gpu, ora, rchars, roffsets)
+        fsp, fep = gpu.find_fixed_batch(chars, 32)            # k-mer form of the same call
+        assert (fsp == sp).all() and (fep == ep).all()
         if ref is None:
             ref = (sp, ep, rsp, rep)
         else:
