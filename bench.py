@@ -291,8 +291,8 @@ def main():
         t = torch.tensor([ms_step, e2e_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step, e2e_ms = float(t[0]), float(t[1])
-        c = torch.tensor([n, found], dtype=torch.int64, device="cuda")
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)                       # NCCL: gather of the result counters
+        from gcsa2_b200 import dist as gd
+        c = gd.all_reduce_counters(gd.find_counters(sp, ep), device="cuda")   # NCCL: gather of the result counters
         total_q, total_found = int(c[0]), int(c[1])
     else:
         total_q, total_found = n, found

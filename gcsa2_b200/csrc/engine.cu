@@ -1455,7 +1455,7 @@ template<class T> int scanExclusive(const T* in, T* out, u64 count, cudaStream_t
 */
 int locateDevice(const gcsa_b200_index* index, const u64* d_sp, const u64* d_ep, u64 n,
                  u64* d_out_offsets, u64* d_values, u64 capacity, u64* needed, cudaStream_t st,
-                 u64** d_values_alloc = nullptr)
+                 u64** d_values_alloc = nullptr, bool sorted_unique = true)
 {
   const DevView& v = index->view;
   const int sm = index->sm_count;
@@ -1507,6 +1507,23 @@ int locateDevice(const gcsa_b200_index* index, const u64* d_sp, const u64* d_ep,
   if(!raw || !sorted || !seg || !flag || !flag_scan) { cleanup(); return fail(GCSA_B200_ERR_NOMEM, "locate: out of device memory"); }
   locate_fill_kernel<<<gridFor(items, sm), 256, 0, st>>>(v, items, first, steps, val_off, raw);
   locate_segments_kernel<<<gridFor(n + 1, sm), 256, 0, st>>>(node_off, val_off, n, seg);
+  if(!sorted_unique)
+  {
+    // sort = false (src/gcsa.cpp:840): the values in the order locateInternal() produces them
+    if(needed) { *needed = total; }
+    LOC_TRY(cudaMemcpyAsync(d_out_offsets, seg, (n + 1) * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+    int rc0 = 0;
+    if(d_values_alloc != nullptr)
+    {
+      void* p = nullptr;
+      LOC_TRY(cudaMallocAsync(&p, std::max<u64>(total, 1) * sizeof(u64), st));
+      *d_values_alloc = (u64*)p; d_values = (u64*)p; capacity = total;
+    }
+    if(d_values == nullptr || capacity < total) { rc0 = GCSA_B200_ERR_CAPACITY; g_last_error = "locate: output capacity too small"; }
+    else { LOC_TRY(cudaMemcpyAsync(d_values, raw, total * sizeof(u64), cudaMemcpyDeviceToDevice, st)); }
+    cleanup();
+    return rc0;
+  }
   {
     size_t bytes = 0;
     LOC_TRY(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, raw, sorted, (long long)total, (long long)n, seg, seg + 1, st));
@@ -1554,8 +1571,23 @@ int gcsa_b200_locate_batch(const gcsa_b200_index* index, const uint64_t* d_sp, c
   return locateDevice(index, (const u64*)d_sp, (const u64*)d_ep, n, (u64*)d_out_offsets, (u64*)d_values, capacity, (u64*)needed, (cudaStream_t)stream);
 }
 
+static int locateHost(const gcsa_b200_index* index, const uint64_t* sp, const uint64_t* ep, uint64_t n,
+                      uint64_t* out_offsets, uint64_t** values, bool sorted_unique);
+
 int gcsa_b200_locate_host(const gcsa_b200_index* index, const uint64_t* sp, const uint64_t* ep, uint64_t n,
                           uint64_t* out_offsets, uint64_t** values)
+{
+  return locateHost(index, sp, ep, n, out_offsets, values, true);
+}
+
+int gcsa_b200_locate_raw_host(const gcsa_b200_index* index, const uint64_t* sp, const uint64_t* ep, uint64_t n,
+                              uint64_t* out_offsets, uint64_t** values)
+{
+  return locateHost(index, sp, ep, n, out_offsets, values, false);
+}
+
+static int locateHost(const gcsa_b200_index* index, const uint64_t* sp, const uint64_t* ep, uint64_t n,
+                      uint64_t* out_offsets, uint64_t** values, bool sorted_unique)
 {
   if(out_offsets == nullptr || values == nullptr) { return fail(GCSA_B200_ERR_INVALID, "locate_host: null argument"); }
   *values = nullptr;
@@ -1568,7 +1600,7 @@ int gcsa_b200_locate_host(const gcsa_b200_index* index, const uint64_t* sp, cons
   if(n == 0) { out_offsets[0] = 0; *values = (uint64_t*)std::malloc(sizeof(u64)); }
   else
   {
-    rc = locateDevice(index, a, b, n, offs, nullptr, 0, &needed, sc.stream, &d_vals);
+    rc = locateDevice(index, a, b, n, offs, nullptr, 0, &needed, sc.stream, &d_vals, sorted_unique);
     if(rc == 0)
     {
       u64* vals = (u64*)std::malloc(std::max<u64>(needed, 1) * sizeof(u64));

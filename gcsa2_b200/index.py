@@ -195,13 +195,16 @@ class GCSA:
         offs, vals = self.locate_batch(sp, ep, max_positions=max_positions)
         return [int(x) for x in vals[int(offs[0]):int(offs[1])]]
 
-    def locate_batch(self, sp, ep, max_positions=None):
-        """CSR result: values[offsets[i]:offsets[i+1]] are the sorted distinct positions of range i."""
+    def locate_batch(self, sp, ep, max_positions=None, sort=True):
+        """CSR result: values[offsets[i]:offsets[i+1]] are the sorted distinct positions of range i
+        (sort=False: every emitted value in the reference's order, gcsa.cpp:840)."""
         n = len(sp)
         sp, ep = capi.as_u64(sp), capi.as_u64(ep)
         offs = np.zeros(n + 1, dtype=np.uint64)
         p = C.c_void_p()
-        if max_positions is None:
+        if max_positions is None and not sort:
+            capi.check(capi.lib().gcsa_b200_locate_raw_host(self._h, sp.ctypes.data, ep.ctypes.data, n, offs.ctypes.data, C.byref(p)))
+        elif max_positions is None:
             capi.check(capi.lib().gcsa_b200_locate_host(self._h, sp.ctypes.data, ep.ctypes.data, n, offs.ctypes.data, C.byref(p)))
         else:
             capi.check(capi.lib().gcsa_b200_locate_max_host(self._h, sp.ctypes.data, ep.ctypes.data, n, int(max_positions),

@@ -169,6 +169,10 @@ int gcsa_b200_locate_host(const gcsa_b200_index* index, const uint64_t* sp, cons
 int gcsa_b200_locate_batch(const gcsa_b200_index* index, const uint64_t* d_sp, const uint64_t* d_ep, uint64_t n,
                            uint64_t* d_out_offsets, uint64_t* d_values, uint64_t capacity, uint64_t* needed,
                            void* stream);
+/* The sort = false form of the same call (src/gcsa.cpp:840): every value locateInternal() emits,
+   duplicates included, in the reference's order (path nodes ascending, samples in stored order). */
+int gcsa_b200_locate_raw_host(const gcsa_b200_index* index, const uint64_t* sp, const uint64_t* ep, uint64_t n,
+                              uint64_t* out_offsets, uint64_t** values);
 /* GCSA::locate(range_type, max_positions, results), src/gcsa.cpp:844-878 (host buffers). */
 int gcsa_b200_locate_max_host(const gcsa_b200_index* index, const uint64_t* sp, const uint64_t* ep, uint64_t n,
                               uint64_t max_positions, uint64_t* out_offsets, uint64_t** values);

@@ -1,0 +1,65 @@
+"""The N > 1 path on CPU: world_size-2 gloo, query sharding and the counter all-reduce.
+The search itself is stood in for by the CPU oracle (test infrastructure) -- what is under test is
+the host-side sharding / gathering logic of gcsa2_b200.dist."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from gcsa2_b200 import dist as gd, synth
+    from gcsa2_b200.builder import build_index
+    from oracle import oracle as orc
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    seq = synth.random_sequence(20000, seed=1)
+    flat, _, _ = build_index(synth.linear_graph(seq), 16, 1)          # every rank: its own replica
+    ora = orc.OracleGCSA(flat)
+    chars, offsets = synth.patterns_from_sequence(seq, 1001, 20, seed=3)
+    rchars, roffsets = synth.random_patterns(500, 20, seed=4)
+    chars = np.concatenate([chars, rchars]); offsets = np.concatenate([offsets, roffsets[1:] + offsets[-1]])
+    my_chars, my_offsets, (q0, q1) = gd.shard_patterns(chars, offsets, rank, world)
+    sp, ep, _ = ora.find_batch(my_chars, my_offsets)
+    total = gd.all_reduce_counters(gd.find_counters(sp, ep))
+    all_sp, all_ep = gd.gather_ranges(sp, ep)
+    if rank == 0:
+        full_sp, full_ep, _ = ora.find_batch(chars, offsets)
+        expect = gd.find_counters(full_sp, full_ep)
+        np.save(os.path.join(out_dir, "ok.npy"), np.array([
+            int((total == expect).all()), int((all_sp == full_sp).all() and (all_ep == full_ep).all()),
+            int(total[0]), int(total[1])]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_bounds_cover_the_batch():
+    from gcsa2_b200.dist import shard_bounds
+    for n in (0, 1, 7, 8, 1001):
+        for world in (1, 2, 3, 8):
+            blocks = [shard_bounds(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_two_rank_gloo_shard_and_gather(tmp_path):
+    port = free_port()
+    mp.spawn(worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ok = np.load(os.path.join(str(tmp_path), "ok.npy"))
+    assert ok[0] == 1 and ok[1] == 1 and ok[2] == 1501 and 1001 <= ok[3] <= 1501
