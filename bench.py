@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--queries", type=int, default=10_000_000, help="patterns per GPU")
     ap.add_argument("--pattern-length", type=int, default=32)
     ap.add_argument("--kmer-table-k", type=int, default=12)
+    ap.add_argument("--two-step", type=int, default=1, help="1 = build and use the two-step blocks")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--index-cache", default="", help="npz file: load the built index from it if present, else save it there")
@@ -227,7 +228,7 @@ def main():
     chars, offsets = make_patterns(seq, n, length, seed=100 + rank)
 
     t0 = time.time()
-    index = GCSA(flat, device=local, kmer_table_k=args.kmer_table_k)
+    index = GCSA(flat, device=local, kmer_table_k=args.kmer_table_k, two_step=bool(args.two_step))
     create_s = time.time() - t0
 
     # ---- device-resident leg ----
@@ -306,7 +307,7 @@ def main():
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": workload_name(args), "queries_per_gpu": n, "pattern_length": length,
                        "index": {"path_nodes": index.size(), "edges": index.edgeCount(), "order": index.order(),
-                                 "device_bytes": index.deviceBytes(), "kmer_table_k": index.kmerTableK()},
+                                 "device_bytes": index.deviceBytes(), "kmer_table_k": index.kmerTableK(), "two_step": index.twoStep()},
                        "parallelism": "queries sharded across %d GPU(s), index replicated" % world,
                        "l2": "no explicit flush: every step streams %.0f MB of patterns/offsets/results, more than the 126 MB L2" % (
                            n * (length + 16) / 1e6)},

@@ -73,6 +73,7 @@ struct DevView
   u64 C[GCSA_B200_SIGMA + 1];
   u64 char_sp[GCSA_B200_SIGMA], char_ep[GCSA_B200_SIGMA];
   const ulonglong4* bwt;
+  const ulonglong4* bwt2;              // two-step blocks (16 sectors per block), or nullptr
   RankVecDev edges, sampled, extra_filter;
   SelVecDev extra_values, redundant;
   const u64* sparse_pos[3]; u64 sparse_n[3];       // comps 0, 5, 6
@@ -223,6 +224,35 @@ __device__ __forceinline__ void lf_range(const DevView& v, u64 sp, u64 ep, u32 c
 }
 
 /*
+  Two backward steps in one probe.  For a pair of fast characters (c1, c2) the block holds the
+  same sector format over the "squared" graph: B2[i] = 1 iff node i has a predecessor j by c2 that
+  itself has a predecessor h by c1; the 2-paths of one label, ordered by target, are ordered by
+  source as well and consecutive sources differ by at most one node, so the source of the x-th
+  2-path is H0 + popcount(boundary bits), exactly like rank(edges, .) in the one-step sector.
+  Equivalent to LF(LF(range, c2), c1) whenever that is non-empty; returns false otherwise (the
+  caller then takes the two single steps, which produce the reference's uncanonicalised pair).
+*/
+__device__ __forceinline__ bool lf2_range(const DevView& v, u64 sp, u64 ep, u32 c1, u32 c2, u64& osp, u64& oep, u32* sectors = nullptr)
+{
+  u64 e1 = ep + 1;
+  u64 bs = sp / BWT_W, be = e1 / BWT_W;
+  u32 os = (u32)(sp - bs * BWT_W), oe = (u32)(e1 - be * BWT_W);
+  u32 label = (c1 - 1) * 4 + (c2 - 1);
+  ulonglong4 a = ld256(v.bwt2 + bs * 16 + label);
+  ulonglong4 b = a;
+  if(be != bs) { b = ld256(v.bwt2 + be * 16 + label); }
+  if(sectors) { *sectors += (be != bs ? 2 : 1); }
+  u32 js = popc_low88(a.y, (u32)(a.x >> 40), os);
+  u32 je = popc_low88(b.y, (u32)(b.x >> 40), oe);
+  u64 f = (a.x & M40) + js;
+  u64 s = (b.x & M40) + je - 1;
+  if(range_empty(f, s)) { return false; }
+  osp = (a.z & M40) + popc_low88(a.w, (u32)(a.z >> 40), js + 1);
+  oep = (b.z & M40) + popc_low88(b.w, (u32)(b.z >> 40), je);
+  return true;
+}
+
+/*
   GCSA::LF(path_node), include/gcsa/gcsa.h:165-183: first predecessor, fast characters first.
   One 128-byte line holds the four fast sectors of the node's block.
 */
@@ -365,11 +395,25 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
       }
       else
       {
-        pos--;
-        u32 c = c2c[chars[pos]];
+        u32 c = c2c[chars[pos - 1]];
         u32 sectors = 0;
-        lf_range(v, sp, ep, c, sp, ep, STATS ? &sectors : nullptr);
-        if(STATS) { st_steps++; st_sectors += sectors; }
+        bool done = false;
+        if(v.bwt2 != nullptr && pos - begin >= 2 && c >= 1 && c <= 4)
+        {
+          u32 c1 = c2c[chars[pos - 2]];
+          if(c1 >= 1 && c1 <= 4 && lf2_range(v, sp, ep, c1, c, sp, ep, STATS ? &sectors : nullptr))
+          {
+            pos -= 2; done = true;
+            if(STATS) { st_steps += 2; }
+          }
+        }
+        if(!done)
+        {
+          pos--;
+          lf_range(v, sp, ep, c, sp, ep, STATS ? &sectors : nullptr);
+          if(STATS) { st_steps++; }
+        }
+        if(STATS) { st_sectors += sectors; }
       }
     }
   }
@@ -430,6 +474,147 @@ table_final_kernel(const DevView v, int k, const ulonglong2* tmp, u64* table)
       u64 entry = (len >= TABLE_ESCAPE || sp > M40) ? (TABLE_ESCAPE << 40) : (sp | (len << 40));
       table[k == 1 ? idx : (idx | ((u64)c << (2 * (k - 1))))] = entry;
     }
+  }
+}
+
+//------------------------------------------------------------------------------
+// Kernels: construction of the two-step blocks from the one-step blocks
+//------------------------------------------------------------------------------
+
+// predecessor of node i by fast character c (0-based) from its fused sector, or false
+__device__ __forceinline__ bool pred_fast(const DevView& v, u64 i, u32 c, u64& pred)
+{
+  u64 b = i / BWT_W; u32 off = (u32)(i - b * BWT_W);
+  ulonglong4 q = ld256(v.bwt + b * 4 + c);
+  bool bit = (off < 64 ? (q.y >> off) & 1 : ((q.x >> 40) >> (off - 64)) & 1);
+  if(!bit) { return false; }
+  u32 j = popc_low88(q.y, (u32)(q.x >> 40), off);
+  pred = (q.z & M40) + popc_low88(q.w, (u32)(q.z >> 40), j + 1);
+  return true;
+}
+
+// 16-bit mask per node: bit c1 * 4 + c2 set iff the 2-path (c1, c2) into the node exists;
+// per block and label the number of set bits.
+__global__ void __launch_bounds__(128)
+two_step_mask_kernel(const DevView v, u64 n_blocks, unsigned short* m2, u32* blockpop)
+{
+  for(u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += (u64)gridDim.x * blockDim.x)
+  {
+    u32 count[16];
+    #pragma unroll
+    for(int p = 0; p < 16; p++) { count[p] = 0; }
+    for(u32 t = 0; t < BWT_W; t++)
+    {
+      u64 i = b * BWT_W + t;
+      if(i >= v.path_nodes) { break; }
+      u32 m = 0;
+      for(u32 c2 = 0; c2 < 4; c2++)
+      {
+        u64 j;
+        if(!pred_fast(v, i, c2, j)) { continue; }
+        for(u32 c1 = 0; c1 < 4; c1++)
+        {
+          u64 h;
+          if(pred_fast(v, j, c1, h)) { m |= 1u << (c1 * 4 + c2); }
+        }
+      }
+      m2[i] = (unsigned short)m;
+      #pragma unroll
+      for(int p = 0; p < 16; p++) { count[p] += (m >> p) & 1; }
+    }
+    #pragma unroll
+    for(int p = 0; p < 16; p++) { blockpop[(u64)p * n_blocks + b] = count[p]; }
+  }
+}
+
+// source node of every 2-path, label by label, in target order
+__global__ void __launch_bounds__(128)
+two_step_source_kernel(const DevView v, u64 n_blocks, const unsigned short* m2, const u64* blockcnt,
+                       const u64* label_base, u64* src)
+{
+  for(u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += (u64)gridDim.x * blockDim.x)
+  {
+    u64 x[16];
+    #pragma unroll
+    for(int p = 0; p < 16; p++) { x[p] = label_base[p] + blockcnt[(u64)p * n_blocks + b]; }
+    for(u32 t = 0; t < BWT_W; t++)
+    {
+      u64 i = b * BWT_W + t;
+      if(i >= v.path_nodes) { break; }
+      u32 m = m2[i];
+      if(m == 0) { continue; }
+      for(u32 c2 = 0; c2 < 4; c2++)
+      {
+        if(((m >> c2) & 0x1111u) == 0) { continue; }
+        u64 j;
+        if(!pred_fast(v, i, c2, j)) { continue; }
+        for(u32 c1 = 0; c1 < 4; c1++)
+        {
+          u32 p = c1 * 4 + c2;
+          u64 h;
+          if(((m >> p) & 1) && pred_fast(v, j, c1, h))
+          {
+            #pragma unroll
+            for(int q = 0; q < 16; q++) { if(q == (int)p) { src[x[q]] = h; x[q]++; } }
+          }
+        }
+      }
+    }
+  }
+}
+
+// consecutive sources of one label must be equal or differ by one node
+__global__ void __launch_bounds__(256)
+two_step_validate_kernel(const u64* src, const u64* label_base, u32* violations)
+{
+  for(int p = 0; p < 16; p++)
+  {
+    u64 lo = label_base[p], hi = label_base[p + 1];
+    for(u64 x = lo + (u64)blockIdx.x * blockDim.x + threadIdx.x; x + 1 < hi; x += (u64)gridDim.x * blockDim.x)
+    {
+      u64 d = src[x + 1] - src[x];
+      if(d > 1) { atomicAdd(violations, 1u); }
+    }
+  }
+}
+
+// one thread per (block, label): assemble the sector
+__global__ void __launch_bounds__(256)
+two_step_build_kernel(u64 path_nodes, u64 n_blocks, const unsigned short* m2, const u64* blockcnt,
+                      const u64* label_base, const u64* src, ulonglong4* out)
+{
+  u64 total = n_blocks * 16;
+  for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x)
+  {
+    u64 b = t >> 4; u32 p = (u32)(t & 15);
+    u64 x0 = blockcnt[(u64)p * n_blocks + b];
+    u64 blo = 0, bhi = 0;
+    for(u32 k = 0; k < BWT_W; k++)
+    {
+      u64 i = b * BWT_W + k;
+      if(i >= path_nodes) { break; }
+      u64 bit = (m2[i] >> p) & 1;
+      if(k < 64) { blo |= bit << k; } else { bhi |= bit << (k - 64); }
+    }
+    const u64* list = src + label_base[p];
+    u64 len = label_base[p + 1] - label_base[p];
+    u64 h0 = 0, wlo = 0, whi = 0;
+    if(len > 0)
+    {
+      // window bit k describes 2-path x0 - 1 + k: 1 iff it is the last 2-path of its source
+      h0 = (x0 == 0 ? list[0] : list[x0 - 1]);
+      for(u32 k = (x0 == 0 ? 1 : 0); k < 88; k++)
+      {
+        u64 x = x0 - 1 + k;
+        if(x + 1 >= len) { break; }
+        u64 bit = (list[x] != list[x + 1]) ? 1 : 0;
+        if(k < 64) { wlo |= bit << k; } else { whi |= bit << (k - 64); }
+      }
+    }
+    ulonglong4 q;
+    q.x = (x0 & M40) | (bhi << 40); q.y = blo;
+    q.z = (h0 & M40) | (whi << 40); q.w = wlo;
+    out[t] = q;
   }
 }
 
@@ -1114,6 +1299,54 @@ int gcsa_b200_index_create(const gcsa_flat_index* host, int device, const gcsa_b
     TRY_RC(buildSelVec(idx, red, &v.redundant));
   }
 
+  // two-step blocks (optional): built on the device from the one-step blocks
+  if(options && options->two_step > 0 && N > 0)
+  {
+    u64 n_blocks = N / BWT_W + 1;
+    unsigned short* m2 = nullptr; u32* blockpop = nullptr; u64* blockcnt = nullptr; u64* d_base = nullptr; u64* src = nullptr;
+    u32* d_viol = nullptr; void* scan_tmp = nullptr; ulonglong4* blocks2 = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto cleanup2 = [&]() { cudaFree(m2); cudaFree(blockpop); cudaFree(blockcnt); cudaFree(d_base); cudaFree(src); cudaFree(d_viol); cudaFree(scan_tmp); };
+    #define TWO_TRY(expr) do { e = (expr); if(e != cudaSuccess) { cleanup2(); if(blocks2) { cudaFree(blocks2); } gcsa_b200_index_destroy(idx); \
+      return fail(GCSA_B200_ERR_CUDA, std::string("two-step build: " #expr ": ") + cudaGetErrorString(e)); } } while(0)
+    TWO_TRY(cudaMalloc(&m2, (N + 1) * sizeof(unsigned short)));
+    TWO_TRY(cudaMalloc(&blockpop, 16 * n_blocks * sizeof(u32)));
+    TWO_TRY(cudaMalloc(&blockcnt, 16 * n_blocks * sizeof(u64)));
+    TWO_TRY(cudaMalloc(&d_base, 17 * sizeof(u64)));
+    TWO_TRY(cudaMalloc(&d_viol, sizeof(u32)));
+    TWO_TRY(cudaMemset(d_viol, 0, sizeof(u32)));
+    two_step_mask_kernel<<<gridFor(n_blocks, idx->sm_count, 16), 128>>>(v, n_blocks, m2, blockpop);
+    TWO_TRY(cudaGetLastError());
+    size_t scan_bytes = 0;
+    TWO_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, blockpop, blockcnt, n_blocks));
+    TWO_TRY(cudaMalloc(&scan_tmp, std::max<size_t>(scan_bytes, 16)));
+    u64 base[17]; base[0] = 0;
+    for(int p = 0; p < 16; p++)
+    {
+      TWO_TRY(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, blockpop + (u64)p * n_blocks, blockcnt + (u64)p * n_blocks, n_blocks));
+      u64 last_cnt = 0; u32 last_pop = 0;
+      TWO_TRY(cudaMemcpy(&last_cnt, blockcnt + (u64)p * n_blocks + (n_blocks - 1), sizeof(u64), cudaMemcpyDeviceToHost));
+      TWO_TRY(cudaMemcpy(&last_pop, blockpop + (u64)p * n_blocks + (n_blocks - 1), sizeof(u32), cudaMemcpyDeviceToHost));
+      base[p + 1] = base[p] + last_cnt + last_pop;
+    }
+    TWO_TRY(cudaMemcpy(d_base, base, sizeof(base), cudaMemcpyHostToDevice));
+    TWO_TRY(cudaMalloc(&src, std::max<u64>(base[16], 1) * sizeof(u64)));
+    two_step_source_kernel<<<gridFor(n_blocks, idx->sm_count, 16), 128>>>(v, n_blocks, m2, blockcnt, d_base, src);
+    two_step_validate_kernel<<<gridFor(base[16] / 16 + 1, idx->sm_count, 8), 256>>>(src, d_base, d_viol);
+    u32 violations = 0;
+    TWO_TRY(cudaMemcpy(&violations, d_viol, sizeof(u32), cudaMemcpyDeviceToHost));
+    if(violations == 0)
+    {
+      TWO_TRY(cudaMalloc(&blocks2, n_blocks * 16 * sizeof(ulonglong4)));
+      two_step_build_kernel<<<gridFor(n_blocks * 16, idx->sm_count, 8), 256>>>(N, n_blocks, m2, blockcnt, d_base, src, blocks2);
+      TWO_TRY(cudaDeviceSynchronize());
+      idx->allocations.push_back(blocks2); idx->device_bytes += n_blocks * 16 * sizeof(ulonglong4);
+      v.bwt2 = blocks2;
+    }
+    cleanup2();
+    #undef TWO_TRY
+  }
+
   // k-mer table
   int k = (options ? options->kmer_table_k : 0);
   if(k < 0) { k = 0; }
@@ -1162,6 +1395,7 @@ int gcsa_b200_index_info(const gcsa_b200_index* index, gcsa_b200_info* info)
   info->order = index->header.order; info->sample_count = index->header.sample_count;
   info->device_bytes = index->device_bytes; info->kmer_table_k = index->view.table_k;
   info->device = index->device; info->sm_count = index->sm_count;
+  info->two_step = (index->view.bwt2 != nullptr ? 1 : 0);
   return 0;
 }
 

@@ -42,12 +42,12 @@ def range_length(rng):
 
 
 class GCSA:
-    def __init__(self, flat, device=0, kmer_table_k=0):
+    def __init__(self, flat, device=0, kmer_table_k=0, two_step=False):
         self._h = None
         L = capi.lib()
         keep = []
         f = capi.flat_struct(flat, keep)
-        opt = capi.Options(); opt.kmer_table_k = int(kmer_table_k)
+        opt = capi.Options(); opt.kmer_table_k = int(kmer_table_k); opt.two_step = int(bool(two_step))
         h = C.c_void_p()
         capi.check(L.gcsa_b200_index_create(C.byref(f), int(device), C.byref(opt), C.byref(h)))
         self._h = h
@@ -77,6 +77,7 @@ class GCSA:
     def sampleCount(self): return int(self._info.sample_count)
     def deviceBytes(self): return int(self._info.device_bytes)
     def kmerTableK(self): return int(self._info.kmer_table_k)
+    def twoStep(self): return bool(self._info.two_step)
     def smCount(self): return int(self._info.sm_count)
     @property
     def handle(self): return self._h

@@ -81,7 +81,9 @@ typedef struct gcsa_b200_options {
   int      kmer_table_k;   /* 0 = none; else a lookup table of find() results for all ACGT strings of
                               this length is built at creation (4^k * 8 bytes) and used to skip the
                               first k backward steps.  -1 = engine default. */
-  int      reserved[7];
+  int      two_step;       /* 1 = also build the two-step blocks (16 sectors per 87 path nodes, 5.9 B per
+                              node): two backward steps per probe for pairs of ACGT characters. */
+  int      reserved[6];
 } gcsa_b200_options;
 
 typedef struct gcsa_b200_info {
@@ -90,7 +92,7 @@ typedef struct gcsa_b200_info {
   int      kmer_table_k;
   int      device;
   int      sm_count;
-  int      reserved;
+  int      two_step;                   /* 1 if the two-step blocks are in use */
 } gcsa_b200_info;
 
 /* Per-batch statistics of find(): filled by gcsa_b200_find_stats_host (measurement only). */

@@ -21,8 +21,8 @@ def empty(sp, ep):
     return ((int(sp) + 1) & M64) > ((int(ep) + 1) & M64)
 
 
-def both(flat, table_k=0):
-    return GCSA(flat, kmer_table_k=table_k), orc.OracleGCSA(flat)
+def both(flat, table_k=0, two_step=False):
+    return GCSA(flat, kmer_table_k=table_k, two_step=two_step), orc.OracleGCSA(flat)
 
 
 def assert_find_equal(gpu, ora, chars, offsets, threads=4):
@@ -79,7 +79,7 @@ def test_all_operations_random_graphs(seed):
                      alphabet=[(1, 2, 3, 4), (1, 2)][seed % 2])
     cg = CharGraph.from_lists(g.comps, g.values, g.succ, g.sources, g.sink)
     flat, flcp, kmers = build_index(cg, 2, 2, sample_period=[4, 64][seed % 2], lcp_branching=[2, 4, 64, 3][seed])
-    gpu, ora = both(flat, table_k=[0, 2, 3, 5][seed])
+    gpu, ora = both(flat, table_k=[0, 2, 3, 5][seed], two_step=(seed >= 2))
     N = flat.path_nodes
 
     # find: patterns of every kind (ragged lengths, empty, with $, #, N, lower case, garbage bytes)
@@ -155,8 +155,9 @@ def test_linear_reference_order128_kmer_table_invariance():
     chars, offsets = synth.patterns_from_sequence(seq, 200_000, 32, seed=5)
     rchars, roffsets = synth.random_patterns(200_000, 32, seed=6)
     ref = None
-    for table_k in (0, 4, 10):
-        gpu = GCSA(flat, kmer_table_k=table_k)
+    for table_k, two_step in ((0, False), (4, False), (10, True), (0, True), (5, True)):
+        gpu = GCSA(flat, kmer_table_k=table_k, two_step=two_step)
+        assert gpu.twoStep() == two_step
         sp, ep = assert_find_equal(gpu, ora, chars, offsets)
         assert not np.any(sp > ep)                       # all sampled patterns occur
         rsp, rep = assert_find_equal(gpu, ora, rchars, roffsets)
@@ -182,7 +183,8 @@ def test_snp_graph_find_locate_parent():
     seq = synth.random_sequence(300_000, seed=3)
     graph, sites, alt = synth.snp_graph(seq, seed=3, snp_rate=0.01)
     flat, flcp, kmers = build_index(graph, 16, 3)
-    gpu, ora = both(flat, table_k=8)
+    gpu, ora = both(flat, table_k=8, two_step=True)
+    assert gpu.twoStep()
     glcp, olcp = LCPArray(flcp), orc.OracleLCP(flcp)
     chars, offsets = synth.patterns_from_snp_graph(seq, sites, alt, 50_000, 64, seed=7)
     sp, ep = assert_find_equal(gpu, ora, chars, offsets)
