@@ -41,8 +41,8 @@ def parse_args():
     ap.add_argument("--ref-mbp", type=float, default=100.0, help="length of the synthetic linear reference (Mbp)")
     ap.add_argument("--queries", type=int, default=10_000_000, help="patterns per GPU")
     ap.add_argument("--pattern-length", type=int, default=32)
-    ap.add_argument("--kmer-table-k", type=int, default=12)
-    ap.add_argument("--two-step", type=int, default=1, help="1 = build and use the two-step blocks")
+    ap.add_argument("--kmer-table-k", type=int, default=14)
+    ap.add_argument("--two-step", type=int, default=-1, help="1 = build and use the two-step blocks, 0 = never, -1 = by index size")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--index-cache", default="", help="npz file: load the built index from it if present, else save it there")
@@ -228,7 +228,7 @@ def main():
     chars, offsets = make_patterns(seq, n, length, seed=100 + rank)
 
     t0 = time.time()
-    index = GCSA(flat, device=local, kmer_table_k=args.kmer_table_k, two_step=bool(args.two_step))
+    index = GCSA(flat, device=local, kmer_table_k=args.kmer_table_k, two_step=(None if args.two_step < 0 else bool(args.two_step)))
     create_s = time.time() - t0
 
     # ---- device-resident leg ----

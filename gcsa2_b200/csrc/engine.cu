@@ -1300,7 +1300,10 @@ int gcsa_b200_index_create(const gcsa_flat_index* host, int device, const gcsa_b
   }
 
   // two-step blocks (optional): built on the device from the one-step blocks
-  if(options && options->two_step > 0 && N > 0)
+  // -1 = automatic: worth it once the one-step blocks are far beyond the L2 (the probe rate no longer
+  // depends on the footprint there, so halving the probes halves the time; measured in DESIGN.md)
+  bool want_two_step = (options != nullptr && (options->two_step > 0 || (options->two_step < 0 && N >= 400000000ull)));
+  if(want_two_step && N > 0)
   {
     u64 n_blocks = N / BWT_W + 1;
     unsigned short* m2 = nullptr; u32* blockpop = nullptr; u64* blockcnt = nullptr; u64* d_base = nullptr; u64* src = nullptr;

@@ -81,7 +81,7 @@ typedef struct gcsa_b200_options {
   int      kmer_table_k;   /* 0 = none; else a lookup table of find() results for all ACGT strings of
                               this length is built at creation (4^k * 8 bytes) and used to skip the
                               first k backward steps.  -1 = engine default. */
-  int      two_step;       /* 1 = also build the two-step blocks (16 sectors per 87 path nodes, 5.9 B per
+  int      two_step;       /* 1 = also build (-1 = decide by index size, 0 = never) the two-step blocks (16 sectors per 87 path nodes, 5.9 B per
                               node): two backward steps per probe for pairs of ACGT characters. */
   int      reserved[6];
 } gcsa_b200_options;
