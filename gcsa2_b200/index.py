@@ -129,6 +129,21 @@ class GCSA:
         capi.check(capi.lib().gcsa_b200_find_batch(self._h, capi.ptr(d_chars), capi.ptr(d_offsets), int(n),
                                                    capi.ptr(d_sp), capi.ptr(d_ep), stream or None))
 
+    # ---- device-pointer forms (stream-ordered; tensors or raw addresses) ----
+    def lf_device(self, d_sp, d_ep, d_comp, n, d_sp_out, d_ep_out, stream=0):
+        capi.check(capi.lib().gcsa_b200_lf_batch(self._h, capi.ptr(d_sp), capi.ptr(d_ep), capi.ptr(d_comp), int(n),
+                                                 capi.ptr(d_sp_out), capi.ptr(d_ep_out), stream or None))
+
+    def count_device(self, d_sp, d_ep, n, d_out, stream=0):
+        capi.check(capi.lib().gcsa_b200_count_batch(self._h, capi.ptr(d_sp), capi.ptr(d_ep), int(n), capi.ptr(d_out), stream or None))
+
+    def locate_device(self, d_sp, d_ep, n, d_offsets, d_values, capacity, stream=0):
+        """Returns the number of values written (raises GCSAError(ERR_CAPACITY) if capacity is too small)."""
+        needed = C.c_uint64()
+        capi.check(capi.lib().gcsa_b200_locate_batch(self._h, capi.ptr(d_sp), capi.ptr(d_ep), int(n), capi.ptr(d_offsets),
+                                                     capi.ptr(d_values), int(capacity), C.byref(needed), stream or None))
+        return int(needed.value)
+
     # ---- low-level interface (gcsa.h:150-183, gcsa.cpp:742-798) ----
     def charRange(self, comp):
         sp, ep = C.c_uint64(), C.c_uint64()
@@ -263,6 +278,12 @@ class LCPArray:
         out = np.zeros((max(n, 1), 5), dtype=np.uint64)
         capi.check(capi.lib().gcsa_b200_parent_host(self._h, sp.ctypes.data, ep.ctypes.data, n, out.ctypes.data))
         return out[:n]
+
+    def parent_device(self, d_sp, d_ep, n, d_out, stream=0):
+        capi.check(capi.lib().gcsa_b200_parent_batch(self._h, capi.ptr(d_sp), capi.ptr(d_ep), int(n), capi.ptr(d_out), stream or None))
+
+    def depth_device(self, d_sp, d_ep, n, d_out, stream=0):
+        capi.check(capi.lib().gcsa_b200_depth_batch(self._h, capi.ptr(d_sp), capi.ptr(d_ep), int(n), capi.ptr(d_out), stream or None))
 
     def depth(self, rng):
         return int(self.depth_batch([rng[0]], [rng[1]])[0])

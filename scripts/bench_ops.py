@@ -1,0 +1,136 @@
+#!/usr/bin/env python
+"""Per-operation measurements on BASELINE.json configs[2] (SNP-bubble variation graph, order 128):
+find(), count(), locate(), parent(), depth() on the GPU (device-resident, CUDA events) next to the
+CPU oracle on the host cores.  Writes one JSON object per operation.
+
+  python scripts/bench_ops.py [--mbp 50] [--queries 10000000] [--length 64] [--out gpurun_out/ops.json]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mbp", type=float, default=50.0)
+    ap.add_argument("--queries", type=int, default=10_000_000)
+    ap.add_argument("--length", type=int, default=64)
+    ap.add_argument("--snp-rate", type=float, default=0.01)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--cpu-sample", type=int, default=2_000_000)
+    ap.add_argument("--kmer-table-k", type=int, default=14)
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+
+    import torch
+    from gcsa2_b200 import GCSA, LCPArray, synth
+    from gcsa2_b200.builder import build_index
+    from oracle import oracle as orc
+
+    L, n, length = int(args.mbp * 1e6), args.queries, args.length
+    t0 = time.time()
+    seq = synth.random_sequence(L, seed=3)
+    graph, sites, alt = synth.snp_graph(seq, seed=3, snp_rate=args.snp_rate)
+    flat, flcp, _ = build_index(graph, 16, 3)
+    build_s = time.time() - t0
+    chars = np.empty(n * length, dtype=np.uint8)
+    for i, q0 in enumerate(range(0, n, 1_000_000)):
+        m = min(1_000_000, n - q0)
+        c, _ = synth.patterns_from_snp_graph(seq, sites, alt, m, length, seed=700 + i)
+        chars[q0 * length:(q0 + m) * length] = c
+    offsets = np.arange(n + 1, dtype=np.uint64) * np.uint64(length)
+
+    index = GCSA(flat, kmer_table_k=args.kmer_table_k)
+    lcp = LCPArray(flcp)
+    ora, olcp = orc.OracleGCSA(flat), orc.OracleLCP(flcp)
+    threads = orc.lib().oracle_max_threads()
+    stream = torch.cuda.current_stream()
+    results = []
+
+    def timed(fn, steps=args.steps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    def report(op, unit, units_per_step, ms, cpu_value, cpu_sample, parity, extra=None):
+        row = {"op": op, "unit": unit, "gpu_value": units_per_step / (ms / 1000.0), "gpu_ms_per_step": ms,
+               "cpu_value": cpu_value, "cpu_cores": threads, "cpu_sample": cpu_sample, "speedup": units_per_step / (ms / 1000.0) / cpu_value,
+               "parity_on_sample": bool(parity)}
+        row.update(extra or {})
+        results.append(row)
+        print(json.dumps(row), flush=True)
+
+    # ---- find ----
+    d_chars = torch.from_numpy(chars).cuda()
+    d_sp = torch.empty(n, dtype=torch.int64, device="cuda"); d_ep = torch.empty_like(d_sp)
+    ms = timed(lambda: index.find_fixed_device(d_chars, length, n, d_sp, d_ep, stream.cuda_stream))
+    sp = d_sp.cpu().numpy().view(np.uint64); ep = d_ep.cpu().numpy().view(np.uint64)
+    m = min(n, args.cpu_sample)
+    osp, oep, secs = ora.find_batch(chars[:m * length], offsets[:m + 1], threads=threads)
+    report("find (%d-mers from walks through the graph)" % length, "queries/s", n, ms, m / secs, m,
+           (osp == sp[:m]).all() and (oep == ep[:m]).all(),
+           {"found": int(np.count_nonzero(sp <= ep)), "index": {"path_nodes": index.size(), "edges": index.edgeCount(),
+                                                               "device_bytes": index.deviceBytes(), "two_step": index.twoStep(),
+                                                               "kmer_table_k": index.kmerTableK()},
+            "build_s": build_s})
+
+    # ---- count ----
+    d_cnt = torch.empty(n, dtype=torch.int64, device="cuda")
+    ms = timed(lambda: index.count_device(d_sp, d_ep, n, d_cnt, stream.cuda_stream))
+    cnt = d_cnt.cpu().numpy().view(np.uint64)
+    ocnt, secs = ora.count_batch(sp[:m], ep[:m], threads=threads)
+    report("count", "ranges/s", n, ms, m / secs, m, (ocnt == cnt[:m]).all())
+
+    # ---- locate ----
+    total = int(cnt.sum())
+    d_offs = torch.empty(n + 1, dtype=torch.int64, device="cuda")
+    d_vals = torch.empty(total + 16, dtype=torch.int64, device="cuda")
+    got = [0]
+    def do_locate():
+        got[0] = index.locate_device(d_sp, d_ep, n, d_offs, d_vals, total + 16, stream.cuda_stream)
+    ms = timed(do_locate, steps=3)
+    offs = d_offs.cpu().numpy().view(np.uint64); vals = d_vals[:got[0]].cpu().numpy().view(np.uint64)
+    ml = min(m, 1_000_000)
+    ooffs, ovals, secs = ora.locate_batch(sp[:ml], ep[:ml], threads=threads)
+    k = int(ooffs[ml])
+    report("locate (sorted distinct positions per range)", "positions/s", got[0], ms, k / secs, ml,
+           (offs[:ml + 1] == ooffs).all() and (vals[:k] == ovals).all() and got[0] == total,
+           {"positions": got[0], "ranges": n})
+
+    # ---- parent / depth ----
+    d_par = torch.empty((n, 5), dtype=torch.int64, device="cuda")
+    ms = timed(lambda: lcp.parent_device(d_sp, d_ep, n, d_par, stream.cuda_stream))
+    par = d_par.cpu().numpy().view(np.uint64)
+    opar, secs = olcp.parent_batch(sp[:m], ep[:m], threads=threads)
+    report("parent", "ranges/s", n, ms, m / secs, m, (opar == par[:m]).all())
+    d_dep = torch.empty(n, dtype=torch.int64, device="cuda")
+    psp = torch.from_numpy(par[:, 0].copy().view(np.int64)).cuda(); pep = torch.from_numpy(par[:, 1].copy().view(np.int64)).cuda()
+    ms = timed(lambda: lcp.depth_device(psp, pep, n, d_dep, stream.cuda_stream))
+    dep = d_dep.cpu().numpy().view(np.uint64)
+    md = min(m, 200_000)
+    t0 = time.time()
+    odep = np.array([olcp.depth((int(a), int(b))) for a, b in zip(par[:md, 0], par[:md, 1])], dtype=np.uint64)
+    secs = time.time() - t0
+    report("depth (of the parents)", "ranges/s", n, ms, md / secs, md, (odep == dep[:md]).all(), {"cpu_note": "single thread through ctypes"})
+
+    if args.out:
+        with open(args.out, "w") as f:
+            json.dump(results, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
