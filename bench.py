@@ -28,6 +28,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# torchrun exports OMP_NUM_THREADS=1; the host-side index build (rank 0) and the CPU baseline are
+# OpenMP code that should see the box's cores.  Must happen before the libraries are loaded.
+if os.environ.get("OMP_NUM_THREADS") == "1" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+
 METRIC = "kmer_find_queries_per_sec"
 UNIT = "queries/s"
 
