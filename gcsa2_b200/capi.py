@@ -37,7 +37,7 @@ class FlatLcp(C.Structure):
 
 
 class Options(C.Structure):
-    _fields_ = [("kmer_table_k", C.c_int), ("two_step", C.c_int), ("reserved", C.c_int * 6)]
+    _fields_ = [("kmer_table_k", C.c_int), ("two_step", C.c_int), ("walk_table", C.c_int), ("reserved", C.c_int * 5)]
 
 
 class Info(C.Structure):

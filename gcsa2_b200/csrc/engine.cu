@@ -79,6 +79,7 @@ struct DevView
   const u64* sparse_pos[3]; u64 sparse_n[3];       // comps 0, 5, 6
   const u64* stored_samples; const u64* sample_start; u64 sample_count;
   const u64* table; int table_k;      // entry = sp | length << 40; length 0xFFFFFF = not tabulated
+  const u32* walk32; const u64* walk64; // locate walk table: LF(i) << 1, or rank(sampled, i) << 1 | 1 for sampled nodes
   u8 char2comp[256];
 };
 
@@ -735,7 +736,22 @@ locate_walk_kernel(const DevView v, const u64* __restrict__ sp, const u64* __res
     u64 node = sp[lo] + (t - node_off[lo]);
     u32 steps = 0;
     u64 r;
-    while(!rv_get_rank(v.sampled, node, r)) { node = lf_node(v, node); steps++; }
+    if(v.walk32 != nullptr)
+    {
+      u32 e = __ldg(v.walk32 + node);
+      while(!(e & 1)) { e = __ldg(v.walk32 + (e >> 1)); steps++; }
+      r = e >> 1;
+    }
+    else if(v.walk64 != nullptr)
+    {
+      u64 e = __ldg(v.walk64 + node);
+      while(!(e & 1)) { e = __ldg(v.walk64 + (e >> 1)); steps++; }
+      r = e >> 1;
+    }
+    else
+    {
+      while(!rv_get_rank(v.sampled, node, r)) { node = lf_node(v, node); steps++; }
+    }
     u64 s0 = v.sample_start[r], s1 = v.sample_start[r + 1];
     first[t] = s0; steps_out[t] = steps; cnt[t] = s1 - s0;
   }
@@ -797,6 +813,20 @@ locate_offsets_kernel(const u64* __restrict__ seg, const u64* __restrict__ flag_
   {
     u64 s = seg[i];
     out_offsets[i] = (s >= total ? distinct : flag_scan[s]);
+  }
+}
+
+// Walk table for locate: one entry per path node, so that a step of locateInternal()
+// (sampled(i) + LF(i), gcsa.cpp:882-887) is a single load.
+template<class T>
+__global__ void __launch_bounds__(256)
+walk_table_kernel(const DevView v, T* table)
+{
+  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < v.path_nodes; i += (u64)gridDim.x * blockDim.x)
+  {
+    u64 r;
+    if(rv_get_rank(v.sampled, i, r)) { table[i] = (T)((r << 1) | 1); }
+    else { table[i] = (T)(lf_node(v, i) << 1); }
   }
 }
 
@@ -1297,6 +1327,35 @@ int gcsa_b200_index_create(const gcsa_flat_index* host, int device, const gcsa_b
     TRY_RC(buildSelVec(idx, values, &v.extra_values));
     HostBits red = { host->redundant, host->redundant_len };
     TRY_RC(buildSelVec(idx, red, &v.redundant));
+  }
+
+  // locate walk table (optional; 4 or 8 bytes per path node)
+  if(N > 0 && (options == nullptr || options->walk_table != 0))
+  {
+    bool narrow = (N < (1ull << 31));
+    size_t bytes = (size_t)N * (narrow ? sizeof(u32) : sizeof(u64));
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    bool forced = (options != nullptr && options->walk_table > 0);
+    if(forced || bytes < free_b / 4)
+    {
+      void* p = nullptr;
+      cudaError_t e = cudaMalloc(&p, bytes);
+      if(e == cudaSuccess)
+      {
+        if(narrow) { walk_table_kernel<u32><<<gridFor(N, idx->sm_count, 8), 256>>>(v, (u32*)p); }
+        else { walk_table_kernel<u64><<<gridFor(N, idx->sm_count, 8), 256>>>(v, (u64*)p); }
+        e = cudaDeviceSynchronize();
+      }
+      if(e != cudaSuccess)
+      {
+        if(p) { cudaFree(p); }
+        gcsa_b200_index_destroy(idx);
+        return fail(GCSA_B200_ERR_CUDA, std::string("walk table: ") + cudaGetErrorString(e));
+      }
+      idx->allocations.push_back(p); idx->device_bytes += bytes;
+      if(narrow) { v.walk32 = (const u32*)p; } else { v.walk64 = (const u64*)p; }
+    }
   }
 
   // two-step blocks (optional): built on the device from the one-step blocks

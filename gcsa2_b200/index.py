@@ -42,12 +42,13 @@ def range_length(rng):
 
 
 class GCSA:
-    def __init__(self, flat, device=0, kmer_table_k=0, two_step=None):
+    def __init__(self, flat, device=0, kmer_table_k=0, two_step=None, walk_table=None):
         self._h = None
         L = capi.lib()
         keep = []
         f = capi.flat_struct(flat, keep)
         opt = capi.Options(); opt.kmer_table_k = int(kmer_table_k); opt.two_step = (-1 if two_step is None else int(bool(two_step)))
+        opt.walk_table = (-1 if walk_table is None else int(bool(walk_table)))
         h = C.c_void_p()
         capi.check(L.gcsa_b200_index_create(C.byref(f), int(device), C.byref(opt), C.byref(h)))
         self._h = h

@@ -87,7 +87,7 @@ public:
   explicit GCSA(const gcsa_flat_index& flat, int device = 0, int kmer_table_k = 12) : handle(nullptr)
   {
     gcsa_b200_options options = {};
-    options.kmer_table_k = kmer_table_k;
+    options.kmer_table_k = kmer_table_k; options.two_step = -1; options.walk_table = -1;
     check(gcsa_b200_index_create(&flat, device, &options, &handle), "GCSA::GCSA()");
     gcsa_b200_index_info(handle, &info);
     for(int i = 0; i < 256; i++) { char2comp[i] = flat.char2comp[i]; }

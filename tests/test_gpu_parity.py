@@ -21,8 +21,8 @@ def empty(sp, ep):
     return ((int(sp) + 1) & M64) > ((int(ep) + 1) & M64)
 
 
-def both(flat, table_k=0, two_step=False):
-    return GCSA(flat, kmer_table_k=table_k, two_step=two_step), orc.OracleGCSA(flat)
+def both(flat, table_k=0, two_step=False, walk_table=None):
+    return GCSA(flat, kmer_table_k=table_k, two_step=two_step, walk_table=walk_table), orc.OracleGCSA(flat)
 
 
 def assert_find_equal(gpu, ora, chars, offsets, threads=4):
@@ -79,7 +79,7 @@ def test_all_operations_random_graphs(seed):
                      alphabet=[(1, 2, 3, 4), (1, 2)][seed % 2])
     cg = CharGraph.from_lists(g.comps, g.values, g.succ, g.sources, g.sink)
     flat, flcp, kmers = build_index(cg, 2, 2, sample_period=[4, 64][seed % 2], lcp_branching=[2, 4, 64, 3][seed])
-    gpu, ora = both(flat, table_k=[0, 2, 3, 5][seed], two_step=(seed >= 2))
+    gpu, ora = both(flat, table_k=[0, 2, 3, 5][seed], two_step=(seed >= 2), walk_table=[True, False, None, True][seed])
     N = flat.path_nodes
 
     # find: patterns of every kind (ragged lengths, empty, with $, #, N, lower case, garbage bytes)
