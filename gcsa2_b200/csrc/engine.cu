@@ -701,6 +701,37 @@ count_kernel(const DevView v, const u64* __restrict__ sp, const u64* __restrict_
 }
 
 //------------------------------------------------------------------------------
+// Kernels: countKMers (src/algorithms.cpp:364-421) as breadth-first frontier expansion
+//------------------------------------------------------------------------------
+
+// One thread per (frontier range, comp): the child range of processSubtree()'s expansion
+// (LF_fast for bases, LF_all with N), and whether it survives (non-empty).
+__global__ void __launch_bounds__(256)
+kmer_expand_kernel(const DevView v, const u64* __restrict__ sp, const u64* __restrict__ ep, u64 n, u32 chars,
+                   u64* __restrict__ csp, u64* __restrict__ cep, u64* __restrict__ flag)
+{
+  u64 total = n * chars;
+  for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x)
+  {
+    u64 i = t / chars; u32 c = (u32)(t - i * chars) + 1;
+    u64 s = sp[i], e = ep[i], a = 1, b = 0;
+    if(s == e) { if(bwt_bit(v, s, c)) { lf_range(v, s, e, c, a, b); } }      // gcsa.cpp:748-756, 774-789
+    else { lf_range(v, s, e, c, a, b); }
+    csp[t] = a; cep[t] = b; flag[t] = (range_empty(a, b) ? 0 : 1);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+kmer_compact_kernel(const u64* __restrict__ csp, const u64* __restrict__ cep, const u64* __restrict__ flag,
+                    const u64* __restrict__ pos, u64 total, u64* __restrict__ sp, u64* __restrict__ ep)
+{
+  for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x)
+  {
+    if(flag[t]) { sp[pos[t]] = csp[t]; ep[pos[t]] = cep[t]; }
+  }
+}
+
+//------------------------------------------------------------------------------
 // Kernels: locate (src/gcsa.cpp:827-842, 880-896)
 //------------------------------------------------------------------------------
 
@@ -2113,3 +2144,72 @@ int gcsa_b200_lcp_rmq_host(const gcsa_b200_lcp* lcp, const uint64_t* sp, const u
 }
 
 
+
+//------------------------------------------------------------------------------
+// countKMers
+//------------------------------------------------------------------------------
+
+/*
+  countKMers(index, k, parameters), src/algorithms.cpp:387-421: the number of distinct k-mers over
+  the bases (include_Ns: bases and N).  The reference walks the trie depth-first, one OpenMP task
+  per 5-mer seed; here every level of the trie is one frontier expanded by one kernel launch.
+  If ranges != NULL, *ranges receives the final frontier (malloc'ed sp[0..count) then ep[0..count)).
+*/
+int gcsa_b200_count_kmers(const gcsa_b200_index* index, uint64_t k, int include_Ns, uint64_t* result, uint64_t** ranges)
+{
+  if(index == nullptr || result == nullptr) { return fail(GCSA_B200_ERR_INVALID, "count_kmers: null argument"); }
+  *result = 0;
+  if(ranges) { *ranges = nullptr; }
+  if(k == 0) { *result = 1; return 0; }
+  if(index->header.path_nodes == 0) { return 0; }
+  DeviceGuard guard(index->device);
+  cudaStream_t st;
+  CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  const u32 chars = (include_Ns ? GCSA_B200_SIGMA - 2 : GCSA_B200_FAST_CHARS);
+  u64 n = 1;
+  u64 *sp = nullptr, *ep = nullptr;
+  cudaError_t e = cudaSuccess;
+  int rc = 0;
+  #define KM_TRY(expr) do { e = (expr); if(e != cudaSuccess) { rc = fail(GCSA_B200_ERR_CUDA, std::string("count_kmers: " #expr ": ") + cudaGetErrorString(e)); goto done; } } while(0)
+  {
+    u64 root[2] = { 0, index->header.path_nodes - 1 };
+    KM_TRY(cudaMallocAsync(&sp, sizeof(u64), st)); KM_TRY(cudaMallocAsync(&ep, sizeof(u64), st));
+    KM_TRY(cudaMemcpyAsync(sp, &root[0], sizeof(u64), cudaMemcpyHostToDevice, st));
+    KM_TRY(cudaMemcpyAsync(ep, &root[1], sizeof(u64), cudaMemcpyHostToDevice, st));
+    for(u64 level = 0; level < k && n > 0; level++)
+    {
+      u64 total = n * chars;
+      u64 *csp = nullptr, *cep = nullptr, *flag = nullptr, *pos = nullptr;
+      KM_TRY(cudaMallocAsync(&csp, total * sizeof(u64), st)); KM_TRY(cudaMallocAsync(&cep, total * sizeof(u64), st));
+      KM_TRY(cudaMallocAsync(&flag, (total + 1) * sizeof(u64), st)); KM_TRY(cudaMallocAsync(&pos, (total + 1) * sizeof(u64), st));
+      KM_TRY(cudaMemsetAsync(flag + total, 0, sizeof(u64), st));
+      kmer_expand_kernel<<<gridFor(total, index->sm_count), 256, 0, st>>>(index->view, sp, ep, n, chars, csp, cep, flag);
+      rc = scanExclusive(flag, pos, total + 1, st);
+      if(rc) { goto done; }
+      u64 next = 0;
+      KM_TRY(cudaMemcpyAsync(&next, pos + total, sizeof(u64), cudaMemcpyDeviceToHost, st));
+      KM_TRY(cudaStreamSynchronize(st));
+      cudaFreeAsync(sp, st); cudaFreeAsync(ep, st); sp = ep = nullptr;
+      KM_TRY(cudaMallocAsync(&sp, std::max<u64>(next, 1) * sizeof(u64), st)); KM_TRY(cudaMallocAsync(&ep, std::max<u64>(next, 1) * sizeof(u64), st));
+      kmer_compact_kernel<<<gridFor(total, index->sm_count), 256, 0, st>>>(csp, cep, flag, pos, total, sp, ep);
+      cudaFreeAsync(csp, st); cudaFreeAsync(cep, st); cudaFreeAsync(flag, st); cudaFreeAsync(pos, st);
+      n = next;
+    }
+    *result = n;
+    if(ranges && n > 0)
+    {
+      u64* out = (u64*)std::malloc(2 * n * sizeof(u64));
+      KM_TRY(cudaMemcpyAsync(out, sp, n * sizeof(u64), cudaMemcpyDeviceToHost, st));
+      KM_TRY(cudaMemcpyAsync(out + n, ep, n * sizeof(u64), cudaMemcpyDeviceToHost, st));
+      *ranges = (uint64_t*)out;
+    }
+  }
+done:
+  if(sp) { cudaFreeAsync(sp, st); }
+  if(ep) { cudaFreeAsync(ep, st); }
+  e = cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  #undef KM_TRY
+  if(rc == 0 && e != cudaSuccess) { rc = fail(GCSA_B200_ERR_CUDA, std::string("count_kmers: ") + cudaGetErrorString(e)); }
+  return rc;
+}

@@ -189,6 +189,20 @@ class GCSA:
         out = self.lf_multi_batch([rng[0]], [rng[1]], 1)[0]
         return [(int(a), int(b)) for a, b in out]
 
+    # ---- countKMers (algorithms.cpp:387-421) ----
+    def count_kmers(self, k, include_Ns=False, return_ranges=False):
+        res = C.c_uint64(); p = C.c_void_p()
+        capi.check(capi.lib().gcsa_b200_count_kmers(self._h, int(k), int(bool(include_Ns)), C.byref(res),
+                                                    C.byref(p) if return_ranges else None))
+        if not return_ranges:
+            return int(res.value)
+        n = int(res.value)
+        if not p.value:
+            return n, np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.uint64)
+        arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(2 * n,)).copy()
+        capi.lib().gcsa_b200_free(p)
+        return n, arr[:n], arr[n:]
+
     # ---- count / locate (gcsa.cpp:802-878) ----
     def count(self, rng):
         return int(self.count_batch([rng[0]], [rng[1]])[0])

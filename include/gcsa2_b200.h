@@ -184,6 +184,12 @@ int gcsa_b200_locate_max_host(const gcsa_b200_index* index, const uint64_t* sp, 
                               uint64_t max_positions, uint64_t* out_offsets, uint64_t** values);
 void gcsa_b200_free(void* p);
 
+/* countKMers(index, k, parameters), src/algorithms.cpp:387-421 (declared include/gcsa/algorithms.h:80-89):
+   the number of distinct k-mers over the bases (include_Ns != 0: bases and N).  If ranges is not NULL it
+   receives the path ranges of those k-mers in lexicographic order, malloc'ed as sp[0..count) followed by
+   ep[0..count) (release with gcsa_b200_free). */
+int gcsa_b200_count_kmers(const gcsa_b200_index* index, uint64_t k, int include_Ns, uint64_t* result, uint64_t** ranges);
+
 /* LCPArray, include/gcsa/lcp.h:90-194; load() at src/lcp.cpp:116-143. */
 int  gcsa_b200_lcp_create(const gcsa_flat_lcp* host, int device, gcsa_b200_lcp** out);
 void gcsa_b200_lcp_destroy(gcsa_b200_lcp* lcp);

@@ -606,6 +606,68 @@ double oracle_locate_batch(const oracle_gcsa* g, const uint64_t* sp, const uint6
 }
 
 /* ------------------------------------------------------------------------------------------
+   countKMers -- src/algorithms.cpp:327-421 (KMerSearchState, KMerCounter, processSubtree)
+   ------------------------------------------------------------------------------------------ */
+
+typedef struct { uint64_t sp, ep, k; } kmer_state;
+
+/* processSubtree (algorithms.cpp:364-385) with the KMerCounter / KMerSeedCollector handlers: report
+   states at depth `depth`, expand shallower ones with LF_fast (bases) or LF_all (bases + N). */
+static uint64_t process_subtree(const oracle_gcsa* g, kmer_state start, uint64_t depth, int include_Ns,
+                                kmer_state** collect, uint64_t* collected, uint64_t* collect_cap)
+{
+  uint64_t count = 0, size = 0, cap = 64;
+  kmer_state* stack = (kmer_state*)malloc(cap * sizeof(kmer_state));
+  stack[size++] = start;
+  uint64_t pred[2 * ORACLE_SIGMA];
+  uint64_t limit = (include_Ns ? g->sigma : g->fast_chars + 2);
+  while(size > 0)
+  {
+    kmer_state curr = stack[--size];
+    if(range_empty(curr.sp, curr.ep)) { continue; }
+    if(curr.k == depth)
+    {
+      count++;
+      if(collect != NULL)
+      {
+        if(*collected == *collect_cap) { *collect_cap = (*collect_cap ? *collect_cap * 2 : 64); *collect = (kmer_state*)realloc(*collect, *collect_cap * sizeof(kmer_state)); }
+        (*collect)[(*collected)++] = curr;
+      }
+    }
+    if(curr.k < depth)
+    {
+      if(include_Ns) { oracle_lf_all(g, curr.sp, curr.ep, pred); } else { oracle_lf_fast(g, curr.sp, curr.ep, pred); }
+      for(uint64_t comp = 1; comp + 1 < limit; comp++)
+      {
+        if(size == cap) { cap *= 2; stack = (kmer_state*)realloc(stack, cap * sizeof(kmer_state)); }
+        kmer_state next = { pred[2 * comp], pred[2 * comp + 1], curr.k + 1 };
+        stack[size++] = next;
+      }
+    }
+  }
+  free(stack);
+  return count;
+}
+
+/* countKMers (algorithms.cpp:387-421): seeds of length min(k, 5) on one thread, then OpenMP over seeds. */
+uint64_t oracle_count_kmers(const oracle_gcsa* g, uint64_t k, int include_Ns, int threads)
+{
+  if(k == 0) { return 1; }
+  if(threads < 1) { threads = 1; }
+  kmer_state* seeds = NULL; uint64_t n_seeds = 0, cap = 0;
+  kmer_state root = { 0, g->path_nodes - 1, 0 };
+  process_subtree(g, root, (k < 5 ? k : 5), include_Ns, &seeds, &n_seeds, &cap);
+  uint64_t result = 0;
+  #pragma omp parallel for schedule(dynamic, 1) num_threads(threads) reduction(+:result)
+  for(uint64_t i = 0; i < n_seeds; i++)
+  {
+    result += process_subtree(g, seeds[i], k, include_Ns, NULL, NULL, NULL);
+  }
+  free(seeds);
+  return result;
+}
+
+/* ------------------------------------------------------------------------------------------
    LCPArray -- include/gcsa/lcp.h:137-178, src/lcp.cpp:152-200 (tree arithmetic), 276-519
    ------------------------------------------------------------------------------------------ */
 

@@ -126,6 +126,8 @@ double oracle_count_batch(const oracle_gcsa* g, const uint64_t* sp, const uint64
 double oracle_locate_batch(const oracle_gcsa* g, const uint64_t* sp, const uint64_t* ep, uint64_t n,
                            uint64_t* out_offsets, uint64_t** values, int threads);
 int    oracle_max_threads(void);
+/* countKMers(index, k), src/algorithms.cpp:387-421 */
+uint64_t oracle_count_kmers(const oracle_gcsa* g, uint64_t k, int include_Ns, int threads);
 
 /* LCP queries */
 void     oracle_lcp_parent(const oracle_lcp* l, uint64_t sp, uint64_t ep, oracle_stnode* out);

@@ -98,6 +98,7 @@ def lib():
     L.oracle_locate_batch.restype = C.c_double
     L.oracle_locate_batch.argtypes = [vp, vp, vp, u64, vp, C.POINTER(u64p), C.c_int]
     L.oracle_max_threads.restype = C.c_int
+    L.oracle_count_kmers.restype = u64; L.oracle_count_kmers.argtypes = [vp, u64, C.c_int, C.c_int]
     L.oracle_lcp_parent.argtypes = [vp, u64, u64, C.POINTER(STNode)]
     L.oracle_lcp_depth.restype = u64; L.oracle_lcp_depth.argtypes = [vp, u64, u64]
     for name in ("psv", "psev", "nsv", "nsev"):
@@ -244,6 +245,10 @@ class OracleGCSA:
         else:
             n = lib().oracle_locate_node(self._h, int(rng_or_node), C.byref(p))
         return self._take(n, p)
+
+    def count_kmers(self, k, include_Ns=False, threads=1):
+        """countKMers(index, k), src/algorithms.cpp:387-421."""
+        return lib().oracle_count_kmers(self._h, int(k), int(bool(include_Ns)), int(threads))
 
     # ---- batch drivers (timed CPU baseline) ----
     def find_batch(self, chars, offsets, threads=1, stats=False):

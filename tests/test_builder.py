@@ -128,3 +128,23 @@ def test_kmers_binary_file_layout(tmp_path):
     assert raw[0] == 0 and raw[1] == kmers.key.size and raw[2] == 8          # GraphFileHeader, files.h:40-52
     assert raw.size == 3 + 3 * kmers.key.size
     assert (raw[3::3] == kmers.key).all() and (raw[4::3] == kmers.from_).all() and (raw[5::3] == kmers.to).all()
+
+
+def test_config1_count_kmers_cpu_plumbing():
+    """BASELINE.json configs[0]: countKMers (src/algorithms.cpp:387-421) on the 10 kbp linear path;
+    the answer is the number of distinct k-mers of the path."""
+    seq = synth.random_sequence(10000, seed=1)
+    flat, _, _ = build_index(synth.linear_graph(seq, node_len=32), 16, 1)
+    index = orc.OracleGCSA(flat)
+    for k in (1, 4, 8, 16, 32):
+        windows = np.lib.stride_tricks.sliding_window_view(seq, k)
+        assert index.count_kmers(k, threads=4) == len({bytes(w) for w in windows})
+    assert index.count_kmers(0) == 1
+    # with N: a path containing Ns has k-mers that only LF_all follows
+    seq2 = seq.copy(); seq2[100:103] = 5
+    flat2, _, _ = build_index(synth.linear_graph(seq2, node_len=32), 16, 1)
+    index2 = orc.OracleGCSA(flat2)
+    windows = np.lib.stride_tricks.sliding_window_view(seq2, 8)
+    all_kmers = {bytes(w) for w in windows}
+    assert index2.count_kmers(8, include_Ns=True) == len(all_kmers)
+    assert index2.count_kmers(8, include_Ns=False) == len({w for w in all_kmers if 5 not in w})

@@ -220,3 +220,28 @@ def test_device_pointer_entry_point_and_empty_batches():
     offs, vals = gpu.locate_batch([], [])
     assert list(offs) == [0] and vals.size == 0
     assert gpu.find("") == (0, flat.path_nodes - 1)
+
+
+def test_count_kmers_frontier_expansion():
+    """countKMers on the device (breadth-first) == the reference's depth-first count (oracle), and the
+    final frontier is find() of every k-mer in lexicographic order."""
+    seq = synth.random_sequence(10000, seed=1)
+    seq[500:503] = 5                                                    # a few Ns
+    flat, _, _ = build_index(synth.linear_graph(seq, node_len=32), 16, 1)
+    gpu, ora = both(flat)
+    for k in (0, 1, 2, 5, 8, 16, 32):
+        for with_n in (False, True):
+            assert gpu.count_kmers(k, include_Ns=with_n) == ora.count_kmers(k, include_Ns=with_n, threads=4), (k, with_n)
+    n, sp, ep = gpu.count_kmers(6, return_ranges=True)
+    kmers = sorted({bytes(w) for w in np.lib.stride_tricks.sliding_window_view(seq, 6) if 5 not in w})
+    assert n == len(kmers)
+    chars, offsets = orc.pack_patterns([bytes(synth.COMP2CHAR[np.frombuffer(k, dtype=np.uint8)]) for k in kmers])
+    fsp, fep = gpu.find_batch(chars, offsets)
+    assert (fsp == sp).all() and (fep == ep).all()
+    # a graph with bubbles
+    seq = synth.random_sequence(100_000, seed=8)
+    graph, _, _ = synth.snp_graph(seq, seed=8, snp_rate=0.02)
+    flat, _, _ = build_index(graph, 16, 2)
+    gpu, ora = both(flat, two_step=True)
+    for k in (3, 9, 12, 20):
+        assert gpu.count_kmers(k) == ora.count_kmers(k, threads=8)
