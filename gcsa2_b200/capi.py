@@ -77,7 +77,7 @@ SYMBOLS = [
     "gcsa_b200_locate_host", "gcsa_b200_locate_raw_host", "gcsa_b200_locate_batch", "gcsa_b200_locate_max_host", "gcsa_b200_free", "gcsa_b200_count_kmers",
     "gcsa_b200_lcp_create", "gcsa_b200_lcp_destroy",
     "gcsa_b200_parent_batch", "gcsa_b200_parent_host", "gcsa_b200_depth_batch", "gcsa_b200_depth_host",
-    "gcsa_b200_lcp_sv_host", "gcsa_b200_lcp_rmq_host",
+    "gcsa_b200_lcp_sv_host", "gcsa_b200_lcp_rmq_host", "gcsa_b200_mem_batch", "gcsa_b200_mem_host",
     "gcsa_b200_build_from_kmers", "gcsa_b200_built_free",
     "gcsa_b200_enumerate_kmers", "gcsa_b200_kmers_free", "gcsa_b200_default_char2comp",
 ]
@@ -133,6 +133,8 @@ def lib():
     L.gcsa_b200_depth_host.argtypes = [vp, vp, vp, u64, vp]
     L.gcsa_b200_lcp_sv_host.argtypes = [vp, i32, vp, u64, vp, vp]
     L.gcsa_b200_lcp_rmq_host.argtypes = [vp, vp, vp, u64, vp, vp]
+    L.gcsa_b200_mem_batch.argtypes = [vp, vp, vp, vp, u64, vp, vp, u64, C.POINTER(u64), vp]
+    L.gcsa_b200_mem_host.argtypes = [vp, vp, vp, vp, u64, vp, C.POINTER(vp)]
     L.gcsa_b200_build_from_kmers.argtypes = [vp, vp, vp, u64, i32, i32, u64, C.POINTER(Built)]
     L.gcsa_b200_built_free.argtypes = [C.POINTER(Built)]; L.gcsa_b200_built_free.restype = None
     L.gcsa_b200_enumerate_kmers.argtypes = [C.POINTER(Graph), i32, C.POINTER(Kmers)]

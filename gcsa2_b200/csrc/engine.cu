@@ -1064,6 +1064,86 @@ lcp_rmq_kernel(const LcpView l, const u64* __restrict__ sp, const u64* __restric
 }
 
 //------------------------------------------------------------------------------
+// Kernel: MEM-style scan (LF + parent), BASELINE.json configs[4]
+//------------------------------------------------------------------------------
+
+/*
+  The driver loop over GCSA::LF (gcsa.h:155-162) and LCPArray::parent (lcp.cpp:276-301): extend the
+  match to the left while possible; when it cannot be extended, report it (if it grew since the last
+  report) and shorten it from the right by moving to the suffix-tree parent.  One pattern per lane;
+  patterns of very different lengths share a warp, so finished lanes are refilled from the warp's
+  slice exactly as in find_kernel.  WRITE = false counts the matches, WRITE = true stores them at
+  the offsets computed from the counts.
+*/
+template<bool WRITE>
+__global__ void __launch_bounds__(256)
+mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const u64* __restrict__ offsets, u64 char_base,
+           u64 n, u64* __restrict__ counts, const u64* __restrict__ out_offsets, u64* __restrict__ matches)
+{
+  __shared__ u8 c2c[256];
+  for(int i = threadIdx.x; i < 256; i += blockDim.x) { c2c[i] = v.char2comp[i]; }
+  __syncthreads();
+
+  const u32 lane = threadIdx.x & 31;
+  const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+  const u64 per = (n + n_warps - 1) / n_warps;
+  u64 next = warp * per;
+  const u64 slice_end = (next + per < n ? next + per : n);
+  if(next >= n || v.path_nodes == 0) { return; }
+
+  u64 q = 0, sp = 0, ep = 0, depth = 0, pos = 0, begin = 0, emitted = 0, out_at = 0;
+  bool live = false, extended = false;
+
+  while(true)
+  {
+    u32 dead = __ballot_sync(0xFFFFFFFFu, !live);
+    if(dead)
+    {
+      u32 my = __popc(dead & ((1u << lane) - 1));
+      if(!live)
+      {
+        u64 cand = next + my;
+        if(cand < slice_end)
+        {
+          q = cand; live = true;
+          begin = offsets[q] - char_base; pos = offsets[q + 1] - char_base;
+          sp = 0; ep = v.path_nodes - 1; depth = 0; extended = false; emitted = 0;
+          if(WRITE) { out_at = out_offsets[q]; }
+        }
+      }
+      next += __popc(dead);
+      if(next > slice_end) { next = slice_end; }
+    }
+    if(__ballot_sync(0xFFFFFFFFu, live) == 0) { break; }
+    if(!live) { continue; }
+
+    if(pos == begin)
+    {
+      if(depth > 0 && extended)
+      {
+        if(WRITE) { u64* m = matches + 4 * (out_at + emitted); m[0] = 0; m[1] = depth; m[2] = sp; m[3] = ep; }
+        emitted++;
+      }
+      if(!WRITE) { counts[q] = emitted; }
+      live = false;
+      continue;
+    }
+    u64 nsp, nep;
+    lf_range(v, sp, ep, c2c[chars[pos - 1]], nsp, nep);
+    if(!range_empty(nsp, nep)) { sp = nsp; ep = nep; depth++; pos--; extended = true; continue; }
+    if(depth == 0) { pos--; continue; }
+    if(extended)
+    {
+      if(WRITE) { u64* m = matches + 4 * (out_at + emitted); m[0] = pos - begin; m[1] = depth; m[2] = sp; m[3] = ep; }
+      emitted++; extended = false;
+    }
+    gcsa_b200_stnode node = lcp_parent(l, sp, ep);
+    sp = node.sp; ep = node.ep; depth = node.node_lcp;
+  }
+}
+
+//------------------------------------------------------------------------------
 // Host side: handles
 //------------------------------------------------------------------------------
 
@@ -2212,4 +2292,65 @@ done:
   #undef KM_TRY
   if(rc == 0 && e != cudaSuccess) { rc = fail(GCSA_B200_ERR_CUDA, std::string("count_kmers: ") + cudaGetErrorString(e)); }
   return rc;
+}
+
+//------------------------------------------------------------------------------
+// MEM-style scan
+//------------------------------------------------------------------------------
+
+int gcsa_b200_mem_batch(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, const uint8_t* d_chars, const uint64_t* d_offsets,
+                        uint64_t n, uint64_t* d_out_offsets, uint64_t* d_matches, uint64_t capacity, uint64_t* needed, void* stream)
+{
+  if(index == nullptr || lcp == nullptr || d_out_offsets == nullptr) { return fail(GCSA_B200_ERR_INVALID, "mem_batch: null argument"); }
+  if(index->device != lcp->device) { return fail(GCSA_B200_ERR_INVALID, "mem_batch: index and LCP array live on different devices"); }
+  if(index->header.path_nodes != lcp->view.size) { return fail(GCSA_B200_ERR_INVALID, "mem_batch: index and LCP array have different sizes"); }
+  DeviceGuard guard(index->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if(needed) { *needed = 0; }
+  CUDA_TRY(cudaMemsetAsync(d_out_offsets, 0, (n + 1) * sizeof(u64), st));
+  if(n == 0 || index->header.path_nodes == 0) { return 0; }
+  u64* counts = nullptr;
+  CUDA_TRY(cudaMallocAsync(&counts, (n + 1) * sizeof(u64), st));
+  CUDA_TRY(cudaMemsetAsync(counts, 0, (n + 1) * sizeof(u64), st));
+  int grid = gridFor(n, index->sm_count, 4);
+  mem_kernel<false><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, nullptr);
+  int rc = scanExclusive(counts, (u64*)d_out_offsets, n + 1, st);
+  cudaFreeAsync(counts, st);
+  if(rc) { return rc; }
+  u64 total = 0;
+  CUDA_TRY(cudaMemcpyAsync(&total, (u64*)d_out_offsets + n, sizeof(u64), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if(needed) { *needed = total; }
+  if(d_matches == nullptr || capacity < total) { return fail(GCSA_B200_ERR_CAPACITY, "mem_batch: output capacity too small"); }
+  mem_kernel<true><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, nullptr, (const u64*)d_out_offsets, (u64*)d_matches);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int gcsa_b200_mem_host(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, const uint8_t* chars, const uint64_t* offsets,
+                       uint64_t n, uint64_t* out_offsets, uint64_t** matches)
+{
+  if(out_offsets == nullptr || matches == nullptr || (n > 0 && (chars == nullptr || offsets == nullptr))) { return fail(GCSA_B200_ERR_INVALID, "mem_host: null argument"); }
+  *matches = nullptr;
+  HOST_PROLOGUE("mem_host", index);
+  u64 total_chars = (n ? offsets[n] : 0);
+  u8* d_chars = sc.in(chars, total_chars + 1 > 1 ? total_chars : 1);
+  u64* d_off = sc.in((const u64*)offsets, n + 1);
+  u64* d_out = sc.alloc<u64>(n + 1);
+  u64 needed = 0;
+  int rc = gcsa_b200_mem_batch(index, lcp, d_chars, d_off, n, d_out, nullptr, 0, &needed, sc.stream);
+  if(rc == GCSA_B200_ERR_CAPACITY || (rc == 0 && needed == 0))
+  {
+    rc = 0;
+    u64* vals = (u64*)std::malloc(std::max<u64>(4 * needed, 1) * sizeof(u64));
+    if(needed > 0)
+    {
+      u64* d_vals = sc.alloc<u64>(4 * needed);
+      rc = gcsa_b200_mem_batch(index, lcp, d_chars, d_off, n, d_out, d_vals, needed, &needed, sc.stream);
+      sc.out(vals, d_vals, 4 * needed);
+    }
+    sc.out((u64*)out_offsets, d_out, n + 1);
+    *matches = (uint64_t*)vals;
+  }
+  HOST_EPILOGUE("mem_host", rc);
 }

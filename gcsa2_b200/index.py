@@ -333,3 +333,30 @@ class LCPArray:
         a = np.zeros(max(n, 1), dtype=np.uint64); b = np.zeros(max(n, 1), dtype=np.uint64)
         capi.check(capi.lib().gcsa_b200_lcp_rmq_host(self._h, sp.ctypes.data, ep.ctypes.data, n, a.ctypes.data, b.ctypes.data))
         return a[:n], b[:n]
+
+
+def mem_batch(index, lcp, patterns, offsets=None):
+    """MEM-style scan (config 5) of every pattern through the engine:
+    -> (out_offsets uint64[n + 1], matches uint64[k, 4] = (start, length, sp, ep))."""
+    if offsets is None:
+        chars, offsets = pack_patterns(patterns)
+    else:
+        chars = np.ascontiguousarray(patterns, dtype=np.uint8); offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    p = C.c_void_p()
+    capi.check(capi.lib().gcsa_b200_mem_host(index.handle, lcp.handle, chars.ctypes.data, offsets.ctypes.data, n,
+                                             offs.ctypes.data, C.byref(p)))
+    total = int(offs[n])
+    if not p.value:
+        return offs, np.zeros((0, 4), dtype=np.uint64)
+    vals = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(max(4 * total, 1),))[:4 * total].copy().reshape(-1, 4)
+    capi.lib().gcsa_b200_free(p)
+    return offs, vals
+
+
+def mem_device(index, lcp, d_chars, d_offsets, n, d_out_offsets, d_matches, capacity, stream=0):
+    needed = C.c_uint64()
+    capi.check(capi.lib().gcsa_b200_mem_batch(index.handle, lcp.handle, capi.ptr(d_chars), capi.ptr(d_offsets), int(n),
+                                              capi.ptr(d_out_offsets), capi.ptr(d_matches), int(capacity), C.byref(needed), stream or None))
+    return int(needed.value)

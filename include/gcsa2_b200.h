@@ -211,6 +211,18 @@ int gcsa_b200_lcp_sv_host(const gcsa_b200_lcp* lcp, int which, const uint64_t* p
 int gcsa_b200_lcp_rmq_host(const gcsa_b200_lcp* lcp, const uint64_t* sp, const uint64_t* ep, uint64_t n,
                            uint64_t* out_pos, uint64_t* out_val);
 
+/* MEM-style scan (BASELINE.json configs[4]): the driver loop over GCSA::LF (gcsa.h:155-162) and
+   LCPArray::parent (src/lcp.cpp:276-301) in the scheme cited at paper/paper.tex:340, 606 -- extend the
+   match to the left while possible, else report it and move to the suffix-tree parent.  The reference
+   ships the two building blocks but no driver; this is the engine's.  Matches of pattern i are the
+   4-tuples (start, length, sp, ep) at matches[4 * out_offsets[i] .. 4 * out_offsets[i + 1]).
+   *_batch: capacity in matches; GCSA_B200_ERR_CAPACITY + *needed if too small (one stream sync). */
+int gcsa_b200_mem_batch(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, const uint8_t* d_chars,
+                        const uint64_t* d_offsets, uint64_t n, uint64_t* d_out_offsets, uint64_t* d_matches,
+                        uint64_t capacity, uint64_t* needed, void* stream);
+int gcsa_b200_mem_host(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, const uint8_t* chars,
+                       const uint64_t* offsets, uint64_t n, uint64_t* out_offsets, uint64_t** matches);
+
 /* ---------------------------------------------------------------------------------------------
    Host-side construction (CPU; gcsa2_b200/csrc/builder.cpp).  Replaces, for in-memory inputs,
    GCSA::GCSA(InputGraph&, ConstructionParameters) (src/gcsa.cpp:447-724) and

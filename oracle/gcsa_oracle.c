@@ -896,3 +896,69 @@ double oracle_parent_batch(const oracle_lcp* l, const uint64_t* sp, const uint64
   for(uint64_t i = 0; i < n; i++) { oracle_lcp_parent(l, sp[i], ep[i], &out[i]); }
   return omp_get_wtime() - start;
 }
+
+/* ------------------------------------------------------------------------------------------
+   MEM-style scan (BASELINE.json configs[4]).  The reference has no such driver: it supplies the
+   building blocks, LF() and LCPArray::parent(), for the scheme of Ohlebusch et al. cited at
+   paper/paper.tex:340, 606.  The loop below is this repository's definition of it; the device
+   kernel mirrors it step by step.
+
+     i = m; range = root; depth = 0; extended = false
+     while i > 0:
+       next = LF(range, comp(P[i-1]))                          (gcsa.h:155-162)
+       if next is not empty:  range = next; depth++; i--; extended = true; continue
+       if depth == 0:         i--; continue                    (character that occurs nowhere)
+       if extended:           emit (i, depth, range); extended = false
+       node = parent(range); range = node.range(); depth = node.lcp()      (lcp.cpp:276-301)
+     if depth > 0 and extended: emit (0, depth, range)
+
+   A match (start, length, sp, ep) says P[start, start + length) occurs with path range [sp, ep]
+   and cannot be extended to the left.
+   ------------------------------------------------------------------------------------------ */
+
+static uint64_t mem_scan(const oracle_gcsa* g, const oracle_lcp* l, const uint8_t* pattern, uint64_t len, uint64_t* out)
+{
+  uint64_t emitted = 0;
+  uint64_t i = len, sp = 0, ep = g->path_nodes - 1, depth = 0;
+  int extended = 0;
+  if(g->path_nodes == 0) { return 0; }
+  while(i > 0)
+  {
+    uint64_t nsp, nep;
+    oracle_lf_range(g, sp, ep, g->char2comp[pattern[i - 1]], &nsp, &nep);
+    if(!range_empty(nsp, nep)) { sp = nsp; ep = nep; depth++; i--; extended = 1; continue; }
+    if(depth == 0) { i--; continue; }
+    if(extended)
+    {
+      if(out) { out[4 * emitted] = i; out[4 * emitted + 1] = depth; out[4 * emitted + 2] = sp; out[4 * emitted + 3] = ep; }
+      emitted++; extended = 0;
+    }
+    oracle_stnode node;
+    oracle_lcp_parent(l, sp, ep, &node);
+    sp = node.sp; ep = node.ep; depth = node.node_lcp;
+  }
+  if(depth > 0 && extended)
+  {
+    if(out) { out[4 * emitted] = 0; out[4 * emitted + 1] = depth; out[4 * emitted + 2] = sp; out[4 * emitted + 3] = ep; }
+    emitted++;
+  }
+  return emitted;
+}
+
+double oracle_mem_batch(const oracle_gcsa* g, const oracle_lcp* l, const uint8_t* chars, const uint64_t* offsets,
+                        uint64_t n, uint64_t* out_offsets, uint64_t** matches, int threads)
+{
+  if(threads < 1) { threads = 1; }
+  double start = omp_get_wtime();
+  uint64_t* cnt = (uint64_t*)calloc(n + 1, sizeof(uint64_t));
+  #pragma omp parallel for schedule(dynamic, 1024) num_threads(threads)
+  for(uint64_t i = 0; i < n; i++) { cnt[i] = mem_scan(g, l, chars + offsets[i], offsets[i + 1] - offsets[i], NULL); }
+  out_offsets[0] = 0;
+  for(uint64_t i = 0; i < n; i++) { out_offsets[i + 1] = out_offsets[i] + cnt[i]; }
+  uint64_t* vals = (uint64_t*)malloc((4 * out_offsets[n] + 1) * sizeof(uint64_t));
+  #pragma omp parallel for schedule(dynamic, 1024) num_threads(threads)
+  for(uint64_t i = 0; i < n; i++) { mem_scan(g, l, chars + offsets[i], offsets[i + 1] - offsets[i], vals + 4 * out_offsets[i]); }
+  free(cnt);
+  *matches = vals;
+  return omp_get_wtime() - start;
+}

@@ -140,6 +140,11 @@ void     oracle_lcp_rmq(const oracle_lcp* l, uint64_t sp, uint64_t ep, uint64_t*
 double   oracle_parent_batch(const oracle_lcp* l, const uint64_t* sp, const uint64_t* ep, uint64_t n,
                              oracle_stnode* out, int threads);
 
+/* MEM-style scan (config 5; this repository's driver over LF + parent, defined in gcsa_oracle.c):
+   matches of pattern i are the 4-tuples (start, length, sp, ep) at matches[4 * out_offsets[i] ...). */
+double   oracle_mem_batch(const oracle_gcsa* g, const oracle_lcp* l, const uint8_t* chars, const uint64_t* offsets,
+                          uint64_t n, uint64_t* out_offsets, uint64_t** matches, int threads);
+
 /* std::mt19937_64 and Thomas Wang's hash, exposed for known-answer tests */
 typedef struct { uint64_t mt[312]; int idx; } oracle_mt64;
 void     oracle_mt64_seed(oracle_mt64* r, uint64_t seed);

@@ -106,6 +106,8 @@ def lib():
     L.oracle_lcp_rmq.argtypes = [vp, u64, u64, u64p, u64p]
     L.oracle_parent_batch.restype = C.c_double
     L.oracle_parent_batch.argtypes = [vp, vp, vp, u64, vp, C.c_int]
+    L.oracle_mem_batch.restype = C.c_double
+    L.oracle_mem_batch.argtypes = [vp, vp, vp, vp, u64, vp, C.POINTER(u64p), C.c_int]
     L.oracle_mt64_seed.argtypes = [C.POINTER(_MT64), u64]
     L.oracle_mt64_next.restype = u64; L.oracle_mt64_next.argtypes = [C.POINTER(_MT64)]
     L.oracle_wang_hash_64.restype = u64; L.oracle_wang_hash_64.argtypes = [u64]
@@ -320,6 +322,19 @@ class OracleLCP:
         n = len(sp); out = np.zeros((max(1, n), 5), dtype=np.uint64)
         secs = lib().oracle_parent_batch(self._h, _ptr(sp), _ptr(ep), n, _ptr(out), threads)
         return out[:n], secs
+
+
+def mem_batch(index, lcp, chars, offsets, threads=1):
+    """MEM-style scan of every pattern: (out_offsets, matches[k, 4] = (start, length, sp, ep), seconds)."""
+    chars = np.ascontiguousarray(chars, dtype=np.uint8); offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    p = C.POINTER(C.c_uint64)()
+    secs = lib().oracle_mem_batch(index._h, lcp._h, _ptr(chars), _ptr(offsets), n, _ptr(offs), C.byref(p), threads)
+    total = int(offs[n])
+    vals = np.ctypeslib.as_array(p, shape=(max(1, 4 * total),))[:4 * total].copy().reshape(-1, 4)
+    lib().oracle_free(p)
+    return offs, vals, secs
 
 
 def mt19937_64(seed, n):

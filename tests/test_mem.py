@@ -1,0 +1,61 @@
+"""The MEM-style scan of config 5 (LF + parent driver): properties of the CPU definition, and
+bit-exact agreement of the device kernel with it."""
+import random
+
+import numpy as np
+import pytest
+
+from gcsa2_b200 import synth
+from gcsa2_b200.builder import build_index
+from oracle import oracle as orc
+
+
+def make(n_patterns, L=50_000, seed=1):
+    seq = synth.random_sequence(L, seed=seed)
+    graph, sites, alt = synth.snp_graph(seq, seed=seed, snp_rate=0.01)
+    flat, flcp, _ = build_index(graph, 16, 3)
+    chars, offsets = synth.mixed_length_patterns(seq, sites, alt, n_patterns, 16, 256, seed=seed + 7, error_rate=0.01)
+    return flat, flcp, chars, offsets
+
+
+def test_mem_scan_definition_properties():
+    flat, flcp, chars, offsets = make(1500)
+    index, lcp = orc.OracleGCSA(flat), orc.OracleLCP(flcp)
+    offs, vals, _ = orc.mem_batch(index, lcp, chars, offsets, threads=4)
+    assert int(offs[-1]) == len(vals) and (np.diff(offs.astype(np.int64)) >= 1).all()
+    for i in random.Random(1).sample(range(1500), 150):
+        P = bytes(chars[int(offsets[i]):int(offsets[i + 1])])
+        ms = vals[int(offs[i]):int(offs[i + 1])]
+        starts = [int(m[0]) for m in ms]
+        assert starts == sorted(starts, reverse=True)                     # reported right to left
+        for st, ln, sp, ep in ((int(a), int(b), int(c), int(d)) for a, b, c, d in ms):
+            assert ln >= 1 and st + ln <= len(P)
+            assert index.find(P[st:st + ln]) == (sp, ep)                  # it is find() of that substring
+            if st > 0:                                                    # and it is left-maximal
+                r = index.find(P[st - 1:st + ln])
+                assert ((r[0] + 1) % 2**64) > ((r[1] + 1) % 2**64)
+    # an exact substring of the graph is one match covering the whole pattern
+    seq = synth.random_sequence(50_000, seed=1)
+    P = bytes(synth.COMP2CHAR[seq[1000:1100]])
+    graph, _, _ = synth.snp_graph(seq, seed=1, snp_rate=0.01)
+    c, o = orc.pack_patterns([P, b"", b"NNNN"])
+    offs, vals, _ = orc.mem_batch(index, lcp, c, o)
+    assert list(offs) == [0, 1, 1, 1] and list(vals[0][:2]) == [0, 100]
+
+
+@pytest.mark.gpu
+def test_mem_scan_device_matches_definition():
+    from gcsa2_b200 import GCSA, LCPArray, mem_batch
+    flat, flcp, chars, offsets = make(30_000, L=200_000, seed=3)
+    index, lcp = orc.OracleGCSA(flat), orc.OracleLCP(flcp)
+    ooffs, ovals, _ = orc.mem_batch(index, lcp, chars, offsets, threads=8)
+    for two_step in (False, True):
+        gpu, glcp = GCSA(flat, kmer_table_k=6, two_step=two_step), LCPArray(flcp)
+        offs, vals = mem_batch(gpu, glcp, chars, offsets)
+        assert (offs == ooffs).all() and vals.shape == ovals.shape and (vals == ovals).all()
+    c, o = orc.pack_patterns([b"", b"ACGT", b"NNNN", b"$", bytes(chars[:300])])
+    offs, vals = mem_batch(gpu, glcp, c, o)
+    eoffs, evals, _ = orc.mem_batch(index, lcp, c, o)
+    assert (offs == eoffs).all() and (vals == evals).all()
+    offs, vals = mem_batch(gpu, glcp, [])
+    assert list(offs) == [0] and vals.shape == (0, 4)
