@@ -127,6 +127,34 @@ def main():
     secs = time.time() - t0
     report("depth (of the parents)", "ranges/s", n, ms, md / secs, md, (odep == dep[:md]).all(), {"cpu_note": "single thread through ctypes"})
 
+    # ---- MEM-style scan (config 5): mixed lengths 16..256, 1 % substitutions ----
+    from gcsa2_b200 import mem_device
+    nm = min(n, 4_000_000)
+    mchars, moffsets = synth.mixed_length_patterns(seq, sites, alt, nm, 16, 256, seed=900, error_rate=0.01)
+    d_mchars = torch.from_numpy(mchars).cuda(); d_moff = torch.from_numpy(moffsets.view(np.int64)).cuda()
+    d_moffs_out = torch.empty(nm + 1, dtype=torch.int64, device="cuda")
+    cap = 16 * nm
+    d_matches = torch.empty((cap, 4), dtype=torch.int64, device="cuda")
+    got = [0]
+    def do_mem():
+        got[0] = mem_device(index, lcp, d_mchars, d_moff, nm, d_moffs_out, d_matches, cap, stream.cuda_stream)
+    ms = timed(do_mem, steps=3)
+    moffs = d_moffs_out.cpu().numpy().view(np.uint64); mvals = d_matches[:got[0]].cpu().numpy().view(np.uint64)
+    mm = min(nm, 400_000)
+    eoffs, evals, secs = orc.mem_batch(ora, olcp, mchars[:int(moffsets[mm])], moffsets[:mm + 1], threads=threads)
+    k = int(eoffs[mm])
+    report("MEM-style scan (LF + parent), lengths 16..256", "patterns/s", nm, ms, mm / secs, mm,
+           (moffs[:mm + 1] == eoffs).all() and (mvals[:k] == evals).all(),
+           {"matches": got[0], "pattern_bytes": int(moffsets[-1])})
+
+    # ---- countKMers ----
+    for k in (12, 16):
+        t0 = time.time(); g = index.count_kmers(k); torch.cuda.synchronize(); gs = time.time() - t0
+        t0 = time.time(); c = ora.count_kmers(k, threads=threads); cs = time.time() - t0
+        row = {"op": "countKMers(k=%d)" % k, "unit": "kmers/s", "gpu_value": g / gs, "gpu_ms_per_step": gs * 1000.0,
+               "cpu_value": c / cs, "cpu_cores": threads, "cpu_sample": "whole index", "speedup": cs / gs, "parity_on_sample": bool(g == c), "kmers": g}
+        results.append(row); print(json.dumps(row), flush=True)
+
     if args.out:
         with open(args.out, "w") as f:
             json.dump(results, f, indent=1)
