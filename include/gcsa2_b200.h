@@ -186,7 +186,8 @@ void gcsa_b200_free(void* p);
 
 /* countKMers(index, k, parameters), src/algorithms.cpp:387-421 (declared include/gcsa/algorithms.h:80-89):
    the number of distinct k-mers over the bases (include_Ns != 0: bases and N).  If ranges is not NULL it
-   receives the path ranges of those k-mers in lexicographic order, malloc'ed as sp[0..count) followed by
+   receives the path ranges of those k-mers (ordered by the reversed k-mer: the trie grows leftwards),
+   malloc'ed as sp[0..count) followed by
    ep[0..count) (release with gcsa_b200_free). */
 int gcsa_b200_count_kmers(const gcsa_b200_index* index, uint64_t k, int include_Ns, uint64_t* result, uint64_t** ranges);
 
