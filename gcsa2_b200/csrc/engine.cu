@@ -301,6 +301,23 @@ __device__ __forceinline__ bool bwt_bit(const DevView& v, u64 i, u32 c)
 // Kernels: find
 //------------------------------------------------------------------------------
 
+// Pattern bytes are read through an 8-byte window (one aligned streaming load per 8 characters,
+// evict-first: the pattern stream must not push index lines out of the L2).
+struct CharWindow
+{
+  u64 word; u64 index;
+  __device__ __forceinline__ CharWindow() : word(0), index(~0ull) {}
+  __device__ __forceinline__ u32 get(const u8* chars, u64 pos)
+  {
+    u64 addr = (u64)(chars + pos);
+    u64 wi = addr >> 3;
+    if(wi != index) { word = __ldcs((const unsigned long long*)(wi << 3)); index = wi; }
+    return (u32)((word >> ((addr & 7) * 8)) & 0xFF);
+  }
+};
+
+
+
 struct FindStatsDev { u64 found, total_length, lf_steps, sector_probes, table_hits; };
 
 /*
@@ -329,6 +346,7 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
 
   u64 q = ~0ull, sp = 0, ep = 0, pos = 0, begin = 0;
   bool live = false;
+  CharWindow win;
   u64 st_found = 0, st_len = 0, st_steps = 0, st_sectors = 0, st_hits = 0;
 
   while(true)
@@ -358,7 +376,7 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
               u64 idx = 0; bool ok = true;
               for(int t = 0; t < v.table_k; t++)
               {
-                u32 c = c2c[chars[e - 1 - t]];
+                u32 c = c2c[win.get(chars, e - 1 - t)];
                 ok = ok && (c >= 1 && c <= 4);
                 idx |= (u64)((c - 1) & 3) << (2 * t);
               }
@@ -375,7 +393,7 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
             }
             if(!used_table)
             {
-              u32 c = c2c[chars[pos]];
+              u32 c = c2c[win.get(chars, pos)];
               sp = v.char_sp[c]; ep = v.char_ep[c];
             }
           }
@@ -390,18 +408,18 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
     {
       if(range_empty(sp, ep) || pos == begin)
       {
-        sp_out[q] = sp; ep_out[q] = ep;
+        __stcs((unsigned long long*)sp_out + q, (unsigned long long)sp); __stcs((unsigned long long*)ep_out + q, (unsigned long long)ep);
         if(STATS && !range_empty(sp, ep)) { st_found++; st_len += ep + 1 - sp; }
         live = false;
       }
       else
       {
-        u32 c = c2c[chars[pos - 1]];
+        u32 c = c2c[win.get(chars, pos - 1)];
         u32 sectors = 0;
         bool done = false;
         if(v.bwt2 != nullptr && pos - begin >= 2 && c >= 1 && c <= 4)
         {
-          u32 c1 = c2c[chars[pos - 2]];
+          u32 c1 = c2c[win.get(chars, pos - 2)];
           if(c1 >= 1 && c1 <= 4 && lf2_range(v, sp, ep, c1, c, sp, ep, STATS ? &sectors : nullptr))
           {
             pos -= 2; done = true;
