@@ -1608,10 +1608,15 @@ static int launchFind(const gcsa_b200_index* index, const u8* d_chars, const u64
   if(n == 0) { return 0; }
   // persistent grid: 8 CTAs of 256 threads per SM (2048 resident threads), slices per warp
   static const int min_blocks = []() { const char* e = std::getenv("GCSA_B200_FIND_MINBLOCKS"); return (e ? std::atoi(e) : 6); }();
-  int grid = gridFor(n, index->sm_count, min_blocks >= 8 ? 8 : 6);
-  if(d_stats) { find_kernel<true, 1><<<grid, 256, 0, stream>>>(index->view, d_chars, d_offsets, char_base, fixed_length, n, d_sp, d_ep, d_stats); }
-  else if(min_blocks >= 8) { find_kernel<false, 8><<<grid, 256, 0, stream>>>(index->view, d_chars, d_offsets, char_base, fixed_length, n, d_sp, d_ep, nullptr); }
-  else { find_kernel<false, 6><<<grid, 256, 0, stream>>>(index->view, d_chars, d_offsets, char_base, fixed_length, n, d_sp, d_ep, nullptr); }
+  int per_sm = (min_blocks >= 8 ? 8 : (min_blocks <= 4 ? 4 : min_blocks));
+  int grid = gridFor(n, index->sm_count, per_sm);
+  #define LAUNCH_FIND(S, B) find_kernel<S, B><<<grid, 256, 0, stream>>>(index->view, d_chars, d_offsets, char_base, fixed_length, n, d_sp, d_ep, d_stats)
+  if(d_stats) { LAUNCH_FIND(true, 1); }
+  else if(per_sm == 8) { LAUNCH_FIND(false, 8); }
+  else if(per_sm == 5) { LAUNCH_FIND(false, 5); }
+  else if(per_sm == 4) { LAUNCH_FIND(false, 4); }
+  else { LAUNCH_FIND(false, 6); }
+  #undef LAUNCH_FIND
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
