@@ -323,7 +323,7 @@ def main():
                     "matches_device_leg": e2e_same},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "find_kernel<false,6>", "peak_source": peak_src,
+                         "traffic": None, "kernel": "find_kernel<false,5>", "peak_source": peak_src,
                          "bytes_per_launch": engine_bytes,
                          "accounting": "64 B per distinct fused-sector probe executed + 8 B per k-mer table entry + |P| + 16 B I/O per query (SURVEY.md 8(d) units)",
                          "lf_steps_per_query": st["lf_steps"] / m, "sector_probes_per_query": st["sector_probes"] / m},

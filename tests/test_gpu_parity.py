@@ -246,3 +246,46 @@ def test_count_kmers_frontier_expansion():
     gpu, ora = both(flat, two_step=True)
     for k in (3, 9, 12, 20):
         assert gpu.count_kmers(k) == ora.count_kmers(k, threads=8)
+
+
+def test_full_size_config2_properties():
+    """BASELINE.json configs[1] at full size: 10 M 32-mers sampled from a 100 Mbp linear reference,
+    order 128.  Size-independent properties: every sampled pattern is found; all engine variants
+    (k-mer table on/off, two-step on/off) give the same 20 M numbers; locate(find(P)) contains the
+    position P was cut from; a 200 k sample equals the oracle bit for bit."""
+    L, n, length = 100_000_000, 10_000_000, 32
+    seq = synth.random_sequence(L, seed=2)
+    graph = synth.linear_graph(seq, node_len=32)
+    flat, _, _ = build_index(graph, 16, 3)
+    assert flat.path_nodes == L + 2 and flat.order == 128
+    chars = np.empty(n * length, dtype=np.uint8)
+    starts = np.empty(n, dtype=np.int64)
+    for i, q0 in enumerate(range(0, n, 1_000_000)):
+        rng = np.random.default_rng(4242 + i)
+        st = rng.integers(0, L - length + 1, size=1_000_000, dtype=np.int64)
+        starts[q0:q0 + 1_000_000] = st
+        chars[q0 * length:(q0 + 1_000_000) * length] = synth.COMP2CHAR[seq[st[:, None] + np.arange(length)[None, :]]].reshape(-1)
+    ref = None
+    for table_k, two_step in ((14, False), (0, False), (12, True)):
+        gpu = GCSA(flat, kmer_table_k=table_k, two_step=two_step)
+        sp, ep = gpu.find_fixed_batch(chars, length)
+        assert not np.any(sp > ep)                                   # everything sampled from the text occurs
+        if ref is None:
+            ref = (sp, ep)
+            m = 1_000_000
+            offs, vals = gpu.locate_batch(sp[:m], ep[:m])
+            want = graph.value[1 + starts[:m]]
+            first = vals[offs[:-1].astype(np.int64)]
+            single = np.diff(offs.astype(np.int64)) == 1
+            assert (first[single] == want[single]).all() and single.mean() > 0.99
+            for i in np.flatnonzero(~single)[:2000]:
+                assert want[i] in vals[int(offs[i]):int(offs[i + 1])]
+            assert (gpu.count_batch(sp[:m], ep[:m]) == np.diff(offs)).all()
+        else:
+            assert (sp == ref[0]).all() and (ep == ref[1]).all()
+        gpu.close()
+    ora = orc.OracleGCSA(flat)
+    k = 200_000
+    offsets = np.arange(k + 1, dtype=np.uint64) * np.uint64(length)
+    osp, oep, _ = ora.find_batch(chars[:k * length], offsets, threads=8)
+    assert (osp == ref[0][:k]).all() and (oep == ref[1][:k]).all()
