@@ -178,6 +178,18 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def recorded_traffic(args, index):
+    """dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture of this
+    very configuration (profiles/traffic_find_cfg2.json); None for any other configuration."""
+    path = os.path.join(ROOT, "profiles", "traffic_find_cfg2.json")
+    default = (args.ref_mbp == 100.0 and args.queries == 10_000_000 and args.pattern_length == 32
+               and index.kmerTableK() == 14 and not index.twoStep())
+    if default and os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    return None
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path (restated in oracle/; the reference itself cannot be
     built here because sdsl-lite is absent), all host threads, a bounded sample per step."""
@@ -323,7 +335,7 @@ def main():
                     "matches_device_leg": e2e_same},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "find_kernel<false,5>", "peak_source": peak_src,
+                         "traffic": recorded_traffic(args, index), "kernel": "find_kernel<false,5>", "peak_source": peak_src,
                          "bytes_per_launch": engine_bytes,
                          "accounting": "64 B per distinct fused-sector probe executed + 8 B per k-mer table entry + |P| + 16 B I/O per query (SURVEY.md 8(d) units)",
                          "lf_steps_per_query": st["lf_steps"] / m, "sector_probes_per_query": st["sector_probes"] / m},
