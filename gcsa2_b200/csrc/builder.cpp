@@ -573,7 +573,11 @@ void enumerate(const gcsa_b200_graph* g, int k, KmerSink& sink)
           u64 key = (label << 16) | ((u64)pmask[v] << 8);
           if(at_sink || f.depth < k)
           {
-            mine.key.push_back(key); mine.from.push_back(g->value[v]); mine.to.push_back(~(u64)0);
+            // A kmer that reached the endmarker is followed by '$' again; the all-'$' kmer of the sink is
+            // followed by '#' (the technical edge sink -> source).  Every kmer needs a successor
+            // (include/gcsa/dbg.h:70-72).
+            u64 succ = (label == 0 ? (u64)1 << 6 : (u64)1 << SINK_COMP);
+            mine.key.push_back(key | succ); mine.from.push_back(g->value[v]); mine.to.push_back(~(u64)0);
           }
           else
           {

@@ -10,10 +10,14 @@
   in the external sdsl-lite fork (vgteam), which is NOT in the reference tree and
   not installed here; it is restated from the mathematical definitions
   (rank1(i) = ones in [0,i), select1(k) = position of the k-th one, k >= 1).
-  PARITY PINNING: pinned at the GCSA API boundary by the paper's Figure 3 worked
-  example (tests/golden/kat1_*.json) and by the verifyIndex predicates
-  (src/algorithms.cpp:101-295); unpinned at the SDSL boundary (no reference tests
-  exist there).
+  PARITY PINNING: pinned against the reference itself.  oracle/_ref/libgcsa2_ref.so is the
+  reference's own, unmodified sources compiled against the SDSL shim of oracle/sdsl_shim/ (the
+  real sdsl-lite fork is unavailable); tests/test_reference.py checks that every function below
+  returns exactly what the reference's own method returns, on indexes the reference's own
+  constructor built and its own verifyIndex() accepted.  Also pinned on the paper's Figure 3
+  worked example (tests/golden/kat1_fig3.json) and the verifyIndex predicates
+  (src/algorithms.cpp:101-295).  What stays unpinned is SDSL itself (not in the tree): rank,
+  select and access have unique mathematical answers, and the shim implements those.
 */
 #ifndef GCSA_ORACLE_H
 #define GCSA_ORACLE_H
