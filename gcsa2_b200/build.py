@@ -9,6 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgcsa2_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include", "gcsa2_b200.h")
+HOST_SOURCES = ["builder.cpp", "gcsa_file.cpp"]      # host-side C++ (g++)
 
 NVCC = os.environ.get("GCSA_B200_NVCC", "nvcc")
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
@@ -25,14 +26,17 @@ def _stale(target, sources):
 
 
 def build(force=False, verbose=False):
-    engine_cu, builder_cpp = os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "builder.cpp")
-    engine_o, builder_o = os.path.join(CSRC, "engine.o"), os.path.join(CSRC, "builder.o")
-    if not force and not _stale(LIB, [engine_cu, builder_cpp, INCLUDE]):
+    engine_cu = os.path.join(CSRC, "engine.cu")
+    host_cpp = [os.path.join(CSRC, name) for name in HOST_SOURCES]
+    engine_o = os.path.join(CSRC, "engine.o")
+    host_o = [src[:-4] + ".o" for src in host_cpp]
+    if not force and not _stale(LIB, [engine_cu, INCLUDE, os.path.join(CSRC, "internal.h")] + host_cpp):
         return LIB
     run = lambda cmd: subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL)
     run([NVCC] + NVCC_FLAGS + ["-c", engine_cu, "-o", engine_o])
-    run([CXX] + CXX_FLAGS + ["-c", builder_cpp, "-o", builder_o])
-    run([NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB, engine_o, builder_o, "-Xcompiler", "-fopenmp", "-lgomp"])
+    for src, obj in zip(host_cpp, host_o):
+        run([CXX] + CXX_FLAGS + ["-c", src, "-o", obj])
+    run([NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB, engine_o] + host_o + ["-Xcompiler", "-fopenmp", "-lgomp"])
     return LIB
 
 

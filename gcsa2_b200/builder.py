@@ -87,22 +87,7 @@ def build_from_kmers(kmers, doubling_steps, sample_period=64, lcp_branching=64, 
     rc = capi.lib().gcsa_b200_build_from_kmers(key.ctypes.data, frm.ctypes.data, to.ctypes.data, int(kmers.key.size),
                                                int(kmers.k), int(doubling_steps), int(sample_period), C.byref(built))
     capi.check(rc, allow=(capi.ERR_INCONSISTENT,) if allow_inconsistent else ())
-    f = built.index
-    def bits(p, n_bits):
-        n = words_for(n_bits) + 1
-        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(n,)).copy()
-    N = int(f.path_nodes)
-    flat = FlatGCSA(
-        path_nodes=N, edge_count=int(f.edge_count), order=int(f.order),
-        C=np.array([f.C[i] for i in range(SIGMA + 1)], dtype=np.uint64),
-        bwt=[bits(f.bwt[c], N) for c in range(SIGMA)],
-        edges=bits(f.edges, f.edge_count), sampled_paths=bits(f.sampled_paths, N),
-        sample_count=int(f.sample_count),
-        stored_samples=np.ctypeslib.as_array(C.cast(f.stored_samples, C.POINTER(C.c_uint64)),
-                                             shape=(max(1, int(f.sample_count)),))[:int(f.sample_count)].copy(),
-        samples=bits(f.samples, f.sample_count), extra_filter=bits(f.extra_filter, N),
-        extra_values_len=int(f.extra_values_len), extra_values=bits(f.extra_values, f.extra_values_len),
-        redundant_len=int(f.redundant_len), redundant=bits(f.redundant, f.redundant_len))
+    flat = capi.flat_from_struct(built.index)
     lcp = np.ctypeslib.as_array(C.cast(built.lcp, C.POINTER(C.c_uint8)), shape=(max(1, int(built.lcp_size)),))[:int(built.lcp_size)].copy()
     capi.lib().gcsa_b200_built_free(C.byref(built))
     flat.consistent = (rc == 0)

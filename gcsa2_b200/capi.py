@@ -80,6 +80,8 @@ SYMBOLS = [
     "gcsa_b200_lcp_sv_host", "gcsa_b200_lcp_rmq_host", "gcsa_b200_mem_batch", "gcsa_b200_mem_host",
     "gcsa_b200_build_from_kmers", "gcsa_b200_built_free",
     "gcsa_b200_enumerate_kmers", "gcsa_b200_kmers_free", "gcsa_b200_default_char2comp",
+    "gcsa_b200_load_gcsa_file", "gcsa_b200_write_gcsa_file", "gcsa_b200_load_lcp_file", "gcsa_b200_write_lcp_file",
+    "gcsa_b200_flat_lcp_free",
 ]
 
 _lib = None
@@ -140,6 +142,11 @@ def lib():
     L.gcsa_b200_enumerate_kmers.argtypes = [C.POINTER(Graph), i32, C.POINTER(Kmers)]
     L.gcsa_b200_kmers_free.argtypes = [C.POINTER(Kmers)]; L.gcsa_b200_kmers_free.restype = None
     L.gcsa_b200_default_char2comp.argtypes = [vp]; L.gcsa_b200_default_char2comp.restype = None
+    L.gcsa_b200_load_gcsa_file.argtypes = [C.c_char_p, C.POINTER(Built)]
+    L.gcsa_b200_write_gcsa_file.argtypes = [C.POINTER(FlatIndex), C.c_char_p]
+    L.gcsa_b200_load_lcp_file.argtypes = [C.c_char_p, C.POINTER(FlatLcp)]
+    L.gcsa_b200_write_lcp_file.argtypes = [C.POINTER(FlatLcp), C.c_char_p]
+    L.gcsa_b200_flat_lcp_free.argtypes = [C.POINTER(FlatLcp)]; L.gcsa_b200_flat_lcp_free.restype = None
     _lib = L
     return L
 
@@ -164,6 +171,41 @@ def ptr(a):
 def as_u64(a):
     a = np.ascontiguousarray(a, dtype=np.uint64)
     return a if a.size else np.zeros(1, dtype=np.uint64)
+
+
+def flat_from_struct(f):
+    """C struct gcsa_flat_index (arrays owned by the library) -> FlatGCSA with its own copies."""
+    from .flat import FlatGCSA, words_for
+    def bits(p, n_bits):
+        n = words_for(n_bits) + 1
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(n,)).copy()
+    N = int(f.path_nodes)
+    return FlatGCSA(
+        path_nodes=N, edge_count=int(f.edge_count), order=int(f.order),
+        C=np.array([f.C[i] for i in range(SIGMA + 1)], dtype=np.uint64),
+        bwt=[bits(f.bwt[c], N) for c in range(SIGMA)],
+        edges=bits(f.edges, f.edge_count), sampled_paths=bits(f.sampled_paths, N),
+        sample_count=int(f.sample_count),
+        stored_samples=np.ctypeslib.as_array(C.cast(f.stored_samples, C.POINTER(C.c_uint64)),
+                                             shape=(max(1, int(f.sample_count)),))[:int(f.sample_count)].copy(),
+        samples=bits(f.samples, f.sample_count), extra_filter=bits(f.extra_filter, N),
+        extra_values_len=int(f.extra_values_len), extra_values=bits(f.extra_values, f.extra_values_len),
+        redundant_len=int(f.redundant_len), redundant=bits(f.redundant, f.redundant_len),
+        sigma=int(f.sigma), fast_chars=int(f.fast_chars),
+        char2comp=np.frombuffer(bytes(f.char2comp), dtype=np.uint8).copy())
+
+
+def lcp_struct(lcp, keep):
+    """FlatLCP (numpy) -> C struct gcsa_flat_lcp."""
+    f = FlatLcp()
+    offsets = as_u64(lcp.offsets)
+    data = np.ascontiguousarray(lcp.data, dtype=np.uint8)
+    if data.size == 0:
+        data = np.zeros(1, dtype=np.uint8)
+    keep.extend([offsets, data])
+    f.size, f.branching, f.levels = int(lcp.size), int(lcp.branching), int(lcp.levels)
+    f.offsets, f.data = offsets.ctypes.data, data.ctypes.data
+    return f
 
 
 def flat_struct(flat, keep):

@@ -37,6 +37,7 @@
 #include <vector>
 
 #include "../../include/gcsa2_b200.h"
+#include "internal.h"
 
 typedef uint64_t u64;
 typedef unsigned long long ull;
@@ -1306,6 +1307,7 @@ struct DeviceGuard
 //------------------------------------------------------------------------------
 
 const char* gcsa_b200_last_error(void) { return g_last_error.c_str(); }
+void gcsa_b200_internal_set_error(const char* message) { g_last_error = (message != nullptr ? message : ""); }
 const char* gcsa_b200_version(void) { return "gcsa2_b200 0.1 (sm_100a; GCSA v3 / LCP v1 semantics of gcsa2 1.3.0)"; }
 
 int gcsa_b200_device_count(void)

@@ -95,6 +95,25 @@ class FlatGCSA:
                  **{"bwt%d" % c: self.bwt[c] for c in range(SIGMA)})
 
     @staticmethod
+    def from_gcsa_file(path):
+        """Reads a .gcsa file of the reference (GCSA::load, src/gcsa.cpp:182-216) through the C ABI."""
+        import ctypes as C
+        from . import capi
+        built = capi.Built()
+        capi.check(capi.lib().gcsa_b200_load_gcsa_file(str(path).encode(), C.byref(built)))
+        flat = capi.flat_from_struct(built.index)
+        capi.lib().gcsa_b200_built_free(C.byref(built))
+        return flat
+
+    def to_gcsa_file(self, path):
+        """Writes the index in the reference's file format (GCSA::serialize, src/gcsa.cpp:140-180)."""
+        import ctypes as C
+        from . import capi
+        keep = []
+        f = capi.flat_struct(self, keep)
+        capi.check(capi.lib().gcsa_b200_write_gcsa_file(C.byref(f), str(path).encode()))
+
+    @staticmethod
     def load(path):
         z = np.load(path)
         h = [int(x) for x in z["header"]]
@@ -113,6 +132,29 @@ class FlatLCP:
     levels: int
     offsets: np.ndarray                # uint64[levels + 1]
     data: np.ndarray                   # uint8[offsets[levels]], levels concatenated (lcp.h:182-190)
+
+    @staticmethod
+    def from_lcp_file(path):
+        """Reads a .lcp file of the reference (LCPArray::load, src/lcp.cpp:128-143) through the C ABI."""
+        import ctypes as C
+        from . import capi
+        f = capi.FlatLcp()
+        capi.check(capi.lib().gcsa_b200_load_lcp_file(str(path).encode(), C.byref(f)))
+        levels, total = int(f.levels), 0
+        offsets = np.ctypeslib.as_array(C.cast(f.offsets, C.POINTER(C.c_uint64)), shape=(levels + 1,)).copy()
+        total = int(offsets[levels])
+        data = np.ctypeslib.as_array(C.cast(f.data, C.POINTER(C.c_uint8)), shape=(max(1, total),))[:total].copy()
+        res = FlatLCP(size=int(f.size), branching=int(f.branching), levels=levels, offsets=offsets, data=data)
+        capi.lib().gcsa_b200_flat_lcp_free(C.byref(f))
+        return res
+
+    def to_lcp_file(self, path):
+        """Writes the array in the reference's file format (LCPArray::serialize, src/lcp.cpp:116-126)."""
+        import ctypes as C
+        from . import capi
+        keep = []
+        f = capi.lcp_struct(self, keep)
+        capi.check(capi.lib().gcsa_b200_write_lcp_file(C.byref(f), str(path).encode()))
 
     @staticmethod
     def from_values(lcp_values, branching=64):

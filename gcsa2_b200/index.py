@@ -59,6 +59,12 @@ class GCSA:
         capi.check(L.gcsa_b200_index_info(self._h, C.byref(info)))
         self._info = info
 
+    @classmethod
+    def load(cls, gcsa_file, **options):
+        """sdsl::load_from_file(index, name) -> GCSA::load() of the reference (src/gcsa.cpp:182-216)."""
+        from .flat import FlatGCSA
+        return cls(FlatGCSA.from_gcsa_file(gcsa_file), **options)
+
     def close(self):
         if self._h is not None:
             capi.lib().gcsa_b200_index_destroy(self._h)
@@ -249,6 +255,12 @@ class GCSA:
 
 
 class LCPArray:
+    @classmethod
+    def load(cls, lcp_file, device=0):
+        """LCPArray::load() of the reference (src/lcp.cpp:128-143)."""
+        from .flat import FlatLCP
+        return cls(FlatLCP.from_lcp_file(lcp_file), device=device)
+
     def __init__(self, flat_lcp, device=0):
         self._h = None
         self._offsets = capi.as_u64(flat_lcp.offsets)

@@ -244,6 +244,24 @@ int  gcsa_b200_build_from_kmers(const uint64_t* keys, const uint64_t* from, cons
                                 gcsa_b200_built* result);
 void gcsa_b200_built_free(gcsa_b200_built* result);
 
+/* ---------------------------------------------------------------------------------------------
+   Index files of the reference (host; gcsa2_b200/csrc/gcsa_file.cpp).
+   gcsa_b200_load_gcsa_file replaces GCSA::load / sdsl::load_from_file(index, name)
+   (src/gcsa.cpp:182-216, src/build_gcsa.cpp:148-160): header check (tag 0x6C5A6C5A, version 3,
+   flags 0; src/files.cpp:540-544), then the members in the reference's order, decoded to plain
+   arrays; the SDSL rank/select supports in the file are skipped.  result->lcp stays NULL; release
+   with gcsa_b200_built_free.  gcsa_b200_write_gcsa_file replaces GCSA::serialize
+   (src/gcsa.cpp:140-180).  The *_lcp_* pair does the same for LCPArray::load / serialize
+   (src/lcp.cpp:116-143; tag 0x6C5A7C94, version 1); release with gcsa_b200_flat_lcp_free.
+   The reader validates sizes, cumulative counts and the end of file and returns
+   GCSA_B200_ERR_INVALID with a message instead of guessing.
+   --------------------------------------------------------------------------------------------- */
+int  gcsa_b200_load_gcsa_file(const char* path, gcsa_b200_built* result);
+int  gcsa_b200_write_gcsa_file(const gcsa_flat_index* index, const char* path);
+int  gcsa_b200_load_lcp_file(const char* path, gcsa_flat_lcp* result);
+int  gcsa_b200_write_lcp_file(const gcsa_flat_lcp* lcp, const char* path);
+void gcsa_b200_flat_lcp_free(gcsa_flat_lcp* lcp);
+
 /* A graph of single-character nodes in CSR form, for the synthetic inputs of the benchmarks. */
 typedef struct gcsa_b200_graph {
   uint64_t nodes;

@@ -92,6 +92,21 @@ public:
     gcsa_b200_index_info(handle, &info);
     for(int i = 0; i < 256; i++) { char2comp[i] = flat.char2comp[i]; }
   }
+  // From a .gcsa file of the reference: sdsl::load_from_file(index, name) -> GCSA::load()
+  // (src/build_gcsa.cpp:148-153, src/gcsa.cpp:182-216); throws std::runtime_error on a bad file
+  // like the reference does (gcsa.cpp:188-193).
+  explicit GCSA(const std::string& gcsa_file, int device = 0, int kmer_table_k = 12) : handle(nullptr)
+  {
+    gcsa_b200_built loaded;
+    check(gcsa_b200_load_gcsa_file(gcsa_file.c_str(), &loaded), "GCSA::load()");
+    gcsa_b200_options options = {};
+    options.kmer_table_k = kmer_table_k; options.two_step = -1; options.walk_table = -1;
+    int rc = gcsa_b200_index_create(&loaded.index, device, &options, &handle);
+    for(int i = 0; i < 256; i++) { char2comp[i] = loaded.index.char2comp[i]; }
+    gcsa_b200_built_free(&loaded);
+    check(rc, "GCSA::load()");
+    gcsa_b200_index_info(handle, &info);
+  }
   ~GCSA() { gcsa_b200_index_destroy(handle); }
   GCSA(const GCSA&) = delete;
   GCSA& operator=(const GCSA&) = delete;
@@ -266,6 +281,16 @@ public:
   {
     check(gcsa_b200_lcp_create(&flat, device, &handle), "LCPArray::LCPArray()");
     size_ = flat.size; levels_ = flat.levels; branching_ = flat.branching; values_ = flat.offsets[flat.levels];
+  }
+  // From a .lcp file of the reference: LCPArray::load(), src/lcp.cpp:128-143.
+  explicit LCPArray(const std::string& lcp_file, int device = 0) : handle(nullptr)
+  {
+    gcsa_flat_lcp flat;
+    check(gcsa_b200_load_lcp_file(lcp_file.c_str(), &flat), "LCPArray::load()");
+    int rc = gcsa_b200_lcp_create(&flat, device, &handle);
+    size_ = flat.size; levels_ = flat.levels; branching_ = flat.branching; values_ = flat.offsets[flat.levels];
+    gcsa_b200_flat_lcp_free(&flat);
+    check(rc, "LCPArray::load()");
   }
   ~LCPArray() { gcsa_b200_lcp_destroy(handle); }
   LCPArray(const LCPArray&) = delete;

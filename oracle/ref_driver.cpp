@@ -152,6 +152,31 @@ RefIndex* ref_from_flat(std::uint64_t path_nodes, std::uint64_t edge_count, std:
   return r;
 }
 
+/* sdsl::store_to_file(index, name) / load_from_file, the way build_gcsa does it (src/build_gcsa.cpp:148-178):
+   GCSA::serialize / GCSA::load and LCPArray::serialize / load are the reference's own. */
+int ref_store(const RefIndex* r, const char* gcsa_file, const char* lcp_file)
+{
+  if(gcsa_file != nullptr && !sdsl::store_to_file(r->index, gcsa_file)) { return 0; }
+  if(lcp_file != nullptr && r->has_lcp && !sdsl::store_to_file(r->lcp, lcp_file)) { return 0; }
+  return 1;
+}
+
+RefIndex* ref_load(const char* gcsa_file, const char* lcp_file)
+{
+  RefIndex* r = new RefIndex();
+  try
+  {
+    if(!sdsl::load_from_file(r->index, gcsa_file)) { delete r; return nullptr; }
+    if(lcp_file != nullptr)
+    {
+      if(!sdsl::load_from_file(r->lcp, lcp_file)) { delete r; return nullptr; }
+      r->has_lcp = true;
+    }
+  }
+  catch(const std::exception&) { delete r; return nullptr; }
+  return r;
+}
+
 int ref_max_threads(void) { return omp_get_max_threads(); }
 
 /* The loop of benchmark/query_gcsa.cpp:88-103 over GCSA::find, OpenMP like src/algorithms.cpp:113. */

@@ -53,6 +53,8 @@ def lib():
     L.ref_sizes.argtypes = [vp, vp]
     L.ref_export.argtypes = [vp] + [vp] * 11
     L.ref_from_flat.restype = vp; L.ref_from_flat.argtypes = [u64, u64, u64, vp, vp, vp, vp, u64, vp, vp]
+    L.ref_store.restype = C.c_int; L.ref_store.argtypes = [vp, C.c_char_p, C.c_char_p]
+    L.ref_load.restype = vp; L.ref_load.argtypes = [C.c_char_p, C.c_char_p]
     L.ref_max_threads.restype = C.c_int
     L.ref_find_batch.restype = C.c_double; L.ref_find_batch.argtypes = [vp, vp, vp, u64, vp, vp, C.c_int]
     L.ref_lf_batch.argtypes = [vp, vp, vp, vp, u64, vp, vp]
@@ -98,6 +100,18 @@ class ReferenceIndex:
         h = lib().ref_from_flat(int(flat.path_nodes), int(flat.edge_count), int(flat.order), Cc.ctypes.data, ptrs,
                                 edges.ctypes.data, sampled.ctypes.data, int(flat.sample_count), stored.ctypes.data, samples.ctypes.data)
         return ReferenceIndex(h, False)
+
+    def store(self, gcsa_path, lcp_path=None):
+        """sdsl::store_to_file -> GCSA::serialize / LCPArray::serialize of the reference (through the shim)."""
+        ok = lib().ref_store(self._h, str(gcsa_path).encode(), str(lcp_path).encode() if lcp_path else None)
+        if not ok:
+            raise IOError("reference could not write %s" % gcsa_path)
+
+    @staticmethod
+    def load(gcsa_path, lcp_path=None):
+        """sdsl::load_from_file -> GCSA::load / LCPArray::load of the reference; None if it rejects the file."""
+        h = lib().ref_load(str(gcsa_path).encode(), str(lcp_path).encode() if lcp_path else None)
+        return ReferenceIndex(h, lcp_path is not None) if h else None
 
     def __del__(self):
         if getattr(self, "_h", None):

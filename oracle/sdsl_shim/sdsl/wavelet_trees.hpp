@@ -234,21 +234,24 @@ public:
   }
   bool operator!=(const int_vector& o) const { return !(*this == o); }
 
+  // On-disk layout of sdsl-lite: size in bits, the width byte only for int_vector<0>, then
+  // ceil(bits / 64) words.
   size_type serialize(std::ostream& out, structure_tree_node* = nullptr, std::string = "") const
   {
-    size_type bytes = 0;
-    bytes += write_member(n, out); bytes += write_member(w, out);
-    std::uint64_t count = words.size();
-    bytes += write_member(count, out);
+    size_type bytes = 0, bit_len = n * w, count = (bit_len + 63) / 64;
+    bytes += write_member(bit_len, out);
+    if(W == 0) { bytes += write_member(w, out); }
     out.write(reinterpret_cast<const char*>(words.data()), count * sizeof(std::uint64_t));
     return bytes + count * sizeof(std::uint64_t);
   }
   void load(std::istream& in)
   {
-    read_member(n, in); read_member(w, in);
-    std::uint64_t count = 0; read_member(count, in);
-    words.assign(count, 0);
-    in.read(reinterpret_cast<char*>(words.data()), count * sizeof(std::uint64_t));
+    size_type bit_len = 0;
+    read_member(bit_len, in);
+    if(W == 0) { read_member(w, in); }
+    n = bit_len / w;
+    words.assign(word_count(n, w), 0);
+    in.read(reinterpret_cast<char*>(words.data()), ((bit_len + 63) / 64) * sizeof(std::uint64_t));
   }
 
 private:
@@ -331,6 +334,88 @@ struct RankedBits
   }
 };
 
+// select_support_mcl on disk: the number of arguments; if there are any, the positions of every
+// 4096th argument, a bit per superblock (1 = short) unless all are short, and per superblock
+// either all positions (long, and always the last partial one) or every 64th relative position.
+inline void writeVarVector(std::ostream& out, const std::vector<std::uint64_t>& values, std::uint64_t count, std::uint8_t width)
+{
+  std::uint64_t bit_len = count * width;
+  std::vector<std::uint64_t> packed((bit_len + 63) / 64 + 1, 0);
+  for(std::uint64_t i = 0; i < values.size(); i++)
+  {
+    std::uint64_t bit = i * width, word = bit >> 6, off = bit & 63;
+    packed[word] |= values[i] << off;
+    if(off + width > 64) { packed[word + 1] |= values[i] >> (64 - off); }
+  }
+  write_member(bit_len, out); write_member(width, out);
+  out.write(reinterpret_cast<const char*>(packed.data()), ((bit_len + 63) / 64) * sizeof(std::uint64_t));
+}
+
+inline void skipVarVector(std::istream& in)
+{
+  std::uint64_t bit_len = 0; std::uint8_t width = 0;
+  read_member(bit_len, in); read_member(width, in);
+  in.seekg(((bit_len + 63) / 64) * sizeof(std::uint64_t), std::ios::cur);
+}
+
+inline std::uint64_t topBit(std::uint64_t x) { return (x == 0 ? 0 : 63 - __builtin_clzll(x)); }
+
+inline void writeSelectDirectory(std::ostream& out, const std::uint64_t* words, std::uint64_t n, bool ones)
+{
+  std::vector<std::uint64_t> pos;
+  for(std::uint64_t i = 0; i < n; i++)
+  {
+    bool bit = (words[i >> 6] >> (i & 63)) & 1;
+    if(bit == ones) { pos.push_back(i); }
+  }
+  std::uint64_t total = pos.size();
+  write_member(total, out);
+  if(total == 0) { return; }
+  std::uint64_t logn = topBit(((n + 63) / 64) * 64) + 1, limit = logn * logn * logn * logn;
+  std::uint64_t superblocks = (total + 4095) / 4096;
+  std::vector<std::uint64_t> firsts(superblocks), kind(superblocks / 64 + 1, 0);
+  bool mixed = false;
+  for(std::uint64_t b = 0; b < superblocks; b++)
+  {
+    std::uint64_t from = b * 4096, to = std::min(from + 4096, total);
+    firsts[b] = pos[from];
+    bool is_short = (to - from == 4096 && pos[to - 1] - pos[from] <= limit);
+    if(is_short) { kind[b >> 6] |= (std::uint64_t)1 << (b & 63); } else { mixed = true; }
+  }
+  writeVarVector(out, firsts, superblocks, (std::uint8_t)logn);
+  std::uint64_t kind_bits = (mixed ? superblocks : 0);
+  write_member(kind_bits, out);
+  out.write(reinterpret_cast<const char*>(kind.data()), ((kind_bits + 63) / 64) * sizeof(std::uint64_t));
+  for(std::uint64_t b = 0; b < superblocks; b++)
+  {
+    std::uint64_t from = b * 4096, to = std::min(from + 4096, total);
+    std::vector<std::uint64_t> values;
+    if((kind[b >> 6] >> (b & 63)) & 1)
+    {
+      for(std::uint64_t j = from; j < to; j += 64) { values.push_back(pos[j] - pos[from]); }
+      writeVarVector(out, values, 64, (std::uint8_t)(topBit(pos[to - 1] - pos[from]) + 1));
+    }
+    else
+    {
+      values.assign(pos.begin() + from, pos.begin() + to);
+      std::uint64_t widest = (to - from == 4096 ? pos[to - 1] : n - 1);
+      writeVarVector(out, values, 4096, (std::uint8_t)(topBit(widest) + 1));
+    }
+  }
+}
+
+inline void skipSelectDirectory(std::istream& in)
+{
+  std::uint64_t total = 0;
+  read_member(total, in);
+  if(total == 0) { return; }
+  skipVarVector(in);
+  std::uint64_t kind_bits = 0;
+  read_member(kind_bits, in);
+  in.seekg(((kind_bits + 63) / 64) * sizeof(std::uint64_t), std::ios::cur);
+  for(std::uint64_t b = 0; b < (total + 4095) / 4096; b++) { skipVarVector(in); }
+}
+
 } // namespace shim_detail
 
 // Supports for bit_vector: they index the vector they were initialised with.
@@ -357,8 +442,14 @@ struct select_support_shim
   std::uint64_t operator()(std::uint64_t k) const { return bits.select(k); }
   std::uint64_t select(std::uint64_t k) const { return bits.select(k); }
   void swap(select_support_shim& o) { std::swap(bits, o.bits); }
-  std::uint64_t serialize(std::ostream&, structure_tree_node* = nullptr, std::string = "") const { return 0; }
-  void load(std::istream&, const bit_vector* v = nullptr) { set_vector(v); }
+  std::uint64_t serialize(std::ostream& out, structure_tree_node* = nullptr, std::string = "") const
+  {
+    std::vector<std::uint64_t> plain((bits.n_bits + 63) / 64 + 1, 0);
+    for(std::uint64_t i = 0; i < bits.n_bits; i++) { if(bits.get(i)) { plain[i >> 6] |= (std::uint64_t)1 << (i & 63); } }
+    shim_detail::writeSelectDirectory(out, plain.data(), bits.n_bits, true);
+    return 0;
+  }
+  void load(std::istream& in, const bit_vector* v = nullptr) { shim_detail::skipSelectDirectory(in); set_vector(v); }
 };
 
 //------------------------------------------------------------------------------
@@ -393,19 +484,58 @@ public:
   bool operator[](size_type i) const { return bits.get(i); }
   void swap(bit_vector_il& o) { std::swap(bits, o.bits); }
 
+  // On-disk layout of sdsl-lite's bit_vector_il: size, number of words, number of blocks, log of
+  // the block size, the interleaved words ([count, 8 data words] per block, data cut at
+  // (size + 64) / 64 words, then the total), and the select samples over the block counts.
   size_type serialize(std::ostream& out, structure_tree_node* = nullptr, std::string = "") const
   {
-    std::uint64_t count = bits.il.size();
-    write_member(bits.n_bits, out); write_member(bits.ones, out); write_member(count, out);
-    out.write(reinterpret_cast<const char*>(bits.il.data()), count * sizeof(std::uint64_t));
-    return (3 + count) * sizeof(std::uint64_t);
+    std::uint64_t zero = 0;
+    if(bits.il.empty())
+    {
+      for(int i = 0; i < 6; i++) { write_member(zero, out); }
+      return 6 * sizeof(std::uint64_t);
+    }
+    std::uint64_t n = bits.n_bits, blocks = (n + B) / B, data_words = (n + 64) / 64, mem = data_words + blocks + 1, shift = bits::hi(B);
+    std::vector<std::uint64_t> data;
+    data.reserve(mem);
+    for(std::uint64_t i = 0; i < data_words; i++)
+    {
+      if(i % 8 == 0) { data.push_back(bits.il[(i / 8) * 9]); }
+      data.push_back(bits.il[(i / 8) * 9 + 1 + i % 8]);
+    }
+    data.push_back(bits.ones);
+    std::uint64_t n_samples = (blocks > 2048 ? 1024 : std::max<std::uint64_t>(1, (std::uint64_t)1 << bits::hi(blocks)));
+    std::vector<std::uint64_t> samples(n_samples, 0);
+    {
+      std::vector<std::pair<std::uint64_t, std::uint64_t>> todo(1, std::make_pair((std::uint64_t)0, blocks));
+      for(std::uint64_t head = 0, idx = 0; head < todo.size() && idx < n_samples; head++)
+      {
+        std::uint64_t lb = todo[head].first, rb = todo[head].second, mid = lb + (rb - lb) / 2;
+        samples[idx++] = (mid * 9 < data.size() ? data[mid * 9] : bits.ones);
+        todo.push_back(std::make_pair(lb, mid)); todo.push_back(std::make_pair(mid + 1, rb));
+      }
+    }
+    write_member(n, out); write_member(mem, out); write_member(blocks, out); write_member(shift, out);
+    std::uint64_t data_bits = data.size() * 64, sample_bits = samples.size() * 64;
+    write_member(data_bits, out);
+    out.write(reinterpret_cast<const char*>(data.data()), data.size() * sizeof(std::uint64_t));
+    write_member(sample_bits, out);
+    out.write(reinterpret_cast<const char*>(samples.data()), samples.size() * sizeof(std::uint64_t));
+    return (6 + data.size() + samples.size()) * sizeof(std::uint64_t);
   }
   void load(std::istream& in)
   {
-    std::uint64_t count = 0;
-    read_member(bits.n_bits, in); read_member(bits.ones, in); read_member(count, in);
-    bits.il.assign(count, 0);
-    in.read(reinterpret_cast<char*>(bits.il.data()), count * sizeof(std::uint64_t));
+    std::uint64_t n = 0, mem = 0, blocks = 0, shift = 0, data_bits = 0, sample_bits = 0;
+    read_member(n, in); read_member(mem, in); read_member(blocks, in); read_member(shift, in);
+    read_member(data_bits, in);
+    std::vector<std::uint64_t> data(data_bits / 64 + 1, 0);
+    in.read(reinterpret_cast<char*>(data.data()), (data_bits / 64) * sizeof(std::uint64_t));
+    read_member(sample_bits, in);
+    in.seekg((sample_bits / 64) * sizeof(std::uint64_t), std::ios::cur);
+    if(data_bits == 0) { bits = shim_detail::RankedBits(); return; }
+    std::vector<std::uint64_t> plain((n + 63) / 64 + 1, 0);
+    for(std::uint64_t i = 0; i < (n + 63) / 64; i++) { plain[i] = data[i + i / 8 + 1]; }
+    bits.build(plain.data(), n);
   }
 
   shim_detail::RankedBits bits;
@@ -505,19 +635,65 @@ public:
 
   void swap(sd_vector& o) { std::swap(n, o.n); positions.swap(o.positions); }
 
+  // On-disk layout of sdsl-lite's sd_vector (Elias-Fano): size, width of the low parts, the low
+  // parts, the unary-coded high parts, and the select directories for the ones and zeros of those.
   size_type serialize(std::ostream& out, structure_tree_node* = nullptr, std::string = "") const
   {
-    std::uint64_t count = positions.size();
-    write_member(n, out); write_member(count, out);
-    out.write(reinterpret_cast<const char*>(positions.data()), count * sizeof(std::uint64_t));
-    return (2 + count) * sizeof(std::uint64_t);
+    std::uint64_t m = positions.size(), zero = 0;
+    if(n == 0 && m == 0)
+    {
+      std::uint8_t wl = 0, width = 64;
+      write_member(zero, out); write_member(wl, out);
+      write_member(zero, out); write_member(width, out);   // low
+      write_member(zero, out);                             // high
+      write_member(zero, out); write_member(zero, out);    // directories
+      return 0;
+    }
+    std::uint64_t logm = bits::hi(m) + 1, logn = bits::hi(n) + 1;
+    if(logm == logn) { logm--; }
+    std::uint8_t wl = (std::uint8_t)(logn - logm);
+    std::uint64_t high_bits = m + ((std::uint64_t)1 << logm);
+    std::vector<std::uint64_t> low(m), high(high_bits / 64 + 2, 0);
+    for(std::uint64_t i = 0; i < m; i++)
+    {
+      low[i] = positions[i] & (((std::uint64_t)1 << wl) - 1);
+      std::uint64_t h = (positions[i] >> wl) + i;
+      high[h >> 6] |= (std::uint64_t)1 << (h & 63);
+    }
+    write_member(n, out); write_member(wl, out);
+    shim_detail::writeVarVector(out, low, m, wl);
+    write_member(high_bits, out);
+    out.write(reinterpret_cast<const char*>(high.data()), ((high_bits + 63) / 64) * sizeof(std::uint64_t));
+    shim_detail::writeSelectDirectory(out, high.data(), high_bits, true);
+    shim_detail::writeSelectDirectory(out, high.data(), high_bits, false);
+    return 0;
   }
   void load(std::istream& in)
   {
-    std::uint64_t count = 0;
-    read_member(n, in); read_member(count, in);
-    positions.assign(count, 0);
-    in.read(reinterpret_cast<char*>(positions.data()), count * sizeof(std::uint64_t));
+    std::uint8_t wl = 0, width = 0;
+    std::uint64_t low_bits = 0, high_bits = 0;
+    read_member(n, in); read_member(wl, in);
+    read_member(low_bits, in); read_member(width, in);
+    std::vector<std::uint64_t> low((low_bits + 63) / 64 + 1, 0);
+    in.read(reinterpret_cast<char*>(low.data()), ((low_bits + 63) / 64) * sizeof(std::uint64_t));
+    read_member(high_bits, in);
+    std::vector<std::uint64_t> high((high_bits + 63) / 64 + 1, 0);
+    in.read(reinterpret_cast<char*>(high.data()), ((high_bits + 63) / 64) * sizeof(std::uint64_t));
+    shim_detail::skipSelectDirectory(in); shim_detail::skipSelectDirectory(in);
+    positions.clear();
+    for(std::uint64_t p = 0, i = 0; p < high_bits; p++)
+    {
+      if(!((high[p >> 6] >> (p & 63)) & 1)) { continue; }
+      std::uint64_t bit = i * wl, word = bit >> 6, off = bit & 63, x = 0;
+      if(wl > 0)
+      {
+        x = low[word] >> off;
+        if(off + wl > 64) { x |= low[word + 1] << (64 - off); }
+        x &= (((std::uint64_t)1 << wl) - 1);
+      }
+      positions.push_back(((p - i) << wl) | x);
+      i++;
+    }
   }
 
   std::uint64_t n;

@@ -121,6 +121,32 @@ int main()
     }
   }
   REQUIRE(found > 200);
+
+  // The same index through the reference's file formats: GCSA::serialize / load, LCPArray::serialize / load
+  // (src/gcsa.cpp:140-216, src/lcp.cpp:116-143; build_gcsa.cpp:148-178).
+  {
+    std::string base = std::string("/tmp/gcsa2_b200_facade_test_") + std::to_string((unsigned long)next_random());
+    REQUIRE(gcsa_b200_write_gcsa_file(&built.index, (base + ".gcsa").c_str()) == 0);
+    REQUIRE(gcsa_b200_write_lcp_file(&flat_lcp, (base + ".lcp").c_str()) == 0);
+    GCSA from_file(base + ".gcsa", 0, 4);
+    LCPArray lcp_from_file(base + ".lcp", 0);
+    REQUIRE(from_file.size() == index.size() && from_file.order() == index.order() && lcp_from_file.size() == lcp.size());
+    std::vector<range_type> again;
+    from_file.find(patterns, again);
+    REQUIRE(again == batch);
+    for(size_type i = 0; i < 50; i++)
+    {
+      if(Range::empty(batch[i])) { continue; }
+      std::vector<node_type> a, b;
+      index.locate(batch[i], a); from_file.locate(batch[i], b);
+      REQUIRE(a == b && from_file.count(batch[i]) == index.count(batch[i]));
+      REQUIRE(lcp_from_file.parent(batch[i]) == lcp.parent(batch[i]));
+    }
+    std::remove((base + ".gcsa").c_str()); std::remove((base + ".lcp").c_str());
+    bool threw = false;
+    try { GCSA missing(base + ".gcsa", 0, 4); } catch(const std::runtime_error&) { threw = true; }
+    REQUIRE(threw);                                                        // GCSA::load throws, gcsa.cpp:188-193
+  }
   std::vector<range_type> fast(GCSA_B200_SIGMA), all(GCSA_B200_SIGMA);
   index.LF_fast(batch[0], fast); index.LF_all(batch[0], all);
   for(comp_type c = 1; c <= 4; c++) { REQUIRE(fast[c] == all[c]); }
