@@ -51,6 +51,12 @@ class FindStats(C.Structure):
                 ("lf_steps", C.c_uint64), ("sector_probes", C.c_uint64), ("table_hits", C.c_uint64)]
 
 
+class VerifyReport(C.Structure):
+    _fields_ = [("unique", C.c_uint64), ("failures", C.c_uint64), ("find_failures", C.c_uint64),
+                ("parent_failures", C.c_uint64), ("depth_failures", C.c_uint64), ("count_failures", C.c_uint64),
+                ("locate_failures", C.c_uint64), ("random_locate_failures", C.c_uint64), ("seconds", C.c_double)]
+
+
 class Built(C.Structure):
     _fields_ = [("index", FlatIndex), ("lcp_size", C.c_uint64), ("lcp", C.c_void_p)]
 
@@ -74,7 +80,7 @@ SYMBOLS = [
     "gcsa_b200_lf_batch", "gcsa_b200_lf_host", "gcsa_b200_lf_node_batch", "gcsa_b200_lf_node_host",
     "gcsa_b200_lf_multi_batch", "gcsa_b200_lf_multi_host",
     "gcsa_b200_count_batch", "gcsa_b200_count_host",
-    "gcsa_b200_locate_host", "gcsa_b200_locate_raw_host", "gcsa_b200_locate_batch", "gcsa_b200_locate_max_host", "gcsa_b200_free", "gcsa_b200_count_kmers",
+    "gcsa_b200_locate_host", "gcsa_b200_locate_raw_host", "gcsa_b200_locate_batch", "gcsa_b200_locate_max_host", "gcsa_b200_free", "gcsa_b200_count_kmers", "gcsa_b200_compare_kmers", "gcsa_b200_verify_index",
     "gcsa_b200_lcp_create", "gcsa_b200_lcp_destroy",
     "gcsa_b200_parent_batch", "gcsa_b200_parent_host", "gcsa_b200_depth_batch", "gcsa_b200_depth_host",
     "gcsa_b200_lcp_sv_host", "gcsa_b200_lcp_rmq_host", "gcsa_b200_mem_batch", "gcsa_b200_mem_host",
@@ -127,6 +133,8 @@ def lib():
     L.gcsa_b200_locate_max_host.argtypes = [vp, vp, vp, u64, u64, vp, C.POINTER(vp)]
     L.gcsa_b200_free.argtypes = [vp]; L.gcsa_b200_free.restype = None
     L.gcsa_b200_count_kmers.argtypes = [vp, u64, i32, C.POINTER(u64), C.POINTER(vp)]
+    L.gcsa_b200_compare_kmers.argtypes = [vp, vp, u64, i32, vp, C.POINTER(vp), C.POINTER(vp)]
+    L.gcsa_b200_verify_index.argtypes = [vp, vp, vp, vp, u64, i32, C.POINTER(VerifyReport)]
     L.gcsa_b200_lcp_create.argtypes = [C.POINTER(FlatLcp), i32, C.POINTER(vp)]
     L.gcsa_b200_lcp_destroy.argtypes = [vp]; L.gcsa_b200_lcp_destroy.restype = None
     L.gcsa_b200_parent_batch.argtypes = [vp, vp, vp, u64, vp, vp]

@@ -751,6 +751,91 @@ kmer_compact_kernel(const u64* __restrict__ csp, const u64* __restrict__ cep, co
 }
 
 //------------------------------------------------------------------------------
+// Kernels: compareKMers (src/algorithms.cpp:505-616) -- the tries of two indexes in lockstep
+//------------------------------------------------------------------------------
+
+// One child range of LF_fast / LF_all (src/gcsa.cpp:742-798): empty input and a single path node
+// without the predecessor give Range::empty_range(); the general case gives LF() uncanonicalised.
+__device__ __forceinline__ void trie_child(const DevView& v, u64 s, u64 e, u32 c, u64& a, u64& b)
+{
+  a = 1; b = 0;
+  if(range_empty(s, e)) { return; }
+  if(s == e) { if(bwt_bit(v, s, c)) { lf_range(v, s, e, c, a, b); } }
+  else { lf_range(v, s, e, c, a, b); }
+}
+
+// states: 4 arrays (left sp, left ep, right sp, right ep) of `stride` entries each; kmers: 3 words per state or null.
+__global__ void __launch_bounds__(256)
+compare_expand_kernel(const DevView vl, const DevView vr, const u64* __restrict__ in, u64 n, const u64* __restrict__ in_kmer,
+                      u32 chars, u64 level, u64* __restrict__ out, u64* __restrict__ out_kmer, u64* __restrict__ flag)
+{
+  u64 total = n * chars;
+  for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x)
+  {
+    u64 i = t / chars; u32 c = (u32)(t - i * chars) + 1;
+    u64 la, lb, ra, rb;
+    trie_child(vl, in[i], in[n + i], c, la, lb);
+    trie_child(vr, in[2 * n + i], in[3 * n + i], c, ra, rb);
+    out[t] = la; out[total + t] = lb; out[2 * total + t] = ra; out[3 * total + t] = rb;
+    flag[t] = ((range_empty(la, lb) && range_empty(ra, rb)) ? 0 : 1);          // algorithms.cpp:514
+    if(out_kmer != nullptr)
+    {
+      u64 w0 = in_kmer[3 * i], w1 = in_kmer[3 * i + 1], w2 = in_kmer[3 * i + 2];
+      u64 bit = level * 3, word = bit >> 6, off = bit & 63, x = (u64)c << off, y = (off > 61 ? (u64)c >> (64 - off) : 0);   // KMerComparisonState::set, algorithms.cpp:451-457
+      if(word == 0) { w0 |= x; w1 |= y; } else if(word == 1) { w1 |= x; w2 |= y; } else { w2 |= x; }
+      out_kmer[3 * t] = w0; out_kmer[3 * t + 1] = w1; out_kmer[3 * t + 2] = w2;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+compare_compact_kernel(const u64* __restrict__ child, const u64* __restrict__ child_kmer, const u64* __restrict__ flag,
+                       const u64* __restrict__ pos, u64 total, u64 next, u64* __restrict__ out, u64* __restrict__ out_kmer)
+{
+  for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x)
+  {
+    if(!flag[t]) { continue; }
+    u64 d = pos[t];
+    for(int f = 0; f < 4; f++) { out[f * next + d] = child[f * total + t]; }
+    if(out_kmer != nullptr) { for(int w = 0; w < 3; w++) { out_kmer[3 * d + w] = child_kmer[3 * t + w]; } }
+  }
+}
+
+// KMerSymmetricDifference::report, algorithms.cpp:488-500: side[i] = 0 shared, 1 left only, 2 right only.
+__global__ void __launch_bounds__(256)
+compare_classify_kernel(const u64* __restrict__ st, u64 n, ull* __restrict__ counts, u64* __restrict__ left_flag, u64* __restrict__ right_flag)
+{
+  ull mine[3] = { 0, 0, 0 };
+  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+  {
+    u64 llen = st[n + i] + 1 - st[i], rlen = st[3 * n + i] + 1 - st[2 * n + i];
+    u32 side = (llen > 0 && rlen > 0 ? 0 : (llen > 0 ? 1 : 2));
+    mine[side]++;
+    if(left_flag != nullptr) { left_flag[i] = (side == 1); right_flag[i] = (side == 2); }
+  }
+  for(int k = 0; k < 3; k++)
+  {
+    ull x = mine[k];
+    for(int d = 16; d > 0; d >>= 1) { x += __shfl_down_sync(0xFFFFFFFFu, x, d); }
+    if((threadIdx.x & 31) == 0 && x > 0) { atomicAdd(counts + k, x); }
+  }
+}
+
+// Unique kmers as gcsa_b200_kmer_state records (8 words each).
+__global__ void __launch_bounds__(256)
+compare_emit_kernel(const u64* __restrict__ st, const u64* __restrict__ kmer, u64 n, u64 k, const u64* __restrict__ flag,
+                    const u64* __restrict__ pos, u64* __restrict__ records)
+{
+  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+  {
+    if(!flag[i]) { continue; }
+    u64* r = records + 8 * pos[i];
+    r[0] = st[i]; r[1] = st[n + i]; r[2] = st[2 * n + i]; r[3] = st[3 * n + i]; r[4] = k;
+    r[5] = kmer[3 * i]; r[6] = kmer[3 * i + 1]; r[7] = kmer[3 * i + 2];
+  }
+}
+
+//------------------------------------------------------------------------------
 // Kernels: locate (src/gcsa.cpp:827-842, 880-896)
 //------------------------------------------------------------------------------
 
@@ -2318,6 +2403,110 @@ done:
   #undef KM_TRY
   if(rc == 0 && e != cudaSuccess) { rc = fail(GCSA_B200_ERR_CUDA, std::string("count_kmers: ") + cudaGetErrorString(e)); }
   return rc;
+}
+
+/*
+  compareKMers(left, right, k, parameters), src/algorithms.cpp:535-616: result = (kmers in both, only
+  in left, only in right).  The reference walks both tries depth-first in lockstep, one OpenMP task per
+  5-mer seed; here every level is one frontier of (left range, right range) states expanded by one launch.
+  Both indexes must live on the same device.
+*/
+int gcsa_b200_compare_kmers(const gcsa_b200_index* left, const gcsa_b200_index* right, uint64_t k, int include_Ns,
+                            uint64_t* result, gcsa_b200_kmer_state** left_kmers, gcsa_b200_kmer_state** right_kmers)
+{
+  if(left == nullptr || right == nullptr || result == nullptr) { return fail(GCSA_B200_ERR_INVALID, "compare_kmers: null argument"); }
+  result[0] = result[1] = result[2] = 0;
+  if(left_kmers) { *left_kmers = nullptr; }
+  if(right_kmers) { *right_kmers = nullptr; }
+  if(k == 0) { result[0] = 1; return 0; }                                         // algorithms.cpp:540
+  if(k > 64) { return fail(GCSA_B200_ERR_INVALID, "compare_kmers: comparison is only supported for k <= 64"); }   // KMerComparisonState::MAX_K
+  if(left->device != right->device) { return fail(GCSA_B200_ERR_INVALID, "compare_kmers: the indexes live on different devices"); }
+  if(left->header.path_nodes == 0 && right->header.path_nodes == 0) { return 0; }
+  const bool want = (left_kmers != nullptr || right_kmers != nullptr);
+  HOST_PROLOGUE("compare_kmers", left);
+  cudaStream_t st = sc.stream;
+  const u32 chars = (include_Ns ? GCSA_B200_SIGMA - 2 : GCSA_B200_FAST_CHARS);
+  int rc = 0;
+  u64 n = 1;
+  u64 root[4] = { 0, left->header.path_nodes - 1, 0, right->header.path_nodes - 1 };
+  u64 zero_kmer[3] = { 0, 0, 0 };
+  u64* state = nullptr; u64* kmer = nullptr;
+  cudaError_t e = cudaSuccess;
+  #define CK_TRY(expr) do { e = (expr); if(e != cudaSuccess) { rc = fail(GCSA_B200_ERR_CUDA, std::string("compare_kmers: " #expr ": ") + cudaGetErrorString(e)); goto done; } } while(0)
+  #define CK_ALLOC(ptr, count) do { CK_TRY(cudaMallocAsync((void**)&(ptr), std::max<u64>((count), 1) * sizeof(u64), st)); } while(0)
+  {
+    CK_ALLOC(state, 4); CK_TRY(cudaMemcpyAsync(state, root, sizeof(root), cudaMemcpyHostToDevice, st));
+    if(want) { CK_ALLOC(kmer, 3); CK_TRY(cudaMemcpyAsync(kmer, zero_kmer, sizeof(zero_kmer), cudaMemcpyHostToDevice, st)); }
+    for(u64 level = 0; level < k && n > 0; level++)
+    {
+      u64 total = n * chars, next = 0;
+      u64 *child = nullptr, *child_kmer = nullptr, *flag = nullptr, *pos = nullptr, *new_state = nullptr, *new_kmer = nullptr;
+      CK_ALLOC(child, 4 * total); CK_ALLOC(flag, total + 1); CK_ALLOC(pos, total + 1);
+      if(want) { CK_ALLOC(child_kmer, 3 * total); }
+      CK_TRY(cudaMemsetAsync(flag + total, 0, sizeof(u64), st));
+      compare_expand_kernel<<<gridFor(total, left->sm_count), 256, 0, st>>>(left->view, right->view, state, n, kmer, chars, level, child, child_kmer, flag);
+      rc = scanExclusive(flag, pos, total + 1, st);
+      if(rc) { goto done; }
+      CK_TRY(cudaMemcpyAsync(&next, pos + total, sizeof(u64), cudaMemcpyDeviceToHost, st));
+      CK_TRY(cudaStreamSynchronize(st));
+      CK_ALLOC(new_state, 4 * next);
+      if(want) { CK_ALLOC(new_kmer, 3 * next); }
+      compare_compact_kernel<<<gridFor(total, left->sm_count), 256, 0, st>>>(child, child_kmer, flag, pos, total, next, new_state, new_kmer);
+      cudaFreeAsync(child, st); cudaFreeAsync(flag, st); cudaFreeAsync(pos, st); cudaFreeAsync(state, st);
+      if(child_kmer) { cudaFreeAsync(child_kmer, st); }
+      if(kmer) { cudaFreeAsync(kmer, st); }
+      state = new_state; kmer = new_kmer; n = next;
+    }
+    if(n > 0)
+    {
+      ull* counts = nullptr; u64 *lflag = nullptr, *rflag = nullptr, *lpos = nullptr, *rpos = nullptr;
+      CK_TRY(cudaMallocAsync((void**)&counts, 3 * sizeof(ull), st));
+      CK_TRY(cudaMemsetAsync(counts, 0, 3 * sizeof(ull), st));
+      if(want)
+      {
+        CK_ALLOC(lflag, n + 1); CK_ALLOC(rflag, n + 1); CK_ALLOC(lpos, n + 1); CK_ALLOC(rpos, n + 1);
+        CK_TRY(cudaMemsetAsync(lflag + n, 0, sizeof(u64), st)); CK_TRY(cudaMemsetAsync(rflag + n, 0, sizeof(u64), st));
+      }
+      compare_classify_kernel<<<gridFor(n, left->sm_count), 256, 0, st>>>(state, n, counts, lflag, rflag);
+      ull host_counts[3] = { 0, 0, 0 };
+      CK_TRY(cudaMemcpyAsync(host_counts, counts, sizeof(host_counts), cudaMemcpyDeviceToHost, st));
+      CK_TRY(cudaStreamSynchronize(st));
+      cudaFreeAsync(counts, st);
+      for(int i = 0; i < 3; i++) { result[i] = host_counts[i]; }
+      if(want)
+      {
+        rc = scanExclusive(lflag, lpos, n + 1, st); if(rc) { goto done; }
+        rc = scanExclusive(rflag, rpos, n + 1, st); if(rc) { goto done; }
+        for(int side = 0; side < 2; side++)
+        {
+          gcsa_b200_kmer_state** target = (side == 0 ? left_kmers : right_kmers);
+          u64 count = result[1 + side];
+          if(target == nullptr || count == 0) { continue; }
+          u64* records = nullptr;
+          CK_ALLOC(records, 8 * count);
+          compare_emit_kernel<<<gridFor(n, left->sm_count), 256, 0, st>>>(state, kmer, n, k, side == 0 ? lflag : rflag, side == 0 ? lpos : rpos, records);
+          gcsa_b200_kmer_state* host = (gcsa_b200_kmer_state*)std::malloc(count * sizeof(gcsa_b200_kmer_state));
+          if(host == nullptr) { rc = fail(GCSA_B200_ERR_NOMEM, "compare_kmers: out of host memory"); cudaFreeAsync(records, st); goto done; }
+          *target = host;
+          CK_TRY(cudaMemcpyAsync(host, records, count * sizeof(gcsa_b200_kmer_state), cudaMemcpyDeviceToHost, st));
+          CK_TRY(cudaStreamSynchronize(st));
+          cudaFreeAsync(records, st);
+        }
+        cudaFreeAsync(lflag, st); cudaFreeAsync(rflag, st); cudaFreeAsync(lpos, st); cudaFreeAsync(rpos, st);
+      }
+    }
+  }
+done:
+  if(state) { cudaFreeAsync(state, st); }
+  if(kmer) { cudaFreeAsync(kmer, st); }
+  #undef CK_TRY
+  #undef CK_ALLOC
+  if(rc != 0)
+  {
+    if(left_kmers && *left_kmers) { std::free(*left_kmers); *left_kmers = nullptr; }
+    if(right_kmers && *right_kmers) { std::free(*right_kmers); *right_kmers = nullptr; }
+  }
+  HOST_EPILOGUE("compare_kmers", rc);
 }
 
 //------------------------------------------------------------------------------

@@ -209,6 +209,33 @@ class GCSA:
         capi.lib().gcsa_b200_free(p)
         return n, arr[:n], arr[n:]
 
+    def verify(self, kmers, lcp=None):
+        """verifyIndex(index, lcp, kmers, kmer_length), src/algorithms.cpp:101-295, batched on the device.
+        kmers: builder.KMers (the construction input).  -> dict of the report; ok iff report["failures"] == 0."""
+        rep = capi.VerifyReport()
+        key, frm = capi.as_u64(kmers.key), capi.as_u64(kmers.from_)
+        capi.check(capi.lib().gcsa_b200_verify_index(self._h, lcp._h if lcp is not None else None, key.ctypes.data, frm.ctypes.data,
+                                                     int(kmers.key.size), int(kmers.k), C.byref(rep)))
+        return {name: getattr(rep, name) for name, _ in capi.VerifyReport._fields_}
+
+    def compare_kmers(self, other, k, include_Ns=False, return_kmers=False):
+        """compareKMers(left, right, k), src/algorithms.cpp:535-616 -> (shared, left only, right only)
+        [, left_kmers, right_kmers as rows of 8 uint64: KMerComparisonState records]."""
+        res = np.zeros(3, dtype=np.uint64)
+        pl, pr = C.c_void_p(), C.c_void_p()
+        capi.check(capi.lib().gcsa_b200_compare_kmers(self._h, other._h, int(k), int(bool(include_Ns)), res.ctypes.data,
+                                                      C.byref(pl) if return_kmers else None, C.byref(pr) if return_kmers else None))
+        counts = tuple(int(x) for x in res)
+        if not return_kmers:
+            return counts
+        def take(p, n):
+            if not p.value or n == 0:
+                return np.zeros((0, 8), dtype=np.uint64)
+            a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(n * 8,)).copy().reshape(n, 8)
+            capi.lib().gcsa_b200_free(p)
+            return a
+        return counts, take(pl, counts[1]), take(pr, counts[2])
+
     # ---- count / locate (gcsa.cpp:802-878) ----
     def count(self, rng):
         return int(self.count_batch([rng[0]], [rng[1]])[0])

@@ -191,6 +191,36 @@ void gcsa_b200_free(void* p);
    ep[0..count) (release with gcsa_b200_free). */
 int gcsa_b200_count_kmers(const gcsa_b200_index* index, uint64_t k, int include_Ns, uint64_t* result, uint64_t** ranges);
 
+/* KMerComparisonState, src/algorithms.cpp:425-460: the record compareKMers() writes to <output>.left /
+   <output>.right -- both ranges, k, and the kmer packed 3 bits per comp in reading order from the right
+   end (comp i of the backward walk at bits [3i, 3i+3)). */
+typedef struct gcsa_b200_kmer_state { uint64_t left_sp, left_ep, right_sp, right_ep, k, kmer[3]; } gcsa_b200_kmer_state;
+
+/* compareKMers(left, right, k, parameters), src/algorithms.cpp:535-616 (declared include/gcsa/algorithms.h:91-97):
+   result[0..3) = kmers in both indexes, only in left, only in right; k <= 64.  If left_kmers / right_kmers are
+   not NULL they receive the unique kmers (result[1] / result[2] records, malloc'ed, release with gcsa_b200_free;
+   order unspecified -- the reference's depends on thread scheduling).  Both handles must be on one device.
+   Like gcsa_b200_count_kmers this does not compare k with order() (parameters.force = true). */
+int gcsa_b200_compare_kmers(const gcsa_b200_index* left, const gcsa_b200_index* right, uint64_t k, int include_Ns,
+                            uint64_t* result, gcsa_b200_kmer_state** left_kmers, gcsa_b200_kmer_state** right_kmers);
+
+/* verifyIndex(index, lcp, kmers, kmer_length), src/algorithms.cpp:101-295 (declared include/gcsa/algorithms.h:40-55),
+   batched: every distinct kmer label of the construction input (keys / from = the KMer records,
+   include/gcsa/support.h:475-497) is searched with find(); parent() must equal the first different range
+   obtained by dropping characters from the right end and depth() must agree; count() must equal the number
+   of distinct start nodes; locate() must return exactly those; locate(range, 10) must return min(10, n) of
+   them.  lcp may be NULL (the parent / depth checks are skipped, like `lcp == 0` in the reference).
+   Returns 0 when the verification ran; the index is correct iff report->failures == 0.  NodeMapping is
+   not supported (identity). */
+typedef struct gcsa_b200_verify_report {
+  uint64_t unique;                      /* distinct labels queried */
+  uint64_t failures;                    /* sum of the stage counters below */
+  uint64_t find_failures, parent_failures, depth_failures, count_failures, locate_failures, random_locate_failures;
+  double   seconds;
+} gcsa_b200_verify_report;
+int gcsa_b200_verify_index(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, const uint64_t* keys,
+                           const uint64_t* from, uint64_t n, int kmer_length, gcsa_b200_verify_report* report);
+
 /* LCPArray, include/gcsa/lcp.h:90-194; load() at src/lcp.cpp:116-143. */
 int  gcsa_b200_lcp_create(const gcsa_flat_lcp* host, int device, gcsa_b200_lcp** out);
 void gcsa_b200_lcp_destroy(gcsa_b200_lcp* lcp);

@@ -668,6 +668,109 @@ uint64_t oracle_count_kmers(const oracle_gcsa* g, uint64_t k, int include_Ns, in
 }
 
 /* ------------------------------------------------------------------------------------------
+   compareKMers -- src/algorithms.cpp:425-616 (KMerComparisonState, KMerSymmetricDifference,
+   processSubtrees): the trie of both indexes walked in lockstep; a state lives while either
+   side is non-empty; at depth k it is shared, left-only or right-only.
+   ------------------------------------------------------------------------------------------ */
+
+/* KMerComparisonState::set, algorithms.cpp:451-457: comp i of the kmer (read right to left), 3 bits each */
+static void cmp_set(uint64_t* kmer, uint64_t i, uint64_t comp)
+{
+  uint64_t offset = (i * 3) >> 6, bit = (i * 3) & 63;
+  kmer[offset] |= comp << bit;
+  if(bit > 61) { kmer[offset + 1] |= comp >> (64 - bit); }      /* the reference ORs 0 when nothing overflows */
+}
+
+typedef struct { oracle_kmer_cmp* left; oracle_kmer_cmp* right; uint64_t n_left, n_right, cap_left, cap_right; } cmp_lists;
+
+static void cmp_push(oracle_kmer_cmp** list, uint64_t* n, uint64_t* cap, const oracle_kmer_cmp* state)
+{
+  if(*n == *cap) { *cap = (*cap ? *cap * 2 : 64); *list = (oracle_kmer_cmp*)realloc(*list, *cap * sizeof(oracle_kmer_cmp)); }
+  (*list)[(*n)++] = *state;
+}
+
+/* processSubtrees (algorithms.cpp:505-533).  collect != NULL: KMerSeedCollector (report = keep the state);
+   else KMerSymmetricDifference (algorithms.cpp:488-500) into counts[3] and, if lists != NULL, the unique kmers. */
+static void process_subtrees(const oracle_gcsa* left, const oracle_gcsa* right, oracle_kmer_cmp start, uint64_t depth, int include_Ns,
+                             oracle_kmer_cmp** collect, uint64_t* collected, uint64_t* collect_cap, uint64_t* counts, cmp_lists* lists)
+{
+  uint64_t size = 0, cap = 64;
+  oracle_kmer_cmp* stack = (oracle_kmer_cmp*)malloc(cap * sizeof(oracle_kmer_cmp));
+  stack[size++] = start;
+  uint64_t lpred[2 * ORACLE_SIGMA], rpred[2 * ORACLE_SIGMA];
+  uint64_t limit = (include_Ns ? left->sigma : left->fast_chars + 2);
+  while(size > 0)
+  {
+    oracle_kmer_cmp curr = stack[--size];
+    int lempty = range_empty(curr.left_sp, curr.left_ep), rempty = range_empty(curr.right_sp, curr.right_ep);
+    if(lempty && rempty) { continue; }
+    if(curr.k == depth)
+    {
+      if(collect != NULL) { cmp_push(collect, collected, collect_cap, &curr); }
+      else
+      {
+        uint64_t llen = curr.left_ep + 1 - curr.left_sp, rlen = curr.right_ep + 1 - curr.right_sp;    /* Range::length */
+        if(llen > 0 && rlen > 0) { counts[0]++; }
+        else if(llen > 0 && rlen == 0) { counts[1]++; if(lists) { cmp_push(&lists->left, &lists->n_left, &lists->cap_left, &curr); } }
+        else if(llen == 0 && rlen > 0) { counts[2]++; if(lists) { cmp_push(&lists->right, &lists->n_right, &lists->cap_right, &curr); } }
+      }
+    }
+    if(curr.k < depth)
+    {
+      if(include_Ns) { oracle_lf_all(left, curr.left_sp, curr.left_ep, lpred); oracle_lf_all(right, curr.right_sp, curr.right_ep, rpred); }
+      else { oracle_lf_fast(left, curr.left_sp, curr.left_ep, lpred); oracle_lf_fast(right, curr.right_sp, curr.right_ep, rpred); }
+      for(uint64_t comp = 1; comp + 1 < limit; comp++)
+      {
+        if(size == cap) { cap *= 2; stack = (oracle_kmer_cmp*)realloc(stack, cap * sizeof(oracle_kmer_cmp)); }
+        oracle_kmer_cmp next = curr;
+        next.left_sp = lpred[2 * comp]; next.left_ep = lpred[2 * comp + 1];
+        next.right_sp = rpred[2 * comp]; next.right_ep = rpred[2 * comp + 1];
+        next.k = curr.k + 1;
+        cmp_set(next.kmer, curr.k, comp);
+        stack[size++] = next;
+      }
+    }
+  }
+  free(stack);
+}
+
+/* compareKMers (algorithms.cpp:535-616): result = (shared, left only, right only); the unique kmers
+   (what the reference writes to <output>.left / .right) are returned malloc'ed if asked for. */
+void oracle_compare_kmers(const oracle_gcsa* left, const oracle_gcsa* right, uint64_t k, int include_Ns, int threads,
+                          uint64_t* result, oracle_kmer_cmp** left_kmers, oracle_kmer_cmp** right_kmers)
+{
+  result[0] = result[1] = result[2] = 0;
+  if(left_kmers) { *left_kmers = NULL; }
+  if(right_kmers) { *right_kmers = NULL; }
+  if(k == 0) { result[0] = 1; return; }
+  if(k > 64) { return; }                                           /* KMerComparisonState::MAX_K */
+  if(threads < 1) { threads = 1; }
+  oracle_kmer_cmp* seeds = NULL; uint64_t n_seeds = 0, cap = 0;
+  oracle_kmer_cmp root; memset(&root, 0, sizeof(root));
+  root.left_ep = left->path_nodes - 1; root.right_ep = right->path_nodes - 1;
+  process_subtrees(left, right, root, (k < 5 ? k : 5), include_Ns, &seeds, &n_seeds, &cap, NULL, NULL);
+  cmp_lists all; memset(&all, 0, sizeof(all));
+  int want = (left_kmers != NULL || right_kmers != NULL);
+  #pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+  for(uint64_t i = 0; i < n_seeds; i++)
+  {
+    uint64_t counts[3] = { 0, 0, 0 };
+    cmp_lists mine; memset(&mine, 0, sizeof(mine));
+    process_subtrees(left, right, seeds[i], k, include_Ns, NULL, NULL, NULL, counts, want ? &mine : NULL);
+    #pragma omp critical
+    {
+      result[0] += counts[0]; result[1] += counts[1]; result[2] += counts[2];
+      for(uint64_t j = 0; j < mine.n_left; j++) { cmp_push(&all.left, &all.n_left, &all.cap_left, &mine.left[j]); }
+      for(uint64_t j = 0; j < mine.n_right; j++) { cmp_push(&all.right, &all.n_right, &all.cap_right, &mine.right[j]); }
+    }
+    free(mine.left); free(mine.right);
+  }
+  free(seeds);
+  if(left_kmers) { *left_kmers = all.left; } else { free(all.left); }
+  if(right_kmers) { *right_kmers = all.right; } else { free(all.right); }
+}
+
+/* ------------------------------------------------------------------------------------------
    LCPArray -- include/gcsa/lcp.h:137-178, src/lcp.cpp:152-200 (tree arithmetic), 276-519
    ------------------------------------------------------------------------------------------ */
 

@@ -133,6 +133,12 @@ int    oracle_max_threads(void);
 /* countKMers(index, k), src/algorithms.cpp:387-421 */
 uint64_t oracle_count_kmers(const oracle_gcsa* g, uint64_t k, int include_Ns, int threads);
 
+/* KMerComparisonState, src/algorithms.cpp:425-460 (the record compareKMers writes to .left / .right) */
+typedef struct oracle_kmer_cmp { uint64_t left_sp, left_ep, right_sp, right_ep, k, kmer[3]; } oracle_kmer_cmp;
+/* compareKMers, src/algorithms.cpp:535-616; result[3] = shared, left only, right only */
+void oracle_compare_kmers(const oracle_gcsa* left, const oracle_gcsa* right, uint64_t k, int include_Ns, int threads,
+                          uint64_t* result, oracle_kmer_cmp** left_kmers, oracle_kmer_cmp** right_kmers);
+
 /* LCP queries */
 void     oracle_lcp_parent(const oracle_lcp* l, uint64_t sp, uint64_t ep, oracle_stnode* out);
 uint64_t oracle_lcp_depth(const oracle_lcp* l, uint64_t sp, uint64_t ep);

@@ -99,6 +99,8 @@ def lib():
     L.oracle_locate_batch.argtypes = [vp, vp, vp, u64, vp, C.POINTER(u64p), C.c_int]
     L.oracle_max_threads.restype = C.c_int
     L.oracle_count_kmers.restype = u64; L.oracle_count_kmers.argtypes = [vp, u64, C.c_int, C.c_int]
+    L.oracle_compare_kmers.restype = None
+    L.oracle_compare_kmers.argtypes = [vp, vp, u64, C.c_int, C.c_int, vp, C.POINTER(vp), C.POINTER(vp)]
     L.oracle_lcp_parent.argtypes = [vp, u64, u64, C.POINTER(STNode)]
     L.oracle_lcp_depth.restype = u64; L.oracle_lcp_depth.argtypes = [vp, u64, u64]
     for name in ("psv", "psev", "nsv", "nsev"):
@@ -251,6 +253,22 @@ class OracleGCSA:
     def count_kmers(self, k, include_Ns=False, threads=1):
         """countKMers(index, k), src/algorithms.cpp:387-421."""
         return lib().oracle_count_kmers(self._h, int(k), int(bool(include_Ns)), int(threads))
+
+    def compare_kmers(self, other, k, include_Ns=False, threads=1):
+        """compareKMers(left, right, k), src/algorithms.cpp:535-616 -> ((shared, left, right), left_kmers, right_kmers);
+        the kmer arrays hold KMerComparisonState records as rows of 8 uint64 (left range, right range, k, kmer[3])."""
+        res = np.zeros(3, dtype=np.uint64)
+        pl, pr = C.c_void_p(), C.c_void_p()
+        lib().oracle_compare_kmers(self._h, other._h, int(k), int(bool(include_Ns)), int(threads), res.ctypes.data, C.byref(pl), C.byref(pr))
+        def take(p, n):
+            if not p or n == 0:
+                return np.zeros((0, 8), dtype=np.uint64)
+            a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(n * 8,)).copy().reshape(n, 8)
+            return a
+        left, right = take(pl, int(res[1])), take(pr, int(res[2]))
+        libc = C.CDLL(None); libc.free.argtypes = [C.c_void_p]
+        libc.free(pl); libc.free(pr)
+        return tuple(int(x) for x in res), left, right
 
     # ---- batch drivers (timed CPU baseline) ----
     def find_batch(self, chars, offsets, threads=1, stats=False):

@@ -278,4 +278,14 @@ std::uint64_t ref_count_kmers(const RefIndex* r, std::uint64_t k, int include_Ns
   return countKMers(r->index, k, parameters);
 }
 
+/* compareKMers(left, right, k, parameters), src/algorithms.cpp:535-616 */
+void ref_compare_kmers(const RefIndex* left, const RefIndex* right, std::uint64_t k, int include_Ns, std::uint64_t* result)
+{
+  KMerSearchParameters parameters;
+  parameters.include_Ns = (include_Ns != 0);
+  parameters.force = true;
+  std::array<size_type, 3> res = compareKMers(left->index, right->index, k, parameters);
+  result[0] = res[0]; result[1] = res[1]; result[2] = res[2];
+}
+
 } // extern "C"

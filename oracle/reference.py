@@ -66,6 +66,7 @@ def lib():
     L.ref_depth_batch.argtypes = [vp, vp, vp, u64, vp]
     L.ref_lcp_query.argtypes = [vp, C.c_int, vp, vp, u64, vp, vp]
     L.ref_count_kmers.restype = u64; L.ref_count_kmers.argtypes = [vp, u64, C.c_int]
+    L.ref_compare_kmers.restype = None; L.ref_compare_kmers.argtypes = [vp, vp, u64, C.c_int, vp]
     _lib = L
     return L
 
@@ -200,3 +201,9 @@ class ReferenceIndex:
 
     def count_kmers(self, k, include_Ns=False):
         return int(lib().ref_count_kmers(self._h, int(k), int(bool(include_Ns))))
+
+    def compare_kmers(self, other, k, include_Ns=False):
+        """compareKMers(left, right, k) of the reference -> (shared, left only, right only)."""
+        res = np.zeros(3, dtype=np.uint64)
+        lib().ref_compare_kmers(self._h, other._h, int(k), int(bool(include_Ns)), res.ctypes.data)
+        return tuple(int(x) for x in res)
