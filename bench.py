@@ -291,6 +291,13 @@ def main():
     h_chars = torch.from_numpy(chars).pin_memory()
     h_sp = torch.empty(n, dtype=torch.int64).pin_memory(); h_ep = torch.empty(n, dtype=torch.int64).pin_memory()
 
+    # Host threads this rank may spend on 2-bit packing before the H2D copy (gcsa2_b200/csrc/pack.cpp):
+    # the box's cores divided among the ranks; below 16 per rank the byte path is faster (the library's own rule).
+    if "GCSA_B200_HOST_PACK" not in os.environ:
+        per_rank = max(1, (os.cpu_count() or 1) // world)
+        os.environ["GCSA_B200_HOST_PACK"] = str(per_rank if per_rank >= 16 else 0)
+    pack_threads = int(os.environ["GCSA_B200_HOST_PACK"] or 0)
+
     def step_e2e():
         index.find_fixed_host_raw(h_chars.data_ptr(), length, n, h_sp.data_ptr(), h_ep.data_ptr())
 
@@ -341,7 +348,10 @@ def main():
             "found": total_found, "queries": total_q,
             "e2e": {"value": total_q / (e2e_ms / 1000.0), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(n * length), "d2h_bytes_per_step": int(n * 16),
-                    "api": "gcsa_b200_find_fixed_host (pinned host buffers, chunked H2D/kernel/D2H pipeline)",
+                    "api": "gcsa_b200_find_fixed_host (pinned host buffers, chunked H2D/kernel/D2H pipeline%s)" % (
+                        "; patterns 2-bit packed by %d host threads before the copy, %d B/query cross PCIe instead of %d" % (
+                            pack_threads, 8 * ((length + 31) // 32), length) if pack_threads > 0 else ""),
+                    "host_pack_threads": pack_threads,
                     "matches_device_leg": e2e_same},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

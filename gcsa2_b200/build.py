@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgcsa2_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include", "gcsa2_b200.h")
-HOST_SOURCES = ["builder.cpp", "gcsa_file.cpp", "verify.cpp"]      # host-side C++ (g++)
+HOST_SOURCES = ["builder.cpp", "gcsa_file.cpp", "verify.cpp", "pack.cpp"]      # host-side C++ (g++)
 
 NVCC = os.environ.get("GCSA_B200_NVCC", "nvcc")
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"

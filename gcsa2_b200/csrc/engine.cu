@@ -31,6 +31,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <omp.h>
 #include <random>
 #include <string>
 #include <unordered_set>
@@ -327,14 +328,20 @@ struct FindStatsDev { u64 found, total_length, lf_steps, sector_probes, table_hi
   range became empty (or whose pattern is exhausted) is refilled on the next step, the
   assignment being computed with one ballot + popc (no atomics, no shared memory).
 */
-template<bool STATS, int MIN_BLOCKS>
+template<bool STATS, int MIN_BLOCKS, bool PACKED = false>
 __global__ void __launch_bounds__(256, MIN_BLOCKS)
 find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict__ offsets, u64 char_base,
             u64 fixed_length, u64 n, u64* __restrict__ sp_out, u64* __restrict__ ep_out, FindStatsDev* stats)
 {
+  // PACKED: `chars` holds ceil(fixed_length / 32) 64-bit words per pattern, character p of a pattern at bits
+  // [2 (p % 32), 2 (p % 32) + 2) of word p / 32, value comp - 1 (ACGT only; packed by the host entry point).
   __shared__ u8 c2c[256];
-  for(int i = threadIdx.x; i < 256; i += blockDim.x) { c2c[i] = v.char2comp[i]; }
-  __syncthreads();
+  if(!PACKED)
+  {
+    for(int i = threadIdx.x; i < 256; i += blockDim.x) { c2c[i] = v.char2comp[i]; }
+    __syncthreads();
+  }
+  const u64 words_per_pattern = (fixed_length + 31) >> 5;
 
   const u32 lane = threadIdx.x & 31;
   const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -349,6 +356,17 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
   bool live = false;
   CharWindow win;
   u64 st_found = 0, st_len = 0, st_steps = 0, st_sectors = 0, st_hits = 0;
+  // comp value of the character at (batch-wide) position p of the current query
+  auto comp_at = [&](u64 p) -> u32
+  {
+    if(PACKED)
+    {
+      u64 rel = p - begin, wi = q * words_per_pattern + (rel >> 5);
+      if(wi != win.index) { win.word = __ldcs((const unsigned long long*)chars + wi); win.index = wi; }
+      return (u32)((win.word >> ((rel & 31) * 2)) & 3) + 1;
+    }
+    return c2c[win.get(chars, p)];
+  };
 
   while(true)
   {
@@ -377,7 +395,7 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
               u64 idx = 0; bool ok = true;
               for(int t = 0; t < v.table_k; t++)
               {
-                u32 c = c2c[win.get(chars, e - 1 - t)];
+                u32 c = comp_at(e - 1 - t);
                 ok = ok && (c >= 1 && c <= 4);
                 idx |= (u64)((c - 1) & 3) << (2 * t);
               }
@@ -394,7 +412,7 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
             }
             if(!used_table)
             {
-              u32 c = c2c[win.get(chars, pos)];
+              u32 c = comp_at(pos);
               sp = v.char_sp[c]; ep = v.char_ep[c];
             }
           }
@@ -415,12 +433,12 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
       }
       else
       {
-        u32 c = c2c[win.get(chars, pos - 1)];
+        u32 c = comp_at(pos - 1);
         u32 sectors = 0;
         bool done = false;
         if(v.bwt2 != nullptr && pos - begin >= 2 && c >= 1 && c <= 4)
         {
-          u32 c1 = c2c[win.get(chars, pos - 2)];
+          u32 c1 = comp_at(pos - 2);
           if(c1 >= 1 && c1 <= 4 && lf2_range(v, sp, ep, c1, c, sp, ep, STATS ? &sectors : nullptr))
           {
             pos -= 2; done = true;
@@ -1259,6 +1277,42 @@ struct gcsa_b200_index
   std::vector<void*> allocations;
   u64 device_bytes = 0;
   gcsa_flat_index header;            // scalars only (pointers nulled)
+
+  // Host-side 2-bit packing of fixed-length patterns (pack.cpp): byte -> comp - 1 or 0xFF, and
+  // whether that table is exactly ACGT / acgt.  Pinned staging buffers are pooled per handle.
+  u8 pack_code[256];
+  bool pack_default = false;
+  mutable std::mutex pool_mutex;
+  mutable std::vector<std::pair<void*, size_t>> pinned_pool;
+
+  void* takePinned(size_t bytes) const
+  {
+    {
+      std::lock_guard<std::mutex> lock(pool_mutex);
+      for(size_t i = 0; i < pinned_pool.size(); i++)
+      {
+        if(pinned_pool[i].second >= bytes)
+        {
+          void* p = pinned_pool[i].first;
+          pinned_pool.erase(pinned_pool.begin() + i);
+          return p;
+        }
+      }
+    }
+    void* p = nullptr;
+    if(cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    sizes_add(p, bytes);
+    return p;
+  }
+  void givePinned(void* p) const
+  {
+    std::lock_guard<std::mutex> lock(pool_mutex);
+    size_t bytes = 0;
+    for(auto& e : pinned_sizes) { if(e.first == p) { bytes = e.second; } }
+    pinned_pool.push_back(std::make_pair(p, bytes));
+  }
+  void sizes_add(void* p, size_t bytes) const { std::lock_guard<std::mutex> lock(pool_mutex); pinned_sizes.push_back(std::make_pair(p, bytes)); }
+  mutable std::vector<std::pair<void*, size_t>> pinned_sizes;     // every pinned buffer ever allocated for this handle
 };
 
 struct gcsa_b200_lcp
@@ -1450,6 +1504,18 @@ int gcsa_b200_index_create(const gcsa_flat_index* host, int device, const gcsa_b
   v.path_nodes = N; v.edge_count = host->edge_count;
   for(int c = 0; c <= GCSA_B200_SIGMA; c++) { v.C[c] = host->C[c]; }
   std::memcpy(v.char2comp, host->char2comp, 256);
+  {
+    u8 def[256]; gcsa_b200_default_char2comp(def);
+    idx->pack_default = true;
+    for(int i = 0; i < 256; i++)
+    {
+      u8 c = host->char2comp[i];
+      bool fast = (c >= 1 && c <= GCSA_B200_FAST_CHARS);
+      idx->pack_code[i] = (fast ? (u8)(c - 1) : (u8)0xFF);
+      bool def_fast = (def[i] >= 1 && def[i] <= GCSA_B200_FAST_CHARS);
+      if(fast != def_fast || (fast && c != def[i])) { idx->pack_default = false; }
+    }
+  }
   for(int i = 0; i < 256; i++) { if(v.char2comp[i] >= GCSA_B200_SIGMA) { delete idx; return fail(GCSA_B200_ERR_INVALID, "index_create: char2comp value out of range"); } }
 
   int rc = 0;
@@ -1662,6 +1728,7 @@ void gcsa_b200_index_destroy(gcsa_b200_index* index)
   if(index == nullptr) { return; }
   DeviceGuard guard(index->device);
   for(void* p : index->allocations) { cudaFree(p); }
+  for(auto& e : index->pinned_sizes) { cudaFreeHost(e.first); }
   delete index;
 }
 
@@ -1690,7 +1757,7 @@ int gcsa_b200_char_range(const gcsa_b200_index* index, uint64_t comp, uint64_t* 
 //------------------------------------------------------------------------------
 
 static int launchFind(const gcsa_b200_index* index, const u8* d_chars, const u64* d_offsets, u64 char_base, u64 fixed_length,
-                      u64 n, u64* d_sp, u64* d_ep, FindStatsDev* d_stats, cudaStream_t stream)
+                      u64 n, u64* d_sp, u64* d_ep, FindStatsDev* d_stats, cudaStream_t stream, bool packed = false)
 {
   if(n == 0) { return 0; }
   // persistent grid: 5 CTAs of 256 threads per SM by default (40+ registers without spills measured
@@ -1699,7 +1766,11 @@ static int launchFind(const gcsa_b200_index* index, const u8* d_chars, const u64
   int per_sm = (min_blocks >= 8 ? 8 : (min_blocks <= 4 ? 4 : min_blocks));
   int grid = gridFor(n, index->sm_count, per_sm);
   #define LAUNCH_FIND(S, B) find_kernel<S, B><<<grid, 256, 0, stream>>>(index->view, d_chars, d_offsets, char_base, fixed_length, n, d_sp, d_ep, d_stats)
-  if(d_stats) { LAUNCH_FIND(true, 1); }
+  if(packed)
+  {
+    find_kernel<false, 5, true><<<gridFor(n, index->sm_count, 5), 256, 0, stream>>>(index->view, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, nullptr);
+  }
+  else if(d_stats) { LAUNCH_FIND(true, 1); }
   else if(per_sm == 8) { LAUNCH_FIND(false, 8); }
   else if(per_sm == 5) { LAUNCH_FIND(false, 5); }
   else if(per_sm == 4) { LAUNCH_FIND(false, 4); }
@@ -1735,6 +1806,17 @@ int gcsa_b200_find_fixed_batch(const gcsa_b200_index* index, const uint8_t* d_ch
   Host-buffer find: the batch is cut into chunks that are pipelined over three streams
   (H2D of chunk i+1 overlaps the kernel of chunk i and the D2H of chunk i-1).
 */
+// Host threads for 2-bit packing in the host entry point of find(); 0 = do not pack.
+// GCSA_B200_HOST_PACK=0 disables, =N forces N threads; by default packing is used when this process
+// has at least 16 OpenMP threads (fewer cannot keep up with a PCIe 5 x16 link at 4 input bytes per packed one).
+static int hostPackThreads()
+{
+  const char* e = std::getenv("GCSA_B200_HOST_PACK");
+  if(e != nullptr && *e != 0) { int v = std::atoi(e); return (v < 0 ? 0 : v); }
+  int t = omp_get_max_threads();
+  return (t >= 16 ? t : 0);
+}
+
 static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const uint64_t* offsets, uint64_t fixed_length,
                     uint64_t n, uint64_t* sp, uint64_t* ep, gcsa_b200_find_stats* stats)
 {
@@ -1748,29 +1830,61 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
 
   // Chunks of >= 1 M queries, at most ~8 per batch: large enough for PCIe to reach its streaming
   // rate, enough of them for the copy engines and the SMs to overlap.
+  // With host cores to spare, fixed-length batches are 2-bit packed on the host first (pack.cpp):
+  // 4x fewer bytes over PCIe, which is what bounds this entry point; a chunk containing any character
+  // other than ACGT/acgt goes through the byte path.  Finer chunks then, so that packing chunk i+1
+  // overlaps the transfers of chunk i.
   const int STREAMS = 3;
-  const u64 CHUNK = std::max<u64>(1ull << 20, (n + 7) / 8);
+  const int pack_threads = hostPackThreads();
+  const bool pack = (pack_threads > 0 && fixed_length > 0 && offsets == nullptr && stats == nullptr && n >= (1u << 16));
+  const u64 CHUNK = (pack ? std::max<u64>(1ull << 18, (n + 15) / 16) : std::max<u64>(1ull << 20, (n + 7) / 8));
+  const u64 words_per_pattern = (fixed_length + 31) / 32;
   cudaStream_t streams[STREAMS];
   for(int s = 0; s < STREAMS; s++) { CUDA_TRY(cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking)); }
   FindStatsDev* d_stats = nullptr;
   if(stats) { CUDA_TRY(cudaMalloc(&d_stats, sizeof(FindStatsDev))); CUDA_TRY(cudaMemset(d_stats, 0, sizeof(FindStatsDev))); }
+  u64* staging[STREAMS] = { nullptr, nullptr, nullptr };
+  cudaEvent_t staged[STREAMS] = { nullptr, nullptr, nullptr };
+  bool use_pack = pack;
+  if(use_pack)
+  {
+    for(int s = 0; s < STREAMS; s++)
+    {
+      staging[s] = (u64*)index->takePinned(CHUNK * words_per_pattern * sizeof(u64));
+      if(staging[s] == nullptr || cudaEventCreateWithFlags(&staged[s], cudaEventDisableTiming) != cudaSuccess) { use_pack = false; }
+    }
+  }
 
   int rc = 0;
   u64 n_chunks = (n + CHUNK - 1) / CHUNK;
   for(u64 c = 0; c < n_chunks && rc == 0; c++)
   {
-    cudaStream_t st = streams[c % STREAMS];
+    const int slot = (int)(c % STREAMS);
+    cudaStream_t st = streams[slot];
     u64 q0 = c * CHUNK, q1 = std::min(n, q0 + CHUNK), m = q1 - q0;
     u64 c0 = (offsets ? offsets[q0] : q0 * fixed_length), c1 = (offsets ? offsets[q1] : q1 * fixed_length), bytes = c1 - c0;
+    bool packed = false;
+    if(use_pack)
+    {
+      if(c >= (u64)STREAMS) { cudaEventSynchronize(staged[slot]); }          // the slot's previous copy has left the buffer
+      packed = (gcsa_b200_internal_pack_patterns(chars + c0, m, fixed_length, index->pack_code, index->pack_default ? 1 : 0,
+                                                 staging[slot], pack_threads) != 0);
+    }
+    if(packed) { bytes = m * words_per_pattern * sizeof(u64); }
     u8* d_chars = nullptr; u64* d_off = nullptr; u64* d_res = nullptr;
     cudaError_t e;
     if((e = cudaMallocAsync(&d_chars, bytes + 16, st)) != cudaSuccess ||
        (offsets && (e = cudaMallocAsync(&d_off, (m + 1) * sizeof(u64), st)) != cudaSuccess) ||
        (e = cudaMallocAsync(&d_res, 2 * m * sizeof(u64), st)) != cudaSuccess)
     { rc = fail(GCSA_B200_ERR_NOMEM, std::string("find_host: ") + cudaGetErrorString(e)); break; }
-    if(bytes) { cudaMemcpyAsync(d_chars, chars + c0, bytes, cudaMemcpyHostToDevice, st); }
+    if(packed)
+    {
+      cudaMemcpyAsync(d_chars, staging[slot], bytes, cudaMemcpyHostToDevice, st);
+      cudaEventRecord(staged[slot], st);
+    }
+    else if(bytes) { cudaMemcpyAsync(d_chars, chars + c0, bytes, cudaMemcpyHostToDevice, st); }
     if(offsets) { cudaMemcpyAsync(d_off, offsets + q0, (m + 1) * sizeof(u64), cudaMemcpyHostToDevice, st); }
-    rc = launchFind(index, d_chars, d_off, c0, fixed_length, m, d_res, d_res + m, d_stats, st);
+    rc = launchFind(index, d_chars, d_off, c0, fixed_length, m, d_res, d_res + m, d_stats, st, packed);
     cudaMemcpyAsync(sp + q0, d_res, m * sizeof(u64), cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(ep + q0, d_res + m, m * sizeof(u64), cudaMemcpyDeviceToHost, st);
     cudaFreeAsync(d_chars, st); if(d_off) { cudaFreeAsync(d_off, st); } cudaFreeAsync(d_res, st);
@@ -1789,7 +1903,12 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
     stats->sector_probes = h.sector_probes; stats->table_hits = h.table_hits;
   }
   if(d_stats) { cudaFree(d_stats); }
-  for(int s = 0; s < STREAMS; s++) { cudaStreamDestroy(streams[s]); }
+  for(int s = 0; s < STREAMS; s++)
+  {
+    cudaStreamDestroy(streams[s]);
+    if(staged[s]) { cudaEventDestroy(staged[s]); }
+    if(staging[s]) { index->givePinned(staging[s]); }
+  }
   if(rc) { return rc; }
   if(err != cudaSuccess) { return fail(GCSA_B200_ERR_CUDA, std::string("find_host: ") + cudaGetErrorString(err)); }
   return 0;

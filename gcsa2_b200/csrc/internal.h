@@ -2,12 +2,21 @@
 #ifndef GCSA2_B200_INTERNAL_H
 #define GCSA2_B200_INTERNAL_H
 
+#include <stdint.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
 
 /* Sets the calling thread's gcsa_b200_last_error() message (defined in engine.cu). */
 void gcsa_b200_internal_set_error(const char* message);
+
+/* pack.cpp: 2-bit packs n patterns of `length` bytes into ceil(length / 32) words each (character p of a
+   pattern at bits [2 (p % 32), +2) of word p / 32).  code[256] maps a byte to comp - 1 for the four fast
+   characters and to 0xFF otherwise; default_alphabet != 0 says the table is exactly ACGT/acgt (enables the
+   AVX2 path).  Returns 1 if every byte was a fast character, else 0 (the output is then unusable). */
+int gcsa_b200_internal_pack_patterns(const uint8_t* chars, uint64_t n, uint64_t length, const uint8_t* code,
+                                     int default_alphabet, uint64_t* out, int threads);
 
 #ifdef __cplusplus
 }

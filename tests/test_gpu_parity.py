@@ -289,3 +289,42 @@ def test_full_size_config2_properties():
     offsets = np.arange(k + 1, dtype=np.uint64) * np.uint64(length)
     osp, oep, _ = ora.find_batch(chars[:k * length], offsets, threads=8)
     assert (osp == ref[0][:k]).all() and (oep == ref[1][:k]).all()
+
+
+def test_host_packed_find_equals_byte_path(monkeypatch):
+    """gcsa_b200_find_fixed_host with host-side 2-bit packing (pack.cpp + find_kernel<.., PACKED>) gives the
+    same ranges as the byte path and the oracle: lengths on and off the 32-character word boundary, mixed
+    case, random (early-exit) patterns, and a batch where one chunk holds an N and must fall back."""
+    seq = synth.random_sequence(300_000, seed=41)
+    flat, _, _ = build_index(synth.linear_graph(seq), 16, 3)
+    ora = orc.OracleGCSA(flat)
+    for table_k in (0, 6):
+        gpu = GCSA(flat, kmer_table_k=table_k)
+        for length in (20, 32, 45, 64, 100):
+            n = 600_000
+            chars, offsets = synth.patterns_from_sequence(seq, n, length, seed=length)
+            chars = chars.copy()
+            rnd, _ = synth.random_patterns(n // 4, length, seed=length + 1)
+            chars[: rnd.size] = rnd                                   # the first quarter: uniform random patterns
+            lower = np.random.default_rng(length).random(chars.size) < 0.3
+            chars[lower] |= 0x20                                      # acgt
+            monkeypatch.setenv("GCSA_B200_HOST_PACK", "0")
+            bsp, bep = gpu.find_fixed_batch(chars, length)
+            monkeypatch.setenv("GCSA_B200_HOST_PACK", "4")
+            psp, pep = gpu.find_fixed_batch(chars, length)
+            assert (psp == bsp).all() and (pep == bep).all(), (table_k, length)
+            osp, oep, _ = ora.find_batch(chars[: 50_000 * length], offsets[: 50_001], threads=4)
+            assert (psp[:50_000] == osp).all() and (pep[:50_000] == oep).all()
+            if length == 32:
+                dirty = chars.copy()
+                dirty[300_000 * length + 7] = ord("N")                # second chunk of three
+                dirty[599_999 * length + 31] = ord("$")
+                monkeypatch.setenv("GCSA_B200_HOST_PACK", "0")
+                bsp, bep = gpu.find_fixed_batch(dirty, length)
+                monkeypatch.setenv("GCSA_B200_HOST_PACK", "4")
+                psp, pep = gpu.find_fixed_batch(dirty, length)
+                assert (psp == bsp).all() and (pep == bep).all()
+                q = np.array([300_000, 599_999])
+                pats = [bytes(dirty[i * length:(i + 1) * length]) for i in q]
+                for i, pat in zip(q, pats):
+                    assert (int(psp[i]), int(pep[i])) == ora.find(pat)
