@@ -291,12 +291,8 @@ def main():
     h_chars = torch.from_numpy(chars).pin_memory()
     h_sp = torch.empty(n, dtype=torch.int64).pin_memory(); h_ep = torch.empty(n, dtype=torch.int64).pin_memory()
 
-    # Host threads this rank may spend on 2-bit packing before the H2D copy (gcsa2_b200/csrc/pack.cpp):
-    # the box's cores divided among the ranks; below 16 per rank the byte path is faster (the library's own rule).
-    if "GCSA_B200_HOST_PACK" not in os.environ:
-        per_rank = max(1, (os.cpu_count() or 1) // world)
-        os.environ["GCSA_B200_HOST_PACK"] = str(per_rank if per_rank >= 16 else 0)
-    pack_threads = int(os.environ["GCSA_B200_HOST_PACK"] or 0)
+    # Host-side 2-bit packing before the H2D copy (gcsa2_b200/csrc/pack.cpp) is opt-in: GCSA_B200_HOST_PACK=threads.
+    pack_threads = int(os.environ.get("GCSA_B200_HOST_PACK") or 0)
 
     def step_e2e():
         index.find_fixed_host_raw(h_chars.data_ptr(), length, n, h_sp.data_ptr(), h_ep.data_ptr())
