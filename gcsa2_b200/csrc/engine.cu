@@ -34,6 +34,7 @@
 #include <omp.h>
 #include <random>
 #include <string>
+#include <unordered_map>
 #include <unordered_set>
 #include <vector>
 
@@ -82,6 +83,7 @@ struct DevView
   const u64* stored_samples; const u64* sample_start; u64 sample_count;
   const u64* table; int table_k;      // entry = sp | length << 40; length 0xFFFFFF = not tabulated
   const u32* walk32; const u64* walk64; // locate walk table: LF(i) << 1, or rank(sampled, i) << 1 | 1 for sampled nodes
+  const u64* loc64;                    // locate table: bit 63 | value for nodes with one start position, else rank of the sampled node << 24 | steps
   u8 char2comp[256];
 };
 
@@ -868,6 +870,43 @@ locate_lengths_kernel(u64 path_nodes, const u64* __restrict__ sp, const u64* __r
   }
 }
 
+// Last r in [0, n) with off[r] <= t (off[0] = 0), starting from a guess: gallop, then bisect.  With
+// ranges of similar length the guess is off by a few entries and the search costs 2-3 loads
+// instead of log2(n).
+__device__ __forceinline__ u64 owner_of(const u64* __restrict__ off, u64 n, u64 t, u64 guess)
+{
+  u64 g = (guess < n ? guess : n - 1), lo, hi;
+  if(__ldg(off + g) <= t)
+  {
+    lo = g;
+    u64 step = 1;
+    while(true)
+    {
+      u64 nxt = lo + step;
+      if(nxt > n - 1) { hi = n - 1; break; }
+      if(__ldg(off + nxt) <= t) { lo = nxt; step <<= 1; } else { hi = nxt - 1; break; }
+    }
+  }
+  else
+  {
+    u64 cur = g, step = 1;
+    while(true)
+    {
+      u64 nxt = (cur >= step ? cur - step : 0);
+      if(__ldg(off + nxt) <= t) { lo = nxt; hi = cur - 1; break; }
+      cur = nxt; step <<= 1;
+    }
+  }
+  while(lo < hi)
+  {
+    u64 mid = lo + (hi - lo + 1) / 2;
+    if(__ldg(off + mid) <= t) { lo = mid; } else { hi = mid - 1; }
+  }
+  return lo;
+}
+
+#define LOC_DIRECT 0xFFFFFFFFu          // steps marker: `first` holds the value itself (locate table, single-valued node)
+
 /*
   One thread per (range, node): walk LF until a sampled node (locateInternal, gcsa.cpp:882-887),
   remember (first sample, steps) and how many values the node stores (firstSample, gcsa.h:202-206;
@@ -877,19 +916,21 @@ __global__ void __launch_bounds__(256)
 locate_walk_kernel(const DevView v, const u64* __restrict__ sp, const u64* __restrict__ node_off, u64 n, u64 items,
                    u64* __restrict__ first, u32* __restrict__ steps_out, u64* __restrict__ cnt)
 {
+  const double ratio = (double)n / (double)items;
   for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < items; t += (u64)gridDim.x * blockDim.x)
   {
     // range owning item t: last r with node_off[r] <= t
-    u64 lo = 0, hi = n - 1;
-    while(lo < hi)
-    {
-      u64 mid = lo + (hi - lo + 1) / 2;
-      if(node_off[mid] <= t) { lo = mid; } else { hi = mid - 1; }
-    }
+    u64 lo = owner_of(node_off, n, t, (u64)((double)t * ratio));
     u64 node = sp[lo] + (t - node_off[lo]);
     u32 steps = 0;
     u64 r;
-    if(v.walk32 != nullptr)
+    if(v.loc64 != nullptr)
+    {
+      u64 e = __ldg(v.loc64 + node);
+      if(e >> 63) { first[t] = e & ~(1ull << 63); steps_out[t] = LOC_DIRECT; cnt[t] = 1; continue; }
+      r = e >> 24; steps = (u32)(e & 0xFFFFFFu);
+    }
+    else if(v.walk32 != nullptr)
     {
       u32 e = __ldg(v.walk32 + node);
       while(!(e & 1)) { e = __ldg(v.walk32 + (e >> 1)); steps++; }
@@ -917,6 +958,7 @@ locate_fill_kernel(const DevView v, u64 items, const u64* __restrict__ first, co
   for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < items; t += (u64)gridDim.x * blockDim.x)
   {
     u64 s0 = first[t], o0 = val_off[t], c = val_off[t + 1] - o0;
+    if(steps[t] == LOC_DIRECT) { raw[o0] = s0; continue; }
     for(u64 j = 0; j < c; j++) { raw[o0 + j] = v.stored_samples[s0 + j] + steps[t]; }   // gcsa.cpp:893
   }
 }
@@ -935,15 +977,11 @@ locate_segments_kernel(const u64* __restrict__ node_off, const u64* __restrict__
 __global__ void __launch_bounds__(256)
 locate_flag_kernel(const u64* __restrict__ sorted, const u64* __restrict__ seg, u64 n, u64 total, u64* __restrict__ flag)
 {
+  const double ratio = (double)n / (double)total;
   for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x)
   {
     // segment of t: last r with seg[r] <= t
-    u64 lo = 0, hi = n;
-    while(lo < hi)
-    {
-      u64 mid = lo + (hi - lo + 1) / 2;
-      if(seg[mid] <= t) { lo = mid; } else { hi = mid - 1; }
-    }
+    u64 lo = owner_of(seg, n, t, (u64)((double)t * ratio));
     flag[t] = (t == seg[lo] || sorted[t] != sorted[t - 1]) ? 1 : 0;
   }
 }
@@ -980,6 +1018,36 @@ walk_table_kernel(const DevView v, T* table)
     u64 r;
     if(rv_get_rank(v.sampled, i, r)) { table[i] = (T)((r << 1) | 1); }
     else { table[i] = (T)(lf_node(v, i) << 1); }
+  }
+}
+
+// Locate table: the whole of locateInternal() (gcsa.cpp:880-896) per path node, precomputed from the walk
+// table.  A node whose sampled ancestor stores one start position holds that position + steps directly
+// (bit 63 set); otherwise the rank of the sampled node and the number of steps.  *overflow is set if a
+// field does not fit (the table is then dropped).
+__global__ void __launch_bounds__(256)
+locate_table_kernel(const DevView v, u64* table, int* overflow)
+{
+  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < v.path_nodes; i += (u64)gridDim.x * blockDim.x)
+  {
+    u64 r, steps = 0;
+    if(v.walk32 != nullptr)
+    {
+      u32 e = __ldg(v.walk32 + i);
+      while(!(e & 1)) { e = __ldg(v.walk32 + (e >> 1)); steps++; }
+      r = e >> 1;
+    }
+    else
+    {
+      u64 e = __ldg(v.walk64 + i);
+      while(!(e & 1)) { e = __ldg(v.walk64 + (e >> 1)); steps++; }
+      r = e >> 1;
+    }
+    u64 s0 = v.sample_start[r], s1 = v.sample_start[r + 1];
+    u64 value = v.stored_samples[s0] + steps;
+    if(steps >= (1ull << 24) || r >= (1ull << 39)) { *overflow = 1; table[i] = 0; }
+    else if(s1 - s0 == 1 && value < (1ull << 63)) { table[i] = (1ull << 63) | value; }
+    else { table[i] = (r << 24) | steps; }
   }
 }
 
@@ -1637,6 +1705,36 @@ int gcsa_b200_index_create(const gcsa_flat_index* host, int device, const gcsa_b
       }
       idx->allocations.push_back(p); idx->device_bytes += bytes;
       if(narrow) { v.walk32 = (const u32*)p; } else { v.walk64 = (const u64*)p; }
+
+      // Locate table (8 bytes per path node) from the walk table, which it then replaces: one load per
+      // located node instead of one per LF step.  walk_table = 2 keeps the walk table instead.
+      size_t loc_bytes = (size_t)N * sizeof(u64);
+      cudaMemGetInfo(&free_b, &total_b);
+      if((options == nullptr || options->walk_table != 2) && (forced || loc_bytes < free_b / 2))
+      {
+        u64* loc = nullptr; int* overflow = nullptr; int host_overflow = 0;
+        e = cudaMalloc((void**)&loc, loc_bytes);
+        if(e == cudaSuccess) { e = cudaMalloc((void**)&overflow, sizeof(int)); }
+        if(e == cudaSuccess) { e = cudaMemset(overflow, 0, sizeof(int)); }
+        if(e == cudaSuccess)
+        {
+          locate_table_kernel<<<gridFor(N, idx->sm_count, 8), 256>>>(v, loc, overflow);
+          e = cudaMemcpy(&host_overflow, overflow, sizeof(int), cudaMemcpyDeviceToHost);
+        }
+        if(overflow) { cudaFree(overflow); }
+        if(e == cudaSuccess && host_overflow == 0)
+        {
+          cudaFree(p); idx->allocations.pop_back(); idx->device_bytes -= bytes;
+          v.walk32 = nullptr; v.walk64 = nullptr;
+          idx->allocations.push_back(loc); idx->device_bytes += loc_bytes;
+          v.loc64 = loc;
+        }
+        else
+        {
+          if(loc) { cudaFree(loc); }
+          cudaGetLastError();               // keep the walk table
+        }
+      }
     }
   }
 
@@ -2266,32 +2364,34 @@ int gcsa_b200_locate_max_host(const gcsa_b200_index* index, const uint64_t* sp, 
   int rc = gcsa_b200_count_host(index, sp, ep, n, (uint64_t*)totals.data());
   if(rc) { return rc; }
 
-  std::vector<std::vector<u64>> results(n);
-  std::vector<std::mt19937_64> rngs; rngs.reserve(n);
-  std::vector<u64> maxes(n);
-  std::vector<u64> full_sp, full_ep, full_id;
-  std::vector<u64> rnd_id;
-  std::vector<std::unordered_set<u64>> found(n);
+  // Only ranges with more occurrences than max_positions need the reference's random machinery
+  // (rng(sp ^ ep), the draw loop, deterministicShuffle); everything else is a plain locate().
+  struct Special { std::mt19937_64 rng; std::unordered_set<u64> found; std::vector<u64> result; u64 draws = 0; };
+  std::unordered_map<u64, Special> special;
+  std::vector<u64> full_sp, full_ep, full_id, rnd_id;
   for(u64 i = 0; i < n; i++)
   {
-    rngs.emplace_back(sp[i] ^ ep[i]);
-    maxes[i] = std::min<u64>(max_positions, totals[i]);
     if(totals[i] == 0) { continue; }
-    if(maxes[i] >= totals[i] / 2) { full_sp.push_back(sp[i]); full_ep.push_back(ep[i]); full_id.push_back(i); }
+    u64 max_i = std::min<u64>(max_positions, totals[i]);
+    if(totals[i] > max_i) { special[i].rng.seed(sp[i] ^ ep[i]); }                 // gcsa.cpp:857
+    if(max_i >= totals[i] / 2) { full_sp.push_back(sp[i]); full_ep.push_back(ep[i]); full_id.push_back(i); }   // gcsa.cpp:860
     else { rnd_id.push_back(i); }
   }
+  std::vector<u64> full_offs(full_id.size() + 1, 0);
+  uint64_t* full_vals = nullptr;
   if(!full_id.empty())
   {
-    std::vector<u64> offs(full_id.size() + 1); uint64_t* vals = nullptr;
-    rc = gcsa_b200_locate_host(index, (const uint64_t*)full_sp.data(), (const uint64_t*)full_ep.data(), full_id.size(), (uint64_t*)offs.data(), &vals);
+    rc = gcsa_b200_locate_host(index, (const uint64_t*)full_sp.data(), (const uint64_t*)full_ep.data(), full_id.size(), (uint64_t*)full_offs.data(), &full_vals);
     if(rc) { return rc; }
-    for(u64 t = 0; t < full_id.size(); t++) { results[full_id[t]].assign(vals + offs[t], vals + offs[t + 1]); }
-    std::free(vals);
+    for(u64 t = 0; t < full_id.size(); t++)
+    {
+      auto it = special.find(full_id[t]);
+      if(it != special.end()) { it->second.result.assign(full_vals + full_offs[t], full_vals + full_offs[t + 1]); }
+    }
   }
   // The reference's loop never ends when count() overestimates the distinct values of a range that
   // is not a suffix-tree node; after 16 * length + 1024 draws the whole range is located instead
   // (the CPU checker used by the tests does the same).
-  std::vector<u64> draws(n, 0);
   std::vector<u64> giveup;
   while(!rnd_id.empty())
   {
@@ -2299,21 +2399,23 @@ int gcsa_b200_locate_max_host(const gcsa_b200_index* index, const uint64_t* sp, 
     for(u64 t = 0; t < rnd_id.size(); t++)
     {
       u64 i = rnd_id[t];
-      if(draws[i]++ >= 16 * (ep[i] + 1 - sp[i]) + 1024) { giveup.push_back(i); continue; }
-      nodes.push_back(sp[i] + rngs[i]() % (ep[i] + 1 - sp[i]));
+      Special& state = special[i];
+      if(state.draws++ >= 16 * (ep[i] + 1 - sp[i]) + 1024) { giveup.push_back(i); continue; }
+      nodes.push_back(sp[i] + state.rng() % (ep[i] + 1 - sp[i]));                 // gcsa.cpp:866
       active.push_back(i);
     }
     if(active.empty()) { break; }
     std::vector<u64> offs(active.size() + 1); uint64_t* vals = nullptr;
     rc = gcsa_b200_locate_host(index, (const uint64_t*)nodes.data(), (const uint64_t*)nodes.data(), active.size(), (uint64_t*)offs.data(), &vals);
-    if(rc) { return rc; }
+    if(rc) { std::free(full_vals); return rc; }
     std::vector<u64> still;
     for(u64 t = 0; t < active.size(); t++)
     {
       u64 i = active[t];
-      for(u64 j = offs[t]; j < offs[t + 1]; j++) { found[i].insert(vals[j]); }
-      if(found[i].size() < maxes[i]) { still.push_back(i); }
-      else { results[i].assign(found[i].begin(), found[i].end()); }
+      Special& state = special[i];
+      for(u64 j = offs[t]; j < offs[t + 1]; j++) { state.found.insert(vals[j]); }
+      if(state.found.size() < std::min<u64>(max_positions, totals[i])) { still.push_back(i); }
+      else { state.result.assign(state.found.begin(), state.found.end()); }
     }
     std::free(vals);
     rnd_id.swap(still);
@@ -2324,30 +2426,53 @@ int gcsa_b200_locate_max_host(const gcsa_b200_index* index, const uint64_t* sp, 
     for(u64 i : giveup) { gsp.push_back(sp[i]); gep.push_back(ep[i]); }
     std::vector<u64> offs(giveup.size() + 1); uint64_t* vals = nullptr;
     rc = gcsa_b200_locate_host(index, (const uint64_t*)gsp.data(), (const uint64_t*)gep.data(), giveup.size(), (uint64_t*)offs.data(), &vals);
-    if(rc) { return rc; }
+    if(rc) { std::free(full_vals); return rc; }
     for(u64 t = 0; t < giveup.size(); t++)
     {
-      u64 i = giveup[t];
-      for(u64 j = offs[t]; j < offs[t + 1]; j++) { found[i].insert(vals[j]); }
-      results[i].assign(found[i].begin(), found[i].end());
+      Special& state = special[giveup[t]];
+      for(u64 j = offs[t]; j < offs[t + 1]; j++) { state.found.insert(vals[j]); }
+      state.result.assign(state.found.begin(), state.found.end());
     }
     std::free(vals);
   }
-  out_offsets[0] = 0;
-  for(u64 i = 0; i < n; i++)
+  for(auto& entry : special)
   {
-    std::vector<u64>& r = results[i];
-    if(r.size() > maxes[i])
+    std::vector<u64>& r = entry.second.result;
+    u64 max_i = std::min<u64>(max_positions, totals[entry.first]);
+    if(r.size() > max_i)
     {
       std::sort(r.begin(), r.end());                        // deterministicShuffle, utils.h:359-370
-      for(u64 j = r.size(); j > 0; j--) { std::swap(r[j - 1], r[rngs[i]() % j]); }
-      r.resize(maxes[i]);
+      for(u64 j = r.size(); j > 0; j--) { std::swap(r[j - 1], r[entry.second.rng() % j]); }
+      r.resize(max_i);
     }
     std::sort(r.begin(), r.end());
-    out_offsets[i + 1] = out_offsets[i] + r.size();
+  }
+  // assemble: plain ranges straight from the full locate, special ones from their state
+  out_offsets[0] = 0;
+  {
+    u64 t = 0;
+    for(u64 i = 0; i < n; i++)
+    {
+      while(t < full_id.size() && full_id[t] < i) { t++; }
+      auto it = special.find(i);
+      u64 size = 0;
+      if(it != special.end()) { size = it->second.result.size(); }
+      else if(t < full_id.size() && full_id[t] == i) { size = full_offs[t + 1] - full_offs[t]; }
+      out_offsets[i + 1] = out_offsets[i] + size;
+    }
   }
   u64* vals = (u64*)std::malloc(std::max<u64>(out_offsets[n], 1) * sizeof(u64));
-  for(u64 i = 0; i < n; i++) { std::copy(results[i].begin(), results[i].end(), vals + out_offsets[i]); }
+  {
+    u64 t = 0;
+    for(u64 i = 0; i < n; i++)
+    {
+      while(t < full_id.size() && full_id[t] < i) { t++; }
+      auto it = special.find(i);
+      if(it != special.end()) { std::copy(it->second.result.begin(), it->second.result.end(), vals + out_offsets[i]); }
+      else if(t < full_id.size() && full_id[t] == i) { std::copy(full_vals + full_offs[t], full_vals + full_offs[t + 1], vals + out_offsets[i]); }
+    }
+  }
+  std::free(full_vals);
   *values = (uint64_t*)vals;
   return 0;
 }

@@ -56,7 +56,8 @@ extern "C" int gcsa_b200_verify_index(const gcsa_b200_index* index, const gcsa_b
 
   // Sort by (label, from): parallelQuickSort(kmers) + the label groups of algorithms.cpp:106-125.
   std::vector<std::pair<u64, u64>> recs(n);
-  for(u64 i = 0; i < n; i++) { recs[i] = std::make_pair(keys[i] >> 16, from[i]); }     // Key::label, support.h:389
+  #pragma omp parallel for schedule(static)
+  for(u64 i = 0; i < n; i++) { recs[i] = std::make_pair(keys[i] >> 16, from[i]); }     // Key::label, support.h:403
   __gnu_parallel::sort(recs.begin(), recs.end());
   std::vector<u64> group_start;
   for(u64 i = 0; i < n; i++) { if(i == 0 || recs[i].first != recs[i - 1].first) { group_start.push_back(i); } }
@@ -68,31 +69,40 @@ extern "C" int gcsa_b200_verify_index(const gcsa_b200_index* index, const gcsa_b
   {
     const u64 m = std::min(CHUNK_LABELS, unique - base);
 
-    // Patterns: Key::decode (support.cpp:254-263), cut after the first endmarker (algorithms.cpp:127-129).
-    std::vector<uint8_t> chars(m * k + 1);
-    std::vector<u64> offsets(m + 1, 0);
+    // Patterns: Key::decode (support.cpp:539-553), cut after the first endmarker (algorithms.cpp:127-129).
+    std::vector<u64> offsets(m + 1, 0), exp_offsets(m + 1, 0);
+    #pragma omp parallel for schedule(static)
     for(u64 g = 0; g < m; g++)
     {
       u64 label = recs[group_start[base + g]].first, len = 0;
-      uint8_t* out = chars.data() + offsets[g];
-      for(u64 i = 0; i < k; i++)
-      {
-        u64 comp = (label >> (3 * (k - 1 - i))) & 7;
-        out[len++] = (uint8_t)comp2char[comp < 7 ? comp : 5];
-        if(comp == 0) { break; }
-      }
-      offsets[g + 1] = offsets[g] + len;
-    }
-
-    // Expected occurrences: distinct `from` values per label (algorithms.cpp:184-187); sorted already.
-    std::vector<u64> exp_offsets(m + 1, 0), expected;
-    for(u64 g = 0; g < m; g++)
-    {
+      for(u64 i = 0; i < k; i++) { len++; if(((label >> (3 * (k - 1 - i))) & 7) == 0) { break; } }
+      offsets[g + 1] = len;
+      u64 distinct = 0;
       for(u64 j = group_start[base + g]; j < group_start[base + g + 1]; j++)
       {
-        if(j == group_start[base + g] || recs[j].second != recs[j - 1].second) { expected.push_back(recs[j].second); }
+        if(j == group_start[base + g] || recs[j].second != recs[j - 1].second) { distinct++; }
       }
-      exp_offsets[g + 1] = expected.size();
+      exp_offsets[g + 1] = distinct;
+    }
+    for(u64 g = 0; g < m; g++) { offsets[g + 1] += offsets[g]; exp_offsets[g + 1] += exp_offsets[g]; }
+    std::vector<uint8_t> chars(offsets[m] + 1);
+    // Expected occurrences: distinct `from` values per label (algorithms.cpp:184-187); sorted already.
+    std::vector<u64> expected(exp_offsets[m]);
+    #pragma omp parallel for schedule(static)
+    for(u64 g = 0; g < m; g++)
+    {
+      u64 label = recs[group_start[base + g]].first;
+      uint8_t* out = chars.data() + offsets[g];
+      for(u64 i = 0; i < offsets[g + 1] - offsets[g]; i++)
+      {
+        u64 comp = (label >> (3 * (k - 1 - i))) & 7;
+        out[i] = (uint8_t)comp2char[comp < 7 ? comp : 5];
+      }
+      u64* e = expected.data() + exp_offsets[g];
+      for(u64 j = group_start[base + g]; j < group_start[base + g + 1]; j++)
+      {
+        if(j == group_start[base + g] || recs[j].second != recs[j - 1].second) { *e++ = recs[j].second; }
+      }
     }
 
     // find() -- algorithms.cpp:131-143

@@ -48,7 +48,7 @@ class GCSA:
         keep = []
         f = capi.flat_struct(flat, keep)
         opt = capi.Options(); opt.kmer_table_k = int(kmer_table_k); opt.two_step = (-1 if two_step is None else int(bool(two_step)))
-        opt.walk_table = (-1 if walk_table is None else int(bool(walk_table)))
+        opt.walk_table = (-1 if walk_table is None else int(walk_table))
         h = C.c_void_p()
         capi.check(L.gcsa_b200_index_create(C.byref(f), int(device), C.byref(opt), C.byref(h)))
         self._h = h

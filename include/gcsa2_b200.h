@@ -83,10 +83,13 @@ typedef struct gcsa_b200_options {
                               first k backward steps.  -1 = engine default. */
   int      two_step;       /* 1 = also build (-1 = decide by index size, 0 = never) the two-step blocks (16 sectors per 87 path nodes, 5.9 B per
                               node): two backward steps per probe for pairs of ACGT characters. */
-  int      walk_table;     /* locate(): one table entry per path node (4 bytes below 2^31 nodes, else 8) holding
-                              LF(node) or, for sampled nodes, the index of their samples, so that a step of the
-                              locate walk is one load.  1 = build, 0 = do not, -1 = build if it fits in a
-                              quarter of the free device memory. */
+  int      walk_table;     /* locate(): precomputed per-node tables.  1 = build the locate table (8 bytes per path node:
+                              the start position itself for nodes with one position, else the sampled node and the
+                              step count, so that locating a node is one load), falling back to the walk table if
+                              that fails; 2 = walk table only (4 bytes per node below 2^31 nodes, else 8: LF(node) or,
+                              for sampled nodes, the index of their samples -- one load per LF step); 0 = neither
+                              (bit vectors only); -1 = what fits: each table must fit in a fraction of the free
+                              device memory. */
   int      reserved[5];
 } gcsa_b200_options;
 

@@ -79,7 +79,7 @@ def test_all_operations_random_graphs(seed):
                      alphabet=[(1, 2, 3, 4), (1, 2)][seed % 2])
     cg = CharGraph.from_lists(g.comps, g.values, g.succ, g.sources, g.sink)
     flat, flcp, kmers = build_index(cg, 2, 2, sample_period=[4, 64][seed % 2], lcp_branching=[2, 4, 64, 3][seed])
-    gpu, ora = both(flat, table_k=[0, 2, 3, 5][seed], two_step=(seed >= 2), walk_table=[True, False, None, True][seed])
+    gpu, ora = both(flat, table_k=[0, 2, 3, 5][seed], two_step=(seed >= 2), walk_table=[True, False, 2, None][seed])
     N = flat.path_nodes
 
     # find: patterns of every kind (ragged lengths, empty, with $, #, N, lower case, garbage bytes)
@@ -328,3 +328,38 @@ def test_host_packed_find_equals_byte_path(monkeypatch):
                 pats = [bytes(dirty[i * length:(i + 1) * length]) for i in q]
                 for i, pat in zip(q, pats):
                     assert (int(psp[i]), int(pep[i])) == ora.find(pat)
+
+
+def test_locate_tables_agree():
+    """locate() through the locate table (one load per node), the walk table (one load per LF step) and the
+    bit vectors alone: identical CSR output, equal to the oracle -- short patterns (wide ranges, many nodes per
+    range, multi-valued nodes at the SNP sites), k-mers, empty and out-of-range ranges, raw and max forms."""
+    seq = synth.random_sequence(200_000, seed=13)
+    seq[5000:5400] = seq[1000:1400]                                   # a repeat: nodes with two start positions
+    graph, sites, alt = synth.snp_graph(seq, seed=13, snp_rate=0.02)
+    flat, _, _ = build_index(graph, 16, 2)
+    ora = orc.OracleGCSA(flat)
+    rng = np.random.default_rng(13)
+    pats = []
+    for length, count in ((3, 50), (6, 2000), (12, 5000), (40, 5000)):
+        c, o = synth.patterns_from_snp_graph(seq, sites, alt, count, length, seed=length)
+        pats += [bytes(c[int(o[i]):int(o[i + 1])]) for i in range(count)]
+    pats += [bytes(seq_to_chars) for seq_to_chars in (synth.COMP2CHAR[seq[1100:1100 + L]] for L in (20, 64, 300))]
+    chars, offsets = orc.pack_patterns(pats)
+    sp, ep, _ = ora.find_batch(chars, offsets, threads=4)
+    sp = np.concatenate([sp, [5, 1, flat.path_nodes - 2, 0]]).astype(np.uint64)
+    ep = np.concatenate([ep, [4, 0, flat.path_nodes + 5, flat.path_nodes - 1]]).astype(np.uint64)   # empty, empty, out of range, everything
+    sp, ep = sp[:-1], ep[:-1]                                         # (the whole index is covered by test_all_operations)
+    ooffs, ovals, _ = ora.locate_batch(sp, ep, threads=4)
+    results = []
+    for walk_table in (1, 2, 0):
+        gpu = GCSA(flat, kmer_table_k=0, walk_table=walk_table)
+        offs, vals = gpu.locate_batch(sp, ep)
+        assert (offs == ooffs).all() and (vals == ovals).all(), walk_table
+        roffs, rvals = gpu.locate_batch(sp[:3000], ep[:3000], sort=False)
+        results.append((roffs, rvals))
+        for i in rng.integers(0, sp.size, size=40):
+            rng_i = (int(sp[i]), int(ep[i]))
+            assert list(gpu.locate(rng_i, max_positions=5)) == list(ora.locate(rng_i, max_positions=5)), (walk_table, rng_i)
+    for roffs, rvals in results[1:]:
+        assert (roffs == results[0][0]).all() and (rvals == results[0][1]).all()
