@@ -2364,8 +2364,9 @@ int gcsa_b200_locate_max_host(const gcsa_b200_index* index, const uint64_t* sp, 
   int rc = gcsa_b200_count_host(index, sp, ep, n, (uint64_t*)totals.data());
   if(rc) { return rc; }
 
-  // Only ranges with more occurrences than max_positions need the reference's random machinery
-  // (rng(sp ^ ep), the draw loop, deterministicShuffle); everything else is a plain locate().
+  // Only ranges that draw random positions or end up with more than max_positions results need the
+  // reference's random machinery (rng(sp ^ ep), the draw loop, deterministicShuffle); everything else
+  // is a plain locate().
   struct Special { std::mt19937_64 rng; std::unordered_set<u64> found; std::vector<u64> result; u64 draws = 0; };
   std::unordered_map<u64, Special> special;
   std::vector<u64> full_sp, full_ep, full_id, rnd_id;
@@ -2373,9 +2374,8 @@ int gcsa_b200_locate_max_host(const gcsa_b200_index* index, const uint64_t* sp, 
   {
     if(totals[i] == 0) { continue; }
     u64 max_i = std::min<u64>(max_positions, totals[i]);
-    if(totals[i] > max_i) { special[i].rng.seed(sp[i] ^ ep[i]); }                 // gcsa.cpp:857
     if(max_i >= totals[i] / 2) { full_sp.push_back(sp[i]); full_ep.push_back(ep[i]); full_id.push_back(i); }   // gcsa.cpp:860
-    else { rnd_id.push_back(i); }
+    else { rnd_id.push_back(i); special[i].rng.seed(sp[i] ^ ep[i]); }             // gcsa.cpp:857
   }
   std::vector<u64> full_offs(full_id.size() + 1, 0);
   uint64_t* full_vals = nullptr;
@@ -2383,10 +2383,17 @@ int gcsa_b200_locate_max_host(const gcsa_b200_index* index, const uint64_t* sp, 
   {
     rc = gcsa_b200_locate_host(index, (const uint64_t*)full_sp.data(), (const uint64_t*)full_ep.data(), full_id.size(), (uint64_t*)full_offs.data(), &full_vals);
     if(rc) { return rc; }
+    // count() may be off for a range that is not a suffix-tree node, so "too many results" (gcsa.cpp:873)
+    // is decided on what locate() returned; the generator is untouched until the shuffle on this path.
     for(u64 t = 0; t < full_id.size(); t++)
     {
-      auto it = special.find(full_id[t]);
-      if(it != special.end()) { it->second.result.assign(full_vals + full_offs[t], full_vals + full_offs[t + 1]); }
+      u64 i = full_id[t];
+      if(full_offs[t + 1] - full_offs[t] > std::min<u64>(max_positions, totals[i]))
+      {
+        Special& state = special[i];
+        state.rng.seed(sp[i] ^ ep[i]);
+        state.result.assign(full_vals + full_offs[t], full_vals + full_offs[t + 1]);
+      }
     }
   }
   // The reference's loop never ends when count() overestimates the distinct values of a range that
