@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--index-cache", default="", help="npz file: load the built index from it if present, else save it there")
+    ap.add_argument("--no-locate", action="store_true", help="skip the locate() leg (BASELINE.json configs[2])")
+    ap.add_argument("--locate-mbp", type=float, default=50.0, help="backbone length of the SNP-bubble graph of the locate() leg (Mbp)")
+    ap.add_argument("--locate-queries", type=int, default=10_000_000, help="64-mers per GPU in the locate() leg")
     return ap.parse_args()
 
 
@@ -178,6 +181,102 @@ def cpu_baseline(flat, chars, offsets, length, sample, threads=None):
     return engine, {"value": n / best, "unit": UNIT, "cores": threads, "kind": kind,
                     "sample": "%d of the same %d-mers, best of 2, %d OpenMP threads (schedule dynamic,4096); %s" % (n, length, threads, what),
                     "seconds": best}
+
+
+def locate_leg(args, rank, world, local, barrier, dist, torch):
+    """The second half of BASELINE.json's metric: locate() positions/s on configs[2] -- 64-mers sampled from walks
+    through a synthetic variation graph (1 % SNP bubbles, order 128), find() then locate(range) as a CSR of sorted
+    distinct positions (GCSA::locate, src/gcsa.cpp:827-842).  Device-resident (CUDA events), end to end through
+    gcsa_b200_locate_host, and the reference's own locate() on the host cores (rank 0)."""
+    from gcsa2_b200 import GCSA, synth
+    from gcsa2_b200.builder import build_index
+    from gcsa2_b200.flat import FlatGCSA
+    L, n, length = int(args.locate_mbp * 1_000_000), args.locate_queries, 64
+    seq = synth.random_sequence(L, seed=3)
+    graph, sites, alt = synth.snp_graph(seq, seed=3, snp_rate=0.01)
+    shared = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir(),
+                          "gcsa2_b200_bench_locate_%d_%d.npz" % (L, os.getppid() if world > 1 else os.getpid()))
+    t0 = time.time()
+    flat = None
+    if rank == 0:
+        flat, _, _ = build_index(graph, 16, 3)
+        if world > 1:
+            flat.save(shared)
+    barrier()
+    if rank != 0:
+        flat = FlatGCSA.load(shared)
+    barrier()
+    if rank == 0 and world > 1 and os.path.exists(shared):
+        os.remove(shared)
+    build_s = time.time() - t0
+    chars = np.empty(n * length, dtype=np.uint8)
+    for i, q0 in enumerate(range(0, n, 1_000_000)):
+        m = min(1_000_000, n - q0)
+        c, _ = synth.patterns_from_snp_graph(seq, sites, alt, m, length, seed=7000 + 100 * rank + i)
+        chars[q0 * length:(q0 + m) * length] = c
+    index = GCSA(flat, device=local, kmer_table_k=args.kmer_table_k)
+    stream = torch.cuda.current_stream()
+    d_chars = torch.from_numpy(chars).cuda()
+    d_sp = torch.empty(n, dtype=torch.int64, device="cuda"); d_ep = torch.empty_like(d_sp)
+    index.find_fixed_device(d_chars, length, n, d_sp, d_ep, stream.cuda_stream)
+    d_cnt = torch.empty(n, dtype=torch.int64, device="cuda")
+    index.count_device(d_sp, d_ep, n, d_cnt, stream.cuda_stream)
+    torch.cuda.synchronize()
+    total = int(d_cnt.sum().item())
+    d_offs = torch.empty(n + 1, dtype=torch.int64, device="cuda")
+    d_vals = torch.empty(total + 16, dtype=torch.int64, device="cuda")
+    got = [0]
+
+    def step():
+        got[0] = index.locate_device(d_sp, d_ep, n, d_offs, d_vals, total + 16, stream.cuda_stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize(); barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    torch.cuda.synchronize(); barrier()
+    ms = ev0.elapsed_time(ev1) / args.steps
+
+    # end to end: ranges in host memory -> CSR in host memory (values malloc'ed by the library)
+    sp = d_sp.cpu().numpy().view(np.uint64); ep = d_ep.cpu().numpy().view(np.uint64)
+    offs, vals = index.locate_batch(sp, ep)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        offs, vals = index.locate_batch(sp, ep)
+    e2e_ms = 1000.0 * (time.perf_counter() - t0) / args.steps
+    same = bool((d_offs.cpu().numpy().view(np.uint64) == offs).all() and (d_vals[:got[0]].cpu().numpy().view(np.uint64) == vals).all())
+
+    positions = got[0]
+    if dist is not None:
+        t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+        c = torch.tensor([positions], dtype=torch.int64, device="cuda")
+        dist.all_reduce(c)
+        positions = int(c[0])
+    out = {"metric": "locate_positions_per_sec", "value": positions / (ms / 1000.0), "unit": "positions/s", "ms_per_step": ms,
+           "positions": positions, "ranges": n * world,
+           "config": {"workload": "cfg3: %d x 64-mers per GPU from walks through a %g Mbp backbone with 1 %% SNP bubbles (seed 3), order-128 index; "
+                                  "find() then locate(range) -> CSR of sorted distinct positions" % (n, args.locate_mbp),
+                      "index": {"path_nodes": index.size(), "edges": index.edgeCount(), "device_bytes": index.deviceBytes()}},
+           "e2e": {"value": positions / (e2e_ms / 1000.0), "unit": "positions/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": int(16 * n), "d2h_bytes_per_step": int(8 * (n + 1) + 8 * got[0]),
+                   "api": "gcsa_b200_locate_host", "matches_device_leg": same},
+           "setup": {"index_build_s": build_s}}
+    if rank == 0 and not args.no_cpu_baseline:
+        engine, kind, threads = cpu_engine(flat)
+        m = min(n, 50_000 * threads)
+        roffs, rvals, secs = engine.locate_batch(sp[:m], ep[:m], threads=threads)
+        k = int(roffs[m])
+        out["cpu_baseline"] = {"value": k / secs, "unit": "positions/s", "cores": threads, "kind": kind,
+                               "sample": "locate() of the first %d ranges, %d OpenMP threads (schedule dynamic,256)" % (m, threads), "seconds": secs,
+                               "parity_on_sample": bool((offs[:m + 1] == roffs).all() and (vals[:k] == rvals).all())}
+    index.close()
+    return out
 
 
 def peaks():
@@ -328,6 +427,14 @@ def main():
     else:
         total_q, total_found = n, found
 
+    locate = None
+    if not args.no_locate:
+        try:
+            del d_chars, h_chars
+            locate = locate_leg(args, rank, world, local, barrier, dist, torch)
+        except Exception as exc:                                    # the find() line must survive a failure here
+            locate = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     if rank == 0:
         peak, peak_src = peaks()
         achieved = engine_bytes / (ms_total / args.steps / 1000.0) / 1e9
@@ -358,6 +465,8 @@ def main():
             "clocks": clocks,
             "setup": {"index_build_s": build_s, "index_create_s": create_s},
         }
+        if locate is not None:
+            line["locate"] = locate
         if not args.no_cpu_baseline:
             from oracle import oracle as orc
             threads = orc.lib().oracle_max_threads()
