@@ -80,7 +80,7 @@ SYMBOLS = [
     "gcsa_b200_lf_batch", "gcsa_b200_lf_host", "gcsa_b200_lf_node_batch", "gcsa_b200_lf_node_host",
     "gcsa_b200_lf_multi_batch", "gcsa_b200_lf_multi_host",
     "gcsa_b200_count_batch", "gcsa_b200_count_host",
-    "gcsa_b200_locate_host", "gcsa_b200_locate_raw_host", "gcsa_b200_locate_batch", "gcsa_b200_locate_max_host", "gcsa_b200_free", "gcsa_b200_count_kmers", "gcsa_b200_compare_kmers", "gcsa_b200_verify_index",
+    "gcsa_b200_locate_host", "gcsa_b200_locate_into_host", "gcsa_b200_locate_raw_host", "gcsa_b200_locate_batch", "gcsa_b200_locate_max_host", "gcsa_b200_free", "gcsa_b200_count_kmers", "gcsa_b200_compare_kmers", "gcsa_b200_verify_index",
     "gcsa_b200_lcp_create", "gcsa_b200_lcp_destroy",
     "gcsa_b200_parent_batch", "gcsa_b200_parent_host", "gcsa_b200_depth_batch", "gcsa_b200_depth_host",
     "gcsa_b200_lcp_sv_host", "gcsa_b200_lcp_rmq_host", "gcsa_b200_mem_batch", "gcsa_b200_mem_host",
@@ -128,6 +128,7 @@ def lib():
     L.gcsa_b200_count_batch.argtypes = [vp, vp, vp, u64, vp, vp]
     L.gcsa_b200_count_host.argtypes = [vp, vp, vp, u64, vp]
     L.gcsa_b200_locate_host.argtypes = [vp, vp, vp, u64, vp, C.POINTER(vp)]
+    L.gcsa_b200_locate_into_host.argtypes = [vp, vp, vp, u64, vp, vp, u64, C.POINTER(u64)]
     L.gcsa_b200_locate_raw_host.argtypes = [vp, vp, vp, u64, vp, C.POINTER(vp)]
     L.gcsa_b200_locate_batch.argtypes = [vp, vp, vp, u64, vp, vp, u64, C.POINTER(u64), vp]
     L.gcsa_b200_locate_max_host.argtypes = [vp, vp, vp, u64, u64, vp, C.POINTER(vp)]

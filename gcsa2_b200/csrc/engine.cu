@@ -2349,6 +2349,95 @@ static int locateHost(const gcsa_b200_index* index, const uint64_t* sp, const ui
   HOST_EPILOGUE("locate_host", rc);
 }
 
+namespace {
+__global__ void __launch_bounds__(256)
+add_base_kernel(u64* __restrict__ x, u64 n, u64 base)
+{
+  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) { x[i] += base; }
+}
+} // namespace
+
+/*
+  locate() into caller-owned host buffers (pinned memory makes the copies run at PCIe speed): the batch is cut
+  into chunks on two streams -- the ranges of chunk i+1 go up and the values of chunk i-1 come down while
+  chunk i is being located.  Same CSR as gcsa_b200_locate_host.
+*/
+int gcsa_b200_locate_into_host(const gcsa_b200_index* index, const uint64_t* sp, const uint64_t* ep, uint64_t n,
+                               uint64_t* out_offsets, uint64_t* values, uint64_t capacity, uint64_t* needed)
+{
+  if(index == nullptr || out_offsets == nullptr || (n > 0 && (sp == nullptr || ep == nullptr)))
+  {
+    return fail(GCSA_B200_ERR_INVALID, "locate_into_host: null argument");
+  }
+  if(needed) { *needed = 0; }
+  out_offsets[0] = 0;
+  if(n == 0) { return 0; }
+  DeviceGuard guard(index->device);
+  const int STREAMS = 2;
+  const u64 CHUNK = std::max<u64>(1ull << 18, (n + 7) / 8);
+  const u64 n_chunks = (n + CHUNK - 1) / CHUNK;
+  cudaStream_t streams[STREAMS];
+  for(int s = 0; s < STREAMS; s++) { CUDA_TRY(cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking)); }
+  struct Chunk { u64* d_sp = nullptr; u64* d_ep = nullptr; u64* d_offs = nullptr; };
+  std::vector<Chunk> chunks(n_chunks);
+  int rc = 0;
+  bool overflow = false;
+  u64 base = 0;
+  auto upload = [&](u64 c) -> int
+  {
+    cudaStream_t st = streams[c % STREAMS];
+    u64 q0 = c * CHUNK, m = std::min(n, q0 + CHUNK) - q0;
+    Chunk& ch = chunks[c];
+    if(cudaMallocAsync((void**)&ch.d_sp, m * sizeof(u64), st) != cudaSuccess || cudaMallocAsync((void**)&ch.d_ep, m * sizeof(u64), st) != cudaSuccess ||
+       cudaMallocAsync((void**)&ch.d_offs, (m + 1) * sizeof(u64), st) != cudaSuccess)
+    {
+      return fail(GCSA_B200_ERR_NOMEM, "locate_into_host: out of device memory");
+    }
+    cudaMemcpyAsync(ch.d_sp, sp + q0, m * sizeof(u64), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(ch.d_ep, ep + q0, m * sizeof(u64), cudaMemcpyHostToDevice, st);
+    return 0;
+  };
+  rc = upload(0);
+  for(u64 c = 0; c < n_chunks && rc == 0; c++)
+  {
+    cudaStream_t st = streams[c % STREAMS];
+    u64 q0 = c * CHUNK, m = std::min(n, q0 + CHUNK) - q0;
+    if(c + 1 < n_chunks) { rc = upload(c + 1); if(rc) { break; } }
+    Chunk& ch = chunks[c];
+    u64 need = 0; u64* d_vals = nullptr;
+    rc = locateDevice(index, ch.d_sp, ch.d_ep, m, ch.d_offs, nullptr, 0, &need, st, &d_vals, true);
+    if(rc) { break; }
+    bool last = (c + 1 == n_chunks);
+    add_base_kernel<<<gridFor(m + 1, index->sm_count), 256, 0, st>>>(ch.d_offs, m + 1, base);
+    cudaMemcpyAsync(out_offsets + q0, ch.d_offs, (m + (last ? 1 : 0)) * sizeof(u64), cudaMemcpyDeviceToHost, st);
+    if(values != nullptr && base + need <= capacity)
+    {
+      if(need > 0) { cudaMemcpyAsync(values + base, d_vals, need * sizeof(u64), cudaMemcpyDeviceToHost, st); }
+    }
+    else if(need > 0) { overflow = true; }
+    if(d_vals) { cudaFreeAsync(d_vals, st); }
+    cudaFreeAsync(ch.d_sp, st); cudaFreeAsync(ch.d_ep, st); cudaFreeAsync(ch.d_offs, st);
+    ch = Chunk();
+    base += need;
+  }
+  for(Chunk& ch : chunks)            // an upload that never ran (error path)
+  {
+    if(ch.d_sp) { cudaFree(ch.d_sp); } if(ch.d_ep) { cudaFree(ch.d_ep); } if(ch.d_offs) { cudaFree(ch.d_offs); }
+  }
+  cudaError_t err = cudaSuccess;
+  for(int s = 0; s < STREAMS; s++)
+  {
+    cudaError_t e = cudaStreamSynchronize(streams[s]);
+    if(e != cudaSuccess) { err = e; }
+    cudaStreamDestroy(streams[s]);
+  }
+  if(rc) { return rc; }
+  if(err != cudaSuccess) { return fail(GCSA_B200_ERR_CUDA, std::string("locate_into_host: ") + cudaGetErrorString(err)); }
+  if(needed) { *needed = base; }
+  if(overflow) { return fail(GCSA_B200_ERR_CAPACITY, "locate_into_host: output capacity too small"); }
+  return 0;
+}
+
 /*
   GCSA::locate(range, max_positions, results), src/gcsa.cpp:844-878, batched.  count() runs on the
   device; ranges with max >= total/2 are located in full on the device; the others draw positions

@@ -259,6 +259,13 @@ class GCSA:
         offs, vals = self.locate_batch(sp, ep, max_positions=max_positions)
         return [int(x) for x in vals[int(offs[0]):int(offs[1])]]
 
+    def locate_into_host_raw(self, sp_ptr, ep_ptr, n, offsets_ptr, values_ptr, capacity):
+        """gcsa_b200_locate_into_host on raw host addresses (pinned buffers); returns the number of values,
+        raises GCSAError(ERR_CAPACITY) if capacity was too small."""
+        needed = C.c_uint64()
+        capi.check(capi.lib().gcsa_b200_locate_into_host(self._h, sp_ptr, ep_ptr, int(n), offsets_ptr, values_ptr, int(capacity), C.byref(needed)))
+        return int(needed.value)
+
     def locate_batch(self, sp, ep, max_positions=None, sort=True):
         """CSR result: values[offsets[i]:offsets[i+1]] are the sorted distinct positions of range i
         (sort=False: every emitted value in the reference's order, gcsa.cpp:840)."""

@@ -178,6 +178,12 @@ int gcsa_b200_locate_host(const gcsa_b200_index* index, const uint64_t* sp, cons
 int gcsa_b200_locate_batch(const gcsa_b200_index* index, const uint64_t* d_sp, const uint64_t* d_ep, uint64_t n,
                            uint64_t* d_out_offsets, uint64_t* d_values, uint64_t capacity, uint64_t* needed,
                            void* stream);
+/* The same CSR into caller-owned host buffers (use pinned memory: the copies then run at PCIe speed and are
+   pipelined with the kernels chunk by chunk).  values holds `capacity` entries; *needed receives the number of
+   values of the whole batch; GCSA_B200_ERR_CAPACITY if they did not fit (out_offsets is complete either way, so
+   a second call with out_offsets[n] entries succeeds). */
+int gcsa_b200_locate_into_host(const gcsa_b200_index* index, const uint64_t* sp, const uint64_t* ep, uint64_t n,
+                               uint64_t* out_offsets, uint64_t* values, uint64_t capacity, uint64_t* needed);
 /* The sort = false form of the same call (src/gcsa.cpp:840): every value locateInternal() emits,
    duplicates included, in the reference's order (path nodes ascending, samples in stored order). */
 int gcsa_b200_locate_raw_host(const gcsa_b200_index* index, const uint64_t* sp, const uint64_t* ep, uint64_t n,

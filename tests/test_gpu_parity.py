@@ -363,3 +363,27 @@ def test_locate_tables_agree():
             assert list(gpu.locate(rng_i, max_positions=5)) == list(ora.locate(rng_i, max_positions=5)), (walk_table, rng_i)
     for roffs, rvals in results[1:]:
         assert (roffs == results[0][0]).all() and (rvals == results[0][1]).all()
+
+
+def test_locate_into_host_buffers():
+    """gcsa_b200_locate_into_host (caller-owned buffers, chunked pipeline) == gcsa_b200_locate_host; too small a
+    buffer is reported with the needed size and complete offsets."""
+    from gcsa2_b200 import capi
+    seq = synth.random_sequence(400_000, seed=17)
+    graph, sites, alt = synth.snp_graph(seq, seed=17, snp_rate=0.02)
+    flat, _, _ = build_index(graph, 16, 2)
+    gpu = GCSA(flat, kmer_table_k=6)
+    n = 700_000                                                          # three chunks
+    chars, offsets = synth.patterns_from_snp_graph(seq, sites, alt, n, 24, seed=3)
+    sp, ep = gpu.find_batch(chars, offsets)
+    sp[::1000] = 7; ep[::1000] = 3                                       # some empty ranges
+    sp[5::5000] = 100; ep[5::5000] = 400                                 # some wide ones
+    offs, vals = gpu.locate_batch(sp, ep)
+    out_offs = np.zeros(n + 1, dtype=np.uint64); out_vals = np.zeros(vals.size + 8, dtype=np.uint64)
+    got = gpu.locate_into_host_raw(sp.ctypes.data, ep.ctypes.data, n, out_offs.ctypes.data, out_vals.ctypes.data, out_vals.size)
+    assert got == vals.size and (out_offs == offs).all() and (out_vals[:got] == vals).all()
+    small = np.zeros(vals.size // 2, dtype=np.uint64); out_offs[:] = 0
+    with pytest.raises(capi.GCSAError) as err:
+        gpu.locate_into_host_raw(sp.ctypes.data, ep.ctypes.data, n, out_offs.ctypes.data, small.ctypes.data, small.size)
+    assert err.value.code == capi.ERR_CAPACITY and (out_offs == offs).all()
+    assert gpu.locate_into_host_raw(sp.ctypes.data, ep.ctypes.data, 0, out_offs.ctypes.data, small.ctypes.data, small.size) == 0
