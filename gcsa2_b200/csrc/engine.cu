@@ -1265,11 +1265,16 @@ lcp_rmq_kernel(const LcpView l, const u64* __restrict__ sp, const u64* __restric
   slice exactly as in find_kernel.  WRITE = false counts the matches, WRITE = true stores them at
   the offsets computed from the counts.
 */
-template<bool WRITE>
+// MODE 0: count the matches of each pattern.  MODE 1: write them at out_offsets (exact positions known).
+// MODE 2: count AND write the first `stride` matches of pattern q at scratch slot q * stride (one pass; the
+// few patterns with more matches are redone in MODE 1 over the id list `ids`).
+template<int MODE>
 __global__ void __launch_bounds__(256)
 mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const u64* __restrict__ offsets, u64 char_base,
-           u64 n, u64* __restrict__ counts, const u64* __restrict__ out_offsets, u64* __restrict__ matches)
+           u64 n, u64* __restrict__ counts, const u64* __restrict__ out_offsets, u64* __restrict__ matches,
+           const u64* __restrict__ ids, u64 stride)
 {
+  constexpr bool WRITE = (MODE == 1);
   __shared__ u8 c2c[256];
   for(int i = threadIdx.x; i < 256; i += blockDim.x) { c2c[i] = v.char2comp[i]; }
   __syncthreads();
@@ -1296,10 +1301,11 @@ mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const
         u64 cand = next + my;
         if(cand < slice_end)
         {
-          q = cand; live = true;
+          q = (ids != nullptr ? ids[cand] : cand); live = true;
           begin = offsets[q] - char_base; pos = offsets[q + 1] - char_base;
           sp = 0; ep = v.path_nodes - 1; depth = 0; extended = false; emitted = 0;
           if(WRITE) { out_at = out_offsets[q]; }
+          if(MODE == 2) { out_at = q * stride; }
         }
       }
       next += __popc(dead);
@@ -1312,7 +1318,7 @@ mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const
     {
       if(depth > 0 && extended)
       {
-        if(WRITE) { u64* m = matches + 4 * (out_at + emitted); m[0] = 0; m[1] = depth; m[2] = sp; m[3] = ep; }
+        if(WRITE || (MODE == 2 && emitted < stride)) { u64* m = matches + 4 * (out_at + emitted); m[0] = 0; m[1] = depth; m[2] = sp; m[3] = ep; }
         emitted++;
       }
       if(!WRITE) { counts[q] = emitted; }
@@ -1325,12 +1331,36 @@ mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const
     if(depth == 0) { pos--; continue; }
     if(extended)
     {
-      if(WRITE) { u64* m = matches + 4 * (out_at + emitted); m[0] = pos - begin; m[1] = depth; m[2] = sp; m[3] = ep; }
+      if(WRITE || (MODE == 2 && emitted < stride)) { u64* m = matches + 4 * (out_at + emitted); m[0] = pos - begin; m[1] = depth; m[2] = sp; m[3] = ep; }
       emitted++; extended = false;
     }
     gcsa_b200_stnode node = lcp_parent(l, sp, ep);
     sp = node.sp; ep = node.ep; depth = node.node_lcp;
   }
+}
+
+// scratch (stride matches per pattern) -> CSR; patterns with more than `stride` matches are listed in `overflow`
+__global__ void __launch_bounds__(256)
+mem_gather_kernel(const ulonglong4* __restrict__ scratch, const u64* __restrict__ counts, const u64* __restrict__ out_offsets,
+                  u64 n, u64 stride, ulonglong4* __restrict__ matches, u64* __restrict__ overflow, ull* __restrict__ n_overflow)
+{
+  for(u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (u64)gridDim.x * blockDim.x)
+  {
+    u64 c = counts[q];
+    if(c > stride) { overflow[atomicAdd(n_overflow, 1ull)] = q; continue; }
+    const ulonglong4* src = scratch + q * stride;
+    ulonglong4* dst = matches + out_offsets[q];
+    for(u64 e = 0; e < c; e++) { dst[e] = src[e]; }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+mem_count_overflow_kernel(const u64* __restrict__ counts, u64 n, u64 stride, ull* __restrict__ n_overflow)
+{
+  ull mine = 0;
+  for(u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (u64)gridDim.x * blockDim.x) { mine += (counts[q] > stride ? 1 : 0); }
+  for(int d = 16; d > 0; d >>= 1) { mine += __shfl_down_sync(0xFFFFFFFFu, mine, d); }
+  if((threadIdx.x & 31) == 0 && mine > 0) { atomicAdd(n_overflow, mine); }
 }
 
 //------------------------------------------------------------------------------
@@ -2855,33 +2885,91 @@ done:
 // MEM-style scan
 //------------------------------------------------------------------------------
 
-int gcsa_b200_mem_batch(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, const uint8_t* d_chars, const uint64_t* d_offsets,
-                        uint64_t n, uint64_t* d_out_offsets, uint64_t* d_matches, uint64_t capacity, uint64_t* needed, void* stream)
+/*
+  One pass over the patterns: every lane counts its matches and writes the first `stride` of them into a
+  scratch slot of its pattern; after the scan of the counts a gather kernel moves them into the CSR, and the
+  few patterns with more matches are redone writing at their final positions.  (The first version ran the
+  whole scan twice, once to count and once to write.)  d_matches_alloc != NULL: the values are allocated
+  here (stream-ordered) instead of being written to d_matches.
+*/
+static int memDevice(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, const uint8_t* d_chars, const uint64_t* d_offsets,
+                     uint64_t n, uint64_t* d_out_offsets, uint64_t* d_matches, uint64_t capacity, uint64_t* needed, cudaStream_t st,
+                     u64** d_matches_alloc)
 {
   if(index == nullptr || lcp == nullptr || d_out_offsets == nullptr) { return fail(GCSA_B200_ERR_INVALID, "mem_batch: null argument"); }
   if(index->device != lcp->device) { return fail(GCSA_B200_ERR_INVALID, "mem_batch: index and LCP array live on different devices"); }
   if(index->header.path_nodes != lcp->view.size) { return fail(GCSA_B200_ERR_INVALID, "mem_batch: index and LCP array have different sizes"); }
   DeviceGuard guard(index->device);
-  cudaStream_t st = (cudaStream_t)stream;
   if(needed) { *needed = 0; }
+  if(d_matches_alloc) { *d_matches_alloc = nullptr; }
   CUDA_TRY(cudaMemsetAsync(d_out_offsets, 0, (n + 1) * sizeof(u64), st));
   if(n == 0 || index->header.path_nodes == 0) { return 0; }
-  u64* counts = nullptr;
-  CUDA_TRY(cudaMallocAsync(&counts, (n + 1) * sizeof(u64), st));
-  CUDA_TRY(cudaMemsetAsync(counts, 0, (n + 1) * sizeof(u64), st));
+
+  // scratch: up to 16 matches per pattern, fewer for huge batches, none (two full passes) if even 4 do not fit
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  u64 stride = std::min<u64>(16, (free_b / 8) / (n * 32));
+  if(const char* e = std::getenv("GCSA_B200_MEM_STRIDE")) { stride = std::min<u64>(stride, (u64)std::atoi(e)); }   // tests: 0 = two passes
+  if(stride < 4 && std::getenv("GCSA_B200_MEM_STRIDE") == nullptr) { stride = 0; }
+
+  std::vector<void*> tmp;
+  auto alloc = [&](u64 bytes) -> void* { void* p = nullptr; if(cudaMallocAsync(&p, std::max<u64>(bytes, 16), st) != cudaSuccess) { cudaGetLastError(); return nullptr; } tmp.push_back(p); return p; };
+  auto cleanup = [&]() { for(void* p : tmp) { cudaFreeAsync(p, st); } tmp.clear(); };
+  #define MEM_TRY(expr) do { cudaError_t e_ = (expr); if(e_ != cudaSuccess) { cleanup(); \
+    return fail(GCSA_B200_ERR_CUDA, std::string("mem_batch: " #expr ": ") + cudaGetErrorString(e_)); } } while(0)
+
+  u64* counts = (u64*)alloc((n + 1) * sizeof(u64));
+  ull* n_overflow = (ull*)alloc(sizeof(ull));
+  u64* scratch = (stride > 0 ? (u64*)alloc(n * stride * 32) : nullptr);
+  if(counts == nullptr || n_overflow == nullptr) { cleanup(); return fail(GCSA_B200_ERR_NOMEM, "mem_batch: out of device memory"); }
+  if(scratch == nullptr) { stride = 0; }
+  MEM_TRY(cudaMemsetAsync(counts, 0, (n + 1) * sizeof(u64), st));
+  MEM_TRY(cudaMemsetAsync(n_overflow, 0, sizeof(ull), st));
   int grid = gridFor(n, index->sm_count, 4);
-  mem_kernel<false><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, nullptr);
+  if(stride > 0) { mem_kernel<2><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, scratch, nullptr, stride); }
+  else { mem_kernel<0><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, nullptr, nullptr, 0); }
   int rc = scanExclusive(counts, (u64*)d_out_offsets, n + 1, st);
-  cudaFreeAsync(counts, st);
-  if(rc) { return rc; }
-  u64 total = 0;
-  CUDA_TRY(cudaMemcpyAsync(&total, (u64*)d_out_offsets + n, sizeof(u64), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  if(rc) { cleanup(); return rc; }
+  if(stride > 0) { mem_count_overflow_kernel<<<gridFor(n, index->sm_count), 256, 0, st>>>(counts, n, stride, n_overflow); }
+  u64 total = 0; ull overflowing = 0;
+  MEM_TRY(cudaMemcpyAsync(&total, (u64*)d_out_offsets + n, sizeof(u64), cudaMemcpyDeviceToHost, st));
+  MEM_TRY(cudaMemcpyAsync(&overflowing, n_overflow, sizeof(ull), cudaMemcpyDeviceToHost, st));
+  MEM_TRY(cudaStreamSynchronize(st));
   if(needed) { *needed = total; }
-  if(d_matches == nullptr || capacity < total) { return fail(GCSA_B200_ERR_CAPACITY, "mem_batch: output capacity too small"); }
-  mem_kernel<true><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, nullptr, (const u64*)d_out_offsets, (u64*)d_matches);
-  CUDA_TRY(cudaGetLastError());
+  if(d_matches_alloc != nullptr)
+  {
+    void* p = nullptr;
+    MEM_TRY(cudaMallocAsync(&p, std::max<u64>(total, 1) * 32, st));
+    *d_matches_alloc = (u64*)p; d_matches = (u64*)p; capacity = total;
+  }
+  if(d_matches == nullptr || capacity < total) { cleanup(); return fail(GCSA_B200_ERR_CAPACITY, "mem_batch: output capacity too small"); }
+  if(stride == 0)
+  {
+    mem_kernel<1><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, nullptr, (const u64*)d_out_offsets, (u64*)d_matches, nullptr, 0);
+  }
+  else
+  {
+    u64* overflow = (u64*)alloc(std::max<u64>(overflowing, 1) * sizeof(u64));
+    if(overflow == nullptr) { cleanup(); return fail(GCSA_B200_ERR_NOMEM, "mem_batch: out of device memory"); }
+    MEM_TRY(cudaMemsetAsync(n_overflow, 0, sizeof(ull), st));
+    mem_gather_kernel<<<gridFor(n, index->sm_count), 256, 0, st>>>((const ulonglong4*)scratch, counts, (const u64*)d_out_offsets, n, stride,
+                                                                   (ulonglong4*)d_matches, overflow, n_overflow);
+    if(overflowing > 0)
+    {
+      mem_kernel<1><<<gridFor(overflowing, index->sm_count, 4), 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, overflowing,
+                                                                            nullptr, (const u64*)d_out_offsets, (u64*)d_matches, overflow, 0);
+    }
+  }
+  MEM_TRY(cudaGetLastError());
+  cleanup();
+  #undef MEM_TRY
   return 0;
+}
+
+int gcsa_b200_mem_batch(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, const uint8_t* d_chars, const uint64_t* d_offsets,
+                        uint64_t n, uint64_t* d_out_offsets, uint64_t* d_matches, uint64_t capacity, uint64_t* needed, void* stream)
+{
+  return memDevice(index, lcp, d_chars, d_offsets, n, d_out_offsets, d_matches, capacity, needed, (cudaStream_t)stream, nullptr);
 }
 
 int gcsa_b200_mem_host(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, const uint8_t* chars, const uint64_t* offsets,
@@ -2895,17 +2983,12 @@ int gcsa_b200_mem_host(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, c
   u64* d_off = sc.in((const u64*)offsets, n + 1);
   u64* d_out = sc.alloc<u64>(n + 1);
   u64 needed = 0;
-  int rc = gcsa_b200_mem_batch(index, lcp, d_chars, d_off, n, d_out, nullptr, 0, &needed, sc.stream);
-  if(rc == GCSA_B200_ERR_CAPACITY || (rc == 0 && needed == 0))
+  u64* d_vals = nullptr;
+  int rc = memDevice(index, lcp, d_chars, d_off, n, d_out, nullptr, 0, &needed, sc.stream, &d_vals);
+  if(rc == 0)
   {
-    rc = 0;
     u64* vals = (u64*)std::malloc(std::max<u64>(4 * needed, 1) * sizeof(u64));
-    if(needed > 0)
-    {
-      u64* d_vals = sc.alloc<u64>(4 * needed);
-      rc = gcsa_b200_mem_batch(index, lcp, d_chars, d_off, n, d_out, d_vals, needed, &needed, sc.stream);
-      sc.out(vals, d_vals, 4 * needed);
-    }
+    if(d_vals != nullptr) { sc.out(vals, d_vals, 4 * needed); sc.ptrs.push_back(d_vals); }
     sc.out((u64*)out_offsets, d_out, n + 1);
     *matches = (uint64_t*)vals;
   }

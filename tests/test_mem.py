@@ -59,3 +59,40 @@ def test_mem_scan_device_matches_definition():
     assert (offs == eoffs).all() and (vals == evals).all()
     offs, vals = mem_batch(gpu, glcp, [])
     assert list(offs) == [0] and vals.shape == (0, 4)
+
+
+@pytest.mark.gpu
+def test_mem_scan_scratch_paths(monkeypatch):
+    """The one-pass scan (matches staged in a per-pattern scratch slot, overflowing patterns redone), with
+    slots of 16, 4 and 1 matches, and the two-pass fallback: all equal to the definition.  Noisy patterns
+    (10 % substitutions) so that many patterns have more matches than a slot holds."""
+    from gcsa2_b200 import GCSA, LCPArray, mem_batch, mem_device
+    import torch
+    seq = synth.random_sequence(100_000, seed=5)
+    graph, sites, alt = synth.snp_graph(seq, seed=5, snp_rate=0.01)
+    flat, flcp, _ = build_index(graph, 16, 3)
+    chars, offsets = synth.mixed_length_patterns(seq, sites, alt, 20_000, 16, 256, seed=11, error_rate=0.10)
+    index, lcp = orc.OracleGCSA(flat), orc.OracleLCP(flcp)
+    ooffs, ovals, _ = orc.mem_batch(index, lcp, chars, offsets, threads=8)
+    counts = np.diff(ooffs.astype(np.int64))
+    assert (counts > 16).sum() > 100 and (counts <= 4).sum() > 100
+    gpu, glcp = GCSA(flat, kmer_table_k=0), LCPArray(flcp)
+    for stride in ("16", "4", "1", "0"):
+        monkeypatch.setenv("GCSA_B200_MEM_STRIDE", stride)
+        offs, vals = mem_batch(gpu, glcp, chars, offsets)
+        assert (offs == ooffs).all() and vals.shape == ovals.shape and (vals == ovals).all(), stride
+    monkeypatch.delenv("GCSA_B200_MEM_STRIDE")
+    # device entry point with a caller buffer: too small -> the needed size, then the same answer
+    from gcsa2_b200 import capi
+    n = len(offsets) - 1
+    d_chars = torch.from_numpy(chars).cuda(); d_off = torch.from_numpy(offsets.view(np.int64)).cuda()
+    d_out = torch.empty(n + 1, dtype=torch.int64, device="cuda")
+    small = torch.empty((10, 4), dtype=torch.int64, device="cuda")
+    with pytest.raises(capi.GCSAError) as err:
+        mem_device(gpu, glcp, d_chars, d_off, n, d_out, small, 10, torch.cuda.current_stream().cuda_stream)
+    assert err.value.code == capi.ERR_CAPACITY
+    total = int(ooffs[-1])
+    big = torch.empty((total, 4), dtype=torch.int64, device="cuda")
+    got = mem_device(gpu, glcp, d_chars, d_off, n, d_out, big, total, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert got == total and (d_out.cpu().numpy().view(np.uint64) == ooffs).all() and (big.cpu().numpy().view(np.uint64) == ovals).all()
