@@ -90,6 +90,7 @@ struct DevView
 struct LcpView
 {
   u64 size, branching, levels, values;
+  int shift;                           // log2(branching) if it is a power of two, else -1
   u64 offsets[16];
   const u8* data;
 };
@@ -1057,8 +1058,16 @@ locate_table_kernel(const DevView v, u64* table, int* overflow)
 
 struct Pair64 { u64 first, second; };
 
-__device__ __forceinline__ u64 rmt_parent(const LcpView& l, u64 node, u64 level) { return l.offsets[level + 1] + (node - l.offsets[level]) / l.branching; }
-__device__ __forceinline__ u64 rmt_first_sibling(const LcpView& l, u64 node, u64 level) { return node - (node - l.offsets[level]) % l.branching; }
+__device__ __forceinline__ u64 rmt_parent(const LcpView& l, u64 node, u64 level)
+{
+  u64 rel = node - l.offsets[level];
+  return l.offsets[level + 1] + (l.shift >= 0 ? rel >> l.shift : rel / l.branching);
+}
+__device__ __forceinline__ u64 rmt_first_sibling(const LcpView& l, u64 node, u64 level)
+{
+  u64 rel = node - l.offsets[level];
+  return node - (l.shift >= 0 ? rel & (l.branching - 1) : rel % l.branching);
+}
 __device__ __forceinline__ u64 rmt_last_sibling(const LcpView& l, u64 first_child, u64 level)
 { u64 a = l.offsets[level + 1], b = first_child + l.branching; return (a < b ? a : b) - 1; }
 __device__ __forceinline__ u64 rmt_first_child(const LcpView& l, u64 node, u64 level) { return l.offsets[level - 1] + (node - l.offsets[level]) * l.branching; }
@@ -1067,30 +1076,69 @@ __device__ __forceinline__ u64 rmt_level(const LcpView& l, u64 node) { u64 level
 
 template<bool OR_EQUAL> __device__ __forceinline__ bool sv_less(u64 a, u64 b) { return (OR_EQUAL ? a <= b : a < b); }
 
+// The sibling scans of psv / nsv (lcp.cpp:354-367, 410-423) read the one-byte values eight at a time:
+// 0x80 in every byte of x that is < thr (1 <= thr <= 256).
+__device__ __forceinline__ u64 bytes_below(u64 x, u32 thr)
+{
+  if(thr >= 256) { return 0x8080808080808080ull; }
+  u32 t = thr * 0x01010101u;
+  u32 lo = __vcmpltu4((u32)x, t), hi = __vcmpltu4((u32)(x >> 32), t);
+  return (((u64)hi << 32) | lo) & 0x8080808080808080ull;
+}
+
+// first / last index in [a, b] (a <= b) whose value is < thr; ~0 if there is none
+__device__ __forceinline__ u64 scan_up(const u8* __restrict__ data, u64 a, u64 b, u32 thr)
+{
+  if(thr == 0) { return ~0ull; }
+  const u64 w0 = a >> 3, w1 = b >> 3;
+  for(u64 w = w0; w <= w1; w++)
+  {
+    u64 m = bytes_below(__ldg((const unsigned long long*)data + w), thr);
+    if(w == w0) { m &= ~0ull << ((a & 7) * 8); }
+    if(w == w1) { m &= ~0ull >> ((7 - (b & 7)) * 8); }
+    if(m) { return w * 8 + ((u64)(__ffsll((long long)m) - 1) >> 3); }
+  }
+  return ~0ull;
+}
+
+__device__ __forceinline__ u64 scan_down(const u8* __restrict__ data, u64 a, u64 b, u32 thr)
+{
+  if(thr == 0) { return ~0ull; }
+  const u64 w0 = a >> 3, w1 = b >> 3;
+  for(u64 w = w1; ; w--)
+  {
+    u64 m = bytes_below(__ldg((const unsigned long long*)data + w), thr);
+    if(w == w0) { m &= ~0ull << ((a & 7) * 8); }
+    if(w == w1) { m &= ~0ull >> ((7 - (b & 7)) * 8); }
+    if(m) { return w * 8 + ((u64)(63 - __clzll((long long)m)) >> 3); }
+    if(w == w0) { break; }
+  }
+  return ~0ull;
+}
+
 // lcp.cpp:333-370
 template<bool OR_EQUAL>
 __device__ Pair64 lcp_psv(const LcpView& l, u64 to)
 {
   Pair64 nf = { l.values, l.values };
   if(to == 0 || to >= l.size) { return nf; }
-  u64 level = 0, val = l.data[to];
-  Pair64 res = nf;
+  u64 level = 0;
+  const u32 thr = (u32)l.data[to] + (OR_EQUAL ? 1 : 0);
+  u64 found = ~0ull;
   while(to != l.values - 1)
   {
-    u64 from = rmt_first_sibling(l, to, level), i = to;
-    res = nf;
-    while(i > from) { i--; u64 x = l.data[i]; if(sv_less<OR_EQUAL>(x, val)) { res.first = i; res.second = x; break; } }
-    if(res.first < l.values) { break; }
+    u64 from = rmt_first_sibling(l, to, level);
+    found = (to > from ? scan_down(l.data, from, to - 1, thr) : ~0ull);
+    if(found != ~0ull) { break; }
     to = rmt_parent(l, to, level); level++;
   }
-  if(res.first >= l.values) { return res; }
+  if(found == ~0ull) { return nf; }
   while(level > 0)
   {
-    u64 from = rmt_first_child(l, res.first, level); level--;
-    u64 i = rmt_last_sibling(l, from, level) + 1;
-    res = nf;
-    while(i > from) { i--; u64 x = l.data[i]; if(sv_less<OR_EQUAL>(x, val)) { res.first = i; res.second = x; break; } }
+    u64 from = rmt_first_child(l, found, level); level--;
+    found = scan_down(l.data, from, rmt_last_sibling(l, from, level), thr);
   }
+  Pair64 res = { found, l.data[found] };
   return res;
 }
 
@@ -1100,24 +1148,23 @@ __device__ Pair64 lcp_nsv(const LcpView& l, u64 from)
 {
   Pair64 nf = { l.values, l.values };
   if(from + 1 >= l.size) { return nf; }
-  u64 level = 0, val = l.data[from];
-  Pair64 res = nf;
+  u64 level = 0;
+  const u32 thr = (u32)l.data[from] + (OR_EQUAL ? 1 : 0);
+  u64 found = ~0ull;
   while(from != l.values - 1)
   {
     u64 to = rmt_last_sibling(l, from, level);
-    res = nf;
-    for(u64 i = from + 1; i <= to; i++) { u64 x = l.data[i]; if(sv_less<OR_EQUAL>(x, val)) { res.first = i; res.second = x; break; } }
-    if(res.first < l.values) { break; }
+    found = (from + 1 <= to ? scan_up(l.data, from + 1, to, thr) : ~0ull);
+    if(found != ~0ull) { break; }
     from = rmt_parent(l, from, level); level++;
   }
-  if(res.first >= l.values) { return res; }
+  if(found == ~0ull) { return nf; }
   while(level > 0)
   {
-    from = rmt_first_child(l, res.first, level); level--;
-    u64 to = rmt_last_sibling(l, from, level);
-    res = nf;
-    for(u64 i = from; i <= to; i++) { u64 x = l.data[i]; if(sv_less<OR_EQUAL>(x, val)) { res.first = i; res.second = x; break; } }
+    from = rmt_first_child(l, found, level); level--;
+    found = scan_up(l.data, from, rmt_last_sibling(l, from, level), thr);
   }
+  Pair64 res = { found, l.data[found] };
   return res;
 }
 
@@ -1272,7 +1319,7 @@ template<int MODE>
 __global__ void __launch_bounds__(256)
 mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const u64* __restrict__ offsets, u64 char_base,
            u64 n, u64* __restrict__ counts, const u64* __restrict__ out_offsets, u64* __restrict__ matches,
-           const u64* __restrict__ ids, u64 stride)
+           const u64* __restrict__ ids, u64 stride, u32 parent_batch)
 {
   constexpr bool WRITE = (MODE == 1);
   __shared__ u8 c2c[256];
@@ -1288,7 +1335,7 @@ mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const
   if(next >= n || v.path_nodes == 0) { return; }
 
   u64 q = 0, sp = 0, ep = 0, depth = 0, pos = 0, begin = 0, emitted = 0, out_at = 0;
-  bool live = false, extended = false;
+  bool live = false, extended = false, need_parent = false;
 
   while(true)
   {
@@ -1301,7 +1348,7 @@ mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const
         u64 cand = next + my;
         if(cand < slice_end)
         {
-          q = (ids != nullptr ? ids[cand] : cand); live = true;
+          q = (ids != nullptr ? ids[cand] : cand); live = true; need_parent = false;
           begin = offsets[q] - char_base; pos = offsets[q + 1] - char_base;
           sp = 0; ep = v.path_nodes - 1; depth = 0; extended = false; emitted = 0;
           if(WRITE) { out_at = out_offsets[q]; }
@@ -1312,7 +1359,24 @@ mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const
       if(next > slice_end) { next = slice_end; }
     }
     if(__ballot_sync(0xFFFFFFFFu, live) == 0) { break; }
-    if(!live) { continue; }
+
+    // Two phases, chosen per warp: backward steps for the lanes that can take one, or parent() for the lanes
+    // whose step failed.  parent() is several times longer than a step, so lanes waiting for it are held back
+    // until `parent_batch` of them wait (or nobody can step): the long path then runs with many lanes active
+    // instead of one or two.
+    u32 waiting = __ballot_sync(0xFFFFFFFFu, live && need_parent);
+    u32 stepping = __ballot_sync(0xFFFFFFFFu, live && !need_parent);
+    if(waiting != 0 && ((u32)__popc(waiting) >= parent_batch || stepping == 0))
+    {
+      if(live && need_parent)
+      {
+        gcsa_b200_stnode node = lcp_parent(l, sp, ep);
+        sp = node.sp; ep = node.ep; depth = node.node_lcp;
+        need_parent = false;
+      }
+      continue;
+    }
+    if(!live || need_parent) { continue; }
 
     if(pos == begin)
     {
@@ -1334,8 +1398,7 @@ mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const
       if(WRITE || (MODE == 2 && emitted < stride)) { u64* m = matches + 4 * (out_at + emitted); m[0] = pos - begin; m[1] = depth; m[2] = sp; m[3] = ep; }
       emitted++; extended = false;
     }
-    gcsa_b200_stnode node = lcp_parent(l, sp, ep);
-    sp = node.sp; ep = node.ep; depth = node.node_lcp;
+    need_parent = true;
   }
 }
 
@@ -2625,7 +2688,10 @@ int gcsa_b200_lcp_create(const gcsa_flat_lcp* host, int device, gcsa_b200_lcp** 
   for(u64 i = 0; i <= host->levels; i++) { v.offsets[i] = host->offsets[i]; }
   for(u64 i = host->levels + 1; i < 16; i++) { v.offsets[i] = ~0ull; }
   v.values = host->offsets[host->levels];
-  cudaError_t e = cudaMalloc(&l->data, std::max<u64>(v.values, 16));
+  v.shift = -1;
+  if((host->branching & (host->branching - 1)) == 0) { v.shift = 0; while((1ull << v.shift) < host->branching) { v.shift++; } }
+  cudaError_t e = cudaMalloc(&l->data, ((std::max<u64>(v.values, 16) + 15) / 8) * 8);      // whole 8-byte words (the scans read words)
+  if(e == cudaSuccess) { e = cudaMemset(l->data, 0xFF, ((std::max<u64>(v.values, 16) + 15) / 8) * 8); }
   if(e == cudaSuccess && v.values) { e = cudaMemcpy(l->data, host->data, v.values, cudaMemcpyHostToDevice); }
   if(e != cudaSuccess) { if(l->data) { cudaFree(l->data); } delete l; return fail(GCSA_B200_ERR_CUDA, std::string("lcp_create: ") + cudaGetErrorString(e)); }
   v.data = (const u8*)l->data;
@@ -2926,8 +2992,10 @@ static int memDevice(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, con
   MEM_TRY(cudaMemsetAsync(counts, 0, (n + 1) * sizeof(u64), st));
   MEM_TRY(cudaMemsetAsync(n_overflow, 0, sizeof(ull), st));
   int grid = gridFor(n, index->sm_count, 4);
-  if(stride > 0) { mem_kernel<2><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, scratch, nullptr, stride); }
-  else { mem_kernel<0><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, nullptr, nullptr, 0); }
+  u32 parent_batch = 8;
+  if(const char* e = std::getenv("GCSA_B200_MEM_PARENT_BATCH")) { parent_batch = (u32)std::max(1, std::atoi(e)); }
+  if(stride > 0) { mem_kernel<2><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, scratch, nullptr, stride, parent_batch); }
+  else { mem_kernel<0><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, nullptr, nullptr, 0, parent_batch); }
   int rc = scanExclusive(counts, (u64*)d_out_offsets, n + 1, st);
   if(rc) { cleanup(); return rc; }
   if(stride > 0) { mem_count_overflow_kernel<<<gridFor(n, index->sm_count), 256, 0, st>>>(counts, n, stride, n_overflow); }
@@ -2945,7 +3013,7 @@ static int memDevice(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, con
   if(d_matches == nullptr || capacity < total) { cleanup(); return fail(GCSA_B200_ERR_CAPACITY, "mem_batch: output capacity too small"); }
   if(stride == 0)
   {
-    mem_kernel<1><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, nullptr, (const u64*)d_out_offsets, (u64*)d_matches, nullptr, 0);
+    mem_kernel<1><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, nullptr, (const u64*)d_out_offsets, (u64*)d_matches, nullptr, 0, parent_batch);
   }
   else
   {
@@ -2957,7 +3025,7 @@ static int memDevice(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, con
     if(overflowing > 0)
     {
       mem_kernel<1><<<gridFor(overflowing, index->sm_count, 4), 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, overflowing,
-                                                                            nullptr, (const u64*)d_out_offsets, (u64*)d_matches, overflow, 0);
+                                                                            nullptr, (const u64*)d_out_offsets, (u64*)d_matches, overflow, 0, parent_batch);
     }
   }
   MEM_TRY(cudaGetLastError());
