@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--ref-mbp", type=float, default=100.0, help="length of the synthetic linear reference (Mbp)")
     ap.add_argument("--queries", type=int, default=10_000_000, help="patterns per GPU")
     ap.add_argument("--pattern-length", type=int, default=32)
-    ap.add_argument("--kmer-table-k", type=int, default=14)
+    ap.add_argument("--kmer-table-k", type=int, default=16, help="k-mer table: find() of all 4^k ACGT strings, 8 B each (16 = 34 GB; profiles/r01_kmer_table_sweep.txt)")
     ap.add_argument("--two-step", type=int, default=-1, help="1 = build and use the two-step blocks, 0 = never, -1 = by index size")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -214,7 +214,7 @@ def locate_leg(args, rank, world, local, barrier, dist, torch):
         m = min(1_000_000, n - q0)
         c, _ = synth.patterns_from_snp_graph(seq, sites, alt, m, length, seed=7000 + 100 * rank + i)
         chars[q0 * length:(q0 + m) * length] = c
-    index = GCSA(flat, device=local, kmer_table_k=args.kmer_table_k)
+    index = GCSA(flat, device=local, kmer_table_k=min(12, args.kmer_table_k))     # find() is untimed here
     stream = torch.cuda.current_stream()
     d_chars = torch.from_numpy(chars).cuda()
     d_sp = torch.empty(n, dtype=torch.int64, device="cuda"); d_ep = torch.empty_like(d_sp)
@@ -301,13 +301,14 @@ def peaks():
 
 def recorded_traffic(args, index):
     """dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture of this
-    very configuration (profiles/traffic_find_cfg2.json); None for any other configuration."""
+    very configuration (profiles/traffic_find_cfg2.json, one entry per k-mer table size); None for any other."""
     path = os.path.join(ROOT, "profiles", "traffic_find_cfg2.json")
-    default = (args.ref_mbp == 100.0 and args.queries == 10_000_000 and args.pattern_length == 32
-               and index.kmerTableK() == 14 and not index.twoStep())
+    default = (args.ref_mbp == 100.0 and args.queries == 10_000_000 and args.pattern_length == 32 and not index.twoStep())
     if default and os.path.exists(path):
         with open(path) as f:
-            return float(json.load(f)["dram_bytes_per_launch"])
+            entry = json.load(f).get("k%d" % index.kmerTableK())
+        if entry:
+            return float(entry["dram_bytes_per_launch"])
     return None
 
 
