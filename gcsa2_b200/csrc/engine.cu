@@ -83,6 +83,7 @@ struct DevView
   const u64* stored_samples; const u64* sample_start; u64 sample_count;
   const u64* table; int table_k;      // entry = sp | length << 40; length 0xFFFFFF = not tabulated
   const u32* walk32; const u64* walk64; // locate walk table: LF(i) << 1, or rank(sampled, i) << 1 | 1 for sampled nodes
+  const u64* jump; u32 jump_k, jump_tbits;   // jump table: len << 59 | 2-bit chars << jump_tbits | target (see jump_extend_kernel)
   const u64* loc64;                    // locate table: bit 63 | value for nodes with one start position, else rank of the sampled node << 24 | steps
   u8 char2comp[256];
 };
@@ -356,7 +357,7 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
   if(next >= n) { return; }
 
   u64 q = ~0ull, sp = 0, ep = 0, pos = 0, begin = 0;
-  bool live = false;
+  bool live = false, try_jump = true;
   CharWindow win;
   u64 st_found = 0, st_len = 0, st_steps = 0, st_sectors = 0, st_hits = 0;
   // comp value of the character at (batch-wide) position p of the current query
@@ -387,7 +388,7 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
           u64 b, e;
           if(offsets != nullptr) { b = offsets[q] - char_base; e = offsets[q + 1] - char_base; }
           else { b = q * fixed_length; e = b + fixed_length; }
-          begin = b; live = true;
+          begin = b; live = true; try_jump = true;
           if(e == b || v.path_nodes == 0) { sp = 0; ep = v.path_nodes - 1; pos = b; }
           else
           {
@@ -436,10 +437,38 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
       }
       else
       {
-        u32 c = comp_at(pos - 1);
         u32 sectors = 0;
         bool done = false;
-        if(v.bwt2 != nullptr && pos - begin >= 2 && c >= 1 && c <= 4)
+        // Singleton range: try the jump table (one load for up to jump_k backward steps along a unary path).
+        if(v.jump != nullptr && try_jump && sp == ep && pos - begin >= 2)
+        {
+          u64 e = __ldg(v.jump + sp);
+          u32 len = (u32)(e >> 59);
+          if(STATS) { sectors++; }
+          if(len >= 2)
+          {
+            if((u64)len > pos - begin) { try_jump = false; }           // the pattern ends inside the jump: single steps from here
+            else
+            {
+              u64 stored = ((e << 5) >> 5) >> v.jump_tbits;
+              bool same = true;
+              for(u32 t = 0; t < len; t++)
+              {
+                u32 pc = comp_at(pos - 1 - t);
+                same = same && (pc == ((u32)(stored >> (2 * t)) & 3) + 1);
+              }
+              if(same)
+              {
+                sp = ep = (e & ((1ull << v.jump_tbits) - 1));
+                pos -= len; done = true;
+                if(STATS) { st_steps += len; }
+              }
+              else { try_jump = false; }                               // it dies within these steps: the exact pair comes from single steps
+            }
+          }
+        }
+        u32 c = (done ? 0 : comp_at(pos - 1));
+        if(!done && v.bwt2 != nullptr && pos - begin >= 2 && c >= 1 && c <= 4)
         {
           u32 c1 = comp_at(pos - 2);
           if(c1 >= 1 && c1 <= 4 && lf2_range(v, sp, ep, c1, c, sp, ep, STATS ? &sectors : nullptr))
@@ -1019,6 +1048,63 @@ walk_table_kernel(const DevView v, T* table)
     u64 r;
     if(rv_get_rank(v.sampled, i, r)) { table[i] = (T)((r << 1) | 1); }
     else { table[i] = (T)(lf_node(v, i) << 1); }
+  }
+}
+
+/*
+  Jump table for find(): for a path node i whose backward path is unary for len steps (every node on it has
+  exactly one predecessor character, a base), the entry holds those len characters and the node reached:
+  LF applied len times to the singleton range [i, i] gives exactly [target, target] when the pattern continues
+  with these characters (each step maps a singleton to a singleton), so one load replaces len backward steps.
+  Entry: len (5 bits) << 59 | characters (comp - 1, 2 bits each, first step lowest) << tbits | target (tbits).
+  Level 1 is computed from the fused blocks and the sparse lists, longer paths by appending level-1 entries.
+*/
+__global__ void __launch_bounds__(256)
+jump_init_kernel(const DevView v, u32 tbits, u64* __restrict__ one, u64* __restrict__ table)
+{
+  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < v.path_nodes; i += (u64)gridDim.x * blockDim.x)
+  {
+    u64 b = i / BWT_W; u32 off = (u32)(i - b * BWT_W);
+    const ulonglong4* line = v.bwt + b * 4;
+    u32 found = 0, which = 0; u64 target = 0;
+    #pragma unroll
+    for(int c = 0; c < 4; c++)
+    {
+      ulonglong4 q = ld256(line + c);
+      bool bit = (off < 64 ? (q.y >> off) & 1 : ((q.x >> 40) >> (off - 64)) & 1);
+      if(bit)
+      {
+        u32 j = popc_low88(q.y, (u32)(q.x >> 40), off);
+        target = (q.z & M40) + popc_low88(q.w, (u32)(q.z >> 40), j + 1);
+        which = (u32)c; found++;
+      }
+    }
+    bool sparse = false;
+    for(int slot = 0; slot < 3; slot++)
+    {
+      u64 r = sparse_rank(v.sparse_pos[slot], v.sparse_n[slot], i);
+      if(r < v.sparse_n[slot] && v.sparse_pos[slot][r] == i) { sparse = true; }
+    }
+    u64 e = 0;
+    if(found == 1 && !sparse) { e = (1ull << 59) | ((u64)which << tbits) | target; }
+    one[i] = e; table[i] = e;
+  }
+}
+
+// entries of length exactly j grow to j + 1 if the node they reach has a level-1 entry
+__global__ void __launch_bounds__(256)
+jump_extend_kernel(u64 n, u32 tbits, u32 j, const u64* __restrict__ one, u64* __restrict__ table)
+{
+  const u64 tmask = (1ull << tbits) - 1;
+  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+  {
+    u64 e = table[i];
+    if((e >> 59) != j) { continue; }
+    u64 next = __ldg(one + (e & tmask));
+    if((next >> 59) == 0) { continue; }
+    u64 chars = ((e << 5) >> 5) >> tbits;
+    chars |= ((next >> tbits) & 3) << (2 * j);
+    table[i] = ((u64)(j + 1) << 59) | (chars << tbits) | (next & tmask);
   }
 }
 
@@ -1831,6 +1917,40 @@ int gcsa_b200_index_create(const gcsa_flat_index* host, int device, const gcsa_b
     }
   }
 
+  // jump table (optional; 8 bytes per path node + as much again while it is built)
+  {
+    int want = (options != nullptr ? options->jump_table : 0);        // 0 = automatic, 1 = build, -1 = do not
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    size_t bytes = (size_t)N * sizeof(u64);
+    u32 tbits = 1; while((1ull << tbits) < N) { tbits++; }
+    int max_len = std::min<int>(16, (59 - (int)tbits) / 2);
+    if(N > 0 && want >= 0 && max_len >= 2 && (want > 0 || 2 * bytes < free_b / 2))
+    {
+      u64 *one = nullptr, *table = nullptr;
+      cudaError_t e = cudaMalloc((void**)&one, bytes);
+      if(e == cudaSuccess) { e = cudaMalloc((void**)&table, bytes); }
+      if(e == cudaSuccess)
+      {
+        jump_init_kernel<<<gridFor(N, idx->sm_count, 8), 256>>>(v, tbits, one, table);
+        for(int j = 1; j < max_len; j++) { jump_extend_kernel<<<gridFor(N, idx->sm_count, 8), 256>>>(N, tbits, (u32)j, one, table); }
+        e = cudaDeviceSynchronize();
+      }
+      if(one) { cudaFree(one); }
+      if(e == cudaSuccess)
+      {
+        idx->allocations.push_back(table); idx->device_bytes += bytes;
+        v.jump = table; v.jump_k = (u32)max_len; v.jump_tbits = tbits;
+      }
+      else
+      {
+        if(table) { cudaFree(table); }
+        cudaGetLastError();
+        if(want > 0) { gcsa_b200_index_destroy(idx); return fail(GCSA_B200_ERR_CUDA, std::string("jump table: ") + cudaGetErrorString(e)); }
+      }
+    }
+  }
+
   // two-step blocks (optional): built on the device from the one-step blocks
   // -1 = automatic: worth it once the one-step blocks are far beyond the L2 (the probe rate no longer
   // depends on the footprint there, so halving the probes halves the time; measured in DESIGN.md)
@@ -1932,6 +2052,7 @@ int gcsa_b200_index_info(const gcsa_b200_index* index, gcsa_b200_info* info)
   info->device_bytes = index->device_bytes; info->kmer_table_k = index->view.table_k;
   info->device = index->device; info->sm_count = index->sm_count;
   info->two_step = (index->view.bwt2 != nullptr ? 1 : 0);
+  info->jump_k = (index->view.jump != nullptr ? (int)index->view.jump_k : 0);
   return 0;
 }
 

@@ -42,13 +42,14 @@ def range_length(rng):
 
 
 class GCSA:
-    def __init__(self, flat, device=0, kmer_table_k=0, two_step=None, walk_table=None):
+    def __init__(self, flat, device=0, kmer_table_k=0, two_step=None, walk_table=None, jump_table=None):
         self._h = None
         L = capi.lib()
         keep = []
         f = capi.flat_struct(flat, keep)
         opt = capi.Options(); opt.kmer_table_k = int(kmer_table_k); opt.two_step = (-1 if two_step is None else int(bool(two_step)))
         opt.walk_table = (-1 if walk_table is None else int(walk_table))
+        opt.jump_table = (0 if jump_table is None else (1 if jump_table else -1))
         h = C.c_void_p()
         capi.check(L.gcsa_b200_index_create(C.byref(f), int(device), C.byref(opt), C.byref(h)))
         self._h = h
@@ -85,6 +86,7 @@ class GCSA:
     def deviceBytes(self): return int(self._info.device_bytes)
     def kmerTableK(self): return int(self._info.kmer_table_k)
     def twoStep(self): return bool(self._info.two_step)
+    def jumpK(self): return int(self._info.jump_k)
     def smCount(self): return int(self._info.sm_count)
     @property
     def handle(self): return self._h

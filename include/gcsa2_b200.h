@@ -90,7 +90,12 @@ typedef struct gcsa_b200_options {
                               for sampled nodes, the index of their samples -- one load per LF step); 0 = neither
                               (bit vectors only); -1 = what fits: each table must fit in a fraction of the free
                               device memory. */
-  int      reserved[5];
+  int      jump_table;     /* find(): one 8-byte entry per path node holding the characters and the end of the unary
+                              backward path starting there (up to 16 steps: every node on it has exactly one
+                              predecessor character), so that a singleton range advances that many characters
+                              with one load.  0 = build if it fits, 1 = build, -1 = do not.  Exact: a pattern that
+                              leaves the path or ends inside it is continued with single steps. */
+  int      reserved[4];
 } gcsa_b200_options;
 
 typedef struct gcsa_b200_info {
@@ -100,6 +105,7 @@ typedef struct gcsa_b200_info {
   int      device;
   int      sm_count;
   int      two_step;                   /* 1 if the two-step blocks are in use */
+  int      jump_k;                     /* longest path of the jump table (0 = no table) */
 } gcsa_b200_info;
 
 /* Per-batch statistics of find(): filled by gcsa_b200_find_stats_host (measurement only). */

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_header():
     assert C.sizeof(capi.FlatIndex) == 8 * 5 + 8 * 8 + 256 + 8 * 7 + 8 * 10
-    assert C.sizeof(capi.FlatLcp) == 40 and C.sizeof(capi.Info) == 56 and C.sizeof(capi.FindStats) == 48
+    assert C.sizeof(capi.FlatLcp) == 40 and C.sizeof(capi.Info) == 64 and C.sizeof(capi.FindStats) == 48
 
 
 def test_no_cuda_device_fails_loudly():

@@ -387,3 +387,43 @@ def test_locate_into_host_buffers():
         gpu.locate_into_host_raw(sp.ctypes.data, ep.ctypes.data, n, out_offs.ctypes.data, small.ctypes.data, small.size)
     assert err.value.code == capi.ERR_CAPACITY and (out_offs == offs).all()
     assert gpu.locate_into_host_raw(sp.ctypes.data, ep.ctypes.data, 0, out_offs.ctypes.data, small.ctypes.data, small.size) == 0
+
+
+def test_jump_table_equals_single_steps():
+    """find() with the jump table (one load for up to 16 steps along a unary backward path) == without it ==
+    the oracle: patterns that follow the path, leave it at every possible distance (one substitution at a random
+    offset: the uncanonicalised empty pair must be the one of the exact failing step), end inside a jump
+    (lengths 17..70), contain N, and walks through a graph with SNP bubbles where paths branch."""
+    rng = np.random.default_rng(23)
+    seq = synth.random_sequence(400_000, seed=23)
+    graph, sites, alt = synth.snp_graph(seq, seed=23, snp_rate=0.01)
+    for name, flat, sampler in (
+            ("linear", build_index(synth.linear_graph(seq), 16, 3)[0], lambda n, L, s: synth.patterns_from_sequence(seq, n, L, seed=s)),
+            ("snp", build_index(graph, 16, 3)[0], lambda n, L, s: synth.patterns_from_snp_graph(seq, sites, alt, n, L, seed=s))):
+        ora = orc.OracleGCSA(flat)
+        pats = []
+        for L in (17, 20, 31, 32, 33, 47, 48, 64, 70):
+            c, o = sampler(3000, L, L)
+            c = c.copy()
+            for i in range(3000):
+                kind = i % 4
+                if kind == 1:                                        # one substitution somewhere
+                    p = int(o[i]) + int(rng.integers(0, L))
+                    c[p] = synth.COMP2CHAR[1 + (int(np.where(synth.COMP2CHAR == c[p])[0][0]) % 4)]
+                elif kind == 2 and i % 8 == 2:                       # an N
+                    c[int(o[i]) + int(rng.integers(0, L))] = ord("N")
+                pats.append(bytes(c[int(o[i]):int(o[i + 1])]))
+        chars, offsets = orc.pack_patterns(pats)
+        osp, oep, _ = ora.find_batch(chars, offsets, threads=4)
+        for table_k, two_step in ((0, False), (8, False), (6, True)):
+            with_jump = GCSA(flat, kmer_table_k=table_k, two_step=two_step, jump_table=True)
+            without = GCSA(flat, kmer_table_k=table_k, two_step=two_step, jump_table=False)
+            assert with_jump.jumpK() == 16 and without.jumpK() == 0
+            a, b = with_jump.find_batch(chars, offsets)
+            c2, d2 = without.find_batch(chars, offsets)
+            bad = np.flatnonzero((a != osp) | (b != oep))
+            assert bad.size == 0, (name, table_k, two_step, bad[:5], [pats[i] for i in bad[:3]])
+            assert (c2 == osp).all() and (d2 == oep).all()
+            _, _, st = with_jump.find_batch(chars, offsets, stats=True)
+            _, _, st0 = without.find_batch(chars, offsets, stats=True)
+            assert st["lf_steps"] == st0["lf_steps"] and st["sector_probes"] < st0["sector_probes"]
