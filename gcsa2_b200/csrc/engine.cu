@@ -83,6 +83,7 @@ struct DevView
   const u64* stored_samples; const u64* sample_start; u64 sample_count;
   const u64* table; int table_k;      // entry = sp | length << 40; length 0xFFFFFF = not tabulated
   const u32* walk32; const u64* walk64; // locate walk table: LF(i) << 1, or rank(sampled, i) << 1 | 1 for sampled nodes
+  u32 default_alphabet;                // char2comp is exactly ACGT / acgt -> 1..4 for the bases (enables the SWAR pattern packing)
   const u64* jump; u32 jump_k, jump_tbits;   // jump table: len << 59 | 2-bit chars << jump_tbits | target (see jump_extend_kernel)
   const u64* loc64;                    // locate table: bit 63 | value for nodes with one start position, else rank of the sampled node << 24 | steps
   u8 char2comp[256];
@@ -326,11 +327,35 @@ struct CharWindow
 
 struct FindStatsDev { u64 found, total_length, lf_steps, sector_probes, table_hits; };
 
+// Eight pattern bytes of the default alphabet (w: lowest address in the low byte) -> their comp - 1 codes,
+// 2 bits each, the LAST byte in the lowest bits.  *good = how many bytes, counted from the last one, are bases
+// in either case (8 if all); the codes of the others are garbage.
+__device__ __forceinline__ u32 pack8_reversed(u64 w, u32* good)
+{
+  const u64 L7 = 0x7F7F7F7F7F7F7F7Full, H8 = 0x8080808080808080ull;
+  u64 x = w & 0xDFDFDFDFDFDFDFDFull;
+  u64 zA = x ^ 0x4141414141414141ull, zC = x ^ 0x4343434343434343ull, zG = x ^ 0x4747474747474747ull, zT = x ^ 0x5454545454545454ull;
+  // 0x80 in every byte that equals one of the four letters (exact zero-byte test, no carries between bytes)
+  u64 valid = ~(((zA & L7) + L7) | zA | L7) | ~(((zC & L7) + L7) | zC | L7) | ~(((zG & L7) + L7) | zG | L7) | ~(((zT & L7) + L7) | zT | L7);
+  u64 inv = ~valid & H8;
+  *good = (inv == 0 ? 8u : 7u - (u32)((63 - __clzll((long long)inv)) >> 3));
+  u64 t = (w >> 1) & 0x0303030303030303ull;                      // A 0, C 1, T 2, G 3
+  u64 code = t ^ ((t >> 1) & 0x0101010101010101ull);               // A 0, C 1, G 2, T 3
+  u64 y = (code | (code >> 6)) & 0x000F000F000F000Full;
+  y = (y | (y >> 12)) & 0x000000FF000000FFull;
+  y = (y | (y >> 24)) & 0xFFFFull;
+  u32 r = __brev((u32)y) >> 16;                                    // reverse the order of the characters ...
+  return ((r >> 1) & 0x5555u) | ((r & 0x5555u) << 1);              // ... not of the two bits of each
+}
+
 /*
-  GCSA::find(begin, end), include/gcsa/gcsa.h:96-110.  One query per lane; the LF loop advances
-  one character per warp-step.  Queries are pulled from a contiguous per-warp slice; a lane whose
-  range became empty (or whose pattern is exhausted) is refilled on the next step, the
-  assignment being computed with one ballot + popc (no atomics, no shared memory).
+  GCSA::find(begin, end), include/gcsa/gcsa.h:96-110.  One query per lane.  Queries are pulled from a
+  contiguous per-warp slice; lanes whose search ended are refilled together once half the warp is idle
+  (one ballot + popc, no atomics).  A refilled lane packs the last 32 characters of its pattern into one
+  register (2 bits each, the last character lowest): the k-mer table index is a bit field of it and a jump
+  along a unary path is one XOR against the table entry.  Anything that does not fit the fast forms (other
+  characters, another alphabet, short remainders) goes through the per-character path, which is the
+  reference's loop verbatim.
 */
 template<bool STATS, int MIN_BLOCKS, bool PACKED = false>
 __global__ void __launch_bounds__(256, MIN_BLOCKS)
@@ -346,6 +371,7 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
     __syncthreads();
   }
   const u64 words_per_pattern = (fixed_length + 31) >> 5;
+  const bool fast_pack = (PACKED || v.default_alphabet != 0);
 
   const u32 lane = threadIdx.x & 31;
   const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -357,11 +383,13 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
   if(next >= n) { return; }
 
   u64 q = ~0ull, sp = 0, ep = 0, pos = 0, begin = 0;
+  u64 tail = 0, tail_end = 0; u32 tail_n = 0;       // characters [tail_end - tail_n, tail_end), the one at tail_end - 1 - t in bits [2t, 2t + 2)
   bool live = false, try_jump = true;
   CharWindow win;
   u64 st_found = 0, st_len = 0, st_steps = 0, st_sectors = 0, st_hits = 0;
-  // comp value of the character at (batch-wide) position p of the current query
-  auto comp_at = [&](u64 p) -> u32
+
+  // comp value of the character at (batch-wide) position p of the current query: the general path
+  auto comp_slow = [&](u64 p) -> u32
   {
     if(PACKED)
     {
@@ -371,12 +399,51 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
     }
     return c2c[win.get(chars, p)];
   };
+  auto comp_at = [&](u64 p) -> u32
+  {
+    u64 off = tail_end - 1 - p;
+    if(off < (u64)tail_n) { return (u32)((tail >> (2 * off)) & 3) + 1; }
+    return comp_slow(p);
+  };
+  // pack the (up to) 32 characters that end at position `end_pos` (exclusive)
+  auto pack_tail = [&](u64 end_pos)
+  {
+    tail = 0; tail_n = 0; tail_end = end_pos;
+    if(!fast_pack) { return; }
+    if(PACKED)
+    {
+      u64 have = end_pos - begin, m = (have < 32 ? have : 32), r0 = have - m;             // pattern-relative [r0, r0 + m)
+      const unsigned long long* words = (const unsigned long long*)chars + q * words_per_pattern;
+      u32 sh = (u32)(r0 & 31) * 2;
+      u64 x = __ldcs(words + (r0 >> 5)) >> sh;
+      if(sh != 0 && (r0 & 31) + m > 32) { x |= __ldcs(words + (r0 >> 5) + 1) << (64 - sh); }
+      u64 r = __brevll(x);
+      r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+      tail = (m < 32 ? r >> (2 * (32 - m)) : r);
+      tail_n = (u32)m;
+      return;
+    }
+    for(u32 w = 0; w < 4; w++)
+    {
+      u64 pe = end_pos - 8 * w;
+      if(pe - begin < 8) { break; }
+      u64 addr = (u64)(chars + pe - 8); u32 a = (u32)(addr & 7);
+      const unsigned long long* base = (const unsigned long long*)(addr - a);
+      u64 word = __ldcs(base);
+      if(a != 0) { word = (word >> (8 * a)) | ((u64)__ldcs(base + 1) << (64 - 8 * a)); }
+      u32 good;
+      u32 r = pack8_reversed(word, &good);
+      tail |= (u64)r << (16 * w);
+      tail_n += good;
+      if(good < 8) { break; }
+    }
+  };
 
   while(true)
   {
-    // refill dead lanes
+    // refill: all idle lanes at once, as soon as half the warp is idle (or nobody is working)
     u32 dead = __ballot_sync(0xFFFFFFFFu, !live);
-    if(dead)
+    if(__popc(dead) >= 16)
     {
       u32 my = __popc(dead & ((1u << lane) - 1));
       if(!live)
@@ -389,19 +456,25 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
           if(offsets != nullptr) { b = offsets[q] - char_base; e = offsets[q + 1] - char_base; }
           else { b = q * fixed_length; e = b + fixed_length; }
           begin = b; live = true; try_jump = true;
+          tail = 0; tail_n = 0; tail_end = e;
           if(e == b || v.path_nodes == 0) { sp = 0; ep = v.path_nodes - 1; pos = b; }
           else
           {
+            pack_tail(e);
             pos = e - 1;
             bool used_table = false;
             if(v.table_k > 0 && e - b >= (u64)v.table_k)
             {
               u64 idx = 0; bool ok = true;
-              for(int t = 0; t < v.table_k; t++)
+              if(tail_n >= (u32)v.table_k) { idx = tail & ((1ull << (2 * v.table_k)) - 1); }
+              else
               {
-                u32 c = comp_at(e - 1 - t);
-                ok = ok && (c >= 1 && c <= 4);
-                idx |= (u64)((c - 1) & 3) << (2 * t);
+                for(int t = 0; t < v.table_k; t++)
+                {
+                  u32 c = comp_at(e - 1 - t);
+                  ok = ok && (c >= 1 && c <= 4);
+                  idx |= (u64)((c - 1) & 3) << (2 * t);
+                }
               }
               if(ok)
               {
@@ -425,17 +498,15 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
       next += __popc(dead);
       if(next > slice_end) { next = slice_end; }
     }
-    if(__ballot_sync(0xFFFFFFFFu, live) == 0) { break; }
+    if(__ballot_sync(0xFFFFFFFFu, live) == 0)
+    {
+      if(next >= slice_end) { break; }
+      continue;
+    }
 
     if(live)
     {
-      if(range_empty(sp, ep) || pos == begin)
-      {
-        __stcs((unsigned long long*)sp_out + q, (unsigned long long)sp); __stcs((unsigned long long*)ep_out + q, (unsigned long long)ep);
-        if(STATS && !range_empty(sp, ep)) { st_found++; st_len += ep + 1 - sp; }
-        live = false;
-      }
-      else
+      if(!(range_empty(sp, ep) || pos == begin))
       {
         u32 sectors = 0;
         bool done = false;
@@ -451,11 +522,17 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
             else
             {
               u64 stored = ((e << 5) >> 5) >> v.jump_tbits;
+              u64 off = tail_end - pos;
+              if(off + len > (u64)tail_n && fast_pack && tail_n == 32) { pack_tail(pos); off = 0; }
               bool same = true;
-              for(u32 t = 0; t < len; t++)
+              if(off + len <= (u64)tail_n) { same = ((((tail >> (2 * off)) ^ stored) & ((1ull << (2 * len)) - 1)) == 0); }
+              else
               {
-                u32 pc = comp_at(pos - 1 - t);
-                same = same && (pc == ((u32)(stored >> (2 * t)) & 3) + 1);
+                for(u32 t = 0; t < len; t++)
+                {
+                  u32 pc = comp_at(pos - 1 - t);
+                  same = same && (pc == ((u32)(stored >> (2 * t)) & 3) + 1);
+                }
               }
               if(same)
               {
@@ -467,6 +544,7 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
             }
           }
         }
+        if(!done && tail_end - pos >= (u64)tail_n && fast_pack && tail_n == 32) { pack_tail(pos); }   // next window of a long pattern
         u32 c = (done ? 0 : comp_at(pos - 1));
         if(!done && v.bwt2 != nullptr && pos - begin >= 2 && c >= 1 && c <= 4)
         {
@@ -484,6 +562,12 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
           if(STATS) { st_steps++; }
         }
         if(STATS) { st_sectors += sectors; }
+      }
+      if(range_empty(sp, ep) || pos == begin)
+      {
+        __stcs((unsigned long long*)sp_out + q, (unsigned long long)sp); __stcs((unsigned long long*)ep_out + q, (unsigned long long)ep);
+        if(STATS && !range_empty(sp, ep)) { st_found++; st_len += ep + 1 - sp; }
+        live = false;
       }
     }
   }
@@ -1762,6 +1846,7 @@ int gcsa_b200_index_create(const gcsa_flat_index* host, int device, const gcsa_b
       bool def_fast = (def[i] >= 1 && def[i] <= GCSA_B200_FAST_CHARS);
       if(fast != def_fast || (fast && c != def[i])) { idx->pack_default = false; }
     }
+    v.default_alphabet = (idx->pack_default ? 1u : 0u);
   }
   for(int i = 0; i < 256; i++) { if(v.char2comp[i] >= GCSA_B200_SIGMA) { delete idx; return fail(GCSA_B200_ERR_INVALID, "index_create: char2comp value out of range"); } }
 
