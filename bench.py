@@ -449,6 +449,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
+        traffic = recorded_traffic(args, index)
         achieved = engine_bytes / (ms_total / args.steps / 1000.0) / 1e9
         line = {
             "metric": METRIC, "value": total_q / (ms_step / 1000.0), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -470,9 +471,13 @@ def main():
                     "matches_device_leg": e2e_same},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": recorded_traffic(args, index), "kernel": "find_kernel<false,5>", "peak_source": peak_src,
+                         "traffic": traffic, "dram_frac": (traffic / (ms_total / args.steps / 1000.0) / 1e9 / peak if traffic else None),
+                         "kernel": "find_kernel<false,4,false>", "peak_source": peak_src,
                          "bytes_per_launch": engine_bytes,
-                         "accounting": "64 B per distinct fused-sector probe executed + 8 B per k-mer table entry + |P| + 16 B I/O per query (SURVEY.md 8(d) units)",
+                         "accounting": "64 B per distinct probe executed (fused sector or jump-table entry) + 8 B per k-mer table entry + |P| + 16 B I/O per query (SURVEY.md 8(d) units); "
+                                       "dram_frac = recorded ncu DRAM bytes of this launch / this run's time / peak: a random probe into tens of GB costs ~128 B of HBM traffic, "
+                                       "twice the 64 B the accounting grants it (profiles/r01_random_probe_microbench.txt)",
+                         "jump_table_k": index.jumpK(),
                          "lf_steps_per_query": st["lf_steps"] / m, "sector_probes_per_query": st["sector_probes"] / m},
             "clocks": clocks,
             "setup": {"index_build_s": build_s, "index_create_s": create_s},

@@ -2157,15 +2157,16 @@ static int launchFind(const gcsa_b200_index* index, const u8* d_chars, const u64
                       u64 n, u64* d_sp, u64* d_ep, FindStatsDev* d_stats, cudaStream_t stream, bool packed = false)
 {
   if(n == 0) { return 0; }
-  // persistent grid: 5 CTAs of 256 threads per SM by default (40+ registers without spills measured
-  // fastest: 4.29 vs 4.06 G queries/s at 6 CTAs/SM and 3.5 at 8), one contiguous slice of queries per warp
-  static const int min_blocks = []() { const char* e = std::getenv("GCSA_B200_FIND_MINBLOCKS"); return (e ? std::atoi(e) : 5); }();
+  // persistent grid: 4 CTAs of 256 threads per SM by default (59 registers, no spills; with the packed pattern
+  // tail 5 CTAs/SM spill: 13.3 vs 13.1 G queries/s with the 16-mer table, but 7.0 vs 8.4 with the 14-mer table,
+  // where more single steps run), one contiguous slice of queries per warp
+  static const int min_blocks = []() { const char* e = std::getenv("GCSA_B200_FIND_MINBLOCKS"); return (e ? std::atoi(e) : 4); }();
   int per_sm = (min_blocks >= 8 ? 8 : (min_blocks <= 4 ? 4 : min_blocks));
   int grid = gridFor(n, index->sm_count, per_sm);
   #define LAUNCH_FIND(S, B) find_kernel<S, B><<<grid, 256, 0, stream>>>(index->view, d_chars, d_offsets, char_base, fixed_length, n, d_sp, d_ep, d_stats)
   if(packed)
   {
-    find_kernel<false, 5, true><<<gridFor(n, index->sm_count, 5), 256, 0, stream>>>(index->view, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, nullptr);
+    find_kernel<false, 4, true><<<gridFor(n, index->sm_count, 4), 256, 0, stream>>>(index->view, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, nullptr);
   }
   else if(d_stats) { LAUNCH_FIND(true, 1); }
   else if(per_sm == 8) { LAUNCH_FIND(false, 8); }
