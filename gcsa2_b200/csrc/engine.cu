@@ -1504,7 +1504,7 @@ mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const
   const u64 slice_end = (next + per < n ? next + per : n);
   if(next >= n || v.path_nodes == 0) { return; }
 
-  u64 q = 0, sp = 0, ep = 0, depth = 0, pos = 0, begin = 0, emitted = 0, out_at = 0, hold_pos = ~0ull;
+  u64 q = 0, sp = 0, ep = 0, depth = 0, pos = 0, begin = 0, emitted = 0, out_at = 0;
   bool live = false, extended = false, need_parent = false;
 
   while(true)
@@ -1518,7 +1518,7 @@ mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const
         u64 cand = next + my;
         if(cand < slice_end)
         {
-          q = (ids != nullptr ? ids[cand] : cand); live = true; need_parent = false; hold_pos = ~0ull;
+          q = (ids != nullptr ? ids[cand] : cand); live = true; need_parent = false;
           begin = offsets[q] - char_base; pos = offsets[q + 1] - char_base;
           sp = 0; ep = v.path_nodes - 1; depth = 0; extended = false; emitted = 0;
           if(WRITE) { out_at = out_offsets[q]; }
@@ -1558,38 +1558,6 @@ mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const
       if(!WRITE) { counts[q] = emitted; }
       live = false;
       continue;
-    }
-    // Singleton range: up to 16 steps along a unary path with one load (the jump table of find()).  On a
-    // mismatch the steps are taken one by one until the offending character is behind us.
-    if(v.jump != nullptr && sp == ep && pos - begin >= 8 && pos <= hold_pos && v.default_alphabet != 0)
-    {
-      u64 e = __ldg(v.jump + sp);
-      u32 len = (u32)(e >> 59);
-      if(len >= 2 && (u64)len <= pos - begin)
-      {
-        u64 pat = 0; u32 have = 0;
-        for(u32 w = 0; w < 2 && have == 8 * w && pos - begin >= 8 * (w + 1) && have < len; w++)
-        {
-          u64 addr = (u64)(chars + pos - 8 * (w + 1)); u32 a = (u32)(addr & 7);
-          const unsigned long long* base = (const unsigned long long*)(addr - a);
-          u64 word = __ldg(base);
-          if(a != 0) { word = (word >> (8 * a)) | ((u64)__ldg(base + 1) << (64 - 8 * a)); }
-          u32 good;
-          pat |= (u64)pack8_reversed(word, &good) << (16 * w);
-          have += good;
-        }
-        if(have >= len)
-        {
-          u64 diff = (pat ^ (((e << 5) >> 5) >> v.jump_tbits)) & ((1ull << (2 * len)) - 1);
-          if(diff == 0)
-          {
-            sp = ep = (e & ((1ull << v.jump_tbits) - 1));
-            depth += len; pos -= len; extended = true;
-            continue;
-          }
-          hold_pos = pos - 1 - (u64)((__ffsll((long long)diff) - 1) >> 1);
-        }
-      }
     }
     u64 nsp, nep;
     lf_range(v, sp, ep, c2c[chars[pos - 1]], nsp, nep);
