@@ -410,7 +410,7 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
   {
     tail = 0; tail_n = 0; tail_end = end_pos;
     if(!fast_pack) { return; }
-    if(PACKED)
+    if constexpr(PACKED)
     {
       u64 have = end_pos - begin, m = (have < 32 ? have : 32), r0 = have - m;             // pattern-relative [r0, r0 + m)
       const unsigned long long* words = (const unsigned long long*)chars + q * words_per_pattern;
@@ -421,21 +421,23 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
       r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
       tail = (m < 32 ? r >> (2 * (32 - m)) : r);
       tail_n = (u32)m;
-      return;
     }
-    for(u32 w = 0; w < 4; w++)
+    else
     {
-      u64 pe = end_pos - 8 * w;
-      if(pe - begin < 8) { break; }
-      u64 addr = (u64)(chars + pe - 8); u32 a = (u32)(addr & 7);
-      const unsigned long long* base = (const unsigned long long*)(addr - a);
-      u64 word = __ldcs(base);
-      if(a != 0) { word = (word >> (8 * a)) | ((u64)__ldcs(base + 1) << (64 - 8 * a)); }
-      u32 good;
-      u32 r = pack8_reversed(word, &good);
-      tail |= (u64)r << (16 * w);
-      tail_n += good;
-      if(good < 8) { break; }
+      for(u32 w = 0; w < 4; w++)
+      {
+        u64 pe = end_pos - 8 * w;
+        if(pe - begin < 8) { break; }
+        u64 addr = (u64)(chars + pe - 8); u32 a = (u32)(addr & 7);
+        const unsigned long long* base = (const unsigned long long*)(addr - a);
+        u64 word = __ldcs(base);
+        if(a != 0) { word = (word >> (8 * a)) | ((u64)__ldcs(base + 1) << (64 - 8 * a)); }
+        u32 good;
+        u32 r = pack8_reversed(word, &good);
+        tail |= (u64)r << (16 * w);
+        tail_n += good;
+        if(good < 8) { break; }
+      }
     }
   };
 
