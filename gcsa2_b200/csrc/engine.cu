@@ -360,7 +360,7 @@ __device__ __forceinline__ u32 pack8_reversed(u64 w, u32* good)
 template<bool STATS, int MIN_BLOCKS, bool PACKED = false>
 __global__ void __launch_bounds__(256, MIN_BLOCKS)
 find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict__ offsets, u64 char_base,
-            u64 fixed_length, u64 n, u64* __restrict__ sp_out, u64* __restrict__ ep_out, FindStatsDev* stats)
+            u64 fixed_length, u64 n, u64* __restrict__ sp_out, u64* __restrict__ ep_out, FindStatsDev* stats, int refill_at)
 {
   // PACKED: `chars` holds ceil(fixed_length / 32) 64-bit words per pattern, character p of a pattern at bits
   // [2 (p % 32), 2 (p % 32) + 2) of word p / 32, value comp - 1 (ACGT only; packed by the host entry point).
@@ -445,7 +445,7 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
   {
     // refill: all idle lanes at once, as soon as half the warp is idle (or nobody is working)
     u32 dead = __ballot_sync(0xFFFFFFFFu, !live);
-    if(__popc(dead) >= 16)
+    if(__popc(dead) >= refill_at)
     {
       u32 my = __popc(dead & ((1u << lane) - 1));
       if(!live)
@@ -2165,10 +2165,12 @@ static int launchFind(const gcsa_b200_index* index, const u8* d_chars, const u64
   static const int min_blocks = []() { const char* e = std::getenv("GCSA_B200_FIND_MINBLOCKS"); return (e ? std::atoi(e) : 4); }();
   int per_sm = (min_blocks >= 8 ? 8 : (min_blocks <= 4 ? 4 : min_blocks));
   int grid = gridFor(n, index->sm_count, per_sm);
-  #define LAUNCH_FIND(S, B) find_kernel<S, B><<<grid, 256, 0, stream>>>(index->view, d_chars, d_offsets, char_base, fixed_length, n, d_sp, d_ep, d_stats)
+  // idle lanes of a warp are refilled together once this many are idle (16 measured best: DESIGN.md)
+  static const int refill_at = []() { const char* e = std::getenv("GCSA_B200_FIND_REFILL"); int r = (e ? std::atoi(e) : 16); return std::min(32, std::max(1, r)); }();
+  #define LAUNCH_FIND(S, B) find_kernel<S, B><<<grid, 256, 0, stream>>>(index->view, d_chars, d_offsets, char_base, fixed_length, n, d_sp, d_ep, d_stats, refill_at)
   if(packed)
   {
-    find_kernel<false, 4, true><<<gridFor(n, index->sm_count, 4), 256, 0, stream>>>(index->view, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, nullptr);
+    find_kernel<false, 4, true><<<gridFor(n, index->sm_count, 4), 256, 0, stream>>>(index->view, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, nullptr, refill_at);
   }
   else if(d_stats) { LAUNCH_FIND(true, 1); }
   else if(per_sm == 8) { LAUNCH_FIND(false, 8); }

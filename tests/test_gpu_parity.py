@@ -427,3 +427,42 @@ def test_jump_table_equals_single_steps():
             _, _, st = with_jump.find_batch(chars, offsets, stats=True)
             _, _, st0 = without.find_batch(chars, offsets, stats=True)
             assert st["lf_steps"] == st0["lf_steps"] and st["sector_probes"] < st0["sector_probes"]
+
+
+def test_custom_alphabet_takes_the_general_path():
+    """An index whose char2comp is not the default table (digits 1-4 are the bases, lower case is N): the SWAR
+    pattern packing is off, the k-mer table and the jump table are reached through the per-character path, and
+    the answers still equal the oracle's (which maps through the same table, gcsa.h:102,106)."""
+    import copy
+    seq = synth.random_sequence(150_000, seed=29)
+    flat, _, _ = build_index(synth.linear_graph(seq), 16, 3)
+    custom = copy.deepcopy(flat)
+    c2c = np.full(256, 5, dtype=np.uint8)
+    c2c[0] = 0; c2c[ord("$")] = 0; c2c[ord("#")] = 6
+    for i, ch in enumerate("1234"):
+        c2c[ord(ch)] = i + 1
+    for i, ch in enumerate("ACGT"):
+        c2c[ord(ch)] = i + 1
+    custom.char2comp = c2c                                            # upper case and digits are bases, lower case is N
+    chars, offsets = synth.patterns_from_sequence(seq, 60_000, 40, seed=9)
+    chars = chars.copy()
+    rng = np.random.default_rng(29)
+    digits = rng.random(chars.size) < 0.5
+    lut = np.arange(256, dtype=np.uint8)
+    for i, ch in enumerate("ACGT"):
+        lut[ord(ch)] = ord("1234"[i])
+    chars[digits] = lut[chars[digits]]                               # half of the characters as digits: same comps
+    lower = rng.random(60_000) < 0.1                                   # a tenth of the patterns get one lower-case letter = N here
+    for i in np.flatnonzero(lower):
+        p = int(offsets[i]) + int(rng.integers(0, 40))
+        chars[p] = ord("acgt"[int(rng.integers(0, 4))])
+    ora = orc.OracleGCSA(custom)
+    osp, oep, _ = ora.find_batch(chars, offsets, threads=4)
+    for table_k, jump in ((0, False), (8, True), (0, True)):
+        gpu = GCSA(custom, kmer_table_k=table_k, jump_table=jump)
+        sp, ep = gpu.find_batch(chars, offsets)
+        assert (sp == osp).all() and (ep == oep).all(), (table_k, jump)
+        fsp, fep = gpu.find_fixed_batch(chars, 40)
+        assert (fsp == osp).all() and (fep == oep).all()
+    found = (osp <= oep)
+    assert found[~lower].all() and not found[lower].any()
