@@ -84,7 +84,8 @@ struct DevView
   const u64* table; int table_k;      // entry = sp | length << 40; length 0xFFFFFF = not tabulated
   const u32* walk32; const u64* walk64; // locate walk table: LF(i) << 1, or rank(sampled, i) << 1 | 1 for sampled nodes
   u32 default_alphabet;                // char2comp is exactly ACGT / acgt -> 1..4 for the bases (enables the SWAR pattern packing)
-  const u64* jump; u32 jump_k, jump_tbits;   // jump table: len << 59 | 2-bit chars << jump_tbits | target (see jump_extend_kernel)
+  const u64* jump; u32 jump_k, jump_tbits;
+  const u64* jump_short;               // the same table cut at 4 steps: for the tail of a pattern that is shorter than the long path   // jump table: len << 59 | 2-bit chars << jump_tbits | target (see jump_extend_kernel)
   const u64* loc64;                    // locate table: bit 63 | value for nodes with one start position, else rank of the sampled node << 24 | steps
   u8 char2comp[256];
 };
@@ -384,7 +385,8 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
 
   u64 q = ~0ull, sp = 0, ep = 0, pos = 0, begin = 0;
   u64 tail = 0, tail_end = 0; u32 tail_n = 0;       // characters [tail_end - tail_n, tail_end), the one at tail_end - 1 - t in bits [2t, 2t + 2)
-  bool live = false, try_jump = true;
+  bool live = false;
+  u32 jump_mode = 2;                   // 2: long jump table, 1: short one (pattern tail), 0: single steps only
   CharWindow win;
   u64 st_found = 0, st_len = 0, st_steps = 0, st_sectors = 0, st_hits = 0;
 
@@ -457,7 +459,7 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
           u64 b, e;
           if(offsets != nullptr) { b = offsets[q] - char_base; e = offsets[q + 1] - char_base; }
           else { b = q * fixed_length; e = b + fixed_length; }
-          begin = b; live = true; try_jump = true;
+          begin = b; live = true; jump_mode = 2;
           tail = 0; tail_n = 0; tail_end = e;
           if(e == b || v.path_nodes == 0) { sp = 0; ep = v.path_nodes - 1; pos = b; }
           else
@@ -513,37 +515,46 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
         u32 sectors = 0;
         bool done = false;
         // Singleton range: try the jump table (one load for up to jump_k backward steps along a unary path).
-        if(v.jump != nullptr && try_jump && sp == ep && pos - begin >= 2)
+        if(v.jump != nullptr && jump_mode != 0 && sp == ep && pos - begin >= 2)
         {
-          u64 e = __ldg(v.jump + sp);
+          u64 e = __ldg((jump_mode == 2 ? v.jump : v.jump_short) + sp);
           u32 len = (u32)(e >> 59);
           if(STATS) { sectors++; }
+          if(len >= 2 && (u64)len > pos - begin)
+          {
+            // the pattern ends inside this path: go on with the short table (if this was the long one), else single steps
+            jump_mode = (jump_mode == 2 && v.jump_short != nullptr && pos - begin >= 2 ? 1 : 0);
+            if(jump_mode == 1)
+            {
+              e = __ldg(v.jump_short + sp);
+              len = (u32)(e >> 59);
+              if(STATS) { sectors++; }
+              if((u64)len > pos - begin) { jump_mode = 0; len = 0; }
+            }
+            else { len = 0; }
+          }
           if(len >= 2)
           {
-            if((u64)len > pos - begin) { try_jump = false; }           // the pattern ends inside the jump: single steps from here
+            u64 stored = ((e << 5) >> 5) >> v.jump_tbits;
+            u64 off = tail_end - pos;
+            if(off + len > (u64)tail_n && fast_pack && tail_n == 32) { pack_tail(pos); off = 0; }
+            bool same = true;
+            if(off + len <= (u64)tail_n) { same = ((((tail >> (2 * off)) ^ stored) & ((1ull << (2 * len)) - 1)) == 0); }
             else
             {
-              u64 stored = ((e << 5) >> 5) >> v.jump_tbits;
-              u64 off = tail_end - pos;
-              if(off + len > (u64)tail_n && fast_pack && tail_n == 32) { pack_tail(pos); off = 0; }
-              bool same = true;
-              if(off + len <= (u64)tail_n) { same = ((((tail >> (2 * off)) ^ stored) & ((1ull << (2 * len)) - 1)) == 0); }
-              else
+              for(u32 t = 0; t < len; t++)
               {
-                for(u32 t = 0; t < len; t++)
-                {
-                  u32 pc = comp_at(pos - 1 - t);
-                  same = same && (pc == ((u32)(stored >> (2 * t)) & 3) + 1);
-                }
+                u32 pc = comp_at(pos - 1 - t);
+                same = same && (pc == ((u32)(stored >> (2 * t)) & 3) + 1);
               }
-              if(same)
-              {
-                sp = ep = (e & ((1ull << v.jump_tbits) - 1));
-                pos -= len; done = true;
-                if(STATS) { st_steps += len; }
-              }
-              else { try_jump = false; }                               // it dies within these steps: the exact pair comes from single steps
             }
+            if(same)
+            {
+              sp = ep = (e & ((1ull << v.jump_tbits) - 1));
+              pos -= len; done = true;
+              if(STATS) { st_steps += len; }
+            }
+            else { jump_mode = 0; }                                  // it dies within these steps: the exact pair comes from single steps
           }
         }
         if(!done && tail_end - pos >= (u64)tail_n && fast_pack && tail_n == 32) { pack_tail(pos); }   // next window of a long pattern
@@ -2014,24 +2025,32 @@ int gcsa_b200_index_create(const gcsa_flat_index* host, int device, const gcsa_b
     int max_len = std::min<int>(16, (59 - (int)tbits) / 2);
     if(N > 0 && want >= 0 && max_len >= 2 && (want > 0 || 2 * bytes < free_b / 2))
     {
-      u64 *one = nullptr, *table = nullptr;
+      u64 *one = nullptr, *table = nullptr, *short_table = nullptr;
+      const int short_len = 4;
       cudaError_t e = cudaMalloc((void**)&one, bytes);
       if(e == cudaSuccess) { e = cudaMalloc((void**)&table, bytes); }
+      if(e == cudaSuccess && max_len > short_len && 3 * bytes < free_b / 2) { if(cudaMalloc((void**)&short_table, bytes) != cudaSuccess) { short_table = nullptr; cudaGetLastError(); } }
       if(e == cudaSuccess)
       {
         jump_init_kernel<<<gridFor(N, idx->sm_count, 8), 256>>>(v, tbits, one, table);
-        for(int j = 1; j < max_len; j++) { jump_extend_kernel<<<gridFor(N, idx->sm_count, 8), 256>>>(N, tbits, (u32)j, one, table); }
-        e = cudaDeviceSynchronize();
+        for(int j = 1; j < max_len; j++)
+        {
+          if(j == short_len && short_table != nullptr) { e = cudaMemcpyAsync(short_table, table, bytes, cudaMemcpyDeviceToDevice, 0); }   // paths of up to 4 steps
+          jump_extend_kernel<<<gridFor(N, idx->sm_count, 8), 256>>>(N, tbits, (u32)j, one, table);
+        }
+        if(e == cudaSuccess) { e = cudaDeviceSynchronize(); }
       }
       if(one) { cudaFree(one); }
       if(e == cudaSuccess)
       {
         idx->allocations.push_back(table); idx->device_bytes += bytes;
         v.jump = table; v.jump_k = (u32)max_len; v.jump_tbits = tbits;
+        if(short_table != nullptr) { idx->allocations.push_back(short_table); idx->device_bytes += bytes; v.jump_short = short_table; }
       }
       else
       {
         if(table) { cudaFree(table); }
+        if(short_table) { cudaFree(short_table); }
         cudaGetLastError();
         if(want > 0) { gcsa_b200_index_destroy(idx); return fail(GCSA_B200_ERR_CUDA, std::string("jump table: ") + cudaGetErrorString(e)); }
       }
