@@ -386,7 +386,7 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
   u64 q = ~0ull, sp = 0, ep = 0, pos = 0, begin = 0;
   u64 tail = 0, tail_end = 0; u32 tail_n = 0;       // characters [tail_end - tail_n, tail_end), the one at tail_end - 1 - t in bits [2t, 2t + 2)
   bool live = false;
-  u32 jump_mode = 2;                   // 2: long jump table, 1: short one (pattern tail), 0: single steps only
+  u32 jump_mode = 1;                   // 0 once a jump failed on a character: this query dies within a few single steps
   CharWindow win;
   u64 st_found = 0, st_len = 0, st_steps = 0, st_sectors = 0, st_hits = 0;
 
@@ -459,7 +459,7 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
           u64 b, e;
           if(offsets != nullptr) { b = offsets[q] - char_base; e = offsets[q + 1] - char_base; }
           else { b = q * fixed_length; e = b + fixed_length; }
-          begin = b; live = true; jump_mode = 2;
+          begin = b; live = true; jump_mode = 1;
           tail = 0; tail_n = 0; tail_end = e;
           if(e == b || v.path_nodes == 0) { sp = 0; ep = v.path_nodes - 1; pos = b; }
           else
@@ -515,24 +515,19 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
         u32 sectors = 0;
         bool done = false;
         // Singleton range: try the jump table (one load for up to jump_k backward steps along a unary path).
-        if(v.jump != nullptr && jump_mode != 0 && sp == ep && pos - begin >= 2)
+        // The table is chosen by what is left of the pattern, so that a path never overshoots its end: the long
+        // table (paths of up to jump_k steps) while at least jump_k characters remain, the short one (4) below that.
+        const u64* jump_from = nullptr;
+        if(v.jump != nullptr && jump_mode != 0 && sp == ep)
         {
-          u64 e = __ldg((jump_mode == 2 ? v.jump : v.jump_short) + sp);
+          u64 left = pos - begin;
+          jump_from = (left >= (u64)v.jump_k ? v.jump : (left >= 4 ? v.jump_short : nullptr));
+        }
+        if(jump_from != nullptr)
+        {
+          u64 e = __ldg(jump_from + sp);
           u32 len = (u32)(e >> 59);
           if(STATS) { sectors++; }
-          if(len >= 2 && (u64)len > pos - begin)
-          {
-            // the pattern ends inside this path: go on with the short table (if this was the long one), else single steps
-            jump_mode = (jump_mode == 2 && v.jump_short != nullptr && pos - begin >= 2 ? 1 : 0);
-            if(jump_mode == 1)
-            {
-              e = __ldg(v.jump_short + sp);
-              len = (u32)(e >> 59);
-              if(STATS) { sectors++; }
-              if((u64)len > pos - begin) { jump_mode = 0; len = 0; }
-            }
-            else { len = 0; }
-          }
           if(len >= 2)
           {
             u64 stored = ((e << 5) >> 5) >> v.jump_tbits;
