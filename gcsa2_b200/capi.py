@@ -105,7 +105,12 @@ def lib():
     except Exception:
         if not os.path.exists(path):
             raise
-    L = C.CDLL(path)
+    _lib = _bind(C.CDLL(path))
+    return _lib
+
+
+def _bind(L):
+    """Declares the prototypes of include/gcsa2_b200.h on a loaded library."""
     vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
     L.gcsa_b200_last_error.restype = C.c_char_p
     L.gcsa_b200_version.restype = C.c_char_p
@@ -156,7 +161,6 @@ def lib():
     L.gcsa_b200_load_lcp_file.argtypes = [C.c_char_p, C.POINTER(FlatLcp)]
     L.gcsa_b200_write_lcp_file.argtypes = [C.POINTER(FlatLcp), C.c_char_p]
     L.gcsa_b200_flat_lcp_free.argtypes = [C.POINTER(FlatLcp)]; L.gcsa_b200_flat_lcp_free.restype = None
-    _lib = L
     return L
 
 

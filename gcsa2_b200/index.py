@@ -44,7 +44,7 @@ def range_length(rng):
 class GCSA:
     def __init__(self, flat, device=0, kmer_table_k=0, two_step=None, walk_table=None, jump_table=None):
         self._h = None
-        L = capi.lib()
+        L = self._L = capi.lib()            # the handle is destroyed by the library that made it
         keep = []
         f = capi.flat_struct(flat, keep)
         opt = capi.Options(); opt.kmer_table_k = int(kmer_table_k); opt.two_step = (-1 if two_step is None else int(bool(two_step)))
@@ -68,7 +68,7 @@ class GCSA:
 
     def close(self):
         if self._h is not None:
-            capi.lib().gcsa_b200_index_destroy(self._h)
+            self._L.gcsa_b200_index_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -307,14 +307,15 @@ class LCPArray:
         f.size, f.branching, f.levels = int(flat_lcp.size), int(flat_lcp.branching), int(flat_lcp.levels)
         f.offsets, f.data = self._offsets.ctypes.data, data.ctypes.data
         h = C.c_void_p()
-        capi.check(capi.lib().gcsa_b200_lcp_create(C.byref(f), int(device), C.byref(h)))
+        self._L = capi.lib()
+        capi.check(self._L.gcsa_b200_lcp_create(C.byref(f), int(device), C.byref(h)))
         self._h = h
         self._size, self._values = int(flat_lcp.size), int(self._offsets[int(flat_lcp.levels)])
         self._branching, self._levels = int(flat_lcp.branching), int(flat_lcp.levels)
 
     def close(self):
         if self._h is not None:
-            capi.lib().gcsa_b200_lcp_destroy(self._h)
+            self._L.gcsa_b200_lcp_destroy(self._h)
             self._h = None
 
     def __del__(self):

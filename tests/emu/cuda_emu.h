@@ -1,0 +1,427 @@
+/*
+  cuda_emu.h -- TEST INFRASTRUCTURE.  A minimal host emulation of the CUDA constructs that
+  gcsa2_b200/csrc/engine.cu uses, so that the kernel SOURCE (not a restatement of it) can be executed
+  and checked against the oracle on a machine without a GPU (tests/test_emu_kernels.py).
+
+  It is never part of the product: the shipped library is built by nvcc for sm_100a only
+  (gcsa2_b200/build.py) and has no CPU path; this header is only ever seen by tests/emu/build_emu.py,
+  which translates engine.cu (kernel launches `k<<<cfg>>>(args)` -> emu::launch, the one inline-PTX load)
+  and compiles the result with g++ into tests/emu/_build/.
+
+  Execution model: one launch runs on the calling OS thread, block after block.  Kernels without warp /
+  block collectives run thread after thread as plain calls.  Kernels with collectives run every thread of a
+  block as a fiber (own stack, hand-written context switch); __ballot_sync / __shfl_*_sync / __syncthreads
+  suspend the fiber until all live participants have arrived, which is the lockstep the kernels rely on.
+  Memory "on the device" is host memory; streams and events are ordered trivially (everything is
+  synchronous).
+*/
+#pragma once
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <sys/mman.h>
+
+//------------------------------------------------------------------------------
+// Vector types, qualifiers
+//------------------------------------------------------------------------------
+
+struct uint3 { unsigned x, y, z; };
+struct dim3
+{
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+  dim3(int x_) : x((unsigned)x_), y(1), z(1) {}
+  dim3(unsigned long x_) : x((unsigned)x_), y(1), z(1) {}
+};
+struct alignas(16) ulonglong2 { unsigned long long x, y; };
+struct alignas(16) ulonglong4 { unsigned long long x, y, z, w; };
+struct alignas(8) uint2 { unsigned x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { ulonglong2 r; r.x = x; r.y = y; return r; }
+static inline ulonglong4 make_ulonglong4(unsigned long long x, unsigned long long y, unsigned long long z, unsigned long long w) { ulonglong4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+static inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y = y; return r; }
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __launch_bounds__(...)
+#define __shared__ static thread_local
+#define __constant__ static
+
+//------------------------------------------------------------------------------
+// Runtime API (the subset engine.cu uses)
+//------------------------------------------------------------------------------
+
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2 };
+struct emu_stream_; typedef emu_stream_* cudaStream_t;
+struct emu_event_;  typedef emu_event_* cudaEvent_t;
+typedef void* cudaMemPool_t;
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0 };
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+enum cudaLimit { cudaLimitMaxL2FetchGranularity = 5 };
+enum cudaMemPoolAttr { cudaMemPoolAttrReleaseThreshold = 4 };
+
+namespace emu
+{
+inline size_t envBytes(const char* name, size_t def) { const char* s = std::getenv(name); return (s != nullptr && *s ? (size_t)std::strtoull(s, nullptr, 10) : def); }
+inline void* alloc(size_t bytes)
+{
+  void* p = nullptr;
+  if(posix_memalign(&p, 256, std::max<size_t>(bytes, 256)) != 0) { return nullptr; }
+  return p;
+}
+}
+
+static inline const char* cudaGetErrorString(cudaError_t e) { return (e == cudaSuccess ? "no error" : (e == cudaErrorMemoryAllocation ? "out of memory (emulated)" : "error (emulated)")); }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int d) { return (d == 0 ? cudaSuccess : cudaErrorInvalidValue); }
+static inline cudaError_t cudaDeviceGetAttribute(int* value, cudaDeviceAttr, int) { *value = (int)emu::envBytes("GCSA_EMU_SMS", 2); return cudaSuccess; }
+static inline cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
+static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+static inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* pool, int) { *pool = nullptr; return cudaSuccess; }
+static inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, cudaMemPoolAttr, void*) { return cudaSuccess; }
+static inline cudaError_t cudaMemGetInfo(size_t* free_b, size_t* total_b) { *free_b = *total_b = emu::envBytes("GCSA_EMU_FREE_BYTES", (size_t)8 << 30); return cudaSuccess; }
+template<class T> static inline cudaError_t cudaMalloc(T** p, size_t bytes) { *p = (T*)emu::alloc(bytes); return (*p != nullptr ? cudaSuccess : cudaErrorMemoryAllocation); }
+template<class T> static inline cudaError_t cudaMallocAsync(T** p, size_t bytes, cudaStream_t) { return cudaMalloc(p, bytes); }
+template<class T> static inline cudaError_t cudaHostAlloc(T** p, size_t bytes, unsigned) { return cudaMalloc(p, bytes); }
+static inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { std::free(p); return cudaSuccess; }
+static inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind) { if(bytes) { std::memmove(dst, src, bytes); } return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind k, cudaStream_t = nullptr) { return cudaMemcpy(dst, src, bytes, k); }
+static inline cudaError_t cudaMemset(void* p, int value, size_t bytes) { if(bytes) { std::memset(p, value, bytes); } return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void* p, int value, size_t bytes, cudaStream_t = nullptr) { return cudaMemset(p, value, bytes); }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)emu::alloc(16); return cudaSuccess; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { std::free((void*)s); return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t)emu::alloc(16); return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { std::free((void*)e); return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+
+//------------------------------------------------------------------------------
+// Thread coordinates and the fiber scheduler
+//------------------------------------------------------------------------------
+
+namespace emu
+{
+
+struct Coords { uint3 tid, bid; dim3 bdim, gdim; };
+inline thread_local Coords coords;
+
+#define threadIdx (emu::coords.tid)
+#define blockIdx  (emu::coords.bid)
+#define blockDim  (emu::coords.bdim)
+#define gridDim   (emu::coords.gdim)
+
+[[noreturn]] inline void die(const char* what) { std::fprintf(stderr, "cuda_emu: %s\n", what); std::abort(); }
+
+// Context switch: callee-saved registers + stack pointer (System V x86-64).
+extern "C" void emu_switch(void** save_sp, void* load_sp);
+#ifdef EMU_DEFINE_SWITCH
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size emu_switch,.-emu_switch
+)");
+#endif
+
+struct Warp
+{
+  unsigned gen = 0, arrived = 0, alive = 0;
+  unsigned pred_bits[2] = {0, 0};
+  unsigned long long vals[2][32];
+};
+
+struct Block;
+struct Fiber
+{
+  void* sp = nullptr; char* stack = nullptr;
+  bool finished = true;
+  unsigned tid = 0;
+};
+
+struct Block
+{
+  static constexpr size_t STACK = 256 << 10;
+  std::vector<Fiber> fibers;
+  std::vector<Warp> warps;
+  void* sched_sp = nullptr;
+  Fiber* current = nullptr;
+  unsigned bar_gen = 0, bar_arrived = 0, alive = 0;
+  unsigned long progress = 0;
+  const void* body = nullptr; void (*invoke)(const void*) = nullptr;
+
+  ~Block() { for(Fiber& f : fibers) { if(f.stack) { munmap(f.stack, STACK); } } }
+  void yield() { Fiber* f = current; emu_switch(&f->sp, sched_sp); }
+};
+inline thread_local Block* block = nullptr;       // non-null while a fiber-mode kernel is running on this OS thread
+
+inline void fiberMain()
+{
+  Block* b = block; Fiber* f = b->current;
+  b->invoke(b->body);
+  f->finished = true;
+  Warp& w = b->warps[f->tid >> 5];
+  b->alive--; w.alive--; b->progress++;
+  // an exited thread no longer takes part: release collectives that were only waiting for it
+  if(w.arrived > 0 && w.arrived >= w.alive) { w.arrived = 0; w.gen++; }
+  if(b->bar_arrived > 0 && b->bar_arrived >= b->alive) { b->bar_arrived = 0; b->bar_gen++; }
+  void* dummy; emu_switch(&dummy, b->sched_sp);
+  die("finished fiber resumed");
+}
+extern "C" inline void emu_fiber_entry() { fiberMain(); }
+
+template<class F> void runBlockFibers(Block& b, unsigned threads, const F& f)
+{
+  if(b.fibers.size() < threads) { b.fibers.resize(threads); }
+  b.warps.assign((threads + 31) / 32, Warp());
+  b.body = &f; b.invoke = [](const void* p) { (*(const F*)p)(); };
+  b.bar_gen = 0; b.bar_arrived = 0; b.alive = threads;
+  for(unsigned t = 0; t < threads; t++)
+  {
+    Fiber& fb = b.fibers[t];
+    if(fb.stack == nullptr)
+    {
+      fb.stack = (char*)mmap(nullptr, Block::STACK, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+      if(fb.stack == MAP_FAILED) { die("mmap of a fiber stack failed"); }
+    }
+    fb.finished = false; fb.tid = t;
+    b.warps[t >> 5].alive++;
+    // initial frame: six zeroed callee-saved registers, then the entry point as the return address;
+    // after `ret` the stack pointer is 8 mod 16, as at any function entry
+    uintptr_t top = ((uintptr_t)(fb.stack + Block::STACK) & ~(uintptr_t)15) - 8;
+    void** sp = (void**)top;
+    *(--sp) = (void*)&emu_fiber_entry;
+    for(int i = 0; i < 6; i++) { *(--sp) = nullptr; }
+    fb.sp = sp;
+  }
+  block = &b;
+  while(b.alive > 0)
+  {
+    unsigned long before = b.progress;
+    for(unsigned t = 0; t < threads; t++)
+    {
+      Fiber& fb = b.fibers[t];
+      if(fb.finished) { continue; }
+      b.current = &fb; coords.tid.x = t;
+      emu_switch(&b.sched_sp, fb.sp);
+    }
+    if(b.progress == before) { die("deadlock: every thread of the block waits at a collective that cannot complete"); }
+  }
+  block = nullptr;
+}
+
+struct Cfg
+{
+  dim3 grid, blockdim;
+  Cfg(dim3 g, dim3 b, size_t = 0, cudaStream_t = nullptr) : grid(g), blockdim(b) {}
+};
+
+template<class F> void launch(const Cfg& cfg, const F& f, bool collectives)
+{
+  if(cfg.grid.y != 1 || cfg.grid.z != 1 || cfg.blockdim.y != 1 || cfg.blockdim.z != 1) { die("only 1-D launches are emulated"); }
+  if(block != nullptr) { die("nested launch"); }
+  Coords saved = coords;
+  coords.gdim = cfg.grid; coords.bdim = cfg.blockdim;
+  coords.tid = uint3{0, 0, 0}; coords.bid = uint3{0, 0, 0};
+  static thread_local Block blk;
+  for(unsigned bx = 0; bx < cfg.grid.x; bx++)
+  {
+    coords.bid.x = bx;
+    if(collectives) { runBlockFibers(blk, cfg.blockdim.x, f); }
+    else { for(unsigned t = 0; t < cfg.blockdim.x; t++) { coords.tid.x = t; f(); } }
+  }
+  coords = saved;
+}
+
+// One warp-wide exchange: every live lane of the warp deposits (pred, value) and gets the generation's
+// buffers back once all live lanes have arrived.
+struct Exchange { unsigned ballot; const unsigned long long* vals; };
+inline Exchange warpExchange(unsigned mask, bool pred, unsigned long long value)
+{
+  Block* b = block;
+  if(b == nullptr) { die("warp collective in a kernel that the translator classified as collective-free"); }
+  unsigned tid = b->current->tid, lane = tid & 31;
+  Warp& w = b->warps[tid >> 5];
+  if(!((mask >> lane) & 1)) { die("calling lane is not in the mask of a *_sync collective"); }
+  unsigned g = w.gen, slot = g & 1;
+  if(w.arrived == 0) { w.pred_bits[slot] = 0; }
+  if(pred) { w.pred_bits[slot] |= (1u << lane); }
+  w.vals[slot][lane] = value;
+  w.arrived++; b->progress++;
+  if(w.arrived >= w.alive) { w.arrived = 0; w.gen++; }
+  else { while(w.gen == g) { b->yield(); } }
+  return Exchange{ w.pred_bits[slot] & mask, w.vals[slot] };
+}
+
+inline void blockBarrier()
+{
+  Block* b = block;
+  if(b == nullptr) { return; }      // direct mode: threads run one after another; a kernel that needs the barrier is run on fibers
+  unsigned g = b->bar_gen;
+  b->bar_arrived++; b->progress++;
+  if(b->bar_arrived >= b->alive) { b->bar_arrived = 0; b->bar_gen++; }
+  else { while(b->bar_gen == g) { b->yield(); } }
+}
+
+} // namespace emu
+
+static inline unsigned __ballot_sync(unsigned mask, int pred) { return emu::warpExchange(mask, pred != 0, 0).ballot; }
+static inline int __any_sync(unsigned mask, int pred) { return emu::warpExchange(mask, pred != 0, 0).ballot != 0; }
+static inline int __all_sync(unsigned mask, int pred) { return emu::warpExchange(mask, pred == 0, 0).ballot == 0; }
+static inline void __syncwarp(unsigned mask = 0xFFFFFFFFu) { emu::warpExchange(mask, false, 0); }
+static inline void __syncthreads() { emu::blockBarrier(); }
+template<class T> static inline T __shfl_sync(unsigned mask, T v, int src, int width = 32)
+{
+  static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");
+  unsigned long long raw = 0; std::memcpy(&raw, &v, sizeof(T));
+  unsigned lane = emu::block->current->tid & 31;
+  emu::Exchange x = emu::warpExchange(mask, false, raw);
+  unsigned from = (lane & ~(unsigned)(width - 1)) | ((unsigned)src & (unsigned)(width - 1));
+  T r; std::memcpy(&r, &x.vals[from], sizeof(T)); return r;
+}
+template<class T> static inline T __shfl_down_sync(unsigned mask, T v, unsigned delta, int width = 32)
+{
+  static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");
+  unsigned long long raw = 0; std::memcpy(&raw, &v, sizeof(T));
+  unsigned lane = emu::block->current->tid & 31;
+  emu::Exchange x = emu::warpExchange(mask, false, raw);
+  unsigned from = lane + delta;
+  if((from & ~(unsigned)(width - 1)) != (lane & ~(unsigned)(width - 1))) { from = lane; }
+  T r; std::memcpy(&r, &x.vals[from], sizeof(T)); return r;
+}
+template<class T> static inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32)
+{
+  unsigned long long raw = 0; std::memcpy(&raw, &v, sizeof(T));
+  unsigned lane = emu::block->current->tid & 31;
+  emu::Exchange x = emu::warpExchange(mask, false, raw);
+  unsigned from = ((lane & (unsigned)(width - 1)) >= delta ? lane - delta : lane);
+  T r; std::memcpy(&r, &x.vals[from], sizeof(T)); return r;
+}
+template<class T> static inline T __shfl_xor_sync(unsigned mask, T v, int lanemask, int width = 32)
+{
+  unsigned long long raw = 0; std::memcpy(&raw, &v, sizeof(T));
+  unsigned lane = emu::block->current->tid & 31;
+  emu::Exchange x = emu::warpExchange(mask, false, raw);
+  unsigned from = lane ^ (unsigned)lanemask; (void)width;
+  T r; std::memcpy(&r, &x.vals[from], sizeof(T)); return r;
+}
+
+//------------------------------------------------------------------------------
+// Device intrinsics
+//------------------------------------------------------------------------------
+
+template<class T> static inline T __ldg(const T* p) { return *p; }
+template<class T> static inline T __ldcs(const T* p) { return *p; }
+template<class T> static inline T __ldcg(const T* p) { return *p; }
+template<class T> static inline void __stcs(T* p, T v) { *p = v; }
+template<class T> static inline void __stcg(T* p, T v) { *p = v; }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+static inline int __clz(int x) { return (x == 0 ? 32 : __builtin_clz((unsigned)x)); }
+static inline int __clzll(long long x) { return (x == 0 ? 64 : __builtin_clzll((unsigned long long)x)); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline int __ffsll(long long x) { return __builtin_ffsll(x); }
+static inline unsigned __brev(unsigned x)
+{
+  x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+  x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+  x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+  return __builtin_bswap32(x);
+}
+static inline unsigned long long __brevll(unsigned long long x) { return ((unsigned long long)__brev((unsigned)x) << 32) | __brev((unsigned)(x >> 32)); }
+// position of the offset-th (1-based) set bit of mask at or above bit `base`; 0xFFFFFFFF if there is none
+static inline unsigned __fns(unsigned mask, unsigned base, int offset)
+{
+  if(offset <= 0) { emu::die("__fns with offset <= 0 is not emulated"); }
+  for(unsigned i = base; i < 32; i++) { if((mask >> i) & 1) { if(--offset == 0) { return i; } } }
+  return 0xFFFFFFFFu;
+}
+static inline unsigned __vcmpltu4(unsigned a, unsigned b)
+{
+  unsigned r = 0;
+  for(int i = 0; i < 4; i++) { if(((a >> (8 * i)) & 0xFF) < ((b >> (8 * i)) & 0xFF)) { r |= 0xFFu << (8 * i); } }
+  return r;
+}
+static inline unsigned __vcmpleu4(unsigned a, unsigned b)
+{
+  unsigned r = 0;
+  for(int i = 0; i < 4; i++) { if(((a >> (8 * i)) & 0xFF) <= ((b >> (8 * i)) & 0xFF)) { r |= 0xFFu << (8 * i); } }
+  return r;
+}
+static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) { return (unsigned long long)(((unsigned __int128)a * b) >> 64); }
+template<class T, class U> static inline T atomicAdd(T* p, U v) { return __atomic_fetch_add(p, (T)v, __ATOMIC_RELAXED); }
+template<class T, class U> static inline T atomicOr(T* p, U v) { return __atomic_fetch_or(p, (T)v, __ATOMIC_RELAXED); }
+template<class T, class U> static inline T atomicMax(T* p, U v) { T old = *p; while(old < (T)v && !__atomic_compare_exchange_n(p, &old, (T)v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return old; }
+template<class T, class U> static inline T atomicMin(T* p, U v) { T old = *p; while(old > (T)v && !__atomic_compare_exchange_n(p, &old, (T)v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return old; }
+template<class T, class U> static inline T atomicExch(T* p, U v) { return __atomic_exchange_n(p, (T)v, __ATOMIC_RELAXED); }
+template<class T, class U> static inline T atomicCAS(T* p, U cmp, U v) { T expected = (T)cmp; __atomic_compare_exchange_n(p, &expected, (T)v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED); return expected; }
+
+//------------------------------------------------------------------------------
+// cub (the two device-wide primitives engine.cu calls)
+//------------------------------------------------------------------------------
+
+namespace cub
+{
+struct DeviceScan
+{
+  template<class In, class Out, class N>
+  static cudaError_t ExclusiveSum(void* tmp, size_t& bytes, In in, Out out, N n, cudaStream_t = nullptr)
+  {
+    if(tmp == nullptr) { bytes = 256; return cudaSuccess; }
+    typedef typename std::remove_cv<typename std::remove_reference<decltype(out[0])>::type>::type T;
+    T sum = 0;
+    for(N i = 0; i < n; i++) { T x = (T)in[i]; out[i] = sum; sum += x; }
+    return cudaSuccess;
+  }
+  template<class In, class Out, class N>
+  static cudaError_t InclusiveSum(void* tmp, size_t& bytes, In in, Out out, N n, cudaStream_t = nullptr)
+  {
+    if(tmp == nullptr) { bytes = 256; return cudaSuccess; }
+    typedef typename std::remove_cv<typename std::remove_reference<decltype(out[0])>::type>::type T;
+    T sum = 0;
+    for(N i = 0; i < n; i++) { sum += (T)in[i]; out[i] = sum; }
+    return cudaSuccess;
+  }
+};
+struct DeviceSegmentedSort
+{
+  template<class K, class B, class E>
+  static cudaError_t SortKeys(void* tmp, size_t& bytes, const K* in, K* out, long long total, long long segments, B begins, E ends, cudaStream_t = nullptr)
+  {
+    if(tmp == nullptr) { bytes = 256; return cudaSuccess; }
+    if(total > 0 && out != in) { std::memcpy(out, in, (size_t)total * sizeof(K)); }
+    for(long long s = 0; s < segments; s++) { std::sort(out + begins[s], out + ends[s]); }
+    return cudaSuccess;
+  }
+};
+}

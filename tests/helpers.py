@@ -51,3 +51,30 @@ def kat1_flat(kat=None):
         extra_values=bits_from_positions(ev_ones, sum(occ)),
         redundant_len=(n - 1) + sum(red), redundant=bits_from_positions(rd_ones, (n - 1) + sum(red)))
     return flat, lcp
+
+
+# ---- "device" buffers for the tests that call the device-pointer entry points -------------------------------
+# Under the host emulation (tests/emu) device memory is host memory and there is one implicit stream.
+EMULATED = False
+
+
+def to_device(array):
+    import torch
+    t = torch.from_numpy(array)
+    return t.clone() if EMULATED else t.cuda()
+
+
+def device_empty(shape, dtype):
+    import torch
+    return torch.empty(shape, dtype=dtype, device="cpu" if EMULATED else "cuda")
+
+
+def current_stream():
+    import torch
+    return 0 if EMULATED else torch.cuda.current_stream().cuda_stream
+
+
+def device_sync():
+    import torch
+    if not EMULATED:
+        torch.cuda.synchronize()

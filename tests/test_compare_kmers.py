@@ -77,7 +77,7 @@ def test_oracle_against_the_reference(pair):
     assert ra.compare_kmers(ra, 12) == (oa.count_kmers(12), 0, 0)
 
 
-@pytest.mark.gpu
+@pytest.mark.engine
 def test_device_compare_kmers(pair):
     from gcsa2_b200 import GCSA
     a, b, fa, fb, _, _ = pair

@@ -131,7 +131,7 @@ def test_reference_loads_our_files(built, tmp_path):
     assert ref.ReferenceIndex.load(tmp_path / "bad.gcsa") is None        # GCSA::load throws on a bad header (gcsa.cpp:188-193)
 
 
-@pytest.mark.gpu
+@pytest.mark.engine
 def test_engine_on_loaded_files(built, tmp_path):
     """The CUDA engine over an index that went through the file formats answers like the oracle."""
     from gcsa2_b200 import GCSA, LCPArray

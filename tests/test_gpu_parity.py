@@ -13,7 +13,7 @@ from gcsa2_b200.builder import CharGraph, build_index
 from gcsa2_b200.flat import FlatLCP
 from oracle import oracle as orc
 
-pytestmark = pytest.mark.gpu
+pytestmark = pytest.mark.engine
 M64 = (1 << 64) - 1
 
 
@@ -203,15 +203,15 @@ def test_snp_graph_find_locate_parent():
 
 def test_device_pointer_entry_point_and_empty_batches():
     import torch
+    from helpers import current_stream, device_empty, device_sync, to_device
     seq = synth.random_sequence(50_000, seed=4)
     flat, _, _ = build_index(synth.linear_graph(seq), 16, 1)
     gpu, ora = both(flat)
     chars, offsets = synth.patterns_from_sequence(seq, 10_000, 24, seed=1)
-    d_chars = torch.from_numpy(chars).cuda(); d_off = torch.from_numpy(offsets.view(np.int64)).cuda()
-    d_sp = torch.empty(10_000, dtype=torch.int64, device="cuda"); d_ep = torch.empty_like(d_sp)
-    stream = torch.cuda.current_stream().cuda_stream
-    gpu.find_device(d_chars, d_off, 10_000, d_sp, d_ep, stream)
-    torch.cuda.synchronize()
+    d_chars = to_device(chars); d_off = to_device(offsets.view(np.int64))
+    d_sp = device_empty(10_000, torch.int64); d_ep = torch.empty_like(d_sp)
+    gpu.find_device(d_chars, d_off, 10_000, d_sp, d_ep, current_stream())
+    device_sync()
     osp, oep, _ = ora.find_batch(chars, offsets)
     assert (d_sp.cpu().numpy().view(np.uint64) == osp).all() and (d_ep.cpu().numpy().view(np.uint64) == oep).all()
     sp, ep = gpu.find_batch([])
@@ -248,6 +248,7 @@ def test_count_kmers_frontier_expansion():
         assert gpu.count_kmers(k) == ora.count_kmers(k, threads=8)
 
 
+@pytest.mark.gpu
 def test_full_size_config2_properties():
     """BASELINE.json configs[1] at full size: 10 M 32-mers sampled from a 100 Mbp linear reference,
     order 128.  Size-independent properties: every sampled pattern is found; all engine variants

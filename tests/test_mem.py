@@ -43,7 +43,7 @@ def test_mem_scan_definition_properties():
     assert list(offs) == [0, 1, 1, 1] and list(vals[0][:2]) == [0, 100]
 
 
-@pytest.mark.gpu
+@pytest.mark.engine
 def test_mem_scan_device_matches_definition():
     from gcsa2_b200 import GCSA, LCPArray, mem_batch
     flat, flcp, chars, offsets = make(30_000, L=200_000, seed=3)
@@ -61,13 +61,14 @@ def test_mem_scan_device_matches_definition():
     assert list(offs) == [0] and vals.shape == (0, 4)
 
 
-@pytest.mark.gpu
+@pytest.mark.engine
 def test_mem_scan_scratch_paths(monkeypatch):
     """The one-pass scan (matches staged in a per-pattern scratch slot, overflowing patterns redone), with
     slots of 16, 4 and 1 matches, and the two-pass fallback: all equal to the definition.  Noisy patterns
     (10 % substitutions) so that many patterns have more matches than a slot holds."""
     from gcsa2_b200 import GCSA, LCPArray, mem_batch, mem_device
     import torch
+    from helpers import current_stream, device_empty, device_sync, to_device
     seq = synth.random_sequence(100_000, seed=5)
     graph, sites, alt = synth.snp_graph(seq, seed=5, snp_rate=0.01)
     flat, flcp, _ = build_index(graph, 16, 3)
@@ -85,14 +86,14 @@ def test_mem_scan_scratch_paths(monkeypatch):
     # device entry point with a caller buffer: too small -> the needed size, then the same answer
     from gcsa2_b200 import capi
     n = len(offsets) - 1
-    d_chars = torch.from_numpy(chars).cuda(); d_off = torch.from_numpy(offsets.view(np.int64)).cuda()
-    d_out = torch.empty(n + 1, dtype=torch.int64, device="cuda")
-    small = torch.empty((10, 4), dtype=torch.int64, device="cuda")
+    d_chars = to_device(chars); d_off = to_device(offsets.view(np.int64))
+    d_out = device_empty(n + 1, torch.int64)
+    small = device_empty((10, 4), torch.int64)
     with pytest.raises(capi.GCSAError) as err:
-        mem_device(gpu, glcp, d_chars, d_off, n, d_out, small, 10, torch.cuda.current_stream().cuda_stream)
+        mem_device(gpu, glcp, d_chars, d_off, n, d_out, small, 10, current_stream())
     assert err.value.code == capi.ERR_CAPACITY
     total = int(ooffs[-1])
-    big = torch.empty((total, 4), dtype=torch.int64, device="cuda")
-    got = mem_device(gpu, glcp, d_chars, d_off, n, d_out, big, total, torch.cuda.current_stream().cuda_stream)
-    torch.cuda.synchronize()
+    big = device_empty((total, 4), torch.int64)
+    got = mem_device(gpu, glcp, d_chars, d_off, n, d_out, big, total, current_stream())
+    device_sync()
     assert got == total and (d_out.cpu().numpy().view(np.uint64) == ooffs).all() and (big.cpu().numpy().view(np.uint64) == ovals).all()

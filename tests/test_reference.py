@@ -113,7 +113,7 @@ def test_reference_loaded_from_flat_arrays_answers_like_its_own_build(built):
     assert (s1 == s2).all() and (e1 == e2).all()
 
 
-@pytest.mark.gpu
+@pytest.mark.engine
 def test_engine_equals_reference(built):
     from gcsa2_b200 import GCSA, LCPArray
     name, flat, flcp, kmers, reference = built

@@ -11,7 +11,7 @@ from gcsa2_b200.builder import KMers, build_index
 from gcsa2_b200.flat import bits_from_positions, positions_from_bits
 from oracle import reference as ref
 
-pytestmark = pytest.mark.gpu
+pytestmark = pytest.mark.engine
 
 
 def graphs():
