@@ -22,6 +22,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 #include <sys/mman.h>
 
@@ -72,11 +74,37 @@ enum cudaMemPoolAttr { cudaMemPoolAttrReleaseThreshold = 4 };
 namespace emu
 {
 inline size_t envBytes(const char* name, size_t def) { const char* s = std::getenv(name); return (s != nullptr && *s ? (size_t)std::strtoull(s, nullptr, 10) : def); }
+// "Device" allocations end right before an inaccessible page (sizes rounded up to 32 bytes, the sector the
+// kernels read): a kernel that reads or writes past the end of a buffer faults here instead of passing silently.
+struct Allocations
+{
+  std::mutex mutex;
+  std::unordered_map<void*, std::pair<void*, size_t>> live;     // pointer -> (mapping, length)
+};
+inline Allocations& allocations() { static Allocations a; return a; }
 inline void* alloc(size_t bytes)
 {
-  void* p = nullptr;
-  if(posix_memalign(&p, 256, std::max<size_t>(bytes, 256)) != 0) { return nullptr; }
+  const size_t page = 4096;
+  size_t total = (std::max<size_t>(bytes, 32) + 31) & ~(size_t)31;
+  size_t pages = (total + page - 1) / page + 1;
+  char* base = (char*)mmap(nullptr, pages * page, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+  if(base == MAP_FAILED) { return nullptr; }
+  mprotect(base + (pages - 1) * page, page, PROT_NONE);
+  void* p = base + (pages - 1) * page - total;
+  Allocations& a = allocations();
+  std::lock_guard<std::mutex> lock(a.mutex);
+  a.live[p] = std::make_pair((void*)base, pages * page);
   return p;
+}
+inline void release(void* p)
+{
+  if(p == nullptr) { return; }
+  Allocations& a = allocations();
+  std::lock_guard<std::mutex> lock(a.mutex);
+  auto it = a.live.find(p);
+  if(it == a.live.end()) { std::fprintf(stderr, "cuda_emu: free of a pointer that was not allocated here\n"); std::abort(); }
+  munmap(it->second.first, it->second.second);
+  a.live.erase(it);
 }
 }
 
@@ -94,19 +122,19 @@ static inline cudaError_t cudaMemGetInfo(size_t* free_b, size_t* total_b) { *fre
 template<class T> static inline cudaError_t cudaMalloc(T** p, size_t bytes) { *p = (T*)emu::alloc(bytes); return (*p != nullptr ? cudaSuccess : cudaErrorMemoryAllocation); }
 template<class T> static inline cudaError_t cudaMallocAsync(T** p, size_t bytes, cudaStream_t) { return cudaMalloc(p, bytes); }
 template<class T> static inline cudaError_t cudaHostAlloc(T** p, size_t bytes, unsigned) { return cudaMalloc(p, bytes); }
-static inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
-static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { std::free(p); return cudaSuccess; }
-static inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
+static inline cudaError_t cudaFree(void* p) { emu::release(p); return cudaSuccess; }
+static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { emu::release(p); return cudaSuccess; }
+static inline cudaError_t cudaFreeHost(void* p) { emu::release(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind) { if(bytes) { std::memmove(dst, src, bytes); } return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind k, cudaStream_t = nullptr) { return cudaMemcpy(dst, src, bytes, k); }
 static inline cudaError_t cudaMemset(void* p, int value, size_t bytes) { if(bytes) { std::memset(p, value, bytes); } return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* p, int value, size_t bytes, cudaStream_t = nullptr) { return cudaMemset(p, value, bytes); }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)emu::alloc(16); return cudaSuccess; }
-static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { std::free((void*)s); return cudaSuccess; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { emu::release((void*)s); return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t)emu::alloc(16); return cudaSuccess; }
-static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { std::free((void*)e); return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { emu::release((void*)e); return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 
