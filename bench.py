@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--queries", type=int, default=10_000_000, help="patterns per GPU")
     ap.add_argument("--pattern-length", type=int, default=32)
     ap.add_argument("--kmer-table-k", type=int, default=16, help="k-mer table: find() of all 4^k ACGT strings, 8 B each (16 = 34 GB; profiles/r01_kmer_table_sweep.txt)")
+    ap.add_argument("--fused-table", type=int, default=-1, help="k-mer table entries of 16 B that carry the first jump (one load per 32-mer with k = 16; 69 GB): 1 = yes, 0 = no, -1 = the engine decides by free memory")
     ap.add_argument("--two-step", type=int, default=-1, help="1 = build and use the two-step blocks, 0 = never, -1 = by index size")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -306,7 +307,7 @@ def recorded_traffic(args, index):
     default = (args.ref_mbp == 100.0 and args.queries == 10_000_000 and args.pattern_length == 32 and not index.twoStep())
     if default and os.path.exists(path):
         with open(path) as f:
-            entry = json.load(f).get("k%d" % index.kmerTableK())
+            entry = json.load(f).get("k%d%s" % (index.kmerTableK(), "f" if index.fusedTable() else ""))
         if entry:
             return float(entry["dram_bytes_per_launch"])
     return None
@@ -366,7 +367,13 @@ def main():
     chars, offsets = make_patterns(seq, n, length, seed=100 + rank)
 
     t0 = time.time()
-    index = GCSA(flat, device=local, kmer_table_k=args.kmer_table_k, two_step=(None if args.two_step < 0 else bool(args.two_step)))
+    options = dict(device=local, kmer_table_k=args.kmer_table_k, two_step=(None if args.two_step < 0 else bool(args.two_step)))
+    create_note = None
+    try:
+        index = GCSA(flat, fused_table=(None if args.fused_table < 0 else bool(args.fused_table)), **options)
+    except Exception as exc:                                        # e.g. not enough free HBM for the 16-byte entries
+        create_note = "fused table failed (%s), 8-byte entries instead" % exc
+        index = GCSA(flat, fused_table=False, **options)
     create_s = time.time() - t0
 
     # ---- device-resident leg ----
@@ -426,7 +433,8 @@ def main():
     # 64 B per distinct rank probe (the HBM access granule: a missed 32-byte sector
     # costs one 64-byte fetch), here one probe = one fused sector; 8 B per k-mer table entry read;
     # |P| + 16 B of I/O per query.
-    engine_bytes = scale * (64.0 * st["sector_probes"] + 8.0 * st["table_hits"]) + float(n) * (length + 16)
+    entry_bytes = 16.0 if index.fusedTable() else 8.0
+    engine_bytes = scale * (64.0 * st["sector_probes"] + entry_bytes * st["table_hits"]) + float(n) * (length + 16)
 
     # ---- max over ranks, totals ----
     if dist is not None:
@@ -457,7 +465,7 @@ def main():
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": workload_name(args), "queries_per_gpu": n, "pattern_length": length,
                        "index": {"path_nodes": index.size(), "edges": index.edgeCount(), "order": index.order(),
-                                 "device_bytes": index.deviceBytes(), "kmer_table_k": index.kmerTableK(), "two_step": index.twoStep()},
+                                 "device_bytes": index.deviceBytes(), "kmer_table_k": index.kmerTableK(), "fused_table": index.fusedTable(), "two_step": index.twoStep()},
                        "parallelism": "queries sharded across %d GPU(s), index replicated" % world,
                        "l2": "no explicit flush: every step streams %.0f MB of patterns/offsets/results, more than the 126 MB L2" % (
                            n * (length + 16) / 1e6)},
@@ -474,7 +482,7 @@ def main():
                          "traffic": traffic, "dram_frac": (traffic / (ms_total / args.steps / 1000.0) / 1e9 / peak if traffic else None),
                          "kernel": "find_kernel<false,4,false>", "peak_source": peak_src,
                          "bytes_per_launch": engine_bytes,
-                         "accounting": "64 B per distinct probe executed (fused sector or jump-table entry) + 8 B per k-mer table entry + |P| + 16 B I/O per query (SURVEY.md 8(d) units); "
+                         "accounting": "64 B per distinct probe executed (fused sector or jump-table entry) + 8 B per k-mer table entry (16 B when it carries the first jump) + |P| + 16 B I/O per query (SURVEY.md 8(d) units); "
                                        "dram_frac = recorded ncu DRAM bytes of this launch / this run's time / peak: a random probe into tens of GB costs ~128 B of HBM traffic, "
                                        "twice the 64 B the accounting grants it (profiles/r01_random_probe_microbench.txt)",
                          "jump_table_k": index.jumpK(),
@@ -482,6 +490,8 @@ def main():
             "clocks": clocks,
             "setup": {"index_build_s": build_s, "index_create_s": create_s},
         }
+        if create_note:
+            line["setup"]["note"] = create_note
         if locate is not None:
             line["locate"] = locate
         if not args.no_cpu_baseline:

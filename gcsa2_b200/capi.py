@@ -37,13 +37,13 @@ class FlatLcp(C.Structure):
 
 
 class Options(C.Structure):
-    _fields_ = [("kmer_table_k", C.c_int), ("two_step", C.c_int), ("walk_table", C.c_int), ("jump_table", C.c_int), ("reserved", C.c_int * 4)]
+    _fields_ = [("kmer_table_k", C.c_int), ("two_step", C.c_int), ("walk_table", C.c_int), ("jump_table", C.c_int), ("fused_table", C.c_int), ("reserved", C.c_int * 3)]
 
 
 class Info(C.Structure):
     _fields_ = [("path_nodes", C.c_uint64), ("edge_count", C.c_uint64), ("order", C.c_uint64),
                 ("sample_count", C.c_uint64), ("device_bytes", C.c_uint64),
-                ("kmer_table_k", C.c_int), ("device", C.c_int), ("sm_count", C.c_int), ("two_step", C.c_int), ("jump_k", C.c_int)]
+                ("kmer_table_k", C.c_int), ("device", C.c_int), ("sm_count", C.c_int), ("two_step", C.c_int), ("jump_k", C.c_int), ("fused_table", C.c_int)]
 
 
 class FindStats(C.Structure):

@@ -82,6 +82,7 @@ struct DevView
   const u64* sparse_pos[3]; u64 sparse_n[3];       // comps 0, 5, 6
   const u64* stored_samples; const u64* sample_start; u64 sample_count;
   const u64* table; int table_k;      // entry = sp | length << 40; length 0xFFFFFF = not tabulated
+  const ulonglong2* table2;            // fused form (replaces `table`): { that entry, the jump entry of sp if the range is a singleton, else 0 }
   const u32* walk32; const u64* walk64; // locate walk table: LF(i) << 1, or rank(sampled, i) << 1 | 1 for sampled nodes
   u32 default_alphabet;                // char2comp is exactly ACGT / acgt -> 1..4 for the bases (enables the SWAR pattern packing)
   const u64* jump; u32 jump_k, jump_tbits;
@@ -482,12 +483,29 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
               }
               if(ok)
               {
-                u64 r = __ldg(v.table + idx);
+                u64 r, je = 0;
+                if(v.table2 != nullptr) { ulonglong2 both = __ldg(v.table2 + idx); r = both.x; je = both.y; }
+                else { r = __ldg(v.table + idx); }
                 u64 len = r >> 40;
                 if(len != TABLE_ESCAPE)
                 {
                   sp = r & M40; ep = sp + len - 1; pos = e - v.table_k; used_table = true;
                   if(STATS) { st_hits++; }
+                  // Fused table: the jump entry of a singleton result came with the same 16-byte load, so the first
+                  // jump costs no probe.  Taken only when the whole path lies inside the packed tail and inside
+                  // the pattern; everything else is left to the main loop.
+                  u32 jl = (u32)(je >> 59);
+                  if(jl >= 2 && (u64)jl <= pos - b && (u32)v.table_k + jl <= tail_n)
+                  {
+                    u64 stored = ((je << 5) >> 5) >> v.jump_tbits;
+                    if((((tail >> (2 * v.table_k)) ^ stored) & ((1ull << (2 * jl)) - 1)) == 0)
+                    {
+                      sp = ep = (je & ((1ull << v.jump_tbits) - 1));
+                      pos -= jl;
+                      if(STATS) { st_steps += jl; }
+                    }
+                    else { jump_mode = 0; }                          // leaves the unary path: it dies within these steps
+                  }
                 }
               }
             }
@@ -621,8 +639,10 @@ table_extend_kernel(const DevView v, int j, ulonglong2* tmp)
 }
 
 // last level: level k - 1 in tmp -> packed level k in table (k >= 2); for k == 1 pack tmp itself
+// With table2 != nullptr the fused form is written instead: next to each entry the jump-table entry of its sp when the
+// result is a single path node (find_kernel then takes the first jump without another probe).
 __global__ void __launch_bounds__(256)
-table_final_kernel(const DevView v, int k, const ulonglong2* tmp, u64* table)
+table_final_kernel(const DevView v, int k, const ulonglong2* tmp, u64* table, ulonglong2* table2)
 {
   u64 total = (k == 1 ? 4 : 1ull << (2 * (k - 1)));
   for(u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x)
@@ -634,7 +654,9 @@ table_final_kernel(const DevView v, int k, const ulonglong2* tmp, u64* table)
       if(k > 1 && !range_empty(sp, ep)) { lf_range(v, sp, ep, c + 1, sp, ep); }
       u64 len = ep + 1 - sp;
       u64 entry = (len >= TABLE_ESCAPE || sp > M40) ? (TABLE_ESCAPE << 40) : (sp | (len << 40));
-      table[k == 1 ? idx : (idx | ((u64)c << (2 * (k - 1))))] = entry;
+      u64 slot = (k == 1 ? idx : (idx | ((u64)c << (2 * (k - 1)))));
+      if(table2 == nullptr) { table[slot] = entry; }
+      else { table2[slot] = make_ulonglong2(entry, (len == 1 && v.jump != nullptr) ? __ldg(v.jump + sp) : 0ull); }
     }
   }
 }
@@ -2111,8 +2133,16 @@ int gcsa_b200_index_create(const gcsa_flat_index* host, int device, const gcsa_b
   {
     u64 entries = 1ull << (2 * k);
     u64 tmp_entries = (k == 1 ? 4 : 1ull << (2 * (k - 1)));
+    // Fused form (16 bytes per entry: the jump entry of a singleton result rides along) when there is a jump table
+    // and the doubled table still leaves most of the device free; fused_table = 1 forces it, -1 forbids it.
+    int want_fused = (options != nullptr ? options->fused_table : 0);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    bool fused = (v.jump != nullptr && want_fused >= 0 &&
+                  (want_fused > 0 || (entries + tmp_entries) * sizeof(ulonglong2) < free_b / 10 * 6));
+    size_t entry_bytes = (fused ? sizeof(ulonglong2) : sizeof(u64));
     void* p = nullptr; void* tmp = nullptr;
-    cudaError_t e = cudaMalloc(&p, entries * sizeof(u64));
+    cudaError_t e = cudaMalloc(&p, entries * entry_bytes);
     if(e == cudaSuccess) { e = cudaMalloc(&tmp, tmp_entries * sizeof(ulonglong2)); }
     if(e != cudaSuccess)
     {
@@ -2120,14 +2150,15 @@ int gcsa_b200_index_create(const gcsa_flat_index* host, int device, const gcsa_b
       gcsa_b200_index_destroy(idx);
       return fail(GCSA_B200_ERR_NOMEM, "index_create: k-mer table allocation failed");
     }
-    idx->allocations.push_back(p); idx->device_bytes += entries * sizeof(u64);
+    idx->allocations.push_back(p); idx->device_bytes += entries * entry_bytes;
     table_init_kernel<<<1, 256>>>(v, (ulonglong2*)tmp);
     for(int j = 1; j + 1 < k; j++) { table_extend_kernel<<<gridFor(1ull << (2 * j), idx->sm_count, 8), 256>>>(v, j, (ulonglong2*)tmp); }
-    table_final_kernel<<<gridFor(tmp_entries, idx->sm_count, 8), 256>>>(v, k, (const ulonglong2*)tmp, (u64*)p);
+    table_final_kernel<<<gridFor(tmp_entries, idx->sm_count, 8), 256>>>(v, k, (const ulonglong2*)tmp, fused ? nullptr : (u64*)p, fused ? (ulonglong2*)p : nullptr);
     e = cudaDeviceSynchronize();
     cudaFree(tmp);
     if(e != cudaSuccess) { gcsa_b200_index_destroy(idx); return fail(GCSA_B200_ERR_CUDA, std::string("k-mer table kernels: ") + cudaGetErrorString(e)); }
-    v.table = (const u64*)p; v.table_k = k;
+    if(fused) { v.table2 = (const ulonglong2*)p; } else { v.table = (const u64*)p; }
+    v.table_k = k;
   }
   #undef TRY_RC
 
@@ -2154,6 +2185,7 @@ int gcsa_b200_index_info(const gcsa_b200_index* index, gcsa_b200_info* info)
   info->device = index->device; info->sm_count = index->sm_count;
   info->two_step = (index->view.bwt2 != nullptr ? 1 : 0);
   info->jump_k = (index->view.jump != nullptr ? (int)index->view.jump_k : 0);
+  info->fused_table = (index->view.table2 != nullptr ? 1 : 0);
   return 0;
 }
 

@@ -42,7 +42,7 @@ def range_length(rng):
 
 
 class GCSA:
-    def __init__(self, flat, device=0, kmer_table_k=0, two_step=None, walk_table=None, jump_table=None):
+    def __init__(self, flat, device=0, kmer_table_k=0, two_step=None, walk_table=None, jump_table=None, fused_table=None):
         self._h = None
         L = self._L = capi.lib()            # the handle is destroyed by the library that made it
         keep = []
@@ -50,6 +50,7 @@ class GCSA:
         opt = capi.Options(); opt.kmer_table_k = int(kmer_table_k); opt.two_step = (-1 if two_step is None else int(bool(two_step)))
         opt.walk_table = (-1 if walk_table is None else int(walk_table))
         opt.jump_table = (0 if jump_table is None else (1 if jump_table else -1))
+        opt.fused_table = (0 if fused_table is None else (1 if fused_table else -1))
         h = C.c_void_p()
         capi.check(L.gcsa_b200_index_create(C.byref(f), int(device), C.byref(opt), C.byref(h)))
         self._h = h
@@ -87,6 +88,7 @@ class GCSA:
     def kmerTableK(self): return int(self._info.kmer_table_k)
     def twoStep(self): return bool(self._info.two_step)
     def jumpK(self): return int(self._info.jump_k)
+    def fusedTable(self): return bool(self._info.fused_table)
     def smCount(self): return int(self._info.sm_count)
     @property
     def handle(self): return self._h

@@ -95,7 +95,12 @@ typedef struct gcsa_b200_options {
                               predecessor character), so that a singleton range advances that many characters
                               with one load.  0 = build if it fits, 1 = build, -1 = do not.  Exact: a pattern that
                               leaves the path or ends inside it is continued with single steps. */
-  int      reserved[4];
+  int      fused_table;    /* find(): k-mer table entries of 16 bytes instead of 8 -- next to the result of the k-mer, the
+                              jump-table entry of its path node when the result is a single node, so that the table
+                              lookup and the first jump are ONE load (a 32-mer with k = 16 is one 16-byte probe).
+                              0 = when there is a jump table and 4^k * 16 bytes fit comfortably, 1 = always (needs
+                              the jump table), -1 = never.  Exact: the same answers as the two separate loads. */
+  int      reserved[3];
 } gcsa_b200_options;
 
 typedef struct gcsa_b200_info {
@@ -106,6 +111,7 @@ typedef struct gcsa_b200_info {
   int      sm_count;
   int      two_step;                   /* 1 if the two-step blocks are in use */
   int      jump_k;                     /* longest path of the jump table (0 = no table) */
+  int      fused_table;                /* 1 if the k-mer table holds fused 16-byte entries */
 } gcsa_b200_info;
 
 /* Per-batch statistics of find(): filled by gcsa_b200_find_stats_host (measurement only). */

@@ -430,6 +430,55 @@ def test_jump_table_equals_single_steps():
             assert st["lf_steps"] == st0["lf_steps"] and st["sector_probes"] < st0["sector_probes"]
 
 
+def test_fused_table_equals_separate_loads():
+    """k-mer table with fused 16-byte entries (result of the k-mer + the jump entry of its node, one load) ==
+    the 8-byte table followed by a separate jump load == the oracle.  Lengths around every boundary: shorter than
+    k, k exactly, k + a partial path, k + 16, beyond the packed 32-character tail; substitutions at random offsets
+    (the early-exit pair of the exact failing step), an N, lower case, random patterns, and a graph with bubbles."""
+    rng = np.random.default_rng(31)
+    seq = synth.random_sequence(300_000, seed=31)
+    graph, sites, alt = synth.snp_graph(seq, seed=31, snp_rate=0.01)
+    for name, flat, sampler in (
+            ("linear", build_index(synth.linear_graph(seq), 16, 3)[0], lambda n, L, s: synth.patterns_from_sequence(seq, n, L, seed=s)),
+            ("snp", build_index(graph, 16, 3)[0], lambda n, L, s: synth.patterns_from_snp_graph(seq, sites, alt, n, L, seed=s))):
+        ora = orc.OracleGCSA(flat)
+        pats = []
+        for L in (5, 8, 9, 10, 12, 17, 23, 24, 25, 31, 32, 33, 40, 64):
+            c, o = sampler(1500, L, 100 + L)
+            c = c.copy()
+            for i in range(1500):
+                kind = i % 5
+                if kind == 1:                                        # one substitution somewhere
+                    p = int(o[i]) + int(rng.integers(0, L))
+                    c[p] = synth.COMP2CHAR[1 + (int(np.where(synth.COMP2CHAR == c[p])[0][0]) % 4)]
+                elif kind == 2 and i % 10 == 2:                      # an N
+                    c[int(o[i]) + int(rng.integers(0, L))] = ord("N")
+                elif kind == 3:                                      # lower case
+                    c[int(o[i]):int(o[i + 1])] |= 0x20
+                pats.append(bytes(c[int(o[i]):int(o[i + 1])]))
+        rc, ro = synth.random_patterns(2000, 32, seed=77)
+        pats += [bytes(rc[int(ro[i]):int(ro[i + 1])]) for i in range(2000)]
+        chars, offsets = orc.pack_patterns(pats)
+        osp, oep, _ = ora.find_batch(chars, offsets, threads=4)
+        for table_k, two_step in ((8, False), (4, False), (9, True), (1, False)):
+            fused = GCSA(flat, kmer_table_k=table_k, two_step=two_step, jump_table=True, fused_table=True)
+            plain = GCSA(flat, kmer_table_k=table_k, two_step=two_step, jump_table=True, fused_table=False)
+            assert fused.fusedTable() and not plain.fusedTable()
+            a, b, st = fused.find_batch(chars, offsets, stats=True)
+            c2, d2, st0 = plain.find_batch(chars, offsets, stats=True)
+            bad = np.flatnonzero((a != osp) | (b != oep))
+            assert bad.size == 0, (name, table_k, two_step, bad[:5], [pats[i] for i in bad[:3]])
+            assert (c2 == osp).all() and (d2 == oep).all()
+            a, b = fused.find_batch(chars, offsets)                  # the kernel variant without statistics
+            assert (a == osp).all() and (b == oep).all()
+            assert st["lf_steps"] == st0["lf_steps"] and st["table_hits"] == st0["table_hits"]
+            if table_k >= 8:                                         # 8-mers of a 300 kbp text are mostly unique: jumps get fused
+                assert st["sector_probes"] < st0["sector_probes"], (name, table_k, st, st0)
+            else:
+                assert st["sector_probes"] <= st0["sector_probes"]
+        assert not GCSA(flat, kmer_table_k=6, jump_table=False, fused_table=True).fusedTable()   # nothing to fuse with
+
+
 def test_custom_alphabet_takes_the_general_path():
     """An index whose char2comp is not the default table (digits 1-4 are the bases, lower case is N): the SWAR
     pattern packing is off, the k-mer table and the jump table are reached through the per-character path, and
