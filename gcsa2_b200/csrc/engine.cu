@@ -26,6 +26,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -2254,18 +2255,43 @@ int gcsa_b200_find_fixed_batch(const gcsa_b200_index* index, const uint8_t* d_ch
   Host-buffer find: the batch is cut into chunks that are pipelined over three streams
   (H2D of chunk i+1 overlaps the kernel of chunk i and the D2H of chunk i-1).
 */
-// Host threads for 2-bit packing in the host entry point of find(); 0 = do not pack (the default).
-// GCSA_B200_HOST_PACK=N packs with N OpenMP threads.  Opt-in because it only pays with many fast host
-// cores: measured on a 16-vCPU B200 box (10 M 32-mers per call) 7.16 ms without packing, 16.0 / 8.7 /
-// 8.0 / 6.5 ms with 4 / 8 / 12 / 16 threads -- PCIe already moves the raw bytes almost as fast as the
-// host can pack them.
-static int hostPackThreads()
+// Host-side 2-bit packing in the host entry point of find() (pack.cpp): 4x fewer bytes over PCIe, which is what
+// bounds that entry point -- but only a gain when the host packs faster than the link moves the raw bytes
+// (measured on a 16-vCPU B200 box with the first packer: break-even at 16 threads).  Policy:
+//   GCSA_B200_HOST_PACK=0     never;   =N (> 0)  always, with N OpenMP threads;
+//   unset or "auto"           decided by measurement: the first large batch is packed with all OpenMP threads
+//                             (GCSA_B200_HOST_PACK_THREADS overrides the count) while the packing rate of its first
+//                             two chunks is timed; packing stays on iff the better of the two reaches
+//                             GCSA_B200_HOST_PACK_MIN_GBS (default 55 GB/s of pattern bytes: the ~50 GB/s the link
+//                             sustains plus a margin).  The decision is kept for the process.
+enum { PACK_UNKNOWN = -1, PACK_OFF = 0, PACK_ON = 1 };
+static std::atomic<int> g_pack_auto(PACK_UNKNOWN);
+struct PackPolicy { int threads; bool calibrate; };
+
+static PackPolicy hostPackPolicy()
 {
   const char* e = std::getenv("GCSA_B200_HOST_PACK");
-  if(e == nullptr || *e == 0) { return 0; }
-  int v = std::atoi(e);
-  return (v < 0 ? 0 : v);
+  if(e != nullptr && *e != 0 && std::strcmp(e, "auto") != 0)
+  {
+    int v = std::atoi(e);
+    return PackPolicy{ (v < 0 ? 0 : v), false };
+  }
+  int state = g_pack_auto.load();
+  if(state == PACK_OFF) { return PackPolicy{ 0, false }; }
+  const char* t = std::getenv("GCSA_B200_HOST_PACK_THREADS");
+  int threads = (t != nullptr && *t != 0 ? std::atoi(t) : omp_get_max_threads());
+  return PackPolicy{ std::max(1, threads), state == PACK_UNKNOWN };
 }
+
+static double hostPackMinRate()
+{
+  const char* e = std::getenv("GCSA_B200_HOST_PACK_MIN_GBS");
+  return (e != nullptr && *e != 0 ? std::atof(e) : 55.0) * 1e9;
+}
+
+// Test / measurement hooks (not part of the C ABI): forget the automatic decision; report it.
+extern "C" void gcsa_b200_internal_pack_reset(void) { g_pack_auto.store(PACK_UNKNOWN); }
+extern "C" int gcsa_b200_internal_pack_state(void) { return g_pack_auto.load(); }
 
 static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const uint64_t* offsets, uint64_t fixed_length,
                     uint64_t n, uint64_t* sp, uint64_t* ep, gcsa_b200_find_stats* stats)
@@ -2285,8 +2311,12 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
   // other than ACGT/acgt goes through the byte path.  Finer chunks then, so that packing chunk i+1
   // overlaps the transfers of chunk i.
   const int STREAMS = 3;
-  const int pack_threads = hostPackThreads();
-  const bool pack = (pack_threads > 0 && fixed_length > 0 && offsets == nullptr && stats == nullptr && n >= (1u << 16));
+  const PackPolicy policy = hostPackPolicy();
+  const int pack_threads = policy.threads;
+  const bool pack = (pack_threads > 0 && fixed_length > 0 && offsets == nullptr && stats == nullptr &&
+                     n >= (policy.calibrate ? (1u << 20) : (1u << 16)));
+  bool calibrating = (pack && policy.calibrate);
+  double best_rate = 0.0; int timed_chunks = 0;
   const u64 CHUNK = (pack ? std::max<u64>(1ull << 18, (n + 15) / 16) : std::max<u64>(1ull << 20, (n + 7) / 8));
   const u64 words_per_pattern = (fixed_length + 31) / 32;
   cudaStream_t streams[STREAMS];
@@ -2317,8 +2347,21 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
     if(use_pack)
     {
       if(c >= (u64)STREAMS) { cudaEventSynchronize(staged[slot]); }          // the slot's previous copy has left the buffer
+      double t0 = (calibrating ? omp_get_wtime() : 0.0);
       packed = (gcsa_b200_internal_pack_patterns(chars + c0, m, fixed_length, index->pack_code, index->pack_default ? 1 : 0,
                                                  staging[slot], pack_threads) != 0);
+      if(calibrating && packed && m == CHUNK)
+      {
+        double secs = omp_get_wtime() - t0;
+        if(secs > 0.0) { best_rate = std::max(best_rate, (double)bytes / secs); }
+        if(++timed_chunks == 2)
+        {
+          calibrating = false;
+          bool keep = (best_rate >= hostPackMinRate());
+          g_pack_auto.store(keep ? PACK_ON : PACK_OFF);
+          if(!keep) { use_pack = false; }                                      // the rest of this batch goes as raw bytes
+        }
+      }
     }
     if(packed) { bytes = m * words_per_pattern * sizeof(u64); }
     u8* d_chars = nullptr; u64* d_off = nullptr; u64* d_res = nullptr;

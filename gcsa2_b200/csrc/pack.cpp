@@ -42,38 +42,58 @@ inline bool packScalar(const uint8_t* p, u64 length, const uint8_t* code, u64* o
 
 #if defined(__x86_64__)
 // 32 characters of the default alphabet (A, C, G, T in either case) -> one word.
-__attribute__((target("avx2")))
-inline bool pack32(const uint8_t* p, u64* out)
+// Codes: bits 1-2 of the byte are A 0, C 1, T 2, G 3; pext gathers them (16 bits per 8 characters) and the xor
+// with the own high bit swaps G and T: comp - 1.  Validity: a nibble lookup (low nibble of the upper-cased byte
+// -> the high nibble it must have), accumulated by the caller; one movemask per block instead of one per pattern.
+__attribute__((target("avx2,bmi2")))
+inline void pack32(const uint8_t* p, u64* out, __m256i& all_valid)
 {
   const __m256i v = _mm256_loadu_si256((const __m256i*)p);
   const __m256i x = _mm256_and_si256(v, _mm256_set1_epi8((char)0xDF));
-  const __m256i valid = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(x, _mm256_set1_epi8('A')), _mm256_cmpeq_epi8(x, _mm256_set1_epi8('C'))),
-                                        _mm256_or_si256(_mm256_cmpeq_epi8(x, _mm256_set1_epi8('G')), _mm256_cmpeq_epi8(x, _mm256_set1_epi8('T'))));
-  // (c >> 1) & 3 = A 0, C 1, T 2, G 3; xor with its own high bit swaps G and T: comp - 1
-  const __m256i t = _mm256_and_si256(_mm256_srli_epi16(v, 1), _mm256_set1_epi8(3));
-  const __m256i code = _mm256_xor_si256(t, _mm256_and_si256(_mm256_srli_epi16(t, 1), _mm256_set1_epi8(1)));
-  const __m256i p16 = _mm256_maddubs_epi16(code, _mm256_set1_epi16(0x0401));          // 2 characters -> 4 bits
-  const __m256i p32 = _mm256_madd_epi16(p16, _mm256_set1_epi32(0x00100001));          // 4 characters -> 8 bits
-  const __m256i gather = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
-                                          0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
-  const __m256i bytes = _mm256_shuffle_epi8(p32, gather);
-  *out = (u64)(uint32_t)_mm256_extract_epi32(bytes, 0) | ((u64)(uint32_t)_mm256_extract_epi32(bytes, 4) << 32);
-  return (uint32_t)_mm256_movemask_epi8(valid) == 0xFFFFFFFFu;
+  const __m256i lut = _mm256_setr_epi8(-1, 4, -1, 4, 5, -1, -1, 4, -1, -1, -1, -1, -1, -1, -1, -1,
+                                       -1, 4, -1, 4, 5, -1, -1, 4, -1, -1, -1, -1, -1, -1, -1, -1);
+  const __m256i want = _mm256_shuffle_epi8(lut, _mm256_and_si256(x, _mm256_set1_epi8(0x0F)));
+  const __m256i high = _mm256_and_si256(_mm256_srli_epi16(x, 4), _mm256_set1_epi8(0x0F));
+  all_valid = _mm256_and_si256(all_valid, _mm256_cmpeq_epi8(want, high));
+  // plain 8-byte loads for the scalar side (the laundered pointer keeps the compiler from carving them out of the
+  // vector register, which costs more port-5 work than the loads do)
+  const uint8_t* p2 = p;
+  asm("" : "+r"(p2));
+  u64 w[4];
+  std::memcpy(w, p2, 32);
+  const u64 M = 0x0606060606060606ull;
+  u64 t = _pext_u64(w[0], M) | (_pext_u64(w[1], M) << 16) | (_pext_u64(w[2], M) << 32) | (_pext_u64(w[3], M) << 48);
+  *out = t ^ ((t >> 1) & 0x5555555555555555ull);
 }
 
-__attribute__((target("avx2")))
+__attribute__((target("avx2,bmi2")))
 bool packRangeAvx2(const uint8_t* chars, u64 first, u64 last, u64 length, const uint8_t* code, u64* out)
 {
   const u64 words = (length + 31) / 32, full = length / 32;
   bool ok = true;
-  for(u64 q = first; q < last; q++)
+  __m256i all_valid = _mm256_set1_epi8(-1);
+  if(length == 32)
   {
-    const uint8_t* p = chars + q * length;
-    u64* o = out + q * words;
-    for(u64 w = 0; w < full; w++) { ok &= pack32(p + 32 * w, o + w); }
-    if(full < words) { ok &= packScalar(p + 32 * full, length - 32 * full, code, o + full); }
+    for(u64 q = first; q < last; q++)
+    {
+      _mm_prefetch((const char*)(chars + 32 * q + 1024), _MM_HINT_NTA);
+      u64 w;
+      pack32(chars + 32 * q, &w, all_valid);
+      _mm_stream_si64((long long*)(out + q), (long long)w);      // the staging buffer is read next by the DMA engine, not by this core
+    }
   }
-  return ok;
+  else
+  {
+    for(u64 q = first; q < last; q++)
+    {
+      const uint8_t* p = chars + q * length;
+      u64* o = out + q * words;
+      for(u64 w = 0; w < full; w++) { pack32(p + 32 * w, o + w, all_valid); }
+      if(full < words) { ok &= packScalar(p + 32 * full, length - 32 * full, code, o + full); }
+    }
+  }
+  _mm_sfence();
+  return ok && ((uint32_t)_mm256_movemask_epi8(all_valid) == 0xFFFFFFFFu);
 }
 #endif
 
@@ -93,7 +113,7 @@ extern "C" int gcsa_b200_internal_pack_patterns(const uint8_t* chars, uint64_t n
   if(threads < 1) { threads = 1; }
   bool simd = false;
 #if defined(__x86_64__)
-  simd = (default_alphabet != 0) && __builtin_cpu_supports("avx2");
+  simd = (default_alphabet != 0) && __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2");
 #endif
   const u64 BLOCK = 8192;
   const u64 blocks = (n + BLOCK - 1) / BLOCK;

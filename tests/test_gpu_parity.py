@@ -331,6 +331,41 @@ def test_host_packed_find_equals_byte_path(monkeypatch):
                     assert (int(psp[i]), int(pep[i])) == ora.find(pat)
 
 
+def test_host_pack_automatic_policy(monkeypatch):
+    """Without GCSA_B200_HOST_PACK (or with "auto") the host entry point times the packing of the first two chunks of
+    the first large batch and keeps packing only if the host is fast enough; the decision is remembered.  Both
+    outcomes (forced through the threshold) give the byte path's answers, also for the batch that was switched
+    half-way."""
+    from gcsa2_b200 import capi
+    L = capi.lib()
+    seq = synth.random_sequence(200_000, seed=43)
+    flat, _, _ = build_index(synth.linear_graph(seq), 16, 3)
+    gpu = GCSA(flat, kmer_table_k=8)
+    n, length = 1_200_000, 32
+    chars, offsets = synth.patterns_from_sequence(seq, n, length, seed=5)
+    chars = chars.copy()
+    rnd, _ = synth.random_patterns(n // 8, length, seed=6)
+    chars[: rnd.size] = rnd
+    monkeypatch.setenv("GCSA_B200_HOST_PACK", "0")
+    bsp, bep = gpu.find_fixed_batch(chars, length)
+    monkeypatch.setenv("GCSA_B200_HOST_PACK_THREADS", "2")
+    for setting, threshold, expected in (("auto", "0", 1), (None, "1000000", 0)):
+        if setting is None:
+            monkeypatch.delenv("GCSA_B200_HOST_PACK")
+        else:
+            monkeypatch.setenv("GCSA_B200_HOST_PACK", setting)
+        monkeypatch.setenv("GCSA_B200_HOST_PACK_MIN_GBS", threshold)
+        L.gcsa_b200_internal_pack_reset()
+        assert L.gcsa_b200_internal_pack_state() == -1
+        for _ in range(2):                                            # the deciding call, then one under the decision
+            sp, ep = gpu.find_fixed_batch(chars, length)
+            assert (sp == bsp).all() and (ep == bep).all(), (setting, threshold)
+            assert L.gcsa_b200_internal_pack_state() == expected
+    small = gpu.find_fixed_batch(chars[: 1000 * length], length)      # too small to decide anything
+    assert (small[0] == bsp[:1000]).all()
+    L.gcsa_b200_internal_pack_reset()
+
+
 def test_locate_tables_agree():
     """locate() through the locate table (one load per node), the walk table (one load per LF step) and the
     bit vectors alone: identical CSR output, equal to the oracle -- short patterns (wide ranges, many nodes per
