@@ -1118,6 +1118,146 @@ locate_segments_kernel(const u64* __restrict__ node_off, const u64* __restrict__
   }
 }
 
+/*
+  Short ranges through the locate table, without the general pipeline: a range of at most LOC_SMALL path nodes
+  whose table entries all hold their start position directly (the usual case: a k-mer that occurs a few times)
+  is gathered, sorted and deduplicated in registers by one thread -- locate(range) of src/gcsa.cpp:827-842 with
+  removeDuplicates (utils.h:350-357) on up to eight values.  Pass 1 counts (and keeps the value of single-valued
+  ranges), an exclusive scan gives the CSR offsets, pass 2 writes.  Every other range (longer, or with a node whose
+  sampled ancestor stores several positions) is appended to a list and goes through the general pipeline below.
+*/
+#define LOC_SMALL 8
+#define LOC_TOP (1ull << 63)
+
+// start positions of the nodes [s, s + len), len <= LOC_SMALL, padded with ~0; false if an entry is not direct
+__device__ __forceinline__ bool locate_small_values(const DevView& v, u64 s, u32 len, u64 (&a)[LOC_SMALL])
+{
+  bool direct = true;
+  #pragma unroll
+  for(u32 j = 0; j < LOC_SMALL; j++)
+  {
+    u64 e = (j < len ? __ldg(v.loc64 + s + j) : ~0ull);
+    direct = direct && ((e >> 63) != 0);
+    a[j] = (j < len ? (e & ~LOC_TOP) : ~0ull);
+  }
+  return direct;
+}
+
+// odd-even transposition network over LOC_SMALL registers (the padding sorts to the end)
+__device__ __forceinline__ void locate_small_sort(u64 (&a)[LOC_SMALL])
+{
+  #pragma unroll
+  for(int r = 0; r < LOC_SMALL; r++)
+  {
+    #pragma unroll
+    for(int j = (r & 1); j + 1 < LOC_SMALL; j += 2)
+    {
+      u64 x = a[j], y = a[j + 1];
+      a[j] = (x < y ? x : y); a[j + 1] = (x < y ? y : x);
+    }
+  }
+}
+
+// Pass 1.  cnt[i] = number of distinct positions of range i (0 for the general ranges, which are appended to
+// glist); stash[i] = the position itself when there is exactly one, LOC_TOP | list slot for a general range.
+__global__ void __launch_bounds__(256)
+locate_small_count_kernel(const DevView v, const u64* __restrict__ sp, const u64* __restrict__ ep, u64 n,
+                          u64* __restrict__ cnt, u64* __restrict__ stash, u64* __restrict__ glist, ull* __restrict__ n_general)
+{
+  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+  {
+    u64 s = sp[i], e = ep[i];
+    u64 c = 0, keep = 0;
+    bool general = false;
+    if(!(range_empty(s, e) || e >= v.path_nodes))                    // gcsa.cpp:831
+    {
+      u64 len = e + 1 - s;
+      if(len == 1)
+      {
+        u64 x = __ldg(v.loc64 + s);
+        if(x >> 63) { c = 1; keep = x & ~LOC_TOP; } else { general = true; }
+      }
+      else if(len <= LOC_SMALL)
+      {
+        u64 a[LOC_SMALL];
+        if(locate_small_values(v, s, (u32)len, a))
+        {
+          locate_small_sort(a);
+          c = 1;
+          #pragma unroll
+          for(u32 j = 1; j < LOC_SMALL; j++) { c += ((j < len && a[j] != a[j - 1]) ? 1 : 0); }
+          keep = a[0];
+        }
+        else { general = true; }
+      }
+      else { general = true; }
+    }
+    if(general)
+    {
+      u64 slot = atomicAdd(n_general, 1ull);
+      glist[slot] = i;
+      keep = LOC_TOP | slot;
+    }
+    cnt[i] = c; stash[i] = keep;
+  }
+}
+
+// the general ranges, in list order
+__global__ void __launch_bounds__(256)
+locate_general_gather_kernel(const u64* __restrict__ sp, const u64* __restrict__ ep, const u64* __restrict__ glist, u64 m,
+                             u64* __restrict__ gsp, u64* __restrict__ gep)
+{
+  for(u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += (u64)gridDim.x * blockDim.x)
+  {
+    u64 i = glist[k];
+    gsp[k] = sp[i]; gep[k] = ep[i];
+  }
+}
+
+// their counts, once the general pipeline has answered
+__global__ void __launch_bounds__(256)
+locate_general_counts_kernel(const u64* __restrict__ glist, const u64* __restrict__ goffs, u64 m, u64* __restrict__ cnt)
+{
+  for(u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += (u64)gridDim.x * blockDim.x)
+  {
+    cnt[glist[k]] = goffs[k + 1] - goffs[k];
+  }
+}
+
+// Pass 2: values[off[i], off[i + 1]) of every range.
+__global__ void __launch_bounds__(256)
+locate_small_fill_kernel(const DevView v, const u64* __restrict__ sp, const u64* __restrict__ ep, u64 n,
+                         const u64* __restrict__ off, const u64* __restrict__ stash,
+                         const u64* __restrict__ goffs, const u64* __restrict__ gvals, u64* __restrict__ values)
+{
+  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+  {
+    u64 o = off[i], c = off[i + 1] - o;
+    if(c == 0) { continue; }
+    u64 keep = stash[i];
+    if(keep >> 63)
+    {
+      u64 g = goffs[keep & ~LOC_TOP];
+      for(u64 j = 0; j < c; j++) { values[o + j] = gvals[g + j]; }
+    }
+    else if(c == 1) { values[o] = keep; }
+    else
+    {
+      u64 s = sp[i], len = ep[i] + 1 - s;
+      u64 a[LOC_SMALL];
+      locate_small_values(v, s, (u32)len, a);
+      locate_small_sort(a);
+      values[o] = a[0];
+      u64 w = 1;
+      #pragma unroll
+      for(u32 j = 1; j < LOC_SMALL; j++)
+      {
+        if(j < len && a[j] != a[j - 1]) { values[o + w] = a[j]; w++; }
+      }
+    }
+  }
+}
+
 // removeDuplicates (utils.h:350-357) after the segmented sort: flag the first copy of each value
 __global__ void __launch_bounds__(256)
 locate_flag_kernel(const u64* __restrict__ sorted, const u64* __restrict__ seg, u64 n, u64 total, u64* __restrict__ flag)
@@ -2583,9 +2723,9 @@ template<class T> int scanExclusive(const T* in, T* out, u64 count, cudaStream_t
   null or capacity is too small, only the sizes are computed and *needed is set.
   Temporaries are stream-ordered allocations.
 */
-int locateDevice(const gcsa_b200_index* index, const u64* d_sp, const u64* d_ep, u64 n,
-                 u64* d_out_offsets, u64* d_values, u64 capacity, u64* needed, cudaStream_t st,
-                 u64** d_values_alloc = nullptr, bool sorted_unique = true)
+int locateGeneral(const gcsa_b200_index* index, const u64* d_sp, const u64* d_ep, u64 n,
+                  u64* d_out_offsets, u64* d_values, u64 capacity, u64* needed, cudaStream_t st,
+                  u64** d_values_alloc = nullptr, bool sorted_unique = true)
 {
   const DevView& v = index->view;
   const int sm = index->sm_count;
@@ -2678,6 +2818,72 @@ int locateDevice(const gcsa_b200_index* index, const u64* d_sp, const u64* d_ep,
   }
   if(d_values == nullptr || capacity < distinct) { rc = GCSA_B200_ERR_CAPACITY; g_last_error = "locate: output capacity too small"; }
   else { locate_compact_kernel<<<gridFor(total, sm), 256, 0, st>>>(sorted, flag, flag_scan, total, d_values, capacity); }
+  LOC_TRY(cudaGetLastError());
+  cleanup();
+  return rc;
+}
+
+/*
+  locate() of a batch of ranges as a CSR of sorted distinct positions.  With the locate table, short ranges are
+  answered by the two register passes above (one thread per range) and only the others go through the general
+  pipeline; without the table, for sort = false, or with GCSA_B200_LOCATE_SMALL=0 everything does.
+*/
+int locateDevice(const gcsa_b200_index* index, const u64* d_sp, const u64* d_ep, u64 n,
+                 u64* d_out_offsets, u64* d_values, u64 capacity, u64* needed, cudaStream_t st,
+                 u64** d_values_alloc = nullptr, bool sorted_unique = true)
+{
+  const DevView& v = index->view;
+  const char* small_env = std::getenv("GCSA_B200_LOCATE_SMALL");
+  const bool small_path = (small_env == nullptr || std::atoi(small_env) != 0);
+  if(!sorted_unique || v.loc64 == nullptr || !small_path || n == 0)
+  {
+    return locateGeneral(index, d_sp, d_ep, n, d_out_offsets, d_values, capacity, needed, st, d_values_alloc, sorted_unique);
+  }
+  const int sm = index->sm_count;
+  std::vector<void*> tmp;
+  u64* gvals = nullptr;
+  auto alloc = [&](u64 bytes) -> void* { void* p = nullptr; if(cudaMallocAsync(&p, std::max<u64>(bytes, 16), st) != cudaSuccess) { return nullptr; } tmp.push_back(p); return p; };
+  auto cleanup = [&]() { for(void* p : tmp) { cudaFreeAsync(p, st); } tmp.clear(); if(gvals) { cudaFreeAsync(gvals, st); gvals = nullptr; } };
+
+  u64* cnt = (u64*)alloc((n + 1) * sizeof(u64));
+  u64* stash = (u64*)alloc(n * sizeof(u64));
+  u64* glist = (u64*)alloc(n * sizeof(u64));
+  ull* d_general = (ull*)alloc(sizeof(ull));
+  if(!cnt || !stash || !glist || !d_general) { cleanup(); return fail(GCSA_B200_ERR_NOMEM, "locate: out of device memory"); }
+  LOC_TRY(cudaMemsetAsync(cnt + n, 0, sizeof(u64), st));
+  LOC_TRY(cudaMemsetAsync(d_general, 0, sizeof(ull), st));
+  locate_small_count_kernel<<<gridFor(n, sm), 256, 0, st>>>(v, d_sp, d_ep, n, cnt, stash, glist, d_general);
+  ull n_general = 0;
+  LOC_TRY(cudaMemcpyAsync(&n_general, d_general, sizeof(ull), cudaMemcpyDeviceToHost, st));
+  LOC_TRY(cudaStreamSynchronize(st));
+  if(std::getenv("GCSA_B200_LOCATE_DEBUG") != nullptr) { std::fprintf(stderr, "locate: %llu of %llu ranges through the general pipeline\n", n_general, (ull)n); }
+
+  u64* goffs = nullptr;
+  if(n_general > 0)
+  {
+    u64* gsp = (u64*)alloc(n_general * sizeof(u64));
+    u64* gep = (u64*)alloc(n_general * sizeof(u64));
+    goffs = (u64*)alloc((n_general + 1) * sizeof(u64));
+    if(!gsp || !gep || !goffs) { cleanup(); return fail(GCSA_B200_ERR_NOMEM, "locate: out of device memory"); }
+    locate_general_gather_kernel<<<gridFor(n_general, sm), 256, 0, st>>>(d_sp, d_ep, glist, n_general, gsp, gep);
+    u64 gneeded = 0;
+    LOC_RC(locateGeneral(index, gsp, gep, n_general, goffs, nullptr, 0, &gneeded, st, &gvals, true));
+    locate_general_counts_kernel<<<gridFor(n_general, sm), 256, 0, st>>>(glist, goffs, n_general, cnt);
+  }
+  LOC_RC(scanExclusive(cnt, d_out_offsets, n + 1, st));
+  u64 distinct = 0;
+  LOC_TRY(cudaMemcpyAsync(&distinct, d_out_offsets + n, sizeof(u64), cudaMemcpyDeviceToHost, st));
+  LOC_TRY(cudaStreamSynchronize(st));
+  if(needed) { *needed = distinct; }
+  int rc = 0;
+  if(d_values_alloc != nullptr)
+  {
+    void* p = nullptr;
+    LOC_TRY(cudaMallocAsync(&p, std::max<u64>(distinct, 1) * sizeof(u64), st));
+    *d_values_alloc = (u64*)p; d_values = (u64*)p; capacity = distinct;
+  }
+  if(d_values == nullptr || capacity < distinct) { rc = GCSA_B200_ERR_CAPACITY; g_last_error = "locate: output capacity too small"; }
+  else if(distinct > 0) { locate_small_fill_kernel<<<gridFor(n, sm), 256, 0, st>>>(v, d_sp, d_ep, n, d_out_offsets, stash, goffs, gvals, d_values); }
   LOC_TRY(cudaGetLastError());
   cleanup();
   #undef LOC_TRY

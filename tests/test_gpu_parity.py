@@ -401,6 +401,58 @@ def test_locate_tables_agree():
         assert (roffs == results[0][0]).all() and (rvals == results[0][1]).all()
 
 
+def test_locate_short_range_path(monkeypatch):
+    """locate() of short ranges in registers (one thread per range, locate table) == the general pipeline == the oracle:
+    every range length around the register limit (8 nodes), duplicates inside a range (a repeat), nodes with several
+    start positions (they send the range to the general pipeline), empty and out-of-range ranges mixed in, all-general
+    and all-short batches, and the capacity protocol of the device entry point."""
+    import torch
+    from helpers import current_stream, device_empty, device_sync, to_device
+    from gcsa2_b200 import capi
+    seq = synth.random_sequence(120_000, seed=19)
+    seq[7000:7600] = seq[2000:2600]                                   # a repeat: nodes with two start positions
+    seq[9000:9300] = seq[2100:2400]
+    graph, sites, alt = synth.snp_graph(seq, seed=19, snp_rate=0.02)
+    flat, _, _ = build_index(graph, 16, 2)
+    ora = orc.OracleGCSA(flat)
+    N = flat.path_nodes
+    rng = np.random.default_rng(19)
+    a = rng.integers(0, N, size=60_000).astype(np.uint64)
+    ln = rng.integers(1, 13, size=a.size).astype(np.uint64)           # 1..12 nodes: both sides of the limit
+    ln[: 30_000] = 1
+    b = np.minimum(a + ln - np.uint64(1), np.uint64(N - 1))
+    sp = np.concatenate([a, np.array([5, 0, N - 3, 0, 7], dtype=np.uint64)])
+    ep = np.concatenate([b, np.array([4, M64, N + 2, N - 1, 7], dtype=np.uint64)])   # empty, empty, out of range, everything, one node
+    order = rng.permutation(sp.size)
+    sp, ep = sp[order], ep[order]
+    ooffs, ovals, _ = ora.locate_batch(sp, ep, threads=4)
+    gpu = GCSA(flat, walk_table=1)
+    for subset in (slice(None), np.flatnonzero(ep - sp < 8), np.flatnonzero((ep - sp >= 8) & (ep < N)), slice(0, 1)):
+        s2, e2 = sp[subset], ep[subset]
+        want_offs, want_vals, _ = ora.locate_batch(s2, e2, threads=4)
+        monkeypatch.setenv("GCSA_B200_LOCATE_SMALL", "1")
+        offs, vals = gpu.locate_batch(s2, e2)
+        monkeypatch.setenv("GCSA_B200_LOCATE_SMALL", "0")
+        goffs, gvals = gpu.locate_batch(s2, e2)
+        assert (offs == want_offs).all() and (vals == want_vals).all()
+        assert (goffs == want_offs).all() and (gvals == want_vals).all()
+    monkeypatch.setenv("GCSA_B200_LOCATE_SMALL", "1")
+    assert (gpu.count_batch(sp, ep)[ep < N] >= 0).all()
+    # device entry point: too small a buffer reports the size and still writes the offsets
+    n = sp.size
+    d_sp, d_ep = to_device(sp.view(np.int64)), to_device(ep.view(np.int64))
+    d_offs = device_empty(n + 1, torch.int64); small = device_empty(10, torch.int64)
+    with pytest.raises(capi.GCSAError) as err:
+        gpu.locate_device(d_sp, d_ep, n, d_offs, small, 10, current_stream())
+    assert err.value.code == capi.ERR_CAPACITY
+    device_sync()
+    assert (d_offs.cpu().numpy().view(np.uint64) == ooffs).all()
+    big = device_empty(int(ooffs[-1]), torch.int64)
+    got = gpu.locate_device(d_sp, d_ep, n, d_offs, big, int(ooffs[-1]), current_stream())
+    device_sync()
+    assert got == int(ooffs[-1]) and (big.cpu().numpy().view(np.uint64) == ovals).all()
+
+
 def test_locate_into_host_buffers():
     """gcsa_b200_locate_into_host (caller-owned buffers, chunked pipeline) == gcsa_b200_locate_host; too small a
     buffer is reported with the needed size and complete offsets."""
