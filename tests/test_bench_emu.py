@@ -1,0 +1,73 @@
+"""bench.py end to end on the host emulation of the engine (tests/emu): every leg of the bench line -- device-resident
+find, the host entry point with its automatic packing policy, the random-pattern leg, the locate leg, the CPU
+baseline and the roofline accounting -- runs at a small size without a GPU, so that a mistake in the script is found
+here and not by the one run on the box.  torch.cuda is replaced by host stand-ins for the duration of the test;
+the numbers printed are meaningless and are not looked at, the structure of the line is."""
+import ctypes
+import json
+import sys
+import time
+
+import pytest
+import torch
+
+
+class _Event:
+    def __init__(self, enable_timing=False):
+        self.t = 0.0
+
+    def record(self, stream=None):
+        self.t = time.perf_counter()
+
+    def elapsed_time(self, other):
+        return max(1e-3, 1000.0 * (other.t - self.t))
+
+
+class _Stream:
+    cuda_stream = 0
+
+
+def test_bench_line_on_the_emulated_engine(monkeypatch, capsys):
+    import bench
+    from emu import build_emu
+    from gcsa2_b200 import capi
+    emulated = capi._bind(ctypes.CDLL(build_emu.build()))
+    monkeypatch.setattr(capi, "_lib", emulated)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a: _Stream())
+    monkeypatch.setattr(torch.cuda, "Event", _Event)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self.clone())
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    real_empty, real_tensor = torch.empty, torch.tensor
+    monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{x: y for x, y in k.items() if x != "device"}))
+    monkeypatch.setattr(torch, "tensor", lambda *a, **k: real_tensor(*a, **{x: y for x, y in k.items() if x != "device"}))
+    monkeypatch.setenv("GCSA_B200_HOST_PACK_THREADS", "2")
+    monkeypatch.setenv("GCSA_B200_HOST_PACK_MIN_GBS", "0")            # the packing branch of the host entry point
+    monkeypatch.delenv("GCSA_B200_HOST_PACK", raising=False)
+    emulated.gcsa_b200_internal_pack_reset()
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "2", "--warmup", "1", "--ref-mbp", "0.2", "--queries", "1100000",
+                                      "--kmer-table-k", "8", "--locate-mbp", "0.2", "--locate-queries", "40000", "--cpu-sample", "20000"])
+    try:
+        bench.main()
+    finally:
+        emulated.gcsa_b200_internal_pack_reset()
+    out = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
+    assert len(out) == 1
+    line = json.loads(out[0])
+    with open(build_emu.OUT + "/bench_line.json", "w") as f:         # for a look at the whole line (git-ignored)
+        json.dump(line, f, indent=1)
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks", "locate", "secondary"):
+        assert key in line, key
+    assert line["found"] == line["queries"] == 1_100_000
+    assert line["config"]["index"]["fused_table"] is True
+    assert line["e2e"]["matches_device_leg"] and line["e2e"]["host_pack"]["in_effect"] and line["e2e"]["h2d_bytes_per_step"] == 8 * 1_100_000
+    assert line["cpu_baseline"]["parity_on_sample"] and line["cpu_baseline"]["kind"] in ("reference", "port")
+    assert line["secondary"]["parity_on_sample"] and line["secondary"]["found"] < 1_100_000 // 2
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in line["roofline"], key
+    loc = line["locate"]
+    assert "error" not in loc, loc
+    assert loc["positions"] >= 40_000 and loc["e2e"]["matches_device_leg"] and loc["cpu_baseline"]["parity_on_sample"]
