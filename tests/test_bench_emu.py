@@ -71,3 +71,13 @@ def test_bench_line_on_the_emulated_engine(monkeypatch, capsys):
     loc = line["locate"]
     assert "error" not in loc, loc
     assert loc["positions"] >= 40_000 and loc["e2e"]["matches_device_leg"] and loc["cpu_baseline"]["parity_on_sample"]
+
+
+def test_smoke_on_the_emulated_engine(monkeypatch, capsys):
+    """__graft_entry__.smoke() -- the one call the driver makes on the box before the bench -- on the emulated engine."""
+    import __graft_entry__ as entry
+    from emu import build_emu
+    from gcsa2_b200 import capi
+    monkeypatch.setattr(capi, "_lib", capi._bind(ctypes.CDLL(build_emu.build())))
+    entry.smoke()
+    assert "smoke ok" in capsys.readouterr().out
