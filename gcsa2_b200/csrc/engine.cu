@@ -1656,7 +1656,11 @@ lcp_rmq_kernel(const LcpView l, const u64* __restrict__ sp, const u64* __restric
 // MODE 0: count the matches of each pattern.  MODE 1: write them at out_offsets (exact positions known).
 // MODE 2: count AND write the first `stride` matches of pattern q at scratch slot q * stride (one pass; the
 // few patterns with more matches are redone in MODE 1 over the id list `ids`).
-template<int MODE>
+// JUMP: singleton ranges advance along the unary backward path of their node with one load (the jump tables of
+// find_kernel): the pattern is kept 2-bit packed, 32 characters at a time, and a path of up to 16 steps is one XOR
+// against it.  A path that the pattern leaves after t characters is followed by t + 1 single steps (the last of
+// which fails, as it must), so matches, depths and ranges are those of the single-step loop.
+template<int MODE, bool JUMP = false>
 __global__ void __launch_bounds__(256)
 mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const u64* __restrict__ offsets, u64 char_base,
            u64 n, u64* __restrict__ counts, const u64* __restrict__ out_offsets, u64* __restrict__ matches,
@@ -1677,6 +1681,36 @@ mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const
 
   u64 q = 0, sp = 0, ep = 0, depth = 0, pos = 0, begin = 0, emitted = 0, out_at = 0;
   bool live = false, extended = false, need_parent = false;
+  u64 tail = 0, tail_end = 0; u32 tail_n = 0, skip = 0;     // JUMP: characters [tail_end - tail_n, tail_end) packed as in find_kernel
+
+  // pack the (up to) 32 characters that end at `end_pos` (exclusive), eight at a time, stopping at a non-base
+  auto pack_tail = [&](u64 end_pos)
+  {
+    tail = 0; tail_n = 0; tail_end = end_pos;
+    for(u32 w = 0; w < 4; w++)
+    {
+      u64 pe = end_pos - 8 * w;
+      if(pe - begin < 8) { break; }
+      u64 addr = (u64)(chars + pe - 8); u32 a = (u32)(addr & 7);
+      const unsigned long long* base = (const unsigned long long*)(addr - a);
+      u64 word = __ldcs(base);
+      if(a != 0) { word = (word >> (8 * a)) | ((u64)__ldcs(base + 1) << (64 - 8 * a)); }
+      u32 good;
+      u32 r = pack8_reversed(word, &good);
+      tail |= (u64)r << (16 * w);
+      tail_n += good;
+      if(good < 8) { break; }
+    }
+  };
+  auto comp_at = [&](u64 p) -> u32
+  {
+    if(JUMP)
+    {
+      u64 off = tail_end - 1 - p;
+      if(off < (u64)tail_n) { return (u32)((tail >> (2 * off)) & 3) + 1; }
+    }
+    return c2c[chars[p]];
+  };
 
   while(true)
   {
@@ -1692,6 +1726,7 @@ mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const
           q = (ids != nullptr ? ids[cand] : cand); live = true; need_parent = false;
           begin = offsets[q] - char_base; pos = offsets[q + 1] - char_base;
           sp = 0; ep = v.path_nodes - 1; depth = 0; extended = false; emitted = 0;
+          if(JUMP) { tail = 0; tail_n = 0; tail_end = pos; skip = 0; }
           if(WRITE) { out_at = out_offsets[q]; }
           if(MODE == 2) { out_at = q * stride; }
         }
@@ -1730,8 +1765,37 @@ mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const
       live = false;
       continue;
     }
+    if(JUMP)
+    {
+      u64 left = pos - begin;
+      if(sp == ep && skip == 0 && left >= 4)
+      {
+        const u64* from = (left >= (u64)v.jump_k ? v.jump : v.jump_short);
+        u64 e = (from != nullptr ? __ldg(from + sp) : 0);
+        u32 len = (u32)(e >> 59);
+        if(len >= 2)
+        {
+          u64 off = tail_end - pos;
+          if(off + len > (u64)tail_n) { pack_tail(pos); off = 0; }
+          if(len <= tail_n)
+          {
+            u64 stored = ((e << 5) >> 5) >> v.jump_tbits;
+            u64 diff = ((tail >> (2 * off)) ^ stored) & ((1ull << (2 * len)) - 1);
+            if(diff == 0)
+            {
+              sp = ep = (e & ((1ull << v.jump_tbits) - 1));
+              depth += len; pos -= len; extended = true;
+              continue;
+            }
+            skip = ((u32)(__ffsll((long long)diff) - 1) >> 1) + 2;       // single steps up to and including the one that fails
+          }
+          else { skip = 9; }                                             // a non-base or the start of the pattern is near: eight single steps
+        }
+      }
+      if(skip > 0) { skip--; }
+    }
     u64 nsp, nep;
-    lf_range(v, sp, ep, c2c[chars[pos - 1]], nsp, nep);
+    lf_range(v, sp, ep, comp_at(pos - 1), nsp, nep);
     if(!range_empty(nsp, nep)) { sp = nsp; ep = nep; depth++; pos--; extended = true; continue; }
     if(depth == 0) { pos--; continue; }
     if(extended)
@@ -2444,8 +2508,9 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
   if(n == 0) { return 0; }
   DeviceGuard guard(index->device);
 
-  // Chunks of >= 1 M queries, at most ~8 per batch: large enough for PCIe to reach its streaming
-  // rate, enough of them for the copy engines and the SMs to overlap.
+  // Chunks of >= 256 k queries (8 MB of 32-mers: PCIe is at its streaming rate), at most ~24 per batch: the H2D
+  // engine is the busy resource from the first byte on, so what the pipeline adds to the transfer time is the kernel
+  // and the D2H of the LAST chunk -- the smaller the chunks, the smaller that tail (8 chunks: +0.45 ms on 6.4 ms).
   // With host cores to spare, fixed-length batches are 2-bit packed on the host first (pack.cpp):
   // 4x fewer bytes over PCIe, which is what bounds this entry point; a chunk containing any character
   // other than ACGT/acgt goes through the byte path.  Finer chunks then, so that packing chunk i+1
@@ -2457,7 +2522,7 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
                      n >= (policy.calibrate ? (1u << 20) : (1u << 16)));
   bool calibrating = (pack && policy.calibrate);
   double best_rate = 0.0; int timed_chunks = 0;
-  const u64 CHUNK = (pack ? std::max<u64>(1ull << 18, (n + 15) / 16) : std::max<u64>(1ull << 20, (n + 7) / 8));
+  const u64 CHUNK = (pack ? std::max<u64>(1ull << 18, (n + 15) / 16) : std::max<u64>(1ull << 18, (n + 23) / 24));
   const u64 words_per_pattern = (fixed_length + 31) / 32;
   cudaStream_t streams[STREAMS];
   for(int s = 0; s < STREAMS; s++) { CUDA_TRY(cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking)); }
@@ -3500,8 +3565,19 @@ static int memDevice(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, con
   int grid = gridFor(n, index->sm_count, 4);
   u32 parent_batch = 8;
   if(const char* e = std::getenv("GCSA_B200_MEM_PARENT_BATCH")) { parent_batch = (u32)std::max(1, std::atoi(e)); }
-  if(stride > 0) { mem_kernel<2><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, scratch, nullptr, stride, parent_batch); }
-  else { mem_kernel<0><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, nullptr, nullptr, 0, parent_batch); }
+  // GCSA_B200_MEM_JUMP=1: singleton ranges follow the jump tables (mem_kernel<.., JUMP>); off by default until measured
+  bool jump = false;
+  if(const char* e = std::getenv("GCSA_B200_MEM_JUMP")) { jump = (std::atoi(e) != 0 && index->view.jump != nullptr && index->view.default_alphabet != 0); }
+  if(stride > 0)
+  {
+    if(jump) { mem_kernel<2, true><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, scratch, nullptr, stride, parent_batch); }
+    else { mem_kernel<2><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, scratch, nullptr, stride, parent_batch); }
+  }
+  else
+  {
+    if(jump) { mem_kernel<0, true><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, nullptr, nullptr, 0, parent_batch); }
+    else { mem_kernel<0><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, nullptr, nullptr, 0, parent_batch); }
+  }
   int rc = scanExclusive(counts, (u64*)d_out_offsets, n + 1, st);
   if(rc) { cleanup(); return rc; }
   if(stride > 0) { mem_count_overflow_kernel<<<gridFor(n, index->sm_count), 256, 0, st>>>(counts, n, stride, n_overflow); }
@@ -3519,7 +3595,8 @@ static int memDevice(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, con
   if(d_matches == nullptr || capacity < total) { cleanup(); return fail(GCSA_B200_ERR_CAPACITY, "mem_batch: output capacity too small"); }
   if(stride == 0)
   {
-    mem_kernel<1><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, nullptr, (const u64*)d_out_offsets, (u64*)d_matches, nullptr, 0, parent_batch);
+    if(jump) { mem_kernel<1, true><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, nullptr, (const u64*)d_out_offsets, (u64*)d_matches, nullptr, 0, parent_batch); }
+    else { mem_kernel<1><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, nullptr, (const u64*)d_out_offsets, (u64*)d_matches, nullptr, 0, parent_batch); }
   }
   else
   {
@@ -3530,8 +3607,16 @@ static int memDevice(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, con
                                                                    (ulonglong4*)d_matches, overflow, n_overflow);
     if(overflowing > 0)
     {
-      mem_kernel<1><<<gridFor(overflowing, index->sm_count, 4), 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, overflowing,
-                                                                            nullptr, (const u64*)d_out_offsets, (u64*)d_matches, overflow, 0, parent_batch);
+      if(jump)
+      {
+        mem_kernel<1, true><<<gridFor(overflowing, index->sm_count, 4), 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, overflowing,
+                                                                                    nullptr, (const u64*)d_out_offsets, (u64*)d_matches, overflow, 0, parent_batch);
+      }
+      else
+      {
+        mem_kernel<1><<<gridFor(overflowing, index->sm_count, 4), 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, overflowing,
+                                                                              nullptr, (const u64*)d_out_offsets, (u64*)d_matches, overflow, 0, parent_batch);
+      }
     }
   }
   MEM_TRY(cudaGetLastError());

@@ -44,15 +44,16 @@ def test_mem_scan_definition_properties():
 
 
 @pytest.mark.engine
-def test_mem_scan_device_matches_definition():
+def test_mem_scan_device_matches_definition(monkeypatch):
     from gcsa2_b200 import GCSA, LCPArray, mem_batch
     flat, flcp, chars, offsets = make(30_000, L=200_000, seed=3)
     index, lcp = orc.OracleGCSA(flat), orc.OracleLCP(flcp)
     ooffs, ovals, _ = orc.mem_batch(index, lcp, chars, offsets, threads=8)
-    for two_step in (False, True):
+    for two_step, jump in ((False, "0"), (True, "0"), (False, "1")):
+        monkeypatch.setenv("GCSA_B200_MEM_JUMP", jump)               # "1": singleton ranges follow the jump tables
         gpu, glcp = GCSA(flat, kmer_table_k=6, two_step=two_step), LCPArray(flcp)
         offs, vals = mem_batch(gpu, glcp, chars, offsets)
-        assert (offs == ooffs).all() and vals.shape == ovals.shape and (vals == ovals).all()
+        assert (offs == ooffs).all() and vals.shape == ovals.shape and (vals == ovals).all(), (two_step, jump)
     c, o = orc.pack_patterns([b"", b"ACGT", b"NNNN", b"$", bytes(chars[:300])])
     offs, vals = mem_batch(gpu, glcp, c, o)
     eoffs, evals, _ = orc.mem_batch(index, lcp, c, o)
@@ -78,11 +79,13 @@ def test_mem_scan_scratch_paths(monkeypatch):
     counts = np.diff(ooffs.astype(np.int64))
     assert (counts > 16).sum() > 100 and (counts <= 4).sum() > 100
     gpu, glcp = GCSA(flat, kmer_table_k=0), LCPArray(flcp)
-    for stride in ("16", "4", "1", "0"):
+    for stride, jump in (("16", "0"), ("4", "0"), ("1", "0"), ("0", "0"), ("4", "1"), ("0", "1")):
         monkeypatch.setenv("GCSA_B200_MEM_STRIDE", stride)
+        monkeypatch.setenv("GCSA_B200_MEM_JUMP", jump)
         offs, vals = mem_batch(gpu, glcp, chars, offsets)
-        assert (offs == ooffs).all() and vals.shape == ovals.shape and (vals == ovals).all(), stride
+        assert (offs == ooffs).all() and vals.shape == ovals.shape and (vals == ovals).all(), (stride, jump)
     monkeypatch.delenv("GCSA_B200_MEM_STRIDE")
+    monkeypatch.delenv("GCSA_B200_MEM_JUMP")
     # device entry point with a caller buffer: too small -> the needed size, then the same answer
     from gcsa2_b200 import capi
     n = len(offsets) - 1
