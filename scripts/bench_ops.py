@@ -144,14 +144,17 @@ def main():
       got = [0]
       def do_mem():
           got[0] = mem_device(index, lcp, d_mchars, d_moff, nm, d_moffs_out, d_matches, cap, stream.cuda_stream)
-      ms = timed(do_mem, steps=3)
-      moffs = d_moffs_out.cpu().numpy().view(np.uint64); mvals = d_matches[:got[0]].cpu().numpy().view(np.uint64)
       mm = min(nm, 400_000)
       eoffs, evals, secs = orc.mem_batch(ora, olcp, mchars[:int(moffsets[mm])], moffsets[:mm + 1], threads=threads)
       k = int(eoffs[mm])
-      report("MEM-style scan (LF + parent), lengths 16..256", "patterns/s", nm, ms, mm / secs, mm,
-             (moffs[:mm + 1] == eoffs).all() and (mvals[:k] == evals).all(),
-             {"matches": got[0], "pattern_bytes": int(moffsets[-1])})
+      for jump in ("0", "1"):                                        # mem_kernel<.., JUMP>: singleton ranges follow the jump tables
+          os.environ["GCSA_B200_MEM_JUMP"] = jump
+          ms = timed(do_mem, steps=3)
+          moffs = d_moffs_out.cpu().numpy().view(np.uint64); mvals = d_matches[:got[0]].cpu().numpy().view(np.uint64)
+          report("MEM-style scan (LF + parent), lengths 16..256, GCSA_B200_MEM_JUMP=" + jump, "patterns/s", nm, ms, mm / secs, mm,
+                 (moffs[:mm + 1] == eoffs).all() and (mvals[:k] == evals).all(),
+                 {"matches": got[0], "pattern_bytes": int(moffsets[-1])})
+      os.environ.pop("GCSA_B200_MEM_JUMP", None)
 
     # ---- countKMers ----
     for k in ((12, 16) if "kmers" in ops else ()):
