@@ -185,6 +185,7 @@ emu_switch:
 struct Warp
 {
   unsigned gen = 0, arrived = 0, alive = 0;
+  int site = 0;                        // source line of the collective the current generation is gathering at
   unsigned pred_bits[2] = {0, 0};
   unsigned long long vals[2][32];
 };
@@ -294,7 +295,7 @@ template<class F> void launch(const Cfg& cfg, const F& f, bool collectives)
 // One warp-wide exchange: every live lane of the warp deposits (pred, value) and gets the generation's
 // buffers back once all live lanes have arrived.
 struct Exchange { unsigned ballot; const unsigned long long* vals; };
-inline Exchange warpExchange(unsigned mask, bool pred, unsigned long long value)
+inline Exchange warpExchange(unsigned mask, bool pred, unsigned long long value, int site)
 {
   Block* b = block;
   if(b == nullptr) { die("warp collective in a kernel that the translator classified as collective-free"); }
@@ -302,7 +303,14 @@ inline Exchange warpExchange(unsigned mask, bool pred, unsigned long long value)
   Warp& w = b->warps[tid >> 5];
   if(!((mask >> lane) & 1)) { die("calling lane is not in the mask of a *_sync collective"); }
   unsigned g = w.gen, slot = g & 1;
-  if(w.arrived == 0) { w.pred_bits[slot] = 0; }
+  // every lane of a generation must be at the same collective: lanes that meet at different call sites are
+  // undefined behaviour on the device (and a wrong answer here), whatever their masks say
+  if(w.arrived == 0) { w.pred_bits[slot] = 0; w.site = site; }
+  else if(w.site != site)
+  {
+    std::fprintf(stderr, "cuda_emu: lanes of one warp wait at different collectives (lines %d and %d)\n", w.site, site);
+    std::abort();
+  }
   if(pred) { w.pred_bits[slot] |= (1u << lane); }
   w.vals[slot][lane] = value;
   w.arrived++; b->progress++;
@@ -323,46 +331,36 @@ inline void blockBarrier()
 
 } // namespace emu
 
-static inline unsigned __ballot_sync(unsigned mask, int pred) { return emu::warpExchange(mask, pred != 0, 0).ballot; }
-static inline int __any_sync(unsigned mask, int pred) { return emu::warpExchange(mask, pred != 0, 0).ballot != 0; }
-static inline int __all_sync(unsigned mask, int pred) { return emu::warpExchange(mask, pred == 0, 0).ballot == 0; }
-static inline void __syncwarp(unsigned mask = 0xFFFFFFFFu) { emu::warpExchange(mask, false, 0); }
+static inline unsigned emu_ballot(unsigned mask, int pred, int site) { return emu::warpExchange(mask, pred != 0, 0, site).ballot; }
+static inline int emu_any(unsigned mask, int pred, int site) { return emu::warpExchange(mask, pred != 0, 0, site).ballot != 0; }
+static inline int emu_all(unsigned mask, int pred, int site) { return emu::warpExchange(mask, pred == 0, 0, site).ballot == 0; }
+static inline void emu_syncwarp(unsigned mask, int site) { emu::warpExchange(mask, false, 0, site); }
 static inline void __syncthreads() { emu::blockBarrier(); }
-template<class T> static inline T __shfl_sync(unsigned mask, T v, int src, int width = 32)
+// kind 0: absolute source lane, 1: down by delta, 2: up by delta, 3: xor
+template<class T> static inline T emu_shfl(unsigned mask, T v, int arg, int width, int kind, int site)
 {
   static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");
   unsigned long long raw = 0; std::memcpy(&raw, &v, sizeof(T));
-  unsigned lane = emu::block->current->tid & 31;
-  emu::Exchange x = emu::warpExchange(mask, false, raw);
-  unsigned from = (lane & ~(unsigned)(width - 1)) | ((unsigned)src & (unsigned)(width - 1));
-  T r; std::memcpy(&r, &x.vals[from], sizeof(T)); return r;
+  unsigned lane = emu::block->current->tid & 31, w = (unsigned)width, base = lane & ~(w - 1), rel = lane & (w - 1), from = lane;
+  emu::Exchange x = emu::warpExchange(mask, false, raw, site);
+  if(kind == 0) { from = base | ((unsigned)arg & (w - 1)); }
+  else if(kind == 1) { from = (rel + (unsigned)arg < w ? lane + (unsigned)arg : lane); }
+  else if(kind == 2) { from = (rel >= (unsigned)arg ? lane - (unsigned)arg : lane); }
+  else { from = lane ^ (unsigned)arg; }
+  T r; std::memcpy(&r, &x.vals[from & 31], sizeof(T)); return r;
 }
-template<class T> static inline T __shfl_down_sync(unsigned mask, T v, unsigned delta, int width = 32)
-{
-  static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");
-  unsigned long long raw = 0; std::memcpy(&raw, &v, sizeof(T));
-  unsigned lane = emu::block->current->tid & 31;
-  emu::Exchange x = emu::warpExchange(mask, false, raw);
-  unsigned from = lane + delta;
-  if((from & ~(unsigned)(width - 1)) != (lane & ~(unsigned)(width - 1))) { from = lane; }
-  T r; std::memcpy(&r, &x.vals[from], sizeof(T)); return r;
-}
-template<class T> static inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32)
-{
-  unsigned long long raw = 0; std::memcpy(&raw, &v, sizeof(T));
-  unsigned lane = emu::block->current->tid & 31;
-  emu::Exchange x = emu::warpExchange(mask, false, raw);
-  unsigned from = ((lane & (unsigned)(width - 1)) >= delta ? lane - delta : lane);
-  T r; std::memcpy(&r, &x.vals[from], sizeof(T)); return r;
-}
-template<class T> static inline T __shfl_xor_sync(unsigned mask, T v, int lanemask, int width = 32)
-{
-  unsigned long long raw = 0; std::memcpy(&raw, &v, sizeof(T));
-  unsigned lane = emu::block->current->tid & 31;
-  emu::Exchange x = emu::warpExchange(mask, false, raw);
-  unsigned from = lane ^ (unsigned)lanemask; (void)width;
-  T r; std::memcpy(&r, &x.vals[from], sizeof(T)); return r;
-}
+#define __ballot_sync(mask, pred) emu_ballot((mask), (pred), __LINE__)
+#define __any_sync(mask, pred) emu_any((mask), (pred), __LINE__)
+#define __all_sync(mask, pred) emu_all((mask), (pred), __LINE__)
+#define __syncwarp(...) emu_syncwarp(emu_first_or_full(__VA_ARGS__), __LINE__)
+static inline unsigned emu_first_or_full(unsigned mask = 0xFFFFFFFFu) { return mask; }
+#define EMU_SHFL_WIDTH(a, b, c, w, ...) w
+#define __shfl_sync(...) emu_shfl(EMU_SHFL3(__VA_ARGS__), EMU_SHFL_WIDTH(__VA_ARGS__, 32, 32), 0, __LINE__)
+#define __shfl_down_sync(...) emu_shfl(EMU_SHFL3(__VA_ARGS__), EMU_SHFL_WIDTH(__VA_ARGS__, 32, 32), 1, __LINE__)
+#define __shfl_up_sync(...) emu_shfl(EMU_SHFL3(__VA_ARGS__), EMU_SHFL_WIDTH(__VA_ARGS__, 32, 32), 2, __LINE__)
+#define __shfl_xor_sync(...) emu_shfl(EMU_SHFL3(__VA_ARGS__), EMU_SHFL_WIDTH(__VA_ARGS__, 32, 32), 3, __LINE__)
+#define EMU_SHFL3(...) EMU_SHFL3_(__VA_ARGS__, 0)
+#define EMU_SHFL3_(a, b, c, ...) (a), (b), (int)(c)
 
 //------------------------------------------------------------------------------
 // Device intrinsics

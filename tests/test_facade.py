@@ -10,12 +10,17 @@ from gcsa2_b200 import build as _build
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def compile_facade_test(tmp_path):
+def compile_facade_test(tmp_path, emulated=False):
+    """Links tests/cpp/facade_test.cpp against the product library, or (emulated) against the host emulation of
+    the engine built by tests/emu -- the same program, the same header."""
     _build.build()
     exe = os.path.join(str(tmp_path), "facade_test")
-    lib_dir = os.path.join(ROOT, "gcsa2_b200")
+    lib_dir, lib = os.path.join(ROOT, "gcsa2_b200"), "gcsa2_b200"
+    if emulated:
+        from emu import build_emu
+        lib_dir, lib = os.path.dirname(build_emu.build()), "gcsa2_b200_emu"
     subprocess.check_call([_build.CXX, "-std=c++17", "-O1", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "tests", "cpp", "facade_test.cpp"), "-L" + lib_dir, "-lgcsa2_b200",
+                           os.path.join(ROOT, "tests", "cpp", "facade_test.cpp"), "-L" + lib_dir, "-l" + lib,
                            "-Wl,-rpath," + lib_dir, "-o", exe])
     return exe
 
@@ -33,4 +38,10 @@ def test_facade_compiles_and_refuses_to_run_without_gpu(tmp_path):
 def test_facade_query_loop_on_gpu(tmp_path):
     exe = compile_facade_test(tmp_path)
     res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "facade_test OK" in res.stdout, res.stdout + res.stderr
+
+
+def test_facade_query_loop_on_the_emulated_engine(tmp_path):
+    exe = compile_facade_test(tmp_path, emulated=True)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "facade_test OK" in res.stdout, res.stdout + res.stderr
