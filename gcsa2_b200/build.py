@@ -1,4 +1,5 @@
-"""Builds gcsa2_b200/libgcsa2_b200.so in-tree: nvcc for sm_100a (engine.cu) + g++ (builder.cpp).
+"""Builds gcsa2_b200/libgcsa2_b200.so in-tree: nvcc for sm_100a (engine.cu, which includes its kernels from
+csrc/device/*.cuh) + g++ (the host-only sources).
 
 The shared library is self-contained (static cudart), so it travels to the GPU box with the
 snapshot and loads on a CPU-only machine too (symbol checks in the CPU test-suite)."""
@@ -30,7 +31,8 @@ def build(force=False, verbose=False):
     host_cpp = [os.path.join(CSRC, name) for name in HOST_SOURCES]
     engine_o = os.path.join(CSRC, "engine.o")
     host_o = [src[:-4] + ".o" for src in host_cpp]
-    if not force and not _stale(LIB, [engine_cu, INCLUDE, os.path.join(CSRC, "internal.h")] + host_cpp):
+    device = [os.path.join(CSRC, "device", f) for f in sorted(os.listdir(os.path.join(CSRC, "device"))) if f.endswith(".cuh")]
+    if not force and not _stale(LIB, [engine_cu, INCLUDE, os.path.join(CSRC, "internal.h")] + device + host_cpp):
         return LIB
     run = lambda cmd: subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL)
     run([NVCC] + NVCC_FLAGS + ["-c", engine_cu, "-o", engine_o])

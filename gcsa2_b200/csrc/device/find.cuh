@@ -1,0 +1,361 @@
+/* device/find.cuh -- find(): the batched backward-search kernel and the construction of the k-mer table.
+   Part of the single translation unit engine.cu (included there in order); sm_100a only. */
+#ifndef GCSA2_B200_DEVICE_FIND_CUH
+#define GCSA2_B200_DEVICE_FIND_CUH
+
+//------------------------------------------------------------------------------
+// Kernels: find
+//------------------------------------------------------------------------------
+
+// Pattern bytes are read through an 8-byte window (one aligned streaming load per 8 characters,
+// evict-first: the pattern stream must not push index lines out of the L2).
+struct CharWindow
+{
+  u64 word; u64 index;
+  __device__ __forceinline__ CharWindow() : word(0), index(~0ull) {}
+  __device__ __forceinline__ u32 get(const u8* chars, u64 pos)
+  {
+    u64 addr = (u64)(chars + pos);
+    u64 wi = addr >> 3;
+    if(wi != index) { word = __ldcs((const unsigned long long*)(wi << 3)); index = wi; }
+    return (u32)((word >> ((addr & 7) * 8)) & 0xFF);
+  }
+};
+
+
+
+struct FindStatsDev { u64 found, total_length, lf_steps, sector_probes, table_hits; };
+
+// Eight pattern bytes of the default alphabet (w: lowest address in the low byte) -> their comp - 1 codes,
+// 2 bits each, the LAST byte in the lowest bits.  *good = how many bytes, counted from the last one, are bases
+// in either case (8 if all); the codes of the others are garbage.
+__device__ __forceinline__ u32 pack8_reversed(u64 w, u32* good)
+{
+  const u64 L7 = 0x7F7F7F7F7F7F7F7Full, H8 = 0x8080808080808080ull;
+  u64 x = w & 0xDFDFDFDFDFDFDFDFull;
+  u64 zA = x ^ 0x4141414141414141ull, zC = x ^ 0x4343434343434343ull, zG = x ^ 0x4747474747474747ull, zT = x ^ 0x5454545454545454ull;
+  // 0x80 in every byte that equals one of the four letters (exact zero-byte test, no carries between bytes)
+  u64 valid = ~(((zA & L7) + L7) | zA | L7) | ~(((zC & L7) + L7) | zC | L7) | ~(((zG & L7) + L7) | zG | L7) | ~(((zT & L7) + L7) | zT | L7);
+  u64 inv = ~valid & H8;
+  *good = (inv == 0 ? 8u : 7u - (u32)((63 - __clzll((long long)inv)) >> 3));
+  u64 t = (w >> 1) & 0x0303030303030303ull;                      // A 0, C 1, T 2, G 3
+  u64 code = t ^ ((t >> 1) & 0x0101010101010101ull);               // A 0, C 1, G 2, T 3
+  u64 y = (code | (code >> 6)) & 0x000F000F000F000Full;
+  y = (y | (y >> 12)) & 0x000000FF000000FFull;
+  y = (y | (y >> 24)) & 0xFFFFull;
+  u32 r = __brev((u32)y) >> 16;                                    // reverse the order of the characters ...
+  return ((r >> 1) & 0x5555u) | ((r & 0x5555u) << 1);              // ... not of the two bits of each
+}
+
+/*
+  GCSA::find(begin, end), include/gcsa/gcsa.h:96-110.  One query per lane.  Queries are pulled from a
+  contiguous per-warp slice; lanes whose search ended are refilled together once half the warp is idle
+  (one ballot + popc, no atomics).  A refilled lane packs the last 32 characters of its pattern into one
+  register (2 bits each, the last character lowest): the k-mer table index is a bit field of it and a jump
+  along a unary path is one XOR against the table entry.  Anything that does not fit the fast forms (other
+  characters, another alphabet, short remainders) goes through the per-character path, which is the
+  reference's loop verbatim.
+*/
+template<bool STATS, int MIN_BLOCKS, bool PACKED = false>
+__global__ void __launch_bounds__(256, MIN_BLOCKS)
+find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict__ offsets, u64 char_base,
+            u64 fixed_length, u64 n, u64* __restrict__ sp_out, u64* __restrict__ ep_out, FindStatsDev* stats, int refill_at)
+{
+  // PACKED: `chars` holds ceil(fixed_length / 32) 64-bit words per pattern, character p of a pattern at bits
+  // [2 (p % 32), 2 (p % 32) + 2) of word p / 32, value comp - 1 (ACGT only; packed by the host entry point).
+  __shared__ u8 c2c[256];
+  if(!PACKED)
+  {
+    for(int i = threadIdx.x; i < 256; i += blockDim.x) { c2c[i] = v.char2comp[i]; }
+    __syncthreads();
+  }
+  const u64 words_per_pattern = (fixed_length + 31) >> 5;
+  const bool fast_pack = (PACKED || v.default_alphabet != 0);
+
+  const u32 lane = threadIdx.x & 31;
+  const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+  // contiguous slice of queries for this warp
+  const u64 per = (n + n_warps - 1) / n_warps;
+  u64 next = warp * per;
+  const u64 slice_end = (next + per < n ? next + per : n);
+  if(next >= n) { return; }
+
+  u64 q = ~0ull, sp = 0, ep = 0, pos = 0, begin = 0;
+  u64 tail = 0, tail_end = 0; u32 tail_n = 0;       // characters [tail_end - tail_n, tail_end), the one at tail_end - 1 - t in bits [2t, 2t + 2)
+  bool live = false;
+  u32 jump_mode = 1;                   // 0 once a jump failed on a character: this query dies within a few single steps
+  CharWindow win;
+  u64 st_found = 0, st_len = 0, st_steps = 0, st_sectors = 0, st_hits = 0;
+
+  // comp value of the character at (batch-wide) position p of the current query: the general path
+  auto comp_slow = [&](u64 p) -> u32
+  {
+    if(PACKED)
+    {
+      u64 rel = p - begin, wi = q * words_per_pattern + (rel >> 5);
+      if(wi != win.index) { win.word = __ldcs((const unsigned long long*)chars + wi); win.index = wi; }
+      return (u32)((win.word >> ((rel & 31) * 2)) & 3) + 1;
+    }
+    return c2c[win.get(chars, p)];
+  };
+  auto comp_at = [&](u64 p) -> u32
+  {
+    u64 off = tail_end - 1 - p;
+    if(off < (u64)tail_n) { return (u32)((tail >> (2 * off)) & 3) + 1; }
+    return comp_slow(p);
+  };
+  // pack the (up to) 32 characters that end at position `end_pos` (exclusive)
+  auto pack_tail = [&](u64 end_pos)
+  {
+    tail = 0; tail_n = 0; tail_end = end_pos;
+    if(!fast_pack) { return; }
+    if constexpr(PACKED)
+    {
+      u64 have = end_pos - begin, m = (have < 32 ? have : 32), r0 = have - m;             // pattern-relative [r0, r0 + m)
+      const unsigned long long* words = (const unsigned long long*)chars + q * words_per_pattern;
+      u32 sh = (u32)(r0 & 31) * 2;
+      u64 x = __ldcs(words + (r0 >> 5)) >> sh;
+      if(sh != 0 && (r0 & 31) + m > 32) { x |= __ldcs(words + (r0 >> 5) + 1) << (64 - sh); }
+      u64 r = __brevll(x);
+      r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+      tail = (m < 32 ? r >> (2 * (32 - m)) : r);
+      tail_n = (u32)m;
+    }
+    else
+    {
+      for(u32 w = 0; w < 4; w++)
+      {
+        u64 pe = end_pos - 8 * w;
+        if(pe - begin < 8) { break; }
+        u64 addr = (u64)(chars + pe - 8); u32 a = (u32)(addr & 7);
+        const unsigned long long* base = (const unsigned long long*)(addr - a);
+        u64 word = __ldcs(base);
+        if(a != 0) { word = (word >> (8 * a)) | ((u64)__ldcs(base + 1) << (64 - 8 * a)); }
+        u32 good;
+        u32 r = pack8_reversed(word, &good);
+        tail |= (u64)r << (16 * w);
+        tail_n += good;
+        if(good < 8) { break; }
+      }
+    }
+  };
+
+  while(true)
+  {
+    // refill: all idle lanes at once, as soon as half the warp is idle (or nobody is working)
+    u32 dead = __ballot_sync(0xFFFFFFFFu, !live);
+    if(__popc(dead) >= refill_at)
+    {
+      u32 my = __popc(dead & ((1u << lane) - 1));
+      if(!live)
+      {
+        u64 cand = next + my;
+        if(cand < slice_end)
+        {
+          q = cand;
+          u64 b, e;
+          if(offsets != nullptr) { b = offsets[q] - char_base; e = offsets[q + 1] - char_base; }
+          else { b = q * fixed_length; e = b + fixed_length; }
+          begin = b; live = true; jump_mode = 1;
+          tail = 0; tail_n = 0; tail_end = e;
+          if(e == b || v.path_nodes == 0) { sp = 0; ep = v.path_nodes - 1; pos = b; }
+          else
+          {
+            pack_tail(e);
+            pos = e - 1;
+            bool used_table = false;
+            if(v.table_k > 0 && e - b >= (u64)v.table_k)
+            {
+              u64 idx = 0; bool ok = true;
+              if(tail_n >= (u32)v.table_k) { idx = tail & ((1ull << (2 * v.table_k)) - 1); }
+              else
+              {
+                for(int t = 0; t < v.table_k; t++)
+                {
+                  u32 c = comp_at(e - 1 - t);
+                  ok = ok && (c >= 1 && c <= 4);
+                  idx |= (u64)((c - 1) & 3) << (2 * t);
+                }
+              }
+              if(ok)
+              {
+                u64 r, je = 0;
+                if(v.table2 != nullptr) { ulonglong2 both = __ldg(v.table2 + idx); r = both.x; je = both.y; }
+                else { r = __ldg(v.table + idx); }
+                u64 len = r >> 40;
+                if(len != TABLE_ESCAPE)
+                {
+                  sp = r & M40; ep = sp + len - 1; pos = e - v.table_k; used_table = true;
+                  if(STATS) { st_hits++; }
+                  // Fused table: the jump entry of a singleton result came with the same 16-byte load, so the first
+                  // jump costs no probe.  Taken only when the whole path lies inside the packed tail and inside
+                  // the pattern; everything else is left to the main loop.
+                  u32 jl = (u32)(je >> 59);
+                  if(jl >= 2 && (u64)jl <= pos - b && (u32)v.table_k + jl <= tail_n)
+                  {
+                    u64 stored = ((je << 5) >> 5) >> v.jump_tbits;
+                    if((((tail >> (2 * v.table_k)) ^ stored) & ((1ull << (2 * jl)) - 1)) == 0)
+                    {
+                      sp = ep = (je & ((1ull << v.jump_tbits) - 1));
+                      pos -= jl;
+                      if(STATS) { st_steps += jl; }
+                    }
+                    else { jump_mode = 0; }                          // leaves the unary path: it dies within these steps
+                  }
+                }
+              }
+            }
+            if(!used_table)
+            {
+              u32 c = comp_at(pos);
+              sp = v.char_sp[c]; ep = v.char_ep[c];
+            }
+          }
+        }
+      }
+      next += __popc(dead);
+      if(next > slice_end) { next = slice_end; }
+    }
+    if(__ballot_sync(0xFFFFFFFFu, live) == 0)
+    {
+      if(next >= slice_end) { break; }
+      continue;
+    }
+
+    if(live)
+    {
+      if(!(range_empty(sp, ep) || pos == begin))
+      {
+        u32 sectors = 0;
+        bool done = false;
+        // Singleton range: try the jump table (one load for up to jump_k backward steps along a unary path).
+        // The table is chosen by what is left of the pattern, so that a path never overshoots its end: the long
+        // table (paths of up to jump_k steps) while at least jump_k characters remain, the short one (4) below that.
+        const u64* jump_from = nullptr;
+        if(v.jump != nullptr && jump_mode != 0 && sp == ep)
+        {
+          u64 left = pos - begin;
+          jump_from = (left >= (u64)v.jump_k ? v.jump : (left >= 4 ? v.jump_short : nullptr));
+        }
+        if(jump_from != nullptr)
+        {
+          u64 e = __ldg(jump_from + sp);
+          u32 len = (u32)(e >> 59);
+          if(STATS) { sectors++; }
+          if(len >= 2)
+          {
+            u64 stored = ((e << 5) >> 5) >> v.jump_tbits;
+            u64 off = tail_end - pos;
+            if(off + len > (u64)tail_n && fast_pack && tail_n == 32) { pack_tail(pos); off = 0; }
+            bool same = true;
+            if(off + len <= (u64)tail_n) { same = ((((tail >> (2 * off)) ^ stored) & ((1ull << (2 * len)) - 1)) == 0); }
+            else
+            {
+              for(u32 t = 0; t < len; t++)
+              {
+                u32 pc = comp_at(pos - 1 - t);
+                same = same && (pc == ((u32)(stored >> (2 * t)) & 3) + 1);
+              }
+            }
+            if(same)
+            {
+              sp = ep = (e & ((1ull << v.jump_tbits) - 1));
+              pos -= len; done = true;
+              if(STATS) { st_steps += len; }
+            }
+            else { jump_mode = 0; }                                  // it dies within these steps: the exact pair comes from single steps
+          }
+        }
+        if(!done && tail_end - pos >= (u64)tail_n && fast_pack && tail_n == 32) { pack_tail(pos); }   // next window of a long pattern
+        u32 c = (done ? 0 : comp_at(pos - 1));
+        if(!done && v.bwt2 != nullptr && pos - begin >= 2 && c >= 1 && c <= 4)
+        {
+          u32 c1 = comp_at(pos - 2);
+          if(c1 >= 1 && c1 <= 4 && lf2_range(v, sp, ep, c1, c, sp, ep, STATS ? &sectors : nullptr))
+          {
+            pos -= 2; done = true;
+            if(STATS) { st_steps += 2; }
+          }
+        }
+        if(!done)
+        {
+          pos--;
+          lf_range(v, sp, ep, c, sp, ep, STATS ? &sectors : nullptr);
+          if(STATS) { st_steps++; }
+        }
+        if(STATS) { st_sectors += sectors; }
+      }
+      if(range_empty(sp, ep) || pos == begin)
+      {
+        __stcs((unsigned long long*)sp_out + q, (unsigned long long)sp); __stcs((unsigned long long*)ep_out + q, (unsigned long long)ep);
+        if(STATS && !range_empty(sp, ep)) { st_found++; st_len += ep + 1 - sp; }
+        live = false;
+      }
+    }
+  }
+
+  if(STATS)
+  {
+    atomicAdd((ull*)&stats->found, (ull)st_found); atomicAdd((ull*)&stats->total_length, (ull)st_len);
+    atomicAdd((ull*)&stats->lf_steps, (ull)st_steps); atomicAdd((ull*)&stats->sector_probes, (ull)st_sectors);
+    atomicAdd((ull*)&stats->table_hits, (ull)st_hits);
+  }
+}
+
+/*
+  k-mer table.  Entry idx describes the string whose t-th character from the END is comp
+  ((idx >> 2t) & 3) + 1 and holds exactly what find() returns for it, early exit included: an
+  empty result keeps the uncanonicalised pair of the step where the search died, and such a pair
+  always has ep = sp - 1 (rank is monotone), so (sp, length) loses nothing.
+  The table is grown one character at a time: level j+1 is one LF step away from level j.
+*/
+__global__ void __launch_bounds__(256)
+table_init_kernel(const DevView v, ulonglong2* tmp)
+{
+  u32 idx = threadIdx.x;
+  if(idx < 4) { tmp[idx] = make_ulonglong2(v.char_sp[idx + 1], v.char_ep[idx + 1]); }
+}
+
+// level j (4^j entries in tmp[0, 4^j)) -> level j + 1 in place: slot idx | c << 2j
+__global__ void __launch_bounds__(256)
+table_extend_kernel(const DevView v, int j, ulonglong2* tmp)
+{
+  u64 total = 1ull << (2 * j);
+  for(u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x)
+  {
+    ulonglong2 r = tmp[idx];
+    #pragma unroll
+    for(u32 c = 4; c-- > 0; )
+    {
+      u64 sp = r.x, ep = r.y;
+      if(!range_empty(sp, ep)) { lf_range(v, sp, ep, c + 1, sp, ep); }
+      tmp[idx | ((u64)c << (2 * j))] = make_ulonglong2(sp, ep);
+    }
+  }
+}
+
+// last level: level k - 1 in tmp -> packed level k in table (k >= 2); for k == 1 pack tmp itself
+// With table2 != nullptr the fused form is written instead: next to each entry the jump-table entry of its sp when the
+// result is a single path node (find_kernel then takes the first jump without another probe).
+__global__ void __launch_bounds__(256)
+table_final_kernel(const DevView v, int k, const ulonglong2* tmp, u64* table, ulonglong2* table2)
+{
+  u64 total = (k == 1 ? 4 : 1ull << (2 * (k - 1)));
+  for(u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x)
+  {
+    ulonglong2 r = tmp[idx];
+    for(u32 c = 0; c < (k == 1 ? 1u : 4u); c++)
+    {
+      u64 sp = r.x, ep = r.y;
+      if(k > 1 && !range_empty(sp, ep)) { lf_range(v, sp, ep, c + 1, sp, ep); }
+      u64 len = ep + 1 - sp;
+      u64 entry = (len >= TABLE_ESCAPE || sp > M40) ? (TABLE_ESCAPE << 40) : (sp | (len << 40));
+      u64 slot = (k == 1 ? idx : (idx | ((u64)c << (2 * (k - 1)))));
+      if(table2 == nullptr) { table[slot] = entry; }
+      else { table2[slot] = make_ulonglong2(entry, (len == 1 && v.jump != nullptr) ? __ldg(v.jump + sp) : 0ull); }
+    }
+  }
+}
+
+#endif

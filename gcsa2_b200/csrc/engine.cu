@@ -42,16 +42,15 @@
 #include "../../include/gcsa2_b200.h"
 #include "internal.h"
 
-typedef uint64_t u64;
-typedef unsigned long long ull;
-typedef unsigned int u32;
-typedef unsigned char u8;
-
-#define BWT_W 87u
-#define RV_W 192u
-#define SEL_HINT 512u
-#define M40 ((1ull << 40) - 1)
-#define TABLE_ESCAPE 0xFFFFFFull
+// Device code: views and primitives, then the kernels by operation.
+#include "device/layout.cuh"
+#include "device/find.cuh"
+#include "device/two_step.cuh"
+#include "device/lf_count.cuh"
+#include "device/kmers.cuh"
+#include "device/locate.cuh"
+#include "device/lcp.cuh"
+#include "device/mem.cuh"
 
 //------------------------------------------------------------------------------
 // Errors
@@ -63,1773 +62,6 @@ static int fail(int code, const std::string& msg) { g_last_error = msg; return c
 
 #define CUDA_TRY(expr) do { cudaError_t e_ = (expr); if(e_ != cudaSuccess) { \
   return fail(GCSA_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } } while(0)
-
-//------------------------------------------------------------------------------
-// Device views
-//------------------------------------------------------------------------------
-
-struct RankVecDev { const ulonglong4* sec; u64 n_bits; u64 n_sec; };
-struct SelVecDev  { RankVecDev rv; const u32* hints; u64 ones; };
-
-struct DevView
-{
-  u64 path_nodes, edge_count;
-  u64 C[GCSA_B200_SIGMA + 1];
-  u64 char_sp[GCSA_B200_SIGMA], char_ep[GCSA_B200_SIGMA];
-  const ulonglong4* bwt;
-  const ulonglong4* bwt2;              // two-step blocks (16 sectors per block), or nullptr
-  RankVecDev edges, sampled, extra_filter;
-  SelVecDev extra_values, redundant;
-  const u64* sparse_pos[3]; u64 sparse_n[3];       // comps 0, 5, 6
-  const u64* stored_samples; const u64* sample_start; u64 sample_count;
-  const u64* table; int table_k;      // entry = sp | length << 40; length 0xFFFFFF = not tabulated
-  const ulonglong2* table2;            // fused form (replaces `table`): { that entry, the jump entry of sp if the range is a singleton, else 0 }
-  const u32* walk32; const u64* walk64; // locate walk table: LF(i) << 1, or rank(sampled, i) << 1 | 1 for sampled nodes
-  u32 default_alphabet;                // char2comp is exactly ACGT / acgt -> 1..4 for the bases (enables the SWAR pattern packing)
-  const u64* jump; u32 jump_k, jump_tbits;
-  const u64* jump_short;               // the same table cut at 4 steps: for the tail of a pattern that is shorter than the long path   // jump table: len << 59 | 2-bit chars << jump_tbits | target (see jump_extend_kernel)
-  const u64* loc64;                    // locate table: bit 63 | value for nodes with one start position, else rank of the sampled node << 24 | steps
-  u8 char2comp[256];
-};
-
-struct LcpView
-{
-  u64 size, branching, levels, values;
-  int shift;                           // log2(branching) if it is a power of two, else -1
-  u64 offsets[16];
-  const u8* data;
-};
-
-//------------------------------------------------------------------------------
-// Device primitives
-//------------------------------------------------------------------------------
-
-__device__ __forceinline__ ulonglong4 ld256(const ulonglong4* p)
-{
-  ulonglong4 r;
-  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.x), "=l"(r.y), "=l"(r.z), "=l"(r.w) : "l"(p));
-  return r;
-}
-
-__device__ __forceinline__ bool range_empty(u64 sp, u64 ep) { return (sp + 1 > ep + 1); }   // utils.h:93-101
-
-// ones among the low k bits of w, 0 <= k <= 64
-__device__ __forceinline__ u32 popc_low(u64 w, u32 k)
-{
-  u64 m = (k >= 64 ? ~0ull : ((1ull << k) - 1));
-  return (u32)__popcll(w & m);
-}
-
-// ones among the low k bits of the (up to) 88-bit string hi:lo, 0 <= k <= 88
-__device__ __forceinline__ u32 popc_low88(u64 lo, u32 hi, u32 k)
-{
-  u32 klo = (k < 64 ? k : 64), khi = k - klo;
-  return popc_low(lo, klo) + (u32)__popc(hi & ((1u << khi) - 1));
-}
-
-__device__ __forceinline__ u64 rv_rank(const RankVecDev& v, u64 i)
-{
-  u64 s = i / RV_W; u32 off = (u32)(i - s * RV_W);
-  ulonglong4 q = ld256(v.sec + s);
-  u32 w = off >> 6, r = off & 63;
-  u64 res = q.x;
-  if(w > 0) { res += __popcll(q.y); }
-  if(w > 1) { res += __popcll(q.z); }
-  u64 word = (w == 0 ? q.y : (w == 1 ? q.z : q.w));
-  return res + popc_low(word, r);
-}
-
-// bit i and rank(i) from one sector
-__device__ __forceinline__ bool rv_get_rank(const RankVecDev& v, u64 i, u64& rank)
-{
-  u64 s = i / RV_W; u32 off = (u32)(i - s * RV_W);
-  ulonglong4 q = ld256(v.sec + s);
-  u32 w = off >> 6, r = off & 63;
-  u64 res = q.x;
-  if(w > 0) { res += __popcll(q.y); }
-  if(w > 1) { res += __popcll(q.z); }
-  u64 word = (w == 0 ? q.y : (w == 1 ? q.z : q.w));
-  rank = res + popc_low(word, r);
-  return (word >> r) & 1;
-}
-
-// position of the j-th (1-based) set bit of w; w has at least j set bits
-__device__ __forceinline__ u32 select_in_word(u64 w, u32 j)
-{
-  u32 lo = (u32)w, c = __popc(lo);
-  if(j <= c) { return __fns(lo, 0, j); }
-  return 32 + __fns((u32)(w >> 32), 0, j - c);
-}
-
-// select1(k), k >= 1 (SadaCount / SadaSparse selects, support.h:253, 324)
-__device__ __forceinline__ u64 sv_select(const SelVecDev& v, u64 k)
-{
-  u64 h = (k - 1) / SEL_HINT;
-  u64 lo = v.hints[h], hi = v.hints[h + 1];
-  // last sector in [lo, hi] whose cumulative count is < k
-  while(lo < hi)
-  {
-    u64 mid = lo + (hi - lo + 1) / 2;
-    u64 cum = __ldg(&(v.rv.sec[mid].x));
-    if(cum < k) { lo = mid; } else { hi = mid - 1; }
-  }
-  ulonglong4 q = ld256(v.rv.sec + lo);
-  u32 need = (u32)(k - q.x);
-  u32 c0 = __popcll(q.y), c1 = __popcll(q.z);
-  u64 base = lo * RV_W;
-  if(need <= c0) { return base + select_in_word(q.y, need); }
-  need -= c0;
-  if(need <= c1) { return base + 64 + select_in_word(q.z, need); }
-  need -= c1;
-  return base + 128 + select_in_word(q.w, need);
-}
-
-// number of list entries < i
-__device__ __forceinline__ u64 sparse_rank(const u64* pos, u64 n, u64 i)
-{
-  u64 lo = 0, hi = n;
-  while(lo < hi)
-  {
-    u64 mid = (lo + hi) >> 1;
-    if(__ldg(pos + mid) < i) { lo = mid + 1; } else { hi = mid; }
-  }
-  return lo;
-}
-
-__device__ __forceinline__ int sparse_slot(u32 c) { return (c == 0 ? 0 : (int)c - 4); }   // 0,5,6 -> 0,1,2
-
-/*
-  GCSA::LF(range, comp), include/gcsa/gcsa.h:155-162 with 262-274 and pathNodeRange 253-258.
-  Fast characters: one fused sector per endpoint.  Sparse characters: list rank + edges rank.
-*/
-__device__ __forceinline__ void lf_range(const DevView& v, u64 sp, u64 ep, u32 c, u64& osp, u64& oep, u32* sectors = nullptr)
-{
-  if(c >= 1 && c <= GCSA_B200_FAST_CHARS)
-  {
-    u64 e1 = ep + 1;
-    u64 bs = sp / BWT_W, be = e1 / BWT_W;
-    u32 os = (u32)(sp - bs * BWT_W), oe = (u32)(e1 - be * BWT_W);
-    ulonglong4 a = ld256(v.bwt + bs * 4 + (c - 1));
-    ulonglong4 b = a;
-    if(be != bs) { b = ld256(v.bwt + be * 4 + (c - 1)); }
-    if(sectors) { *sectors += (be != bs ? 2 : 1); }
-    u32 js = popc_low88(a.y, (u32)(a.x >> 40), os);
-    u32 je = popc_low88(b.y, (u32)(b.x >> 40), oe);
-    u64 f = (a.x & M40) + js;
-    u64 s = (b.x & M40) + je - 1;
-    if(range_empty(f, s)) { osp = f; oep = s; return; }
-    osp = (a.z & M40) + popc_low88(a.w, (u32)(a.z >> 40), js + 1);
-    oep = (b.z & M40) + popc_low88(b.w, (u32)(b.z >> 40), je);
-  }
-  else if(c < GCSA_B200_SIGMA)
-  {
-    int slot = sparse_slot(c);
-    u64 f = v.C[c] + sparse_rank(v.sparse_pos[slot], v.sparse_n[slot], sp);
-    u64 s = v.C[c] + sparse_rank(v.sparse_pos[slot], v.sparse_n[slot], ep + 1) - 1;
-    if(range_empty(f, s)) { osp = f; oep = s; return; }
-    osp = rv_rank(v.edges, f);
-    oep = rv_rank(v.edges, s);
-    if(sectors) { *sectors += 2; }
-  }
-  else { osp = 1; oep = 0; }    // not a comp value: Range::empty_range()
-}
-
-/*
-  Two backward steps in one probe.  For a pair of fast characters (c1, c2) the block holds the
-  same sector format over the "squared" graph: B2[i] = 1 iff node i has a predecessor j by c2 that
-  itself has a predecessor h by c1; the 2-paths of one label, ordered by target, are ordered by
-  source as well and consecutive sources differ by at most one node, so the source of the x-th
-  2-path is H0 + popcount(boundary bits), exactly like rank(edges, .) in the one-step sector.
-  Equivalent to LF(LF(range, c2), c1) whenever that is non-empty; returns false otherwise (the
-  caller then takes the two single steps, which produce the reference's uncanonicalised pair).
-*/
-__device__ __forceinline__ bool lf2_range(const DevView& v, u64 sp, u64 ep, u32 c1, u32 c2, u64& osp, u64& oep, u32* sectors = nullptr)
-{
-  u64 e1 = ep + 1;
-  u64 bs = sp / BWT_W, be = e1 / BWT_W;
-  u32 os = (u32)(sp - bs * BWT_W), oe = (u32)(e1 - be * BWT_W);
-  u32 label = (c1 - 1) * 4 + (c2 - 1);
-  ulonglong4 a = ld256(v.bwt2 + bs * 16 + label);
-  ulonglong4 b = a;
-  if(be != bs) { b = ld256(v.bwt2 + be * 16 + label); }
-  if(sectors) { *sectors += (be != bs ? 2 : 1); }
-  u32 js = popc_low88(a.y, (u32)(a.x >> 40), os);
-  u32 je = popc_low88(b.y, (u32)(b.x >> 40), oe);
-  u64 f = (a.x & M40) + js;
-  u64 s = (b.x & M40) + je - 1;
-  if(range_empty(f, s)) { return false; }
-  osp = (a.z & M40) + popc_low88(a.w, (u32)(a.z >> 40), js + 1);
-  oep = (b.z & M40) + popc_low88(b.w, (u32)(b.z >> 40), je);
-  return true;
-}
-
-/*
-  GCSA::LF(path_node), include/gcsa/gcsa.h:165-183: first predecessor, fast characters first.
-  One 128-byte line holds the four fast sectors of the node's block.
-*/
-__device__ __forceinline__ u64 lf_node(const DevView& v, u64 i)
-{
-  u64 b = i / BWT_W; u32 off = (u32)(i - b * BWT_W);
-  const ulonglong4* line = v.bwt + b * 4;
-  ulonglong4 q[4];
-  #pragma unroll
-  for(int c = 0; c < 4; c++) { q[c] = ld256(line + c); }
-  #pragma unroll
-  for(int c = 0; c < 4; c++)
-  {
-    bool bit = (off < 64 ? (q[c].y >> off) & 1 : ((q[c].x >> 40) >> (off - 64)) & 1);
-    if(bit)
-    {
-      u32 j = popc_low88(q[c].y, (u32)(q[c].x >> 40), off);
-      return (q[c].z & M40) + popc_low88(q[c].w, (u32)(q[c].z >> 40), j + 1);
-    }
-  }
-  for(u32 c = GCSA_B200_FAST_CHARS + 1; c < GCSA_B200_SIGMA; c++)
-  {
-    int slot = sparse_slot(c);
-    u64 r = sparse_rank(v.sparse_pos[slot], v.sparse_n[slot], i);
-    if(r < v.sparse_n[slot] && v.sparse_pos[slot][r] == i) { return rv_rank(v.edges, v.C[c] + r); }
-  }
-  return rv_rank(v.edges, v.C[0] + sparse_rank(v.sparse_pos[0], v.sparse_n[0], i));
-}
-
-// bit B_c[i] for any comp (used by LF_fast / LF_all single-node shortcut, src/gcsa.cpp:748-756)
-__device__ __forceinline__ bool bwt_bit(const DevView& v, u64 i, u32 c)
-{
-  if(c >= 1 && c <= GCSA_B200_FAST_CHARS)
-  {
-    u64 b = i / BWT_W; u32 off = (u32)(i - b * BWT_W);
-    ulonglong4 q = ld256(v.bwt + b * 4 + (c - 1));
-    return (off < 64 ? (q.y >> off) & 1 : ((q.x >> 40) >> (off - 64)) & 1);
-  }
-  int slot = sparse_slot(c);
-  u64 r = sparse_rank(v.sparse_pos[slot], v.sparse_n[slot], i);
-  return (r < v.sparse_n[slot] && v.sparse_pos[slot][r] == i);
-}
-
-//------------------------------------------------------------------------------
-// Kernels: find
-//------------------------------------------------------------------------------
-
-// Pattern bytes are read through an 8-byte window (one aligned streaming load per 8 characters,
-// evict-first: the pattern stream must not push index lines out of the L2).
-struct CharWindow
-{
-  u64 word; u64 index;
-  __device__ __forceinline__ CharWindow() : word(0), index(~0ull) {}
-  __device__ __forceinline__ u32 get(const u8* chars, u64 pos)
-  {
-    u64 addr = (u64)(chars + pos);
-    u64 wi = addr >> 3;
-    if(wi != index) { word = __ldcs((const unsigned long long*)(wi << 3)); index = wi; }
-    return (u32)((word >> ((addr & 7) * 8)) & 0xFF);
-  }
-};
-
-
-
-struct FindStatsDev { u64 found, total_length, lf_steps, sector_probes, table_hits; };
-
-// Eight pattern bytes of the default alphabet (w: lowest address in the low byte) -> their comp - 1 codes,
-// 2 bits each, the LAST byte in the lowest bits.  *good = how many bytes, counted from the last one, are bases
-// in either case (8 if all); the codes of the others are garbage.
-__device__ __forceinline__ u32 pack8_reversed(u64 w, u32* good)
-{
-  const u64 L7 = 0x7F7F7F7F7F7F7F7Full, H8 = 0x8080808080808080ull;
-  u64 x = w & 0xDFDFDFDFDFDFDFDFull;
-  u64 zA = x ^ 0x4141414141414141ull, zC = x ^ 0x4343434343434343ull, zG = x ^ 0x4747474747474747ull, zT = x ^ 0x5454545454545454ull;
-  // 0x80 in every byte that equals one of the four letters (exact zero-byte test, no carries between bytes)
-  u64 valid = ~(((zA & L7) + L7) | zA | L7) | ~(((zC & L7) + L7) | zC | L7) | ~(((zG & L7) + L7) | zG | L7) | ~(((zT & L7) + L7) | zT | L7);
-  u64 inv = ~valid & H8;
-  *good = (inv == 0 ? 8u : 7u - (u32)((63 - __clzll((long long)inv)) >> 3));
-  u64 t = (w >> 1) & 0x0303030303030303ull;                      // A 0, C 1, T 2, G 3
-  u64 code = t ^ ((t >> 1) & 0x0101010101010101ull);               // A 0, C 1, G 2, T 3
-  u64 y = (code | (code >> 6)) & 0x000F000F000F000Full;
-  y = (y | (y >> 12)) & 0x000000FF000000FFull;
-  y = (y | (y >> 24)) & 0xFFFFull;
-  u32 r = __brev((u32)y) >> 16;                                    // reverse the order of the characters ...
-  return ((r >> 1) & 0x5555u) | ((r & 0x5555u) << 1);              // ... not of the two bits of each
-}
-
-/*
-  GCSA::find(begin, end), include/gcsa/gcsa.h:96-110.  One query per lane.  Queries are pulled from a
-  contiguous per-warp slice; lanes whose search ended are refilled together once half the warp is idle
-  (one ballot + popc, no atomics).  A refilled lane packs the last 32 characters of its pattern into one
-  register (2 bits each, the last character lowest): the k-mer table index is a bit field of it and a jump
-  along a unary path is one XOR against the table entry.  Anything that does not fit the fast forms (other
-  characters, another alphabet, short remainders) goes through the per-character path, which is the
-  reference's loop verbatim.
-*/
-template<bool STATS, int MIN_BLOCKS, bool PACKED = false>
-__global__ void __launch_bounds__(256, MIN_BLOCKS)
-find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict__ offsets, u64 char_base,
-            u64 fixed_length, u64 n, u64* __restrict__ sp_out, u64* __restrict__ ep_out, FindStatsDev* stats, int refill_at)
-{
-  // PACKED: `chars` holds ceil(fixed_length / 32) 64-bit words per pattern, character p of a pattern at bits
-  // [2 (p % 32), 2 (p % 32) + 2) of word p / 32, value comp - 1 (ACGT only; packed by the host entry point).
-  __shared__ u8 c2c[256];
-  if(!PACKED)
-  {
-    for(int i = threadIdx.x; i < 256; i += blockDim.x) { c2c[i] = v.char2comp[i]; }
-    __syncthreads();
-  }
-  const u64 words_per_pattern = (fixed_length + 31) >> 5;
-  const bool fast_pack = (PACKED || v.default_alphabet != 0);
-
-  const u32 lane = threadIdx.x & 31;
-  const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
-  // contiguous slice of queries for this warp
-  const u64 per = (n + n_warps - 1) / n_warps;
-  u64 next = warp * per;
-  const u64 slice_end = (next + per < n ? next + per : n);
-  if(next >= n) { return; }
-
-  u64 q = ~0ull, sp = 0, ep = 0, pos = 0, begin = 0;
-  u64 tail = 0, tail_end = 0; u32 tail_n = 0;       // characters [tail_end - tail_n, tail_end), the one at tail_end - 1 - t in bits [2t, 2t + 2)
-  bool live = false;
-  u32 jump_mode = 1;                   // 0 once a jump failed on a character: this query dies within a few single steps
-  CharWindow win;
-  u64 st_found = 0, st_len = 0, st_steps = 0, st_sectors = 0, st_hits = 0;
-
-  // comp value of the character at (batch-wide) position p of the current query: the general path
-  auto comp_slow = [&](u64 p) -> u32
-  {
-    if(PACKED)
-    {
-      u64 rel = p - begin, wi = q * words_per_pattern + (rel >> 5);
-      if(wi != win.index) { win.word = __ldcs((const unsigned long long*)chars + wi); win.index = wi; }
-      return (u32)((win.word >> ((rel & 31) * 2)) & 3) + 1;
-    }
-    return c2c[win.get(chars, p)];
-  };
-  auto comp_at = [&](u64 p) -> u32
-  {
-    u64 off = tail_end - 1 - p;
-    if(off < (u64)tail_n) { return (u32)((tail >> (2 * off)) & 3) + 1; }
-    return comp_slow(p);
-  };
-  // pack the (up to) 32 characters that end at position `end_pos` (exclusive)
-  auto pack_tail = [&](u64 end_pos)
-  {
-    tail = 0; tail_n = 0; tail_end = end_pos;
-    if(!fast_pack) { return; }
-    if constexpr(PACKED)
-    {
-      u64 have = end_pos - begin, m = (have < 32 ? have : 32), r0 = have - m;             // pattern-relative [r0, r0 + m)
-      const unsigned long long* words = (const unsigned long long*)chars + q * words_per_pattern;
-      u32 sh = (u32)(r0 & 31) * 2;
-      u64 x = __ldcs(words + (r0 >> 5)) >> sh;
-      if(sh != 0 && (r0 & 31) + m > 32) { x |= __ldcs(words + (r0 >> 5) + 1) << (64 - sh); }
-      u64 r = __brevll(x);
-      r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
-      tail = (m < 32 ? r >> (2 * (32 - m)) : r);
-      tail_n = (u32)m;
-    }
-    else
-    {
-      for(u32 w = 0; w < 4; w++)
-      {
-        u64 pe = end_pos - 8 * w;
-        if(pe - begin < 8) { break; }
-        u64 addr = (u64)(chars + pe - 8); u32 a = (u32)(addr & 7);
-        const unsigned long long* base = (const unsigned long long*)(addr - a);
-        u64 word = __ldcs(base);
-        if(a != 0) { word = (word >> (8 * a)) | ((u64)__ldcs(base + 1) << (64 - 8 * a)); }
-        u32 good;
-        u32 r = pack8_reversed(word, &good);
-        tail |= (u64)r << (16 * w);
-        tail_n += good;
-        if(good < 8) { break; }
-      }
-    }
-  };
-
-  while(true)
-  {
-    // refill: all idle lanes at once, as soon as half the warp is idle (or nobody is working)
-    u32 dead = __ballot_sync(0xFFFFFFFFu, !live);
-    if(__popc(dead) >= refill_at)
-    {
-      u32 my = __popc(dead & ((1u << lane) - 1));
-      if(!live)
-      {
-        u64 cand = next + my;
-        if(cand < slice_end)
-        {
-          q = cand;
-          u64 b, e;
-          if(offsets != nullptr) { b = offsets[q] - char_base; e = offsets[q + 1] - char_base; }
-          else { b = q * fixed_length; e = b + fixed_length; }
-          begin = b; live = true; jump_mode = 1;
-          tail = 0; tail_n = 0; tail_end = e;
-          if(e == b || v.path_nodes == 0) { sp = 0; ep = v.path_nodes - 1; pos = b; }
-          else
-          {
-            pack_tail(e);
-            pos = e - 1;
-            bool used_table = false;
-            if(v.table_k > 0 && e - b >= (u64)v.table_k)
-            {
-              u64 idx = 0; bool ok = true;
-              if(tail_n >= (u32)v.table_k) { idx = tail & ((1ull << (2 * v.table_k)) - 1); }
-              else
-              {
-                for(int t = 0; t < v.table_k; t++)
-                {
-                  u32 c = comp_at(e - 1 - t);
-                  ok = ok && (c >= 1 && c <= 4);
-                  idx |= (u64)((c - 1) & 3) << (2 * t);
-                }
-              }
-              if(ok)
-              {
-                u64 r, je = 0;
-                if(v.table2 != nullptr) { ulonglong2 both = __ldg(v.table2 + idx); r = both.x; je = both.y; }
-                else { r = __ldg(v.table + idx); }
-                u64 len = r >> 40;
-                if(len != TABLE_ESCAPE)
-                {
-                  sp = r & M40; ep = sp + len - 1; pos = e - v.table_k; used_table = true;
-                  if(STATS) { st_hits++; }
-                  // Fused table: the jump entry of a singleton result came with the same 16-byte load, so the first
-                  // jump costs no probe.  Taken only when the whole path lies inside the packed tail and inside
-                  // the pattern; everything else is left to the main loop.
-                  u32 jl = (u32)(je >> 59);
-                  if(jl >= 2 && (u64)jl <= pos - b && (u32)v.table_k + jl <= tail_n)
-                  {
-                    u64 stored = ((je << 5) >> 5) >> v.jump_tbits;
-                    if((((tail >> (2 * v.table_k)) ^ stored) & ((1ull << (2 * jl)) - 1)) == 0)
-                    {
-                      sp = ep = (je & ((1ull << v.jump_tbits) - 1));
-                      pos -= jl;
-                      if(STATS) { st_steps += jl; }
-                    }
-                    else { jump_mode = 0; }                          // leaves the unary path: it dies within these steps
-                  }
-                }
-              }
-            }
-            if(!used_table)
-            {
-              u32 c = comp_at(pos);
-              sp = v.char_sp[c]; ep = v.char_ep[c];
-            }
-          }
-        }
-      }
-      next += __popc(dead);
-      if(next > slice_end) { next = slice_end; }
-    }
-    if(__ballot_sync(0xFFFFFFFFu, live) == 0)
-    {
-      if(next >= slice_end) { break; }
-      continue;
-    }
-
-    if(live)
-    {
-      if(!(range_empty(sp, ep) || pos == begin))
-      {
-        u32 sectors = 0;
-        bool done = false;
-        // Singleton range: try the jump table (one load for up to jump_k backward steps along a unary path).
-        // The table is chosen by what is left of the pattern, so that a path never overshoots its end: the long
-        // table (paths of up to jump_k steps) while at least jump_k characters remain, the short one (4) below that.
-        const u64* jump_from = nullptr;
-        if(v.jump != nullptr && jump_mode != 0 && sp == ep)
-        {
-          u64 left = pos - begin;
-          jump_from = (left >= (u64)v.jump_k ? v.jump : (left >= 4 ? v.jump_short : nullptr));
-        }
-        if(jump_from != nullptr)
-        {
-          u64 e = __ldg(jump_from + sp);
-          u32 len = (u32)(e >> 59);
-          if(STATS) { sectors++; }
-          if(len >= 2)
-          {
-            u64 stored = ((e << 5) >> 5) >> v.jump_tbits;
-            u64 off = tail_end - pos;
-            if(off + len > (u64)tail_n && fast_pack && tail_n == 32) { pack_tail(pos); off = 0; }
-            bool same = true;
-            if(off + len <= (u64)tail_n) { same = ((((tail >> (2 * off)) ^ stored) & ((1ull << (2 * len)) - 1)) == 0); }
-            else
-            {
-              for(u32 t = 0; t < len; t++)
-              {
-                u32 pc = comp_at(pos - 1 - t);
-                same = same && (pc == ((u32)(stored >> (2 * t)) & 3) + 1);
-              }
-            }
-            if(same)
-            {
-              sp = ep = (e & ((1ull << v.jump_tbits) - 1));
-              pos -= len; done = true;
-              if(STATS) { st_steps += len; }
-            }
-            else { jump_mode = 0; }                                  // it dies within these steps: the exact pair comes from single steps
-          }
-        }
-        if(!done && tail_end - pos >= (u64)tail_n && fast_pack && tail_n == 32) { pack_tail(pos); }   // next window of a long pattern
-        u32 c = (done ? 0 : comp_at(pos - 1));
-        if(!done && v.bwt2 != nullptr && pos - begin >= 2 && c >= 1 && c <= 4)
-        {
-          u32 c1 = comp_at(pos - 2);
-          if(c1 >= 1 && c1 <= 4 && lf2_range(v, sp, ep, c1, c, sp, ep, STATS ? &sectors : nullptr))
-          {
-            pos -= 2; done = true;
-            if(STATS) { st_steps += 2; }
-          }
-        }
-        if(!done)
-        {
-          pos--;
-          lf_range(v, sp, ep, c, sp, ep, STATS ? &sectors : nullptr);
-          if(STATS) { st_steps++; }
-        }
-        if(STATS) { st_sectors += sectors; }
-      }
-      if(range_empty(sp, ep) || pos == begin)
-      {
-        __stcs((unsigned long long*)sp_out + q, (unsigned long long)sp); __stcs((unsigned long long*)ep_out + q, (unsigned long long)ep);
-        if(STATS && !range_empty(sp, ep)) { st_found++; st_len += ep + 1 - sp; }
-        live = false;
-      }
-    }
-  }
-
-  if(STATS)
-  {
-    atomicAdd((ull*)&stats->found, (ull)st_found); atomicAdd((ull*)&stats->total_length, (ull)st_len);
-    atomicAdd((ull*)&stats->lf_steps, (ull)st_steps); atomicAdd((ull*)&stats->sector_probes, (ull)st_sectors);
-    atomicAdd((ull*)&stats->table_hits, (ull)st_hits);
-  }
-}
-
-/*
-  k-mer table.  Entry idx describes the string whose t-th character from the END is comp
-  ((idx >> 2t) & 3) + 1 and holds exactly what find() returns for it, early exit included: an
-  empty result keeps the uncanonicalised pair of the step where the search died, and such a pair
-  always has ep = sp - 1 (rank is monotone), so (sp, length) loses nothing.
-  The table is grown one character at a time: level j+1 is one LF step away from level j.
-*/
-__global__ void __launch_bounds__(256)
-table_init_kernel(const DevView v, ulonglong2* tmp)
-{
-  u32 idx = threadIdx.x;
-  if(idx < 4) { tmp[idx] = make_ulonglong2(v.char_sp[idx + 1], v.char_ep[idx + 1]); }
-}
-
-// level j (4^j entries in tmp[0, 4^j)) -> level j + 1 in place: slot idx | c << 2j
-__global__ void __launch_bounds__(256)
-table_extend_kernel(const DevView v, int j, ulonglong2* tmp)
-{
-  u64 total = 1ull << (2 * j);
-  for(u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x)
-  {
-    ulonglong2 r = tmp[idx];
-    #pragma unroll
-    for(u32 c = 4; c-- > 0; )
-    {
-      u64 sp = r.x, ep = r.y;
-      if(!range_empty(sp, ep)) { lf_range(v, sp, ep, c + 1, sp, ep); }
-      tmp[idx | ((u64)c << (2 * j))] = make_ulonglong2(sp, ep);
-    }
-  }
-}
-
-// last level: level k - 1 in tmp -> packed level k in table (k >= 2); for k == 1 pack tmp itself
-// With table2 != nullptr the fused form is written instead: next to each entry the jump-table entry of its sp when the
-// result is a single path node (find_kernel then takes the first jump without another probe).
-__global__ void __launch_bounds__(256)
-table_final_kernel(const DevView v, int k, const ulonglong2* tmp, u64* table, ulonglong2* table2)
-{
-  u64 total = (k == 1 ? 4 : 1ull << (2 * (k - 1)));
-  for(u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x)
-  {
-    ulonglong2 r = tmp[idx];
-    for(u32 c = 0; c < (k == 1 ? 1u : 4u); c++)
-    {
-      u64 sp = r.x, ep = r.y;
-      if(k > 1 && !range_empty(sp, ep)) { lf_range(v, sp, ep, c + 1, sp, ep); }
-      u64 len = ep + 1 - sp;
-      u64 entry = (len >= TABLE_ESCAPE || sp > M40) ? (TABLE_ESCAPE << 40) : (sp | (len << 40));
-      u64 slot = (k == 1 ? idx : (idx | ((u64)c << (2 * (k - 1)))));
-      if(table2 == nullptr) { table[slot] = entry; }
-      else { table2[slot] = make_ulonglong2(entry, (len == 1 && v.jump != nullptr) ? __ldg(v.jump + sp) : 0ull); }
-    }
-  }
-}
-
-//------------------------------------------------------------------------------
-// Kernels: construction of the two-step blocks from the one-step blocks
-//------------------------------------------------------------------------------
-
-// predecessor of node i by fast character c (0-based) from its fused sector, or false
-__device__ __forceinline__ bool pred_fast(const DevView& v, u64 i, u32 c, u64& pred)
-{
-  u64 b = i / BWT_W; u32 off = (u32)(i - b * BWT_W);
-  ulonglong4 q = ld256(v.bwt + b * 4 + c);
-  bool bit = (off < 64 ? (q.y >> off) & 1 : ((q.x >> 40) >> (off - 64)) & 1);
-  if(!bit) { return false; }
-  u32 j = popc_low88(q.y, (u32)(q.x >> 40), off);
-  pred = (q.z & M40) + popc_low88(q.w, (u32)(q.z >> 40), j + 1);
-  return true;
-}
-
-// 16-bit mask per node: bit c1 * 4 + c2 set iff the 2-path (c1, c2) into the node exists;
-// per block and label the number of set bits.
-__global__ void __launch_bounds__(128)
-two_step_mask_kernel(const DevView v, u64 n_blocks, unsigned short* m2, u32* blockpop)
-{
-  for(u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += (u64)gridDim.x * blockDim.x)
-  {
-    u32 count[16];
-    #pragma unroll
-    for(int p = 0; p < 16; p++) { count[p] = 0; }
-    for(u32 t = 0; t < BWT_W; t++)
-    {
-      u64 i = b * BWT_W + t;
-      if(i >= v.path_nodes) { break; }
-      u32 m = 0;
-      for(u32 c2 = 0; c2 < 4; c2++)
-      {
-        u64 j;
-        if(!pred_fast(v, i, c2, j)) { continue; }
-        for(u32 c1 = 0; c1 < 4; c1++)
-        {
-          u64 h;
-          if(pred_fast(v, j, c1, h)) { m |= 1u << (c1 * 4 + c2); }
-        }
-      }
-      m2[i] = (unsigned short)m;
-      #pragma unroll
-      for(int p = 0; p < 16; p++) { count[p] += (m >> p) & 1; }
-    }
-    #pragma unroll
-    for(int p = 0; p < 16; p++) { blockpop[(u64)p * n_blocks + b] = count[p]; }
-  }
-}
-
-// source node of every 2-path, label by label, in target order
-__global__ void __launch_bounds__(128)
-two_step_source_kernel(const DevView v, u64 n_blocks, const unsigned short* m2, const u64* blockcnt,
-                       const u64* label_base, u64* src)
-{
-  for(u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += (u64)gridDim.x * blockDim.x)
-  {
-    u64 x[16];
-    #pragma unroll
-    for(int p = 0; p < 16; p++) { x[p] = label_base[p] + blockcnt[(u64)p * n_blocks + b]; }
-    for(u32 t = 0; t < BWT_W; t++)
-    {
-      u64 i = b * BWT_W + t;
-      if(i >= v.path_nodes) { break; }
-      u32 m = m2[i];
-      if(m == 0) { continue; }
-      for(u32 c2 = 0; c2 < 4; c2++)
-      {
-        if(((m >> c2) & 0x1111u) == 0) { continue; }
-        u64 j;
-        if(!pred_fast(v, i, c2, j)) { continue; }
-        for(u32 c1 = 0; c1 < 4; c1++)
-        {
-          u32 p = c1 * 4 + c2;
-          u64 h;
-          if(((m >> p) & 1) && pred_fast(v, j, c1, h))
-          {
-            #pragma unroll
-            for(int q = 0; q < 16; q++) { if(q == (int)p) { src[x[q]] = h; x[q]++; } }
-          }
-        }
-      }
-    }
-  }
-}
-
-// consecutive sources of one label must be equal or differ by one node
-__global__ void __launch_bounds__(256)
-two_step_validate_kernel(const u64* src, const u64* label_base, u32* violations)
-{
-  for(int p = 0; p < 16; p++)
-  {
-    u64 lo = label_base[p], hi = label_base[p + 1];
-    for(u64 x = lo + (u64)blockIdx.x * blockDim.x + threadIdx.x; x + 1 < hi; x += (u64)gridDim.x * blockDim.x)
-    {
-      u64 d = src[x + 1] - src[x];
-      if(d > 1) { atomicAdd(violations, 1u); }
-    }
-  }
-}
-
-// one thread per (block, label): assemble the sector
-__global__ void __launch_bounds__(256)
-two_step_build_kernel(u64 path_nodes, u64 n_blocks, const unsigned short* m2, const u64* blockcnt,
-                      const u64* label_base, const u64* src, ulonglong4* out)
-{
-  u64 total = n_blocks * 16;
-  for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x)
-  {
-    u64 b = t >> 4; u32 p = (u32)(t & 15);
-    u64 x0 = blockcnt[(u64)p * n_blocks + b];
-    u64 blo = 0, bhi = 0;
-    for(u32 k = 0; k < BWT_W; k++)
-    {
-      u64 i = b * BWT_W + k;
-      if(i >= path_nodes) { break; }
-      u64 bit = (m2[i] >> p) & 1;
-      if(k < 64) { blo |= bit << k; } else { bhi |= bit << (k - 64); }
-    }
-    const u64* list = src + label_base[p];
-    u64 len = label_base[p + 1] - label_base[p];
-    u64 h0 = 0, wlo = 0, whi = 0;
-    if(len > 0)
-    {
-      // window bit k describes 2-path x0 - 1 + k: 1 iff it is the last 2-path of its source
-      h0 = (x0 == 0 ? list[0] : list[x0 - 1]);
-      for(u32 k = (x0 == 0 ? 1 : 0); k < 88; k++)
-      {
-        u64 x = x0 - 1 + k;
-        if(x + 1 >= len) { break; }
-        u64 bit = (list[x] != list[x + 1]) ? 1 : 0;
-        if(k < 64) { wlo |= bit << k; } else { whi |= bit << (k - 64); }
-      }
-    }
-    ulonglong4 q;
-    q.x = (x0 & M40) | (bhi << 40); q.y = blo;
-    q.z = (h0 & M40) | (whi << 40); q.w = wlo;
-    out[t] = q;
-  }
-}
-
-//------------------------------------------------------------------------------
-// Kernels: LF, count
-//------------------------------------------------------------------------------
-
-__global__ void __launch_bounds__(256)
-lf_kernel(const DevView v, const u64* __restrict__ sp, const u64* __restrict__ ep, const u8* __restrict__ comp,
-          u64 n, u64* __restrict__ osp, u64* __restrict__ oep)
-{
-  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
-  {
-    u64 a, b;
-    lf_range(v, sp[i], ep[i], comp[i], a, b);
-    osp[i] = a; oep[i] = b;
-  }
-}
-
-__global__ void __launch_bounds__(256)
-lf_node_kernel(const DevView v, const u64* __restrict__ nodes, u64 n, u64* __restrict__ out)
-{
-  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
-  {
-    out[i] = lf_node(v, nodes[i]);
-  }
-}
-
-// GCSA::LF_fast / LF_all, src/gcsa.cpp:742-798.  One thread per (range, comp).
-__global__ void __launch_bounds__(256)
-lf_multi_kernel(const DevView v, const u64* __restrict__ sp, const u64* __restrict__ ep, u64 n, int all_chars,
-                u64* __restrict__ out)
-{
-  u64 total = n * GCSA_B200_SIGMA;
-  for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x)
-  {
-    u64 i = t / GCSA_B200_SIGMA; u32 c = (u32)(t - i * GCSA_B200_SIGMA);
-    u64 a = 1, b = 0;                                        // Range::empty_range()
-    u32 last = (all_chars ? GCSA_B200_SIGMA - 2 : GCSA_B200_FAST_CHARS);
-    u64 s = sp[i], e = ep[i];
-    if(c >= 1 && c <= last && !range_empty(s, e))
-    {
-      if(s == e)                                             // single path node: follow set bits only
-      {
-        if(bwt_bit(v, s, c)) { lf_range(v, s, e, c, a, b); }
-      }
-      else { lf_range(v, s, e, c, a, b); }
-    }
-    out[t * 2] = a; out[t * 2 + 1] = b;
-  }
-}
-
-// SadaSparse::count, support.h:329-335
-__device__ __forceinline__ u64 sada_sparse_count(const DevView& v, u64 sp, u64 ep)
-{
-  u64 a = rv_rank(v.extra_filter, sp), b = rv_rank(v.extra_filter, ep + 1);
-  if(b <= a) { return 0; }
-  return (sv_select(v.extra_values, b) + 1) - (a > 0 ? sv_select(v.extra_values, a) + 1 : 0);
-}
-
-// SadaCount::count, support.h:255-258
-__device__ __forceinline__ u64 sada_count(const DevView& v, u64 sp, u64 ep)
-{
-  return (sv_select(v.redundant, ep + 1) - ep) - (sp > 0 ? sv_select(v.redundant, sp) + 1 - sp : 0);
-}
-
-// GCSA::count, src/gcsa.cpp:802-809
-__device__ __forceinline__ u64 count_range(const DevView& v, u64 sp, u64 ep)
-{
-  if(range_empty(sp, ep) || ep >= v.path_nodes) { return 0; }
-  u64 res = sada_sparse_count(v, sp, ep) + (ep + 1 - sp);
-  if(ep > sp) { res -= sada_count(v, sp, ep - 1); }
-  return res;
-}
-
-__global__ void __launch_bounds__(256)
-count_kernel(const DevView v, const u64* __restrict__ sp, const u64* __restrict__ ep, u64 n, u64* __restrict__ out)
-{
-  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
-  {
-    out[i] = count_range(v, sp[i], ep[i]);
-  }
-}
-
-//------------------------------------------------------------------------------
-// Kernels: countKMers (src/algorithms.cpp:364-421) as breadth-first frontier expansion
-//------------------------------------------------------------------------------
-
-// One thread per (frontier range, comp): the child range of processSubtree()'s expansion
-// (LF_fast for bases, LF_all with N), and whether it survives (non-empty).
-__global__ void __launch_bounds__(256)
-kmer_expand_kernel(const DevView v, const u64* __restrict__ sp, const u64* __restrict__ ep, u64 n, u32 chars,
-                   u64* __restrict__ csp, u64* __restrict__ cep, u64* __restrict__ flag)
-{
-  u64 total = n * chars;
-  for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x)
-  {
-    u64 i = t / chars; u32 c = (u32)(t - i * chars) + 1;
-    u64 s = sp[i], e = ep[i], a = 1, b = 0;
-    if(s == e) { if(bwt_bit(v, s, c)) { lf_range(v, s, e, c, a, b); } }      // gcsa.cpp:748-756, 774-789
-    else { lf_range(v, s, e, c, a, b); }
-    csp[t] = a; cep[t] = b; flag[t] = (range_empty(a, b) ? 0 : 1);
-  }
-}
-
-__global__ void __launch_bounds__(256)
-kmer_compact_kernel(const u64* __restrict__ csp, const u64* __restrict__ cep, const u64* __restrict__ flag,
-                    const u64* __restrict__ pos, u64 total, u64* __restrict__ sp, u64* __restrict__ ep)
-{
-  for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x)
-  {
-    if(flag[t]) { sp[pos[t]] = csp[t]; ep[pos[t]] = cep[t]; }
-  }
-}
-
-//------------------------------------------------------------------------------
-// Kernels: compareKMers (src/algorithms.cpp:505-616) -- the tries of two indexes in lockstep
-//------------------------------------------------------------------------------
-
-// One child range of LF_fast / LF_all (src/gcsa.cpp:742-798): empty input and a single path node
-// without the predecessor give Range::empty_range(); the general case gives LF() uncanonicalised.
-__device__ __forceinline__ void trie_child(const DevView& v, u64 s, u64 e, u32 c, u64& a, u64& b)
-{
-  a = 1; b = 0;
-  if(range_empty(s, e)) { return; }
-  if(s == e) { if(bwt_bit(v, s, c)) { lf_range(v, s, e, c, a, b); } }
-  else { lf_range(v, s, e, c, a, b); }
-}
-
-// states: 4 arrays (left sp, left ep, right sp, right ep) of `stride` entries each; kmers: 3 words per state or null.
-__global__ void __launch_bounds__(256)
-compare_expand_kernel(const DevView vl, const DevView vr, const u64* __restrict__ in, u64 n, const u64* __restrict__ in_kmer,
-                      u32 chars, u64 level, u64* __restrict__ out, u64* __restrict__ out_kmer, u64* __restrict__ flag)
-{
-  u64 total = n * chars;
-  for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x)
-  {
-    u64 i = t / chars; u32 c = (u32)(t - i * chars) + 1;
-    u64 la, lb, ra, rb;
-    trie_child(vl, in[i], in[n + i], c, la, lb);
-    trie_child(vr, in[2 * n + i], in[3 * n + i], c, ra, rb);
-    out[t] = la; out[total + t] = lb; out[2 * total + t] = ra; out[3 * total + t] = rb;
-    flag[t] = ((range_empty(la, lb) && range_empty(ra, rb)) ? 0 : 1);          // algorithms.cpp:514
-    if(out_kmer != nullptr)
-    {
-      u64 w0 = in_kmer[3 * i], w1 = in_kmer[3 * i + 1], w2 = in_kmer[3 * i + 2];
-      u64 bit = level * 3, word = bit >> 6, off = bit & 63, x = (u64)c << off, y = (off > 61 ? (u64)c >> (64 - off) : 0);   // KMerComparisonState::set, algorithms.cpp:451-457
-      if(word == 0) { w0 |= x; w1 |= y; } else if(word == 1) { w1 |= x; w2 |= y; } else { w2 |= x; }
-      out_kmer[3 * t] = w0; out_kmer[3 * t + 1] = w1; out_kmer[3 * t + 2] = w2;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256)
-compare_compact_kernel(const u64* __restrict__ child, const u64* __restrict__ child_kmer, const u64* __restrict__ flag,
-                       const u64* __restrict__ pos, u64 total, u64 next, u64* __restrict__ out, u64* __restrict__ out_kmer)
-{
-  for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x)
-  {
-    if(!flag[t]) { continue; }
-    u64 d = pos[t];
-    for(int f = 0; f < 4; f++) { out[f * next + d] = child[f * total + t]; }
-    if(out_kmer != nullptr) { for(int w = 0; w < 3; w++) { out_kmer[3 * d + w] = child_kmer[3 * t + w]; } }
-  }
-}
-
-// KMerSymmetricDifference::report, algorithms.cpp:488-500: side[i] = 0 shared, 1 left only, 2 right only.
-__global__ void __launch_bounds__(256)
-compare_classify_kernel(const u64* __restrict__ st, u64 n, ull* __restrict__ counts, u64* __restrict__ left_flag, u64* __restrict__ right_flag)
-{
-  ull mine[3] = { 0, 0, 0 };
-  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
-  {
-    u64 llen = st[n + i] + 1 - st[i], rlen = st[3 * n + i] + 1 - st[2 * n + i];
-    u32 side = (llen > 0 && rlen > 0 ? 0 : (llen > 0 ? 1 : 2));
-    mine[side]++;
-    if(left_flag != nullptr) { left_flag[i] = (side == 1); right_flag[i] = (side == 2); }
-  }
-  for(int k = 0; k < 3; k++)
-  {
-    ull x = mine[k];
-    for(int d = 16; d > 0; d >>= 1) { x += __shfl_down_sync(0xFFFFFFFFu, x, d); }
-    if((threadIdx.x & 31) == 0 && x > 0) { atomicAdd(counts + k, x); }
-  }
-}
-
-// Unique kmers as gcsa_b200_kmer_state records (8 words each).
-__global__ void __launch_bounds__(256)
-compare_emit_kernel(const u64* __restrict__ st, const u64* __restrict__ kmer, u64 n, u64 k, const u64* __restrict__ flag,
-                    const u64* __restrict__ pos, u64* __restrict__ records)
-{
-  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
-  {
-    if(!flag[i]) { continue; }
-    u64* r = records + 8 * pos[i];
-    r[0] = st[i]; r[1] = st[n + i]; r[2] = st[2 * n + i]; r[3] = st[3 * n + i]; r[4] = k;
-    r[5] = kmer[3 * i]; r[6] = kmer[3 * i + 1]; r[7] = kmer[3 * i + 2];
-  }
-}
-
-//------------------------------------------------------------------------------
-// Kernels: locate (src/gcsa.cpp:827-842, 880-896)
-//------------------------------------------------------------------------------
-
-// number of path nodes each range contributes (0 for empty / out-of-range ranges, gcsa.cpp:831)
-__global__ void __launch_bounds__(256)
-locate_lengths_kernel(u64 path_nodes, const u64* __restrict__ sp, const u64* __restrict__ ep, u64 n, u64* __restrict__ len)
-{
-  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
-  {
-    u64 s = sp[i], e = ep[i];
-    len[i] = ((range_empty(s, e) || e >= path_nodes) ? 0 : e + 1 - s);
-  }
-}
-
-// Last r in [0, n) with off[r] <= t (off[0] = 0), starting from a guess: gallop, then bisect.  With
-// ranges of similar length the guess is off by a few entries and the search costs 2-3 loads
-// instead of log2(n).
-__device__ __forceinline__ u64 owner_of(const u64* __restrict__ off, u64 n, u64 t, u64 guess)
-{
-  u64 g = (guess < n ? guess : n - 1), lo, hi;
-  if(__ldg(off + g) <= t)
-  {
-    lo = g;
-    u64 step = 1;
-    while(true)
-    {
-      u64 nxt = lo + step;
-      if(nxt > n - 1) { hi = n - 1; break; }
-      if(__ldg(off + nxt) <= t) { lo = nxt; step <<= 1; } else { hi = nxt - 1; break; }
-    }
-  }
-  else
-  {
-    u64 cur = g, step = 1;
-    while(true)
-    {
-      u64 nxt = (cur >= step ? cur - step : 0);
-      if(__ldg(off + nxt) <= t) { lo = nxt; hi = cur - 1; break; }
-      cur = nxt; step <<= 1;
-    }
-  }
-  while(lo < hi)
-  {
-    u64 mid = lo + (hi - lo + 1) / 2;
-    if(__ldg(off + mid) <= t) { lo = mid; } else { hi = mid - 1; }
-  }
-  return lo;
-}
-
-#define LOC_DIRECT 0xFFFFFFFFu          // steps marker: `first` holds the value itself (locate table, single-valued node)
-
-/*
-  One thread per (range, node): walk LF until a sampled node (locateInternal, gcsa.cpp:882-887),
-  remember (first sample, steps) and how many values the node stores (firstSample, gcsa.h:202-206;
-  the select on `samples` is an explicit offset array here).
-*/
-__global__ void __launch_bounds__(256)
-locate_walk_kernel(const DevView v, const u64* __restrict__ sp, const u64* __restrict__ node_off, u64 n, u64 items,
-                   u64* __restrict__ first, u32* __restrict__ steps_out, u64* __restrict__ cnt)
-{
-  const double ratio = (double)n / (double)items;
-  for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < items; t += (u64)gridDim.x * blockDim.x)
-  {
-    // range owning item t: last r with node_off[r] <= t
-    u64 lo = owner_of(node_off, n, t, (u64)((double)t * ratio));
-    u64 node = sp[lo] + (t - node_off[lo]);
-    u32 steps = 0;
-    u64 r;
-    if(v.loc64 != nullptr)
-    {
-      u64 e = __ldg(v.loc64 + node);
-      if(e >> 63) { first[t] = e & ~(1ull << 63); steps_out[t] = LOC_DIRECT; cnt[t] = 1; continue; }
-      r = e >> 24; steps = (u32)(e & 0xFFFFFFu);
-    }
-    else if(v.walk32 != nullptr)
-    {
-      u32 e = __ldg(v.walk32 + node);
-      while(!(e & 1)) { e = __ldg(v.walk32 + (e >> 1)); steps++; }
-      r = e >> 1;
-    }
-    else if(v.walk64 != nullptr)
-    {
-      u64 e = __ldg(v.walk64 + node);
-      while(!(e & 1)) { e = __ldg(v.walk64 + (e >> 1)); steps++; }
-      r = e >> 1;
-    }
-    else
-    {
-      while(!rv_get_rank(v.sampled, node, r)) { node = lf_node(v, node); steps++; }
-    }
-    u64 s0 = v.sample_start[r], s1 = v.sample_start[r + 1];
-    first[t] = s0; steps_out[t] = steps; cnt[t] = s1 - s0;
-  }
-}
-
-__global__ void __launch_bounds__(256)
-locate_fill_kernel(const DevView v, u64 items, const u64* __restrict__ first, const u32* __restrict__ steps,
-                   const u64* __restrict__ val_off, u64* __restrict__ raw)
-{
-  for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < items; t += (u64)gridDim.x * blockDim.x)
-  {
-    u64 s0 = first[t], o0 = val_off[t], c = val_off[t + 1] - o0;
-    if(steps[t] == LOC_DIRECT) { raw[o0] = s0; continue; }
-    for(u64 j = 0; j < c; j++) { raw[o0 + j] = v.stored_samples[s0 + j] + steps[t]; }   // gcsa.cpp:893
-  }
-}
-
-// segment boundaries of the raw values, per range: seg[r] = val_off[node_off[r]]
-__global__ void __launch_bounds__(256)
-locate_segments_kernel(const u64* __restrict__ node_off, const u64* __restrict__ val_off, u64 n, u64* __restrict__ seg)
-{
-  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (u64)gridDim.x * blockDim.x)
-  {
-    seg[i] = val_off[node_off[i]];
-  }
-}
-
-/*
-  Short ranges through the locate table, without the general pipeline: a range of at most LOC_SMALL path nodes
-  whose table entries all hold their start position directly (the usual case: a k-mer that occurs a few times)
-  is gathered, sorted and deduplicated in registers by one thread -- locate(range) of src/gcsa.cpp:827-842 with
-  removeDuplicates (utils.h:350-357) on up to eight values.  Pass 1 counts (and keeps the value of single-valued
-  ranges), an exclusive scan gives the CSR offsets, pass 2 writes.  Every other range (longer, or with a node whose
-  sampled ancestor stores several positions) is appended to a list and goes through the general pipeline below.
-*/
-#define LOC_SMALL 8
-#define LOC_TOP (1ull << 63)
-
-// start positions of the nodes [s, s + len), len <= LOC_SMALL, padded with ~0; false if an entry is not direct
-__device__ __forceinline__ bool locate_small_values(const DevView& v, u64 s, u32 len, u64 (&a)[LOC_SMALL])
-{
-  bool direct = true;
-  #pragma unroll
-  for(u32 j = 0; j < LOC_SMALL; j++)
-  {
-    u64 e = (j < len ? __ldg(v.loc64 + s + j) : ~0ull);
-    direct = direct && ((e >> 63) != 0);
-    a[j] = (j < len ? (e & ~LOC_TOP) : ~0ull);
-  }
-  return direct;
-}
-
-// odd-even transposition network over LOC_SMALL registers (the padding sorts to the end)
-__device__ __forceinline__ void locate_small_sort(u64 (&a)[LOC_SMALL])
-{
-  #pragma unroll
-  for(int r = 0; r < LOC_SMALL; r++)
-  {
-    #pragma unroll
-    for(int j = (r & 1); j + 1 < LOC_SMALL; j += 2)
-    {
-      u64 x = a[j], y = a[j + 1];
-      a[j] = (x < y ? x : y); a[j + 1] = (x < y ? y : x);
-    }
-  }
-}
-
-// Pass 1.  cnt[i] = number of distinct positions of range i (0 for the general ranges, which are appended to
-// glist); stash[i] = the position itself when there is exactly one, LOC_TOP | list slot for a general range.
-__global__ void __launch_bounds__(256)
-locate_small_count_kernel(const DevView v, const u64* __restrict__ sp, const u64* __restrict__ ep, u64 n,
-                          u64* __restrict__ cnt, u64* __restrict__ stash, u64* __restrict__ glist, ull* __restrict__ n_general)
-{
-  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
-  {
-    u64 s = sp[i], e = ep[i];
-    u64 c = 0, keep = 0;
-    bool general = false;
-    if(!(range_empty(s, e) || e >= v.path_nodes))                    // gcsa.cpp:831
-    {
-      u64 len = e + 1 - s;
-      if(len == 1)
-      {
-        u64 x = __ldg(v.loc64 + s);
-        if(x >> 63) { c = 1; keep = x & ~LOC_TOP; } else { general = true; }
-      }
-      else if(len <= LOC_SMALL)
-      {
-        u64 a[LOC_SMALL];
-        if(locate_small_values(v, s, (u32)len, a))
-        {
-          locate_small_sort(a);
-          c = 1;
-          #pragma unroll
-          for(u32 j = 1; j < LOC_SMALL; j++) { c += ((j < len && a[j] != a[j - 1]) ? 1 : 0); }
-          keep = a[0];
-        }
-        else { general = true; }
-      }
-      else { general = true; }
-    }
-    if(general)
-    {
-      u64 slot = atomicAdd(n_general, 1ull);
-      glist[slot] = i;
-      keep = LOC_TOP | slot;
-    }
-    cnt[i] = c; stash[i] = keep;
-  }
-}
-
-// the general ranges, in list order
-__global__ void __launch_bounds__(256)
-locate_general_gather_kernel(const u64* __restrict__ sp, const u64* __restrict__ ep, const u64* __restrict__ glist, u64 m,
-                             u64* __restrict__ gsp, u64* __restrict__ gep)
-{
-  for(u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += (u64)gridDim.x * blockDim.x)
-  {
-    u64 i = glist[k];
-    gsp[k] = sp[i]; gep[k] = ep[i];
-  }
-}
-
-// their counts, once the general pipeline has answered
-__global__ void __launch_bounds__(256)
-locate_general_counts_kernel(const u64* __restrict__ glist, const u64* __restrict__ goffs, u64 m, u64* __restrict__ cnt)
-{
-  for(u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += (u64)gridDim.x * blockDim.x)
-  {
-    cnt[glist[k]] = goffs[k + 1] - goffs[k];
-  }
-}
-
-// Pass 2: values[off[i], off[i + 1]) of every range.
-__global__ void __launch_bounds__(256)
-locate_small_fill_kernel(const DevView v, const u64* __restrict__ sp, const u64* __restrict__ ep, u64 n,
-                         const u64* __restrict__ off, const u64* __restrict__ stash,
-                         const u64* __restrict__ goffs, const u64* __restrict__ gvals, u64* __restrict__ values)
-{
-  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
-  {
-    u64 o = off[i], c = off[i + 1] - o;
-    if(c == 0) { continue; }
-    u64 keep = stash[i];
-    if(keep >> 63)
-    {
-      u64 g = goffs[keep & ~LOC_TOP];
-      for(u64 j = 0; j < c; j++) { values[o + j] = gvals[g + j]; }
-    }
-    else if(c == 1) { values[o] = keep; }
-    else
-    {
-      u64 s = sp[i], len = ep[i] + 1 - s;
-      u64 a[LOC_SMALL];
-      locate_small_values(v, s, (u32)len, a);
-      locate_small_sort(a);
-      values[o] = a[0];
-      u64 w = 1;
-      #pragma unroll
-      for(u32 j = 1; j < LOC_SMALL; j++)
-      {
-        if(j < len && a[j] != a[j - 1]) { values[o + w] = a[j]; w++; }
-      }
-    }
-  }
-}
-
-// removeDuplicates (utils.h:350-357) after the segmented sort: flag the first copy of each value
-__global__ void __launch_bounds__(256)
-locate_flag_kernel(const u64* __restrict__ sorted, const u64* __restrict__ seg, u64 n, u64 total, u64* __restrict__ flag)
-{
-  const double ratio = (double)n / (double)total;
-  for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x)
-  {
-    // segment of t: last r with seg[r] <= t
-    u64 lo = owner_of(seg, n, t, (u64)((double)t * ratio));
-    flag[t] = (t == seg[lo] || sorted[t] != sorted[t - 1]) ? 1 : 0;
-  }
-}
-
-__global__ void __launch_bounds__(256)
-locate_compact_kernel(const u64* __restrict__ sorted, const u64* __restrict__ flag, const u64* __restrict__ flag_scan,
-                      u64 total, u64* __restrict__ values, u64 capacity)
-{
-  for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x)
-  {
-    if(flag[t] && flag_scan[t] < capacity) { values[flag_scan[t]] = sorted[t]; }
-  }
-}
-
-__global__ void __launch_bounds__(256)
-locate_offsets_kernel(const u64* __restrict__ seg, const u64* __restrict__ flag_scan, u64 n, u64 total, u64 distinct,
-                      u64* __restrict__ out_offsets)
-{
-  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (u64)gridDim.x * blockDim.x)
-  {
-    u64 s = seg[i];
-    out_offsets[i] = (s >= total ? distinct : flag_scan[s]);
-  }
-}
-
-// Walk table for locate: one entry per path node, so that a step of locateInternal()
-// (sampled(i) + LF(i), gcsa.cpp:882-887) is a single load.
-template<class T>
-__global__ void __launch_bounds__(256)
-walk_table_kernel(const DevView v, T* table)
-{
-  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < v.path_nodes; i += (u64)gridDim.x * blockDim.x)
-  {
-    u64 r;
-    if(rv_get_rank(v.sampled, i, r)) { table[i] = (T)((r << 1) | 1); }
-    else { table[i] = (T)(lf_node(v, i) << 1); }
-  }
-}
-
-/*
-  Jump table for find(): for a path node i whose backward path is unary for len steps (every node on it has
-  exactly one predecessor character, a base), the entry holds those len characters and the node reached:
-  LF applied len times to the singleton range [i, i] gives exactly [target, target] when the pattern continues
-  with these characters (each step maps a singleton to a singleton), so one load replaces len backward steps.
-  Entry: len (5 bits) << 59 | characters (comp - 1, 2 bits each, first step lowest) << tbits | target (tbits).
-  Level 1 is computed from the fused blocks and the sparse lists, longer paths by appending level-1 entries.
-*/
-__global__ void __launch_bounds__(256)
-jump_init_kernel(const DevView v, u32 tbits, u64* __restrict__ one, u64* __restrict__ table)
-{
-  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < v.path_nodes; i += (u64)gridDim.x * blockDim.x)
-  {
-    u64 b = i / BWT_W; u32 off = (u32)(i - b * BWT_W);
-    const ulonglong4* line = v.bwt + b * 4;
-    u32 found = 0, which = 0; u64 target = 0;
-    #pragma unroll
-    for(int c = 0; c < 4; c++)
-    {
-      ulonglong4 q = ld256(line + c);
-      bool bit = (off < 64 ? (q.y >> off) & 1 : ((q.x >> 40) >> (off - 64)) & 1);
-      if(bit)
-      {
-        u32 j = popc_low88(q.y, (u32)(q.x >> 40), off);
-        target = (q.z & M40) + popc_low88(q.w, (u32)(q.z >> 40), j + 1);
-        which = (u32)c; found++;
-      }
-    }
-    bool sparse = false;
-    for(int slot = 0; slot < 3; slot++)
-    {
-      u64 r = sparse_rank(v.sparse_pos[slot], v.sparse_n[slot], i);
-      if(r < v.sparse_n[slot] && v.sparse_pos[slot][r] == i) { sparse = true; }
-    }
-    u64 e = 0;
-    if(found == 1 && !sparse) { e = (1ull << 59) | ((u64)which << tbits) | target; }
-    one[i] = e; table[i] = e;
-  }
-}
-
-// entries of length exactly j grow to j + 1 if the node they reach has a level-1 entry
-__global__ void __launch_bounds__(256)
-jump_extend_kernel(u64 n, u32 tbits, u32 j, const u64* __restrict__ one, u64* __restrict__ table)
-{
-  const u64 tmask = (1ull << tbits) - 1;
-  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
-  {
-    u64 e = table[i];
-    if((e >> 59) != j) { continue; }
-    u64 next = __ldg(one + (e & tmask));
-    if((next >> 59) == 0) { continue; }
-    u64 chars = ((e << 5) >> 5) >> tbits;
-    chars |= ((next >> tbits) & 3) << (2 * j);
-    table[i] = ((u64)(j + 1) << 59) | (chars << tbits) | (next & tmask);
-  }
-}
-
-// Locate table: the whole of locateInternal() (gcsa.cpp:880-896) per path node, precomputed from the walk
-// table.  A node whose sampled ancestor stores one start position holds that position + steps directly
-// (bit 63 set); otherwise the rank of the sampled node and the number of steps.  *overflow is set if a
-// field does not fit (the table is then dropped).
-__global__ void __launch_bounds__(256)
-locate_table_kernel(const DevView v, u64* table, int* overflow)
-{
-  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < v.path_nodes; i += (u64)gridDim.x * blockDim.x)
-  {
-    u64 r, steps = 0;
-    if(v.walk32 != nullptr)
-    {
-      u32 e = __ldg(v.walk32 + i);
-      while(!(e & 1)) { e = __ldg(v.walk32 + (e >> 1)); steps++; }
-      r = e >> 1;
-    }
-    else
-    {
-      u64 e = __ldg(v.walk64 + i);
-      while(!(e & 1)) { e = __ldg(v.walk64 + (e >> 1)); steps++; }
-      r = e >> 1;
-    }
-    u64 s0 = v.sample_start[r], s1 = v.sample_start[r + 1];
-    u64 value = v.stored_samples[s0] + steps;
-    if(steps >= (1ull << 24) || r >= (1ull << 39)) { *overflow = 1; table[i] = 0; }
-    else if(s1 - s0 == 1 && value < (1ull << 63)) { table[i] = (1ull << 63) | value; }
-    else { table[i] = (r << 24) | steps; }
-  }
-}
-
-//------------------------------------------------------------------------------
-// Kernels: LCP (src/lcp.cpp:152-200, 276-519)
-//------------------------------------------------------------------------------
-
-struct Pair64 { u64 first, second; };
-
-__device__ __forceinline__ u64 rmt_parent(const LcpView& l, u64 node, u64 level)
-{
-  u64 rel = node - l.offsets[level];
-  return l.offsets[level + 1] + (l.shift >= 0 ? rel >> l.shift : rel / l.branching);
-}
-__device__ __forceinline__ u64 rmt_first_sibling(const LcpView& l, u64 node, u64 level)
-{
-  u64 rel = node - l.offsets[level];
-  return node - (l.shift >= 0 ? rel & (l.branching - 1) : rel % l.branching);
-}
-__device__ __forceinline__ u64 rmt_last_sibling(const LcpView& l, u64 first_child, u64 level)
-{ u64 a = l.offsets[level + 1], b = first_child + l.branching; return (a < b ? a : b) - 1; }
-__device__ __forceinline__ u64 rmt_first_child(const LcpView& l, u64 node, u64 level) { return l.offsets[level - 1] + (node - l.offsets[level]) * l.branching; }
-__device__ __forceinline__ u64 rmt_last_child(const LcpView& l, u64 node, u64 level) { return rmt_last_sibling(l, rmt_first_child(l, node, level), level - 1); }
-__device__ __forceinline__ u64 rmt_level(const LcpView& l, u64 node) { u64 level = 0; while(l.offsets[level + 1] <= node) { level++; } return level; }
-
-template<bool OR_EQUAL> __device__ __forceinline__ bool sv_less(u64 a, u64 b) { return (OR_EQUAL ? a <= b : a < b); }
-
-// The sibling scans of psv / nsv (lcp.cpp:354-367, 410-423) read the one-byte values eight at a time:
-// 0x80 in every byte of x that is < thr (1 <= thr <= 256).
-__device__ __forceinline__ u64 bytes_below(u64 x, u32 thr)
-{
-  if(thr >= 256) { return 0x8080808080808080ull; }
-  u32 t = thr * 0x01010101u;
-  u32 lo = __vcmpltu4((u32)x, t), hi = __vcmpltu4((u32)(x >> 32), t);
-  return (((u64)hi << 32) | lo) & 0x8080808080808080ull;
-}
-
-// first / last index in [a, b] (a <= b) whose value is < thr; ~0 if there is none
-__device__ __forceinline__ u64 scan_up(const u8* __restrict__ data, u64 a, u64 b, u32 thr)
-{
-  if(thr == 0) { return ~0ull; }
-  const u64 w0 = a >> 3, w1 = b >> 3;
-  for(u64 w = w0; w <= w1; w++)
-  {
-    u64 m = bytes_below(__ldg((const unsigned long long*)data + w), thr);
-    if(w == w0) { m &= ~0ull << ((a & 7) * 8); }
-    if(w == w1) { m &= ~0ull >> ((7 - (b & 7)) * 8); }
-    if(m) { return w * 8 + ((u64)(__ffsll((long long)m) - 1) >> 3); }
-  }
-  return ~0ull;
-}
-
-__device__ __forceinline__ u64 scan_down(const u8* __restrict__ data, u64 a, u64 b, u32 thr)
-{
-  if(thr == 0) { return ~0ull; }
-  const u64 w0 = a >> 3, w1 = b >> 3;
-  for(u64 w = w1; ; w--)
-  {
-    u64 m = bytes_below(__ldg((const unsigned long long*)data + w), thr);
-    if(w == w0) { m &= ~0ull << ((a & 7) * 8); }
-    if(w == w1) { m &= ~0ull >> ((7 - (b & 7)) * 8); }
-    if(m) { return w * 8 + ((u64)(63 - __clzll((long long)m)) >> 3); }
-    if(w == w0) { break; }
-  }
-  return ~0ull;
-}
-
-// lcp.cpp:333-370
-template<bool OR_EQUAL>
-__device__ Pair64 lcp_psv(const LcpView& l, u64 to)
-{
-  Pair64 nf = { l.values, l.values };
-  if(to == 0 || to >= l.size) { return nf; }
-  u64 level = 0;
-  const u32 thr = (u32)l.data[to] + (OR_EQUAL ? 1 : 0);
-  u64 found = ~0ull;
-  while(to != l.values - 1)
-  {
-    u64 from = rmt_first_sibling(l, to, level);
-    found = (to > from ? scan_down(l.data, from, to - 1, thr) : ~0ull);
-    if(found != ~0ull) { break; }
-    to = rmt_parent(l, to, level); level++;
-  }
-  if(found == ~0ull) { return nf; }
-  while(level > 0)
-  {
-    u64 from = rmt_first_child(l, found, level); level--;
-    found = scan_down(l.data, from, rmt_last_sibling(l, from, level), thr);
-  }
-  Pair64 res = { found, l.data[found] };
-  return res;
-}
-
-// lcp.cpp:389-426
-template<bool OR_EQUAL>
-__device__ Pair64 lcp_nsv(const LcpView& l, u64 from)
-{
-  Pair64 nf = { l.values, l.values };
-  if(from + 1 >= l.size) { return nf; }
-  u64 level = 0;
-  const u32 thr = (u32)l.data[from] + (OR_EQUAL ? 1 : 0);
-  u64 found = ~0ull;
-  while(from != l.values - 1)
-  {
-    u64 to = rmt_last_sibling(l, from, level);
-    found = (from + 1 <= to ? scan_up(l.data, from + 1, to, thr) : ~0ull);
-    if(found != ~0ull) { break; }
-    from = rmt_parent(l, from, level); level++;
-  }
-  if(found == ~0ull) { return nf; }
-  while(level > 0)
-  {
-    from = rmt_first_child(l, found, level); level--;
-    found = scan_up(l.data, from, rmt_last_sibling(l, from, level), thr);
-  }
-  Pair64 res = { found, l.data[found] };
-  return res;
-}
-
-/*
-  lcp.cpp:448-513 rmq(sp, ep): leftmost minimum.  The reference collects the right-hand partial
-  sibling groups on a stack and pops them afterwards so that positions are visited left to right;
-  here the right-hand side keeps its own running minimum with "<=" (a later, more-left group wins
-  ties), which yields the same leftmost minimum without a stack.
-*/
-__device__ Pair64 lcp_rmq(const LcpView& l, u64 sp, u64 ep)
-{
-  Pair64 nf = { l.values, l.values };
-  if(sp > ep || ep >= l.size) { return nf; }
-  if(sp == ep) { Pair64 r = { sp, l.data[sp] }; return r; }
-
-  Pair64 res = { l.values, l.size };
-  Pair64 tail = { l.values, ~0ull };
-  u64 level = 0, left = sp, right = ep;
-  while(true)
-  {
-    u64 left_par = rmt_parent(l, left, level), right_par = rmt_parent(l, right, level);
-    if(left_par == right_par)
-    {
-      for(u64 i = left; i <= right; i++) { u64 x = l.data[i]; if(x < res.second) { res.first = i; res.second = x; } }
-      break;
-    }
-    u64 left_child = rmt_first_child(l, left_par, level + 1);
-    if(left != left_child)
-    {
-      u64 last_child = rmt_last_sibling(l, left_child, level);
-      for(u64 i = left; i <= last_child; i++) { u64 x = l.data[i]; if(x < res.second) { res.first = i; res.second = x; } }
-      left_par++;
-    }
-    u64 right_child = rmt_last_child(l, right_par, level + 1);
-    if(right != right_child)
-    {
-      u64 first_child = rmt_first_sibling(l, right_child, level);
-      // this group lies to the LEFT of everything already in tail: it wins ties; inside the group
-      // the leftmost minimum wins.
-      Pair64 grp = { l.values, ~0ull };
-      for(u64 i = first_child; i <= right; i++) { u64 x = l.data[i]; if(x < grp.second) { grp.first = i; grp.second = x; } }
-      if(grp.second <= tail.second) { tail = grp; }
-      right_par--;
-    }
-    if(left_par >= right_par)
-    {
-      if(left_par == right_par) { u64 x = l.data[left_par]; if(x < res.second) { res.first = left_par; res.second = x; } }
-      break;
-    }
-    left = left_par; right = right_par; level++;
-  }
-  if(tail.first < l.values && tail.second < res.second) { res = tail; }
-  if(res.first >= l.values) { return res; }
-
-  level = rmt_level(l, res.first);
-  while(level > 0)
-  {
-    res.first = rmt_first_child(l, res.first, level); level--;
-    while(l.data[res.first] != res.second) { res.first++; }
-  }
-  return res;
-}
-
-// LCPArray::parent(range), lcp.cpp:276-301 with nodeFor (lcp.h:163-175) and root (lcp.h:137)
-__device__ gcsa_b200_stnode lcp_parent(const LcpView& l, u64 sp, u64 ep)
-{
-  gcsa_b200_stnode out;
-  if(sp == 0 && ep == l.size - 1) { out.sp = 0; out.ep = l.size - 1; out.left_lcp = 0; out.right_lcp = 0; out.node_lcp = 0; return out; }
-  u64 left_lcp = l.data[sp];
-  u64 right_lcp = (ep + 1 < l.size ? l.data[ep + 1] : 0);
-  u64 node_lcp = (left_lcp > right_lcp ? left_lcp : right_lcp);
-  Pair64 left = { sp, left_lcp }, right = { ep + 1, right_lcp };
-  if(left_lcp == node_lcp)
-  {
-    left = lcp_psv<false>(l, sp);
-    if(left.first == l.values && left.second == l.values) { left.first = 0; left.second = 0; }
-  }
-  if(right_lcp == node_lcp)
-  {
-    right = lcp_nsv<false>(l, ep + 1);
-    if(right.first == l.values && right.second == l.values) { right.first = l.size; right.second = 0; }
-  }
-  out.sp = left.first; out.ep = right.first - 1; out.left_lcp = left.second; out.right_lcp = right.second; out.node_lcp = node_lcp;
-  return out;
-}
-
-__global__ void __launch_bounds__(256)
-parent_kernel(const LcpView l, const u64* __restrict__ sp, const u64* __restrict__ ep, u64 n, gcsa_b200_stnode* __restrict__ out)
-{
-  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
-  {
-    out[i] = lcp_parent(l, sp[i], ep[i]);
-  }
-}
-
-__global__ void __launch_bounds__(256)
-depth_kernel(const LcpView l, const u64* __restrict__ sp, const u64* __restrict__ ep, u64 n, u64* __restrict__ out)
-{
-  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
-  {
-    u64 s = sp[i], e = ep[i];
-    u64 res = GCSA_B200_UNKNOWN;
-    if(e + 1 - s > 1)                                                  // lcp.cpp:321
-    {
-      Pair64 r = lcp_rmq(l, s + 1, e);
-      if(!(r.first == l.values && r.second == l.values)) { res = r.second; }
-    }
-    out[i] = res;
-  }
-}
-
-__global__ void __launch_bounds__(256)
-lcp_sv_kernel(const LcpView l, int which, const u64* __restrict__ pos, u64 n, u64* __restrict__ opos, u64* __restrict__ oval)
-{
-  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
-  {
-    Pair64 r;
-    if(which == 0) { r = lcp_psv<false>(l, pos[i]); }
-    else if(which == 1) { r = lcp_psv<true>(l, pos[i]); }
-    else if(which == 2) { r = lcp_nsv<false>(l, pos[i]); }
-    else { r = lcp_nsv<true>(l, pos[i]); }
-    opos[i] = r.first; oval[i] = r.second;
-  }
-}
-
-__global__ void __launch_bounds__(256)
-lcp_rmq_kernel(const LcpView l, const u64* __restrict__ sp, const u64* __restrict__ ep, u64 n, u64* __restrict__ opos, u64* __restrict__ oval)
-{
-  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
-  {
-    Pair64 r = lcp_rmq(l, sp[i], ep[i]);
-    opos[i] = r.first; oval[i] = r.second;
-  }
-}
-
-//------------------------------------------------------------------------------
-// Kernel: MEM-style scan (LF + parent), BASELINE.json configs[4]
-//------------------------------------------------------------------------------
-
-/*
-  The driver loop over GCSA::LF (gcsa.h:155-162) and LCPArray::parent (lcp.cpp:276-301): extend the
-  match to the left while possible; when it cannot be extended, report it (if it grew since the last
-  report) and shorten it from the right by moving to the suffix-tree parent.  One pattern per lane;
-  patterns of very different lengths share a warp, so finished lanes are refilled from the warp's
-  slice exactly as in find_kernel.  WRITE = false counts the matches, WRITE = true stores them at
-  the offsets computed from the counts.
-*/
-// MODE 0: count the matches of each pattern.  MODE 1: write them at out_offsets (exact positions known).
-// MODE 2: count AND write the first `stride` matches of pattern q at scratch slot q * stride (one pass; the
-// few patterns with more matches are redone in MODE 1 over the id list `ids`).
-// JUMP: singleton ranges advance along the unary backward path of their node with one load (the jump tables of
-// find_kernel): the pattern is kept 2-bit packed, 32 characters at a time, and a path of up to 16 steps is one XOR
-// against it.  A path that the pattern leaves after t characters is followed by t + 1 single steps (the last of
-// which fails, as it must), so matches, depths and ranges are those of the single-step loop.
-template<int MODE, bool JUMP = false>
-__global__ void __launch_bounds__(256)
-mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const u64* __restrict__ offsets, u64 char_base,
-           u64 n, u64* __restrict__ counts, const u64* __restrict__ out_offsets, u64* __restrict__ matches,
-           const u64* __restrict__ ids, u64 stride, u32 parent_batch)
-{
-  constexpr bool WRITE = (MODE == 1);
-  __shared__ u8 c2c[256];
-  for(int i = threadIdx.x; i < 256; i += blockDim.x) { c2c[i] = v.char2comp[i]; }
-  __syncthreads();
-
-  const u32 lane = threadIdx.x & 31;
-  const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
-  const u64 per = (n + n_warps - 1) / n_warps;
-  u64 next = warp * per;
-  const u64 slice_end = (next + per < n ? next + per : n);
-  if(next >= n || v.path_nodes == 0) { return; }
-
-  u64 q = 0, sp = 0, ep = 0, depth = 0, pos = 0, begin = 0, emitted = 0, out_at = 0;
-  bool live = false, extended = false, need_parent = false;
-  u64 tail = 0, tail_end = 0; u32 tail_n = 0, skip = 0;     // JUMP: characters [tail_end - tail_n, tail_end) packed as in find_kernel
-
-  // pack the (up to) 32 characters that end at `end_pos` (exclusive), eight at a time, stopping at a non-base
-  auto pack_tail = [&](u64 end_pos)
-  {
-    tail = 0; tail_n = 0; tail_end = end_pos;
-    for(u32 w = 0; w < 4; w++)
-    {
-      u64 pe = end_pos - 8 * w;
-      if(pe - begin < 8) { break; }
-      u64 addr = (u64)(chars + pe - 8); u32 a = (u32)(addr & 7);
-      const unsigned long long* base = (const unsigned long long*)(addr - a);
-      u64 word = __ldcs(base);
-      if(a != 0) { word = (word >> (8 * a)) | ((u64)__ldcs(base + 1) << (64 - 8 * a)); }
-      u32 good;
-      u32 r = pack8_reversed(word, &good);
-      tail |= (u64)r << (16 * w);
-      tail_n += good;
-      if(good < 8) { break; }
-    }
-  };
-  auto comp_at = [&](u64 p) -> u32
-  {
-    if(JUMP)
-    {
-      u64 off = tail_end - 1 - p;
-      if(off < (u64)tail_n) { return (u32)((tail >> (2 * off)) & 3) + 1; }
-    }
-    return c2c[chars[p]];
-  };
-
-  while(true)
-  {
-    u32 dead = __ballot_sync(0xFFFFFFFFu, !live);
-    if(dead)
-    {
-      u32 my = __popc(dead & ((1u << lane) - 1));
-      if(!live)
-      {
-        u64 cand = next + my;
-        if(cand < slice_end)
-        {
-          q = (ids != nullptr ? ids[cand] : cand); live = true; need_parent = false;
-          begin = offsets[q] - char_base; pos = offsets[q + 1] - char_base;
-          sp = 0; ep = v.path_nodes - 1; depth = 0; extended = false; emitted = 0;
-          if(JUMP) { tail = 0; tail_n = 0; tail_end = pos; skip = 0; }
-          if(WRITE) { out_at = out_offsets[q]; }
-          if(MODE == 2) { out_at = q * stride; }
-        }
-      }
-      next += __popc(dead);
-      if(next > slice_end) { next = slice_end; }
-    }
-    if(__ballot_sync(0xFFFFFFFFu, live) == 0) { break; }
-
-    // Two phases, chosen per warp: backward steps for the lanes that can take one, or parent() for the lanes
-    // whose step failed.  parent() is several times longer than a step, so lanes waiting for it are held back
-    // until `parent_batch` of them wait (or nobody can step): the long path then runs with many lanes active
-    // instead of one or two.
-    u32 waiting = __ballot_sync(0xFFFFFFFFu, live && need_parent);
-    u32 stepping = __ballot_sync(0xFFFFFFFFu, live && !need_parent);
-    if(waiting != 0 && ((u32)__popc(waiting) >= parent_batch || stepping == 0))
-    {
-      if(live && need_parent)
-      {
-        gcsa_b200_stnode node = lcp_parent(l, sp, ep);
-        sp = node.sp; ep = node.ep; depth = node.node_lcp;
-        need_parent = false;
-      }
-      continue;
-    }
-    if(!live || need_parent) { continue; }
-
-    if(pos == begin)
-    {
-      if(depth > 0 && extended)
-      {
-        if(WRITE || (MODE == 2 && emitted < stride)) { u64* m = matches + 4 * (out_at + emitted); m[0] = 0; m[1] = depth; m[2] = sp; m[3] = ep; }
-        emitted++;
-      }
-      if(!WRITE) { counts[q] = emitted; }
-      live = false;
-      continue;
-    }
-    if(JUMP)
-    {
-      u64 left = pos - begin;
-      if(sp == ep && skip == 0 && left >= 4)
-      {
-        const u64* from = (left >= (u64)v.jump_k ? v.jump : v.jump_short);
-        u64 e = (from != nullptr ? __ldg(from + sp) : 0);
-        u32 len = (u32)(e >> 59);
-        if(len >= 2)
-        {
-          u64 off = tail_end - pos;
-          if(off + len > (u64)tail_n) { pack_tail(pos); off = 0; }
-          if(len <= tail_n)
-          {
-            u64 stored = ((e << 5) >> 5) >> v.jump_tbits;
-            u64 diff = ((tail >> (2 * off)) ^ stored) & ((1ull << (2 * len)) - 1);
-            if(diff == 0)
-            {
-              sp = ep = (e & ((1ull << v.jump_tbits) - 1));
-              depth += len; pos -= len; extended = true;
-              continue;
-            }
-            skip = ((u32)(__ffsll((long long)diff) - 1) >> 1) + 2;       // single steps up to and including the one that fails
-          }
-          else { skip = 9; }                                             // a non-base or the start of the pattern is near: eight single steps
-        }
-      }
-      if(skip > 0) { skip--; }
-    }
-    u64 nsp, nep;
-    lf_range(v, sp, ep, comp_at(pos - 1), nsp, nep);
-    if(!range_empty(nsp, nep)) { sp = nsp; ep = nep; depth++; pos--; extended = true; continue; }
-    if(depth == 0) { pos--; continue; }
-    if(extended)
-    {
-      if(WRITE || (MODE == 2 && emitted < stride)) { u64* m = matches + 4 * (out_at + emitted); m[0] = pos - begin; m[1] = depth; m[2] = sp; m[3] = ep; }
-      emitted++; extended = false;
-    }
-    need_parent = true;
-  }
-}
-
-// scratch (stride matches per pattern) -> CSR; patterns with more than `stride` matches are listed in `overflow`
-__global__ void __launch_bounds__(256)
-mem_gather_kernel(const ulonglong4* __restrict__ scratch, const u64* __restrict__ counts, const u64* __restrict__ out_offsets,
-                  u64 n, u64 stride, ulonglong4* __restrict__ matches, u64* __restrict__ overflow, ull* __restrict__ n_overflow)
-{
-  for(u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (u64)gridDim.x * blockDim.x)
-  {
-    u64 c = counts[q];
-    if(c > stride) { overflow[atomicAdd(n_overflow, 1ull)] = q; continue; }
-    const ulonglong4* src = scratch + q * stride;
-    ulonglong4* dst = matches + out_offsets[q];
-    for(u64 e = 0; e < c; e++) { dst[e] = src[e]; }
-  }
-}
-
-__global__ void __launch_bounds__(256)
-mem_count_overflow_kernel(const u64* __restrict__ counts, u64 n, u64 stride, ull* __restrict__ n_overflow)
-{
-  ull mine = 0;
-  for(u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (u64)gridDim.x * blockDim.x) { mine += (counts[q] > stride ? 1 : 0); }
-  for(int d = 16; d > 0; d >>= 1) { mine += __shfl_down_sync(0xFFFFFFFFu, mine, d); }
-  if((threadIdx.x & 31) == 0 && mine > 0) { atomicAdd(n_overflow, mine); }
-}
 
 //------------------------------------------------------------------------------
 // Host side: handles

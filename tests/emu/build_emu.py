@@ -59,8 +59,18 @@ def _functions(text, qualifier):
     return out
 
 
+def inline_device_headers(text):
+    """engine.cu is one translation unit that includes its kernels from csrc/device/*.cuh: paste them in."""
+    def paste(m):
+        with open(os.path.join(CSRC, m.group(1))) as f:
+            return "// ---- %s ----\n%s" % (m.group(1), f.read())
+    return re.sub(r'#include "(device/[a-z_]+\.cuh)"', paste, text)
+
+
 def translate(text):
-    text = text.replace("#include <cuda_runtime.h>", '#define EMU_DEFINE_SWITCH\n#include "cuda_emu.h"')
+    text = inline_device_headers(text)
+    text = text.replace("#include <cuda_runtime.h>", '#define EMU_DEFINE_SWITCH\n#include "cuda_emu.h"', 1)
+    text = text.replace("#include <cuda_runtime.h>", '#include "cuda_emu.h"')
     text = text.replace("#include <cub/cub.cuh>", "")
     text, n_asm = re.subn(r'asm volatile\("ld\.global\.nc\.v4\.u64[^;]*;[^;]*;', "r = *p;", text)
     assert n_asm == 1, "expected exactly one inline-PTX load in engine.cu, found %d" % n_asm
@@ -104,14 +114,16 @@ def translate(text):
 def build(force=False, verbose=False):
     os.makedirs(OUT, exist_ok=True)
     engine_cu = os.path.join(CSRC, "engine.cu")
+    device = [os.path.join(CSRC, "device", f) for f in sorted(os.listdir(os.path.join(CSRC, "device"))) if f.endswith(".cuh")]
     sources = [engine_cu, os.path.join(CSRC, "internal.h"), os.path.join(HERE, "cuda_emu.h"), os.path.abspath(__file__),
-               os.path.join(ROOT, "include", "gcsa2_b200.h")] + [os.path.join(CSRC, s) for s in HOST_SOURCES]
+               os.path.join(ROOT, "include", "gcsa2_b200.h")] + device + [os.path.join(CSRC, s) for s in HOST_SOURCES]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in sources):
         return LIB
     with open(engine_cu) as f:
         translated, kernels = translate(f.read())
     # the translated file sits in _build/, the relative includes of engine.cu are resolved against csrc/
-    translated = translated.replace('#include "../../include/gcsa2_b200.h"', '#include "%s"' % os.path.join(ROOT, "include", "gcsa2_b200.h"))
+    for relative in ('#include "../../include/gcsa2_b200.h"', '#include "../../../include/gcsa2_b200.h"'):
+        translated = translated.replace(relative, '#include "%s"' % os.path.join(ROOT, "include", "gcsa2_b200.h"))
     translated = translated.replace('#include "internal.h"', '#include "%s"' % os.path.join(CSRC, "internal.h"))
     engine_cpp = os.path.join(OUT, "engine_emu.cpp")
     with open(engine_cpp, "w") as f:
