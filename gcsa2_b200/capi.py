@@ -54,7 +54,8 @@ class FindStats(C.Structure):
 class VerifyReport(C.Structure):
     _fields_ = [("unique", C.c_uint64), ("failures", C.c_uint64), ("find_failures", C.c_uint64),
                 ("parent_failures", C.c_uint64), ("depth_failures", C.c_uint64), ("count_failures", C.c_uint64),
-                ("locate_failures", C.c_uint64), ("random_locate_failures", C.c_uint64), ("seconds", C.c_double)]
+                ("locate_failures", C.c_uint64), ("random_locate_failures", C.c_uint64), ("seconds", C.c_double),
+                ("engine_seconds", C.c_double)]
 
 
 class Built(C.Structure):

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -33,6 +34,19 @@ constexpr u64 CHUNK_LABELS = 4u << 20;        // labels per batch (bounds the ho
 
 inline bool rangeEmpty(u64 sp, u64 ep) { return (sp + 1 > ep + 1); }
 
+// Wall-clock time spent inside the engine's entry points (the rest of verifyIndex is host work).
+struct EngineClock
+{
+  double seconds = 0.0;
+  template<class F> int operator()(F&& call)
+  {
+    auto t0 = std::chrono::steady_clock::now();
+    int rc = call();
+    seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+  }
+};
+
 struct Malloced
 {
   u64* p = nullptr;
@@ -51,6 +65,18 @@ extern "C" int gcsa_b200_verify_index(const gcsa_b200_index* index, const gcsa_b
   }
   std::memset(report, 0, sizeof(*report));
   auto started = std::chrono::steady_clock::now();
+  EngineClock engine;
+  // GCSA_B200_VERIFY_DEBUG: host and engine seconds per stage on stderr
+  const bool debug = (std::getenv("GCSA_B200_VERIFY_DEBUG") != nullptr);
+  auto lap_start = started; double lap_engine = 0.0;
+  auto lap = [&](const char* what)
+  {
+    if(!debug) { return; }
+    auto now = std::chrono::steady_clock::now();
+    double total = std::chrono::duration<double>(now - lap_start).count();
+    std::fprintf(stderr, "verify: %-28s host %.3f s, engine %.3f s\n", what, total - (engine.seconds - lap_engine), engine.seconds - lap_engine);
+    lap_start = now; lap_engine = engine.seconds;
+  };
   const u64 k = (u64)kmer_length;
   const char* comp2char = "$ACGTN#";           // src/support.cpp:92
 
@@ -64,6 +90,7 @@ extern "C" int gcsa_b200_verify_index(const gcsa_b200_index* index, const gcsa_b
   group_start.push_back(n);
   const u64 unique = group_start.size() - 1;
   report->unique = unique;
+  lap("sort + groups");
 
   for(u64 base = 0; base < unique; base += CHUNK_LABELS)
   {
@@ -105,9 +132,10 @@ extern "C" int gcsa_b200_verify_index(const gcsa_b200_index* index, const gcsa_b
       }
     }
 
+    lap("patterns + expected");
     // find() -- algorithms.cpp:131-143
     std::vector<u64> sp(m + 1), ep(m + 1);
-    int rc = gcsa_b200_find_host(index, chars.data(), offsets.data(), m, sp.data(), ep.data());
+    int rc = engine([&] { return gcsa_b200_find_host(index, chars.data(), offsets.data(), m, sp.data(), ep.data()); });
     if(rc != 0) { return rc; }
     std::vector<uint8_t> alive(m, 1);
     for(u64 g = 0; g < m; g++)
@@ -115,6 +143,7 @@ extern "C" int gcsa_b200_verify_index(const gcsa_b200_index* index, const gcsa_b
       if(rangeEmpty(sp[g], ep[g])) { alive[g] = 0; report->find_failures++; }
     }
 
+    lap("find");
     // parent() and depth() -- algorithms.cpp:145-181
     if(lcp != nullptr)
     {
@@ -123,7 +152,7 @@ extern "C" int gcsa_b200_verify_index(const gcsa_b200_index* index, const gcsa_b
       std::vector<u64> a(ids.size() + 1), b(ids.size() + 1);
       for(u64 i = 0; i < ids.size(); i++) { a[i] = sp[ids[i]]; b[i] = ep[ids[i]]; }
       std::vector<gcsa_b200_stnode> parents(ids.size() + 1);
-      rc = gcsa_b200_parent_host(lcp, a.data(), b.data(), ids.size(), parents.data());
+      rc = engine([&] { return gcsa_b200_parent_host(lcp, a.data(), b.data(), ids.size(), parents.data()); });
       if(rc != 0) { return rc; }
 
       // query_res: drop characters from the right end until the range changes, all labels of a round in one batch
@@ -141,7 +170,7 @@ extern "C" int gcsa_b200_verify_index(const gcsa_b200_index* index, const gcsa_b
         }
         sub.push_back(0);
         std::vector<u64> s(todo.size() + 1), e(todo.size() + 1);
-        rc = gcsa_b200_find_host(index, sub.data(), sub_offsets.data(), todo.size(), s.data(), e.data());
+        rc = engine([&] { return gcsa_b200_find_host(index, sub.data(), sub_offsets.data(), todo.size(), s.data(), e.data()); });
         if(rc != 0) { return rc; }
         std::vector<u64> again;
         for(u64 i = 0; i < todo.size(); i++)
@@ -163,7 +192,7 @@ extern "C" int gcsa_b200_verify_index(const gcsa_b200_index* index, const gcsa_b
       }
       std::vector<u64> da(depth_ids.size() + 1), db(depth_ids.size() + 1), depth(depth_ids.size() + 1);
       for(u64 i = 0; i < depth_ids.size(); i++) { da[i] = parents[depth_ids[i]].sp; db[i] = parents[depth_ids[i]].ep; }
-      rc = gcsa_b200_depth_host(lcp, da.data(), db.data(), depth_ids.size(), depth.data());
+      rc = engine([&] { return gcsa_b200_depth_host(lcp, da.data(), db.data(), depth_ids.size(), depth.data()); });
       if(rc != 0) { return rc; }
       for(u64 i = 0; i < depth_ids.size(); i++)
       {
@@ -171,12 +200,13 @@ extern "C" int gcsa_b200_verify_index(const gcsa_b200_index* index, const gcsa_b
       }
     }
 
+    lap("parent + depth");
     // count() -- algorithms.cpp:183-200
     std::vector<u64> ids;
     for(u64 g = 0; g < m; g++) { if(alive[g]) { ids.push_back(g); } }
     std::vector<u64> a(ids.size() + 1), b(ids.size() + 1), counts(ids.size() + 1);
     for(u64 i = 0; i < ids.size(); i++) { a[i] = sp[ids[i]]; b[i] = ep[ids[i]]; }
-    rc = gcsa_b200_count_host(index, a.data(), b.data(), ids.size(), counts.data());
+    rc = engine([&] { return gcsa_b200_count_host(index, a.data(), b.data(), ids.size(), counts.data()); });
     if(rc != 0) { return rc; }
     {
       std::vector<u64> keep;
@@ -190,10 +220,11 @@ extern "C" int gcsa_b200_verify_index(const gcsa_b200_index* index, const gcsa_b
     }
     for(u64 i = 0; i < ids.size(); i++) { a[i] = sp[ids[i]]; b[i] = ep[ids[i]]; }
 
+    lap("count");
     // locate() -- algorithms.cpp:202-234
     std::vector<u64> loc_offsets(ids.size() + 1, 0);
     Malloced located;
-    rc = gcsa_b200_locate_host(index, a.data(), b.data(), ids.size(), loc_offsets.data(), &located.p);
+    rc = engine([&] { return gcsa_b200_locate_host(index, a.data(), b.data(), ids.size(), loc_offsets.data(), &located.p); });
     if(rc != 0) { return rc; }
     std::vector<u64> random_ids;                 // positions in ids whose locate() was right
     for(u64 i = 0; i < ids.size(); i++)
@@ -205,11 +236,12 @@ extern "C" int gcsa_b200_verify_index(const gcsa_b200_index* index, const gcsa_b
       if(got == want) { random_ids.push_back(i); }     // the reference still tries the random locate after a value mismatch
     }
 
+    lap("locate");
     // locate(range, 10) -- algorithms.cpp:236-274
     std::vector<u64> ra(random_ids.size() + 1), rb(random_ids.size() + 1), rnd_offsets(random_ids.size() + 1, 0);
     for(u64 i = 0; i < random_ids.size(); i++) { ra[i] = a[random_ids[i]]; rb[i] = b[random_ids[i]]; }
     Malloced randoms;
-    rc = gcsa_b200_locate_max_host(index, ra.data(), rb.data(), random_ids.size(), RANDOM_LOCATE_SIZE, rnd_offsets.data(), &randoms.p);
+    rc = engine([&] { return gcsa_b200_locate_max_host(index, ra.data(), rb.data(), random_ids.size(), RANDOM_LOCATE_SIZE, rnd_offsets.data(), &randoms.p); });
     if(rc != 0) { return rc; }
     for(u64 i = 0; i < random_ids.size(); i++)
     {
@@ -228,8 +260,10 @@ extern "C" int gcsa_b200_verify_index(const gcsa_b200_index* index, const gcsa_b
     }
   }
 
+  lap("locate(range, 10)");
   report->failures = report->find_failures + report->parent_failures + report->depth_failures + report->count_failures +
                      report->locate_failures + report->random_locate_failures;
   report->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - started).count();
+  report->engine_seconds = engine.seconds;
   return GCSA_B200_OK;
 }

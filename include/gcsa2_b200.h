@@ -237,7 +237,8 @@ typedef struct gcsa_b200_verify_report {
   uint64_t unique;                      /* distinct labels queried */
   uint64_t failures;                    /* sum of the stage counters below */
   uint64_t find_failures, parent_failures, depth_failures, count_failures, locate_failures, random_locate_failures;
-  double   seconds;
+  double   seconds;                     /* wall clock of the whole verification */
+  double   engine_seconds;              /* of which inside the engine's entry points (the rest is host work) */
 } gcsa_b200_verify_report;
 int gcsa_b200_verify_index(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, const uint64_t* keys,
                            const uint64_t* from, uint64_t n, int kmer_length, gcsa_b200_verify_report* report);
