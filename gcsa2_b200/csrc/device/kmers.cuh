@@ -89,17 +89,18 @@ compare_compact_kernel(const u64* __restrict__ child, const u64* __restrict__ ch
 __global__ void __launch_bounds__(256)
 compare_classify_kernel(const u64* __restrict__ st, u64 n, ull* __restrict__ counts, u64* __restrict__ left_flag, u64* __restrict__ right_flag)
 {
-  ull mine[3] = { 0, 0, 0 };
+  ull shared_n = 0, left_n = 0, right_n = 0;
   for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
   {
     u64 llen = st[n + i] + 1 - st[i], rlen = st[3 * n + i] + 1 - st[2 * n + i];
     u32 side = (llen > 0 && rlen > 0 ? 0 : (llen > 0 ? 1 : 2));
-    mine[side]++;
+    shared_n += (side == 0); left_n += (side == 1); right_n += (side == 2);
     if(left_flag != nullptr) { left_flag[i] = (side == 1); right_flag[i] = (side == 2); }
   }
+  #pragma unroll
   for(int k = 0; k < 3; k++)
   {
-    ull x = mine[k];
+    ull x = (k == 0 ? shared_n : (k == 1 ? left_n : right_n));
     for(int d = 16; d > 0; d >>= 1) { x += __shfl_down_sync(0xFFFFFFFFu, x, d); }
     if((threadIdx.x & 31) == 0 && x > 0) { atomicAdd(counts + k, x); }
   }

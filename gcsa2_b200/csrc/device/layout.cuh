@@ -226,19 +226,18 @@ __device__ __forceinline__ u64 lf_node(const DevView& v, u64 i)
 {
   u64 b = i / BWT_W; u32 off = (u32)(i - b * BWT_W);
   const ulonglong4* line = v.bwt + b * 4;
-  ulonglong4 q[4];
-  #pragma unroll
-  for(int c = 0; c < 4; c++) { q[c] = ld256(line + c); }
-  #pragma unroll
-  for(int c = 0; c < 4; c++)
+  // the four sectors of the line are requested together (named registers: an array of them ends up in local memory)
+  const ulonglong4 q0 = ld256(line), q1 = ld256(line + 1), q2 = ld256(line + 2), q3 = ld256(line + 3);
+  auto has = [off](const ulonglong4& q) -> bool { return (off < 64 ? (q.y >> off) & 1 : ((q.x >> 40) >> (off - 64)) & 1); };
+  auto pred = [off](const ulonglong4& q) -> u64
   {
-    bool bit = (off < 64 ? (q[c].y >> off) & 1 : ((q[c].x >> 40) >> (off - 64)) & 1);
-    if(bit)
-    {
-      u32 j = popc_low88(q[c].y, (u32)(q[c].x >> 40), off);
-      return (q[c].z & M40) + popc_low88(q[c].w, (u32)(q[c].z >> 40), j + 1);
-    }
-  }
+    u32 j = popc_low88(q.y, (u32)(q.x >> 40), off);
+    return (q.z & M40) + popc_low88(q.w, (u32)(q.z >> 40), j + 1);
+  };
+  if(has(q0)) { return pred(q0); }
+  if(has(q1)) { return pred(q1); }
+  if(has(q2)) { return pred(q2); }
+  if(has(q3)) { return pred(q3); }
   for(u32 c = GCSA_B200_FAST_CHARS + 1; c < GCSA_B200_SIGMA; c++)
   {
     int slot = sparse_slot(c);

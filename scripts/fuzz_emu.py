@@ -105,6 +105,22 @@ def main():
         osp, oep, _ = ora.find_batch(chars, offsets, threads=4)
         assert (sp == osp).all() and (ep == oep).all(), ("find", tag, np.flatnonzero((sp != osp) | (ep != oep))[:5])
 
+        # fixed-length batches through the host entry point, with and without host-side 2-bit packing
+        if sampler is not None and rounds % 4 == 0:
+            ln = int(rng.choice([20, 32, 33, 45, 64]))
+            fc, fo = sampler(70_000, ln, int(rng.integers(0, 1 << 30)))
+            fc = fc.copy()
+            rc, _ = synth.random_patterns(10_000, ln, seed=seed)
+            fc[: rc.size] = rc
+            if rng.random() < 0.5:
+                fc[int(rng.integers(0, fc.size))] = ord("N")
+            fsp0, fep0, _ = ora.find_batch(fc, fo, threads=4)
+            for packing in ("0", "2"):
+                os.environ["GCSA_B200_HOST_PACK"] = packing
+                fsp, fep = gpu.find_fixed_batch(fc, ln)
+                assert (fsp == fsp0).all() and (fep == fep0).all(), ("find_fixed", packing, tag)
+            os.environ.pop("GCSA_B200_HOST_PACK")
+
         # ranges: what find() produced plus arbitrary ones
         a = rng.integers(0, N, size=500).astype(np.uint64)
         b = np.minimum(a + rng.integers(0, 20, size=500).astype(np.uint64), np.uint64(N + 2))
