@@ -182,6 +182,39 @@ emu_switch:
 )");
 #endif
 
+// GCSA_EMU_SHUFFLE=seed: blocks of a launch, threads of a block (and the order in which waiting fibers are resumed)
+// run in a pseudo-random order instead of ascending, so that results which depend on the order in which threads
+// reach an atomic or a buffer -- arbitrary on the device -- show up as differences.
+inline unsigned long long& shuffleState()
+{
+  static thread_local unsigned long long state = 0;
+  return state;
+}
+inline bool shuffling()
+{
+  static const unsigned long long seed = envBytes("GCSA_EMU_SHUFFLE", 0);
+  if(seed != 0 && shuffleState() == 0) { shuffleState() = seed * 0x9E3779B97F4A7C15ull + 1; }
+  return seed != 0;
+}
+inline unsigned long long nextRandom()
+{
+  unsigned long long& s = shuffleState();
+  s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+  return s;
+}
+// i-th element of a pseudo-random permutation of [0, n): an affine map with a multiplier coprime to n
+struct Permutation
+{
+  unsigned long long n, mul, add;
+  explicit Permutation(unsigned long long n_) : n(n_), mul(1), add(0)
+  {
+    if(!shuffling() || n < 2) { return; }
+    add = nextRandom() % n;
+    do { mul = nextRandom() % n; } while(mul == 0 || std::__gcd(mul, n) != 1);
+  }
+  unsigned operator()(unsigned long long i) const { return (unsigned)((i * mul + add) % n); }
+};
+
 struct Warp
 {
   unsigned gen = 0, arrived = 0, alive = 0;
@@ -257,8 +290,10 @@ template<class F> void runBlockFibers(Block& b, unsigned threads, const F& f)
   while(b.alive > 0)
   {
     unsigned long before = b.progress;
-    for(unsigned t = 0; t < threads; t++)
+    const Permutation order(threads);
+    for(unsigned i = 0; i < threads; i++)
     {
+      const unsigned t = order(i);
       Fiber& fb = b.fibers[t];
       if(fb.finished) { continue; }
       b.current = &fb; coords.tid.x = t;
@@ -283,11 +318,16 @@ template<class F> void launch(const Cfg& cfg, const F& f, bool collectives)
   coords.gdim = cfg.grid; coords.bdim = cfg.blockdim;
   coords.tid = uint3{0, 0, 0}; coords.bid = uint3{0, 0, 0};
   static thread_local Block blk;
-  for(unsigned bx = 0; bx < cfg.grid.x; bx++)
+  const Permutation block_order(cfg.grid.x);
+  for(unsigned i = 0; i < cfg.grid.x; i++)
   {
-    coords.bid.x = bx;
+    coords.bid.x = block_order(i);
     if(collectives) { runBlockFibers(blk, cfg.blockdim.x, f); }
-    else { for(unsigned t = 0; t < cfg.blockdim.x; t++) { coords.tid.x = t; f(); } }
+    else
+    {
+      const Permutation thread_order(cfg.blockdim.x);
+      for(unsigned t = 0; t < cfg.blockdim.x; t++) { coords.tid.x = thread_order(t); f(); }
+    }
   }
   coords = saved;
 }
