@@ -434,9 +434,8 @@ def main():
     h_chars = torch.from_numpy(chars).pin_memory()
     h_sp = torch.empty(n, dtype=torch.int64).pin_memory(); h_ep = torch.empty(n, dtype=torch.int64).pin_memory()
 
-    # Host-side 2-bit packing before the H2D copy (gcsa2_b200/csrc/pack.cpp): GCSA_B200_HOST_PACK=threads forces it,
-    # 0 forbids it; by default the library times the packing of the first batch and keeps it only if the host packs
-    # faster than PCIe moves the raw bytes (decided during the warm-up steps below).
+    # Host-side 2-bit packing before the H2D copy (gcsa2_b200/csrc/pack.cpp): the host entry point shares the batch
+    # between a raw-copy thread and the packing threads (GCSA_B200_HOST_PACK=0 forbids packing, =N sets the threads).
     if world > 1 and not os.environ.get("GCSA_B200_HOST_PACK_THREADS"):
         os.environ["GCSA_B200_HOST_PACK_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
 
@@ -453,11 +452,14 @@ def main():
     e2e_ms = 1000.0 * (time.perf_counter() - t0) / args.steps
     barrier()
     e2e_same = bool((h_sp.numpy().view(np.uint64) == sp).all() and (h_ep.numpy().view(np.uint64) == ep).all())
+    import ctypes
     from gcsa2_b200 import capi
     pack_env = os.environ.get("GCSA_B200_HOST_PACK") or "auto"
-    pack_on = (capi.lib().gcsa_b200_internal_pack_state() == 1) if pack_env == "auto" else (int(pack_env) > 0)
+    c_packed, c_total = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+    capi.lib().gcsa_b200_internal_pack_share(ctypes.byref(c_packed), ctypes.byref(c_total))     # of the last e2e step
+    pack_share = c_packed.value / max(1, c_total.value)
     pack_threads = 0
-    if pack_on:
+    if pack_env != "0":
         pack_threads = int(pack_env) if pack_env != "auto" else int(os.environ.get("GCSA_B200_HOST_PACK_THREADS") or os.environ.get("OMP_NUM_THREADS") or os.cpu_count() or 1)
 
     # ---- work counters for the roofline (untimed; a 1 M sample through the stats kernel) ----
@@ -507,11 +509,11 @@ def main():
                            n * (length + 16) / 1e6, "more than" if n * (length + 16) > 126e6 else "LESS than (reduced run: not a valid timing)")},
             "found": total_found, "queries": total_q,
             "e2e": {"value": total_q / (e2e_ms / 1000.0), "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(n * 8 * ((length + 31) // 32)) if pack_on else int(n * length), "d2h_bytes_per_step": int(n * 16),
+                    "h2d_bytes_per_step": int(n * (pack_share * 8 * ((length + 31) // 32) + (1.0 - pack_share) * length)), "d2h_bytes_per_step": int(n * 16),
                     "api": "gcsa_b200_find_fixed_host (pinned host buffers, chunked H2D/kernel/D2H pipeline%s)" % (
-                        "; patterns 2-bit packed by %d host threads before the copy, %d B/query cross PCIe instead of %d" % (
-                            pack_threads, 8 * ((length + 31) // 32), length) if pack_threads > 0 else ""),
-                    "host_pack": {"policy": pack_env, "in_effect": pack_on, "threads": pack_threads},
+                        "; a raw-copy thread and %d packing threads share the batch: %.0f %% of the chunks crossed PCIe 2-bit packed, %d B/query instead of %d" % (
+                            pack_threads, 100.0 * pack_share, 8 * ((length + 31) // 32), length) if pack_threads > 0 else ""),
+                    "host_pack": {"policy": pack_env, "threads": pack_threads, "packed_chunks": c_packed.value, "chunks": c_total.value},
                     "matches_device_leg": e2e_same},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -27,6 +27,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -35,6 +36,7 @@
 #include <omp.h>
 #include <random>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -688,46 +690,37 @@ int gcsa_b200_find_fixed_batch(const gcsa_b200_index* index, const uint8_t* d_ch
 }
 
 /*
-  Host-buffer find: the batch is cut into chunks that are pipelined over three streams
-  (H2D of chunk i+1 overlaps the kernel of chunk i and the D2H of chunk i-1).
-*/
-// Host-side 2-bit packing in the host entry point of find() (pack.cpp): 4x fewer bytes over PCIe, which is what
-// bounds that entry point -- but only a gain when the host packs faster than the link moves the raw bytes
-// (measured on a 16-vCPU B200 box with the first packer: break-even at 16 threads).  Policy:
-//   GCSA_B200_HOST_PACK=0     never;   =N (> 0)  always, with N OpenMP threads;
-//   unset or "auto"           decided by measurement: the first large batch is packed with all OpenMP threads
-//                             (GCSA_B200_HOST_PACK_THREADS overrides the count) while the packing rate of its first
-//                             two chunks is timed; packing stays on iff the better of the two reaches
-//                             GCSA_B200_HOST_PACK_MIN_GBS (default 55 GB/s of pattern bytes: the ~50 GB/s the link
-//                             sustains plus a margin).  The decision is kept for the process.
-enum { PACK_UNKNOWN = -1, PACK_OFF = 0, PACK_ON = 1 };
-static std::atomic<int> g_pack_auto(PACK_UNKNOWN);
-struct PackPolicy { int threads; bool calibrate; };
+  Host-buffer find.  The batch is cut into chunks that are pipelined over a few streams (H2D of one chunk
+  overlaps the kernel of another and the D2H of a third).  What bounds this entry point is the H2D copy of the
+  patterns (32 pattern bytes in, 16 result bytes out per 32-mer), so fixed-length ACGT batches are also 2-bit packed
+  on the host (pack.cpp): 4x fewer bytes over the link -- for the chunks the host manages to pack.
 
-static PackPolicy hostPackPolicy()
+  Raw copying and packing SHARE the batch instead of one being chosen over the other: a helper thread feeds raw
+  chunks from the front of the batch to the copy engine (at most three copies queued ahead, so it sleeps while the
+  link is busy), the calling thread packs chunks from the back with its OpenMP team and sends those.  Whatever the
+  ratio of packing rate to link rate, the two meet in the middle: with packing as fast as the link the batch takes
+  0.57 of the raw transfer time, with packing twice as fast 0.4, with a slow host the helper thread simply does nearly
+  all of it (the packer only claims a chunk when enough raw chunks remain to cover the time it will need for it, so
+  its last chunk cannot become a tail).  A chunk with any character other than ACGT/acgt is sent raw.
+    GCSA_B200_HOST_PACK=0   no packing (one thread, raw chunks);   =N   N packing threads;
+    unset or "auto"         all OpenMP threads (GCSA_B200_HOST_PACK_THREADS overrides the count).
+*/
+static int hostPackThreads()
 {
   const char* e = std::getenv("GCSA_B200_HOST_PACK");
-  if(e != nullptr && *e != 0 && std::strcmp(e, "auto") != 0)
-  {
-    int v = std::atoi(e);
-    return PackPolicy{ (v < 0 ? 0 : v), false };
-  }
-  int state = g_pack_auto.load();
-  if(state == PACK_OFF) { return PackPolicy{ 0, false }; }
+  if(e != nullptr && *e != 0 && std::strcmp(e, "auto") != 0) { return std::max(0, std::atoi(e)); }
   const char* t = std::getenv("GCSA_B200_HOST_PACK_THREADS");
   int threads = (t != nullptr && *t != 0 ? std::atoi(t) : omp_get_max_threads());
-  return PackPolicy{ std::max(1, threads), state == PACK_UNKNOWN };
+  return std::max(1, threads);
 }
 
-static double hostPackMinRate()
+// Measurement hook (not part of the C ABI): chunks of the last host-buffer find of this process that went packed, and all.
+static std::atomic<unsigned long long> g_last_packed_chunks(0), g_last_chunks(0);
+extern "C" void gcsa_b200_internal_pack_share(unsigned long long* packed, unsigned long long* total)
 {
-  const char* e = std::getenv("GCSA_B200_HOST_PACK_MIN_GBS");
-  return (e != nullptr && *e != 0 ? std::atof(e) : 55.0) * 1e9;
+  if(packed) { *packed = g_last_packed_chunks.load(); }
+  if(total) { *total = g_last_chunks.load(); }
 }
-
-// Test / measurement hooks (not part of the C ABI): forget the automatic decision; report it.
-extern "C" void gcsa_b200_internal_pack_reset(void) { g_pack_auto.store(PACK_UNKNOWN); }
-extern "C" int gcsa_b200_internal_pack_state(void) { return g_pack_auto.load(); }
 
 static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const uint64_t* offsets, uint64_t fixed_length,
                     uint64_t n, uint64_t* sp, uint64_t* ep, gcsa_b200_find_stats* stats)
@@ -740,90 +733,138 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
   if(n == 0) { return 0; }
   DeviceGuard guard(index->device);
 
-  // Chunks of >= 256 k queries (8 MB of 32-mers: PCIe is at its streaming rate), at most ~24 per batch: the H2D
-  // engine is the busy resource from the first byte on, so what the pipeline adds to the transfer time is the kernel
-  // and the D2H of the LAST chunk -- the smaller the chunks, the smaller that tail (8 chunks: +0.45 ms on 6.4 ms).
-  // With host cores to spare, fixed-length batches are 2-bit packed on the host first (pack.cpp):
-  // 4x fewer bytes over PCIe, which is what bounds this entry point; a chunk containing any character
-  // other than ACGT/acgt goes through the byte path.  Finer chunks then, so that packing chunk i+1
-  // overlaps the transfers of chunk i.
-  const int STREAMS = 3;
-  const PackPolicy policy = hostPackPolicy();
-  const int pack_threads = policy.threads;
-  const bool pack = (pack_threads > 0 && fixed_length > 0 && offsets == nullptr && stats == nullptr &&
-                     n >= (policy.calibrate ? (1u << 20) : (1u << 16)));
-  bool calibrating = (pack && policy.calibrate);
-  double best_rate = 0.0; int timed_chunks = 0;
-  const u64 CHUNK = (pack ? std::max<u64>(1ull << 18, (n + 15) / 16) : std::max<u64>(1ull << 18, (n + 23) / 24));
+  const int pack_threads = hostPackThreads();
+  const bool pack = (pack_threads > 0 && fixed_length > 0 && offsets == nullptr && stats == nullptr && n >= (1u << 16));
+  // Chunks of >= 128 k queries (4 MB of 32-mers: the link is at its streaming rate), at most ~24 per batch (48 when
+  // two threads share it): the H2D engine is the busy resource from the first byte on, so what the pipeline adds to
+  // the transfer time is the kernel and the D2H of the LAST chunk -- the smaller the chunks, the smaller that tail.
+  const u64 CHUNK = (pack ? std::max<u64>(1ull << 17, (n + 47) / 48) : std::max<u64>(1ull << 18, (n + 23) / 24));
+  const u64 n_chunks = (n + CHUNK - 1) / CHUNK;
   const u64 words_per_pattern = (fixed_length + 31) / 32;
-  cudaStream_t streams[STREAMS];
-  for(int s = 0; s < STREAMS; s++) { CUDA_TRY(cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking)); }
+  const int RAW = 3, PACKED = 3;                         // streams of the raw path; streams + staging buffers of the packed path
+  cudaStream_t raw_streams[RAW] = { nullptr, nullptr, nullptr }, pack_streams[PACKED] = { nullptr, nullptr, nullptr };
+  cudaEvent_t raw_copied[RAW] = { nullptr, nullptr, nullptr }, staged[PACKED] = { nullptr, nullptr, nullptr };
+  u64* staging[PACKED] = { nullptr, nullptr, nullptr };
   FindStatsDev* d_stats = nullptr;
-  if(stats) { CUDA_TRY(cudaMalloc(&d_stats, sizeof(FindStatsDev))); CUDA_TRY(cudaMemset(d_stats, 0, sizeof(FindStatsDev))); }
-  u64* staging[STREAMS] = { nullptr, nullptr, nullptr };
-  cudaEvent_t staged[STREAMS] = { nullptr, nullptr, nullptr };
-  bool use_pack = pack;
-  if(use_pack)
+  int rc = 0;
+  for(int s = 0; s < RAW && rc == 0; s++)
   {
-    for(int s = 0; s < STREAMS; s++)
-    {
-      staging[s] = (u64*)index->takePinned(CHUNK * words_per_pattern * sizeof(u64));
-      if(staging[s] == nullptr || cudaEventCreateWithFlags(&staged[s], cudaEventDisableTiming) != cudaSuccess) { use_pack = false; }
-    }
+    if(cudaStreamCreateWithFlags(&raw_streams[s], cudaStreamNonBlocking) != cudaSuccess ||
+       cudaEventCreateWithFlags(&raw_copied[s], cudaEventDisableTiming) != cudaSuccess) { rc = fail(GCSA_B200_ERR_CUDA, "find_host: stream creation failed"); }
+  }
+  bool use_pack = (pack && rc == 0);
+  for(int s = 0; s < PACKED && use_pack; s++)
+  {
+    staging[s] = (u64*)index->takePinned(CHUNK * words_per_pattern * sizeof(u64));
+    if(staging[s] == nullptr || cudaStreamCreateWithFlags(&pack_streams[s], cudaStreamNonBlocking) != cudaSuccess ||
+       cudaEventCreateWithFlags(&staged[s], cudaEventDisableTiming) != cudaSuccess) { use_pack = false; cudaGetLastError(); }
+  }
+  if(stats && rc == 0)
+  {
+    if(cudaMalloc(&d_stats, sizeof(FindStatsDev)) != cudaSuccess || cudaMemset(d_stats, 0, sizeof(FindStatsDev)) != cudaSuccess) { rc = fail(GCSA_B200_ERR_CUDA, "find_host: out of device memory"); }
   }
 
-  int rc = 0;
-  u64 n_chunks = (n + CHUNK - 1) / CHUNK;
-  for(u64 c = 0; c < n_chunks && rc == 0; c++)
+  // One chunk through one stream: device buffers, H2D (raw bytes, or the packed words of `from`), kernel, D2H.
+  // `copied` (optional) is recorded right after the H2D copy.  Returns 0 or an error code; the message goes to *error.
+  auto enqueue = [&](u64 c, cudaStream_t st, const u64* from, cudaEvent_t copied, std::string* error) -> int
   {
-    const int slot = (int)(c % STREAMS);
-    cudaStream_t st = streams[slot];
     u64 q0 = c * CHUNK, q1 = std::min(n, q0 + CHUNK), m = q1 - q0;
-    u64 c0 = (offsets ? offsets[q0] : q0 * fixed_length), c1 = (offsets ? offsets[q1] : q1 * fixed_length), bytes = c1 - c0;
-    bool packed = false;
-    if(use_pack)
-    {
-      if(c >= (u64)STREAMS) { cudaEventSynchronize(staged[slot]); }          // the slot's previous copy has left the buffer
-      double t0 = (calibrating ? omp_get_wtime() : 0.0);
-      packed = (gcsa_b200_internal_pack_patterns(chars + c0, m, fixed_length, index->pack_code, index->pack_default ? 1 : 0,
-                                                 staging[slot], pack_threads) != 0);
-      if(calibrating && packed && m == CHUNK)
-      {
-        double secs = omp_get_wtime() - t0;
-        if(secs > 0.0) { best_rate = std::max(best_rate, (double)bytes / secs); }
-        if(++timed_chunks == 2)
-        {
-          calibrating = false;
-          bool keep = (best_rate >= hostPackMinRate());
-          g_pack_auto.store(keep ? PACK_ON : PACK_OFF);
-          if(!keep) { use_pack = false; }                                      // the rest of this batch goes as raw bytes
-        }
-      }
-    }
-    if(packed) { bytes = m * words_per_pattern * sizeof(u64); }
+    u64 c0 = (offsets ? offsets[q0] : q0 * fixed_length), c1 = (offsets ? offsets[q1] : q1 * fixed_length);
+    u64 bytes = (from != nullptr ? m * words_per_pattern * sizeof(u64) : c1 - c0);
     u8* d_chars = nullptr; u64* d_off = nullptr; u64* d_res = nullptr;
     cudaError_t e;
     if((e = cudaMallocAsync(&d_chars, bytes + 16, st)) != cudaSuccess ||
        (offsets && (e = cudaMallocAsync(&d_off, (m + 1) * sizeof(u64), st)) != cudaSuccess) ||
        (e = cudaMallocAsync(&d_res, 2 * m * sizeof(u64), st)) != cudaSuccess)
-    { rc = fail(GCSA_B200_ERR_NOMEM, std::string("find_host: ") + cudaGetErrorString(e)); break; }
-    if(packed)
     {
-      cudaMemcpyAsync(d_chars, staging[slot], bytes, cudaMemcpyHostToDevice, st);
-      cudaEventRecord(staged[slot], st);
+      *error = std::string("find_host: ") + cudaGetErrorString(e);
+      return GCSA_B200_ERR_NOMEM;
     }
+    if(from != nullptr) { cudaMemcpyAsync(d_chars, from, bytes, cudaMemcpyHostToDevice, st); }
     else if(bytes) { cudaMemcpyAsync(d_chars, chars + c0, bytes, cudaMemcpyHostToDevice, st); }
     if(offsets) { cudaMemcpyAsync(d_off, offsets + q0, (m + 1) * sizeof(u64), cudaMemcpyHostToDevice, st); }
-    rc = launchFind(index, d_chars, d_off, c0, fixed_length, m, d_res, d_res + m, d_stats, st, packed);
+    if(copied != nullptr) { cudaEventRecord(copied, st); }
+    int r = launchFind(index, d_chars, d_off, c0, fixed_length, m, d_res, d_res + m, d_stats, st, from != nullptr);
+    if(r != 0) { *error = g_last_error; }
     cudaMemcpyAsync(sp + q0, d_res, m * sizeof(u64), cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(ep + q0, d_res + m, m * sizeof(u64), cudaMemcpyDeviceToHost, st);
     cudaFreeAsync(d_chars, st); if(d_off) { cudaFreeAsync(d_off, st); } cudaFreeAsync(d_res, st);
-  }
-  cudaError_t err = cudaSuccess;
-  for(int s = 0; s < STREAMS; s++)
+    return r;
+  };
+
+  // Unclaimed chunks are [front, back): the raw path claims from the front, the packer from the back.
+  std::mutex claim;
+  u64 front = 0, back = n_chunks;
+  std::atomic<bool> failed(false);
+  auto claim_front = [&](u64* c) -> bool
   {
-    cudaError_t e = cudaStreamSynchronize(streams[s]);
-    if(e != cudaSuccess) { err = e; }
+    std::lock_guard<std::mutex> lock(claim);
+    if(front >= back || failed.load()) { return false; }
+    *c = front++; return true;
+  };
+  auto claim_back = [&](u64 reserve, u64* c) -> bool
+  {
+    std::lock_guard<std::mutex> lock(claim);
+    if(back - front <= reserve || failed.load()) { return false; }
+    *c = --back; return true;
+  };
+
+  // The raw path: at most RAW copies queued ahead of the copy engine.
+  int raw_rc = 0; std::string raw_error;
+  auto raw_path = [&]()
+  {
+    cudaSetDevice(index->device);
+    for(u64 k = 0; ; k++)
+    {
+      const int slot = (int)(k % RAW);
+      if(k >= (u64)RAW) { cudaEventSynchronize(raw_copied[slot]); }
+      u64 c;
+      if(!claim_front(&c)) { break; }
+      int r = enqueue(c, raw_streams[slot], nullptr, raw_copied[slot], &raw_error);
+      if(r != 0) { raw_rc = r; failed.store(true); break; }
+    }
+  };
+
+  u64 packed_chunks = 0;
+  if(rc == 0 && !use_pack) { raw_path(); }
+  else if(rc == 0)
+  {
+    std::thread helper(raw_path);
+    // The packer.  `rate` is what the last chunk achieved (bytes of patterns per second); a chunk is only claimed
+    // while the raw path still has at least as much work ahead as this chunk will take here.
+    const double link_rate = 50e9;
+    double rate = link_rate;
+    std::string pack_error;
+    for(u64 j = 0; ; j++)
+    {
+      const int slot = (int)(j % PACKED);
+      u64 reserve = (u64)std::min(1e6, std::ceil(link_rate / std::max(rate, 1e6))) + 1;
+      u64 c;
+      if(!claim_back(reserve, &c)) { break; }
+      if(j >= (u64)PACKED) { cudaEventSynchronize(staged[slot]); }          // the slot's previous copy has left the buffer
+      u64 q0 = c * CHUNK, m = std::min(n, q0 + CHUNK) - q0;
+      double t0 = omp_get_wtime();
+      bool ok = (gcsa_b200_internal_pack_patterns(chars + q0 * fixed_length, m, fixed_length, index->pack_code, index->pack_default ? 1 : 0,
+                                                  staging[slot], pack_threads) != 0);
+      double secs = omp_get_wtime() - t0;
+      if(ok && secs > 0.0) { rate = (double)(m * fixed_length) / secs; }
+      int r = enqueue(c, pack_streams[slot], ok ? staging[slot] : nullptr, staged[slot], &pack_error);
+      if(ok) { packed_chunks++; }
+      if(r != 0) { rc = fail(r, pack_error); failed.store(true); break; }
+    }
+    helper.join();
+  }
+  if(rc == 0 && raw_rc != 0) { rc = fail(raw_rc, raw_error); }
+  g_last_packed_chunks.store(packed_chunks); g_last_chunks.store(n_chunks);
+
+  cudaError_t err = cudaSuccess;
+  for(int s = 0; s < RAW; s++)
+  {
+    if(raw_streams[s]) { cudaError_t e = cudaStreamSynchronize(raw_streams[s]); if(e != cudaSuccess) { err = e; } }
+  }
+  for(int s = 0; s < PACKED; s++)
+  {
+    if(pack_streams[s]) { cudaError_t e = cudaStreamSynchronize(pack_streams[s]); if(e != cudaSuccess) { err = e; } }
   }
   if(stats && err == cudaSuccess && rc == 0)
   {
@@ -833,9 +874,14 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
     stats->sector_probes = h.sector_probes; stats->table_hits = h.table_hits;
   }
   if(d_stats) { cudaFree(d_stats); }
-  for(int s = 0; s < STREAMS; s++)
+  for(int s = 0; s < RAW; s++)
   {
-    cudaStreamDestroy(streams[s]);
+    if(raw_streams[s]) { cudaStreamDestroy(raw_streams[s]); }
+    if(raw_copied[s]) { cudaEventDestroy(raw_copied[s]); }
+  }
+  for(int s = 0; s < PACKED; s++)
+  {
+    if(pack_streams[s]) { cudaStreamDestroy(pack_streams[s]); }
     if(staged[s]) { cudaEventDestroy(staged[s]); }
     if(staging[s]) { index->givePinned(staging[s]); }
   }

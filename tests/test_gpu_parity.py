@@ -332,11 +332,12 @@ def test_host_packed_find_equals_byte_path(monkeypatch):
                     assert (int(psp[i]), int(pep[i])) == ora.find(pat)
 
 
-def test_host_pack_automatic_policy(monkeypatch):
-    """Without GCSA_B200_HOST_PACK (or with "auto") the host entry point times the packing of the first two chunks of
-    the first large batch and keeps packing only if the host is fast enough; the decision is remembered.  Both
-    outcomes (forced through the threshold) give the byte path's answers, also for the batch that was switched
-    half-way."""
+def test_host_pack_shares_the_batch_with_the_raw_path(monkeypatch):
+    """The host entry point of find() with packing enabled (the default): a helper thread sends raw chunks from the
+    front of the batch while the caller packs chunks from the back; which chunk goes which way depends on timing, the
+    answers do not -- equal to the unpacked path for every setting, with a chunk that cannot be packed (an N) in the
+    batch, and the share of packed chunks is reported."""
+    import ctypes
     from gcsa2_b200 import capi
     L = capi.lib()
     seq = synth.random_sequence(200_000, seed=43)
@@ -347,24 +348,28 @@ def test_host_pack_automatic_policy(monkeypatch):
     chars = chars.copy()
     rnd, _ = synth.random_patterns(n // 8, length, seed=6)
     chars[: rnd.size] = rnd
+    chars[(n - 5) * length + 3] = ord("N")                             # in the last chunk: the packer's first claim
     monkeypatch.setenv("GCSA_B200_HOST_PACK", "0")
     bsp, bep = gpu.find_fixed_batch(chars, length)
-    monkeypatch.setenv("GCSA_B200_HOST_PACK_THREADS", "2")
-    for setting, threshold, expected in (("auto", "0", 1), (None, "1000000", 0)):
+    packed, total = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+    L.gcsa_b200_internal_pack_share(ctypes.byref(packed), ctypes.byref(total))
+    assert packed.value == 0 and total.value >= 1
+    osp, oep, _ = orc.OracleGCSA(flat).find_batch(chars[-200_000 * length:], offsets[:200_001], threads=4)
+    assert (bsp[-200_000:] == osp).all() and (bep[-200_000:] == oep).all()
+    for setting, threads in (("auto", "2"), (None, "3"), ("4", None), ("1", None)):
         if setting is None:
             monkeypatch.delenv("GCSA_B200_HOST_PACK")
         else:
             monkeypatch.setenv("GCSA_B200_HOST_PACK", setting)
-        monkeypatch.setenv("GCSA_B200_HOST_PACK_MIN_GBS", threshold)
-        L.gcsa_b200_internal_pack_reset()
-        assert L.gcsa_b200_internal_pack_state() == -1
-        for _ in range(2):                                            # the deciding call, then one under the decision
+        if threads is not None:
+            monkeypatch.setenv("GCSA_B200_HOST_PACK_THREADS", threads)
+        for _ in range(2):
             sp, ep = gpu.find_fixed_batch(chars, length)
-            assert (sp == bsp).all() and (ep == bep).all(), (setting, threshold)
-            assert L.gcsa_b200_internal_pack_state() == expected
-    small = gpu.find_fixed_batch(chars[: 1000 * length], length)      # too small to decide anything
+            assert (sp == bsp).all() and (ep == bep).all(), (setting, threads)
+            L.gcsa_b200_internal_pack_share(ctypes.byref(packed), ctypes.byref(total))
+            assert total.value == 10 and packed.value <= total.value - 2          # the raw path always keeps the reserve
+    small = gpu.find_fixed_batch(chars[: 1000 * length], length)      # too small for the two-thread pipeline
     assert (small[0] == bsp[:1000]).all()
-    L.gcsa_b200_internal_pack_reset()
 
 
 def test_locate_tables_agree():
