@@ -750,7 +750,8 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
   for(int s = 0; s < RAW && rc == 0; s++)
   {
     if(cudaStreamCreateWithFlags(&raw_streams[s], cudaStreamNonBlocking) != cudaSuccess ||
-       cudaEventCreateWithFlags(&raw_copied[s], cudaEventDisableTiming) != cudaSuccess) { rc = fail(GCSA_B200_ERR_CUDA, "find_host: stream creation failed"); }
+       // blocking sync: the helper thread sleeps while the link is busy instead of spinning on a core the packers want
+       cudaEventCreateWithFlags(&raw_copied[s], cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) { rc = fail(GCSA_B200_ERR_CUDA, "find_host: stream creation failed"); }
   }
   bool use_pack = (pack && rc == 0);
   for(int s = 0; s < PACKED && use_pack; s++)

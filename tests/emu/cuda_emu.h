@@ -66,7 +66,7 @@ struct emu_stream_; typedef emu_stream_* cudaStream_t;
 struct emu_event_;  typedef emu_event_* cudaEvent_t;
 typedef void* cudaMemPool_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
-enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0 };
+enum { cudaStreamNonBlocking = 1, cudaEventBlockingSync = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0 };
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
 enum cudaLimit { cudaLimitMaxL2FetchGranularity = 5 };
 enum cudaMemPoolAttr { cudaMemPoolAttrReleaseThreshold = 4 };
