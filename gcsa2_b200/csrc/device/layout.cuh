@@ -41,8 +41,8 @@ struct DevView
   const ulonglong2* table2;            // fused form (replaces `table`): { that entry, the jump entry of sp if the range is a singleton, else 0 }
   const u32* walk32; const u64* walk64; // locate walk table: LF(i) << 1, or rank(sampled, i) << 1 | 1 for sampled nodes
   u32 default_alphabet;                // char2comp is exactly ACGT / acgt -> 1..4 for the bases (enables the SWAR pattern packing)
-  const u64* jump; u32 jump_k, jump_tbits;
-  const u64* jump_short;               // the same table cut at 4 steps: for the tail of a pattern that is shorter than the long path   // jump table: len << 59 | 2-bit chars << jump_tbits | target (see jump_extend_kernel)
+  const u64* jump; u32 jump_k, jump_tbits;   // jump table: len << 59 | 2-bit chars << jump_tbits | target (see jump_extend_kernel)
+  const u64* jump_short;               // the same table cut at 4 steps: for the tail of a pattern that is shorter than the long path
   const u64* loc64;                    // locate table: bit 63 | value for nodes with one start position, else rank of the sampled node << 24 | steps
   u8 char2comp[256];
 };
