@@ -1316,8 +1316,10 @@ int gcsa_b200_locate_into_host(const gcsa_b200_index* index, const uint64_t* sp,
   out_offsets[0] = 0;
   if(n == 0) { return 0; }
   DeviceGuard guard(index->device);
-  const int STREAMS = 2;
-  const u64 CHUNK = std::max<u64>(1ull << 18, (n + 7) / 8);
+  // Three streams: a stream's next upload queues behind its previous chunk's D2H, so with two streams the H2D engine
+  // idles for the length of a locate + D2H every other chunk; with three the uploads run back to back.
+  const int STREAMS = 3;
+  const u64 CHUNK = std::max<u64>(1ull << 18, (n + 11) / 12);
   const u64 n_chunks = (n + CHUNK - 1) / CHUNK;
   cudaStream_t streams[STREAMS];
   for(int s = 0; s < STREAMS; s++) { CUDA_TRY(cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking)); }
