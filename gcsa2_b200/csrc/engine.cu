@@ -827,10 +827,15 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
   };
 
   u64 packed_chunks = 0;
+  std::thread helper;
+  if(rc == 0 && use_pack)
+  {
+    try { helper = std::thread(raw_path); }
+    catch(...) { use_pack = false; }                      // no second thread to be had: everything goes raw from this one
+  }
   if(rc == 0 && !use_pack) { raw_path(); }
   else if(rc == 0)
   {
-    std::thread helper(raw_path);
     // The packer.  `rate` is what the last chunk achieved (bytes of patterns per second); a chunk is only claimed
     // while the raw path still has at least as much work ahead as this chunk will take here.
     const double link_rate = 50e9;
