@@ -18,7 +18,12 @@ kmer_expand_kernel(const DevView v, const u64* __restrict__ sp, const u64* __res
   {
     u64 i = t / chars; u32 c = (u32)(t - i * chars) + 1;
     u64 s = sp[i], e = ep[i], a = 1, b = 0;
-    if(s == e) { if(bwt_bit(v, s, c)) { lf_range(v, s, e, c, a, b); } }      // gcsa.cpp:748-756, 774-789
+    if(s == e)                                                                // gcsa.cpp:748-756, 774-789
+    {
+      // a single path node: the bit test and the step read the same sector -- one load, not two
+      if(c <= GCSA_B200_FAST_CHARS) { u64 p; if(pred_fast(v, s, c - 1, p)) { a = b = p; } }
+      else if(bwt_bit(v, s, c)) { lf_range(v, s, e, c, a, b); }
+    }
     else { lf_range(v, s, e, c, a, b); }
     csp[t] = a; cep[t] = b; flag[t] = (range_empty(a, b) ? 0 : 1);
   }
@@ -44,7 +49,11 @@ __device__ __forceinline__ void trie_child(const DevView& v, u64 s, u64 e, u32 c
 {
   a = 1; b = 0;
   if(range_empty(s, e)) { return; }
-  if(s == e) { if(bwt_bit(v, s, c)) { lf_range(v, s, e, c, a, b); } }
+  if(s == e)
+  {
+    if(c <= GCSA_B200_FAST_CHARS) { u64 p; if(pred_fast(v, s, c - 1, p)) { a = b = p; } }      // one sector: bit and step
+    else if(bwt_bit(v, s, c)) { lf_range(v, s, e, c, a, b); }
+  }
   else { lf_range(v, s, e, c, a, b); }
 }
 
