@@ -20,7 +20,13 @@
   * samples/select (gcsa.h:235-236) is replaced by an explicit start-offset array per sampled node.
   * sparse characters ($, N, #; sparse_bwt of gcsa.h:221-223) are sorted position lists.
   * optional k-mer table: find() results of all 4^k ACGT strings of length k, 8 bytes each
-    (sp in 40 bits, range length in 24 bits; an empty result always has ep = sp - 1).
+    (sp in 40 bits, range length in 24 bits; an empty result always has ep = sp - 1); in its fused
+    form 16 bytes: the same entry and the jump-table entry of its path node.
+  * optional per-node tables: jump tables for find() (the unary backward path of a node, up to 16 and up
+    to 4 steps), walk / locate tables for locate().
+
+  This file is the host side (handles, construction of the layout, C ABI entry points and their
+  pipelines); the kernels are in device/*.cuh, included below in dependency order.
 */
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
