@@ -73,11 +73,13 @@ def test_mem_scan_scratch_paths(monkeypatch):
     seq = synth.random_sequence(100_000, seed=5)
     graph, sites, alt = synth.snp_graph(seq, seed=5, snp_rate=0.01)
     flat, flcp, _ = build_index(graph, 16, 3)
-    chars, offsets = synth.mixed_length_patterns(seq, sites, alt, 20_000, 16, 256, seed=11, error_rate=0.10)
+    import helpers
+    n_patterns = 8_000 if helpers.EMULATED else 20_000                # the emulated run is the slowest test of the CPU suite
+    chars, offsets = synth.mixed_length_patterns(seq, sites, alt, n_patterns, 16, 256, seed=11, error_rate=0.10)
     index, lcp = orc.OracleGCSA(flat), orc.OracleLCP(flcp)
     ooffs, ovals, _ = orc.mem_batch(index, lcp, chars, offsets, threads=8)
     counts = np.diff(ooffs.astype(np.int64))
-    assert (counts > 16).sum() > 100 and (counts <= 4).sum() > 100
+    assert (counts > 16).sum() > 40 and (counts <= 4).sum() > 40
     gpu, glcp = GCSA(flat, kmer_table_k=0), LCPArray(flcp)
     for stride, jump in (("16", "0"), ("4", "0"), ("1", "0"), ("0", "0"), ("4", "1"), ("0", "1")):
         monkeypatch.setenv("GCSA_B200_MEM_STRIDE", stride)
