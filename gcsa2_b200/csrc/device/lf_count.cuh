@@ -44,7 +44,8 @@ lf_multi_kernel(const DevView v, const u64* __restrict__ sp, const u64* __restri
     {
       if(s == e)                                             // single path node: follow set bits only
       {
-        if(bwt_bit(v, s, c)) { lf_range(v, s, e, c, a, b); }
+        if(c <= GCSA_B200_FAST_CHARS) { u64 p; if(pred_fast(v, s, c - 1, p)) { a = b = p; } }   // bit and step from one sector
+        else if(bwt_bit(v, s, c)) { lf_range(v, s, e, c, a, b); }
       }
       else { lf_range(v, s, e, c, a, b); }
     }
