@@ -27,8 +27,8 @@ class _Stream:
     cuda_stream = 0
 
 
-def test_bench_line_on_the_emulated_engine(monkeypatch, capsys):
-    import bench
+def host_stand_ins(monkeypatch):
+    """The emulated engine behind capi.lib() and torch.cuda replaced by host stand-ins (device memory is host memory)."""
     from emu import build_emu
     from gcsa2_b200 import capi
     emulated = capi._bind(ctypes.CDLL(build_emu.build()))
@@ -43,6 +43,12 @@ def test_bench_line_on_the_emulated_engine(monkeypatch, capsys):
     real_empty, real_tensor = torch.empty, torch.tensor
     monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{x: y for x, y in k.items() if x != "device"}))
     monkeypatch.setattr(torch, "tensor", lambda *a, **k: real_tensor(*a, **{x: y for x, y in k.items() if x != "device"}))
+    return build_emu
+
+
+def test_bench_line_on_the_emulated_engine(monkeypatch, capsys):
+    import bench
+    build_emu = host_stand_ins(monkeypatch)
     monkeypatch.setenv("GCSA_B200_HOST_PACK_THREADS", "2")
     monkeypatch.delenv("GCSA_B200_HOST_PACK", raising=False)         # the default: raw copies and packing share the batch
     monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "2", "--warmup", "1", "--ref-mbp", "0.2", "--queries", "1100000",
@@ -78,3 +84,24 @@ def test_smoke_on_the_emulated_engine(monkeypatch, capsys):
     monkeypatch.setattr(capi, "_lib", capi._bind(ctypes.CDLL(build_emu.build())))
     entry.smoke()
     assert "smoke ok" in capsys.readouterr().out
+
+
+def test_bench_ops_on_the_emulated_engine(monkeypatch, capsys, tmp_path):
+    """scripts/bench_ops.py (every operation on the variation-graph config, next to the CPU oracle) at a small size."""
+    import importlib.util
+    import os
+    host_stand_ins(monkeypatch)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_ops", os.path.join(root, "scripts", "bench_ops.py"))
+    bench_ops = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench_ops)
+    out = str(tmp_path / "ops.json")
+    monkeypatch.setattr(sys, "argv", ["bench_ops.py", "--mbp", "0.1", "--queries", "20000", "--steps", "1", "--cpu-sample", "5000",
+                                      "--kmer-table-k", "8", "--ops", "count,locate,parent,mem,kmers,compare", "--out", out])
+    bench_ops.main()
+    with open(out) as f:
+        rows = json.load(f)
+    names = " | ".join(r["op"] for r in rows)
+    for expected in ("find", "count", "locate", "parent", "depth", "GCSA_B200_MEM_JUMP=0", "GCSA_B200_MEM_JUMP=1", "countKMers(k=12)", "compareKMers(k=16)"):
+        assert expected in names, (expected, names)
+    assert all(r["parity_on_sample"] for r in rows), [r["op"] for r in rows if not r["parity_on_sample"]]
