@@ -26,6 +26,25 @@ def shard_patterns(chars, offsets, rank, world):
     return chars[c0:c1], (offsets[q0:q1 + 1] - offsets[q0]).astype(np.uint64), (q0, q1)
 
 
+def shard_patterns_by_length(chars, offsets, rank, world):
+    """Shard of a batch of patterns of very different lengths (BASELINE.json configs[4]: 16-256 bp): the patterns
+    are ordered by length and dealt round-robin, so every rank gets the same mix of lengths and the same number of
+    characters to within one pattern per length class.  Returns (chars, offsets, ids): the rank's patterns packed
+    contiguously in increasing id order, and their indexes in the original batch (for scattering the results back)."""
+    offsets = np.asarray(offsets, dtype=np.uint64)
+    lengths = np.diff(offsets.astype(np.int64))
+    order = np.argsort(lengths, kind="stable")
+    ids = np.sort(order[int(rank)::int(world)])
+    mine = lengths[ids]
+    out_offsets = np.zeros(ids.size + 1, dtype=np.uint64)
+    out_offsets[1:] = np.cumsum(mine)
+    # gather the characters of the selected patterns: positions offsets[id] + (0 .. length - 1)
+    starts = np.repeat(offsets[ids].astype(np.int64) - out_offsets[:-1].astype(np.int64), mine)
+    index = starts + np.arange(int(out_offsets[-1]), dtype=np.int64)
+    out_chars = np.asarray(chars)[index] if index.size else np.zeros(1, dtype=np.uint8)
+    return out_chars, out_offsets, ids
+
+
 def find_counters(sp, ep, occurrences=0):
     """Per-shard result counters of a find() batch (what a caller aggregates: query_gcsa.cpp:98-103)."""
     sp = np.asarray(sp, dtype=np.uint64); ep = np.asarray(ep, dtype=np.uint64)

@@ -63,3 +63,25 @@ def test_two_rank_gloo_shard_and_gather(tmp_path):
     mp.spawn(worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     ok = np.load(os.path.join(str(tmp_path), "ok.npy"))
     assert ok[0] == 1 and ok[1] == 1 and ok[2] == 1501 and 1001 <= ok[3] <= 1501
+
+
+def test_shard_by_length_gives_every_rank_the_same_mix():
+    """configs[4] (patterns of 16-256 bp): the shards cover the batch exactly once, hold the right characters, and
+    carry the same number of characters to within one pattern per rank."""
+    from gcsa2_b200.dist import shard_patterns_by_length
+    rng = np.random.default_rng(5)
+    lengths = rng.integers(16, 257, size=5003)
+    lengths[:7] = 0                                                    # empty patterns too
+    offsets = np.zeros(lengths.size + 1, dtype=np.uint64); offsets[1:] = np.cumsum(lengths)
+    chars = rng.integers(65, 91, size=int(offsets[-1]), dtype=np.uint8)
+    for world in (1, 2, 4, 7):
+        seen, totals = [], []
+        for rank in range(world):
+            c, o, ids = shard_patterns_by_length(chars, offsets, rank, world)
+            assert o[0] == 0 and len(o) == len(ids) + 1 and (np.diff(ids) > 0).all()
+            for j in (0, len(ids) // 2, len(ids) - 1):
+                i = int(ids[j])
+                assert bytes(c[int(o[j]):int(o[j + 1])]) == bytes(chars[int(offsets[i]):int(offsets[i + 1])])
+            seen.append(ids); totals.append(int(o[-1]))
+        assert sorted(np.concatenate(seen).tolist()) == list(range(lengths.size))
+        assert max(totals) - min(totals) <= 256 * 2
