@@ -91,6 +91,9 @@ inline void* alloc(size_t bytes)
   if(base == MAP_FAILED) { return nullptr; }
   mprotect(base + (pages - 1) * page, page, PROT_NONE);
   void* p = base + (pages - 1) * page - total;
+  // cudaMalloc does not clear memory: poison it, so that a kernel relying on zeroes it never wrote shows up here
+  static const bool poison = (envBytes("GCSA_EMU_NO_POISON", 0) == 0);
+  if(poison) { std::memset(p, 0xA5, total); }
   Allocations& a = allocations();
   std::lock_guard<std::mutex> lock(a.mutex);
   a.live[p] = std::make_pair((void*)base, pages * page);
