@@ -72,7 +72,7 @@ def translate(text):
     text = text.replace("#include <cuda_runtime.h>", '#define EMU_DEFINE_SWITCH\n#include "cuda_emu.h"', 1)
     text = text.replace("#include <cuda_runtime.h>", '#include "cuda_emu.h"')
     text = text.replace("#include <cub/cub.cuh>", "")
-    text, n_asm = re.subn(r'asm volatile\("ld\.global\.nc\.v4\.u64[^;]*;[^;]*;', "r = *p;", text)
+    text, n_asm = re.subn(r'asm volatile\("ld\.global\.nc\.v4\.u64[^;]*;[^;]*;', "emu::checkAligned(p, 32); r = *p;", text)
     assert n_asm == 1, "expected exactly one inline-PTX load in engine.cu, found %d" % n_asm
     assert "asm" not in re.sub(r"//.*", "", text), "untranslated inline assembly"
 

@@ -409,11 +409,19 @@ static inline unsigned emu_first_or_full(unsigned mask = 0xFFFFFFFFu) { return m
 // Device intrinsics
 //------------------------------------------------------------------------------
 
-template<class T> static inline T __ldg(const T* p) { return *p; }
-template<class T> static inline T __ldcs(const T* p) { return *p; }
-template<class T> static inline T __ldcg(const T* p) { return *p; }
-template<class T> static inline void __stcs(T* p, T v) { *p = v; }
-template<class T> static inline void __stcg(T* p, T v) { *p = v; }
+// The device faults on an access that is not aligned to its size ("misaligned address"); x86 does not.
+namespace emu
+{
+inline void checkAligned(const void* p, size_t size)
+{
+  if(((uintptr_t)p & (size - 1)) != 0) { std::fprintf(stderr, "cuda_emu: %zu-byte access at %p is misaligned\n", size, p); std::abort(); }
+}
+}
+template<class T> static inline T __ldg(const T* p) { emu::checkAligned(p, sizeof(T)); return *p; }
+template<class T> static inline T __ldcs(const T* p) { emu::checkAligned(p, sizeof(T)); return *p; }
+template<class T> static inline T __ldcg(const T* p) { emu::checkAligned(p, sizeof(T)); return *p; }
+template<class T> static inline void __stcs(T* p, T v) { emu::checkAligned(p, sizeof(T)); *p = v; }
+template<class T> static inline void __stcg(T* p, T v) { emu::checkAligned(p, sizeof(T)); *p = v; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 static inline int __clz(int x) { return (x == 0 ? 32 : __builtin_clz((unsigned)x)); }
