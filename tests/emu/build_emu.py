@@ -4,9 +4,9 @@ executed and compared with the oracle on a machine without a GPU.
 
 The translation is textual and small:
   * `#include <cuda_runtime.h>` / `<cub/cub.cuh>`  ->  `#include "cuda_emu.h"`;
-  * `kernel<T...><<<cfg>>>(args);`                 ->  `emu::launch(emu::Cfg(cfg), [&] { kernel<T...>(args); }, collectives);`
+  * `kernel<T...><<<cfg>>>(args);`                 ->  `emu::launchChecked(emu::Cfg(cfg), collectives, [&](auto&&... a) { kernel<T...>(a...); }, args);`
     where `collectives` says whether the kernel (or a device function it names) uses a warp / block collective
-    and therefore has to run on fibers;
+    and therefore has to run on fibers; pointer arguments must be device pointers;
   * the one inline-PTX statement (`ld.global.nc.v4.u64`, a 32-byte load) -> a plain load.
 Nothing under gcsa2_b200/ knows about this; the product library has no CPU path."""
 import os
@@ -102,8 +102,8 @@ def translate(text):
         name, targs = m.group(1), m.group(2) or ""
         assert name in kernels, "launch of an unknown kernel: " + name
         out.append(text[pos:m.start()])
-        out.append("emu::launch(emu::Cfg(%s), [&] { %s%s%s; }, %s)" % (
-            text[m.end():cfg_end], name, targs, text[args_open:args_end], "true" if kernels[name] else "false"))
+        out.append("emu::launchChecked(emu::Cfg(%s), %s, [&](auto&&... emu_args) { %s%s(emu_args...); }, %s)" % (
+            text[m.end():cfg_end], "true" if kernels[name] else "false", name, targs, text[args_open + 1:args_end - 1]))
         pos = args_end
         launches += 1
     out.append(text[pos:])

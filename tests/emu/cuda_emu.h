@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -80,8 +81,11 @@ struct Allocations
 {
   std::mutex mutex;
   std::unordered_map<void*, std::pair<void*, size_t>> live;     // pointer -> (mapping, length)
+  std::map<uintptr_t, size_t> extent;                            // pointer -> usable bytes (range lookups)
 };
 inline Allocations& allocations() { static Allocations a; return a; }
+// true if p points into (or one past the end of) memory obtained from cudaMalloc* / cudaHostAlloc
+inline bool isDeviceVisible(const void* p);
 inline void* alloc(size_t bytes)
 {
   const size_t page = 4096;
@@ -97,6 +101,7 @@ inline void* alloc(size_t bytes)
   Allocations& a = allocations();
   std::lock_guard<std::mutex> lock(a.mutex);
   a.live[p] = std::make_pair((void*)base, pages * page);
+  a.extent[(uintptr_t)p] = total;
   return p;
 }
 inline void release(void* p)
@@ -108,8 +113,39 @@ inline void release(void* p)
   if(it == a.live.end()) { std::fprintf(stderr, "cuda_emu: free of a pointer that was not allocated here\n"); std::abort(); }
   munmap(it->second.first, it->second.second);
   a.live.erase(it);
+  a.extent.erase((uintptr_t)p);
 }
 }
+
+namespace emu
+{
+inline bool isDeviceVisible(const void* p)
+{
+  Allocations& a = allocations();
+  std::lock_guard<std::mutex> lock(a.mutex);
+  auto it = a.extent.upper_bound((uintptr_t)p);
+  if(it == a.extent.begin()) { return false; }
+  --it;
+  return (uintptr_t)p <= it->first + it->second;
+}
+}
+
+// Memory that did not come from cudaMalloc here but stands for device memory (the tests' torch tensors): the test
+// registers it so that kernels may be handed pointers into it.
+#ifdef EMU_DEFINE_SWITCH
+extern "C" void emu_register_device_range(const void* p, size_t bytes)
+{
+  emu::Allocations& a = emu::allocations();
+  std::lock_guard<std::mutex> lock(a.mutex);
+  a.extent[(uintptr_t)p] = bytes;
+}
+extern "C" void emu_unregister_device_range(const void* p)
+{
+  emu::Allocations& a = emu::allocations();
+  std::lock_guard<std::mutex> lock(a.mutex);
+  a.extent.erase((uintptr_t)p);
+}
+#endif
 
 static inline const char* cudaGetErrorString(cudaError_t e) { return (e == cudaSuccess ? "no error" : (e == cudaErrorMemoryAllocation ? "out of memory (emulated)" : "error (emulated)")); }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
@@ -333,6 +369,24 @@ template<class F> void launch(const Cfg& cfg, const F& f, bool collectives)
     }
   }
   coords = saved;
+}
+
+// A kernel launch with its arguments: every pointer argument must be null or point into memory the device can see
+// (cudaMalloc*, cudaHostAlloc) -- a pointer to ordinary host memory works here but faults on the device.
+template<class T> inline void checkKernelArgument(const T&, int) {}
+template<class T> inline void checkKernelArgument(T* const& p, int position)
+{
+  if(p != nullptr && !isDeviceVisible((const void*)p))
+  {
+    std::fprintf(stderr, "cuda_emu: kernel argument %d (%p) is not a device pointer\n", position, (const void*)p);
+    std::abort();
+  }
+}
+template<class K, class... A> void launchChecked(const Cfg& cfg, bool collectives, K&& kernel, A&&... args)
+{
+  int position = 0;
+  (checkKernelArgument(args, position++), ...);
+  launch(cfg, [&] { kernel(args...); }, collectives);
 }
 
 // One warp-wide exchange: every live lane of the warp deposits (pred, value) and gets the generation's

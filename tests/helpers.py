@@ -58,15 +58,29 @@ def kat1_flat(kat=None):
 EMULATED = False
 
 
+def as_emulated_device_memory(tensor):
+    """Under the emulation a host tensor stands for device memory: tell the emulated runtime, which refuses kernel
+    arguments that point anywhere else (as the device would fault on them)."""
+    import ctypes
+    import weakref
+    from gcsa2_b200 import capi
+    lib, address = capi.lib(), tensor.data_ptr()
+    lib.emu_register_device_range(ctypes.c_void_p(address), ctypes.c_size_t(max(1, tensor.numel() * tensor.element_size())))
+    weakref.finalize(tensor, lib.emu_unregister_device_range, ctypes.c_void_p(address))
+    return tensor
+
+
 def to_device(array):
     import torch
     t = torch.from_numpy(array)
-    return t.clone() if EMULATED else t.cuda()
+    return as_emulated_device_memory(t.clone()) if EMULATED else t.cuda()
 
 
 def device_empty(shape, dtype):
     import torch
-    return torch.empty(shape, dtype=dtype, device="cpu" if EMULATED else "cuda")
+    if EMULATED:
+        return as_emulated_device_memory(torch.empty(shape, dtype=dtype))
+    return torch.empty(shape, dtype=dtype, device="cuda")
 
 
 def current_stream():

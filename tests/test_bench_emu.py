@@ -38,10 +38,13 @@ def host_stand_ins(monkeypatch):
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a: _Stream())
     monkeypatch.setattr(torch.cuda, "Event", _Event)
-    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self.clone())
+    from helpers import as_emulated_device_memory as on_device
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: on_device(self.clone()))
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
-    real_empty, real_tensor = torch.empty, torch.tensor
-    monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{x: y for x, y in k.items() if x != "device"}))
+    real_empty, real_tensor, real_empty_like = torch.empty, torch.tensor, torch.empty_like
+    monkeypatch.setattr(torch, "empty", lambda *a, **k: (on_device if "device" in k else (lambda t: t))(
+        real_empty(*a, **{x: y for x, y in k.items() if x != "device"})))
+    monkeypatch.setattr(torch, "empty_like", lambda t, *a, **k: on_device(real_empty_like(t, *a, **k)))
     monkeypatch.setattr(torch, "tensor", lambda *a, **k: real_tensor(*a, **{x: y for x, y in k.items() if x != "device"}))
     return build_emu
 

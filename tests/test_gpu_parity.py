@@ -209,7 +209,7 @@ def test_device_pointer_entry_point_and_empty_batches():
     gpu, ora = both(flat)
     chars, offsets = synth.patterns_from_sequence(seq, 10_000, 24, seed=1)
     d_chars = to_device(chars); d_off = to_device(offsets.view(np.int64))
-    d_sp = device_empty(10_000, torch.int64); d_ep = torch.empty_like(d_sp)
+    d_sp = device_empty(10_000, torch.int64); d_ep = device_empty(10_000, torch.int64)
     gpu.find_device(d_chars, d_off, 10_000, d_sp, d_ep, current_stream())
     device_sync()
     osp, oep, _ = ora.find_batch(chars, offsets)
