@@ -164,7 +164,16 @@ template<class T> static inline cudaError_t cudaHostAlloc(T** p, size_t bytes, u
 static inline cudaError_t cudaFree(void* p) { emu::release(p); return cudaSuccess; }
 static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { emu::release(p); return cudaSuccess; }
 static inline cudaError_t cudaFreeHost(void* p) { emu::release(p); return cudaSuccess; }
-static inline cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind) { if(bytes) { std::memmove(dst, src, bytes); } return cudaSuccess; }
+static inline cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind)
+{
+  if(bytes == 0) { return cudaSuccess; }
+  // the device side of a copy must be device memory (the runtime returns cudaErrorInvalidValue otherwise)
+  bool dst_ok = (kind == cudaMemcpyHostToDevice || kind == cudaMemcpyDeviceToDevice ? emu::isDeviceVisible(dst) && emu::isDeviceVisible((const char*)dst + bytes) : true);
+  bool src_ok = (kind == cudaMemcpyDeviceToHost || kind == cudaMemcpyDeviceToDevice ? emu::isDeviceVisible(src) && emu::isDeviceVisible((const char*)src + bytes) : true);
+  if(!dst_ok || !src_ok) { std::fprintf(stderr, "cuda_emu: cudaMemcpy kind %d with a %s that is not device memory (or runs past its end)\n", (int)kind, dst_ok ? "source" : "destination"); std::abort(); }
+  std::memmove(dst, src, bytes);
+  return cudaSuccess;
+}
 static inline cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind k, cudaStream_t = nullptr) { return cudaMemcpy(dst, src, bytes, k); }
 static inline cudaError_t cudaMemset(void* p, int value, size_t bytes) { if(bytes) { std::memset(p, value, bytes); } return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* p, int value, size_t bytes, cudaStream_t = nullptr) { return cudaMemset(p, value, bytes); }
