@@ -740,7 +740,8 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
   DeviceGuard guard(index->device);
 
   const int pack_threads = hostPackThreads();
-  const bool pack = (pack_threads > 0 && fixed_length > 0 && offsets == nullptr && stats == nullptr && n >= (1u << 16));
+  // (below three chunks of 128 k queries the packer could never claim one: no helper thread, no staging buffers)
+  const bool pack = (pack_threads > 0 && fixed_length > 0 && offsets == nullptr && stats == nullptr && n > (2u << 17));
   // Chunks of >= 128 k queries (4 MB of 32-mers: the link is at its streaming rate), at most ~24 per batch (48 when
   // two threads share it): the H2D engine is the busy resource from the first byte on, so what the pipeline adds to
   // the transfer time is the kernel and the D2H of the LAST chunk -- the smaller the chunks, the smaller that tail.

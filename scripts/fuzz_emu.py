@@ -106,9 +106,9 @@ def main():
         assert (sp == osp).all() and (ep == oep).all(), ("find", tag, np.flatnonzero((sp != osp) | (ep != oep))[:5])
 
         # fixed-length batches through the host entry point, with and without host-side 2-bit packing
-        if sampler is not None and rounds % 4 == 0:
+        if sampler is not None and rounds % 8 == 0:
             ln = int(rng.choice([20, 32, 33, 45, 64]))
-            n_fixed = 420_000 if rounds % 16 == 0 else 70_000         # several chunks now and then: raw copies and packing share the batch
+            n_fixed = 540_000 if rounds % 16 == 0 else 280_000        # three to five chunks: raw copies and packing share the batch
             fc, fo = sampler(n_fixed, ln, int(rng.integers(0, 1 << 30)))
             fc = fc.copy()
             rc, _ = synth.random_patterns(10_000, ln, seed=seed)
