@@ -149,11 +149,13 @@ def test_all_operations_random_graphs(seed):
 def test_linear_reference_order128_kmer_table_invariance():
     """1 Mbp linear reference, order 128: 32-mers sampled from it and uniform random 32-mers;
     identical answers with and without the k-mer table."""
+    import helpers
+    n = 60_000 if helpers.EMULATED else 200_000                       # (the emulated run is one of the slowest CPU tests)
     seq = synth.random_sequence(1_000_000, seed=2)
     flat, flcp, _ = build_index(synth.linear_graph(seq), 16, 3)
     ora = orc.OracleGCSA(flat)
-    chars, offsets = synth.patterns_from_sequence(seq, 200_000, 32, seed=5)
-    rchars, roffsets = synth.random_patterns(200_000, 32, seed=6)
+    chars, offsets = synth.patterns_from_sequence(seq, n, 32, seed=5)
+    rchars, roffsets = synth.random_patterns(n, 32, seed=6)
     ref = None
     for table_k, two_step in ((0, False), (4, False), (10, True), (0, True), (5, True)):
         gpu = GCSA(flat, kmer_table_k=table_k, two_step=two_step)
@@ -168,7 +170,7 @@ def test_linear_reference_order128_kmer_table_invariance():
         else:
             assert all((a == b).all() for a, b in zip(ref, (sp, ep, rsp, rep)))
         # round trip: locate(find(P)) contains the position P was cut from
-        starts = np.random.default_rng(5).integers(0, seq.size - 32 + 1, size=200_000)
+        starts = np.random.default_rng(5).integers(0, seq.size - 32 + 1, size=n)
         offs, vals = gpu.locate_batch(sp[:5000], ep[:5000])
         graph_values = synth.linear_graph(seq).value
         for i in range(5000):
