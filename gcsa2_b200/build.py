@@ -1,5 +1,5 @@
-"""Builds gcsa2_b200/libgcsa2_b200.so in-tree: nvcc for sm_100a (engine.cu, which includes its kernels from
-csrc/device/*.cuh) + g++ (the host-only sources).
+"""Builds gcsa2_b200/libgcsa2_b200.so in-tree: nvcc for sm_100a (the CUDA translation units; engine.cu includes its
+kernels from csrc/device/*.cuh) + g++ (the host-only sources).
 
 The shared library is self-contained (static cudart), so it travels to the GPU box with the
 snapshot and loads on a CPU-only machine too (symbol checks in the CPU test-suite)."""
@@ -10,6 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgcsa2_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include", "gcsa2_b200.h")
+DEVICE_SOURCES = ["engine.cu", "linear_builder.cu"]                          # CUDA translation units (nvcc, sm_100a)
 HOST_SOURCES = ["builder.cpp", "gcsa_file.cpp", "verify.cpp", "pack.cpp"]      # host-side C++ (g++)
 
 NVCC = os.environ.get("GCSA_B200_NVCC", "nvcc")
@@ -27,18 +28,23 @@ def _stale(target, sources):
 
 
 def build(force=False, verbose=False):
-    engine_cu = os.path.join(CSRC, "engine.cu")
+    device_cu = [os.path.join(CSRC, name) for name in DEVICE_SOURCES]
     host_cpp = [os.path.join(CSRC, name) for name in HOST_SOURCES]
-    engine_o = os.path.join(CSRC, "engine.o")
+    device_o = [src[:-3] + ".o" for src in device_cu]
     host_o = [src[:-4] + ".o" for src in host_cpp]
-    device = [os.path.join(CSRC, "device", f) for f in sorted(os.listdir(os.path.join(CSRC, "device"))) if f.endswith(".cuh")]
-    if not force and not _stale(LIB, [engine_cu, INCLUDE, os.path.join(CSRC, "internal.h")] + device + host_cpp):
+    headers = [os.path.join(CSRC, "device", f) for f in sorted(os.listdir(os.path.join(CSRC, "device"))) if f.endswith(".cuh")]
+    headers += [INCLUDE, os.path.join(CSRC, "internal.h")]
+    if not force and not _stale(LIB, device_cu + headers + host_cpp):
         return LIB
     run = lambda cmd: subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL)
-    run([NVCC] + NVCC_FLAGS + ["-c", engine_cu, "-o", engine_o])
+    # only what changed is recompiled (engine.cu takes a minute)
+    for src, obj in zip(device_cu, device_o):
+        if force or _stale(obj, [src] + headers):
+            run([NVCC] + NVCC_FLAGS + ["-c", src, "-o", obj])
     for src, obj in zip(host_cpp, host_o):
-        run([CXX] + CXX_FLAGS + ["-c", src, "-o", obj])
-    run([NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB, engine_o] + host_o + ["-Xcompiler", "-fopenmp", "-lgomp"])
+        if force or _stale(obj, [src] + headers):
+            run([CXX] + CXX_FLAGS + ["-c", src, "-o", obj])
+    run([NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB] + device_o + host_o + ["-Xcompiler", "-fopenmp", "-lgomp"])
     return LIB
 
 

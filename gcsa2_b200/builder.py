@@ -99,3 +99,21 @@ def build_index(graph, k, doubling_steps, sample_period=64, lcp_branching=64, al
     kmers = enumerate_kmers(graph, k)
     flat, lcp = build_from_kmers(kmers, doubling_steps, sample_period, lcp_branching, allow_inconsistent)
     return flat, lcp, kmers
+
+
+def build_linear(seq, k=16, doubling_steps=3, node_len=32, sample_period=64, lcp_branching=64, device=0):
+    """Index of the linear reference `seq` (comp values 1..5; a numpy array or a CUDA uint8 tensor) built on the
+    device (csrc/linear_builder.cu): the same arrays build_index(synth.linear_graph(seq, node_len), k, doubling_steps)
+    returns, without enumerating kmers.  -> (FlatGCSA, FlatLCP)."""
+    on_device = not isinstance(seq, np.ndarray)
+    if not on_device:
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+    built = capi.Built()
+    capi.check(capi.lib().gcsa_b200_build_linear(capi.ptr(seq), int(seq.numel() if on_device else seq.size), int(on_device),
+                                                 int(node_len), int(k), int(doubling_steps), int(sample_period), int(device),
+                                                 C.byref(built)))
+    flat = capi.flat_from_struct(built.index)
+    lcp = np.ctypeslib.as_array(C.cast(built.lcp, C.POINTER(C.c_uint8)), shape=(max(1, int(built.lcp_size)),))[:int(built.lcp_size)].copy()
+    capi.lib().gcsa_b200_built_free(C.byref(built))
+    flat.consistent = True
+    return flat, FlatLCP.from_values(lcp, branching=lcp_branching)

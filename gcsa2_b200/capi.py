@@ -85,7 +85,7 @@ SYMBOLS = [
     "gcsa_b200_lcp_create", "gcsa_b200_lcp_destroy",
     "gcsa_b200_parent_batch", "gcsa_b200_parent_host", "gcsa_b200_depth_batch", "gcsa_b200_depth_host",
     "gcsa_b200_lcp_sv_host", "gcsa_b200_lcp_rmq_host", "gcsa_b200_mem_batch", "gcsa_b200_mem_host",
-    "gcsa_b200_build_from_kmers", "gcsa_b200_built_free",
+    "gcsa_b200_build_from_kmers", "gcsa_b200_built_free", "gcsa_b200_build_linear",
     "gcsa_b200_enumerate_kmers", "gcsa_b200_kmers_free", "gcsa_b200_default_char2comp",
     "gcsa_b200_load_gcsa_file", "gcsa_b200_write_gcsa_file", "gcsa_b200_load_lcp_file", "gcsa_b200_write_lcp_file",
     "gcsa_b200_flat_lcp_free",
@@ -154,6 +154,7 @@ def _bind(L):
     L.gcsa_b200_mem_host.argtypes = [vp, vp, vp, vp, u64, vp, C.POINTER(vp)]
     L.gcsa_b200_build_from_kmers.argtypes = [vp, vp, vp, u64, i32, i32, u64, C.POINTER(Built)]
     L.gcsa_b200_built_free.argtypes = [C.POINTER(Built)]; L.gcsa_b200_built_free.restype = None
+    L.gcsa_b200_build_linear.argtypes = [vp, u64, i32, u64, i32, i32, u64, i32, C.POINTER(Built)]
     L.gcsa_b200_enumerate_kmers.argtypes = [C.POINTER(Graph), i32, C.POINTER(Kmers)]
     L.gcsa_b200_kmers_free.argtypes = [C.POINTER(Kmers)]; L.gcsa_b200_kmers_free.restype = None
     L.gcsa_b200_default_char2comp.argtypes = [vp]; L.gcsa_b200_default_char2comp.restype = None

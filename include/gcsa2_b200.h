@@ -296,6 +296,19 @@ int  gcsa_b200_build_from_kmers(const uint64_t* keys, const uint64_t* from, cons
                                 gcsa_b200_built* result);
 void gcsa_b200_built_free(gcsa_b200_built* result);
 
+/* The same construction for a graph that is ONE PATH (# -> s[0] -> ... -> s[length-1] -> $), on the device
+   (gcsa2_b200/csrc/linear_builder.cu): what GCSA::GCSA(InputGraph&, ...) (src/gcsa.cpp:447-724) produces for the
+   kmers of a linear reference has a closed form -- the path nodes are the distinct length-K prefixes of the
+   suffixes, K = kmer_length << doubling_steps -- so the index is built by radix-sorting suffixes instead of
+   doubling paths.  sequence: comp values 1..5 (A C G T N), a host pointer or (sequence_on_device != 0) a device
+   pointer on `device`.  Node ids as vg assigns them to a chopped path: the source is node 1, base i is node
+   2 + i / node_length at offset i % node_length (node_length <= 1024), the sink is the next free id.
+   Bit-identical to gcsa_b200_build_from_kmers on the kmers of that graph; length + 2 < 2^32 - 1.
+   result as for gcsa_b200_build_from_kmers (release with gcsa_b200_built_free). */
+int  gcsa_b200_build_linear(const uint8_t* sequence, uint64_t length, int sequence_on_device, uint64_t node_length,
+                            int kmer_length, int doubling_steps, uint64_t sample_period, int device,
+                            gcsa_b200_built* result);
+
 /* ---------------------------------------------------------------------------------------------
    Index files of the reference (host; gcsa2_b200/csrc/gcsa_file.cpp).
    gcsa_b200_load_gcsa_file replaces GCSA::load / sdsl::load_from_file(index, name)

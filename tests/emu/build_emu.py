@@ -18,6 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "gcsa2_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libgcsa2_b200_emu.so")
+DEVICE_SOURCES = ["engine.cu", "linear_builder.cu"]       # the first one carries the emulation's out-of-line definitions
 HOST_SOURCES = ["builder.cpp", "gcsa_file.cpp", "verify.cpp", "pack.cpp"]
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 COLLECTIVES = ("__ballot_sync", "__any_sync", "__all_sync", "__syncwarp", "__syncthreads", "__shfl_sync",
@@ -67,13 +68,15 @@ def inline_device_headers(text):
     return re.sub(r'#include "(device/[a-z_]+\.cuh)"', paste, text)
 
 
-def translate(text):
+def translate(text, main=True):
+    """main: the translation unit that defines the emulation's out-of-line symbols (and holds the one inline-PTX load)."""
     text = inline_device_headers(text)
-    text = text.replace("#include <cuda_runtime.h>", '#define EMU_DEFINE_SWITCH\n#include "cuda_emu.h"', 1)
+    if main:
+        text = text.replace("#include <cuda_runtime.h>", '#define EMU_DEFINE_SWITCH\n#include "cuda_emu.h"', 1)
     text = text.replace("#include <cuda_runtime.h>", '#include "cuda_emu.h"')
     text = text.replace("#include <cub/cub.cuh>", "")
     text, n_asm = re.subn(r'asm volatile\("ld\.global\.nc\.v4\.u64[^;]*;[^;]*;', "emu::checkAligned(p, 32); r = *p;", text)
-    assert n_asm == 1, "expected exactly one inline-PTX load in engine.cu, found %d" % n_asm
+    assert n_asm == (1 if main else 0), "expected exactly one inline-PTX load (in engine.cu), found %d" % n_asm
     assert "asm" not in re.sub(r"//.*", "", text), "untranslated inline assembly"
 
     # which functions use collectives, directly or through a device function they name
@@ -113,26 +116,34 @@ def translate(text):
 
 def build(force=False, verbose=False):
     os.makedirs(OUT, exist_ok=True)
-    engine_cu = os.path.join(CSRC, "engine.cu")
+    device_cu = [os.path.join(CSRC, s) for s in DEVICE_SOURCES]
     device = [os.path.join(CSRC, "device", f) for f in sorted(os.listdir(os.path.join(CSRC, "device"))) if f.endswith(".cuh")]
-    sources = [engine_cu, os.path.join(CSRC, "internal.h"), os.path.join(HERE, "cuda_emu.h"), os.path.abspath(__file__),
+    sources = device_cu + [os.path.join(CSRC, "internal.h"), os.path.join(HERE, "cuda_emu.h"), os.path.abspath(__file__),
                os.path.join(ROOT, "include", "gcsa2_b200.h")] + device + [os.path.join(CSRC, s) for s in HOST_SOURCES]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in sources):
         return LIB
-    with open(engine_cu) as f:
-        translated, kernels = translate(f.read())
-    # the translated file sits in _build/, the relative includes of engine.cu are resolved against csrc/
-    for relative in ('#include "../../include/gcsa2_b200.h"', '#include "../../../include/gcsa2_b200.h"'):
-        translated = translated.replace(relative, '#include "%s"' % os.path.join(ROOT, "include", "gcsa2_b200.h"))
-    translated = translated.replace('#include "internal.h"', '#include "%s"' % os.path.join(CSRC, "internal.h"))
-    engine_cpp = os.path.join(OUT, "engine_emu.cpp")
-    with open(engine_cpp, "w") as f:
-        f.write("// GENERATED by tests/emu/build_emu.py from gcsa2_b200/csrc/engine.cu -- test infrastructure, do not edit\n")
-        f.write(translated)
     flags = ["-O1", "-g", "-std=c++17", "-fopenmp", "-fPIC", "-fno-strict-aliasing", "-I", HERE, "-w"]
     run = lambda cmd: subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL)
-    objs = [os.path.join(OUT, "engine_emu.o")]
-    run([CXX] + flags + ["-c", engine_cpp, "-o", objs[0]])
+    objs = []
+    for i, source in enumerate(device_cu):
+        stem = os.path.basename(source)[:-3]
+        obj = os.path.join(OUT, stem + "_emu.o")
+        objs.append(obj)
+        deps = [source, os.path.join(CSRC, "internal.h"), os.path.join(HERE, "cuda_emu.h"), os.path.abspath(__file__),
+                os.path.join(ROOT, "include", "gcsa2_b200.h")] + (device if i == 0 else [])
+        if not force and os.path.exists(obj) and all(os.path.getmtime(s) <= os.path.getmtime(obj) for s in deps):
+            continue
+        with open(source) as f:
+            translated, kernels = translate(f.read(), main=(i == 0))
+        # the translated file sits in _build/, the relative includes of the source are resolved against csrc/
+        for relative in ('#include "../../include/gcsa2_b200.h"', '#include "../../../include/gcsa2_b200.h"'):
+            translated = translated.replace(relative, '#include "%s"' % os.path.join(ROOT, "include", "gcsa2_b200.h"))
+        translated = translated.replace('#include "internal.h"', '#include "%s"' % os.path.join(CSRC, "internal.h"))
+        cpp = os.path.join(OUT, stem + "_emu.cpp")
+        with open(cpp, "w") as f:
+            f.write("// GENERATED by tests/emu/build_emu.py from gcsa2_b200/csrc/%s -- test infrastructure, do not edit\n" % os.path.basename(source))
+            f.write(translated)
+        run([CXX] + flags + ["-c", cpp, "-o", obj])
     for s in HOST_SOURCES:
         obj = os.path.join(OUT, s[:-4] + ".o")
         run([CXX, "-O2", "-march=x86-64-v2", "-std=c++17", "-fopenmp", "-fPIC", "-c", os.path.join(CSRC, s), "-o", obj])

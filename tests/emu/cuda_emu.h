@@ -553,6 +553,29 @@ struct DeviceScan
     return cudaSuccess;
   }
 };
+struct DeviceRadixSort
+{
+  // stable, by bits [begin_bit, end_bit) of the key
+  template<class K, class V, class N>
+  static cudaError_t SortPairs(void* tmp, size_t& bytes, const K* keys_in, K* keys_out, const V* vals_in, V* vals_out, N n,
+                               int begin_bit = 0, int end_bit = (int)sizeof(K) * 8, cudaStream_t = nullptr)
+  {
+    if(tmp == nullptr) { bytes = 256; return cudaSuccess; }
+    if(keys_in == keys_out || (vals_in != nullptr && (const void*)vals_in == (const void*)vals_out)) { emu::die("DeviceRadixSort: in-place sorting is not allowed"); }
+    const K mask = (end_bit - begin_bit >= (int)sizeof(K) * 8 ? ~(K)0 : (((K)1 << (end_bit - begin_bit)) - 1));
+    std::vector<size_t> order((size_t)n);
+    for(size_t i = 0; i < (size_t)n; i++) { order[i] = i; }
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return ((keys_in[a] >> begin_bit) & mask) < ((keys_in[b] >> begin_bit) & mask); });
+    for(size_t i = 0; i < (size_t)n; i++) { keys_out[i] = keys_in[order[i]]; if(vals_in != nullptr) { vals_out[i] = vals_in[order[i]]; } }
+    return cudaSuccess;
+  }
+  template<class K, class N>
+  static cudaError_t SortKeys(void* tmp, size_t& bytes, const K* keys_in, K* keys_out, N n,
+                              int begin_bit = 0, int end_bit = (int)sizeof(K) * 8, cudaStream_t s = nullptr)
+  {
+    return SortPairs(tmp, bytes, keys_in, keys_out, (const char*)nullptr, (char*)nullptr, n, begin_bit, end_bit, s);
+  }
+};
 struct DeviceSegmentedSort
 {
   template<class K, class B, class E>
