@@ -151,3 +151,66 @@ def mixed_length_patterns(seq, sites, alt, n, min_len, max_len, seed, error_rate
     err = rng.random(total) < error_rate
     comps = np.where(err, (comps - 1 + rng.integers(1, 4, size=total)) % 4 + 1, comps).astype(np.uint8)
     return COMP2CHAR[comps], offsets
+
+
+# ---- device-side generators (configs[3]: a 3 Gbp reference and 125 M patterns per GPU never touch the host) -------------
+# A counter-based generator (splitmix64 of the element index) so that every rank, and the host, regenerate the same data.
+
+_SM_GOLDEN, _SM_C1, _SM_C2 = 0x9E3779B97F4A7C15, 0xBF58476D1CE4E5B9, 0x94D049BB133111EB
+
+
+def _as_i64(x):
+    return x - (1 << 64) if x >= (1 << 63) else x
+
+
+def splitmix64_numpy(index, seed):
+    """splitmix64 of (index + (seed + 1) * golden), as uint64."""
+    with np.errstate(over="ignore"):
+        x = index.astype(np.uint64) + np.uint64((seed + 1) * _SM_GOLDEN & ((1 << 64) - 1))
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(_SM_C1)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(_SM_C2)
+        return x ^ (x >> np.uint64(31))
+
+
+def _splitmix64_torch(index, seed):
+    """The same function on an int64 CUDA tensor (two's complement arithmetic; logical shifts by masking)."""
+    x = index + _as_i64((seed + 1) * _SM_GOLDEN & ((1 << 64) - 1))
+    x = (x ^ ((x >> 30) & ((1 << 34) - 1))) * _as_i64(_SM_C1)
+    x = (x ^ ((x >> 27) & ((1 << 37) - 1))) * _as_i64(_SM_C2)
+    return x ^ ((x >> 31) & ((1 << 33) - 1))
+
+
+def counter_sequence(length, seed):
+    """Host version of device_sequence (tests)."""
+    return (1 + (splitmix64_numpy(np.arange(int(length), dtype=np.uint64), seed) >> np.uint64(62))).astype(np.uint8)
+
+
+def device_sequence(length, seed, device="cuda", chunk=1 << 27):
+    """Uniform i.i.d. ACGT as comp values 1..4 in a CUDA uint8 tensor: 1 + the top two bits of splitmix64(i, seed)."""
+    import torch
+    out = torch.empty(int(length), dtype=torch.uint8, device=device)
+    for a in range(0, int(length), chunk):
+        b = min(int(length), a + chunk)
+        h = _splitmix64_torch(torch.arange(a, b, dtype=torch.int64, device=device), seed)
+        out[a:b] = (1 + ((h >> 62) & 3)).to(torch.uint8)
+    return out
+
+
+def device_pattern_starts(seq_length, n, length, seed, device="cuda"):
+    import torch
+    h = _splitmix64_torch(torch.arange(int(n), dtype=torch.int64, device=device), seed)
+    return ((h >> 1) & ((1 << 62) - 1)) % (int(seq_length) - int(length) + 1)
+
+
+def device_patterns(seq, n, length, seed, chunk=1 << 23):
+    """n substrings of the device-resident reference as ASCII bytes (CUDA uint8 tensor of n * length bytes)."""
+    import torch
+    starts = device_pattern_starts(seq.numel(), n, length, seed, device=seq.device)
+    windows = seq.unfold(0, int(length), 1)                   # (L - length + 1, length) view, no copy
+    lut = torch.tensor(list(COMP2CHAR), dtype=torch.uint8, device=seq.device)
+    out = torch.empty(int(n) * int(length), dtype=torch.uint8, device=seq.device)
+    for a in range(0, int(n), chunk):
+        b = min(int(n), a + chunk)
+        comps = windows[starts[a:b]]
+        out[a * length:b * length] = lut[comps.reshape(-1).long()]
+    return out
