@@ -101,10 +101,60 @@ def build_index(graph, k, doubling_steps, sample_period=64, lcp_branching=64, al
     return flat, lcp, kmers
 
 
-def build_linear(seq, k=16, doubling_steps=3, node_len=32, sample_period=64, lcp_branching=64, device=0):
+class BuiltIndex:
+    """The arrays of a freshly built index, still owned by the library (struct gcsa_b200_built): hand it to GCSA(...)
+    as it is -- no numpy copies, which matters at 3 Gbp -- or take copies with flat() / lcp().  free() releases it."""
+
+    def __init__(self, built):
+        self._built = built
+
+    @property
+    def struct(self):
+        if self._built is None:
+            raise ValueError("BuiltIndex: already freed")
+        return self._built.index
+
+    @property
+    def char2comp(self):
+        return np.frombuffer(bytes(self.struct.char2comp), dtype=np.uint8).copy()
+
+    @property
+    def C(self):
+        return np.array([self.struct.C[i] for i in range(SIGMA + 1)], dtype=np.uint64)
+
+    @property
+    def path_nodes(self):
+        return int(self.struct.path_nodes)
+
+    def flat(self):
+        flat = capi.flat_from_struct(self.struct)
+        flat.consistent = True
+        return flat
+
+    def lcp_values(self):
+        n = int(self._built.lcp_size)
+        return np.ctypeslib.as_array(C.cast(self._built.lcp, C.POINTER(C.c_uint8)), shape=(max(1, n),))[:n].copy()
+
+    def lcp(self, branching=64):
+        return FlatLCP.from_values(self.lcp_values(), branching=branching)
+
+    def free(self):
+        if self._built is not None:
+            capi.lib().gcsa_b200_built_free(C.byref(self._built))
+            self._built = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def build_linear(seq, k=16, doubling_steps=3, node_len=32, sample_period=64, lcp_branching=64, device=0, raw=False):
     """Index of the linear reference `seq` (comp values 1..5; a numpy array or a CUDA uint8 tensor) built on the
     device (csrc/linear_builder.cu): the same arrays build_index(synth.linear_graph(seq, node_len), k, doubling_steps)
-    returns, without enumerating kmers.  -> (FlatGCSA, FlatLCP)."""
+    returns, without enumerating kmers.  -> (FlatGCSA, FlatLCP), or with raw=True a BuiltIndex (the arrays stay in the
+    library's buffers)."""
     on_device = not isinstance(seq, np.ndarray)
     if not on_device:
         seq = np.ascontiguousarray(seq, dtype=np.uint8)
@@ -112,8 +162,9 @@ def build_linear(seq, k=16, doubling_steps=3, node_len=32, sample_period=64, lcp
     capi.check(capi.lib().gcsa_b200_build_linear(capi.ptr(seq), int(seq.numel() if on_device else seq.size), int(on_device),
                                                  int(node_len), int(k), int(doubling_steps), int(sample_period), int(device),
                                                  C.byref(built)))
-    flat = capi.flat_from_struct(built.index)
-    lcp = np.ctypeslib.as_array(C.cast(built.lcp, C.POINTER(C.c_uint8)), shape=(max(1, int(built.lcp_size)),))[:int(built.lcp_size)].copy()
-    capi.lib().gcsa_b200_built_free(C.byref(built))
-    flat.consistent = True
-    return flat, FlatLCP.from_values(lcp, branching=lcp_branching)
+    res = BuiltIndex(built)
+    if raw:
+        return res
+    flat, lcp = res.flat(), res.lcp(lcp_branching)
+    res.free()
+    return flat, lcp

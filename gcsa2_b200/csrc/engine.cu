@@ -75,6 +75,59 @@ static int fail(int code, const std::string& msg) { g_last_error = msg; return c
 // Host side: handles
 //------------------------------------------------------------------------------
 
+/*
+  One set of resources for a host-buffer call: SLOTS chunks can be in flight, each with its own stream, device input
+  and result buffers, a pinned staging buffer for packed patterns and two events (input copied, results delivered).
+  Buffers only grow.  Not shared between concurrent calls (gcsa_b200_index::takePipe / givePipe).
+*/
+struct HostPipe
+{
+  static const int SLOTS = 8;
+  cudaStream_t stream[SLOTS] = {};
+  cudaEvent_t copied[SLOTS] = {}, done[SLOTS] = {};
+  void* d_in[SLOTS] = {}; size_t in_bytes[SLOTS] = {};
+  void* d_off[SLOTS] = {}; size_t off_bytes[SLOTS] = {};
+  void* d_res[SLOTS] = {}; size_t res_bytes[SLOTS] = {};
+  void* staging[SLOTS] = {}; size_t staging_bytes[SLOTS] = {};
+  bool used[SLOTS] = {};                 // `done` has been recorded at least once
+  bool ready = false;
+
+  cudaError_t init()
+  {
+    if(ready) { return cudaSuccess; }
+    for(int s = 0; s < SLOTS; s++)
+    {
+      cudaError_t e = cudaStreamCreateWithFlags(&stream[s], cudaStreamNonBlocking);
+      if(e == cudaSuccess) { e = cudaEventCreateWithFlags(&copied[s], cudaEventDisableTiming); }
+      if(e == cudaSuccess) { e = cudaEventCreateWithFlags(&done[s], cudaEventDisableTiming); }
+      if(e != cudaSuccess) { return e; }
+    }
+    ready = true;
+    return cudaSuccess;
+  }
+  static cudaError_t grow(void** p, size_t* have, size_t want, bool pinned)
+  {
+    if(*have >= want) { return cudaSuccess; }
+    if(*p != nullptr) { if(pinned) { cudaFreeHost(*p); } else { cudaFree(*p); } *p = nullptr; *have = 0; }
+    cudaError_t e = (pinned ? cudaHostAlloc(p, want, cudaHostAllocDefault) : cudaMalloc(p, want));
+    if(e == cudaSuccess) { *have = want; } else { *p = nullptr; }
+    return e;
+  }
+  void destroy()
+  {
+    for(int s = 0; s < SLOTS; s++)
+    {
+      if(stream[s]) { cudaStreamSynchronize(stream[s]); cudaStreamDestroy(stream[s]); }
+      if(copied[s]) { cudaEventDestroy(copied[s]); }
+      if(done[s]) { cudaEventDestroy(done[s]); }
+      if(d_in[s]) { cudaFree(d_in[s]); }
+      if(d_off[s]) { cudaFree(d_off[s]); }
+      if(d_res[s]) { cudaFree(d_res[s]); }
+      if(staging[s]) { cudaFreeHost(staging[s]); }
+    }
+  }
+};
+
 struct gcsa_b200_index
 {
   int device = 0;
@@ -85,40 +138,27 @@ struct gcsa_b200_index
   gcsa_flat_index header;            // scalars only (pointers nulled)
 
   // Host-side 2-bit packing of fixed-length patterns (pack.cpp): byte -> comp - 1 or 0xFF, and
-  // whether that table is exactly ACGT / acgt.  Pinned staging buffers are pooled per handle.
+  // whether that table is exactly ACGT / acgt.
   u8 pack_code[256];
   bool pack_default = false;
-  mutable std::mutex pool_mutex;
-  mutable std::vector<std::pair<void*, size_t>> pinned_pool;
 
-  void* takePinned(size_t bytes) const
+  // Resources of the host-buffer entry points (streams, events, device chunk buffers, pinned staging): created on
+  // first use, kept for the life of the handle and handed from call to call, one set per concurrent caller.
+  mutable std::mutex pool_mutex;
+  mutable std::vector<HostPipe*> pipes;
+  HostPipe* takePipe() const
   {
     {
       std::lock_guard<std::mutex> lock(pool_mutex);
-      for(size_t i = 0; i < pinned_pool.size(); i++)
-      {
-        if(pinned_pool[i].second >= bytes)
-        {
-          void* p = pinned_pool[i].first;
-          pinned_pool.erase(pinned_pool.begin() + i);
-          return p;
-        }
-      }
+      if(!pipes.empty()) { HostPipe* p = pipes.back(); pipes.pop_back(); return p; }
     }
-    void* p = nullptr;
-    if(cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    sizes_add(p, bytes);
-    return p;
+    return new HostPipe();
   }
-  void givePinned(void* p) const
+  void givePipe(HostPipe* p) const
   {
     std::lock_guard<std::mutex> lock(pool_mutex);
-    size_t bytes = 0;
-    for(auto& e : pinned_sizes) { if(e.first == p) { bytes = e.second; } }
-    pinned_pool.push_back(std::make_pair(p, bytes));
+    pipes.push_back(p);
   }
-  void sizes_add(void* p, size_t bytes) const { std::lock_guard<std::mutex> lock(pool_mutex); pinned_sizes.push_back(std::make_pair(p, bytes)); }
-  mutable std::vector<std::pair<void*, size_t>> pinned_sizes;     // every pinned buffer ever allocated for this handle
 };
 
 struct gcsa_b200_lcp
@@ -616,7 +656,7 @@ void gcsa_b200_index_destroy(gcsa_b200_index* index)
   if(index == nullptr) { return; }
   DeviceGuard guard(index->device);
   for(void* p : index->allocations) { cudaFree(p); }
-  for(auto& e : index->pinned_sizes) { cudaFreeHost(e.first); }
+  for(HostPipe* p : index->pipes) { p->destroy(); delete p; }
   delete index;
 }
 
@@ -696,19 +736,20 @@ int gcsa_b200_find_fixed_batch(const gcsa_b200_index* index, const uint8_t* d_ch
 }
 
 /*
-  Host-buffer find.  The batch is cut into chunks that are pipelined over a few streams (H2D of one chunk
-  overlaps the kernel of another and the D2H of a third).  What bounds this entry point is the H2D copy of the
-  patterns (32 pattern bytes in, 16 result bytes out per 32-mer), so fixed-length ACGT batches are also 2-bit packed
-  on the host (pack.cpp): 4x fewer bytes over the link -- for the chunks the host manages to pack.
+  Host-buffer find.  The batch is cut into chunks that are pipelined over the slots of a HostPipe (the H2D copy of
+  one chunk overlaps the kernel of another and the D2H copy of a third).  What bounds this entry point is the H2D
+  copy of the patterns (32 pattern bytes in, 16 result bytes out per 32-mer), so fixed-length ACGT batches are also
+  2-bit packed on the host (pack.cpp): 4x fewer bytes over the link -- for the chunks the host manages to pack.
 
-  Raw copying and packing SHARE the batch instead of one being chosen over the other: a helper thread feeds raw
-  chunks from the front of the batch to the copy engine (at most three copies queued ahead, so it sleeps while the
-  link is busy), the calling thread packs chunks from the back with its OpenMP team and sends those.  Whatever the
-  ratio of packing rate to link rate, the two meet in the middle: with packing as fast as the link the batch takes
-  0.57 of the raw transfer time, with packing twice as fast 0.4, with a slow host the helper thread simply does nearly
-  all of it (the packer only claims a chunk when enough raw chunks remain to cover the time it will need for it, so
-  its last chunk cannot become a tail).  A chunk with any character other than ACGT/acgt is sent raw.
-    GCSA_B200_HOST_PACK=0   no packing (one thread, raw chunks);   =N   N packing threads;
+  Raw copying and packing SHARE the batch, and one thread drives both: it keeps a few raw chunks from the FRONT of the
+  batch queued ahead of the copy engine (a non-blocking look at their events), then packs one chunk from the BACK with
+  its OpenMP team and sends that, and so on until the two ends meet.  While the team packs, the copy engine works
+  through the queued raw chunks; the raw path only claims a chunk when its queue runs low, so the split adapts to the
+  ratio of packing rate to link rate by itself (a packer as fast as the link leaves the batch at 0.57 of the raw
+  transfer time, twice as fast at 0.4; with a slow host nearly everything goes raw).  There is no second thread that
+  could be starved of a core by the packing team (the first version had one; profiles/r02_bench_cfg2_*pack*.json).
+  A chunk with any character other than ACGT/acgt is sent raw.
+    GCSA_B200_HOST_PACK=0   no packing;   =N   N packing threads;
     unset or "auto"         all OpenMP threads (GCSA_B200_HOST_PACK_THREADS overrides the count).
 */
 static int hostPackThreads()
@@ -740,144 +781,108 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
   DeviceGuard guard(index->device);
 
   const int pack_threads = hostPackThreads();
-  // (below three chunks of 128 k queries the packer could never claim one: no helper thread, no staging buffers)
+  // (below three chunks of 128 k queries there is nothing to share)
   const bool pack = (pack_threads > 0 && fixed_length > 0 && offsets == nullptr && stats == nullptr && n > (2u << 17));
   // Chunks of >= 128 k queries (4 MB of 32-mers: the link is at its streaming rate), at most ~24 per batch (48 when
-  // two threads share it): the H2D engine is the busy resource from the first byte on, so what the pipeline adds to
+  // packing shares it): the H2D engine is the busy resource from the first byte on, so what the pipeline adds to
   // the transfer time is the kernel and the D2H of the LAST chunk -- the smaller the chunks, the smaller that tail.
   const u64 CHUNK = (pack ? std::max<u64>(1ull << 17, (n + 47) / 48) : std::max<u64>(1ull << 18, (n + 23) / 24));
   const u64 n_chunks = (n + CHUNK - 1) / CHUNK;
   const u64 words_per_pattern = (fixed_length + 31) / 32;
-  const int RAW = 3, PACKED = 3;                         // streams of the raw path; streams + staging buffers of the packed path
-  cudaStream_t raw_streams[RAW] = { nullptr, nullptr, nullptr }, pack_streams[PACKED] = { nullptr, nullptr, nullptr };
-  cudaEvent_t raw_copied[RAW] = { nullptr, nullptr, nullptr }, staged[PACKED] = { nullptr, nullptr, nullptr };
-  u64* staging[PACKED] = { nullptr, nullptr, nullptr };
+  const int SLOTS = HostPipe::SLOTS;
+  // Raw H2D copies kept queued ahead of the copy engine while the team packs one chunk: as many as the link moves in
+  // the time the last chunk took to pack (at the link's nominal 50 GB/s; a slower link just keeps the queue fuller).
+  int raw_ahead = 3;
+
+  HostPipe* pipe = index->takePipe();
+  struct Return { const gcsa_b200_index* index; HostPipe* pipe; ~Return() { index->givePipe(pipe); } } give_back = { index, pipe };
+  {
+    cudaError_t e = pipe->init();
+    if(e != cudaSuccess) { return fail(GCSA_B200_ERR_CUDA, std::string("find_host: stream creation: ") + cudaGetErrorString(e)); }
+  }
   FindStatsDev* d_stats = nullptr;
-  int rc = 0;
-  for(int s = 0; s < RAW && rc == 0; s++)
+  if(stats)
   {
-    if(cudaStreamCreateWithFlags(&raw_streams[s], cudaStreamNonBlocking) != cudaSuccess ||
-       // blocking sync: the helper thread sleeps while the link is busy instead of spinning on a core the packers want
-       cudaEventCreateWithFlags(&raw_copied[s], cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) { rc = fail(GCSA_B200_ERR_CUDA, "find_host: stream creation failed"); }
-  }
-  bool use_pack = (pack && rc == 0);
-  for(int s = 0; s < PACKED && use_pack; s++)
-  {
-    staging[s] = (u64*)index->takePinned(CHUNK * words_per_pattern * sizeof(u64));
-    if(staging[s] == nullptr || cudaStreamCreateWithFlags(&pack_streams[s], cudaStreamNonBlocking) != cudaSuccess ||
-       cudaEventCreateWithFlags(&staged[s], cudaEventDisableTiming) != cudaSuccess) { use_pack = false; cudaGetLastError(); }
-  }
-  if(stats && rc == 0)
-  {
-    if(cudaMalloc(&d_stats, sizeof(FindStatsDev)) != cudaSuccess || cudaMemset(d_stats, 0, sizeof(FindStatsDev)) != cudaSuccess) { rc = fail(GCSA_B200_ERR_CUDA, "find_host: out of device memory"); }
+    if(cudaMalloc(&d_stats, sizeof(FindStatsDev)) != cudaSuccess || cudaMemset(d_stats, 0, sizeof(FindStatsDev)) != cudaSuccess)
+    {
+      if(d_stats) { cudaFree(d_stats); }
+      return fail(GCSA_B200_ERR_CUDA, "find_host: out of device memory");
+    }
   }
 
-  // One chunk through one stream: device buffers, H2D (raw bytes, or the packed words of `from`), kernel, D2H.
-  // `copied` (optional) is recorded right after the H2D copy.  Returns 0 or an error code; the message goes to *error.
-  auto enqueue = [&](u64 c, cudaStream_t st, const u64* from, cudaEvent_t copied, std::string* error) -> int
+  int rc = 0;
+  u64 issued = 0;                        // chunks enqueued so far: chunk number k uses slot k % SLOTS
+  // One chunk through the next slot: H2D (raw bytes, or the words packed into the slot's staging buffer), kernel, D2H.
+  auto enqueue = [&](u64 c, bool packed) -> int
   {
+    const int slot = (int)(issued % SLOTS);
+    cudaStream_t st = pipe->stream[slot];
     u64 q0 = c * CHUNK, q1 = std::min(n, q0 + CHUNK), m = q1 - q0;
     u64 c0 = (offsets ? offsets[q0] : q0 * fixed_length), c1 = (offsets ? offsets[q1] : q1 * fixed_length);
-    u64 bytes = (from != nullptr ? m * words_per_pattern * sizeof(u64) : c1 - c0);
-    u8* d_chars = nullptr; u64* d_off = nullptr; u64* d_res = nullptr;
-    cudaError_t e;
-    if((e = cudaMallocAsync(&d_chars, bytes + 16, st)) != cudaSuccess ||
-       (offsets && (e = cudaMallocAsync(&d_off, (m + 1) * sizeof(u64), st)) != cudaSuccess) ||
-       (e = cudaMallocAsync(&d_res, 2 * m * sizeof(u64), st)) != cudaSuccess)
+    u64 bytes = (packed ? m * words_per_pattern * sizeof(u64) : c1 - c0);
+    #define PIPE_TRY(expr) do { cudaError_t e_ = (expr); if(e_ != cudaSuccess) { \
+      return fail(e_ == cudaErrorMemoryAllocation ? GCSA_B200_ERR_NOMEM : GCSA_B200_ERR_CUDA, std::string("find_host: " #expr ": ") + cudaGetErrorString(e_)); } } while(0)
+    // (a packed chunk waited for the slot before packing into its staging buffer)
+    if(pipe->used[slot] && !packed) { PIPE_TRY(cudaEventSynchronize(pipe->done[slot])); }
+    PIPE_TRY(HostPipe::grow(&pipe->d_in[slot], &pipe->in_bytes[slot], bytes + 16, false));
+    PIPE_TRY(HostPipe::grow(&pipe->d_res[slot], &pipe->res_bytes[slot], 2 * m * sizeof(u64), false));
+    if(offsets) { PIPE_TRY(HostPipe::grow(&pipe->d_off[slot], &pipe->off_bytes[slot], (m + 1) * sizeof(u64), false)); }
+    u8* d_chars = (u8*)pipe->d_in[slot]; u64* d_off = (offsets ? (u64*)pipe->d_off[slot] : nullptr); u64* d_res = (u64*)pipe->d_res[slot];
+    if(packed) { PIPE_TRY(cudaMemcpyAsync(d_chars, pipe->staging[slot], bytes, cudaMemcpyHostToDevice, st)); }
+    else if(bytes) { PIPE_TRY(cudaMemcpyAsync(d_chars, chars + c0, bytes, cudaMemcpyHostToDevice, st)); }
+    if(offsets) { PIPE_TRY(cudaMemcpyAsync(d_off, offsets + q0, (m + 1) * sizeof(u64), cudaMemcpyHostToDevice, st)); }
+    PIPE_TRY(cudaEventRecord(pipe->copied[slot], st));
+    int r = launchFind(index, d_chars, d_off, c0, fixed_length, m, d_res, d_res + m, d_stats, st, packed);
+    if(r != 0) { return r; }
+    PIPE_TRY(cudaMemcpyAsync(sp + q0, d_res, m * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    PIPE_TRY(cudaMemcpyAsync(ep + q0, d_res + m, m * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    PIPE_TRY(cudaEventRecord(pipe->done[slot], st));
+    #undef PIPE_TRY
+    pipe->used[slot] = true;
+    issued++;
+    return 0;
+  };
+
+  // Unclaimed chunks are [front, back): raw chunks are claimed from the front, packed ones from the back.
+  u64 front = 0, back = n_chunks, packed_chunks = 0;
+  std::vector<int> raw_slots;            // slots of the raw chunks whose H2D copy may still be queued, oldest first
+  auto raw_queued = [&]() -> size_t
+  {
+    while(!raw_slots.empty() && cudaEventQuery(pipe->copied[raw_slots.front()]) == cudaSuccess) { raw_slots.erase(raw_slots.begin()); }
+    cudaGetLastError();                  // cudaErrorNotReady is not an error
+    return raw_slots.size();
+  };
+  while(front < back && rc == 0)
+  {
+    while(front < back && rc == 0 && (!pack || raw_queued() < (size_t)raw_ahead))
     {
-      *error = std::string("find_host: ") + cudaGetErrorString(e);
-      return GCSA_B200_ERR_NOMEM;
+      const int slot = (int)(issued % SLOTS);
+      rc = enqueue(front, false);
+      if(rc == 0) { front++; raw_slots.push_back(slot); }
     }
-    if(from != nullptr) { cudaMemcpyAsync(d_chars, from, bytes, cudaMemcpyHostToDevice, st); }
-    else if(bytes) { cudaMemcpyAsync(d_chars, chars + c0, bytes, cudaMemcpyHostToDevice, st); }
-    if(offsets) { cudaMemcpyAsync(d_off, offsets + q0, (m + 1) * sizeof(u64), cudaMemcpyHostToDevice, st); }
-    if(copied != nullptr) { cudaEventRecord(copied, st); }
-    int r = launchFind(index, d_chars, d_off, c0, fixed_length, m, d_res, d_res + m, d_stats, st, from != nullptr);
-    if(r != 0) { *error = g_last_error; }
-    cudaMemcpyAsync(sp + q0, d_res, m * sizeof(u64), cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(ep + q0, d_res + m, m * sizeof(u64), cudaMemcpyDeviceToHost, st);
-    cudaFreeAsync(d_chars, st); if(d_off) { cudaFreeAsync(d_off, st); } cudaFreeAsync(d_res, st);
-    return r;
-  };
-
-  // Unclaimed chunks are [front, back): the raw path claims from the front, the packer from the back.
-  std::mutex claim;
-  u64 front = 0, back = n_chunks;
-  std::atomic<bool> failed(false);
-  auto claim_front = [&](u64* c) -> bool
-  {
-    std::lock_guard<std::mutex> lock(claim);
-    if(front >= back || failed.load()) { return false; }
-    *c = front++; return true;
-  };
-  auto claim_back = [&](u64 reserve, u64* c) -> bool
-  {
-    std::lock_guard<std::mutex> lock(claim);
-    if(back - front <= reserve || failed.load()) { return false; }
-    *c = --back; return true;
-  };
-
-  // The raw path: at most RAW copies queued ahead of the copy engine.
-  int raw_rc = 0; std::string raw_error;
-  auto raw_path = [&]()
-  {
-    cudaSetDevice(index->device);
-    for(u64 k = 0; ; k++)
-    {
-      const int slot = (int)(k % RAW);
-      if(k >= (u64)RAW) { cudaEventSynchronize(raw_copied[slot]); }
-      u64 c;
-      if(!claim_front(&c)) { break; }
-      int r = enqueue(c, raw_streams[slot], nullptr, raw_copied[slot], &raw_error);
-      if(r != 0) { raw_rc = r; failed.store(true); break; }
-    }
-  };
-
-  u64 packed_chunks = 0;
-  std::thread helper;
-  if(rc == 0 && use_pack)
-  {
-    try { helper = std::thread(raw_path); }
-    catch(...) { use_pack = false; }                      // no second thread to be had: everything goes raw from this one
+    if(!pack || front >= back || rc != 0) { break; }
+    // pack the last unclaimed chunk into the staging buffer of the slot it will use
+    const int slot = (int)(issued % SLOTS);
+    u64 c = back - 1, q0 = c * CHUNK, m = std::min(n, q0 + CHUNK) - q0;
+    cudaError_t e = cudaSuccess;
+    if(pipe->used[slot]) { e = cudaEventSynchronize(pipe->done[slot]); }              // its previous chunk has left the buffers
+    if(e == cudaSuccess) { e = HostPipe::grow(&pipe->staging[slot], &pipe->staging_bytes[slot], CHUNK * words_per_pattern * sizeof(u64), true); }
+    if(e != cudaSuccess) { rc = fail(GCSA_B200_ERR_CUDA, std::string("find_host: staging buffer: ") + cudaGetErrorString(e)); break; }
+    const double t0 = omp_get_wtime();
+    bool ok = (gcsa_b200_internal_pack_patterns(chars + q0 * fixed_length, m, fixed_length, index->pack_code, index->pack_default ? 1 : 0,
+                                                (u64*)pipe->staging[slot], pack_threads) != 0);
+    const double link_chunks = (omp_get_wtime() - t0) * 50e9 / (double)(CHUNK * fixed_length);
+    raw_ahead = (int)std::min<double>(SLOTS - 2, std::max(2.0, std::ceil(link_chunks) + 1.0));
+    rc = enqueue(c, ok);
+    if(rc == 0) { back--; if(ok) { packed_chunks++; } }
   }
-  if(rc == 0 && !use_pack) { raw_path(); }
-  else if(rc == 0)
-  {
-    // The packer.  `rate` is what the last chunk achieved (bytes of patterns per second); a chunk is only claimed
-    // while the raw path still has at least as much work ahead as this chunk will take here.
-    const double link_rate = 50e9;
-    double rate = link_rate;
-    std::string pack_error;
-    for(u64 j = 0; ; j++)
-    {
-      const int slot = (int)(j % PACKED);
-      u64 reserve = (u64)std::min(1e6, std::ceil(link_rate / std::max(rate, 1e6))) + 1;
-      u64 c;
-      if(!claim_back(reserve, &c)) { break; }
-      if(j >= (u64)PACKED) { cudaEventSynchronize(staged[slot]); }          // the slot's previous copy has left the buffer
-      u64 q0 = c * CHUNK, m = std::min(n, q0 + CHUNK) - q0;
-      double t0 = omp_get_wtime();
-      bool ok = (gcsa_b200_internal_pack_patterns(chars + q0 * fixed_length, m, fixed_length, index->pack_code, index->pack_default ? 1 : 0,
-                                                  staging[slot], pack_threads) != 0);
-      double secs = omp_get_wtime() - t0;
-      if(ok && secs > 0.0) { rate = (double)(m * fixed_length) / secs; }
-      int r = enqueue(c, pack_streams[slot], ok ? staging[slot] : nullptr, staged[slot], &pack_error);
-      if(ok) { packed_chunks++; }
-      if(r != 0) { rc = fail(r, pack_error); failed.store(true); break; }
-    }
-    helper.join();
-  }
-  if(rc == 0 && raw_rc != 0) { rc = fail(raw_rc, raw_error); }
   g_last_packed_chunks.store(packed_chunks); g_last_chunks.store(n_chunks);
 
+  // everything that was enqueued must have left the caller's buffers before this returns, error or not
   cudaError_t err = cudaSuccess;
-  for(int s = 0; s < RAW; s++)
+  for(int s = 0; s < SLOTS; s++)
   {
-    if(raw_streams[s]) { cudaError_t e = cudaStreamSynchronize(raw_streams[s]); if(e != cudaSuccess) { err = e; } }
-  }
-  for(int s = 0; s < PACKED; s++)
-  {
-    if(pack_streams[s]) { cudaError_t e = cudaStreamSynchronize(pack_streams[s]); if(e != cudaSuccess) { err = e; } }
+    if(pipe->stream[s]) { cudaError_t e = cudaStreamSynchronize(pipe->stream[s]); if(e != cudaSuccess) { err = e; } }
   }
   if(stats && err == cudaSuccess && rc == 0)
   {
@@ -887,17 +892,6 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
     stats->sector_probes = h.sector_probes; stats->table_hits = h.table_hits;
   }
   if(d_stats) { cudaFree(d_stats); }
-  for(int s = 0; s < RAW; s++)
-  {
-    if(raw_streams[s]) { cudaStreamDestroy(raw_streams[s]); }
-    if(raw_copied[s]) { cudaEventDestroy(raw_copied[s]); }
-  }
-  for(int s = 0; s < PACKED; s++)
-  {
-    if(pack_streams[s]) { cudaStreamDestroy(pack_streams[s]); }
-    if(staged[s]) { cudaEventDestroy(staged[s]); }
-    if(staging[s]) { index->givePinned(staging[s]); }
-  }
   if(rc) { return rc; }
   if(err != cudaSuccess) { return fail(GCSA_B200_ERR_CUDA, std::string("find_host: ") + cudaGetErrorString(err)); }
   return 0;

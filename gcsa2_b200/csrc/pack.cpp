@@ -8,6 +8,7 @@
   character p at bits [2 (p % 32), 2 (p % 32) + 2) of word p / 32, value = comp - 1.
 */
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <omp.h>
 
@@ -95,6 +96,47 @@ bool packRangeAvx2(const uint8_t* chars, u64 first, u64 last, u64 length, const 
   _mm_sfence();
   return ok && ((uint32_t)_mm256_movemask_epi8(all_valid) == 0xFFFFFFFFu);
 }
+
+// The same with 512-bit registers: 64 characters (two words) per step.  Bits 1 and 2 of every byte come out as two
+// 64-bit masks (vptestmb), comp - 1 = (b2, b1 ^ b2), and pdep interleaves the two masks into the 2-bit codes; validity
+// is one byte shuffle (low nibble -> the only upper-cased letter with that nibble) and one compare into a mask.
+__attribute__((target("avx512f,avx512bw,bmi2")))
+inline void pack64(const uint8_t* p, u64* out, __mmask64& all_valid)
+{
+  const __m512i v = _mm512_loadu_si512((const void*)p);
+  const __m512i x = _mm512_and_si512(v, _mm512_set1_epi8((char)0xDF));
+  const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8(-1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1));
+  const __m512i want = _mm512_shuffle_epi8(lut, _mm512_and_si512(x, _mm512_set1_epi8(0x0F)));
+  all_valid &= _mm512_cmpeq_epi8_mask(want, x);
+  const u64 b1 = _mm512_test_epi8_mask(v, _mm512_set1_epi8(0x02)), b2 = _mm512_test_epi8_mask(v, _mm512_set1_epi8(0x04));
+  const u64 lo = b1 ^ b2, hi = b2;
+  const u64 EVEN = 0x5555555555555555ull, ODD = 0xAAAAAAAAAAAAAAAAull;
+  _mm_stream_si64((long long*)out, (long long)(_pdep_u64(lo & 0xFFFFFFFFull, EVEN) | _pdep_u64(hi & 0xFFFFFFFFull, ODD)));
+  _mm_stream_si64((long long*)(out + 1), (long long)(_pdep_u64(lo >> 32, EVEN) | _pdep_u64(hi >> 32, ODD)));
+}
+
+// Patterns whose length is a multiple of 32: the batch is one stream of 32-character words.
+__attribute__((target("avx512f,avx512bw,bmi2")))
+bool packStreamAvx512(const uint8_t* chars, u64 first_word, u64 last_word, u64* out)
+{
+  __mmask64 all_valid = ~(__mmask64)0;
+  u64 w = first_word;
+  for(; w + 8 <= last_word; w += 8)
+  {
+    pack64(chars + 32 * w, out + w, all_valid); pack64(chars + 32 * w + 64, out + w + 2, all_valid);
+    pack64(chars + 32 * w + 128, out + w + 4, all_valid); pack64(chars + 32 * w + 192, out + w + 6, all_valid);
+  }
+  for(; w + 2 <= last_word; w += 2) { pack64(chars + 32 * w, out + w, all_valid); }
+  bool ok = (all_valid == ~(__mmask64)0);
+  if(w < last_word)
+  {
+    __m256i valid256 = _mm256_set1_epi8(-1);
+    pack32(chars + 32 * w, out + w, valid256);
+    ok = ok && ((uint32_t)_mm256_movemask_epi8(valid256) == 0xFFFFFFFFu);
+  }
+  _mm_sfence();
+  return ok;
+}
 #endif
 
 bool packRangeScalar(const uint8_t* chars, u64 first, u64 last, u64 length, const uint8_t* code, u64* out)
@@ -114,6 +156,20 @@ extern "C" int gcsa_b200_internal_pack_patterns(const uint8_t* chars, uint64_t n
   bool simd = false;
 #if defined(__x86_64__)
   simd = (default_alphabet != 0) && __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2");
+  static const bool no512 = (std::getenv("GCSA_B200_PACK_NO_AVX512") != nullptr);
+  if(simd && !no512 && length > 0 && length % 32 == 0 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw"))
+  {
+    // one stream of words, cut into blocks of 16 k words (512 kB of characters) that the threads take in turn
+    const u64 total = n * (length / 32), WBLOCK = 16384, wblocks = (total + WBLOCK - 1) / WBLOCK;
+    int all = 1;
+    #pragma omp parallel for schedule(static) num_threads(threads) reduction(&:all)
+    for(u64 b = 0; b < wblocks; b++)
+    {
+      u64 first = b * WBLOCK, last = (first + WBLOCK < total ? first + WBLOCK : total);
+      all &= (packStreamAvx512(chars, first, last, out) ? 1 : 0);
+    }
+    return all;
+  }
 #endif
   const u64 BLOCK = 8192;
   const u64 blocks = (n + BLOCK - 1) / BLOCK;

@@ -46,7 +46,8 @@ class GCSA:
         self._h = None
         L = self._L = capi.lib()            # the handle is destroyed by the library that made it
         keep = []
-        f = capi.flat_struct(flat, keep)
+        # a FlatGCSA (numpy arrays) or a builder.BuiltIndex (the library's own buffers, no copies)
+        f = flat.struct if hasattr(flat, "struct") else capi.flat_struct(flat, keep)
         opt = capi.Options(); opt.kmer_table_k = int(kmer_table_k); opt.two_step = (-1 if two_step is None else int(bool(two_step)))
         opt.walk_table = (-1 if walk_table is None else int(walk_table))
         opt.jump_table = (0 if jump_table is None else (1 if jump_table else -1))

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--kmer-table-k", type=int, default=16)
     ap.add_argument("--queries", type=int, default=10_000_000)
+    ap.add_argument("--options", default="{}", help="JSON: several option sets for GCSA(...) as a list of objects, tried one after the other on each index")
     args = ap.parse_args()
     import torch
     from gcsa2_b200 import GCSA, synth
@@ -34,40 +35,53 @@ def main():
         torch.cuda.synchronize()
         out["sequence_s"] = time.time() - t0
         t0 = time.time()
-        flat, lcp = build_linear(seq, k=16, doubling_steps=3)
+        built = build_linear(seq, k=16, doubling_steps=3, raw=True)
         out["build_linear_s"] = time.time() - t0
-        out["path_nodes"] = flat.path_nodes
+        out["path_nodes"] = built.path_nodes
         if args.check:
+            flat, lcp = built.flat(), built.lcp()
             host, hlcp, _ = build_index(synth.linear_graph(seq.cpu().numpy(), node_len=32), 16, 3)
             same = all((np.asarray(a) == np.asarray(b)).all() for a, b in
                        [(flat.C, host.C), (flat.edges, host.edges), (flat.sampled_paths, host.sampled_paths),
                         (flat.stored_samples, host.stored_samples), (flat.samples, host.samples), (lcp.data, hlcp.data)] +
                        [(flat.bwt[c], host.bwt[c]) for c in range(7)])
             out["same_as_host_builder"] = bool(same)
-        t0 = time.time()
-        index = GCSA(flat, device=0, kmer_table_k=args.kmer_table_k)
-        torch.cuda.synchronize()
-        out["index_create_s"] = time.time() - t0
-        out["device_bytes"] = index.deviceBytes(); out["fused_table"] = index.fusedTable(); out["two_step"] = index.twoStep(); out["jump_k"] = index.jumpK()
         n, length = args.queries, 32
         chars = synth.device_patterns(seq, n, length, seed=17)
         d_sp = torch.empty(n, dtype=torch.int64, device="cuda"); d_ep = torch.empty_like(d_sp)
         stream = torch.cuda.current_stream()
-        for _ in range(3):
-            index.find_fixed_device(chars, length, n, d_sp, d_ep, stream.cuda_stream)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(5):
-            index.find_fixed_device(chars, length, n, d_sp, d_ep, stream.cuda_stream)
-        e1.record(stream); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 5
-        out["find_ms"] = ms; out["find_gqps"] = n / ms / 1e6
-        out["found"] = int(((d_sp + 1) <= (d_ep + 1)).sum().item())
-        index.close()
-        del index, chars, d_sp, d_ep, seq, flat, lcp
+        option_sets = json.loads(args.options)
+        for options in (option_sets if isinstance(option_sets, list) else [option_sets]):
+            res = dict(out); res["options"] = options
+            try:
+                t0 = time.time()
+                index = GCSA(built, device=0, kmer_table_k=args.kmer_table_k, **options)
+                torch.cuda.synchronize()
+                res["index_create_s"] = time.time() - t0
+                res["device_bytes"] = index.deviceBytes(); res["fused_table"] = index.fusedTable(); res["two_step"] = index.twoStep(); res["jump_k"] = index.jumpK()
+                for _ in range(3):
+                    index.find_fixed_device(chars, length, n, d_sp, d_ep, stream.cuda_stream)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(5):
+                    index.find_fixed_device(chars, length, n, d_sp, d_ep, stream.cuda_stream)
+                e1.record(stream); torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 5
+                res["find_ms"] = ms; res["find_gqps"] = n / ms / 1e6
+                res["found"] = int(((d_sp + 1) <= (d_ep + 1)).sum().item())
+                m = min(n, 1_000_000)
+                _, _, st = index.find_batch(chars[:m * length].cpu().numpy(), np.arange(m + 1, dtype=np.uint64) * np.uint64(length), stats=True)
+                res["probes_per_query"] = (st["sector_probes"] + st["table_hits"]) / m; res["lf_steps_per_query"] = st["lf_steps"] / m
+                index.close()
+                del index
+            except Exception as exc:
+                res["error"] = "%s: %s" % (type(exc).__name__, exc)
+            torch.cuda.empty_cache()
+            print(json.dumps(res), flush=True)
+        built.free()
+        del chars, d_sp, d_ep, seq
         torch.cuda.empty_cache()
-        print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":
