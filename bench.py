@@ -55,6 +55,12 @@ def parse_args():
     ap.add_argument("--no-locate", action="store_true", help="skip the locate() leg (BASELINE.json configs[2])")
     ap.add_argument("--locate-mbp", type=float, default=50.0, help="backbone length of the SNP-bubble graph of the locate() leg (Mbp)")
     ap.add_argument("--locate-queries", type=int, default=10_000_000, help="64-mers per GPU in the locate() leg")
+    ap.add_argument("--host-builder", action="store_true", help="build the cfg2 index with the host builder (builder.cpp, ~55 s) instead of the device builder")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the configs[3] leg (3 Gbp index, 1 B queries sharded over the GPUs)")
+    ap.add_argument("--cfg4-mbp", type=float, default=3000.0, help="reference length of the configs[3] leg (Mbp)")
+    ap.add_argument("--cfg4-queries", type=int, default=1_000_000_000, help="queries of the configs[3] leg, WHOLE JOB (strong scaling)")
+    ap.add_argument("--cfg4-chunk", type=int, default=125_000_000, help="queries per resident chunk of the configs[3] leg")
+    ap.add_argument("--cfg4-steps", type=int, default=3, help="timed passes over every chunk of the configs[3] leg")
     return ap.parse_args()
 
 
@@ -70,13 +76,20 @@ def workload_name(args):
         args.queries, args.pattern_length, args.ref_mbp)
 
 
-def build_or_load_index(args, rank, world, barrier):
-    """Rank 0 builds the index on the host (CPU, untimed) and shares it through /dev/shm."""
+def build_or_load_index(args, rank, world, barrier, device=None):
+    """The index of configs[1].  With a GPU at hand every rank builds its own copy on its device
+    (gcsa_b200_build_linear, about a second for 100 Mbp); otherwise -- or with --host-builder / --index-cache -- rank 0
+    builds it on the host (builder.cpp, ~55 s) and shares it through /dev/shm.  Both builders emit identical arrays
+    (tests/test_linear_builder.py)."""
     from gcsa2_b200 import synth
-    from gcsa2_b200.builder import build_index
+    from gcsa2_b200.builder import build_index, build_linear
     from gcsa2_b200.flat import FlatGCSA
     L = int(args.ref_mbp * 1_000_000)
     seq = synth.random_sequence(L, seed=2)
+    if device is not None and not args.host_builder and not args.index_cache:
+        t0 = time.time()
+        flat, _ = build_linear(seq, k=16, doubling_steps=3, node_len=32, device=device)
+        return seq, flat, time.time() - t0
     shared = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir(),
                           "gcsa2_b200_bench_%d_%d.npz" % (L, os.getppid() if world > 1 else os.getpid()))
     flat = None
@@ -291,6 +304,101 @@ def locate_leg(args, rank, world, local, barrier, dist, torch):
     return out
 
 
+def cfg4_leg(args, rank, world, local, barrier, dist, torch):
+    """BASELINE.json configs[3]: 1 B 32-mers on a 3 Gbp linear-path order-128 index, the batch sharded across the
+    GPUs, the index replicated -- STRONG scaling: the job is the same 1 B queries for every N.  Nothing of it touches
+    the host: the reference is generated on the device (counter-based generator, identical on every rank), the index
+    is built there (gcsa_b200_build_linear), and so are the patterns, one resident chunk of --cfg4-chunk queries at a
+    time (a rank owns the chunks c with c % world == rank; 1 B x 32 B would not fit next to the index on one GPU).
+    Timed: --cfg4-steps passes of find() over every chunk (CUDA events on the launching stream), chunk generation
+    excluded; value = queries of the whole job / max over ranks of the summed time of one pass."""
+    from gcsa2_b200 import GCSA, synth
+    from gcsa2_b200.builder import build_linear
+    L, total, chunk, length = int(args.cfg4_mbp * 1_000_000), args.cfg4_queries, args.cfg4_chunk, 32
+    n_chunks = (total + chunk - 1) // chunk
+    mine = [c for c in range(n_chunks) if c % world == rank]
+    t0 = time.time()
+    seq = synth.device_sequence(L, seed=4)
+    built = build_linear(seq, k=16, doubling_steps=3, node_len=32, device=local, raw=True)
+    torch.cuda.synchronize()
+    build_s = time.time() - t0
+    t0 = time.time()
+    index = GCSA(built, device=local, kmer_table_k=args.kmer_table_k, walk_table=0, two_step=False, fused_table=False)     # find() only: no locate tables
+    torch.cuda.synchronize()
+    create_s = time.time() - t0
+    flat = built.flat() if (rank == 0 and not args.no_cpu_baseline) else None
+    built.free()
+    stream = torch.cuda.current_stream()
+    d_sp = torch.empty(min(chunk, total), dtype=torch.int64, device="cuda"); d_ep = torch.empty_like(d_sp)
+    ms_pass, found, queries, sample = 0.0, 0, 0, None
+    for c in mine:
+        m = min(chunk, total - c * chunk)
+        d_chars = synth.device_patterns(seq, m, length, seed=4000 + c)
+        for _ in range(2):
+            index.find_fixed_device(d_chars, length, m, d_sp, d_ep, stream.cuda_stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.cfg4_steps):
+            index.find_fixed_device(d_chars, length, m, d_sp, d_ep, stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms_pass += e0.elapsed_time(e1) / args.cfg4_steps
+        found += int(((d_sp[:m] + 1) <= (d_ep[:m] + 1)).sum().item()); queries += m
+        if sample is None and rank == 0:
+            k = min(m, 1_000_000)
+            sample = (d_chars[:k * length].cpu().numpy(), d_sp[:k].cpu().numpy().view(np.uint64).copy(), d_ep[:k].cpu().numpy().view(np.uint64).copy())
+        del d_chars
+    barrier()
+    # work counters of the kernel on the parity sample (untimed, stats variant)
+    st = None
+    if sample is not None:
+        k = sample[1].size
+        _, _, st = index.find_batch(sample[0], np.arange(k + 1, dtype=np.uint64) * np.uint64(length), stats=True)
+    info = {"path_nodes": index.size(), "edges": index.edgeCount(), "order": index.order(), "device_bytes": index.deviceBytes(),
+            "kmer_table_k": index.kmerTableK(), "fused_table": index.fusedTable(), "two_step": index.twoStep(), "jump_k": index.jumpK()}
+    index.close()
+    del seq, d_sp, d_ep
+    torch.cuda.empty_cache()
+    if dist is not None:
+        t = torch.tensor([ms_pass], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_pass = float(t[0])
+        cnt = torch.tensor([queries, found], dtype=torch.int64, device="cuda")
+        dist.all_reduce(cnt)                                          # NCCL: the gather of the result counters
+        queries, found = int(cnt[0]), int(cnt[1])
+    out = {"metric": METRIC, "value": queries / (ms_pass / 1000.0), "unit": UNIT, "scaling": "strong", "n_gpus": world,
+           "ms_per_pass": ms_pass, "queries": queries, "found": found,
+           "config": {"workload": "cfg4: %d x 32-mers sampled from a %g Mbp synthetic linear reference (device generator, seed 4), order-128 index "
+                                  "(k=16, 3 doubling steps) built on the device; %d resident chunks of %d queries dealt round-robin to %d GPU(s), index replicated" % (
+                                      total, args.cfg4_mbp, n_chunks, chunk, world),
+                      "index": info, "steps_per_chunk": args.cfg4_steps},
+           "setup": {"sequence_and_build_s": build_s, "index_create_s": create_s}}
+    if rank == 0 and st is not None:
+        peak, peak_src = peaks()
+        k = sample[1].size
+        per_query = 64.0 * (st["sector_probes"] + st["table_hits"]) / k + length + 16
+        secs = ms_pass / 1000.0
+        rank0_queries = sum(min(chunk, total - c * chunk) for c in mine)
+        out["roofline"] = {"bound": "hbm", "achieved": per_query * rank0_queries / secs / 1e9, "peak": peak, "unit": "GB/s",
+                           "frac": per_query * rank0_queries / secs / 1e9 / peak, "traffic": None, "kernel": "find_kernel<false,4,false>",
+                           "peak_source": peak_src, "probes_per_query": (st["sector_probes"] + st["table_hits"]) / k,
+                           "lf_steps_per_query": st["lf_steps"] / k,
+                           "accounting": "per GPU (rank 0): 64 B per distinct probe executed + |P| + 16 B I/O per query, over the time of one pass"}
+    if rank == 0 and flat is not None:
+        t0 = time.time()
+        engine, kind, threads = cpu_engine(flat)
+        load_s = time.time() - t0
+        k = sample[1].size
+        offsets = np.arange(k + 1, dtype=np.uint64) * np.uint64(length)
+        csp, cep, secs = engine.find_batch(sample[0], offsets, threads=threads)
+        out["cpu_baseline"] = {"value": k / secs, "unit": UNIT, "cores": threads, "kind": kind, "seconds": secs,
+                               "sample": "the first %d queries of chunk 0, %d OpenMP threads; %s" % (
+                                   k, threads, "reference sources + SDSL shim" if kind == "reference" else "C restatement of the reference"),
+                               "parity_on_sample": bool((csp == sample[1]).all() and (cep == sample[2]).all()), "index_load_s": load_s}
+    return out
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -318,10 +426,19 @@ def run_reference(args, rank, world):
     built here because sdsl-lite is absent), all host threads, a bounded sample per step."""
     if rank != 0:
         return
-    seq, flat, build_s = build_or_load_index(args, 0, 1, lambda: None)
+    device = None
+    try:                                    # the fixture may be built on a GPU if there is one; the timed loop below is CPU only
+        import torch
+        if torch.cuda.is_available():
+            device = 0
+    except Exception:
+        device = None
+    seq, flat, build_s = build_or_load_index(args, 0, 1, lambda: None, device=device)
     engine, kind, threads = cpu_engine(flat)
     sample = args.cpu_sample or min(args.queries, 200_000 * threads)
-    chars, offsets = make_patterns(seq, sample, args.pattern_length, seed=11)
+    # the first `sample` queries of the very batch rank 0 of the GPU arm searches (seed 100)
+    chars, offsets = make_patterns(seq, args.queries, args.pattern_length, seed=100)
+    chars, offsets = chars[:sample * args.pattern_length], offsets[:sample + 1]
     times = []
     for i in range(args.warmup + args.steps):
         _, _, secs = engine.find_batch(chars, offsets, threads=threads)
@@ -332,7 +449,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "step": "bounded sample of %d queries per step" % sample},
+            "config": {"workload": workload_name(args), "step": "bounded sample per step: the first %d queries of the GPU arm's rank-0 batch (seed 100)" % sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
                              "sample": "%d queries per step, %d OpenMP threads; %s" % (
                                  sample, threads, "reference sources + SDSL shim" if kind == "reference" else "C restatement")},
@@ -362,7 +479,7 @@ def main():
             dist.barrier(device_ids=[local])
 
     from gcsa2_b200 import GCSA
-    seq, flat, build_s = build_or_load_index(args, rank, world, barrier)
+    seq, flat, build_s = build_or_load_index(args, rank, world, barrier, device=local)
     n, length = args.queries, args.pattern_length
     chars, offsets = make_patterns(seq, n, length, seed=100 + rank)
 
@@ -500,6 +617,18 @@ def main():
         except Exception as exc:                                    # the find() line must survive a failure here
             locate = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
+    cfg4 = None
+    if not args.no_cfg4:
+        try:
+            if torch.cuda.get_device_properties(local).total_memory < 150e9:
+                raise RuntimeError("needs a GPU with more than 150 GB")
+            index.close()                                           # the 3 Gbp index needs the HBM (the accessors below are cached)
+            d_sp = d_ep = h_sp = h_ep = None
+            torch.cuda.empty_cache()
+            cfg4 = cfg4_leg(args, rank, world, local, barrier, dist, torch)
+        except Exception as exc:                                    # the find() line must survive a failure here
+            cfg4 = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     if rank == 0:
         peak, peak_src = peaks()
         traffic = recorded_traffic(args, index)
@@ -515,6 +644,7 @@ def main():
                        "l2": "no explicit flush: every step streams %.0f MB of patterns/offsets/results, %s the 126 MB L2" % (
                            n * (length + 16) / 1e6, "more than" if n * (length + 16) > 126e6 else "LESS than (reduced run: not a valid timing)")},
             "found": total_found, "queries": total_q,
+            "device_bytes": index.deviceBytes(), "kmer_table_k": index.kmerTableK(),
             "e2e": {"value": total_q / (e2e_ms / 1000.0), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(n * (pack_share * 8 * ((length + 31) // 32) + (1.0 - pack_share) * length)), "d2h_bytes_per_step": int(n * 16),
                     "api": "gcsa_b200_find_fixed_host (pinned host buffers, chunked H2D/kernel/D2H pipeline%s)" % (
@@ -544,6 +674,8 @@ def main():
             line["e2e"]["note"] = e2e_note
         if locate is not None:
             line["locate"] = locate
+        if cfg4 is not None:
+            line["cfg4"] = cfg4
         if secondary is not None:
             if dist is not None and "value" in secondary:
                 secondary["note"] = "rank 0 only"

@@ -46,6 +46,14 @@ def host_stand_ins(monkeypatch):
         real_empty(*a, **{x: y for x, y in k.items() if x != "device"})))
     monkeypatch.setattr(torch, "empty_like", lambda t, *a, **k: on_device(real_empty_like(t, *a, **k)))
     monkeypatch.setattr(torch, "tensor", lambda *a, **k: real_tensor(*a, **{x: y for x, y in k.items() if x != "device"}))
+    # the device-side generators of configs[3] run on the host, their results stand for device memory
+    from types import SimpleNamespace
+    from gcsa2_b200 import synth
+    real_sequence, real_patterns = synth.device_sequence, synth.device_patterns
+    monkeypatch.setattr(synth, "device_sequence", lambda length, seed, **k: on_device(real_sequence(length, seed, device="cpu")))
+    monkeypatch.setattr(synth, "device_patterns", lambda *a, **k: on_device(real_patterns(*a, **k)))
+    monkeypatch.setattr(torch.cuda, "empty_cache", lambda: None)
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda d: SimpleNamespace(total_memory=192 << 30))
     return build_emu
 
 
@@ -55,7 +63,8 @@ def test_bench_line_on_the_emulated_engine(monkeypatch, capsys):
     monkeypatch.setenv("GCSA_B200_HOST_PACK_THREADS", "2")
     monkeypatch.delenv("GCSA_B200_HOST_PACK", raising=False)         # the default: raw copies and packing share the batch
     monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "2", "--warmup", "1", "--ref-mbp", "0.2", "--queries", "1100000",
-                                      "--kmer-table-k", "8", "--locate-mbp", "0.2", "--locate-queries", "40000", "--cpu-sample", "20000"])
+                                      "--kmer-table-k", "8", "--locate-mbp", "0.2", "--locate-queries", "40000", "--cpu-sample", "20000",
+                                      "--cfg4-mbp", "0.05", "--cfg4-queries", "250000", "--cfg4-chunk", "100000", "--cfg4-steps", "1"])
     bench.main()
     out = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
     assert len(out) == 1
@@ -74,6 +83,10 @@ def test_bench_line_on_the_emulated_engine(monkeypatch, capsys):
     assert line["secondary"]["parity_on_sample"] and line["secondary"]["found"] < 1_100_000 // 2
     for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert key in line["roofline"], key
+    c4 = line["cfg4"]
+    assert "error" not in c4, c4
+    assert c4["queries"] == c4["found"] == 250_000 and c4["scaling"] == "strong" and c4["cpu_baseline"]["parity_on_sample"]
+    assert c4["config"]["index"]["path_nodes"] == 50_002 and "roofline" in c4
     loc = line["locate"]
     assert "error" not in loc, loc
     assert loc["positions"] >= 40_000 and loc["e2e"]["matches_device_leg"] and loc["cpu_baseline"]["parity_on_sample"]
