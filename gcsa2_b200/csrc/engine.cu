@@ -88,7 +88,10 @@ struct HostPipe
   void* d_in[SLOTS] = {}; size_t in_bytes[SLOTS] = {};
   void* d_off[SLOTS] = {}; size_t off_bytes[SLOTS] = {};
   void* d_res[SLOTS] = {}; size_t res_bytes[SLOTS] = {};
-  void* staging[SLOTS] = {}; size_t staging_bytes[SLOTS] = {};
+  static const int STAGING = 4;          // pinned buffers the packers fill (a ring, independent of the slots)
+  void* staging[STAGING] = {}; size_t staging_bytes[STAGING] = {};
+  cudaEvent_t staged[STAGING] = {};      // the copy engine has read the buffer
+  bool staged_used[STAGING] = {};
   bool used[SLOTS] = {};                 // `done` has been recorded at least once
   bool ready = false;
 
@@ -100,6 +103,11 @@ struct HostPipe
       cudaError_t e = cudaStreamCreateWithFlags(&stream[s], cudaStreamNonBlocking);
       if(e == cudaSuccess) { e = cudaEventCreateWithFlags(&copied[s], cudaEventDisableTiming); }
       if(e == cudaSuccess) { e = cudaEventCreateWithFlags(&done[s], cudaEventDisableTiming); }
+      if(e != cudaSuccess) { return e; }
+    }
+    for(int b = 0; b < STAGING; b++)
+    {
+      cudaError_t e = cudaEventCreateWithFlags(&staged[b], cudaEventDisableTiming);
       if(e != cudaSuccess) { return e; }
     }
     ready = true;
@@ -123,7 +131,11 @@ struct HostPipe
       if(d_in[s]) { cudaFree(d_in[s]); }
       if(d_off[s]) { cudaFree(d_off[s]); }
       if(d_res[s]) { cudaFree(d_res[s]); }
-      if(staging[s]) { cudaFreeHost(staging[s]); }
+    }
+    for(int b = 0; b < STAGING; b++)
+    {
+      if(staged[b]) { cudaEventDestroy(staged[b]); }
+      if(staging[b]) { cudaFreeHost(staging[b]); }
     }
   }
 };
@@ -741,13 +753,15 @@ int gcsa_b200_find_fixed_batch(const gcsa_b200_index* index, const uint8_t* d_ch
   copy of the patterns (32 pattern bytes in, 16 result bytes out per 32-mer), so fixed-length ACGT batches are also
   2-bit packed on the host (pack.cpp): 4x fewer bytes over the link -- for the chunks the host manages to pack.
 
-  Raw copying and packing SHARE the batch, and one thread drives both: it keeps a few raw chunks from the FRONT of the
-  batch queued ahead of the copy engine (a non-blocking look at their events), then packs one chunk from the BACK with
-  its OpenMP team and sends that, and so on until the two ends meet.  While the team packs, the copy engine works
-  through the queued raw chunks; the raw path only claims a chunk when its queue runs low, so the split adapts to the
-  ratio of packing rate to link rate by itself (a packer as fast as the link leaves the batch at 0.57 of the raw
-  transfer time, twice as fast at 0.4; with a slow host nearly everything goes raw).  There is no second thread that
-  could be starved of a core by the packing team (the first version had one; profiles/r02_bench_cfg2_*pack*.json).
+  Raw copying and packing SHARE the batch.  The calling thread is the driver -- the only thread that talks to the
+  CUDA runtime: it keeps a few raw chunks from the FRONT of the batch queued ahead of the copy engine and sends every
+  packed chunk as soon as it is complete.  The other threads of its OpenMP team are packers: they work through the
+  chunks the driver opens for them from the BACK of the batch, one sub-block of 8192 patterns at a time, into a ring
+  of pinned staging buffers.  The two ends meet wherever the ratio of packing rate to link rate puts them (a packer as
+  fast as the link leaves the batch at 0.57 of the raw transfer time, twice as fast at 0.4; with a slow host nearly
+  everything goes raw).  Nobody waits for anybody: the first version had a helper thread for the raw copies that the
+  packing team starved of a core, the second one packed and enqueued in turns on one thread (measured 7.1 and 5.5 ms
+  per 10 M 32-mers, profiles/r02_bench_cfg2_*pack*.json).
   A chunk with any character other than ACGT/acgt is sent raw.
     GCSA_B200_HOST_PACK=0   no packing;   =N   N packing threads;
     unset or "auto"         all OpenMP threads (GCSA_B200_HOST_PACK_THREADS overrides the count).
@@ -759,6 +773,13 @@ static int hostPackThreads()
   const char* t = std::getenv("GCSA_B200_HOST_PACK_THREADS");
   int threads = (t != nullptr && *t != 0 ? std::atoi(t) : omp_get_max_threads());
   return std::max(1, threads);
+}
+
+static inline void cpuRelax()
+{
+#if defined(__x86_64__)
+  __builtin_ia32_pause();
+#endif
 }
 
 // Measurement hook (not part of the C ABI): chunks of the last host-buffer find of this process that went packed, and all.
@@ -813,8 +834,9 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
   int rc = 0;
   u64 issued = 0;                        // chunks enqueued so far: chunk number k uses slot k % SLOTS
   // One chunk through the next slot: H2D (raw bytes, or the words packed into the slot's staging buffer), kernel, D2H.
-  auto enqueue = [&](u64 c, bool packed) -> int
+  auto enqueue = [&](u64 c, int staging_buffer) -> int
   {
+    const bool packed = (staging_buffer >= 0);
     const int slot = (int)(issued % SLOTS);
     cudaStream_t st = pipe->stream[slot];
     u64 q0 = c * CHUNK, q1 = std::min(n, q0 + CHUNK), m = q1 - q0;
@@ -822,13 +844,17 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
     u64 bytes = (packed ? m * words_per_pattern * sizeof(u64) : c1 - c0);
     #define PIPE_TRY(expr) do { cudaError_t e_ = (expr); if(e_ != cudaSuccess) { \
       return fail(e_ == cudaErrorMemoryAllocation ? GCSA_B200_ERR_NOMEM : GCSA_B200_ERR_CUDA, std::string("find_host: " #expr ": ") + cudaGetErrorString(e_)); } } while(0)
-    // (a packed chunk waited for the slot before packing into its staging buffer)
-    if(pipe->used[slot] && !packed) { PIPE_TRY(cudaEventSynchronize(pipe->done[slot])); }
+    if(pipe->used[slot]) { PIPE_TRY(cudaEventSynchronize(pipe->done[slot])); }       // the slot's previous chunk has left its buffers
     PIPE_TRY(HostPipe::grow(&pipe->d_in[slot], &pipe->in_bytes[slot], bytes + 16, false));
     PIPE_TRY(HostPipe::grow(&pipe->d_res[slot], &pipe->res_bytes[slot], 2 * m * sizeof(u64), false));
     if(offsets) { PIPE_TRY(HostPipe::grow(&pipe->d_off[slot], &pipe->off_bytes[slot], (m + 1) * sizeof(u64), false)); }
     u8* d_chars = (u8*)pipe->d_in[slot]; u64* d_off = (offsets ? (u64*)pipe->d_off[slot] : nullptr); u64* d_res = (u64*)pipe->d_res[slot];
-    if(packed) { PIPE_TRY(cudaMemcpyAsync(d_chars, pipe->staging[slot], bytes, cudaMemcpyHostToDevice, st)); }
+    if(packed)
+    {
+      PIPE_TRY(cudaMemcpyAsync(d_chars, pipe->staging[staging_buffer], bytes, cudaMemcpyHostToDevice, st));
+      PIPE_TRY(cudaEventRecord(pipe->staged[staging_buffer], st));       // the buffer may be packed into again
+      pipe->staged_used[staging_buffer] = true;
+    }
     else if(bytes) { PIPE_TRY(cudaMemcpyAsync(d_chars, chars + c0, bytes, cudaMemcpyHostToDevice, st)); }
     if(offsets) { PIPE_TRY(cudaMemcpyAsync(d_off, offsets + q0, (m + 1) * sizeof(u64), cudaMemcpyHostToDevice, st)); }
     PIPE_TRY(cudaEventRecord(pipe->copied[slot], st));
@@ -843,7 +869,8 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
     return 0;
   };
 
-  // Unclaimed chunks are [front, back): raw chunks are claimed from the front, packed ones from the back.
+  // Unclaimed chunks are [front, back): raw chunks are claimed from the front, packed ones from the back.  Only the
+  // driver claims (it opens chunks for the packers), so front / back need no lock.
   u64 front = 0, back = n_chunks, packed_chunks = 0;
   std::vector<int> raw_slots;            // slots of the raw chunks whose H2D copy may still be queued, oldest first
   auto raw_queued = [&]() -> size_t
@@ -852,29 +879,98 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
     cudaGetLastError();                  // cudaErrorNotReady is not an error
     return raw_slots.size();
   };
-  while(front < back && rc == 0)
+  auto send_raw = [&]() -> int
   {
-    while(front < back && rc == 0 && (!pack || raw_queued() < (size_t)raw_ahead))
-    {
-      const int slot = (int)(issued % SLOTS);
-      rc = enqueue(front, false);
-      if(rc == 0) { front++; raw_slots.push_back(slot); }
-    }
-    if(!pack || front >= back || rc != 0) { break; }
-    // pack the last unclaimed chunk into the staging buffer of the slot it will use
     const int slot = (int)(issued % SLOTS);
-    u64 c = back - 1, q0 = c * CHUNK, m = std::min(n, q0 + CHUNK) - q0;
-    cudaError_t e = cudaSuccess;
-    if(pipe->used[slot]) { e = cudaEventSynchronize(pipe->done[slot]); }              // its previous chunk has left the buffers
-    if(e == cudaSuccess) { e = HostPipe::grow(&pipe->staging[slot], &pipe->staging_bytes[slot], CHUNK * words_per_pattern * sizeof(u64), true); }
-    if(e != cudaSuccess) { rc = fail(GCSA_B200_ERR_CUDA, std::string("find_host: staging buffer: ") + cudaGetErrorString(e)); break; }
-    const double t0 = omp_get_wtime();
-    bool ok = (gcsa_b200_internal_pack_patterns(chars + q0 * fixed_length, m, fixed_length, index->pack_code, index->pack_default ? 1 : 0,
-                                                (u64*)pipe->staging[slot], pack_threads) != 0);
-    const double link_chunks = (omp_get_wtime() - t0) * 50e9 / (double)(CHUNK * fixed_length);
-    raw_ahead = (int)std::min<double>(SLOTS - 2, std::max(2.0, std::ceil(link_chunks) + 1.0));
-    rc = enqueue(c, ok);
-    if(rc == 0) { back--; if(ok) { packed_chunks++; } }
+    int r = enqueue(front, -1);
+    if(r == 0) { front++; raw_slots.push_back(slot); }
+    return r;
+  };
+
+  const int team = (pack ? std::min(pack_threads + 1, std::max(2, omp_get_max_threads())) : 1);     // the driver and the packers
+  if(team < 2)
+  {
+    while(front < back && rc == 0) { rc = send_raw(); }
+  }
+  else
+  {
+    // Packed chunk j (the j-th from the back) is chunk n_chunks - 1 - j and uses staging buffer j % STAGING.
+    const int STAGING = HostPipe::STAGING;
+    const u64 SUB = 8192;                                            // patterns per work item
+    const u64 subs_per_chunk = (CHUNK + SUB - 1) / SUB;
+    std::vector<std::atomic<u32>> blocks_done(n_chunks), blocks_bad(n_chunks);
+    for(u64 j = 0; j < n_chunks; j++) { blocks_done[j].store(0); blocks_bad[j].store(0); }
+    std::atomic<u64> ticket(0), opened(0);
+    std::atomic<bool> closing(false);
+    for(int b = 0; b < STAGING && rc == 0; b++)
+    {
+      cudaError_t e = HostPipe::grow(&pipe->staging[b], &pipe->staging_bytes[b], CHUNK * words_per_pattern * sizeof(u64), true);
+      if(e != cudaSuccess) { rc = fail(GCSA_B200_ERR_CUDA, std::string("find_host: staging buffer: ") + cudaGetErrorString(e)); }
+    }
+    int raw_ahead = 3;                                               // raw H2D copies kept queued ahead of the copy engine
+
+    #pragma omp parallel num_threads(team)
+    {
+      if(omp_get_thread_num() != 0)
+      {
+        // ---- packer: work items (chunk j, sub-block b) in order; wait until the driver has opened chunk j ----
+        while(true)
+        {
+          u64 t = ticket.fetch_add(1), j = t / subs_per_chunk, b = t % subs_per_chunk;
+          u32 spins = 0;
+          while(j >= opened.load(std::memory_order_acquire) && !closing.load(std::memory_order_acquire))
+          {
+            if(++spins < 2000) { cpuRelax(); } else { std::this_thread::yield(); }
+          }
+          if(j >= opened.load(std::memory_order_acquire)) { break; }                       // closing: no more chunks
+          u64 c = n_chunks - 1 - j, q0 = c * CHUNK, m = std::min(n, q0 + CHUNK) - q0;
+          u64 first = b * SUB, last = std::min(m, first + SUB);
+          if(first < last)
+          {
+            int good = gcsa_b200_internal_pack_range(chars + q0 * fixed_length, first, last, fixed_length, index->pack_code,
+                                                     index->pack_default ? 1 : 0, (u64*)pipe->staging[j % STAGING]);
+            if(!good) { blocks_bad[j].fetch_add(1, std::memory_order_relaxed); }
+          }
+          blocks_done[j].fetch_add(1, std::memory_order_release);
+        }
+      }
+      else
+      {
+        // ---- driver ----
+        u64 sent = 0;                                                // packed chunks handed to the copy engine
+        while(rc == 0 && (front < back || sent < opened.load(std::memory_order_relaxed)))
+        {
+          bool progress = false;
+          // a packed chunk is complete: send it (raw from the caller's buffer if it held another character)
+          if(sent < opened.load(std::memory_order_relaxed) && blocks_done[sent].load(std::memory_order_acquire) == subs_per_chunk)
+          {
+            bool ok = (blocks_bad[sent].load() == 0);
+            rc = enqueue(n_chunks - 1 - sent, ok ? (int)(sent % STAGING) : -1);
+            if(rc == 0 && ok) { packed_chunks++; }
+            sent++;
+            continue;
+          }
+          // open the next chunk for the packers: one being packed and one waiting is enough to keep them busy, and its
+          // staging buffer must have been read by the copy engine (the packed chunk STAGING places before it)
+          u64 open_now = opened.load(std::memory_order_relaxed);
+          if(front < back && open_now - sent < 2)
+          {
+            const int buffer = (int)(open_now % STAGING);            // last used by packed chunk open_now - STAGING < sent
+            bool free_buffer = true;
+            if(pipe->staged_used[buffer])
+            {
+              if(cudaEventQuery(pipe->staged[buffer]) == cudaSuccess) { pipe->staged_used[buffer] = false; }
+              else { free_buffer = false; cudaGetLastError(); }
+            }
+            if(free_buffer) { back--; opened.store(open_now + 1, std::memory_order_release); progress = true; }
+          }
+          // keep the copy engine fed with raw chunks
+          if(front < back && raw_queued() < (size_t)raw_ahead) { rc = send_raw(); progress = true; }
+          if(!progress) { cpuRelax(); }
+        }
+        closing.store(true, std::memory_order_release);
+      }
+    }
   }
   g_last_packed_chunks.store(packed_chunks); g_last_chunks.store(n_chunks);
 

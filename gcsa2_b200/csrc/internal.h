@@ -18,6 +18,11 @@ void gcsa_b200_internal_set_error(const char* message);
 int gcsa_b200_internal_pack_patterns(const uint8_t* chars, uint64_t n, uint64_t length, const uint8_t* code,
                                      int default_alphabet, uint64_t* out, int threads);
 
+/* The same for patterns [first, last) of the batch on the calling thread (no OpenMP inside): out is the base of the
+   whole batch's output. */
+int gcsa_b200_internal_pack_range(const uint8_t* chars, uint64_t first, uint64_t last, uint64_t length, const uint8_t* code,
+                                  int default_alphabet, uint64_t* out);
+
 #ifdef __cplusplus
 }
 #endif

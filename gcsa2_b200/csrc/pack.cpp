@@ -149,28 +149,29 @@ bool packRangeScalar(const uint8_t* chars, u64 first, u64 last, u64 length, cons
 
 } // namespace
 
+// Patterns [first, last) of the batch, on the calling thread: the widest path the CPU and the alphabet allow.
+extern "C" int gcsa_b200_internal_pack_range(const uint8_t* chars, uint64_t first, uint64_t last, uint64_t length, const uint8_t* code,
+                                             int default_alphabet, uint64_t* out)
+{
+  if(first >= last) { return 1; }
+#if defined(__x86_64__)
+  static const bool avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2");
+  static const bool avx512 = avx2 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
+                             std::getenv("GCSA_B200_PACK_NO_AVX512") == nullptr;
+  if(default_alphabet != 0 && avx512 && length > 0 && length % 32 == 0)
+  {
+    const u64 words = length / 32;                                // the patterns are one stream of 32-character words
+    return packStreamAvx512(chars, first * words, last * words, out) ? 1 : 0;
+  }
+  if(default_alphabet != 0 && avx2) { return packRangeAvx2(chars, first, last, length, code, out) ? 1 : 0; }
+#endif
+  return packRangeScalar(chars, first, last, length, code, out) ? 1 : 0;
+}
+
 extern "C" int gcsa_b200_internal_pack_patterns(const uint8_t* chars, uint64_t n, uint64_t length, const uint8_t* code,
                                                  int default_alphabet, uint64_t* out, int threads)
 {
   if(threads < 1) { threads = 1; }
-  bool simd = false;
-#if defined(__x86_64__)
-  simd = (default_alphabet != 0) && __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2");
-  static const bool no512 = (std::getenv("GCSA_B200_PACK_NO_AVX512") != nullptr);
-  if(simd && !no512 && length > 0 && length % 32 == 0 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw"))
-  {
-    // one stream of words, cut into blocks of 16 k words (512 kB of characters) that the threads take in turn
-    const u64 total = n * (length / 32), WBLOCK = 16384, wblocks = (total + WBLOCK - 1) / WBLOCK;
-    int all = 1;
-    #pragma omp parallel for schedule(static) num_threads(threads) reduction(&:all)
-    for(u64 b = 0; b < wblocks; b++)
-    {
-      u64 first = b * WBLOCK, last = (first + WBLOCK < total ? first + WBLOCK : total);
-      all &= (packStreamAvx512(chars, first, last, out) ? 1 : 0);
-    }
-    return all;
-  }
-#endif
   const u64 BLOCK = 8192;
   const u64 blocks = (n + BLOCK - 1) / BLOCK;
   int ok = 1;
@@ -178,13 +179,7 @@ extern "C" int gcsa_b200_internal_pack_patterns(const uint8_t* chars, uint64_t n
   for(u64 b = 0; b < blocks; b++)
   {
     u64 first = b * BLOCK, last = (first + BLOCK < n ? first + BLOCK : n);
-    bool good;
-#if defined(__x86_64__)
-    if(simd) { good = packRangeAvx2(chars, first, last, length, code, out); }
-    else
-#endif
-    { good = packRangeScalar(chars, first, last, length, code, out); }
-    ok &= (good ? 1 : 0);
+    ok &= gcsa_b200_internal_pack_range(chars, first, last, length, code, default_alphabet, out);
   }
   return ok;
 }
