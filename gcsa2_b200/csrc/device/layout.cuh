@@ -43,6 +43,8 @@ struct DevView
   u32 default_alphabet;                // char2comp is exactly ACGT / acgt -> 1..4 for the bases (enables the SWAR pattern packing)
   const u64* jump; u32 jump_k, jump_tbits;   // jump table: len << 59 | 2-bit chars << jump_tbits | target (see jump_extend_kernel)
   const u64* jump_short;               // the same table cut at 4 steps: for the tail of a pattern that is shorter than the long path
+  const ulonglong2* jump_wide;         // the long table with 16-byte entries { target | len << 40, characters } for indexes whose node numbers
+                                       // leave fewer than 16 characters in an 8-byte entry (replaces `jump`; jump_k stays the longest path)
   const u64* loc64;                    // locate table: bit 63 | value for nodes with one start position, else rank of the sampled node << 24 | steps
   u8 char2comp[256];
 };
@@ -67,6 +69,19 @@ __device__ __forceinline__ ulonglong4 ld256(const ulonglong4* p)
 }
 
 __device__ __forceinline__ bool range_empty(u64 sp, u64 ep) { return (sp + 1 > ep + 1); }   // utils.h:93-101
+
+// A jump-table entry, whichever table it came from: the unary backward path of a node.
+struct JumpPath { u32 len; u64 chars, target; };      // chars: comp - 1, 2 bits each, first step lowest
+__device__ __forceinline__ JumpPath jump_decode(u64 e, u32 tbits)
+{
+  JumpPath p; p.len = (u32)(e >> 59); p.chars = ((e << 5) >> 5) >> tbits; p.target = e & ((1ull << tbits) - 1);
+  return p;
+}
+__device__ __forceinline__ JumpPath jump_decode_wide(ulonglong2 e)
+{
+  JumpPath p; p.len = (u32)(e.x >> 40) & 63u; p.chars = e.y; p.target = e.x & M40;
+  return p;
+}
 
 // ones among the low k bits of w, 0 <= k <= 64
 __device__ __forceinline__ u32 popc_low(u64 w, u32 k)

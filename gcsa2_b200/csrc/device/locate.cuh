@@ -366,6 +366,33 @@ jump_extend_kernel(u64 n, u32 tbits, u32 j, const u64* __restrict__ one, u64* __
   }
 }
 
+// The long table with 16-byte entries (indexes with more than 2^27 path nodes: an 8-byte entry has no room for 16
+// characters next to a node number of that size).  Same construction: level 1 from `one`, one more step per round.
+__global__ void __launch_bounds__(256)
+jump_wide_init_kernel(u64 n, u32 tbits, const u64* __restrict__ one, ulonglong2* __restrict__ wide)
+{
+  const u64 tmask = (1ull << tbits) - 1;
+  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+  {
+    u64 e = one[i];
+    wide[i] = ((e >> 59) == 0 ? make_ulonglong2(0, 0) : make_ulonglong2((e & tmask) | (1ull << 40), (e >> tbits) & 3));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+jump_wide_extend_kernel(u64 n, u32 tbits, u32 j, const u64* __restrict__ one, ulonglong2* __restrict__ wide)
+{
+  const u64 tmask = (1ull << tbits) - 1;
+  for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+  {
+    ulonglong2 e = wide[i];
+    if(((e.x >> 40) & 63u) != j) { continue; }
+    u64 next = __ldg(one + (e.x & M40));
+    if((next >> 59) == 0) { continue; }
+    wide[i] = make_ulonglong2((next & tmask) | ((u64)(j + 1) << 40), e.y | (((next >> tbits) & 3) << (2 * j)));
+  }
+}
+
 // Locate table: the whole of locateInternal() (gcsa.cpp:880-896) per path node, precomputed from the walk
 // table.  A node whose sampled ancestor stores one start position holds that position + steps directly
 // (bit 63 set); otherwise the rank of the sampled node and the number of steps.  *overflow is set if a

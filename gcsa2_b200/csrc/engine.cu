@@ -529,28 +529,39 @@ int gcsa_b200_index_create(const gcsa_flat_index* host, int device, const gcsa_b
     }
   }
 
-  // jump table (optional; 8 bytes per path node + as much again while it is built)
+  // jump tables (optional; 8 bytes per path node each + as much again while they are built)
   {
-    int want = (options != nullptr ? options->jump_table : 0);        // 0 = automatic, 1 = build, -1 = do not
+    int want = (options != nullptr ? options->jump_table : 0);        // 0 = automatic, 1 = build, 2 = build with 16-byte entries, -1 = do not
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     size_t bytes = (size_t)N * sizeof(u64);
     u32 tbits = 1; while((1ull << tbits) < N) { tbits++; }
     int max_len = std::min<int>(16, (59 - (int)tbits) / 2);
-    if(N > 0 && want >= 0 && max_len >= 2 && (want > 0 || 2 * bytes < free_b / 2))
+    // An 8-byte entry holds (59 - tbits) / 2 characters: 16 up to 2^27 path nodes, 13 at 3 G.  Beyond that the long
+    // table gets 16-byte entries (16 characters again: a 32-mer is the k-mer table and one jump), memory permitting.
+    bool wide = (want == 2 || (want >= 0 && max_len < 16 && 4 * bytes < free_b / 2));
+    const int short_len = 4;
+    if(N > 0 && want >= 0 && (max_len >= 2 || wide) && (want > 0 || 2 * bytes < free_b / 2))
     {
-      u64 *one = nullptr, *table = nullptr, *short_table = nullptr;
-      const int short_len = 4;
+      u64 *one = nullptr, *table = nullptr, *short_table = nullptr; ulonglong2* wide_table = nullptr;
       cudaError_t e = cudaMalloc((void**)&one, bytes);
       if(e == cudaSuccess) { e = cudaMalloc((void**)&table, bytes); }
-      if(e == cudaSuccess && max_len > short_len && 3 * bytes < free_b / 2) { if(cudaMalloc((void**)&short_table, bytes) != cudaSuccess) { short_table = nullptr; cudaGetLastError(); } }
+      if(e == cudaSuccess && wide) { e = cudaMalloc((void**)&wide_table, 2 * bytes); }
+      if(e == cudaSuccess && !wide && max_len > short_len && 3 * bytes < free_b / 2) { if(cudaMalloc((void**)&short_table, bytes) != cudaSuccess) { short_table = nullptr; cudaGetLastError(); } }
       if(e == cudaSuccess)
       {
         jump_init_kernel<<<gridFor(N, idx->sm_count, 8), 256>>>(v, tbits, one, table);
-        for(int j = 1; j < max_len; j++)
+        // with 16-byte entries for the long paths, `table` only grows to the short length and IS the short table
+        const int grow_to = (wide ? std::min(short_len, max_len) : max_len);
+        for(int j = 1; j < grow_to; j++)
         {
           if(j == short_len && short_table != nullptr) { e = cudaMemcpyAsync(short_table, table, bytes, cudaMemcpyDeviceToDevice, 0); }   // paths of up to 4 steps
           jump_extend_kernel<<<gridFor(N, idx->sm_count, 8), 256>>>(N, tbits, (u32)j, one, table);
+        }
+        if(wide)
+        {
+          jump_wide_init_kernel<<<gridFor(N, idx->sm_count, 8), 256>>>(N, tbits, one, wide_table);
+          for(int j = 1; j < 16; j++) { jump_wide_extend_kernel<<<gridFor(N, idx->sm_count, 8), 256>>>(N, tbits, (u32)j, one, wide_table); }
         }
         if(e == cudaSuccess) { e = cudaDeviceSynchronize(); }
       }
@@ -558,13 +569,23 @@ int gcsa_b200_index_create(const gcsa_flat_index* host, int device, const gcsa_b
       if(e == cudaSuccess)
       {
         idx->allocations.push_back(table); idx->device_bytes += bytes;
-        v.jump = table; v.jump_k = (u32)max_len; v.jump_tbits = tbits;
-        if(short_table != nullptr) { idx->allocations.push_back(short_table); idx->device_bytes += bytes; v.jump_short = short_table; }
+        v.jump_tbits = tbits;
+        if(wide)
+        {
+          idx->allocations.push_back(wide_table); idx->device_bytes += 2 * bytes;
+          v.jump_wide = wide_table; v.jump_short = table; v.jump_k = 16;
+        }
+        else
+        {
+          v.jump = table; v.jump_k = (u32)max_len;
+          if(short_table != nullptr) { idx->allocations.push_back(short_table); idx->device_bytes += bytes; v.jump_short = short_table; }
+        }
       }
       else
       {
         if(table) { cudaFree(table); }
         if(short_table) { cudaFree(short_table); }
+        if(wide_table) { cudaFree(wide_table); }
         cudaGetLastError();
         if(want > 0) { gcsa_b200_index_destroy(idx); return fail(GCSA_B200_ERR_CUDA, std::string("jump table: ") + cudaGetErrorString(e)); }
       }
@@ -681,7 +702,7 @@ int gcsa_b200_index_info(const gcsa_b200_index* index, gcsa_b200_info* info)
   info->device_bytes = index->device_bytes; info->kmer_table_k = index->view.table_k;
   info->device = index->device; info->sm_count = index->sm_count;
   info->two_step = (index->view.bwt2 != nullptr ? 1 : 0);
-  info->jump_k = (index->view.jump != nullptr ? (int)index->view.jump_k : 0);
+  info->jump_k = (index->view.jump != nullptr || index->view.jump_wide != nullptr ? (int)index->view.jump_k : 0);
   info->fused_table = (index->view.table2 != nullptr ? 1 : 0);
   return 0;
 }
@@ -811,9 +832,6 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
   const u64 n_chunks = (n + CHUNK - 1) / CHUNK;
   const u64 words_per_pattern = (fixed_length + 31) / 32;
   const int SLOTS = HostPipe::SLOTS;
-  // Raw H2D copies kept queued ahead of the copy engine while the team packs one chunk: as many as the link moves in
-  // the time the last chunk took to pack (at the link's nominal 50 GB/s; a slower link just keeps the queue fuller).
-  int raw_ahead = 3;
 
   HostPipe* pipe = index->takePipe();
   struct Return { const gcsa_b200_index* index; HostPipe* pipe; ~Return() { index->givePipe(pipe); } } give_back = { index, pipe };
@@ -872,18 +890,24 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
   // Unclaimed chunks are [front, back): raw chunks are claimed from the front, packed ones from the back.  Only the
   // driver claims (it opens chunks for the packers), so front / back need no lock.
   u64 front = 0, back = n_chunks, packed_chunks = 0;
-  std::vector<int> raw_slots;            // slots of the raw chunks whose H2D copy may still be queued, oldest first
-  auto raw_queued = [&]() -> size_t
+  std::vector<int> h2d_slots;            // slots of the chunks (raw or packed) whose H2D copy may still be queued, oldest first
+  auto h2d_queued = [&]() -> size_t
   {
-    while(!raw_slots.empty() && cudaEventQuery(pipe->copied[raw_slots.front()]) == cudaSuccess) { raw_slots.erase(raw_slots.begin()); }
+    while(!h2d_slots.empty() && cudaEventQuery(pipe->copied[h2d_slots.front()]) == cudaSuccess) { h2d_slots.erase(h2d_slots.begin()); }
     cudaGetLastError();                  // cudaErrorNotReady is not an error
-    return raw_slots.size();
+    return h2d_slots.size();
+  };
+  auto send = [&](u64 c, int staging_buffer) -> int
+  {
+    const int slot = (int)(issued % SLOTS);
+    int r = enqueue(c, staging_buffer);
+    if(r == 0) { h2d_slots.push_back(slot); }
+    return r;
   };
   auto send_raw = [&]() -> int
   {
-    const int slot = (int)(issued % SLOTS);
-    int r = enqueue(front, -1);
-    if(r == 0) { front++; raw_slots.push_back(slot); }
+    int r = send(front, -1);
+    if(r == 0) { front++; }
     return r;
   };
 
@@ -907,7 +931,11 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
       cudaError_t e = HostPipe::grow(&pipe->staging[b], &pipe->staging_bytes[b], CHUNK * words_per_pattern * sizeof(u64), true);
       if(e != cudaSuccess) { rc = fail(GCSA_B200_ERR_CUDA, std::string("find_host: staging buffer: ") + cudaGetErrorString(e)); }
     }
-    int raw_ahead = 3;                                               // raw H2D copies kept queued ahead of the copy engine
+    // A raw chunk is sent only when the copy engine is about to run dry (fewer than this many H2D copies queued,
+    // packed ones included): every chunk the packers finish in time crosses the link at a quarter of the bytes, and
+    // the raw chunks fill the gaps they leave.  (Keeping raw copies queued regardless gave the raw path half of the
+    // batch however fast the packers were: profiles/r02_bench_cfg2_pipe3_pack_*.json.)
+    const size_t feed_below = 2;
 
     #pragma omp parallel num_threads(team)
     {
@@ -945,7 +973,7 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
           if(sent < opened.load(std::memory_order_relaxed) && blocks_done[sent].load(std::memory_order_acquire) == subs_per_chunk)
           {
             bool ok = (blocks_bad[sent].load() == 0);
-            rc = enqueue(n_chunks - 1 - sent, ok ? (int)(sent % STAGING) : -1);
+            rc = send(n_chunks - 1 - sent, ok ? (int)(sent % STAGING) : -1);
             if(rc == 0 && ok) { packed_chunks++; }
             sent++;
             continue;
@@ -964,8 +992,8 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
             }
             if(free_buffer) { back--; opened.store(open_now + 1, std::memory_order_release); progress = true; }
           }
-          // keep the copy engine fed with raw chunks
-          if(front < back && raw_queued() < (size_t)raw_ahead) { rc = send_raw(); progress = true; }
+          // keep the copy engine fed
+          if(front < back && h2d_queued() < feed_below) { rc = send_raw(); progress = true; }
           if(!progress) { cpuRelax(); }
         }
         closing.store(true, std::memory_order_release);

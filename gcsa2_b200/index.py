@@ -50,7 +50,7 @@ class GCSA:
         f = flat.struct if hasattr(flat, "struct") else capi.flat_struct(flat, keep)
         opt = capi.Options(); opt.kmer_table_k = int(kmer_table_k); opt.two_step = (-1 if two_step is None else int(bool(two_step)))
         opt.walk_table = (-1 if walk_table is None else int(walk_table))
-        opt.jump_table = (0 if jump_table is None else (1 if jump_table else -1))
+        opt.jump_table = (0 if jump_table is None else (2 if jump_table == "wide" else (1 if jump_table else -1)))
         opt.fused_table = (0 if fused_table is None else (1 if fused_table else -1))
         h = C.c_void_p()
         capi.check(L.gcsa_b200_index_create(C.byref(f), int(device), C.byref(opt), C.byref(h)))

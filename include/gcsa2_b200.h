@@ -94,7 +94,9 @@ typedef struct gcsa_b200_options {
                               backward path starting there (up to 16 steps: every node on it has exactly one
                               predecessor character), so that a singleton range advances that many characters
                               with one load.  0 = build if it fits, 1 = build, -1 = do not.  Exact: a pattern that
-                              leaves the path or ends inside it is continued with single steps. */
+                              leaves the path or ends inside it is continued with single steps.  An 8-byte entry
+                              has room for 16 characters up to 2^27 path nodes (13 at 3 G nodes); beyond that the
+                              long table gets 16-byte entries when they fit (2 = force 16-byte entries). */
   int      fused_table;    /* find(): k-mer table entries of 16 bytes instead of 8 -- next to the result of the k-mer, the
                               jump-table entry of its path node when the result is a single node, so that the table
                               lookup and the first jump are ONE load (a 32-mer with k = 16 is one 16-byte probe).
