@@ -56,6 +56,10 @@ def parse_args():
     ap.add_argument("--locate-mbp", type=float, default=50.0, help="backbone length of the SNP-bubble graph of the locate() leg (Mbp)")
     ap.add_argument("--locate-queries", type=int, default=10_000_000, help="64-mers per GPU in the locate() leg")
     ap.add_argument("--host-builder", action="store_true", help="build the cfg2 index with the host builder (builder.cpp, ~55 s) instead of the device builder")
+    ap.add_argument("--no-mem", action="store_true", help="skip the configs[4] leg (MEM-style scan of mixed-length patterns)")
+    ap.add_argument("--mem-patterns", type=int, default=4_000_000, help="patterns of the configs[4] leg, WHOLE JOB (strong scaling)")
+    ap.add_argument("--mem-steps", type=int, default=3)
+    ap.add_argument("--mem-cpu-sample", type=int, default=200_000)
     ap.add_argument("--no-cfg4", action="store_true", help="skip the configs[3] leg (3 Gbp index, 1 B queries sharded over the GPUs)")
     ap.add_argument("--cfg4-mbp", type=float, default=3000.0, help="reference length of the configs[3] leg (Mbp)")
     ap.add_argument("--cfg4-queries", type=int, default=1_000_000_000, help="queries of the configs[3] leg, WHOLE JOB (strong scaling)")
@@ -197,32 +201,46 @@ def cpu_baseline(flat, chars, offsets, length, sample, threads=None):
                     "seconds": best}
 
 
-def locate_leg(args, rank, world, local, barrier, dist, torch):
+def cfg3_fixture(args, rank, world, barrier):
+    """The index of BASELINE.json configs[2] and configs[4]: a synthetic variation graph (1 % SNP bubbles over a
+    random backbone, seed 3), order 128, with its LCP array.  A graph needs the host builder (rank 0, ~30 s for 50 Mbp);
+    the other ranks read the arrays from /dev/shm."""
+    from gcsa2_b200 import synth
+    from gcsa2_b200.builder import build_index
+    from gcsa2_b200.flat import FlatGCSA, FlatLCP
+    L = int(args.locate_mbp * 1_000_000)
+    seq = synth.random_sequence(L, seed=3)
+    graph, sites, alt = synth.snp_graph(seq, seed=3, snp_rate=0.01)
+    base = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir(),
+                        "gcsa2_b200_bench_cfg3_%d_%d" % (L, os.getppid() if world > 1 else os.getpid()))
+    t0 = time.time()
+    flat = lcp = None
+    if rank == 0:
+        flat, lcp, _ = build_index(graph, 16, 3)
+        if world > 1:
+            flat.save(base + ".npz")
+            np.savez(base + "_lcp.npz", header=np.array([lcp.size, lcp.branching, lcp.levels], dtype=np.uint64), offsets=lcp.offsets, data=lcp.data)
+    barrier()
+    if rank != 0:
+        flat = FlatGCSA.load(base + ".npz")
+        z = np.load(base + "_lcp.npz")
+        lcp = FlatLCP(size=int(z["header"][0]), branching=int(z["header"][1]), levels=int(z["header"][2]), offsets=z["offsets"], data=z["data"])
+    barrier()
+    if rank == 0 and world > 1:
+        for name in (base + ".npz", base + "_lcp.npz"):
+            if os.path.exists(name):
+                os.remove(name)
+    return {"seq": seq, "sites": sites, "alt": alt, "flat": flat, "lcp": lcp, "build_s": time.time() - t0, "length": L}
+
+
+def locate_leg(args, rank, world, local, barrier, dist, torch, fixture):
     """The second half of BASELINE.json's metric: locate() positions/s on configs[2] -- 64-mers sampled from walks
     through a synthetic variation graph (1 % SNP bubbles, order 128), find() then locate(range) as a CSR of sorted
     distinct positions (GCSA::locate, src/gcsa.cpp:827-842).  Device-resident (CUDA events), end to end through
     gcsa_b200_locate_host, and the reference's own locate() on the host cores (rank 0)."""
     from gcsa2_b200 import GCSA, synth
-    from gcsa2_b200.builder import build_index
-    from gcsa2_b200.flat import FlatGCSA
-    L, n, length = int(args.locate_mbp * 1_000_000), args.locate_queries, 64
-    seq = synth.random_sequence(L, seed=3)
-    graph, sites, alt = synth.snp_graph(seq, seed=3, snp_rate=0.01)
-    shared = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir(),
-                          "gcsa2_b200_bench_locate_%d_%d.npz" % (L, os.getppid() if world > 1 else os.getpid()))
-    t0 = time.time()
-    flat = None
-    if rank == 0:
-        flat, _, _ = build_index(graph, 16, 3)
-        if world > 1:
-            flat.save(shared)
-    barrier()
-    if rank != 0:
-        flat = FlatGCSA.load(shared)
-    barrier()
-    if rank == 0 and world > 1 and os.path.exists(shared):
-        os.remove(shared)
-    build_s = time.time() - t0
+    n, length = args.locate_queries, 64
+    seq, sites, alt, flat, build_s = fixture["seq"], fixture["sites"], fixture["alt"], fixture["flat"], fixture["build_s"]
     chars = np.empty(n * length, dtype=np.uint8)
     for i, q0 in enumerate(range(0, n, 1_000_000)):
         m = min(1_000_000, n - q0)
@@ -301,6 +319,84 @@ def locate_leg(args, rank, world, local, barrier, dist, torch):
                                "sample": "locate() of the first %d ranges, %d OpenMP threads (schedule dynamic,256)" % (m, threads), "seconds": secs,
                                "parity_on_sample": bool((offs[:m + 1] == roffs).all() and (vals[:k] == rvals).all())}
     index.close()
+    return out
+
+
+def mem_leg(args, rank, world, local, barrier, dist, torch, fixture):
+    """BASELINE.json configs[4]: mixed-length 16-256 bp patterns through the MEM-style scan (GCSA::LF + LCPArray::parent,
+    include/gcsa/gcsa.h:155-162, src/lcp.cpp:276-301) on the configs[2] graph and its LCP array -- the warp-divergence
+    stress.  STRONG scaling: the job is --mem-patterns patterns for every N; they are generated on the device (the
+    same batch on every rank), ordered by length and dealt round-robin (gcsa2_b200.dist.shard_patterns_by_length's rule),
+    so every rank scans the same mix of lengths.  value = patterns of the whole job / max over ranks of the scan time."""
+    from gcsa2_b200 import GCSA, LCPArray, mem_device, synth
+    flat, flcp = fixture["flat"], fixture["lcp"]
+    total = args.mem_patterns
+    d_seq = torch.from_numpy(fixture["seq"]).cuda()
+    all_chars, all_offsets = synth.device_mixed_length_patterns(d_seq, fixture["sites"], fixture["alt"], total, 16, 256, seed=5, error_rate=0.01)
+    d_chars, d_offsets, ids = synth.device_shard_by_length(all_chars, all_offsets, rank, world)
+    total_bytes = int(all_chars.numel())
+    del all_chars, all_offsets, d_seq
+    n = int(ids.numel())
+    index = GCSA(flat, device=local, kmer_table_k=0, walk_table=0, jump_table=False)      # the scan uses the fused blocks only
+    lcp = LCPArray(flcp, device=local)
+    stream = torch.cuda.current_stream()
+    d_out = torch.empty(n + 1, dtype=torch.int64, device="cuda")
+    cap = 16 * n
+    d_matches = torch.empty((cap, 4), dtype=torch.int64, device="cuda")
+    got = [0]
+
+    def step():
+        got[0] = mem_device(index, lcp, d_chars, d_offsets, n, d_out, d_matches, cap, stream.cuda_stream)
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize(); barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.mem_steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize(); barrier()
+    ms = e0.elapsed_time(e1) / args.mem_steps
+    matches, patterns, my_bytes = got[0], n, int(d_offsets[-1].item())
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        cnt = torch.tensor([patterns, matches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(cnt)
+        patterns, matches = int(cnt[0]), int(cnt[1])
+    out = {"metric": "mem_scan_patterns_per_sec", "value": patterns / (ms / 1000.0), "unit": "patterns/s", "scaling": "strong", "n_gpus": world,
+           "ms_per_step": ms, "patterns": patterns, "matches": matches, "pattern_bytes": total_bytes,
+           "config": {"workload": "cfg5: %d patterns, lengths uniform in 16..256, sampled from walks through the %g Mbp 1 %% SNP graph (seed 3) with 1 %% "
+                                  "substitutions (device generator, seed 5); MEM-style scan (LF while the range is not empty, else report and parent()); "
+                                  "dealt round-robin in length order to %d GPU(s), index + LCP array replicated" % (total, args.locate_mbp, world),
+                      "index": {"path_nodes": index.size(), "device_bytes": index.deviceBytes(), "lcp_levels": int(flcp.levels)},
+                      "steps": args.mem_steps}}
+    if rank == 0:
+        # Work of the reference loop on this rank's share: one LF step per pattern character (2 rank probes on B_c and 2 on
+        # `edges` in the reference; here two fused sectors at most) and one parent() per reported match; 32 B per match out.
+        peak, peak_src = peaks()
+        algorithmic = 128.0 * my_bytes + 128.0 * got[0] + 32.0 * got[0] + my_bytes + 8.0 * n
+        out["roofline"] = {"bound": "hbm", "achieved": algorithmic / (ms / 1000.0) / 1e9, "peak": peak, "unit": "GB/s",
+                           "frac": algorithmic / (ms / 1000.0) / 1e9 / peak, "traffic": None, "kernel": "mem_kernel<2,false>", "peak_source": peak_src,
+                           "accounting": "per GPU (rank 0): 2 fused sectors (2 x 64 B) per pattern character, 2 x 64 B per parent(), 32 B per match written, "
+                                         "the pattern bytes and 8 B of offsets per pattern.  The index (84 MB of fused blocks, 58 MB of LCP tree) fits the L2, "
+                                         "so this path is bound by instruction issue and divergence, not by HBM: see profiles/"}
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import oracle as orc
+        threads = orc.lib().oracle_max_threads()
+        m = min(n, args.mem_cpu_sample)
+        h_off = d_offsets[:m + 1].cpu().numpy().astype(np.uint64)
+        h_chars = d_chars[:int(h_off[m])].cpu().numpy()
+        eoffs, evals, secs = orc.mem_batch(orc.OracleGCSA(flat), orc.OracleLCP(flcp), h_chars, h_off, threads=threads)
+        k = int(eoffs[m])
+        moffs = d_out[:m + 1].cpu().numpy().view(np.uint64); mvals = d_matches[:k].cpu().numpy().view(np.uint64)
+        out["cpu_baseline"] = {"value": m / secs, "unit": "patterns/s", "cores": threads, "kind": "port", "seconds": secs,
+                               "sample": "the first %d patterns of rank 0's share, %d OpenMP threads; the scan loop is this repository's (the reference ships "
+                                         "LF and parent but no driver), run over the C restatement of both" % (m, threads),
+                               "parity_on_sample": bool((moffs == eoffs).all() and (mvals.reshape(-1, 4) == evals.reshape(-1, 4)).all())}
+    index.close(); lcp.close()
     return out
 
 
@@ -609,13 +705,25 @@ def main():
     else:
         total_q, total_found = n, found
 
-    locate = None
-    if not args.no_locate:
+    locate = mem = fixture = None
+    if not (args.no_locate and args.no_mem):
         try:
             del d_chars, h_chars
-            locate = locate_leg(args, rank, world, local, barrier, dist, torch)
+            fixture = cfg3_fixture(args, rank, world, barrier)
+        except Exception as exc:
+            locate = mem = {"error": "cfg3 fixture: %s: %s" % (type(exc).__name__, exc)}
+    if fixture is not None and not args.no_locate:
+        try:
+            locate = locate_leg(args, rank, world, local, barrier, dist, torch, fixture)
         except Exception as exc:                                    # the find() line must survive a failure here
             locate = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    if fixture is not None and not args.no_mem:
+        try:
+            torch.cuda.empty_cache()
+            mem = mem_leg(args, rank, world, local, barrier, dist, torch, fixture)
+        except Exception as exc:
+            mem = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    fixture = None
 
     cfg4 = None
     if not args.no_cfg4:
@@ -674,6 +782,8 @@ def main():
             line["e2e"]["note"] = e2e_note
         if locate is not None:
             line["locate"] = locate
+        if mem is not None:
+            line["cfg5"] = mem
         if cfg4 is not None:
             line["cfg4"] = cfg4
         if secondary is not None:

@@ -56,11 +56,21 @@ __device__ __forceinline__ u32 pack8_reversed(u64 w, u32* good)
   characters, another alphabet, short remainders) goes through the per-character path, which is the
   reference's loop verbatim.
 */
-template<bool STATS, int MIN_BLOCKS, bool PACKED = false>
+// Work-list entries of the two-kernel form (find_fast_kernel below leaves what it cannot finish with one or two
+// probes to this kernel): query number | remaining characters << 48 | flags.
+#define WORK_QUERY_MASK ((1ull << 48) - 1)
+#define WORK_NO_JUMP (1ull << 62)        // a jump failed on a character: the query dies within a few single steps
+#define WORK_FRESH   (1ull << 63)        // nothing is known yet: search from the last character
+
+template<bool STATS, int MIN_BLOCKS, bool PACKED = false, bool WORK = false>
 __global__ void __launch_bounds__(256, MIN_BLOCKS)
 find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict__ offsets, u64 char_base,
-            u64 fixed_length, u64 n, u64* __restrict__ sp_out, u64* __restrict__ ep_out, FindStatsDev* stats, int refill_at)
+            u64 fixed_length, u64 n, u64* __restrict__ sp_out, u64* __restrict__ ep_out, FindStatsDev* stats, int refill_at,
+            const u64* __restrict__ work = nullptr, const unsigned long long* __restrict__ work_count = nullptr)
 {
+  // WORK: the queries are those of the work list (fixed-length patterns); an entry that is not FRESH resumes from the
+  // range stored in sp_out / ep_out with `remaining` characters to go.
+  if(WORK) { n = *work_count; }
   // PACKED: `chars` holds ceil(fixed_length / 32) 64-bit words per pattern, character p of a pattern at bits
   // [2 (p % 32), 2 (p % 32) + 2) of word p / 32, value comp - 1 (ACGT only; packed by the host entry point).
   __shared__ u8 c2c[256];
@@ -154,12 +164,21 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
         if(cand < slice_end)
         {
           q = cand;
+          u64 entry = 0;
+          if(WORK) { entry = work[cand]; q = entry & WORK_QUERY_MASK; }
           u64 b, e;
           if(offsets != nullptr) { b = offsets[q] - char_base; e = offsets[q + 1] - char_base; }
           else { b = q * fixed_length; e = b + fixed_length; }
           begin = b; live = true; jump_mode = 1;
           tail = 0; tail_n = 0; tail_end = e;
           if(e == b || v.path_nodes == 0) { sp = 0; ep = v.path_nodes - 1; pos = b; }
+          else if(WORK && !(entry & WORK_FRESH))
+          {
+            pack_tail(e);
+            sp = sp_out[q]; ep = ep_out[q];
+            pos = b + ((entry >> 48) & 0xFF);
+            if(entry & WORK_NO_JUMP) { jump_mode = 0; }
+          }
           else
           {
             pack_tail(e);
@@ -232,20 +251,21 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
         // Singleton range: try the jump table (one load for up to jump_k backward steps along a unary path).
         // The table is chosen by what is left of the pattern, so that a path never overshoots its end: the long
         // table (paths of up to jump_k steps) while at least jump_k characters remain, the short one (4) below that.
-        const u64* jump_from = nullptr;
-        if(v.jump != nullptr && jump_mode != 0 && sp == ep)
+        const u64* jump_from = nullptr; bool jump_wide = false;
+        if((v.jump != nullptr || v.jump_wide != nullptr) && jump_mode != 0 && sp == ep)
         {
           u64 left = pos - begin;
-          jump_from = (left >= (u64)v.jump_k ? v.jump : (left >= 4 ? v.jump_short : nullptr));
+          if(left >= (u64)v.jump_k) { jump_from = v.jump; jump_wide = (v.jump_wide != nullptr); }
+          else if(left >= 4) { jump_from = v.jump_short; }
         }
-        if(jump_from != nullptr)
+        if(jump_from != nullptr || jump_wide)
         {
-          u64 e = __ldg(jump_from + sp);
-          u32 len = (u32)(e >> 59);
+          JumpPath path = (jump_wide ? jump_decode_wide(__ldg(v.jump_wide + sp)) : jump_decode(__ldg(jump_from + sp), v.jump_tbits));
+          u32 len = path.len;
           if(STATS) { sectors++; }
           if(len >= 2)
           {
-            u64 stored = ((e << 5) >> 5) >> v.jump_tbits;
+            u64 stored = path.chars;
             u64 off = tail_end - pos;
             if(off + len > (u64)tail_n && fast_pack && tail_n == 32) { pack_tail(pos); off = 0; }
             bool same = true;
@@ -260,7 +280,7 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
             }
             if(same)
             {
-              sp = ep = (e & ((1ull << v.jump_tbits) - 1));
+              sp = ep = path.target;
               pos -= len; done = true;
               if(STATS) { st_steps += len; }
             }
@@ -295,6 +315,123 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
     }
   }
 
+  if(STATS)
+  {
+    atomicAdd((ull*)&stats->found, (ull)st_found); atomicAdd((ull*)&stats->total_length, (ull)st_len);
+    atomicAdd((ull*)&stats->lf_steps, (ull)st_steps); atomicAdd((ull*)&stats->sector_probes, (ull)st_sectors);
+    atomicAdd((ull*)&stats->table_hits, (ull)st_hits);
+  }
+}
+
+/*
+  The first kernel of the two-kernel form of find() for batches of k-mers (one fixed length L, table_k <= L <= 32,
+  default alphabet, a k-mer table): ONE QUERY PER THREAD, no loop.  A thread reads its pattern (consecutive threads,
+  consecutive patterns: the loads coalesce), packs it to 2 bits per character, looks the last table_k characters up in
+  the k-mer table and, if the result is one path node and characters remain, takes one jump (fused with the table
+  entry, or one more load).  That finishes most k-mers of a large reference (a 32-mer over a 16-mer table: table
+  entry + 16-step jump); the queries it cannot finish -- a range of several nodes, a jump that is too short or fails,
+  another character in the pattern -- are appended to a work list with their state (the range goes into sp_out /
+  ep_out) and the general kernel resumes them (find_kernel<.., WORK = true>).  Compared with running everything through
+  the general kernel: no refill logic, no divergence between lanes in different phases, a third of the instructions.
+*/
+template<bool STATS, bool PACKED>
+__global__ void __launch_bounds__(256)
+find_fast_kernel(const DevView v, const u8* __restrict__ chars, u32 L, u64 n, u64* __restrict__ sp_out, u64* __restrict__ ep_out,
+                 u64* __restrict__ work, unsigned long long* __restrict__ work_count, FindStatsDev* stats)
+{
+  const u32 lane = threadIdx.x & 31;
+  const u32 k = (u32)v.table_k;
+  const u64 kmask = (k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1));
+  u64 st_found = 0, st_len = 0, st_steps = 0, st_sectors = 0, st_hits = 0;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const u64 rounds = (n + stride - 1) / stride;
+  for(u64 r = 0; r < rounds; r++)
+  {
+    const u64 q = r * stride + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 entry = 0;                         // work-list entry, 0 = finished here
+    if(q < n)
+    {
+      // ---- the pattern, 2 bits per character, the LAST character in the lowest bits ----
+      u64 tail = 0; bool valid = true;
+      if(PACKED)
+      {
+        u64 x = __ldcs((const unsigned long long*)chars + q);
+        u64 t = __brevll(x);
+        t = ((t >> 1) & 0x5555555555555555ull) | ((t & 0x5555555555555555ull) << 1);
+        tail = (L < 32 ? t >> (2 * (32 - L)) : t);
+      }
+      else
+      {
+        // the 32 bytes that end with the pattern (the first of them belong to the previous pattern if L < 32)
+        const u64 end = (u64)chars + (q + 1) * (u64)L;
+        if(end - 32 < (u64)chars) { valid = false; }                     // would read before the buffer: left to the general kernel
+        else
+        {
+          const u64 a = end - 32; const u32 sh = (u32)(a & 7) * 8;
+          const unsigned long long* base = (const unsigned long long*)(a - (a & 7));
+          u64 w0 = __ldcs(base), w1 = __ldcs(base + 1), w2 = __ldcs(base + 2), w3 = __ldcs(base + 3);
+          if(sh != 0)
+          {
+            u64 w4 = __ldcs(base + 4);
+            w0 = (w0 >> sh) | (w1 << (64 - sh)); w1 = (w1 >> sh) | (w2 << (64 - sh));
+            w2 = (w2 >> sh) | (w3 << (64 - sh)); w3 = (w3 >> sh) | (w4 << (64 - sh));
+          }
+          u32 g0, g1, g2, g3;
+          u64 p3 = pack8_reversed(w3, &g3), p2 = pack8_reversed(w2, &g2), p1 = pack8_reversed(w1, &g1), p0 = pack8_reversed(w0, &g0);
+          tail = p3 | (p2 << 16) | (p1 << 32) | (p0 << 48);
+          // how many characters, counted from the last one, are bases
+          u32 good = (g3 < 8 ? g3 : 8 + (g2 < 8 ? g2 : 8 + (g1 < 8 ? g1 : 8 + g0)));
+          valid = (good >= L);
+        }
+      }
+      if(!valid) { entry = q | WORK_FRESH; }
+      else
+      {
+        u64 res, je = 0;
+        const u64 idx = tail & kmask;
+        if(v.table2 != nullptr) { ulonglong2 both = __ldg(v.table2 + idx); res = both.x; je = both.y; }
+        else { res = __ldg(v.table + idx); }
+        if(STATS) { st_hits++; }
+        const u64 len = res >> 40;
+        if(len == TABLE_ESCAPE) { entry = q | WORK_FRESH; }
+        else
+        {
+          u64 sp = res & M40, ep = sp + len - 1;
+          u32 rem = L - k;
+          if(len == 1 && rem > 0)
+          {
+            // one path node: its unary backward path, from the fused entry or from the long jump table
+            JumpPath path; path.len = 0; path.chars = 0; path.target = 0;
+            if(v.table2 != nullptr) { path = jump_decode(je, v.jump_tbits); }
+            else if(rem >= v.jump_k && v.jump_wide != nullptr) { path = jump_decode_wide(__ldg(v.jump_wide + sp)); if(STATS) { st_sectors++; } }
+            else if(rem >= v.jump_k && v.jump != nullptr) { path = jump_decode(__ldg(v.jump + sp), v.jump_tbits); if(STATS) { st_sectors++; } }
+            if(path.len >= 2 && path.len <= rem)
+            {
+              if((((tail >> (2 * k)) ^ path.chars) & ((1ull << (2 * path.len)) - 1)) == 0)
+              {
+                sp = ep = path.target; rem -= path.len;
+                if(STATS) { st_steps += path.len; }
+              }
+              else { entry = q | ((u64)rem << 48) | WORK_NO_JUMP; }       // it dies within these steps: the exact pair comes from single steps
+            }
+          }
+          if(entry == 0 && rem > 0 && len > 0) { entry = q | ((u64)rem << 48); }
+          __stcs((unsigned long long*)sp_out + q, (unsigned long long)sp); __stcs((unsigned long long*)ep_out + q, (unsigned long long)ep);
+          if(STATS && entry == 0 && !range_empty(sp, ep)) { st_found++; st_len += ep + 1 - sp; }
+        }
+      }
+    }
+    // append the unfinished queries of the warp to the work list (one atomic per warp)
+    const u32 todo = __ballot_sync(0xFFFFFFFFu, entry != 0);
+    if(todo != 0)
+    {
+      unsigned long long base = 0;
+      const u32 leader = (u32)__ffs((int)todo) - 1;
+      if(lane == leader) { base = atomicAdd(work_count, (unsigned long long)__popc(todo)); }
+      base = __shfl_sync(0xFFFFFFFFu, base, (int)leader);
+      if(entry != 0) { work[base + __popc(todo & ((1u << lane) - 1))] = entry; }
+    }
+  }
   if(STATS)
   {
     atomicAdd((ull*)&stats->found, (ull)st_found); atomicAdd((ull*)&stats->total_length, (ull)st_len);

@@ -72,6 +72,41 @@ static int fail(int code, const std::string& msg) { g_last_error = msg; return c
   return fail(GCSA_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } } while(0)
 
 //------------------------------------------------------------------------------
+// Stream-ordered temporaries come from a pool of the library's own (one per device, created on first use, never
+// trimmed between calls): the host application's default pool and its attributes are left alone.
+//------------------------------------------------------------------------------
+
+static cudaError_t enginePoolAlloc(void** p, size_t bytes, cudaStream_t stream)
+{
+  static std::mutex mutex;
+  static cudaMemPool_t pools[64] = {};
+  int device = 0;
+  cudaError_t e = cudaGetDevice(&device);
+  if(e != cudaSuccess) { return e; }
+  if(device < 0 || device >= 64) { return cudaErrorInvalidValue; }
+  cudaMemPool_t pool = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(mutex);
+    if(pools[device] == nullptr)
+    {
+      cudaMemPoolProps props;
+      std::memset(&props, 0, sizeof(props));
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = device;
+      e = cudaMemPoolCreate(&pools[device], &props);
+      if(e != cudaSuccess) { pools[device] = nullptr; return e; }
+      uint64_t keep = ~0ull;      // do not hand the memory back to the driver between calls
+      cudaMemPoolSetAttribute(pools[device], cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    pool = pools[device];
+  }
+  return cudaMallocFromPoolAsync(p, bytes, pool, stream);
+}
+template<class T> static cudaError_t engineMallocAsync(T** p, size_t bytes, cudaStream_t stream) { return enginePoolAlloc((void**)p, bytes, stream); }
+
+//------------------------------------------------------------------------------
 // Host side: handles
 //------------------------------------------------------------------------------
 
@@ -334,14 +369,6 @@ int gcsa_b200_index_create(const gcsa_flat_index* host, int device, const gcsa_b
   DeviceGuard guard(device);
   if(!guard.ok) { return fail(GCSA_B200_ERR_CUDA, "index_create: cudaSetDevice failed"); }
 
-  {
-    cudaMemPool_t pool;
-    if(cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
-    {
-      uint64_t keep = ~0ull;      // do not hand stream-ordered allocations back to the OS between calls
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-  }
   if(const char* g = std::getenv("GCSA_B200_L2_FETCH"))
   {
     // Random 32-byte sector probes: ask the L2 not to over-fetch neighbouring sectors from HBM.
@@ -719,6 +746,10 @@ int gcsa_b200_char_range(const gcsa_b200_index* index, uint64_t comp, uint64_t* 
 // find
 //------------------------------------------------------------------------------
 
+// Measurement hook (not part of the C ABI): how many batches of this process took the two-kernel form.
+static std::atomic<unsigned long long> g_fast_launches(0);
+extern "C" unsigned long long gcsa_b200_internal_fast_launches(void) { return g_fast_launches.load(); }
+
 static int launchFind(const gcsa_b200_index* index, const u8* d_chars, const u64* d_offsets, u64 char_base, u64 fixed_length,
                       u64 n, u64* d_sp, u64* d_ep, FindStatsDev* d_stats, cudaStream_t stream, bool packed = false)
 {
@@ -731,6 +762,43 @@ static int launchFind(const gcsa_b200_index* index, const u8* d_chars, const u64
   int grid = gridFor(n, index->sm_count, per_sm);
   // idle lanes of a warp are refilled together once this many are idle (16 measured best: DESIGN.md)
   static const int refill_at = []() { const char* e = std::getenv("GCSA_B200_FIND_REFILL"); int r = (e ? std::atoi(e) : 16); return std::min(32, std::max(1, r)); }();
+  // Batches of k-mers (one length between the k-mer table's and 32, the default alphabet): the two-kernel form -- one
+  // probe (or two) per thread for everything, then the general kernel for the work list of what that left unfinished.
+  static const bool fast_off = []() { const char* e = std::getenv("GCSA_B200_FIND_FAST"); return (e != nullptr && std::atoi(e) == 0); }();
+  const DevView& v = index->view;
+  if(!fast_off && d_offsets == nullptr && fixed_length <= 32 && v.table_k > 0 && fixed_length >= (u64)v.table_k &&
+     (packed || v.default_alphabet != 0) && n >= 4096 && n < (1ull << 47))
+  {
+    u64* work = nullptr; unsigned long long* count = nullptr;
+    CUDA_TRY(engineMallocAsync(&work, n * sizeof(u64) + 256, stream));
+    count = (unsigned long long*)(work + n);                           // the counter lives behind the list
+    cudaError_t e = cudaMemsetAsync(count, 0, sizeof(unsigned long long), stream);
+    if(e == cudaSuccess)
+    {
+      int fast_grid = gridFor(n, index->sm_count, 8);
+      int slow_grid = gridFor(n, index->sm_count, d_stats ? 1 : 4);
+      const u32 L = (u32)fixed_length;
+      if(d_stats)
+      {
+        if(packed) { find_fast_kernel<true, true><<<fast_grid, 256, 0, stream>>>(v, d_chars, L, n, d_sp, d_ep, work, count, d_stats); }
+        else { find_fast_kernel<true, false><<<fast_grid, 256, 0, stream>>>(v, d_chars, L, n, d_sp, d_ep, work, count, d_stats); }
+        if(packed) { find_kernel<true, 1, true, true><<<slow_grid, 256, 0, stream>>>(v, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, d_stats, refill_at, work, count); }
+        else { find_kernel<true, 1, false, true><<<slow_grid, 256, 0, stream>>>(v, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, d_stats, refill_at, work, count); }
+      }
+      else
+      {
+        if(packed) { find_fast_kernel<false, true><<<fast_grid, 256, 0, stream>>>(v, d_chars, L, n, d_sp, d_ep, work, count, nullptr); }
+        else { find_fast_kernel<false, false><<<fast_grid, 256, 0, stream>>>(v, d_chars, L, n, d_sp, d_ep, work, count, nullptr); }
+        if(packed) { find_kernel<false, 4, true, true><<<slow_grid, 256, 0, stream>>>(v, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, nullptr, refill_at, work, count); }
+        else { find_kernel<false, 4, false, true><<<slow_grid, 256, 0, stream>>>(v, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, nullptr, refill_at, work, count); }
+      }
+      e = cudaGetLastError();
+    }
+    cudaFreeAsync(work, stream);
+    CUDA_TRY(e);
+    g_fast_launches.fetch_add(1);
+    return 0;
+  }
   #define LAUNCH_FIND(S, B) find_kernel<S, B><<<grid, 256, 0, stream>>>(index->view, d_chars, d_offsets, char_base, fixed_length, n, d_sp, d_ep, d_stats, refill_at)
   if(packed)
   {
@@ -1056,7 +1124,7 @@ struct Scratch
   template<class T> T* alloc(u64 count)
   {
     void* p = nullptr;
-    if(cudaMallocAsync(&p, std::max<u64>(count, 1) * sizeof(T), stream) != cudaSuccess) { return nullptr; }
+    if(engineMallocAsync(&p, std::max<u64>(count, 1) * sizeof(T), stream) != cudaSuccess) { return nullptr; }
     ptrs.push_back(p);
     return (T*)p;
   }
@@ -1185,7 +1253,7 @@ template<class T> int scanExclusive(const T* in, T* out, u64 count, cudaStream_t
   size_t bytes = 0;
   CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, count, st));
   void* tmp = nullptr;
-  CUDA_TRY(cudaMallocAsync(&tmp, std::max<size_t>(bytes, 16), st));
+  CUDA_TRY(engineMallocAsync(&tmp, std::max<size_t>(bytes, 16), st));
   cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, count, st);
   cudaFreeAsync(tmp, st);
   CUDA_TRY(e);
@@ -1204,7 +1272,7 @@ int locateGeneral(const gcsa_b200_index* index, const u64* d_sp, const u64* d_ep
   const DevView& v = index->view;
   const int sm = index->sm_count;
   std::vector<void*> tmp;
-  auto alloc = [&](u64 bytes) -> void* { void* p = nullptr; if(cudaMallocAsync(&p, std::max<u64>(bytes, 16), st) != cudaSuccess) { return nullptr; } tmp.push_back(p); return p; };
+  auto alloc = [&](u64 bytes) -> void* { void* p = nullptr; if(engineMallocAsync(&p, std::max<u64>(bytes, 16), st) != cudaSuccess) { return nullptr; } tmp.push_back(p); return p; };
   auto cleanup = [&]() { for(void* p : tmp) { cudaFreeAsync(p, st); } tmp.clear(); };
   #define LOC_TRY(expr) do { cudaError_t e_ = (expr); if(e_ != cudaSuccess) { cleanup(); \
     return fail(GCSA_B200_ERR_CUDA, std::string("locate: " #expr ": ") + cudaGetErrorString(e_)); } } while(0)
@@ -1260,7 +1328,7 @@ int locateGeneral(const gcsa_b200_index* index, const u64* d_sp, const u64* d_ep
     if(d_values_alloc != nullptr)
     {
       void* p = nullptr;
-      LOC_TRY(cudaMallocAsync(&p, std::max<u64>(total, 1) * sizeof(u64), st));
+      LOC_TRY(engineMallocAsync(&p, std::max<u64>(total, 1) * sizeof(u64), st));
       *d_values_alloc = (u64*)p; d_values = (u64*)p; capacity = total;
     }
     if(d_values == nullptr || capacity < total) { rc0 = GCSA_B200_ERR_CAPACITY; g_last_error = "locate: output capacity too small"; }
@@ -1287,7 +1355,7 @@ int locateGeneral(const gcsa_b200_index* index, const u64* d_sp, const u64* d_ep
   if(d_values_alloc != nullptr)
   {
     void* p = nullptr;
-    LOC_TRY(cudaMallocAsync(&p, std::max<u64>(distinct, 1) * sizeof(u64), st));
+    LOC_TRY(engineMallocAsync(&p, std::max<u64>(distinct, 1) * sizeof(u64), st));
     *d_values_alloc = (u64*)p; d_values = (u64*)p; capacity = distinct;
   }
   if(d_values == nullptr || capacity < distinct) { rc = GCSA_B200_ERR_CAPACITY; g_last_error = "locate: output capacity too small"; }
@@ -1316,7 +1384,7 @@ int locateDevice(const gcsa_b200_index* index, const u64* d_sp, const u64* d_ep,
   const int sm = index->sm_count;
   std::vector<void*> tmp;
   u64* gvals = nullptr;
-  auto alloc = [&](u64 bytes) -> void* { void* p = nullptr; if(cudaMallocAsync(&p, std::max<u64>(bytes, 16), st) != cudaSuccess) { return nullptr; } tmp.push_back(p); return p; };
+  auto alloc = [&](u64 bytes) -> void* { void* p = nullptr; if(engineMallocAsync(&p, std::max<u64>(bytes, 16), st) != cudaSuccess) { return nullptr; } tmp.push_back(p); return p; };
   auto cleanup = [&]() { for(void* p : tmp) { cudaFreeAsync(p, st); } tmp.clear(); if(gvals) { cudaFreeAsync(gvals, st); gvals = nullptr; } };
 
   u64* cnt = (u64*)alloc((n + 1) * sizeof(u64));
@@ -1353,7 +1421,7 @@ int locateDevice(const gcsa_b200_index* index, const u64* d_sp, const u64* d_ep,
   if(d_values_alloc != nullptr)
   {
     void* p = nullptr;
-    LOC_TRY(cudaMallocAsync(&p, std::max<u64>(distinct, 1) * sizeof(u64), st));
+    LOC_TRY(engineMallocAsync(&p, std::max<u64>(distinct, 1) * sizeof(u64), st));
     *d_values_alloc = (u64*)p; d_values = (u64*)p; capacity = distinct;
   }
   if(d_values == nullptr || capacity < distinct) { rc = GCSA_B200_ERR_CAPACITY; g_last_error = "locate: output capacity too small"; }
@@ -1463,8 +1531,8 @@ int gcsa_b200_locate_into_host(const gcsa_b200_index* index, const uint64_t* sp,
     cudaStream_t st = streams[c % STREAMS];
     u64 q0 = c * CHUNK, m = std::min(n, q0 + CHUNK) - q0;
     Chunk& ch = chunks[c];
-    if(cudaMallocAsync((void**)&ch.d_sp, m * sizeof(u64), st) != cudaSuccess || cudaMallocAsync((void**)&ch.d_ep, m * sizeof(u64), st) != cudaSuccess ||
-       cudaMallocAsync((void**)&ch.d_offs, (m + 1) * sizeof(u64), st) != cudaSuccess)
+    if(engineMallocAsync((void**)&ch.d_sp, m * sizeof(u64), st) != cudaSuccess || engineMallocAsync((void**)&ch.d_ep, m * sizeof(u64), st) != cudaSuccess ||
+       engineMallocAsync((void**)&ch.d_offs, (m + 1) * sizeof(u64), st) != cudaSuccess)
     {
       return fail(GCSA_B200_ERR_NOMEM, "locate_into_host: out of device memory");
     }
@@ -1784,15 +1852,15 @@ int gcsa_b200_count_kmers(const gcsa_b200_index* index, uint64_t k, int include_
   #define KM_TRY(expr) do { e = (expr); if(e != cudaSuccess) { rc = fail(GCSA_B200_ERR_CUDA, std::string("count_kmers: " #expr ": ") + cudaGetErrorString(e)); goto done; } } while(0)
   {
     u64 root[2] = { 0, index->header.path_nodes - 1 };
-    KM_TRY(cudaMallocAsync(&sp, sizeof(u64), st)); KM_TRY(cudaMallocAsync(&ep, sizeof(u64), st));
+    KM_TRY(engineMallocAsync(&sp, sizeof(u64), st)); KM_TRY(engineMallocAsync(&ep, sizeof(u64), st));
     KM_TRY(cudaMemcpyAsync(sp, &root[0], sizeof(u64), cudaMemcpyHostToDevice, st));
     KM_TRY(cudaMemcpyAsync(ep, &root[1], sizeof(u64), cudaMemcpyHostToDevice, st));
     for(u64 level = 0; level < k && n > 0; level++)
     {
       u64 total = n * chars;
       u64 *csp = nullptr, *cep = nullptr, *flag = nullptr, *pos = nullptr;
-      KM_TRY(cudaMallocAsync(&csp, total * sizeof(u64), st)); KM_TRY(cudaMallocAsync(&cep, total * sizeof(u64), st));
-      KM_TRY(cudaMallocAsync(&flag, (total + 1) * sizeof(u64), st)); KM_TRY(cudaMallocAsync(&pos, (total + 1) * sizeof(u64), st));
+      KM_TRY(engineMallocAsync(&csp, total * sizeof(u64), st)); KM_TRY(engineMallocAsync(&cep, total * sizeof(u64), st));
+      KM_TRY(engineMallocAsync(&flag, (total + 1) * sizeof(u64), st)); KM_TRY(engineMallocAsync(&pos, (total + 1) * sizeof(u64), st));
       KM_TRY(cudaMemsetAsync(flag + total, 0, sizeof(u64), st));
       kmer_expand_kernel<<<gridFor(total, index->sm_count), 256, 0, st>>>(index->view, sp, ep, n, chars, csp, cep, flag);
       rc = scanExclusive(flag, pos, total + 1, st);
@@ -1801,7 +1869,7 @@ int gcsa_b200_count_kmers(const gcsa_b200_index* index, uint64_t k, int include_
       KM_TRY(cudaMemcpyAsync(&next, pos + total, sizeof(u64), cudaMemcpyDeviceToHost, st));
       KM_TRY(cudaStreamSynchronize(st));
       cudaFreeAsync(sp, st); cudaFreeAsync(ep, st); sp = ep = nullptr;
-      KM_TRY(cudaMallocAsync(&sp, std::max<u64>(next, 1) * sizeof(u64), st)); KM_TRY(cudaMallocAsync(&ep, std::max<u64>(next, 1) * sizeof(u64), st));
+      KM_TRY(engineMallocAsync(&sp, std::max<u64>(next, 1) * sizeof(u64), st)); KM_TRY(engineMallocAsync(&ep, std::max<u64>(next, 1) * sizeof(u64), st));
       kmer_compact_kernel<<<gridFor(total, index->sm_count), 256, 0, st>>>(csp, cep, flag, pos, total, sp, ep);
       cudaFreeAsync(csp, st); cudaFreeAsync(cep, st); cudaFreeAsync(flag, st); cudaFreeAsync(pos, st);
       n = next;
@@ -1853,7 +1921,7 @@ int gcsa_b200_compare_kmers(const gcsa_b200_index* left, const gcsa_b200_index* 
   u64* state = nullptr; u64* kmer = nullptr;
   cudaError_t e = cudaSuccess;
   #define CK_TRY(expr) do { e = (expr); if(e != cudaSuccess) { rc = fail(GCSA_B200_ERR_CUDA, std::string("compare_kmers: " #expr ": ") + cudaGetErrorString(e)); goto done; } } while(0)
-  #define CK_ALLOC(ptr, count) do { CK_TRY(cudaMallocAsync((void**)&(ptr), std::max<u64>((count), 1) * sizeof(u64), st)); } while(0)
+  #define CK_ALLOC(ptr, count) do { CK_TRY(engineMallocAsync((void**)&(ptr), std::max<u64>((count), 1) * sizeof(u64), st)); } while(0)
   {
     CK_ALLOC(state, 4); CK_TRY(cudaMemcpyAsync(state, root, sizeof(root), cudaMemcpyHostToDevice, st));
     if(want) { CK_ALLOC(kmer, 3); CK_TRY(cudaMemcpyAsync(kmer, zero_kmer, sizeof(zero_kmer), cudaMemcpyHostToDevice, st)); }
@@ -1880,7 +1948,7 @@ int gcsa_b200_compare_kmers(const gcsa_b200_index* left, const gcsa_b200_index* 
     if(n > 0)
     {
       ull* counts = nullptr; u64 *lflag = nullptr, *rflag = nullptr, *lpos = nullptr, *rpos = nullptr;
-      CK_TRY(cudaMallocAsync((void**)&counts, 3 * sizeof(ull), st));
+      CK_TRY(engineMallocAsync((void**)&counts, 3 * sizeof(ull), st));
       CK_TRY(cudaMemsetAsync(counts, 0, 3 * sizeof(ull), st));
       if(want)
       {
@@ -1961,7 +2029,7 @@ static int memDevice(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, con
   if(stride < 4 && std::getenv("GCSA_B200_MEM_STRIDE") == nullptr) { stride = 0; }
 
   std::vector<void*> tmp;
-  auto alloc = [&](u64 bytes) -> void* { void* p = nullptr; if(cudaMallocAsync(&p, std::max<u64>(bytes, 16), st) != cudaSuccess) { cudaGetLastError(); return nullptr; } tmp.push_back(p); return p; };
+  auto alloc = [&](u64 bytes) -> void* { void* p = nullptr; if(engineMallocAsync(&p, std::max<u64>(bytes, 16), st) != cudaSuccess) { cudaGetLastError(); return nullptr; } tmp.push_back(p); return p; };
   auto cleanup = [&]() { for(void* p : tmp) { cudaFreeAsync(p, st); } tmp.clear(); };
   #define MEM_TRY(expr) do { cudaError_t e_ = (expr); if(e_ != cudaSuccess) { cleanup(); \
     return fail(GCSA_B200_ERR_CUDA, std::string("mem_batch: " #expr ": ") + cudaGetErrorString(e_)); } } while(0)
@@ -2000,7 +2068,7 @@ static int memDevice(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, con
   if(d_matches_alloc != nullptr)
   {
     void* p = nullptr;
-    MEM_TRY(cudaMallocAsync(&p, std::max<u64>(total, 1) * 32, st));
+    MEM_TRY(engineMallocAsync(&p, std::max<u64>(total, 1) * 32, st));
     *d_matches_alloc = (u64*)p; d_matches = (u64*)p; capacity = total;
   }
   if(d_matches == nullptr || capacity < total) { cleanup(); return fail(GCSA_B200_ERR_CAPACITY, "mem_batch: output capacity too small"); }

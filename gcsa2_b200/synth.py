@@ -214,3 +214,63 @@ def device_patterns(seq, n, length, seed, chunk=1 << 23):
         comps = windows[starts[a:b]]
         out[a * length:b * length] = lut[comps.reshape(-1).long()]
     return out
+
+
+def device_mixed_length_patterns(seq, sites, alt, n, min_len, max_len, seed, error_rate=0.01):
+    """Config 5 on the device: n patterns, lengths uniform in [min_len, max_len], each a walk through the SNP graph
+    (every site takes the alternative allele with probability 1/2) with substitutions at `error_rate`.  seq: CUDA uint8
+    comps; sites / alt: host arrays of snp_graph().  Counter-based randomness (splitmix64 of the pattern / character
+    index), so every rank regenerates the same batch.  -> (chars uint8 CUDA tensor of ASCII bytes, offsets int64 CUDA
+    tensor of n + 1)."""
+    import torch
+    dev = seq.device
+    L = int(seq.numel())
+    ids = torch.arange(int(n), dtype=torch.int64, device=dev)
+    h = _splitmix64_torch(ids, seed)
+    lengths = int(min_len) + (((h >> 1) & ((1 << 62) - 1)) % (int(max_len) - int(min_len) + 1))
+    starts = ((_splitmix64_torch(ids, seed + 1) >> 1) & ((1 << 62) - 1)) % (L - int(max_len))
+    offsets = torch.zeros(int(n) + 1, dtype=torch.int64, device=dev)
+    offsets[1:] = torch.cumsum(lengths, 0)
+    total = int(offsets[-1].item())
+    alt_full = torch.zeros(L, dtype=torch.uint8, device=dev)
+    alt_full[torch.as_tensor(np.asarray(sites, dtype=np.int64), device=dev)] = torch.as_tensor(np.asarray(alt, dtype=np.uint8), device=dev)
+    lut = torch.tensor(list(COMP2CHAR), dtype=torch.uint8, device=dev)
+    chars = torch.empty(total, dtype=torch.uint8, device=dev)
+    block = 1 << 18                                                   # patterns per block (bounds the int64 temporaries)
+    for a in range(0, int(n), block):
+        b = min(int(n), a + block)
+        c0, c1 = int(offsets[a].item()), int(offsets[b].item())
+        owner = torch.repeat_interleave(torch.arange(a, b, dtype=torch.int64, device=dev), lengths[a:b])
+        k = torch.arange(c0, c1, dtype=torch.int64, device=dev)
+        pos = starts[owner] + (k - offsets[owner])
+        comps = seq[pos]
+        r = _splitmix64_torch(k, seed + 2)
+        alts = alt_full[pos]
+        use_alt = (alts > 0) & (((r >> 40) & 1) == 1)
+        comps = torch.where(use_alt, alts, comps)
+        err = ((r >> 8) & 0xFFFFFF) < int(error_rate * (1 << 24))
+        shifted = ((comps.to(torch.int64) - 1 + 1 + ((r >> 34) & 3) % 3) % 4 + 1).to(torch.uint8)
+        comps = torch.where(err, shifted, comps)
+        chars[c0:c1] = lut[comps.long()]
+    return chars, offsets
+
+
+def device_shard_by_length(chars, offsets, rank, world):
+    """dist.shard_patterns_by_length on the device: the patterns ordered by length are dealt round-robin, the rank's
+    share is packed contiguously in increasing id order.  -> (chars, offsets, ids) CUDA tensors."""
+    import torch
+    lengths = offsets[1:] - offsets[:-1]
+    order = torch.sort(lengths, stable=True).indices
+    ids = torch.sort(order[int(rank)::int(world)]).values
+    mine = lengths[ids]
+    out_offsets = torch.zeros(ids.numel() + 1, dtype=torch.int64, device=chars.device)
+    out_offsets[1:] = torch.cumsum(mine, 0)
+    total = int(out_offsets[-1].item())
+    out_chars = torch.empty(max(total, 1), dtype=torch.uint8, device=chars.device)
+    block = 1 << 18
+    for a in range(0, int(ids.numel()), block):
+        b = min(int(ids.numel()), a + block)
+        c0, c1 = int(out_offsets[a].item()), int(out_offsets[b].item())
+        shift = torch.repeat_interleave(offsets[ids[a:b]] - out_offsets[a:b], mine[a:b])
+        out_chars[c0:c1] = chars[shift + torch.arange(c0, c1, dtype=torch.int64, device=chars.device)]
+    return out_chars[:total], out_offsets, ids

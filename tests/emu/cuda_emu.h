@@ -157,9 +157,13 @@ static inline cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuc
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* pool, int) { *pool = nullptr; return cudaSuccess; }
 static inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, cudaMemPoolAttr, void*) { return cudaSuccess; }
+enum { cudaMemAllocationTypePinned = 1, cudaMemHandleTypeNone = 0, cudaMemLocationTypeDevice = 1 };
+struct cudaMemPoolProps { int allocType, handleTypes; struct { int type, id; } location; };
+static inline cudaError_t cudaMemPoolCreate(cudaMemPool_t* pool, const cudaMemPoolProps*) { static int token; *pool = &token; return cudaSuccess; }
 static inline cudaError_t cudaMemGetInfo(size_t* free_b, size_t* total_b) { *free_b = *total_b = emu::envBytes("GCSA_EMU_FREE_BYTES", (size_t)8 << 30); return cudaSuccess; }
 template<class T> static inline cudaError_t cudaMalloc(T** p, size_t bytes) { *p = (T*)emu::alloc(bytes); return (*p != nullptr ? cudaSuccess : cudaErrorMemoryAllocation); }
 template<class T> static inline cudaError_t cudaMallocAsync(T** p, size_t bytes, cudaStream_t) { return cudaMalloc(p, bytes); }
+template<class T> static inline cudaError_t cudaMallocFromPoolAsync(T** p, size_t bytes, cudaMemPool_t, cudaStream_t) { return cudaMalloc(p, bytes); }
 template<class T> static inline cudaError_t cudaHostAlloc(T** p, size_t bytes, unsigned) { return cudaMalloc(p, bytes); }
 static inline cudaError_t cudaFree(void* p) { emu::release(p); return cudaSuccess; }
 static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { emu::release(p); return cudaSuccess; }

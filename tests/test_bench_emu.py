@@ -52,6 +52,9 @@ def host_stand_ins(monkeypatch):
     real_sequence, real_patterns = synth.device_sequence, synth.device_patterns
     monkeypatch.setattr(synth, "device_sequence", lambda length, seed, **k: on_device(real_sequence(length, seed, device="cpu")))
     monkeypatch.setattr(synth, "device_patterns", lambda *a, **k: on_device(real_patterns(*a, **k)))
+    real_mixed, real_shard = synth.device_mixed_length_patterns, synth.device_shard_by_length
+    monkeypatch.setattr(synth, "device_mixed_length_patterns", lambda *a, **k: tuple(on_device(t) for t in real_mixed(*a, **k)))
+    monkeypatch.setattr(synth, "device_shard_by_length", lambda *a, **k: tuple(on_device(t.clone()) for t in real_shard(*a, **k)))
     monkeypatch.setattr(torch.cuda, "empty_cache", lambda: None)
     monkeypatch.setattr(torch.cuda, "get_device_properties", lambda d: SimpleNamespace(total_memory=192 << 30))
     return build_emu
@@ -64,7 +67,8 @@ def test_bench_line_on_the_emulated_engine(monkeypatch, capsys):
     monkeypatch.delenv("GCSA_B200_HOST_PACK", raising=False)         # the default: raw copies and packing share the batch
     monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "2", "--warmup", "1", "--ref-mbp", "0.2", "--queries", "1100000",
                                       "--kmer-table-k", "8", "--locate-mbp", "0.2", "--locate-queries", "40000", "--cpu-sample", "20000",
-                                      "--cfg4-mbp", "0.05", "--cfg4-queries", "250000", "--cfg4-chunk", "100000", "--cfg4-steps", "1"])
+                                      "--cfg4-mbp", "0.05", "--cfg4-queries", "250000", "--cfg4-chunk", "100000", "--cfg4-steps", "1",
+                                      "--mem-patterns", "3000", "--mem-steps", "1", "--mem-cpu-sample", "1000"])
     bench.main()
     out = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
     assert len(out) == 1
@@ -83,6 +87,9 @@ def test_bench_line_on_the_emulated_engine(monkeypatch, capsys):
     assert line["secondary"]["parity_on_sample"] and line["secondary"]["found"] < 1_100_000 // 2
     for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert key in line["roofline"], key
+    c5 = line["cfg5"]
+    assert "error" not in c5, c5
+    assert c5["patterns"] == 3000 and c5["matches"] > 3000 and c5["cpu_baseline"]["parity_on_sample"] and "roofline" in c5
     c4 = line["cfg4"]
     assert "error" not in c4, c4
     assert c4["queries"] == c4["found"] == 250_000 and c4["scaling"] == "strong" and c4["cpu_baseline"]["parity_on_sample"]

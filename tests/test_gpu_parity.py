@@ -2,13 +2,15 @@
 
 Bit-exact comparison of every operation of SURVEY.md section 8(a): find, charRange, LF(range),
 LF(node), LF_fast/LF_all, count, locate (x3), parent, depth, psv/psev/nsv/nsev, rmq."""
+import ctypes
+
 import numpy as np
 import pytest
 
 from brute import random_graph
 from helpers import kat1_flat, load_kat1
 from verify import kmer_table, verify_index
-from gcsa2_b200 import GCSA, LCPArray, synth
+from gcsa2_b200 import GCSA, LCPArray, capi, synth
 from gcsa2_b200.builder import CharGraph, build_index
 from gcsa2_b200.flat import FlatLCP
 from oracle import oracle as orc
@@ -611,3 +613,57 @@ def test_custom_alphabet_takes_the_general_path():
         assert (fsp == osp).all() and (fep == oep).all()
     found = (osp <= oep)
     assert found[~lower].all() and not found[lower].any()
+
+
+def test_kmer_batches_two_kernel_form(monkeypatch):
+    """Batches of k-mers (one length <= 32, at least 4096 of them) go through find_fast_kernel + the work list resumed by
+    the general kernel; they must equal the oracle and the single general kernel (GCSA_B200_FIND_FAST=0 is read once
+    per process, so the general kernel is reached through the offsets form of the same patterns).  Every table shape:
+    fused and plain entries, 8- and 16-byte jump entries, no jump table, two-step blocks; lengths equal to k, between
+    k and k + a path, 32; substitutions (a jump that fails on a character), N, lower case, random patterns (misses in
+    the table), a repetitive text (ranges of several nodes after the table), a graph with bubbles."""
+    rng = np.random.default_rng(41)
+    seq = synth.random_sequence(200_000, seed=41)
+    rep = np.concatenate([np.tile(synth.random_sequence(500, seed=42), 40), synth.random_sequence(30_000, seed=43)])
+    graph, sites, alt = synth.snp_graph(seq, seed=41, snp_rate=0.01)
+    cases = (("linear", build_index(synth.linear_graph(seq), 16, 3)[0], lambda n, L, s: synth.patterns_from_sequence(seq, n, L, seed=s)),
+             ("repeats", build_index(synth.linear_graph(rep), 16, 3)[0], lambda n, L, s: synth.patterns_from_sequence(rep, n, L, seed=s)),
+             ("snp", build_index(graph, 16, 3)[0], lambda n, L, s: synth.patterns_from_snp_graph(seq, sites, alt, n, L, seed=s)))
+    for name, flat, sampler in cases:
+        ora = orc.OracleGCSA(flat)
+        for L in (8, 11, 24, 31, 32):
+            n = 6000
+            c, o = sampler(n, L, 200 + L)
+            c = c.copy()
+            for i in range(n):
+                kind = i % 6
+                if kind == 1:                                        # one substitution somewhere
+                    p = int(o[i]) + int(rng.integers(0, L))
+                    c[p] = synth.COMP2CHAR[1 + (int(np.where(synth.COMP2CHAR == c[p])[0][0]) % 4)]
+                elif kind == 2 and i % 12 == 2:                      # an N
+                    c[int(o[i]) + int(rng.integers(0, L))] = ord("N")
+                elif kind == 3:                                      # lower case
+                    c[int(o[i]):int(o[i + 1])] |= 0x20
+                elif kind == 4 and i % 12 == 4:                      # a random pattern
+                    c[int(o[i]):int(o[i + 1])] = synth.random_patterns(1, L, seed=i)[0]
+            osp, oep, _ = ora.find_batch(c, o, threads=4)
+            for options in (dict(kmer_table_k=8, jump_table=True, fused_table=True), dict(kmer_table_k=8, jump_table=True, fused_table=False),
+                            dict(kmer_table_k=8, jump_table="wide"), dict(kmer_table_k=6, jump_table=False),
+                            dict(kmer_table_k=7, jump_table="wide", two_step=True), dict(kmer_table_k=5, jump_table=True, fused_table=True)):
+                if options["kmer_table_k"] > L:
+                    continue
+                gpu = GCSA(flat, **options)
+                if options.get("jump_table") == "wide":
+                    assert gpu.jumpK() == 16 and not gpu.fusedTable()
+                fast = capi.lib().gcsa_b200_internal_fast_launches
+                fast.restype = ctypes.c_ulonglong
+                before = fast()
+                sp, ep = gpu.find_fixed_batch(c, L)                  # the two-kernel form
+                assert fast() == before + 1
+                bad = np.flatnonzero((sp != osp) | (ep != oep))
+                assert bad.size == 0, (name, L, options, bad[:5], [bytes(c[int(o[i]):int(o[i + 1])]) for i in bad[:3]])
+                gsp, gep = gpu.find_batch(c, o)                      # the general kernel
+                assert (gsp == osp).all() and (gep == oep).all(), (name, L, options)
+                ssp, sep, st = gpu.find_batch(c, o, stats=True)
+                assert (ssp == osp).all() and (sep == oep).all() and st["queries"] == n
+                gpu.close()
