@@ -334,8 +334,13 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
   ep_out) and the general kernel resumes them (find_kernel<.., WORK = true>).  Compared with running everything through
   the general kernel: no refill logic, no divergence between lanes in different phases, a third of the instructions.
 */
-template<bool STATS, bool PACKED>
-__global__ void __launch_bounds__(256)
+// Queries per thread and round.  What bounds this kernel is how many random table probes the chip has in flight
+// (ncu: 94 % occupancy, 31 registers, and still 62 cycles of long-scoreboard stall per issue with ONE probe per thread:
+// 17.5 G probes/s where dependent-chain microbenchmarks reach 44 G/s), so a thread issues the probes of several
+// queries back to back before it looks at any of them.
+
+template<bool STATS, bool PACKED, int U>
+__global__ void __launch_bounds__(256, STATS ? 1 : (U >= 4 ? 4 : (U == 2 ? 6 : 8)))
 find_fast_kernel(const DevView v, const u8* __restrict__ chars, u32 L, u64 n, u64* __restrict__ sp_out, u64* __restrict__ ep_out,
                  u64* __restrict__ work, unsigned long long* __restrict__ work_count, FindStatsDev* stats)
 {
@@ -343,93 +348,134 @@ find_fast_kernel(const DevView v, const u8* __restrict__ chars, u32 L, u64 n, u6
   const u32 k = (u32)v.table_k;
   const u64 kmask = (k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1));
   u64 st_found = 0, st_len = 0, st_steps = 0, st_sectors = 0, st_hits = 0;
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  const u64 rounds = (n + stride - 1) / stride;
+  // a warp takes 32 * U consecutive queries per round: lane l the queries base + 32 j + l (coalesced for every j)
+  const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+  const u64 per_round = 32ull * U;
+  const u64 rounds = (n + n_warps * per_round - 1) / (n_warps * per_round);
   for(u64 r = 0; r < rounds; r++)
   {
-    const u64 q = r * stride + (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    u64 entry = 0;                         // work-list entry, 0 = finished here
-    if(q < n)
+    const u64 base = (r * n_warps + warp) * per_round + lane;
+    u64 tail[U], res[U], je[U], entry[U];
+    bool valid[U];
+    // ---- the patterns, 2 bits per character, the LAST character in the lowest bits ----
+    #pragma unroll
+    for(int j = 0; j < U; j++)
     {
-      // ---- the pattern, 2 bits per character, the LAST character in the lowest bits ----
-      u64 tail = 0; bool valid = true;
-      if(PACKED)
+      const u64 q = base + 32ull * j;
+      tail[j] = 0; valid[j] = (q < n); entry[j] = 0; res[j] = 0; je[j] = 0;
+      if(q < n)
       {
-        u64 x = __ldcs((const unsigned long long*)chars + q);
-        u64 t = __brevll(x);
-        t = ((t >> 1) & 0x5555555555555555ull) | ((t & 0x5555555555555555ull) << 1);
-        tail = (L < 32 ? t >> (2 * (32 - L)) : t);
-      }
-      else
-      {
-        // the 32 bytes that end with the pattern (the first of them belong to the previous pattern if L < 32)
-        const u64 end = (u64)chars + (q + 1) * (u64)L;
-        if(end - 32 < (u64)chars) { valid = false; }                     // would read before the buffer: left to the general kernel
+        if(PACKED)
+        {
+          u64 x = __ldcs((const unsigned long long*)chars + q);
+          u64 t = __brevll(x);
+          t = ((t >> 1) & 0x5555555555555555ull) | ((t & 0x5555555555555555ull) << 1);
+          tail[j] = (L < 32 ? t >> (2 * (32 - L)) : t);
+        }
         else
         {
-          const u64 a = end - 32; const u32 sh = (u32)(a & 7) * 8;
-          const unsigned long long* base = (const unsigned long long*)(a - (a & 7));
-          u64 w0 = __ldcs(base), w1 = __ldcs(base + 1), w2 = __ldcs(base + 2), w3 = __ldcs(base + 3);
-          if(sh != 0)
+          // the 32 bytes that end with the pattern (the first of them belong to the previous pattern if L < 32)
+          const u64 end = (u64)chars + (q + 1) * (u64)L;
+          if(end - 32 < (u64)chars) { entry[j] = q | WORK_FRESH; }          // would read before the buffer: left to the general kernel
+          else
           {
-            u64 w4 = __ldcs(base + 4);
-            w0 = (w0 >> sh) | (w1 << (64 - sh)); w1 = (w1 >> sh) | (w2 << (64 - sh));
-            w2 = (w2 >> sh) | (w3 << (64 - sh)); w3 = (w3 >> sh) | (w4 << (64 - sh));
+            const u64 a = end - 32; const u32 sh = (u32)(a & 7) * 8;
+            const unsigned long long* words = (const unsigned long long*)(a - (a & 7));
+            u64 w0 = __ldcs(words), w1 = __ldcs(words + 1), w2 = __ldcs(words + 2), w3 = __ldcs(words + 3);
+            if(sh != 0)
+            {
+              u64 w4 = __ldcs(words + 4);
+              w0 = (w0 >> sh) | (w1 << (64 - sh)); w1 = (w1 >> sh) | (w2 << (64 - sh));
+              w2 = (w2 >> sh) | (w3 << (64 - sh)); w3 = (w3 >> sh) | (w4 << (64 - sh));
+            }
+            u32 g0, g1, g2, g3;
+            u64 p3 = pack8_reversed(w3, &g3), p2 = pack8_reversed(w2, &g2), p1 = pack8_reversed(w1, &g1), p0 = pack8_reversed(w0, &g0);
+            tail[j] = p3 | (p2 << 16) | (p1 << 32) | (p0 << 48);
+            // how many characters, counted from the last one, are bases
+            u32 good = (g3 < 8 ? g3 : 8 + (g2 < 8 ? g2 : 8 + (g1 < 8 ? g1 : 8 + g0)));
+            if(good < L) { entry[j] = q | WORK_FRESH; }
           }
-          u32 g0, g1, g2, g3;
-          u64 p3 = pack8_reversed(w3, &g3), p2 = pack8_reversed(w2, &g2), p1 = pack8_reversed(w1, &g1), p0 = pack8_reversed(w0, &g0);
-          tail = p3 | (p2 << 16) | (p1 << 32) | (p0 << 48);
-          // how many characters, counted from the last one, are bases
-          u32 good = (g3 < 8 ? g3 : 8 + (g2 < 8 ? g2 : 8 + (g1 < 8 ? g1 : 8 + g0)));
-          valid = (good >= L);
         }
       }
-      if(!valid) { entry = q | WORK_FRESH; }
-      else
+    }
+    // ---- the table probes of all U queries, issued before any is used ----
+    #pragma unroll
+    for(int j = 0; j < U; j++)
+    {
+      if(valid[j] && entry[j] == 0)
       {
-        u64 res, je = 0;
-        const u64 idx = tail & kmask;
-        if(v.table2 != nullptr) { ulonglong2 both = __ldg(v.table2 + idx); res = both.x; je = both.y; }
-        else { res = __ldg(v.table + idx); }
+        const u64 idx = tail[j] & kmask;
+        if(v.table2 != nullptr) { ulonglong2 both = __ldg(v.table2 + idx); res[j] = both.x; je[j] = both.y; }
+        else { res[j] = __ldg(v.table + idx); }
         if(STATS) { st_hits++; }
-        const u64 len = res >> 40;
-        if(len == TABLE_ESCAPE) { entry = q | WORK_FRESH; }
+      }
+    }
+    // ---- separate long jump table: the second probe of the queries whose k-mer is one path node ----
+    u64 jx[U], jy[U];
+    #pragma unroll
+    for(int j = 0; j < U; j++)
+    {
+      jx[j] = 0; jy[j] = 0;
+      const u32 rem = L - k;
+      if(valid[j] && entry[j] == 0 && v.table2 == nullptr && (res[j] >> 40) == 1 && rem >= v.jump_k && rem > 0)
+      {
+        const u64 node = res[j] & M40;
+        if(v.jump_wide != nullptr) { ulonglong2 e = __ldg(v.jump_wide + node); jx[j] = e.x; jy[j] = e.y; if(STATS) { st_sectors++; } }
+        else if(v.jump != nullptr) { jx[j] = __ldg(v.jump + node); if(STATS) { st_sectors++; } }
+      }
+    }
+    // ---- resolve ----
+    #pragma unroll
+    for(int j = 0; j < U; j++)
+    {
+      const u64 q = base + 32ull * j;
+      if(valid[j] && entry[j] == 0)
+      {
+        const u64 len = res[j] >> 40;
+        if(len == TABLE_ESCAPE) { entry[j] = q | WORK_FRESH; }
         else
         {
-          u64 sp = res & M40, ep = sp + len - 1;
+          u64 sp = res[j] & M40, ep = sp + len - 1;
           u32 rem = L - k;
           if(len == 1 && rem > 0)
           {
             // one path node: its unary backward path, from the fused entry or from the long jump table
             JumpPath path; path.len = 0; path.chars = 0; path.target = 0;
-            if(v.table2 != nullptr) { path = jump_decode(je, v.jump_tbits); }
-            else if(rem >= v.jump_k && v.jump_wide != nullptr) { path = jump_decode_wide(__ldg(v.jump_wide + sp)); if(STATS) { st_sectors++; } }
-            else if(rem >= v.jump_k && v.jump != nullptr) { path = jump_decode(__ldg(v.jump + sp), v.jump_tbits); if(STATS) { st_sectors++; } }
+            if(v.table2 != nullptr) { path = jump_decode(je[j], v.jump_tbits); }
+            else if(v.jump_wide != nullptr) { path = jump_decode_wide(make_ulonglong2(jx[j], jy[j])); }
+            else if(jx[j] != 0) { path = jump_decode(jx[j], v.jump_tbits); }
             if(path.len >= 2 && path.len <= rem)
             {
-              if((((tail >> (2 * k)) ^ path.chars) & ((1ull << (2 * path.len)) - 1)) == 0)
+              if((((tail[j] >> (2 * k)) ^ path.chars) & ((1ull << (2 * path.len)) - 1)) == 0)
               {
                 sp = ep = path.target; rem -= path.len;
                 if(STATS) { st_steps += path.len; }
               }
-              else { entry = q | ((u64)rem << 48) | WORK_NO_JUMP; }       // it dies within these steps: the exact pair comes from single steps
+              else { entry[j] = q | ((u64)rem << 48) | WORK_NO_JUMP; }    // it dies within these steps: the exact pair comes from single steps
             }
           }
-          if(entry == 0 && rem > 0 && len > 0) { entry = q | ((u64)rem << 48); }
+          if(entry[j] == 0 && rem > 0 && len > 0) { entry[j] = q | ((u64)rem << 48); }
           __stcs((unsigned long long*)sp_out + q, (unsigned long long)sp); __stcs((unsigned long long*)ep_out + q, (unsigned long long)ep);
-          if(STATS && entry == 0 && !range_empty(sp, ep)) { st_found++; st_len += ep + 1 - sp; }
+          if(STATS && entry[j] == 0 && !range_empty(sp, ep)) { st_found++; st_len += ep + 1 - sp; }
         }
       }
     }
-    // append the unfinished queries of the warp to the work list (one atomic per warp)
-    const u32 todo = __ballot_sync(0xFFFFFFFFu, entry != 0);
-    if(todo != 0)
+    // ---- append the unfinished queries of the warp to the work list (one atomic per warp and round) ----
+    u32 todo[U]; u32 total = 0;
+    #pragma unroll
+    for(int j = 0; j < U; j++) { todo[j] = __ballot_sync(0xFFFFFFFFu, entry[j] != 0); total += __popc(todo[j]); }
+    if(total != 0)
     {
-      unsigned long long base = 0;
-      const u32 leader = (u32)__ffs((int)todo) - 1;
-      if(lane == leader) { base = atomicAdd(work_count, (unsigned long long)__popc(todo)); }
-      base = __shfl_sync(0xFFFFFFFFu, base, (int)leader);
-      if(entry != 0) { work[base + __popc(todo & ((1u << lane) - 1))] = entry; }
+      unsigned long long at = 0;
+      if(lane == 0) { at = atomicAdd(work_count, (unsigned long long)total); }
+      at = __shfl_sync(0xFFFFFFFFu, at, 0);
+      #pragma unroll
+      for(int j = 0; j < U; j++)
+      {
+        if(entry[j] != 0) { work[at + __popc(todo[j] & ((1u << lane) - 1))] = entry[j]; }
+        at += __popc(todo[j]);
+      }
     }
   }
   if(STATS)

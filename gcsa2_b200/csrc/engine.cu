@@ -566,9 +566,16 @@ int gcsa_b200_index_create(const gcsa_flat_index* host, int device, const gcsa_b
     int max_len = std::min<int>(16, (59 - (int)tbits) / 2);
     // An 8-byte entry holds (59 - tbits) / 2 characters: 16 up to 2^27 path nodes, 13 at 3 G.  Beyond that the long
     // table gets 16-byte entries (16 characters again: a 32-mer is the k-mer table and one jump), memory permitting.
-    bool wide = (want == 2 || (want >= 0 && max_len < 16 && 4 * bytes < free_b / 2));
+    // (while it is built: level 1, the short table and the 16-byte table, 4 x 8 bytes per node; the k-mer table comes after)
+    size_t kmer_table_bytes = 0;
+    if(options != nullptr && options->kmer_table_k > 0)
+    {
+      int tk = std::min(16, options->kmer_table_k);
+      kmer_table_bytes = ((size_t)1 << (2 * tk)) * sizeof(u64) + ((size_t)1 << (2 * std::max(1, tk - 1))) * sizeof(ulonglong2);
+    }
+    bool wide = (want == 2 || (want >= 0 && max_len < 16 && (double)(4 * bytes + kmer_table_bytes) < 0.9 * (double)free_b));
     const int short_len = 4;
-    if(N > 0 && want >= 0 && (max_len >= 2 || wide) && (want > 0 || 2 * bytes < free_b / 2))
+    if(N > 0 && want >= 0 && (max_len >= 2 || wide) && (want > 0 || wide || 2 * bytes < free_b / 2))
     {
       u64 *one = nullptr, *table = nullptr, *short_table = nullptr; ulonglong2* wide_table = nullptr;
       cudaError_t e = cudaMalloc((void**)&one, bytes);
@@ -775,23 +782,27 @@ static int launchFind(const gcsa_b200_index* index, const u8* d_chars, const u64
     cudaError_t e = cudaMemsetAsync(count, 0, sizeof(unsigned long long), stream);
     if(e == cudaSuccess)
     {
-      int fast_grid = gridFor(n, index->sm_count, 8);
+      // queries per thread and round in the first kernel (GCSA_B200_FIND_UNROLL = 1, 2 or 4: measured in DESIGN.md)
+      static const int unroll = []() { const char* e = std::getenv("GCSA_B200_FIND_UNROLL"); int u = (e ? std::atoi(e) : 4); return (u == 1 || u == 2 ? u : 4); }();
+      int fast_grid = gridFor((n + unroll - 1) / unroll, index->sm_count, 8);
       int slow_grid = gridFor(n, index->sm_count, d_stats ? 1 : 4);
       const u32 L = (u32)fixed_length;
+      #define LAUNCH_FAST(S, P, U) find_fast_kernel<S, P, U><<<fast_grid, 256, 0, stream>>>(v, d_chars, L, n, d_sp, d_ep, work, count, d_stats)
+      #define LAUNCH_FAST_U(S, P) do { if(unroll == 1) { LAUNCH_FAST(S, P, 1); } else if(unroll == 2) { LAUNCH_FAST(S, P, 2); } else { LAUNCH_FAST(S, P, 4); } } while(0)
       if(d_stats)
       {
-        if(packed) { find_fast_kernel<true, true><<<fast_grid, 256, 0, stream>>>(v, d_chars, L, n, d_sp, d_ep, work, count, d_stats); }
-        else { find_fast_kernel<true, false><<<fast_grid, 256, 0, stream>>>(v, d_chars, L, n, d_sp, d_ep, work, count, d_stats); }
+        if(packed) { LAUNCH_FAST(true, true, 4); } else { LAUNCH_FAST(true, false, 4); }
         if(packed) { find_kernel<true, 1, true, true><<<slow_grid, 256, 0, stream>>>(v, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, d_stats, refill_at, work, count); }
         else { find_kernel<true, 1, false, true><<<slow_grid, 256, 0, stream>>>(v, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, d_stats, refill_at, work, count); }
       }
       else
       {
-        if(packed) { find_fast_kernel<false, true><<<fast_grid, 256, 0, stream>>>(v, d_chars, L, n, d_sp, d_ep, work, count, nullptr); }
-        else { find_fast_kernel<false, false><<<fast_grid, 256, 0, stream>>>(v, d_chars, L, n, d_sp, d_ep, work, count, nullptr); }
+        if(packed) { LAUNCH_FAST_U(false, true); } else { LAUNCH_FAST_U(false, false); }
         if(packed) { find_kernel<false, 4, true, true><<<slow_grid, 256, 0, stream>>>(v, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, nullptr, refill_at, work, count); }
         else { find_kernel<false, 4, false, true><<<slow_grid, 256, 0, stream>>>(v, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, nullptr, refill_at, work, count); }
       }
+      #undef LAUNCH_FAST_U
+      #undef LAUNCH_FAST
       e = cudaGetLastError();
     }
     cudaFreeAsync(work, stream);
@@ -880,7 +891,7 @@ extern "C" void gcsa_b200_internal_pack_share(unsigned long long* packed, unsign
 }
 
 static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const uint64_t* offsets, uint64_t fixed_length,
-                    uint64_t n, uint64_t* sp, uint64_t* ep, gcsa_b200_find_stats* stats)
+                    uint64_t n, uint64_t* sp, uint64_t* ep, gcsa_b200_find_stats* stats, int pack_threads_override = -1)
 {
   if(index == nullptr || (n > 0 && (chars == nullptr || sp == nullptr || ep == nullptr)))
   {
@@ -890,7 +901,7 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
   if(n == 0) { return 0; }
   DeviceGuard guard(index->device);
 
-  const int pack_threads = hostPackThreads();
+  const int pack_threads = (pack_threads_override >= 0 ? pack_threads_override : hostPackThreads());
   // (below three chunks of 128 k queries there is nothing to share)
   const bool pack = (pack_threads > 0 && fixed_length > 0 && offsets == nullptr && stats == nullptr && n > (2u << 17));
   // Chunks of >= 128 k queries (4 MB of 32-mers: the link is at its streaming rate), at most ~24 per batch (48 when
@@ -1108,6 +1119,88 @@ int gcsa_b200_find_stats_host(const gcsa_b200_index* index, const uint8_t* chars
   if(stats == nullptr) { return fail(GCSA_B200_ERR_INVALID, "find_stats_host: null stats"); }
   if(n > 0 && offsets == nullptr) { return fail(GCSA_B200_ERR_INVALID, "find_stats_host: null offsets"); }
   return findHost(index, chars, offsets, 0, n, sp, ep, stats);
+}
+
+//------------------------------------------------------------------------------
+// One process, several GPUs: the batch is cut into contiguous blocks, one per handle (each handle on its own
+// device, the index replicated), and one host thread per handle runs the single-device pipeline on its block,
+// writing straight into the caller's arrays.  This is what a caller that parallelises over queries with OpenMP
+// threads in one process (src/algorithms.cpp:113, 409; vg) can use; there is no exchange between the devices.
+//------------------------------------------------------------------------------
+
+namespace {
+
+// Block g of `count` over n items: [first, last)
+inline void shardBlock(u64 n, int count, int g, u64* first, u64* last)
+{
+  u64 base = n / (u64)count, extra = n % (u64)count;
+  *first = (u64)g * base + std::min<u64>((u64)g, extra);
+  *last = *first + base + ((u64)g < extra ? 1 : 0);
+}
+
+// Runs work(g) on one thread per handle; returns the first failure (its message becomes the caller's last error).
+template<class Work> int runPerHandle(int count, const char* what, Work work)
+{
+  std::vector<int> rcs(count, 0);
+  std::vector<std::string> errors(count);
+  std::vector<std::thread> threads;
+  for(int g = 1; g < count; g++)
+  {
+    try { threads.emplace_back([&, g]() { rcs[g] = work(g); if(rcs[g] != 0) { errors[g] = g_last_error; } }); }
+    catch(...) { rcs[g] = GCSA_B200_ERR_NOMEM; errors[g] = std::string(what) + ": cannot start a host thread"; }
+  }
+  rcs[0] = work(0);
+  if(rcs[0] != 0) { errors[0] = g_last_error; }
+  for(std::thread& t : threads) { t.join(); }
+  for(int g = 0; g < count; g++) { if(rcs[g] != 0) { return fail(rcs[g], errors[g]); } }
+  return 0;
+}
+
+int checkHandles(const gcsa_b200_index* const* indexes, int count, const char* what)
+{
+  if(indexes == nullptr || count < 1) { return fail(GCSA_B200_ERR_INVALID, std::string(what) + ": no handles"); }
+  for(int g = 0; g < count; g++)
+  {
+    if(indexes[g] == nullptr) { return fail(GCSA_B200_ERR_INVALID, std::string(what) + ": null handle"); }
+    if(indexes[g]->header.path_nodes != indexes[0]->header.path_nodes || indexes[g]->header.edge_count != indexes[0]->header.edge_count)
+    {
+      return fail(GCSA_B200_ERR_INVALID, std::string(what) + ": the handles are not replicas of one index");
+    }
+  }
+  return 0;
+}
+
+} // namespace
+
+int gcsa_b200_find_fixed_host_multi(const gcsa_b200_index* const* indexes, int count, const uint8_t* chars, uint64_t pattern_length,
+                                    uint64_t n, uint64_t* sp, uint64_t* ep)
+{
+  int rc = checkHandles(indexes, count, "find_fixed_host_multi");
+  if(rc != 0) { return rc; }
+  if(count == 1) { return findHost(indexes[0], chars, nullptr, pattern_length, n, sp, ep, nullptr); }
+  const int per_handle = std::max(1, hostPackThreads() / count);       // the packing threads are shared out
+  return runPerHandle(count, "find_fixed_host_multi", [&](int g) -> int
+  {
+    u64 q0, q1; shardBlock(n, count, g, &q0, &q1);
+    if(q0 == q1) { return 0; }
+    return findHost(indexes[g], chars + q0 * pattern_length, nullptr, pattern_length, q1 - q0, sp + q0, ep + q0, nullptr,
+                    hostPackThreads() == 0 ? 0 : per_handle);
+  });
+}
+
+int gcsa_b200_find_host_multi(const gcsa_b200_index* const* indexes, int count, const uint8_t* chars, const uint64_t* offsets,
+                              uint64_t n, uint64_t* sp, uint64_t* ep)
+{
+  int rc = checkHandles(indexes, count, "find_host_multi");
+  if(rc != 0) { return rc; }
+  if(n > 0 && offsets == nullptr) { return fail(GCSA_B200_ERR_INVALID, "find_host_multi: null offsets"); }
+  if(count == 1) { return findHost(indexes[0], chars, offsets, 0, n, sp, ep, nullptr); }
+  return runPerHandle(count, "find_host_multi", [&](int g) -> int
+  {
+    u64 q0, q1; shardBlock(n, count, g, &q0, &q1);
+    if(q0 == q1) { return 0; }
+    return findHost(indexes[g], chars, offsets + q0, 0, q1 - q0, sp + q0, ep + q0, nullptr);      // offsets stay batch-wide
+  });
 }
 
 //------------------------------------------------------------------------------
@@ -1578,6 +1671,68 @@ int gcsa_b200_locate_into_host(const gcsa_b200_index* index, const uint64_t* sp,
   if(err != cudaSuccess) { return fail(GCSA_B200_ERR_CUDA, std::string("locate_into_host: ") + cudaGetErrorString(err)); }
   if(needed) { *needed = base; }
   if(overflow) { return fail(GCSA_B200_ERR_CAPACITY, "locate_into_host: output capacity too small"); }
+  return 0;
+}
+
+/*
+  The same CSR from several GPUs (one handle per device, see gcsa_b200_find_fixed_host_multi).  The place of a block's
+  values in the caller's buffer depends on the sizes of the blocks before it, so there are two rounds: count() of
+  every range (GCSA::count is exactly the size of the sorted distinct locate() result, src/gcsa.cpp:802-809) into the
+  offsets array, then locate() of every block straight into its final place.
+*/
+int gcsa_b200_locate_into_host_multi(const gcsa_b200_index* const* indexes, int count, const uint64_t* sp, const uint64_t* ep, uint64_t n,
+                                     uint64_t* out_offsets, uint64_t* values, uint64_t capacity, uint64_t* needed)
+{
+  int rc = checkHandles(indexes, count, "locate_into_host_multi");
+  if(rc != 0) { return rc; }
+  if(count == 1) { return gcsa_b200_locate_into_host(indexes[0], sp, ep, n, out_offsets, values, capacity, needed); }
+  if(out_offsets == nullptr || (n > 0 && (sp == nullptr || ep == nullptr))) { return fail(GCSA_B200_ERR_INVALID, "locate_into_host_multi: null argument"); }
+  if(needed) { *needed = 0; }
+  out_offsets[0] = 0;
+  if(n == 0) { return 0; }
+  std::vector<u64> total(count, 0), base(count + 1, 0);
+  rc = runPerHandle(count, "locate_into_host_multi", [&](int g) -> int
+  {
+    u64 q0, q1; shardBlock(n, count, g, &q0, &q1);
+    if(q0 == q1) { return 0; }
+    int r = gcsa_b200_count_host(indexes[g], sp + q0, ep + q0, q1 - q0, out_offsets + q0 + 1);
+    if(r != 0) { return r; }
+    u64 sum = 0;
+    for(u64 q = q0; q < q1; q++) { sum += out_offsets[q + 1]; }
+    total[g] = sum;
+    return 0;
+  });
+  if(rc != 0) { return rc; }
+  for(int g = 0; g < count; g++) { base[g + 1] = base[g] + total[g]; }
+  if(needed) { *needed = base[count]; }
+  if(values == nullptr || base[count] > capacity)
+  {
+    // the offsets are complete either way: prefix sums of the counts
+    u64 sum = 0;
+    for(u64 q = 0; q < n; q++) { sum += out_offsets[q + 1]; out_offsets[q + 1] = sum; }
+    return fail(GCSA_B200_ERR_CAPACITY, "locate_into_host_multi: output capacity too small");
+  }
+  std::vector<u64> got(count, 0);
+  rc = runPerHandle(count, "locate_into_host_multi", [&](int g) -> int
+  {
+    u64 q0, q1; shardBlock(n, count, g, &q0, &q1);
+    if(q0 == q1) { return 0; }
+    // block-local offsets into out_offsets[q0 .. q1]; the entry at q1 is also the first of the next block and is set below
+    return gcsa_b200_locate_into_host(indexes[g], sp + q0, ep + q0, q1 - q0, out_offsets + q0, values + base[g], total[g], &got[g]);
+  });
+  if(rc != 0) { return rc; }
+  for(int g = 0; g < count; g++)
+  {
+    if(got[g] != total[g]) { return fail(GCSA_B200_ERR_INCONSISTENT, "locate_into_host_multi: count() and locate() disagree on the size of a block"); }
+  }
+  #pragma omp parallel for schedule(static)
+  for(int g = 0; g < count; g++)
+  {
+    u64 q0, q1; shardBlock(n, count, g, &q0, &q1);
+    out_offsets[q0] = base[g];
+    for(u64 q = q0 + 1; q < q1; q++) { out_offsets[q] += base[g]; }
+  }
+  out_offsets[n] = base[count];
   return 0;
 }
 

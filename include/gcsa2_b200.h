@@ -207,6 +207,20 @@ int gcsa_b200_locate_max_host(const gcsa_b200_index* index, const uint64_t* sp, 
                               uint64_t max_positions, uint64_t* out_offsets, uint64_t** values);
 void gcsa_b200_free(void* p);
 
+/* One process, several GPUs.  The reference's callers parallelise over independent queries with OpenMP threads
+   inside one process (src/algorithms.cpp:113, 409; vg does the same); these are the entry points such a caller
+   uses when the box has more than one GPU: `indexes` are `count` handles of the SAME index, one per device
+   (gcsa_b200_index_create once per device); the batch is cut into `count` contiguous blocks, one host thread per
+   handle drives its device, results land in place in the caller's arrays.  Same arguments and results as the
+   single-handle calls; there is no exchange between the devices. */
+int gcsa_b200_find_fixed_host_multi(const gcsa_b200_index* const* indexes, int count, const uint8_t* chars,
+                                    uint64_t pattern_length, uint64_t n, uint64_t* sp, uint64_t* ep);
+int gcsa_b200_find_host_multi(const gcsa_b200_index* const* indexes, int count, const uint8_t* chars,
+                              const uint64_t* offsets, uint64_t n, uint64_t* sp, uint64_t* ep);
+int gcsa_b200_locate_into_host_multi(const gcsa_b200_index* const* indexes, int count, const uint64_t* sp,
+                                     const uint64_t* ep, uint64_t n, uint64_t* out_offsets, uint64_t* values,
+                                     uint64_t capacity, uint64_t* needed);
+
 /* countKMers(index, k, parameters), src/algorithms.cpp:387-421 (declared include/gcsa/algorithms.h:80-89):
    the number of distinct k-mers over the bases (include_Ns != 0: bases and N).  If ranges is not NULL it
    receives the path ranges of those k-mers (ordered by the reversed k-mer: the trie grows leftwards),
