@@ -5,5 +5,5 @@ of include/gcsa2_b200.h.  This package is the Python host-side mirror of the ref
 interface (GCSA, LCPArray), the builder wrapper and the synthetic inputs of the benchmarks.
 """
 from .flat import FlatGCSA, FlatLCP, node_encode, node_id, node_offset, node_rc  # noqa: F401
-from .index import GCSA, LCPArray, pack_patterns, range_empty, range_length, mem_batch, mem_device, UNKNOWN  # noqa: F401
+from .index import GCSA, LCPArray, MultiGCSA, pack_patterns, range_empty, range_length, mem_batch, mem_device, UNKNOWN  # noqa: F401
 from .capi import GCSAError  # noqa: F401

@@ -61,6 +61,7 @@ __device__ __forceinline__ u32 pack8_reversed(u64 w, u32* good)
 #define WORK_QUERY_MASK ((1ull << 48) - 1)
 #define WORK_NO_JUMP (1ull << 62)        // a jump failed on a character: the query dies within a few single steps
 #define WORK_FRESH   (1ull << 63)        // nothing is known yet: search from the last character
+#define WORK_QUAD    (1ull << 61)        // (inside find_fast_kernel only) goes to the list of find_quad_kernel
 
 template<bool STATS, int MIN_BLOCKS, bool PACKED = false, bool WORK = false>
 __global__ void __launch_bounds__(256, MIN_BLOCKS)
@@ -342,7 +343,8 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
 template<bool STATS, bool PACKED, int U>
 __global__ void __launch_bounds__(256, STATS ? 1 : (U >= 4 ? 4 : (U == 2 ? 6 : 8)))
 find_fast_kernel(const DevView v, const u8* __restrict__ chars, u32 L, u64 n, u64* __restrict__ sp_out, u64* __restrict__ ep_out,
-                 u64* __restrict__ work, unsigned long long* __restrict__ work_count, FindStatsDev* stats)
+                 u64* __restrict__ work, unsigned long long* __restrict__ work_count,
+                 ulonglong2* __restrict__ quad_work, unsigned long long* __restrict__ quad_count, FindStatsDev* stats)
 {
   const u32 lane = threadIdx.x & 31;
   const u32 k = (u32)v.table_k;
@@ -455,16 +457,26 @@ find_fast_kernel(const DevView v, const u8* __restrict__ chars, u32 L, u64 n, u6
               else { entry[j] = q | ((u64)rem << 48) | WORK_NO_JUMP; }    // it dies within these steps: the exact pair comes from single steps
             }
           }
-          if(entry[j] == 0 && rem > 0 && len > 0) { entry[j] = q | ((u64)rem << 48); }
+          if(entry[j] == 0 && rem > 0 && len > 0)
+          {
+            entry[j] = q | ((u64)rem << 48);
+            // a range of a few path nodes with a whole long path to go: their paths are probed side by side (find_quad_kernel)
+            if(quad_work != nullptr && len >= 2 && len <= 4 && rem >= v.jump_k) { entry[j] |= WORK_QUAD; }
+          }
           __stcs((unsigned long long*)sp_out + q, (unsigned long long)sp); __stcs((unsigned long long*)ep_out + q, (unsigned long long)ep);
           if(STATS && entry[j] == 0 && !range_empty(sp, ep)) { st_found++; st_len += ep + 1 - sp; }
         }
       }
     }
-    // ---- append the unfinished queries of the warp to the work list (one atomic per warp and round) ----
-    u32 todo[U]; u32 total = 0;
+    // ---- append the unfinished queries of the warp to the work lists (one atomic per warp, list and round) ----
+    u32 todo[U], quads[U]; u32 total = 0, total_quads = 0;
     #pragma unroll
-    for(int j = 0; j < U; j++) { todo[j] = __ballot_sync(0xFFFFFFFFu, entry[j] != 0); total += __popc(todo[j]); }
+    for(int j = 0; j < U; j++)
+    {
+      todo[j] = __ballot_sync(0xFFFFFFFFu, entry[j] != 0 && !(entry[j] & WORK_QUAD));
+      quads[j] = __ballot_sync(0xFFFFFFFFu, (entry[j] & WORK_QUAD) != 0);
+      total += __popc(todo[j]); total_quads += __popc(quads[j]);
+    }
     if(total != 0)
     {
       unsigned long long at = 0;
@@ -473,8 +485,20 @@ find_fast_kernel(const DevView v, const u8* __restrict__ chars, u32 L, u64 n, u6
       #pragma unroll
       for(int j = 0; j < U; j++)
       {
-        if(entry[j] != 0) { work[at + __popc(todo[j] & ((1u << lane) - 1))] = entry[j]; }
+        if((todo[j] >> lane) & 1) { work[at + __popc(todo[j] & ((1u << lane) - 1))] = entry[j]; }
         at += __popc(todo[j]);
+      }
+    }
+    if(total_quads != 0)
+    {
+      unsigned long long at = 0;
+      if(lane == 0) { at = atomicAdd(quad_count, (unsigned long long)total_quads); }
+      at = __shfl_sync(0xFFFFFFFFu, at, 0);
+      #pragma unroll
+      for(int j = 0; j < U; j++)
+      {
+        if((quads[j] >> lane) & 1) { quad_work[at + __popc(quads[j] & ((1u << lane) - 1))] = make_ulonglong2(entry[j] & ~WORK_QUAD, tail[j]); }
+        at += __popc(quads[j]);
       }
     }
   }
@@ -483,6 +507,95 @@ find_fast_kernel(const DevView v, const u8* __restrict__ chars, u32 L, u64 n, u6
     atomicAdd((ull*)&stats->found, (ull)st_found); atomicAdd((ull*)&stats->total_length, (ull)st_len);
     atomicAdd((ull*)&stats->lf_steps, (ull)st_steps); atomicAdd((ull*)&stats->sector_probes, (ull)st_sectors);
     atomicAdd((ull*)&stats->table_hits, (ull)st_hits);
+  }
+}
+
+/*
+  The second kernel of the k-mer form: the queries whose k-mer table result is a range of two to four path nodes (a
+  k-mer that occurs a few times: half of the 16-mers of a 3 Gbp reference) and that still have a whole long jump to go.
+  LF of a range is the union of LF of its nodes, so instead of single steps until the range is one node, the long paths
+  of all its nodes are probed SIDE BY SIDE: four lanes per query, lane t takes node sp + t, and the quad combines what
+  the lanes found -- the nodes whose path spells the pattern's next characters map to the new range.  Exact when every
+  node of the range has a path of one common length and the targets of the matching ones are contiguous (then the new
+  range is [min, max] of them); anything else -- paths of different lengths, no match at all (the early-exit pair must
+  come from the step that fails) -- goes on to the general kernel's work list unchanged.
+*/
+template<bool STATS>
+__global__ void __launch_bounds__(256)
+find_quad_kernel(const DevView v, u32 L, const ulonglong2* __restrict__ quad_work, const unsigned long long* __restrict__ quad_count,
+                 u64* __restrict__ sp_out, u64* __restrict__ ep_out, u64* __restrict__ work, unsigned long long* __restrict__ work_count,
+                 FindStatsDev* stats)
+{
+  const u64 n = *quad_count;
+  const u32 lane = threadIdx.x & 31, t = lane & 3, quad_shift = lane & ~3u;
+  u64 st_found = 0, st_len = 0, st_steps = 0, st_sectors = 0;
+  const u64 stride = ((u64)gridDim.x * blockDim.x) >> 2;
+  const u64 rounds = (n + stride - 1) / stride;
+  for(u64 r = 0; r < rounds; r++)
+  {
+    // (every lane of the warp goes through the same collectives; a quad without an item carries dummies)
+    const u64 i = r * stride + (((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 2);
+    const bool active = (i < n);
+    u64 push = 0;                                                      // lane 0 of a quad: entry for the general kernel's list
+    u64 q = 0, tail = 0, sp = 0, ep = 0; u32 rem = 0, nodes = 0;
+    if(active)
+    {
+      const ulonglong2 item = quad_work[i];
+      q = item.x & WORK_QUERY_MASK; tail = item.y; rem = (u32)((item.x >> 48) & 0xFF);
+      sp = sp_out[q]; ep = ep_out[q];
+      nodes = (u32)(ep - sp + 1);
+    }
+    // lane t: the long path of node sp + t
+    JumpPath path; path.len = 0; path.chars = 0; path.target = 0;
+    if(active && t < nodes)
+    {
+      if(v.jump_wide != nullptr) { path = jump_decode_wide(__ldg(v.jump_wide + sp + t)); }
+      else { path = jump_decode(__ldg(v.jump + sp + t), v.jump_tbits); }
+      if(STATS) { st_sectors++; }
+    }
+    const u32 consumed = L - rem;
+    const bool exists = (active && t < nodes);
+    const bool usable = !exists || (path.len >= 2 && path.len <= rem);
+    const bool match = exists && usable && ((((tail >> (2 * consumed)) ^ path.chars) & ((1ull << (2 * path.len)) - 1)) == 0);
+    // combine over the quad: one common length, the matching targets
+    const u32 len0 = __shfl_sync(0xFFFFFFFFu, path.len, 0, 4);                                   // node sp always exists
+    const u32 all_usable = (__ballot_sync(0xFFFFFFFFu, usable && (!exists || path.len == len0)) >> quad_shift) & 0xFu;
+    const u32 matches = (__ballot_sync(0xFFFFFFFFu, match) >> quad_shift) & 0xFu;
+    u64 lo = (match ? path.target : ~0ull), hi = (match ? path.target : 0ull);
+    #pragma unroll
+    for(int d = 1; d < 4; d <<= 1)
+    {
+      u64 olo = __shfl_xor_sync(0xFFFFFFFFu, lo, d, 4), ohi = __shfl_xor_sync(0xFFFFFFFFu, hi, d, 4);
+      lo = (olo < lo ? olo : lo); hi = (ohi > hi ? ohi : hi);
+    }
+    if(active && t == 0)
+    {
+      const u32 count = (u32)__popc(matches);
+      if(all_usable != 0xFu) { push = q | ((u64)rem << 48); }                                   // paths of different lengths: single steps
+      else if(count == 0) { push = q | ((u64)rem << 48) | WORK_NO_JUMP; }                       // dies within these steps: the exact pair from single steps
+      else if(hi - lo + 1 != (u64)count) { push = q | ((u64)rem << 48); }                       // (cannot happen: LF of a range is a range)
+      else
+      {
+        rem -= len0;
+        __stcs((unsigned long long*)sp_out + q, (unsigned long long)lo); __stcs((unsigned long long*)ep_out + q, (unsigned long long)hi);
+        if(STATS) { st_steps += len0; }
+        if(rem > 0) { push = q | ((u64)rem << 48); }
+        else if(STATS) { st_found++; st_len += hi + 1 - lo; }
+      }
+    }
+    const u32 todo = __ballot_sync(0xFFFFFFFFu, push != 0);
+    if(todo != 0)
+    {
+      unsigned long long at = 0;
+      if(lane == 0) { at = atomicAdd(work_count, (unsigned long long)__popc(todo)); }
+      at = __shfl_sync(0xFFFFFFFFu, at, 0);
+      if(push != 0) { work[at + __popc(todo & ((1u << lane) - 1))] = push; }
+    }
+  }
+  if(STATS)
+  {
+    atomicAdd((ull*)&stats->found, (ull)st_found); atomicAdd((ull*)&stats->total_length, (ull)st_len);
+    atomicAdd((ull*)&stats->lf_steps, (ull)st_steps); atomicAdd((ull*)&stats->sector_probes, (ull)st_sectors);
   }
 }
 

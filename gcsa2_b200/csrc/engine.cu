@@ -776,10 +776,14 @@ static int launchFind(const gcsa_b200_index* index, const u8* d_chars, const u64
   if(!fast_off && d_offsets == nullptr && fixed_length <= 32 && v.table_k > 0 && fixed_length >= (u64)v.table_k &&
      (packed || v.default_alphabet != 0) && n >= 4096 && n < (1ull << 47))
   {
-    u64* work = nullptr; unsigned long long* count = nullptr;
-    CUDA_TRY(engineMallocAsync(&work, n * sizeof(u64) + 256, stream));
-    count = (unsigned long long*)(work + n);                           // the counter lives behind the list
-    cudaError_t e = cudaMemsetAsync(count, 0, sizeof(unsigned long long), stream);
+    // work list of the general kernel (8 bytes per entry), work list of the quad kernel (16), the two counters
+    const bool use_quads = (v.jump_wide != nullptr || v.jump != nullptr);
+    u64* work = nullptr;
+    CUDA_TRY(engineMallocAsync(&work, n * sizeof(u64) * (use_quads ? 3 : 1) + 256, stream));
+    ulonglong2* quad_work = (use_quads ? (ulonglong2*)(work + n) : nullptr);
+    unsigned long long* count = (unsigned long long*)(work + n * (use_quads ? 3 : 1));
+    unsigned long long* quad_count = count + 1;
+    cudaError_t e = cudaMemsetAsync(count, 0, 2 * sizeof(unsigned long long), stream);
     if(e == cudaSuccess)
     {
       // queries per thread and round in the first kernel (GCSA_B200_FIND_UNROLL = 1, 2 or 4: measured in DESIGN.md)
@@ -787,17 +791,19 @@ static int launchFind(const gcsa_b200_index* index, const u8* d_chars, const u64
       int fast_grid = gridFor((n + unroll - 1) / unroll, index->sm_count, 8);
       int slow_grid = gridFor(n, index->sm_count, d_stats ? 1 : 4);
       const u32 L = (u32)fixed_length;
-      #define LAUNCH_FAST(S, P, U) find_fast_kernel<S, P, U><<<fast_grid, 256, 0, stream>>>(v, d_chars, L, n, d_sp, d_ep, work, count, d_stats)
+      #define LAUNCH_FAST(S, P, U) find_fast_kernel<S, P, U><<<fast_grid, 256, 0, stream>>>(v, d_chars, L, n, d_sp, d_ep, work, count, quad_work, quad_count, d_stats)
       #define LAUNCH_FAST_U(S, P) do { if(unroll == 1) { LAUNCH_FAST(S, P, 1); } else if(unroll == 2) { LAUNCH_FAST(S, P, 2); } else { LAUNCH_FAST(S, P, 4); } } while(0)
       if(d_stats)
       {
         if(packed) { LAUNCH_FAST(true, true, 4); } else { LAUNCH_FAST(true, false, 4); }
+        if(use_quads) { find_quad_kernel<true><<<gridFor(n, index->sm_count, 8), 256, 0, stream>>>(v, L, quad_work, quad_count, d_sp, d_ep, work, count, d_stats); }
         if(packed) { find_kernel<true, 1, true, true><<<slow_grid, 256, 0, stream>>>(v, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, d_stats, refill_at, work, count); }
         else { find_kernel<true, 1, false, true><<<slow_grid, 256, 0, stream>>>(v, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, d_stats, refill_at, work, count); }
       }
       else
       {
         if(packed) { LAUNCH_FAST_U(false, true); } else { LAUNCH_FAST_U(false, false); }
+        if(use_quads) { find_quad_kernel<false><<<gridFor(n, index->sm_count, 8), 256, 0, stream>>>(v, L, quad_work, quad_count, d_sp, d_ep, work, count, nullptr); }
         if(packed) { find_kernel<false, 4, true, true><<<slow_grid, 256, 0, stream>>>(v, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, nullptr, refill_at, work, count); }
         else { find_kernel<false, 4, false, true><<<slow_grid, 256, 0, stream>>>(v, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, nullptr, refill_at, work, count); }
       }

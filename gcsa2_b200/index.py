@@ -293,6 +293,62 @@ class GCSA:
         return offs, vals
 
 
+class MultiGCSA:
+    """Replicas of one index on several devices behind the single-process multi-GPU entry points
+    (gcsa_b200_find_fixed_host_multi / _find_host_multi / _locate_into_host_multi): the batch is cut into contiguous
+    blocks, one per replica, each driven by its own host thread.  `devices` may name a device more than once."""
+
+    def __init__(self, flat, devices, **options):
+        self.replicas = [GCSA(flat, device=d, **options) for d in devices]
+        self._handles = (C.c_void_p * len(self.replicas))(*[r.handle for r in self.replicas])
+
+    def close(self):
+        for r in self.replicas:
+            r.close()
+
+    def size(self): return self.replicas[0].size()
+
+    def find_fixed_host_raw(self, chars_ptr, pattern_length, n, sp_ptr, ep_ptr):
+        capi.check(capi.lib().gcsa_b200_find_fixed_host_multi(self._handles, len(self.replicas), chars_ptr, int(pattern_length), int(n), sp_ptr, ep_ptr))
+
+    def find_fixed_batch(self, chars, pattern_length):
+        chars = np.ascontiguousarray(chars, dtype=np.uint8)
+        n = chars.size // int(pattern_length) if pattern_length else 0
+        sp = np.zeros(max(n, 1), dtype=np.uint64); ep = np.zeros(max(n, 1), dtype=np.uint64)
+        self.find_fixed_host_raw(chars.ctypes.data, pattern_length, n, sp.ctypes.data, ep.ctypes.data)
+        return sp[:n], ep[:n]
+
+    def find_batch(self, patterns, offsets=None):
+        if offsets is None:
+            chars, offsets = pack_patterns(patterns)
+        else:
+            chars = np.ascontiguousarray(patterns, dtype=np.uint8); offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        sp = np.zeros(max(n, 1), dtype=np.uint64); ep = np.zeros(max(n, 1), dtype=np.uint64)
+        capi.check(capi.lib().gcsa_b200_find_host_multi(self._handles, len(self.replicas), chars.ctypes.data, offsets.ctypes.data, n,
+                                                        sp.ctypes.data, ep.ctypes.data))
+        return sp[:n], ep[:n]
+
+    def locate_into_host_raw(self, sp_ptr, ep_ptr, n, offsets_ptr, values_ptr, capacity):
+        needed = C.c_uint64()
+        capi.check(capi.lib().gcsa_b200_locate_into_host_multi(self._handles, len(self.replicas), sp_ptr, ep_ptr, int(n), offsets_ptr,
+                                                               values_ptr, int(capacity), C.byref(needed)))
+        return int(needed.value)
+
+    def locate_batch(self, sp, ep):
+        """CSR of sorted distinct positions, like GCSA.locate_batch."""
+        n = len(sp)
+        sp, ep = capi.as_u64(sp), capi.as_u64(ep)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        needed = C.c_uint64()
+        rc = capi.lib().gcsa_b200_locate_into_host_multi(self._handles, len(self.replicas), sp.ctypes.data, ep.ctypes.data, n,
+                                                         offs.ctypes.data, None, 0, C.byref(needed))
+        capi.check(rc, allow=(capi.ERR_CAPACITY,))
+        vals = np.zeros(max(1, int(needed.value)), dtype=np.uint64)
+        got = self.locate_into_host_raw(sp.ctypes.data, ep.ctypes.data, n, offs.ctypes.data, vals.ctypes.data, vals.size)
+        return offs, vals[:got]
+
+
 class LCPArray:
     @classmethod
     def load(cls, lcp_file, device=0):

@@ -270,6 +270,45 @@ private:
 
 //------------------------------------------------------------------------------
 
+//------------------------------------------------------------------------------
+// One process, several GPUs: `replicas` are GCSA objects of the same index, one per device.  The batch is cut into
+// contiguous blocks, one per replica, each driven by its own host thread (gcsa_b200_*_multi); results as for the
+// member functions of the same name.  This is the form an OpenMP-over-queries caller (src/algorithms.cpp:113) uses
+// on a box with several GPUs.
+//------------------------------------------------------------------------------
+
+inline void find(const std::vector<const GCSA*>& replicas, const std::vector<std::string>& patterns, std::vector<range_type>& results)
+{
+  std::vector<const gcsa_b200_index*> handles;
+  for(const GCSA* r : replicas) { handles.push_back(r->handle); }
+  std::vector<std::uint64_t> offsets(patterns.size() + 1, 0);
+  for(size_type i = 0; i < patterns.size(); i++) { offsets[i + 1] = offsets[i] + patterns[i].size(); }
+  std::vector<std::uint8_t> chars(offsets.back() + 1);
+  for(size_type i = 0; i < patterns.size(); i++) { std::copy(patterns[i].begin(), patterns[i].end(), chars.begin() + offsets[i]); }
+  std::vector<std::uint64_t> sp(patterns.size() + 1), ep(patterns.size() + 1);
+  gcsa_b200_find_host_multi(handles.data(), (int)handles.size(), chars.data(), offsets.data(), patterns.size(), sp.data(), ep.data());
+  results.resize(patterns.size());
+  for(size_type i = 0; i < patterns.size(); i++) { results[i] = range_type(sp[i], ep[i]); }
+}
+
+// CSR of sorted distinct values, values[offsets[i] .. offsets[i+1]) for ranges[i]
+inline void locate(const std::vector<const GCSA*>& replicas, const std::vector<range_type>& ranges, std::vector<size_type>& offsets, std::vector<node_type>& values)
+{
+  std::vector<const gcsa_b200_index*> handles;
+  for(const GCSA* r : replicas) { handles.push_back(r->handle); }
+  std::vector<std::uint64_t> sp(ranges.size() + 1), ep(ranges.size() + 1);
+  for(size_type i = 0; i < ranges.size(); i++) { sp[i] = ranges[i].first; ep[i] = ranges[i].second; }
+  offsets.assign(ranges.size() + 1, 0);
+  std::uint64_t needed = 0;
+  gcsa_b200_locate_into_host_multi(handles.data(), (int)handles.size(), sp.data(), ep.data(), ranges.size(), offsets.data(), nullptr, 0, &needed);
+  values.assign(needed + 1, 0);
+  if(gcsa_b200_locate_into_host_multi(handles.data(), (int)handles.size(), sp.data(), ep.data(), ranges.size(), offsets.data(), values.data(), needed, &needed) != 0)
+  {
+    needed = 0; offsets.assign(ranges.size() + 1, 0);
+  }
+  values.resize(needed);
+}
+
 class LCPArray
 {
 public:

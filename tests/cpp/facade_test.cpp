@@ -77,6 +77,20 @@ int main()
 
   std::vector<range_type> batch;
   index.find(patterns, batch);
+
+  // one process, several replicas (here two handles on device 0): the same answers, results in place
+  {
+    GCSA second(built.index, 0, 4);
+    std::vector<const GCSA*> replicas = { &index, &second };
+    std::vector<range_type> from_replicas;
+    gcsa_b200::find(replicas, patterns, from_replicas);
+    REQUIRE(from_replicas == batch);
+    std::vector<size_type> offsets_one, offsets_two;
+    std::vector<node_type> values_one, values_two;
+    index.locate(batch, offsets_one, values_one);
+    gcsa_b200::locate(replicas, batch, offsets_two, values_two);
+    REQUIRE(offsets_one == offsets_two && values_one == values_two);
+  }
   size_type found = 0;
   for(size_type i = 0; i < patterns.size(); i++)
   {

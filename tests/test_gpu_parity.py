@@ -667,3 +667,32 @@ def test_kmer_batches_two_kernel_form(monkeypatch):
                 ssp, sep, st = gpu.find_batch(c, o, stats=True)
                 assert (ssp == osp).all() and (sep == oep).all() and st["queries"] == n
                 gpu.close()
+
+
+def test_single_process_multi_gpu_entry_points():
+    """gcsa_b200_find_fixed_host_multi / _find_host_multi / _locate_into_host_multi: the batch cut into blocks over several
+    handles (here replicas on one device; tests/test_multi_gpu.py runs them on two devices) == the single-handle calls."""
+    from gcsa2_b200 import MultiGCSA
+    seq = synth.random_sequence(120_000, seed=51)
+    graph, sites, alt = synth.snp_graph(seq, seed=51, snp_rate=0.02)
+    flat, _, _ = build_index(graph, 16, 3)
+    one = GCSA(flat, kmer_table_k=8)
+    for replicas in (2, 3):
+        multi = MultiGCSA(flat, [0] * replicas, kmer_table_k=8)
+        chars, offsets = synth.patterns_from_snp_graph(seq, sites, alt, 30_001, 32, seed=52)
+        a, b = one.find_fixed_batch(chars, 32)
+        c, d = multi.find_fixed_batch(chars, 32)
+        assert (a == c).all() and (b == d).all()
+        mchars, moffsets = synth.mixed_length_patterns(seq, sites, alt, 5003, 10, 90, seed=53, error_rate=0.02)
+        e, f = one.find_batch(mchars, moffsets)
+        g, h = multi.find_batch(mchars, moffsets)
+        assert (e == g).all() and (f == h).all()
+        # locate: short patterns have wide ranges, mixed with the 32-mers' short ones and with empty ranges
+        sp = np.concatenate([e[:2000], a[:20_000]]); ep = np.concatenate([f[:2000], b[:20_000]])
+        offs, vals = one.locate_batch(sp, ep)
+        moffs, mvals = multi.locate_batch(sp, ep)
+        assert (offs == moffs).all() and (vals == mvals).all()
+        empty_offs, empty_vals = multi.locate_batch(sp[:0], ep[:0])
+        assert empty_offs.tolist() == [0] and empty_vals.size == 0
+        multi.close()
+    one.close()
