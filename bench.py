@@ -450,7 +450,7 @@ def cfg4_leg(args, rank, world, local, barrier, dist, torch):
     st = None
     if sample is not None:
         k = sample[1].size
-        _, _, st = index.find_batch(sample[0], np.arange(k + 1, dtype=np.uint64) * np.uint64(length), stats=True)
+        _, _, st = index.find_fixed_batch(sample[0], length, stats=True)
     info = {"path_nodes": index.size(), "edges": index.edgeCount(), "order": index.order(), "device_bytes": index.deviceBytes(),
             "kmer_table_k": index.kmerTableK(), "fused_table": index.fusedTable(), "two_step": index.twoStep(), "jump_k": index.jumpK()}
     index.close()
@@ -477,7 +477,7 @@ def cfg4_leg(args, rank, world, local, barrier, dist, torch):
         secs = ms_pass / 1000.0
         rank0_queries = sum(min(chunk, total - c * chunk) for c in mine)
         out["roofline"] = {"bound": "hbm", "achieved": per_query * rank0_queries / secs / 1e9, "peak": peak, "unit": "GB/s",
-                           "frac": per_query * rank0_queries / secs / 1e9 / peak, "traffic": None, "kernel": "find_kernel<false,4,false>",
+                           "frac": per_query * rank0_queries / secs / 1e9 / peak, "traffic": None, "kernel": "find_fast_kernel<false,false,4> (+ find_quad_kernel, find_kernel<false,4,false,true> for the work lists)",
                            "peak_source": peak_src, "probes_per_query": (st["sector_probes"] + st["table_hits"]) / k,
                            "lf_steps_per_query": st["lf_steps"] / k,
                            "accounting": "per GPU (rank 0): 64 B per distinct probe executed + |P| + 16 B I/O per query, over the time of one pass"}
@@ -684,7 +684,7 @@ def main():
 
     # ---- work counters for the roofline (untimed; a 1 M sample through the stats kernel) ----
     m = min(n, 1_000_000)
-    _, _, st = index.find_batch(chars[:m * length], offsets[:m + 1], stats=True)
+    _, _, st = index.find_fixed_batch(chars[:m * length], length, stats=True)       # the kernels of the k-mer form
     scale = n / m
     # 64 B per distinct probe (the HBM access granule: a missed 32-byte sector costs one 64-byte
     # fetch) + |P| + 16 B of I/O per query.  A probe here is a fused sector, a jump-table entry or a k-mer table
@@ -763,7 +763,7 @@ def main():
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "dram_frac": (traffic / (ms_total / args.steps / 1000.0) / 1e9 / peak if traffic else None),
-                         "kernel": "find_kernel<false,4,false>", "peak_source": peak_src,
+                         "kernel": "find_fast_kernel<false,false,4> (+ find_quad_kernel, find_kernel<false,4,false,true> for the work lists)", "peak_source": peak_src,
                          "bytes_per_launch": engine_bytes,
                          "achieved_payload": payload_bytes / (ms_total / args.steps / 1000.0) / 1e9,
                          "probes_per_query": (st["sector_probes"] + st["table_hits"]) / m,

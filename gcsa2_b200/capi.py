@@ -77,7 +77,7 @@ SYMBOLS = [
     "gcsa_b200_last_error", "gcsa_b200_version", "gcsa_b200_device_count",
     "gcsa_b200_index_create", "gcsa_b200_index_destroy", "gcsa_b200_index_info",
     "gcsa_b200_find_batch", "gcsa_b200_find_host", "gcsa_b200_find_fixed_batch", "gcsa_b200_find_fixed_host",
-    "gcsa_b200_find_stats_host", "gcsa_b200_char_range",
+    "gcsa_b200_find_stats_host", "gcsa_b200_find_fixed_stats_host", "gcsa_b200_char_range",
     "gcsa_b200_find_fixed_host_multi", "gcsa_b200_find_host_multi", "gcsa_b200_locate_into_host_multi",
     "gcsa_b200_lf_batch", "gcsa_b200_lf_host", "gcsa_b200_lf_node_batch", "gcsa_b200_lf_node_host",
     "gcsa_b200_lf_multi_batch", "gcsa_b200_lf_multi_host",
@@ -128,6 +128,7 @@ def _bind(L):
     L.gcsa_b200_find_fixed_host_multi.argtypes = [vp, i32, vp, u64, u64, vp, vp]
     L.gcsa_b200_find_host_multi.argtypes = [vp, i32, vp, vp, u64, vp, vp]
     L.gcsa_b200_locate_into_host_multi.argtypes = [vp, i32, vp, vp, u64, vp, vp, u64, C.POINTER(u64)]
+    L.gcsa_b200_find_fixed_stats_host.argtypes = [vp, vp, u64, u64, vp, vp, C.POINTER(FindStats)]
     L.gcsa_b200_char_range.argtypes = [vp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.gcsa_b200_lf_batch.argtypes = [vp, vp, vp, vp, u64, vp, vp, vp]
     L.gcsa_b200_lf_host.argtypes = [vp, vp, vp, vp, u64, vp, vp]

@@ -140,7 +140,9 @@ void prune(Paths& paths)
   right part's `to`, so joining with a sorted path yields a sorted path.  New ranks come from
   one sort of (rank(left), rank(right)).
 */
-void extend(Paths& paths, u32 positions)
+// Path numbers and label ranks are 32-bit (KeyIdx::idx, Paths::rank): returns false if the step would create more
+// paths than that (the reference's disk-based builder has no such limit; this in-memory one is for fixtures).
+bool extend(Paths& paths, u32 positions)
 {
   size_t n = paths.size();
   // Bucket the paths by start position.
@@ -161,6 +163,7 @@ void extend(Paths& paths, u32 positions)
   }
   for(size_t i = 0; i < n; i++) { out_pos[i + 1] += out_pos[i]; }
   size_t total = out_pos[n];
+  if(total >= (size_t)SORTED) { return false; }
 
   Paths out; out.M = paths.M; out.resize(total);
   std::vector<KeyIdx> order(total);
@@ -200,6 +203,7 @@ void extend(Paths& paths, u32 positions)
     out.rank[order[i].idx] = rank;
   }
   paths = std::move(out);
+  return true;
 }
 
 struct Builder
@@ -251,6 +255,7 @@ struct Output
 int buildIndex(const u64* keys, const u64* from, const u64* to, u64 n, int k, int steps, u64 sample_period, Output& out)
 {
   if(n == 0 || k < 1 || k > 16 || steps < 0 || steps > 4) { return GCSA_B200_ERR_INVALID; }
+  if(n >= (u64)SORTED) { return GCSA_B200_ERR_INVALID; }            // 32-bit path numbers (see extend)
   Builder B; B.k = k; B.steps = steps; B.M = 1 << steps; B.K = k << steps; B.sample_period = (sample_period ? sample_period : 64);
   if(B.K > 255) { return GCSA_B200_ERR_INVALID; }    // LCP values are bytes (include/gcsa/support.h:44)
   const int M = B.M;
@@ -299,7 +304,8 @@ int buildIndex(const u64* keys, const u64* from, const u64* to, u64 n, int k, in
     bool all_sorted = true;
     for(size_t i = 0; i < paths.size(); i++) { if(paths.to[i] != SORTED) { all_sorted = false; break; } }
     if(all_sorted) { break; }
-    extend(paths, (u32)B.positions.size()); timer.lap("extend");
+    if(!extend(paths, (u32)B.positions.size())) { return GCSA_B200_ERR_INVALID; }
+    timer.lap("extend");
   }
 
   // ---- merge: equal labels -> groups; maximal subtrees with one start set -> nodes ----

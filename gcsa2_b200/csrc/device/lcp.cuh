@@ -183,6 +183,8 @@ __device__ Pair64 lcp_rmq(const LcpView& l, u64 sp, u64 ep)
 __device__ gcsa_b200_stnode lcp_parent(const LcpView& l, u64 sp, u64 ep)
 {
   gcsa_b200_stnode out;
+  // a start outside the array (the reference would read past its vector): the root, like a range that covers everything
+  if(sp >= l.size) { out.sp = 0; out.ep = l.size - 1; out.left_lcp = 0; out.right_lcp = 0; out.node_lcp = 0; return out; }
   if(sp == 0 && ep == l.size - 1) { out.sp = 0; out.ep = l.size - 1; out.left_lcp = 0; out.right_lcp = 0; out.node_lcp = 0; return out; }
   u64 left_lcp = l.data[sp];
   u64 right_lcp = (ep + 1 < l.size ? l.data[ep + 1] : 0);

@@ -13,8 +13,13 @@ lf_kernel(const DevView v, const u64* __restrict__ sp, const u64* __restrict__ e
 {
   for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
   {
-    u64 a, b;
-    lf_range(v, sp[i], ep[i], comp[i], a, b);
+    // The reference does no sanity checks here (gcsa.h:132-135) and a rank past the end of a vector is undefined
+    // there; on the device it would be a read outside the index that poisons the whole context, so positions past
+    // the end are clamped to the end (rank(size) is defined: the number of ones).
+    u64 s = sp[i], e = ep[i], a, b;
+    if(s > v.path_nodes) { s = v.path_nodes; }
+    if(e != ~0ull && e >= v.path_nodes) { e = v.path_nodes - 1; }
+    lf_range(v, s, e, comp[i], a, b);
     osp[i] = a; oep[i] = b;
   }
 }
@@ -24,7 +29,8 @@ lf_node_kernel(const DevView v, const u64* __restrict__ nodes, u64 n, u64* __res
 {
   for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
   {
-    out[i] = lf_node(v, nodes[i]);
+    u64 node = nodes[i];
+    out[i] = (node < v.path_nodes ? lf_node(v, node) : ~0ull);      // no such node (the reference reads past its vectors here)
   }
 }
 
@@ -40,7 +46,8 @@ lf_multi_kernel(const DevView v, const u64* __restrict__ sp, const u64* __restri
     u64 a = 1, b = 0;                                        // Range::empty_range()
     u32 last = (all_chars ? GCSA_B200_SIGMA - 2 : GCSA_B200_FAST_CHARS);
     u64 s = sp[i], e = ep[i];
-    if(c >= 1 && c <= last && !range_empty(s, e))
+    if(e != ~0ull && e >= v.path_nodes) { e = v.path_nodes - 1; }     // clamped like in lf_kernel
+    if(c >= 1 && c <= last && !range_empty(s, e) && s < v.path_nodes)
     {
       if(s == e)                                             // single path node: follow set bits only
       {

@@ -778,10 +778,12 @@ static int launchFind(const gcsa_b200_index* index, const u8* d_chars, const u64
   {
     // work list of the general kernel (8 bytes per entry), work list of the quad kernel (16), the two counters
     const bool use_quads = (v.jump_wide != nullptr || v.jump != nullptr);
-    u64* work = nullptr;
-    CUDA_TRY(engineMallocAsync(&work, n * sizeof(u64) * (use_quads ? 3 : 1) + 256, stream));
-    ulonglong2* quad_work = (use_quads ? (ulonglong2*)(work + n) : nullptr);
-    unsigned long long* count = (unsigned long long*)(work + n * (use_quads ? 3 : 1));
+    // (the 16-byte entries first: the allocation is aligned, the end of an odd number of 8-byte entries is not)
+    u64* buffer = nullptr;
+    CUDA_TRY(engineMallocAsync(&buffer, n * sizeof(u64) * (use_quads ? 3 : 1) + 256, stream));
+    ulonglong2* quad_work = (use_quads ? (ulonglong2*)buffer : nullptr);
+    u64* work = buffer + (use_quads ? 2 * n : 0);
+    unsigned long long* count = (unsigned long long*)(work + n);
     unsigned long long* quad_count = count + 1;
     cudaError_t e = cudaMemsetAsync(count, 0, 2 * sizeof(unsigned long long), stream);
     if(e == cudaSuccess)
@@ -811,7 +813,7 @@ static int launchFind(const gcsa_b200_index* index, const u8* d_chars, const u64
       #undef LAUNCH_FAST
       e = cudaGetLastError();
     }
-    cudaFreeAsync(work, stream);
+    cudaFreeAsync(buffer, stream);
     CUDA_TRY(e);
     g_fast_launches.fetch_add(1);
     return 0;
@@ -1117,6 +1119,13 @@ int gcsa_b200_find_fixed_host(const gcsa_b200_index* index, const uint8_t* chars
                               uint64_t n, uint64_t* sp, uint64_t* ep)
 {
   return findHost(index, chars, nullptr, pattern_length, n, sp, ep, nullptr);
+}
+
+int gcsa_b200_find_fixed_stats_host(const gcsa_b200_index* index, const uint8_t* chars, uint64_t pattern_length,
+                                    uint64_t n, uint64_t* sp, uint64_t* ep, gcsa_b200_find_stats* stats)
+{
+  if(stats == nullptr) { return fail(GCSA_B200_ERR_INVALID, "find_fixed_stats_host: null stats"); }
+  return findHost(index, chars, nullptr, pattern_length, n, sp, ep, stats);
 }
 
 int gcsa_b200_find_stats_host(const gcsa_b200_index* index, const uint8_t* chars, const uint64_t* offsets,

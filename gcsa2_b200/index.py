@@ -125,10 +125,15 @@ class GCSA:
         """k-mer form: n patterns of one length back to back, host pointers."""
         capi.check(capi.lib().gcsa_b200_find_fixed_host(self._h, chars_ptr, int(pattern_length), int(n), sp_ptr, ep_ptr))
 
-    def find_fixed_batch(self, chars, pattern_length):
+    def find_fixed_batch(self, chars, pattern_length, stats=False):
         chars = np.ascontiguousarray(chars, dtype=np.uint8)
         n = chars.size // int(pattern_length) if pattern_length else 0
         sp = np.zeros(max(n, 1), dtype=np.uint64); ep = np.zeros(max(n, 1), dtype=np.uint64)
+        if stats:
+            st = capi.FindStats()
+            capi.check(capi.lib().gcsa_b200_find_fixed_stats_host(self._h, chars.ctypes.data, int(pattern_length), n,
+                                                                  sp.ctypes.data, ep.ctypes.data, C.byref(st)))
+            return sp[:n], ep[:n], {k: int(getattr(st, k)) for k, _ in capi.FindStats._fields_}
         self.find_fixed_host_raw(chars.ctypes.data, pattern_length, n, sp.ctypes.data, ep.ctypes.data)
         return sp[:n], ep[:n]
 

@@ -151,6 +151,9 @@ int gcsa_b200_find_fixed_host(const gcsa_b200_index* index, const uint8_t* chars
 /* Same answers plus executed-work counters (slower; for the roofline accounting only). */
 int gcsa_b200_find_stats_host(const gcsa_b200_index* index, const uint8_t* chars, const uint64_t* offsets,
                               uint64_t n, uint64_t* sp, uint64_t* ep, gcsa_b200_find_stats* stats);
+/* The same for the k-mer form (counts what the kernels of gcsa_b200_find_fixed_* execute). */
+int gcsa_b200_find_fixed_stats_host(const gcsa_b200_index* index, const uint8_t* chars, uint64_t pattern_length,
+                                    uint64_t n, uint64_t* sp, uint64_t* ep, gcsa_b200_find_stats* stats);
 
 /* GCSA::charRange(comp), include/gcsa/gcsa.h:150-153 (host-side, O(1), no device work). */
 int gcsa_b200_char_range(const gcsa_b200_index* index, uint64_t comp, uint64_t* sp, uint64_t* ep);
@@ -306,7 +309,9 @@ typedef struct gcsa_b200_built {
 /* keys / from / to: the KMer records of the reference (include/gcsa/support.h:475-497):
    key = label (3 bits per character, first character most significant) << 16 | predecessor
    comp mask << 8 | successor comp mask; from / to = node_type; to = ~0 for kmers that are not
-   extended.  Returns 0, or GCSA_B200_ERR_INCONSISTENT (arrays still returned) / other error. */
+   extended.  Returns 0, or GCSA_B200_ERR_INCONSISTENT (arrays still returned) / other error;
+   GCSA_B200_ERR_INVALID if the input has, or a doubling step would create, 2^32 - 1 paths or more (this in-memory
+   builder numbers paths with 32 bits; gcsa_b200_build_linear handles 3 Gbp linear references). */
 int  gcsa_b200_build_from_kmers(const uint64_t* keys, const uint64_t* from, const uint64_t* to, uint64_t n,
                                 int kmer_length, int doubling_steps, uint64_t sample_period,
                                 gcsa_b200_built* result);

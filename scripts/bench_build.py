@@ -71,7 +71,7 @@ def main():
                 res["find_ms"] = ms; res["find_gqps"] = n / ms / 1e6
                 res["found"] = int(((d_sp + 1) <= (d_ep + 1)).sum().item())
                 m = min(n, 1_000_000)
-                _, _, st = index.find_batch(chars[:m * length].cpu().numpy(), np.arange(m + 1, dtype=np.uint64) * np.uint64(length), stats=True)
+                _, _, st = index.find_fixed_batch(chars[:m * length].cpu().numpy(), length, stats=True)
                 res["probes_per_query"] = (st["sector_probes"] + st["table_hits"]) / m; res["lf_steps_per_query"] = st["lf_steps"] / m
                 index.close()
                 del index

@@ -388,11 +388,20 @@ template<class F> void launch(const Cfg& cfg, const F& f, bool collectives)
 // A kernel launch with its arguments: every pointer argument must be null or point into memory the device can see
 // (cudaMalloc*, cudaHostAlloc) -- a pointer to ordinary host memory works here but faults on the device.
 template<class T> inline void checkKernelArgument(const T&, int) {}
+template<class T> struct AlignOf { static constexpr size_t value = alignof(T); };
+template<> struct AlignOf<void> { static constexpr size_t value = 1; };
+template<> struct AlignOf<const void> { static constexpr size_t value = 1; };
 template<class T> inline void checkKernelArgument(T* const& p, int position)
 {
   if(p != nullptr && !isDeviceVisible((const void*)p))
   {
     std::fprintf(stderr, "cuda_emu: kernel argument %d (%p) is not a device pointer\n", position, (const void*)p);
+    std::abort();
+  }
+  // the device faults on an access that is not aligned to its size: a pointer to 16-byte elements must be 16-byte aligned
+  if(((uintptr_t)p % AlignOf<T>::value) != 0)
+  {
+    std::fprintf(stderr, "cuda_emu: kernel argument %d (%p) is not aligned to its element type (%zu bytes)\n", position, (const void*)p, AlignOf<T>::value);
     std::abort();
   }
 }

@@ -148,3 +148,14 @@ def test_config1_count_kmers_cpu_plumbing():
     all_kmers = {bytes(w) for w in windows}
     assert index2.count_kmers(8, include_Ns=True) == len(all_kmers)
     assert index2.count_kmers(8, include_Ns=False) == len({w for w in all_kmers if 5 not in w})
+
+
+def test_builder_refuses_more_paths_than_it_can_number():
+    """Path numbers are 32-bit: a kmer count at the limit is refused instead of wrapping around (the arrays are never
+    touched: the check comes first)."""
+    import ctypes as C
+    from gcsa2_b200 import capi
+    built = capi.Built()
+    dummy = np.zeros(8, dtype=np.uint64)
+    rc = capi.lib().gcsa_b200_build_from_kmers(dummy.ctypes.data, dummy.ctypes.data, dummy.ctypes.data, (1 << 32) - 1, 16, 3, 64, C.byref(built))
+    assert rc == capi.ERR_INVALID
