@@ -50,6 +50,23 @@ class KMers:
         lab = self.key >> np.uint64(16)
         return [tuple(int((x >> np.uint64(3 * (self.k - 1 - i))) & np.uint64(7)) for i in range(self.k)) for x in lab]
 
+    def write_text(self, path):
+        """Text .gcsa2 format of the reference (src/files.cpp:86-124): kmer, start position, predecessor characters,
+        successor characters, successor positions; one line per (kmer, start position)."""
+        comp2char = "$ACGTN#"
+        def node(v):
+            v = int(v)
+            return "%d:%s%d" % (v >> 11, "-" if (v >> 10) & 1 else "", v & 0x3FF)
+        def chars(mask):
+            return ",".join(comp2char[c] for c in range(7) if (mask >> c) & 1)
+        lines = {}
+        for key, frm, to in zip(self.key.tolist(), self.from_.tolist(), self.to.tolist()):
+            lines.setdefault((key, frm), []).append(to)
+        with open(path, "w") as f:
+            for (key, frm), tos in lines.items():
+                label = "".join(comp2char[(key >> (16 + 3 * (self.k - 1 - i))) & 7] for i in range(self.k))
+                f.write("%s\t%s\t%s\t%s\t%s\n" % (label, node(frm), chars((key >> 8) & 0xFF), chars(key & 0xFF), ",".join(node(t) for t in tos)))
+
     def write_binary(self, path):
         """Binary .graph format of the reference: 24-byte GraphFileHeader {flags, kmer_count,
         kmer_length} followed by 24-byte KMer {key, from, to} records (include/gcsa/files.h:40-52,
@@ -59,6 +76,55 @@ class KMers:
             rec = np.empty((self.key.size, 3), dtype=np.uint64)
             rec[:, 0], rec[:, 1], rec[:, 2] = self.key, self.from_, self.to
             rec.tofile(f)
+
+
+@dataclass
+class NodeMapping:
+    """NodeMapping of the reference (include/gcsa/support.h:167-222): node ids first .. first + len(ids) - 1 of the input
+    graph are reported as ids[id - first]."""
+    first: int
+    ids: np.ndarray
+
+    def __call__(self, values):
+        """Node::map (src/support.cpp:604-612) on an array of node_type values."""
+        values = np.asarray(values, dtype=np.uint64)
+        node = (values >> np.uint64(11)).astype(np.int64)
+        inside = (node >= self.first) & (node < self.first + len(self.ids))
+        mapped = np.where(inside, np.asarray(self.ids, dtype=np.uint64)[np.clip(node - self.first, 0, max(0, len(self.ids) - 1))], node.astype(np.uint64))
+        return (mapped << np.uint64(11)) | (values & np.uint64(0x7FF))
+
+    def write(self, path):
+        """NodeMapping::serialize (src/support.cpp:316-333): first_node, next_node, the ids."""
+        with open(path, "wb") as f:
+            np.array([self.first, self.first + len(self.ids)], dtype=np.uint64).tofile(f)
+            np.asarray(self.ids, dtype=np.uint64).tofile(f)
+
+    @staticmethod
+    def load(path):
+        first, p, size = C.c_uint64(), C.c_void_p(), C.c_uint64()
+        capi.check(capi.lib().gcsa_b200_load_node_mapping(str(path).encode(), C.byref(first), C.byref(p), C.byref(size)))
+        n = int(size.value)
+        ids = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(max(n, 1),))[:n].copy()
+        capi.lib().gcsa_b200_free(p)
+        return NodeMapping(first=int(first.value), ids=ids)
+
+
+def read_kmers(paths, binary=True, char2comp=None):
+    """The kmer files of the reference (vg's output): binary .graph or text .gcsa2 (src/files.cpp:86-167); several files
+    are concatenated like InputGraph does.  -> KMers."""
+    if isinstance(paths, (str, bytes)) or hasattr(paths, "__fspath__"):
+        paths = [paths]
+    arr = (C.c_char_p * len(paths))(*[str(p).encode() for p in paths])
+    out = capi.Kmers(); k = C.c_int()
+    table = None if char2comp is None else np.ascontiguousarray(char2comp, dtype=np.uint8)
+    capi.check(capi.lib().gcsa_b200_read_kmer_files(arr, len(paths), int(bool(binary)), None if table is None else table.ctypes.data,
+                                                    C.byref(out), C.byref(k)))
+    n = int(out.n)
+    def take(p):
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(max(n, 1),))[:n].copy()
+    res = KMers(key=take(out.key), from_=take(out.from_), to=take(out.to), k=int(k.value))
+    capi.lib().gcsa_b200_kmers_free(C.byref(out))
+    return res
 
 
 def enumerate_kmers(graph, k):
@@ -79,13 +145,18 @@ def enumerate_kmers(graph, k):
     return res
 
 
-def build_from_kmers(kmers, doubling_steps, sample_period=64, lcp_branching=64, allow_inconsistent=False):
+def build_from_kmers(kmers, doubling_steps, sample_period=64, lcp_branching=64, allow_inconsistent=False, mapping=None):
     """-> (FlatGCSA, FlatLCP).  Raises GCSAError(ERR_INCONSISTENT) if the kmers do not describe a
-    graph whose order-K pruned de Bruijn graph satisfies the GCSA invariants."""
+    graph whose order-K pruned de Bruijn graph satisfies the GCSA invariants.  mapping: a NodeMapping (the index
+    reports mapped node ids, InputGraph::mapping of the reference)."""
     key, frm, to = capi.as_u64(kmers.key), capi.as_u64(kmers.from_), capi.as_u64(kmers.to)
     built = capi.Built()
-    rc = capi.lib().gcsa_b200_build_from_kmers(key.ctypes.data, frm.ctypes.data, to.ctypes.data, int(kmers.key.size),
-                                               int(kmers.k), int(doubling_steps), int(sample_period), C.byref(built))
+    ids = capi.as_u64(mapping.ids) if mapping is not None else None
+    rc = capi.lib().gcsa_b200_build_from_kmers_mapped(key.ctypes.data, frm.ctypes.data, to.ctypes.data, int(kmers.key.size),
+                                                      int(kmers.k), int(doubling_steps), int(sample_period),
+                                                      int(mapping.first) if mapping is not None else 0,
+                                                      ids.ctypes.data if mapping is not None else None,
+                                                      len(mapping.ids) if mapping is not None else 0, C.byref(built))
     capi.check(rc, allow=(capi.ERR_INCONSISTENT,) if allow_inconsistent else ())
     flat = capi.flat_from_struct(built.index)
     lcp = np.ctypeslib.as_array(C.cast(built.lcp, C.POINTER(C.c_uint8)), shape=(max(1, int(built.lcp_size)),))[:int(built.lcp_size)].copy()

@@ -86,7 +86,8 @@ SYMBOLS = [
     "gcsa_b200_lcp_create", "gcsa_b200_lcp_destroy",
     "gcsa_b200_parent_batch", "gcsa_b200_parent_host", "gcsa_b200_depth_batch", "gcsa_b200_depth_host",
     "gcsa_b200_lcp_sv_host", "gcsa_b200_lcp_rmq_host", "gcsa_b200_mem_batch", "gcsa_b200_mem_host",
-    "gcsa_b200_build_from_kmers", "gcsa_b200_built_free", "gcsa_b200_build_linear",
+    "gcsa_b200_build_from_kmers", "gcsa_b200_built_free", "gcsa_b200_build_linear", "gcsa_b200_build_from_kmers_mapped",
+    "gcsa_b200_verify_index_mapped", "gcsa_b200_read_kmer_files", "gcsa_b200_load_node_mapping",
     "gcsa_b200_enumerate_kmers", "gcsa_b200_kmers_free", "gcsa_b200_default_char2comp",
     "gcsa_b200_load_gcsa_file", "gcsa_b200_write_gcsa_file", "gcsa_b200_load_lcp_file", "gcsa_b200_write_lcp_file",
     "gcsa_b200_flat_lcp_free",
@@ -158,6 +159,10 @@ def _bind(L):
     L.gcsa_b200_mem_batch.argtypes = [vp, vp, vp, vp, u64, vp, vp, u64, C.POINTER(u64), vp]
     L.gcsa_b200_mem_host.argtypes = [vp, vp, vp, vp, u64, vp, C.POINTER(vp)]
     L.gcsa_b200_build_from_kmers.argtypes = [vp, vp, vp, u64, i32, i32, u64, C.POINTER(Built)]
+    L.gcsa_b200_build_from_kmers_mapped.argtypes = [vp, vp, vp, u64, i32, i32, u64, u64, vp, u64, C.POINTER(Built)]
+    L.gcsa_b200_verify_index_mapped.argtypes = [vp, vp, vp, vp, u64, i32, u64, vp, u64, C.POINTER(VerifyReport)]
+    L.gcsa_b200_read_kmer_files.argtypes = [C.POINTER(C.c_char_p), i32, i32, vp, C.POINTER(Kmers), C.POINTER(i32)]
+    L.gcsa_b200_load_node_mapping.argtypes = [C.c_char_p, C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)]
     L.gcsa_b200_built_free.argtypes = [C.POINTER(Built)]; L.gcsa_b200_built_free.restype = None
     L.gcsa_b200_build_linear.argtypes = [vp, u64, i32, u64, i32, i32, u64, i32, C.POINTER(Built)]
     L.gcsa_b200_enumerate_kmers.argtypes = [C.POINTER(Graph), i32, C.POINTER(Kmers)]

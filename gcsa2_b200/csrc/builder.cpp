@@ -252,7 +252,21 @@ struct Output
 /*
   Build everything.  Returns 0 on success, a negative GCSA_B200_ERR_* code otherwise.
 */
-int buildIndex(const u64* keys, const u64* from, const u64* to, u64 n, int k, int steps, u64 sample_period, Output& out)
+// NodeMapping, include/gcsa/support.h:167-222: node ids in [first, first + size) are reported as mapping[id - first].
+struct Mapping
+{
+  u64 first = 0; const u64* ids = nullptr; u64 size = 0;
+  bool empty() const { return size == 0; }
+  // Node::map, src/support.cpp:604-612: the id of a node_type (value >> 11) is mapped, offset and orientation stay
+  u64 operator()(u64 value) const
+  {
+    u64 id = value >> 11;
+    if(id < first || id - first >= size) { return value; }
+    return (ids[id - first] << 11) | (value & 0x7FF);
+  }
+};
+
+int buildIndex(const u64* keys, const u64* from, const u64* to, u64 n, int k, int steps, u64 sample_period, const Mapping& mapping, Output& out)
 {
   if(n == 0 || k < 1 || k > 16 || steps < 0 || steps > 4) { return GCSA_B200_ERR_INVALID; }
   if(n >= (u64)SORTED) { return GCSA_B200_ERR_INVALID; }            // 32-bit path numbers (see extend)
@@ -380,6 +394,53 @@ int buildIndex(const u64* keys, const u64* from, const u64* to, u64 n, int k, in
   }
   size_t N = nfirst.size();
 
+  /*
+    The values of a node: the start positions of (any of) its labels, reported through the NodeMapping
+    (MergedGraphReader::fromNodes, src/gcsa.cpp:428-443: map, then sort and remove duplicates).  The mapping is
+    applied only here, after merging, as in the reference (support.h:178-183): everything emitted below --
+    samples, SadaSparse / SadaCount counters -- is about mapped values.  value_ids are dense ids into `values`
+    (sorted distinct mapped positions; without a mapping: B.positions and the ids of the group).
+  */
+  std::vector<u64> values;
+  std::vector<u64> nv_start(N + 1, 0);
+  std::vector<u32> nv_id;
+  if(mapping.empty())
+  {
+    values = B.positions;
+    nv_id.reserve(N);
+    for(size_t v = 0; v < N; v++)
+    {
+      u64 g = nfirst[v];
+      nv_start[v] = nv_id.size();
+      nv_id.insert(nv_id.end(), gfrom.begin() + gfrom_start[g], gfrom.begin() + gfrom_start[g + 1]);
+    }
+    nv_start[N] = nv_id.size();
+  }
+  else
+  {
+    std::vector<u64> mapped(B.positions.size());
+    #pragma omp parallel for
+    for(size_t i = 0; i < mapped.size(); i++) { mapped[i] = mapping(B.positions[i]); }
+    values = mapped;
+    psort(values.begin(), values.end());
+    values.erase(std::unique(values.begin(), values.end()), values.end());
+    std::vector<u32> mapped_id(mapped.size());
+    #pragma omp parallel for
+    for(size_t i = 0; i < mapped.size(); i++) { mapped_id[i] = (u32)(std::lower_bound(values.begin(), values.end(), mapped[i]) - values.begin()); }
+    std::vector<u32> tmp;
+    for(size_t v = 0; v < N; v++)
+    {
+      u64 g = nfirst[v];
+      nv_start[v] = nv_id.size();
+      tmp.clear();
+      for(u64 t = gfrom_start[g]; t < gfrom_start[g + 1]; t++) { tmp.push_back(mapped_id[gfrom[t]]); }
+      std::sort(tmp.begin(), tmp.end());
+      tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+      nv_id.insert(nv_id.end(), tmp.begin(), tmp.end());
+    }
+    nv_start[N] = nv_id.size();
+  }
+
   out.path_nodes = N; out.order = B.K;
   out.lcp.assign(N, 0);
   for(size_t v = 0; v < N; v++) { out.lcp[v] = (u8)(v == 0 ? 0 : left_lcp[nfirst[v]]); }
@@ -398,8 +459,7 @@ int buildIndex(const u64* keys, const u64* from, const u64* to, u64 n, int k, in
   }
   auto nodeValues = [&](size_t v, std::vector<u64>& res) {
     res.clear();
-    u64 g = nfirst[v];
-    for(u64 t = gfrom_start[g]; t < gfrom_start[g + 1]; t++) { res.push_back(B.positions[gfrom[t]]); }
+    for(u64 t = nv_start[v]; t < nv_start[v + 1]; t++) { res.push_back(values[nv_id[t]]); }
   };   // already sorted and distinct: ids are assigned in value order
 
   timer.lap("node info");
@@ -494,23 +554,22 @@ int buildIndex(const u64* keys, const u64* from, const u64* to, u64 n, int k, in
   // ---- counting structures (src/gcsa.cpp:590-619, 668-672; support.h:264-279, 341-364) ----
   {
     std::vector<u32> redundant(N > 0 ? N - 1 : 0, 0);
-    std::vector<u64> prev_occ(B.positions.size(), 0);
+    std::vector<u64> prev_occ(values.size(), 0);
     std::vector<u64> node_lcp, first_time, last_time;
     out.extra_filter.assign(wordsFor(N), 0);
     u64 occ_total = 0;
     std::vector<u64> extra_ones;
     for(size_t v = 0; v < N; v++)
     {
-      u64 g = nfirst[v];
-      u64 nvals = gfrom_start[g + 1] - gfrom_start[g];
+      u64 nvals = nv_start[v + 1] - nv_start[v];
       if(nvals > 1) { setBit(out.extra_filter, v); occ_total += nvals - 1; extra_ones.push_back(occ_total - 1); }
       u64 curr_lcp = (u64)out.lcp[v] + (v > 0 ? 1 : 0);
       while(!node_lcp.empty() && node_lcp.back() > curr_lcp) { node_lcp.pop_back(); first_time.pop_back(); last_time.pop_back(); }
       if(!node_lcp.empty() && node_lcp.back() == curr_lcp) { last_time.back() = v; }
       else { node_lcp.push_back(curr_lcp); first_time.push_back(v); last_time.push_back(v); }
-      for(u64 t = gfrom_start[g]; t < gfrom_start[g + 1]; t++)
+      for(u64 t = nv_start[v]; t < nv_start[v + 1]; t++)
       {
-        u32 id = gfrom[t];
+        u32 id = nv_id[t];
         if(prev_occ[id] > 0)
         {
           size_t pos = std::lower_bound(last_time.begin(), last_time.end(), prev_occ[id]) - last_time.begin();
@@ -633,10 +692,19 @@ int gcsa_b200_build_from_kmers(const uint64_t* keys, const uint64_t* from, const
                                int kmer_length, int doubling_steps, uint64_t sample_period,
                                gcsa_b200_built* result)
 {
-  if(result == nullptr) { return GCSA_B200_ERR_INVALID; }
+  return gcsa_b200_build_from_kmers_mapped(keys, from, to, n, kmer_length, doubling_steps, sample_period, 0, nullptr, 0, result);
+}
+
+int gcsa_b200_build_from_kmers_mapped(const uint64_t* keys, const uint64_t* from, const uint64_t* to, uint64_t n,
+                                      int kmer_length, int doubling_steps, uint64_t sample_period,
+                                      uint64_t mapping_first_node, const uint64_t* mapping_ids, uint64_t mapping_size,
+                                      gcsa_b200_built* result)
+{
+  if(result == nullptr || (mapping_size > 0 && mapping_ids == nullptr)) { return GCSA_B200_ERR_INVALID; }
   std::memset(result, 0, sizeof(*result));
   Output out;
-  int status = buildIndex(keys, from, to, n, kmer_length, doubling_steps, sample_period, out);
+  Mapping mapping; mapping.first = mapping_first_node; mapping.ids = mapping_ids; mapping.size = mapping_size;
+  int status = buildIndex(keys, from, to, n, kmer_length, doubling_steps, sample_period, mapping, out);
   if(status != 0 && status != GCSA_B200_ERR_INCONSISTENT) { return status; }
 
   gcsa_flat_index& f = result->index;

@@ -58,6 +58,25 @@ struct Malloced
 extern "C" int gcsa_b200_verify_index(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, const uint64_t* keys,
                                       const uint64_t* from, uint64_t n, int kmer_length, gcsa_b200_verify_report* report)
 {
+  return gcsa_b200_verify_index_mapped(index, lcp, keys, from, n, kmer_length, 0, nullptr, 0, report);
+}
+
+extern "C" int gcsa_b200_verify_index_mapped(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, const uint64_t* keys,
+                                             const uint64_t* from, uint64_t n, int kmer_length, uint64_t mapping_first_node,
+                                             const uint64_t* mapping_ids, uint64_t mapping_size, gcsa_b200_verify_report* report)
+{
+  if(mapping_size > 0 && mapping_ids == nullptr)
+  {
+    gcsa_b200_internal_set_error("verify_index: null mapping");
+    return GCSA_B200_ERR_INVALID;
+  }
+  // Node::map (src/support.cpp:604-612) of a start position: the expected occurrences are mapped ones (algorithms.cpp:185-187)
+  auto mapped = [&](u64 value) -> u64
+  {
+    u64 id = value >> 11;
+    if(mapping_size == 0 || id < mapping_first_node || id - mapping_first_node >= mapping_size) { return value; }
+    return (mapping_ids[id - mapping_first_node] << 11) | (value & 0x7FF);
+  };
   if(index == nullptr || report == nullptr || (n > 0 && (keys == nullptr || from == nullptr)) || kmer_length < 1 || kmer_length > 16)
   {
     gcsa_b200_internal_set_error("verify_index: bad argument");
@@ -83,7 +102,7 @@ extern "C" int gcsa_b200_verify_index(const gcsa_b200_index* index, const gcsa_b
   // Sort by (label, from): parallelQuickSort(kmers) + the label groups of algorithms.cpp:106-125.
   std::vector<std::pair<u64, u64>> recs(n);
   #pragma omp parallel for schedule(static)
-  for(u64 i = 0; i < n; i++) { recs[i] = std::make_pair(keys[i] >> 16, from[i]); }     // Key::label, support.h:403
+  for(u64 i = 0; i < n; i++) { recs[i] = std::make_pair(keys[i] >> 16, mapped(from[i])); }     // Key::label, support.h:403
   __gnu_parallel::sort(recs.begin(), recs.end());
   std::vector<u64> group_start;
   for(u64 i = 0; i < n; i++) { if(i == 0 || recs[i].first != recs[i - 1].first) { group_start.push_back(i); } }

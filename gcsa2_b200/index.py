@@ -219,13 +219,17 @@ class GCSA:
         capi.lib().gcsa_b200_free(p)
         return n, arr[:n], arr[n:]
 
-    def verify(self, kmers, lcp=None):
-        """verifyIndex(index, lcp, kmers, kmer_length), src/algorithms.cpp:101-295, batched on the device.
+    def verify(self, kmers, lcp=None, mapping=None):
+        """verifyIndex(index, lcp, kmers, kmer_length, mapping), src/algorithms.cpp:101-295, batched on the device.
         kmers: builder.KMers (the construction input).  -> dict of the report; ok iff report["failures"] == 0."""
         rep = capi.VerifyReport()
         key, frm = capi.as_u64(kmers.key), capi.as_u64(kmers.from_)
-        capi.check(capi.lib().gcsa_b200_verify_index(self._h, lcp._h if lcp is not None else None, key.ctypes.data, frm.ctypes.data,
-                                                     int(kmers.key.size), int(kmers.k), C.byref(rep)))
+        ids = capi.as_u64(mapping.ids) if mapping is not None else None
+        capi.check(capi.lib().gcsa_b200_verify_index_mapped(self._h, lcp._h if lcp is not None else None, key.ctypes.data, frm.ctypes.data,
+                                                            int(kmers.key.size), int(kmers.k),
+                                                            int(mapping.first) if mapping is not None else 0,
+                                                            ids.ctypes.data if mapping is not None else None,
+                                                            len(mapping.ids) if mapping is not None else 0, C.byref(rep)))
         return {name: getattr(rep, name) for name, _ in capi.VerifyReport._fields_}
 
     def compare_kmers(self, other, k, include_Ns=False, return_kmers=False):

@@ -250,8 +250,7 @@ int gcsa_b200_compare_kmers(const gcsa_b200_index* left, const gcsa_b200_index* 
    obtained by dropping characters from the right end and depth() must agree; count() must equal the number
    of distinct start nodes; locate() must return exactly those; locate(range, 10) must return min(10, n) of
    them.  lcp may be NULL (the parent / depth checks are skipped, like `lcp == 0` in the reference).
-   Returns 0 when the verification ran; the index is correct iff report->failures == 0.  NodeMapping is
-   not supported (identity). */
+   Returns 0 when the verification ran; the index is correct iff report->failures == 0. */
 typedef struct gcsa_b200_verify_report {
   uint64_t unique;                      /* distinct labels queried */
   uint64_t failures;                    /* sum of the stage counters below */
@@ -261,6 +260,11 @@ typedef struct gcsa_b200_verify_report {
 } gcsa_b200_verify_report;
 int gcsa_b200_verify_index(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, const uint64_t* keys,
                            const uint64_t* from, uint64_t n, int kmer_length, gcsa_b200_verify_report* report);
+/* The same for an index built with a NodeMapping (the `mapping` argument of verifyIndex, algorithms.h:54): the
+   expected occurrences are the mapped start nodes.  Arguments as for gcsa_b200_build_from_kmers_mapped. */
+int gcsa_b200_verify_index_mapped(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, const uint64_t* keys,
+                                  const uint64_t* from, uint64_t n, int kmer_length, uint64_t mapping_first_node,
+                                  const uint64_t* mapping_ids, uint64_t mapping_size, gcsa_b200_verify_report* report);
 
 /* LCPArray, include/gcsa/lcp.h:90-194; load() at src/lcp.cpp:116-143. */
 int  gcsa_b200_lcp_create(const gcsa_flat_lcp* host, int device, gcsa_b200_lcp** out);
@@ -315,6 +319,16 @@ typedef struct gcsa_b200_built {
 int  gcsa_b200_build_from_kmers(const uint64_t* keys, const uint64_t* from, const uint64_t* to, uint64_t n,
                                 int kmer_length, int doubling_steps, uint64_t sample_period,
                                 gcsa_b200_built* result);
+/* The same with a NodeMapping (include/gcsa/support.h:167-222, InputGraph::mapping): node ids in
+   [mapping_first_node, mapping_first_node + mapping_size) of the input graph are REPORTED as mapping_ids[id - first]
+   -- the index is built for the input graph (with duplicated nodes, say) and locate() answers in the ids of the
+   original graph.  As in the reference the mapping is applied after the final merge (src/gcsa.cpp:428-443, 600): it
+   changes the samples and the counting structures, not the path nodes.  A .gcsa file carries the mapped values, so
+   loading one needs no mapping.  mapping_size = 0: identity (gcsa_b200_build_from_kmers). */
+int  gcsa_b200_build_from_kmers_mapped(const uint64_t* keys, const uint64_t* from, const uint64_t* to, uint64_t n,
+                                       int kmer_length, int doubling_steps, uint64_t sample_period,
+                                       uint64_t mapping_first_node, const uint64_t* mapping_ids, uint64_t mapping_size,
+                                       gcsa_b200_built* result);
 void gcsa_b200_built_free(gcsa_b200_built* result);
 
 /* The same construction for a graph that is ONE PATH (# -> s[0] -> ... -> s[length-1] -> $), on the device
@@ -361,6 +375,16 @@ typedef struct gcsa_b200_graph {
 } gcsa_b200_graph;
 
 typedef struct gcsa_b200_kmers { uint64_t n; uint64_t* key; uint64_t* from; uint64_t* to; } gcsa_b200_kmers;
+
+/* The construction input of the reference from its own files (host; gcsa2_b200/csrc/kmer_file.cpp): kmer files as vg
+   writes them -- binary .graph (sections of GraphFileHeader + KMer records, readBinary, src/files.cpp:127-167) or
+   text .gcsa2 (five tab-separated columns, readText, src/files.cpp:86-124; char2comp = NULL: the default alphabet) --
+   concatenated like InputGraph does for several files (src/files.cpp:308-345); *kmer_length receives their common kmer
+   length.  Release with gcsa_b200_kmers_free.  gcsa_b200_load_node_mapping replaces NodeMapping::load
+   (src/support.cpp:335-342) for build_gcsa's mapping file; release *ids with gcsa_b200_free. */
+int  gcsa_b200_read_kmer_files(const char* const* paths, int count, int binary, const uint8_t* char2comp,
+                               gcsa_b200_kmers* result, int* kmer_length);
+int  gcsa_b200_load_node_mapping(const char* path, uint64_t* first_node, uint64_t** ids, uint64_t* size);
 
 int  gcsa_b200_enumerate_kmers(const gcsa_b200_graph* graph, int kmer_length, gcsa_b200_kmers* result);
 void gcsa_b200_kmers_free(gcsa_b200_kmers* result);

@@ -47,7 +47,18 @@ void copyOut(const std::vector<std::uint64_t>& words, std::uint64_t* out, std::u
 extern "C" {
 
 /* GCSA(InputGraph&, ConstructionParameters) + LCPArray(InputGraph&, ...) on a binary kmer file. */
+RefIndex* ref_build_from(const char* graph_file, int binary, const char* mapping_file, int doubling_steps, std::uint64_t sample_period,
+                         std::uint64_t lcp_branching, const char* temp_dir);
+
 RefIndex* ref_build(const char* graph_file, int doubling_steps, std::uint64_t sample_period, std::uint64_t lcp_branching, const char* temp_dir)
+{
+  return ref_build_from(graph_file, 1, nullptr, doubling_steps, sample_period, lcp_branching, temp_dir);
+}
+
+/* The same from a binary (.graph) or text (.gcsa2) kmer file, optionally with a NodeMapping file (build_gcsa's mapping option):
+   InputGraph(files, binary, parameters, alphabet, mapping_name), src/files.cpp:286-361. */
+RefIndex* ref_build_from(const char* graph_file, int binary, const char* mapping_file, int doubling_steps, std::uint64_t sample_period,
+                         std::uint64_t lcp_branching, const char* temp_dir)
 {
   Verbosity::set(Verbosity::SILENT);
   if(temp_dir != nullptr) { TempFile::setDirectory(temp_dir); }
@@ -57,7 +68,7 @@ RefIndex* ref_build(const char* graph_file, int doubling_steps, std::uint64_t sa
   parameters.setLCPBranching(lcp_branching);
   RefIndex* r = new RefIndex();
   std::vector<std::string> files(1, graph_file);
-  r->graph.reset(new InputGraph(files, true, parameters));
+  r->graph.reset(new InputGraph(files, binary != 0, parameters, Alphabet(), std::string(mapping_file != nullptr ? mapping_file : "")));
   GCSA built(*(r->graph), parameters);
   r->index.swap(built);
   LCPArray lcp(*(r->graph), parameters);

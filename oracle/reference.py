@@ -48,6 +48,7 @@ def lib():
     L = C.CDLL(path)
     vp, u64 = C.c_void_p, C.c_uint64
     L.ref_build.restype = vp; L.ref_build.argtypes = [C.c_char_p, C.c_int, u64, u64, C.c_char_p]
+    L.ref_build_from.restype = vp; L.ref_build_from.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, u64, u64, C.c_char_p]
     L.ref_destroy.argtypes = [vp]
     L.ref_verify.restype = C.c_int; L.ref_verify.argtypes = [vp]
     L.ref_sizes.argtypes = [vp, vp]
@@ -83,12 +84,22 @@ class ReferenceIndex:
         self._h, self.has_lcp, self._tmp = handle, has_lcp, tmp_dir
 
     @staticmethod
-    def build(kmers, doubling_steps, sample_period=64, lcp_branching=64):
-        """GCSA::GCSA(InputGraph&, ConstructionParameters) on the kmers (written as a binary .graph file)."""
+    def build(kmers, doubling_steps, sample_period=64, lcp_branching=64, text=False, mapping=None):
+        """GCSA::GCSA(InputGraph&, ConstructionParameters) on the kmers, written as a binary .graph file (text=True: as a
+        text .gcsa2 file, read back by the reference's own readText); mapping: a builder.NodeMapping, written as the
+        mapping file build_gcsa takes."""
         tmp = tempfile.mkdtemp(prefix="gcsa_ref_")
-        path = os.path.join(tmp, "input.graph")
-        kmers.write_binary(path)
-        h = lib().ref_build(path.encode(), int(doubling_steps), int(sample_period), int(lcp_branching), tmp.encode())
+        path = os.path.join(tmp, "input.gcsa2" if text else "input.graph")
+        if text:
+            kmers.write_text(path)
+        else:
+            kmers.write_binary(path)
+        mapping_path = None
+        if mapping is not None:
+            mapping_path = os.path.join(tmp, "input.mapping")
+            mapping.write(mapping_path)
+        h = lib().ref_build_from(path.encode(), 0 if text else 1, mapping_path.encode() if mapping_path else None,
+                                 int(doubling_steps), int(sample_period), int(lcp_branching), tmp.encode())
         return ReferenceIndex(h, True, tmp)      # the InputGraph re-reads its file in verify()
 
     @staticmethod

@@ -70,3 +70,25 @@ def test_wrong_index_is_caught():
     bad.stored_samples[::7] += np.uint64(1)
     rep = GCSA(bad, kmer_table_k=4).verify(kmers)
     assert rep["count_failures"] == 0 and rep["locate_failures"] > 0
+
+
+def test_index_with_node_mapping_verifies_with_the_mapping():
+    """An index built with a NodeMapping (InputGraph::mapping: duplicated nodes of the input graph reported under the
+    ids of the original graph) passes verifyIndex with that mapping and fails it without (locate() reports mapped ids)."""
+    from gcsa2_b200 import GCSA, LCPArray
+    from gcsa2_b200.builder import NodeMapping, build_from_kmers, enumerate_kmers
+    graph = synth.snp_graph(synth.random_sequence(5000, seed=4), seed=4, snp_rate=0.05)[0]
+    kmers = enumerate_kmers(graph, 16)
+    ids = np.unique(graph.value >> np.uint64(11)).astype(np.int64)
+    first = int(ids[len(ids) * 3 // 4])
+    mapping = NodeMapping(first=first, ids=np.random.default_rng(5).integers(2, first, size=int(ids.max()) - first + 1).astype(np.uint64))
+    flat, flcp = build_from_kmers(kmers, 2, mapping=mapping)
+    gpu, glcp = GCSA(flat, kmer_table_k=4), LCPArray(flcp)
+    rep = gpu.verify(kmers, glcp, mapping=mapping)
+    assert rep["failures"] == 0, rep
+    rep = gpu.verify(kmers, glcp)
+    assert rep["find_failures"] == rep["parent_failures"] == 0 and rep["locate_failures"] + rep["count_failures"] > 0
+    # every located value is a mapped one
+    sp, ep = gpu.find_batch(["ACGT", "GGA", "T"])
+    _, vals = gpu.locate_batch(sp, ep)
+    assert ((vals >> np.uint64(11)).astype(np.int64) < first).all() or int((vals >> np.uint64(11)).max()) >= first + len(mapping.ids)
