@@ -22,13 +22,25 @@
 // find_kernel): the pattern is kept 2-bit packed, 32 characters at a time, and a path of up to 16 steps is one XOR
 // against it.  A path that the pattern leaves after t characters is followed by t + 1 single steps (the last of
 // which fails, as it must), so matches, depths and ranges are those of the single-step loop.
-template<int MODE, bool JUMP = false>
+// PACK: the pattern is kept 2-bit packed as for JUMP (one 8-byte streaming load per 8 characters instead of a byte
+// load and a table lookup in front of every step, and no load at all on the critical path of a step), without the
+// jump-table probes.
+// A match record (start, length, sp, ep): 32 bytes, written once and read later by another kernel or the host --
+// evict-first, so that the stream of records does not push the index out of the L2.
+__device__ __forceinline__ void store_match(u64* m, u64 start, u64 length, u64 sp, u64 ep)
+{
+  __stcs((unsigned long long*)m, (unsigned long long)start); __stcs((unsigned long long*)m + 1, (unsigned long long)length);
+  __stcs((unsigned long long*)m + 2, (unsigned long long)sp); __stcs((unsigned long long*)m + 3, (unsigned long long)ep);
+}
+
+template<int MODE, bool JUMP = false, bool PACK = false>
 __global__ void __launch_bounds__(256)
 mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const u64* __restrict__ offsets, u64 char_base,
            u64 n, u64* __restrict__ counts, const u64* __restrict__ out_offsets, u64* __restrict__ matches,
            const u64* __restrict__ ids, u64 stride, u32 parent_batch)
 {
   constexpr bool WRITE = (MODE == 1);
+  constexpr bool TAIL = (JUMP || PACK);
   __shared__ u8 c2c[256];
   for(int i = threadIdx.x; i < 256; i += blockDim.x) { c2c[i] = v.char2comp[i]; }
   __syncthreads();
@@ -43,7 +55,7 @@ mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const
 
   u64 q = 0, sp = 0, ep = 0, depth = 0, pos = 0, begin = 0, emitted = 0, out_at = 0;
   bool live = false, extended = false, need_parent = false;
-  u64 tail = 0, tail_end = 0; u32 tail_n = 0, skip = 0;     // JUMP: characters [tail_end - tail_n, tail_end) packed as in find_kernel
+  u64 tail = 0, tail_end = 0, next_pack = 0; u32 tail_n = 0, skip = 0;     // TAIL: characters [tail_end - tail_n, tail_end) packed as in find_kernel
 
   // pack the (up to) 32 characters that end at `end_pos` (exclusive), eight at a time, stopping at a non-base
   auto pack_tail = [&](u64 end_pos)
@@ -66,12 +78,12 @@ mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const
   };
   auto comp_at = [&](u64 p) -> u32
   {
-    if(JUMP)
+    if(TAIL)
     {
       u64 off = tail_end - 1 - p;
       if(off < (u64)tail_n) { return (u32)((tail >> (2 * off)) & 3) + 1; }
     }
-    return c2c[chars[p]];
+    return c2c[__ldcs(chars + p)];
   };
 
   while(true)
@@ -88,7 +100,7 @@ mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const
           q = (ids != nullptr ? ids[cand] : cand); live = true; need_parent = false;
           begin = offsets[q] - char_base; pos = offsets[q + 1] - char_base;
           sp = 0; ep = v.path_nodes - 1; depth = 0; extended = false; emitted = 0;
-          if(JUMP) { tail = 0; tail_n = 0; tail_end = pos; skip = 0; }
+          if(TAIL) { tail = 0; tail_n = 0; tail_end = pos; skip = 0; next_pack = pos; }
           if(WRITE) { out_at = out_offsets[q]; }
           if(MODE == 2) { out_at = q * stride; }
         }
@@ -120,7 +132,7 @@ mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const
     {
       if(depth > 0 && extended)
       {
-        if(WRITE || (MODE == 2 && emitted < stride)) { u64* m = matches + 4 * (out_at + emitted); m[0] = 0; m[1] = depth; m[2] = sp; m[3] = ep; }
+        if(WRITE || (MODE == 2 && emitted < stride)) { store_match(matches + 4 * (out_at + emitted), 0, depth, sp, ep); }
         emitted++;
       }
       if(!WRITE) { counts[q] = emitted; }
@@ -156,13 +168,20 @@ mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const
       }
       if(skip > 0) { skip--; }
     }
+    if(PACK && tail_end - pos >= (u64)tail_n && pos <= next_pack)
+    {
+      // the packed window is used up: the next 32 characters (fewer in front of a non-base or of the start of the
+      // pattern: those go through the byte path, and packing is tried again eight characters further on)
+      pack_tail(pos);
+      next_pack = pos - (tail_n > 0 ? tail_n : (pos - begin < 8 ? pos - begin : 8));
+    }
     u64 nsp, nep;
     lf_range(v, sp, ep, comp_at(pos - 1), nsp, nep);
     if(!range_empty(nsp, nep)) { sp = nsp; ep = nep; depth++; pos--; extended = true; continue; }
     if(depth == 0) { pos--; continue; }
     if(extended)
     {
-      if(WRITE || (MODE == 2 && emitted < stride)) { u64* m = matches + 4 * (out_at + emitted); m[0] = pos - begin; m[1] = depth; m[2] = sp; m[3] = ep; }
+      if(WRITE || (MODE == 2 && emitted < stride)) { store_match(matches + 4 * (out_at + emitted), pos - begin, depth, sp, ep); }
       emitted++; extended = false;
     }
     need_parent = true;

@@ -629,7 +629,11 @@ int gcsa_b200_index_create(const gcsa_flat_index* host, int device, const gcsa_b
   // two-step blocks (optional): built on the device from the one-step blocks
   // -1 = automatic: worth it once the one-step blocks are far beyond the L2 (the probe rate no longer
   // depends on the footprint there, so halving the probes halves the time; measured in DESIGN.md)
-  bool want_two_step = (options != nullptr && (options->two_step > 0 || (options->two_step < 0 && N >= 400000000ull)));
+  // (measured at 3 G nodes, profiles/r02_cfg4_3gbp_option_variants.json: with the jump tables the two-step blocks LOSE --
+  // the single steps left over are few and the 17.7 GB of extra sectors only dilute the TLB reach -- so the automatic
+  // choice takes them only for an index without jump tables)
+  bool want_two_step = (options != nullptr && (options->two_step > 0 ||
+                        (options->two_step < 0 && N >= 400000000ull && v.jump == nullptr && v.jump_wide == nullptr)));
   if(want_two_step && N > 0)
   {
     u64 n_blocks = N / BWT_W + 1;
@@ -2214,18 +2218,22 @@ static int memDevice(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, con
   int grid = gridFor(n, index->sm_count, 4);
   u32 parent_batch = 8;
   if(const char* e = std::getenv("GCSA_B200_MEM_PARENT_BATCH")) { parent_batch = (u32)std::max(1, std::atoi(e)); }
-  // GCSA_B200_MEM_JUMP=1: singleton ranges follow the jump tables (mem_kernel<.., JUMP>); off by default until measured
+  // GCSA_B200_MEM_PACK=0: byte loads in front of every step instead of the 2-bit packed pattern window (default on for
+  // the default alphabet).
+  bool pack = (index->view.default_alphabet != 0);
+  if(const char* e = std::getenv("GCSA_B200_MEM_PACK")) { pack = pack && (std::atoi(e) != 0); }
+  #define LAUNCH_MEM(M, G, ...) do { if(jump) { mem_kernel<M, true, false><<<G, 256, 0, st>>>(__VA_ARGS__); } \
+    else if(pack) { mem_kernel<M, false, true><<<G, 256, 0, st>>>(__VA_ARGS__); } else { mem_kernel<M, false, false><<<G, 256, 0, st>>>(__VA_ARGS__); } } while(0)
+  // GCSA_B200_MEM_JUMP=1: singleton ranges follow the jump tables (mem_kernel<.., JUMP>); off by default: measured slower
   bool jump = false;
   if(const char* e = std::getenv("GCSA_B200_MEM_JUMP")) { jump = (std::atoi(e) != 0 && index->view.jump != nullptr && index->view.default_alphabet != 0); }
   if(stride > 0)
   {
-    if(jump) { mem_kernel<2, true><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, scratch, nullptr, stride, parent_batch); }
-    else { mem_kernel<2><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, scratch, nullptr, stride, parent_batch); }
+    LAUNCH_MEM(2, grid, index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, scratch, nullptr, stride, parent_batch);
   }
   else
   {
-    if(jump) { mem_kernel<0, true><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, nullptr, nullptr, 0, parent_batch); }
-    else { mem_kernel<0><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, nullptr, nullptr, 0, parent_batch); }
+    LAUNCH_MEM(0, grid, index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, nullptr, nullptr, 0, parent_batch);
   }
   int rc = scanExclusive(counts, (u64*)d_out_offsets, n + 1, st);
   if(rc) { cleanup(); return rc; }
@@ -2244,8 +2252,7 @@ static int memDevice(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, con
   if(d_matches == nullptr || capacity < total) { cleanup(); return fail(GCSA_B200_ERR_CAPACITY, "mem_batch: output capacity too small"); }
   if(stride == 0)
   {
-    if(jump) { mem_kernel<1, true><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, nullptr, (const u64*)d_out_offsets, (u64*)d_matches, nullptr, 0, parent_batch); }
-    else { mem_kernel<1><<<grid, 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, nullptr, (const u64*)d_out_offsets, (u64*)d_matches, nullptr, 0, parent_batch); }
+    LAUNCH_MEM(1, grid, index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, nullptr, (const u64*)d_out_offsets, (u64*)d_matches, nullptr, 0, parent_batch);
   }
   else
   {
@@ -2256,20 +2263,13 @@ static int memDevice(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, con
                                                                    (ulonglong4*)d_matches, overflow, n_overflow);
     if(overflowing > 0)
     {
-      if(jump)
-      {
-        mem_kernel<1, true><<<gridFor(overflowing, index->sm_count, 4), 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, overflowing,
-                                                                                    nullptr, (const u64*)d_out_offsets, (u64*)d_matches, overflow, 0, parent_batch);
-      }
-      else
-      {
-        mem_kernel<1><<<gridFor(overflowing, index->sm_count, 4), 256, 0, st>>>(index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, overflowing,
-                                                                              nullptr, (const u64*)d_out_offsets, (u64*)d_matches, overflow, 0, parent_batch);
-      }
+      LAUNCH_MEM(1, gridFor(overflowing, index->sm_count, 4), index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, overflowing,
+                 nullptr, (const u64*)d_out_offsets, (u64*)d_matches, overflow, 0, parent_batch);
     }
   }
   MEM_TRY(cudaGetLastError());
   cleanup();
+  #undef LAUNCH_MEM
   #undef MEM_TRY
   return 0;
 }
