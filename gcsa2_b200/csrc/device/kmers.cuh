@@ -39,6 +39,54 @@ kmer_compact_kernel(const u64* __restrict__ csp, const u64* __restrict__ cep, co
   }
 }
 
+__device__ __forceinline__ void trie_child(const DevView& v, u64 s, u64 e, u32 c, u64& a, u64& b);
+
+// The same level in ONE kernel when only the NUMBER of k-mers is wanted (the order of the frontier is then free):
+// one thread per frontier range computes all its children -- for a single path node its four fast sectors are one
+// 128-byte line, read once -- and the surviving ones are appended to the next frontier at a position taken from a
+// counter (one atomic per warp).  No flags, no scan, no second pass, no host round trip inside a level.
+__global__ void __launch_bounds__(256)
+kmer_level_kernel(const DevView v, const ulonglong2* __restrict__ in, u64 n, u32 chars, ulonglong2* __restrict__ out,
+                  unsigned long long* __restrict__ out_count, u64 capacity)
+{
+  const u32 lane = threadIdx.x & 31;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const u64 rounds = (n + stride - 1) / stride;
+  for(u64 r = 0; r < rounds; r++)
+  {
+    const u64 i = r * stride + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 a[6], b[6]; u32 alive = 0;
+    if(i < n)
+    {
+      const ulonglong2 range = __ldcs(in + i);
+      #pragma unroll
+      for(u32 c = 1; c <= 5; c++)
+      {
+        a[c] = 1; b[c] = 0;
+        if(c > chars) { continue; }
+        trie_child(v, range.x, range.y, c, a[c], b[c]);
+        if(!range_empty(a[c], b[c])) { alive |= 1u << c; }
+      }
+    }
+    // positions in the next frontier: exclusive prefix of the survivor counts over the warp
+    const u32 mine = (u32)__popc(alive);
+    u32 before = mine;
+    #pragma unroll
+    for(int d = 1; d < 32; d <<= 1) { u32 o = __shfl_up_sync(0xFFFFFFFFu, before, d); if(lane >= (u32)d) { before += o; } }
+    const u32 warp_total = __shfl_sync(0xFFFFFFFFu, before, 31);
+    before -= mine;
+    unsigned long long base = 0;
+    if(lane == 0 && warp_total > 0) { base = atomicAdd(out_count, (unsigned long long)warp_total); }
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    u64 at = base + before;
+    #pragma unroll
+    for(u32 c = 1; c <= 5; c++)
+    {
+      if((alive >> c) & 1) { if(at < capacity) { __stcs((ulonglong2*)out + at, make_ulonglong2(a[c], b[c])); } at++; }
+    }
+  }
+}
+
 //------------------------------------------------------------------------------
 // Kernels: compareKMers (src/algorithms.cpp:505-616) -- the tries of two indexes in lockstep
 //------------------------------------------------------------------------------

@@ -23,18 +23,17 @@
 // against it.  A path that the pattern leaves after t characters is followed by t + 1 single steps (the last of
 // which fails, as it must), so matches, depths and ranges are those of the single-step loop.
 // PACK: the pattern is kept 2-bit packed as for JUMP (one 8-byte streaming load per 8 characters instead of a byte
-// load and a table lookup in front of every step, and no load at all on the critical path of a step), without the
-// jump-table probes.
-// A match record (start, length, sp, ep): 32 bytes, written once and read later by another kernel or the host --
-// evict-first, so that the stream of records does not push the index out of the L2.
+// load and a table lookup in front of every step), without the jump-table probes.  Measured slower than the byte
+// loads (34.2 vs 27.6 ms per 4 M patterns, profiles/r02_mem_scan_variants.txt): the bytes hit the L1, the packing costs
+// registers and instructions in a kernel that is short of both; opt-in (GCSA_B200_MEM_PACK=1).
+// A match record (start, length, sp, ep)
 __device__ __forceinline__ void store_match(u64* m, u64 start, u64 length, u64 sp, u64 ep)
 {
-  __stcs((unsigned long long*)m, (unsigned long long)start); __stcs((unsigned long long*)m + 1, (unsigned long long)length);
-  __stcs((unsigned long long*)m + 2, (unsigned long long)sp); __stcs((unsigned long long*)m + 3, (unsigned long long)ep);
+  m[0] = start; m[1] = length; m[2] = sp; m[3] = ep;
 }
 
-template<int MODE, bool JUMP = false, bool PACK = false>
-__global__ void __launch_bounds__(256)
+template<int MODE, bool JUMP = false, bool PACK = false, int MIN_BLOCKS = 4>
+__global__ void __launch_bounds__(256, MIN_BLOCKS)
 mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const u64* __restrict__ offsets, u64 char_base,
            u64 n, u64* __restrict__ counts, const u64* __restrict__ out_offsets, u64* __restrict__ matches,
            const u64* __restrict__ ids, u64 stride, u32 parent_batch)
@@ -83,7 +82,7 @@ mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const
       u64 off = tail_end - 1 - p;
       if(off < (u64)tail_n) { return (u32)((tail >> (2 * off)) & 3) + 1; }
     }
-    return c2c[__ldcs(chars + p)];
+    return c2c[chars[p]];      // (plain loads: the 32-byte sector stays in the L1 for the following steps; evict-first loads measured 13 % slower)
   };
 
   while(true)

@@ -2024,6 +2024,38 @@ int gcsa_b200_count_kmers(const gcsa_b200_index* index, uint64_t k, int include_
   cudaError_t e = cudaSuccess;
   int rc = 0;
   #define KM_TRY(expr) do { e = (expr); if(e != cudaSuccess) { rc = fail(GCSA_B200_ERR_CUDA, std::string("count_kmers: " #expr ": ") + cudaGetErrorString(e)); goto done; } } while(0)
+  // Only the number is wanted: the frontier need not stay ordered, one kernel per level (kmer_level_kernel).  The
+  // frontier of a level is at most `chars` times the one before, and the two buffers are sized for that.
+  static const bool unordered_off = []() { const char* s_ = std::getenv("GCSA_B200_KMERS_ORDERED"); return (s_ != nullptr && std::atoi(s_) != 0); }();
+  ulonglong2 *cur = nullptr, *next_buf = nullptr; unsigned long long* counter = nullptr;
+  if(ranges == nullptr && !unordered_off)
+  {
+    u64 cur_capacity = 0, next_capacity = 0;
+    {
+      ulonglong2 root = make_ulonglong2(0, index->header.path_nodes - 1);
+      KM_TRY(engineMallocAsync(&cur, sizeof(ulonglong2), st)); cur_capacity = 1;
+      KM_TRY(engineMallocAsync(&counter, sizeof(unsigned long long), st));
+      KM_TRY(cudaMemcpyAsync(cur, &root, sizeof(root), cudaMemcpyHostToDevice, st));
+      for(u64 level = 0; level < k && n > 0; level++)
+      {
+        u64 want = n * chars;
+        if(next_buf == nullptr || next_capacity < want)
+        {
+          if(next_buf) { cudaFreeAsync(next_buf, st); next_buf = nullptr; }
+          KM_TRY(engineMallocAsync(&next_buf, want * sizeof(ulonglong2), st)); next_capacity = want;
+        }
+        KM_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+        kmer_level_kernel<<<gridFor(n, index->sm_count), 256, 0, st>>>(index->view, cur, n, chars, next_buf, counter, next_capacity);
+        unsigned long long produced = 0;
+        KM_TRY(cudaMemcpyAsync(&produced, counter, sizeof(produced), cudaMemcpyDeviceToHost, st));
+        KM_TRY(cudaStreamSynchronize(st));
+        std::swap(cur, next_buf); std::swap(cur_capacity, next_capacity);
+        n = produced;
+      }
+      *result = n;
+    }
+    goto done;
+  }
   {
     u64 root[2] = { 0, index->header.path_nodes - 1 };
     KM_TRY(engineMallocAsync(&sp, sizeof(u64), st)); KM_TRY(engineMallocAsync(&ep, sizeof(u64), st));
@@ -2060,6 +2092,9 @@ int gcsa_b200_count_kmers(const gcsa_b200_index* index, uint64_t k, int include_
 done:
   if(sp) { cudaFreeAsync(sp, st); }
   if(ep) { cudaFreeAsync(ep, st); }
+  if(cur) { cudaFreeAsync(cur, st); }
+  if(next_buf) { cudaFreeAsync(next_buf, st); }
+  if(counter) { cudaFreeAsync(counter, st); }
   e = cudaStreamSynchronize(st);
   cudaStreamDestroy(st);
   #undef KM_TRY
@@ -2215,15 +2250,19 @@ static int memDevice(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, con
   if(scratch == nullptr) { stride = 0; }
   MEM_TRY(cudaMemsetAsync(counts, 0, (n + 1) * sizeof(u64), st));
   MEM_TRY(cudaMemsetAsync(n_overflow, 0, sizeof(ull), st));
-  int grid = gridFor(n, index->sm_count, 4);
+  static const int mem_blocks = []() { const char* e_ = std::getenv("GCSA_B200_MEM_MINBLOCKS"); int m_ = (e_ != nullptr ? std::atoi(e_) : 4); return (m_ >= 6 ? 6 : (m_ == 5 ? 5 : 4)); }();
+  int grid = gridFor(n, index->sm_count, mem_blocks);
   u32 parent_batch = 8;
   if(const char* e = std::getenv("GCSA_B200_MEM_PARENT_BATCH")) { parent_batch = (u32)std::max(1, std::atoi(e)); }
-  // GCSA_B200_MEM_PACK=0: byte loads in front of every step instead of the 2-bit packed pattern window (default on for
-  // the default alphabet).
-  bool pack = (index->view.default_alphabet != 0);
-  if(const char* e = std::getenv("GCSA_B200_MEM_PACK")) { pack = pack && (std::atoi(e) != 0); }
+  // GCSA_B200_MEM_PACK=1: the 2-bit packed pattern window instead of byte loads (measured slower: mem.cuh); off by default.
+  // GCSA_B200_MEM_MINBLOCKS=6: more resident warps at fewer registers each (experiments).
+  bool pack = false;
+  if(const char* e = std::getenv("GCSA_B200_MEM_PACK")) { pack = (index->view.default_alphabet != 0) && (std::atoi(e) != 0); }
   #define LAUNCH_MEM(M, G, ...) do { if(jump) { mem_kernel<M, true, false><<<G, 256, 0, st>>>(__VA_ARGS__); } \
-    else if(pack) { mem_kernel<M, false, true><<<G, 256, 0, st>>>(__VA_ARGS__); } else { mem_kernel<M, false, false><<<G, 256, 0, st>>>(__VA_ARGS__); } } while(0)
+    else if(pack) { mem_kernel<M, false, true><<<G, 256, 0, st>>>(__VA_ARGS__); } \
+    else if(mem_blocks >= 6) { mem_kernel<M, false, false, 6><<<G, 256, 0, st>>>(__VA_ARGS__); } \
+    else if(mem_blocks == 5) { mem_kernel<M, false, false, 5><<<G, 256, 0, st>>>(__VA_ARGS__); } \
+    else { mem_kernel<M, false, false><<<G, 256, 0, st>>>(__VA_ARGS__); } } while(0)
   // GCSA_B200_MEM_JUMP=1: singleton ranges follow the jump tables (mem_kernel<.., JUMP>); off by default: measured slower
   bool jump = false;
   if(const char* e = std::getenv("GCSA_B200_MEM_JUMP")) { jump = (std::atoi(e) != 0 && index->view.jump != nullptr && index->view.default_alphabet != 0); }
