@@ -105,51 +105,74 @@ __device__ __forceinline__ void trie_child(const DevView& v, u64 s, u64 e, u32 c
   else { lf_range(v, s, e, c, a, b); }
 }
 
+// One level of the two tries in lockstep, in one kernel: one thread per state (a pair of ranges, left and right index)
+// computes its children in both indexes and appends those that are alive in either (algorithms.cpp:514) to the next
+// frontier at a position taken from a counter (one atomic per warp).  The order of the frontier is free: the counts
+// do not depend on it and the reference's own output order depends on thread scheduling.
 // states: 4 arrays (left sp, left ep, right sp, right ep) of `stride` entries each; kmers: 3 words per state or null.
 __global__ void __launch_bounds__(256)
-compare_expand_kernel(const DevView vl, const DevView vr, const u64* __restrict__ in, u64 n, const u64* __restrict__ in_kmer,
-                      u32 chars, u64 level, u64* __restrict__ out, u64* __restrict__ out_kmer, u64* __restrict__ flag)
+compare_level_kernel(const DevView vl, const DevView vr, const u64* __restrict__ in, u64 n, u64 in_stride, const u64* __restrict__ in_kmer,
+                     u32 chars, u64 level, u64* __restrict__ out, u64 out_stride, u64* __restrict__ out_kmer,
+                     unsigned long long* __restrict__ out_count)
 {
-  u64 total = n * chars;
-  for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x)
+  const u32 lane = threadIdx.x & 31;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const u64 rounds = (n + stride - 1) / stride;
+  for(u64 r = 0; r < rounds; r++)
   {
-    u64 i = t / chars; u32 c = (u32)(t - i * chars) + 1;
-    u64 la, lb, ra, rb;
-    trie_child(vl, in[i], in[n + i], c, la, lb);
-    trie_child(vr, in[2 * n + i], in[3 * n + i], c, ra, rb);
-    out[t] = la; out[total + t] = lb; out[2 * total + t] = ra; out[3 * total + t] = rb;
-    flag[t] = ((range_empty(la, lb) && range_empty(ra, rb)) ? 0 : 1);          // algorithms.cpp:514
-    if(out_kmer != nullptr)
+    const u64 i = r * stride + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 la[6], lb[6], ra[6], rb[6]; u32 alive = 0;
+    if(i < n)
     {
-      u64 w0 = in_kmer[3 * i], w1 = in_kmer[3 * i + 1], w2 = in_kmer[3 * i + 2];
-      u64 bit = level * 3, word = bit >> 6, off = bit & 63, x = (u64)c << off, y = (off > 61 ? (u64)c >> (64 - off) : 0);   // KMerComparisonState::set, algorithms.cpp:451-457
-      if(word == 0) { w0 |= x; w1 |= y; } else if(word == 1) { w1 |= x; w2 |= y; } else { w2 |= x; }
-      out_kmer[3 * t] = w0; out_kmer[3 * t + 1] = w1; out_kmer[3 * t + 2] = w2;
+      const u64 ls = in[i], le = in[in_stride + i], rs = in[2 * in_stride + i], re = in[3 * in_stride + i];
+      #pragma unroll
+      for(u32 c = 1; c <= 5; c++)
+      {
+        la[c] = 1; lb[c] = 0; ra[c] = 1; rb[c] = 0;
+        if(c > chars) { continue; }
+        trie_child(vl, ls, le, c, la[c], lb[c]);
+        trie_child(vr, rs, re, c, ra[c], rb[c]);
+        if(!(range_empty(la[c], lb[c]) && range_empty(ra[c], rb[c]))) { alive |= 1u << c; }
+      }
     }
-  }
-}
-
-__global__ void __launch_bounds__(256)
-compare_compact_kernel(const u64* __restrict__ child, const u64* __restrict__ child_kmer, const u64* __restrict__ flag,
-                       const u64* __restrict__ pos, u64 total, u64 next, u64* __restrict__ out, u64* __restrict__ out_kmer)
-{
-  for(u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x)
-  {
-    if(!flag[t]) { continue; }
-    u64 d = pos[t];
-    for(int f = 0; f < 4; f++) { out[f * next + d] = child[f * total + t]; }
-    if(out_kmer != nullptr) { for(int w = 0; w < 3; w++) { out_kmer[3 * d + w] = child_kmer[3 * t + w]; } }
+    const u32 mine = (u32)__popc(alive);
+    u32 before = mine;
+    #pragma unroll
+    for(int d = 1; d < 32; d <<= 1) { u32 o = __shfl_up_sync(0xFFFFFFFFu, before, d); if(lane >= (u32)d) { before += o; } }
+    const u32 warp_total = __shfl_sync(0xFFFFFFFFu, before, 31);
+    before -= mine;
+    unsigned long long base = 0;
+    if(lane == 0 && warp_total > 0) { base = atomicAdd(out_count, (unsigned long long)warp_total); }
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    u64 at = base + before;
+    #pragma unroll
+    for(u32 c = 1; c <= 5; c++)
+    {
+      if(!((alive >> c) & 1)) { continue; }
+      if(at < out_stride)
+      {
+        out[at] = la[c]; out[out_stride + at] = lb[c]; out[2 * out_stride + at] = ra[c]; out[3 * out_stride + at] = rb[c];
+        if(out_kmer != nullptr)
+        {
+          u64 w0 = in_kmer[3 * i], w1 = in_kmer[3 * i + 1], w2 = in_kmer[3 * i + 2];
+          u64 bit = level * 3, word = bit >> 6, off = bit & 63, x = (u64)c << off, y = (off > 61 ? (u64)c >> (64 - off) : 0);   // KMerComparisonState::set, algorithms.cpp:451-457
+          if(word == 0) { w0 |= x; w1 |= y; } else if(word == 1) { w1 |= x; w2 |= y; } else { w2 |= x; }
+          out_kmer[3 * at] = w0; out_kmer[3 * at + 1] = w1; out_kmer[3 * at + 2] = w2;
+        }
+      }
+      at++;
+    }
   }
 }
 
 // KMerSymmetricDifference::report, algorithms.cpp:488-500: side[i] = 0 shared, 1 left only, 2 right only.
 __global__ void __launch_bounds__(256)
-compare_classify_kernel(const u64* __restrict__ st, u64 n, ull* __restrict__ counts, u64* __restrict__ left_flag, u64* __restrict__ right_flag)
+compare_classify_kernel(const u64* __restrict__ st, u64 n, u64 st_stride, ull* __restrict__ counts, u64* __restrict__ left_flag, u64* __restrict__ right_flag)
 {
   ull shared_n = 0, left_n = 0, right_n = 0;
   for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
   {
-    u64 llen = st[n + i] + 1 - st[i], rlen = st[3 * n + i] + 1 - st[2 * n + i];
+    u64 llen = st[st_stride + i] + 1 - st[i], rlen = st[3 * st_stride + i] + 1 - st[2 * st_stride + i];
     u32 side = (llen > 0 && rlen > 0 ? 0 : (llen > 0 ? 1 : 2));
     shared_n += (side == 0); left_n += (side == 1); right_n += (side == 2);
     if(left_flag != nullptr) { left_flag[i] = (side == 1); right_flag[i] = (side == 2); }
@@ -165,14 +188,14 @@ compare_classify_kernel(const u64* __restrict__ st, u64 n, ull* __restrict__ cou
 
 // Unique kmers as gcsa_b200_kmer_state records (8 words each).
 __global__ void __launch_bounds__(256)
-compare_emit_kernel(const u64* __restrict__ st, const u64* __restrict__ kmer, u64 n, u64 k, const u64* __restrict__ flag,
+compare_emit_kernel(const u64* __restrict__ st, u64 st_stride, const u64* __restrict__ kmer, u64 n, u64 k, const u64* __restrict__ flag,
                     const u64* __restrict__ pos, u64* __restrict__ records)
 {
   for(u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
   {
     if(!flag[i]) { continue; }
     u64* r = records + 8 * pos[i];
-    r[0] = st[i]; r[1] = st[n + i]; r[2] = st[2 * n + i]; r[3] = st[3 * n + i]; r[4] = k;
+    r[0] = st[i]; r[1] = st[st_stride + i]; r[2] = st[2 * st_stride + i]; r[3] = st[3 * st_stride + i]; r[4] = k;
     r[5] = kmer[3 * i]; r[6] = kmer[3 * i + 1]; r[7] = kmer[3 * i + 2];
   }
 }

@@ -68,8 +68,8 @@ struct emu_event_;  typedef emu_event_* cudaEvent_t;
 typedef void* cudaMemPool_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
 enum { cudaStreamNonBlocking = 1, cudaEventBlockingSync = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0 };
-enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
-enum cudaLimit { cudaLimitMaxL2FetchGranularity = 5 };
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16, cudaDevAttrMaxPersistingL2CacheSize = 108, cudaDevAttrMaxAccessPolicyWindowSize = 109 };
+enum cudaLimit { cudaLimitMaxL2FetchGranularity = 5, cudaLimitPersistingL2CacheSize = 6 };
 enum cudaMemPoolAttr { cudaMemPoolAttrReleaseThreshold = 4 };
 
 namespace emu
@@ -152,7 +152,7 @@ static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int d) { return (d == 0 ? cudaSuccess : cudaErrorInvalidValue); }
-static inline cudaError_t cudaDeviceGetAttribute(int* value, cudaDeviceAttr, int) { *value = (int)emu::envBytes("GCSA_EMU_SMS", 2); return cudaSuccess; }
+static inline cudaError_t cudaDeviceGetAttribute(int* value, cudaDeviceAttr attr, int) { *value = (attr == cudaDevAttrMultiProcessorCount ? (int)emu::envBytes("GCSA_EMU_SMS", 2) : 0); return cudaSuccess; }
 static inline cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* pool, int) { *pool = nullptr; return cudaSuccess; }
@@ -184,6 +184,10 @@ static inline cudaError_t cudaMemsetAsync(void* p, int value, size_t bytes, cuda
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)emu::alloc(16); return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { emu::release((void*)s); return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+enum { cudaAccessPropertyPersisting = 2, cudaAccessPropertyStreaming = 1, cudaStreamAttributeAccessPolicyWindow = 1 };
+struct cudaAccessPolicyWindow { void* base_ptr; size_t num_bytes; float hitRatio; int hitProp, missProp; };
+union cudaStreamAttrValue { cudaAccessPolicyWindow accessPolicyWindow; };
+static inline cudaError_t cudaStreamSetAttribute(cudaStream_t, int, const cudaStreamAttrValue*) { return cudaSuccess; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t)emu::alloc(16); return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { emu::release((void*)e); return cudaSuccess; }
