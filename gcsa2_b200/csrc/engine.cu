@@ -35,7 +35,6 @@
 #include <atomic>
 #include <cmath>
 #include <cstdint>
-#include <memory>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -2251,42 +2250,6 @@ static int memDevice(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, con
   if(scratch == nullptr) { stride = 0; }
   MEM_TRY(cudaMemsetAsync(counts, 0, (n + 1) * sizeof(u64), st));
   MEM_TRY(cudaMemsetAsync(n_overflow, 0, sizeof(ull), st));
-  // The fused blocks are what every step of the scan reads; the pattern, offset and match streams flow through the
-  // same L2 and push them out (ncu: 35 % L2 hit rate on an index that would fit).  GCSA_B200_MEM_L2_PERSIST=1 asks the
-  // L2 to keep the blocks (an access-policy window on the stream for the duration of the call).
-  static const bool l2_persist = []() { const char* e_ = std::getenv("GCSA_B200_MEM_L2_PERSIST"); return (e_ != nullptr && std::atoi(e_) != 0); }();
-  struct PersistWindow
-  {
-    cudaStream_t stream; bool on = false;
-    PersistWindow(cudaStream_t st_, const void* base, size_t bytes, int device) : stream(st_)
-    {
-      int max_persist = 0, max_window = 0;
-      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
-      cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
-      if(max_persist <= 0 || max_window <= 0 || bytes == 0) { cudaGetLastError(); return; }
-      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
-      cudaStreamAttrValue attr;
-      std::memset(&attr, 0, sizeof(attr));
-      attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
-      attr.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)max_window);
-      attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)attr.accessPolicyWindow.num_bytes);
-      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-      on = (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess);
-      cudaGetLastError();
-    }
-    ~PersistWindow()
-    {
-      if(!on) { return; }
-      cudaStreamAttrValue attr;
-      std::memset(&attr, 0, sizeof(attr));
-      attr.accessPolicyWindow.num_bytes = 0;
-      cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
-      cudaGetLastError();
-    }
-  };
-  std::unique_ptr<PersistWindow> persist;
-  if(l2_persist) { persist.reset(new PersistWindow(st, index->view.bwt, (size_t)(index->view.path_nodes / BWT_W + 1) * 4 * sizeof(ulonglong4), index->device)); }
   static const int mem_blocks = []() { const char* e_ = std::getenv("GCSA_B200_MEM_MINBLOCKS"); int m_ = (e_ != nullptr ? std::atoi(e_) : 5); return (m_ >= 6 ? 6 : (m_ == 5 ? 5 : 4)); }();   // 5: 23.3 ms against 24.2 (4) and 36.5 (6) per 4 M patterns
   int grid = gridFor(n, index->sm_count, mem_blocks);
   u32 parent_batch = 8;

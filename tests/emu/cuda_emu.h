@@ -184,10 +184,6 @@ static inline cudaError_t cudaMemsetAsync(void* p, int value, size_t bytes, cuda
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)emu::alloc(16); return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { emu::release((void*)s); return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-enum { cudaAccessPropertyPersisting = 2, cudaAccessPropertyStreaming = 1, cudaStreamAttributeAccessPolicyWindow = 1 };
-struct cudaAccessPolicyWindow { void* base_ptr; size_t num_bytes; float hitRatio; int hitProp, missProp; };
-union cudaStreamAttrValue { cudaAccessPolicyWindow accessPolicyWindow; };
-static inline cudaError_t cudaStreamSetAttribute(cudaStream_t, int, const cudaStreamAttrValue*) { return cudaSuccess; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t)emu::alloc(16); return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { emu::release((void*)e); return cudaSuccess; }
