@@ -35,6 +35,10 @@ if os.environ.get("OMP_NUM_THREADS") == "1" and int(os.environ.get("WORLD_SIZE",
 
 METRIC = "kmer_find_queries_per_sec"
 UNIT = "queries/s"
+# Dependent chains of random 32-byte sector reads over footprints beyond 4 GB: 43.4-44.7 G probes/s on a B200
+# (scripts/gather_probe.cu, profiles/r01_random_probe_microbench.txt) -- the ceiling of a kernel whose work is random probes.
+PROBE_CEILING = 44.0e9
+PROBE_CEILING_SOURCE = "profiles/r01_random_probe_microbench.txt (scripts/gather_probe.cu, footprints of 4.8-19 GB)"
 
 
 def parse_args():
@@ -310,6 +314,27 @@ def locate_leg(args, rank, world, local, barrier, dist, torch, fixture):
                    "h2d_bytes_per_step": int(16 * n), "d2h_bytes_per_step": int(8 * (n + 1) + 8 * got[0]),
                    "api": "gcsa_b200_locate_into_host (pinned host buffers, chunked H2D/locate/D2H pipeline)", "matches_device_leg": same},
            "setup": {"index_build_s": build_s}}
+    if rank == 0:
+        # SURVEY.md 8(d), locate: per located node one probe of the locate table (64 B), per range 16 B in and 8 B of
+        # offsets out, per position 8 B out.  (locate_small_count / fill read the table once per node: every 64-mer of
+        # this workload is a range of at most a few nodes with direct entries.)
+        peak, peak_src = peaks()
+        nodes = float((d_ep - d_sp + 1).clamp(min=0).sum().item())
+        algorithmic = 64.0 * nodes + 24.0 * n + 8.0 * got[0]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic_find_cfg2.json")
+        if os.path.exists(tpath) and n == 10_000_000 and args.locate_mbp == 50.0:
+            with open(tpath) as f:
+                entry = json.load(f).get("locate_cfg3")
+            traffic = float(entry["dram_bytes_per_launch"]) if entry else None
+        out["roofline"] = {"bound": "hbm", "achieved": algorithmic / (ms / 1000.0) / 1e9, "peak": peak, "unit": "GB/s",
+                           "frac": algorithmic / (ms / 1000.0) / 1e9 / peak, "traffic": traffic,
+                           "dram_frac": (traffic / (ms / 1000.0) / 1e9 / peak if traffic else None),
+                           "kernel": "locate_small_count_kernel + locate_small_fill_kernel", "peak_source": peak_src,
+                           "probe_ceiling": PROBE_CEILING, "probe_rate": nodes / (ms / 1000.0),
+                           "probe_frac": (nodes / PROBE_CEILING + (24.0 * n + 8.0 * got[0]) / (peak * 1e9)) / (ms / 1000.0),
+                           "accounting": "64 B per located path node (one locate-table entry) + 16 B per range in + 8 B of offsets and 8 B per position out; "
+                                         "probe_frac as for find(): time at the HBM random-access rate for the probes + time at the copy peak for the streams, over the time taken"}
     if rank == 0 and not args.no_cpu_baseline:
         engine, kind, threads = cpu_engine(flat)
         m = min(n, 50_000 * threads)
@@ -479,6 +504,9 @@ def cfg4_leg(args, rank, world, local, barrier, dist, torch):
         out["roofline"] = {"bound": "hbm", "achieved": per_query * rank0_queries / secs / 1e9, "peak": peak, "unit": "GB/s",
                            "frac": per_query * rank0_queries / secs / 1e9 / peak, "traffic": None, "kernel": "find_fast_kernel<false,false,4> (+ find_quad_kernel, find_kernel<false,4,false,true> for the work lists)",
                            "peak_source": peak_src, "probes_per_query": (st["sector_probes"] + st["table_hits"]) / k,
+                           "probe_ceiling": PROBE_CEILING, "probe_ceiling_source": PROBE_CEILING_SOURCE,
+                           "probe_rate": (st["sector_probes"] + st["table_hits"]) / k * rank0_queries / secs,
+                           "probe_frac": ((st["sector_probes"] + st["table_hits"]) / k * rank0_queries / PROBE_CEILING + (length + 16.0) * rank0_queries / (peak * 1e9)) / secs,
                            "lf_steps_per_query": st["lf_steps"] / k,
                            "accounting": "per GPU (rank 0): 64 B per distinct probe executed + |P| + 16 B I/O per query, over the time of one pass"}
     if rank == 0 and flat is not None:
@@ -771,6 +799,11 @@ def main():
                                        "achieved_payload charges a k-mer table entry its payload only (8 B, 16 B fused), as the lines of profiles/r01_bench_cfg2_*.json did; "
                                        "dram_frac = recorded ncu DRAM bytes of this launch / this run's time / peak: a random probe into tens of GB costs ~128 B of HBM traffic, "
                                        "twice the 64 B the accounting grants it (profiles/r01_random_probe_microbench.txt)",
+                         # the roofline that binds a random probe into tens of GB is the HBM random-access rate, not the copy
+                         # bandwidth: time at that rate for the probes + time at the copy peak for the streams, over the time taken
+                         "probe_ceiling": PROBE_CEILING, "probe_ceiling_source": PROBE_CEILING_SOURCE,
+                         "probe_rate": scale * (st["sector_probes"] + st["table_hits"]) / (ms_total / args.steps / 1000.0),
+                         "probe_frac": (scale * (st["sector_probes"] + st["table_hits"]) / PROBE_CEILING + float(n) * (length + 16) / (peak * 1e9)) / (ms_total / args.steps / 1000.0),
                          "jump_table_k": index.jumpK(),
                          "lf_steps_per_query": st["lf_steps"] / m, "sector_probes_per_query": st["sector_probes"] / m},
             "clocks": clocks,

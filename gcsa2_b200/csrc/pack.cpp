@@ -97,6 +97,11 @@ bool packRangeAvx2(const uint8_t* chars, u64 first, u64 last, u64 length, const 
   return ok && ((uint32_t)_mm256_movemask_epi8(all_valid) == 0xFFFFFFFFu);
 }
 
+// Streaming stores send the packed words past the caches to memory; plain stores leave them in the last-level cache,
+// where the copy engine's reads can find them (the staging ring of the host pipeline is a few MB).
+// GCSA_B200_PACK_STREAM=0 selects plain stores.
+static const bool g_stream_stores = []() { const char* e = std::getenv("GCSA_B200_PACK_STREAM"); return !(e != nullptr && std::atoi(e) == 0); }();
+
 // The same with 512-bit registers: 64 characters (two words) per step.  Bits 1 and 2 of every byte come out as two
 // 64-bit masks (vptestmb), comp - 1 = (b2, b1 ^ b2), and pdep interleaves the two masks into the 2-bit codes; validity
 // is one byte shuffle (low nibble -> the only upper-cased letter with that nibble) and one compare into a mask.
@@ -111,8 +116,10 @@ inline void pack64(const uint8_t* p, u64* out, __mmask64& all_valid)
   const u64 b1 = _mm512_test_epi8_mask(v, _mm512_set1_epi8(0x02)), b2 = _mm512_test_epi8_mask(v, _mm512_set1_epi8(0x04));
   const u64 lo = b1 ^ b2, hi = b2;
   const u64 EVEN = 0x5555555555555555ull, ODD = 0xAAAAAAAAAAAAAAAAull;
-  _mm_stream_si64((long long*)out, (long long)(_pdep_u64(lo & 0xFFFFFFFFull, EVEN) | _pdep_u64(hi & 0xFFFFFFFFull, ODD)));
-  _mm_stream_si64((long long*)(out + 1), (long long)(_pdep_u64(lo >> 32, EVEN) | _pdep_u64(hi >> 32, ODD)));
+  const u64 w0 = _pdep_u64(lo & 0xFFFFFFFFull, EVEN) | _pdep_u64(hi & 0xFFFFFFFFull, ODD);
+  const u64 w1 = _pdep_u64(lo >> 32, EVEN) | _pdep_u64(hi >> 32, ODD);
+  if(g_stream_stores) { _mm_stream_si64((long long*)out, (long long)w0); _mm_stream_si64((long long*)(out + 1), (long long)w1); }
+  else { out[0] = w0; out[1] = w1; }
 }
 
 // Patterns whose length is a multiple of 32: the batch is one stream of 32-character words.
