@@ -189,6 +189,14 @@ struct gcsa_b200_index
   u8 pack_code[256];
   bool pack_default = false;
 
+  // Automatic choice between packing and raw copies in the host entry point of find() (GCSA_B200_HOST_PACK unset):
+  // seconds per query of the recent large batches either way.  Packing moves fewer bytes over the link but more through
+  // host memory (32 B read + 8 written + 8 read + 16 written per 32-mer against 32 + 16 raw), so it wins while the link
+  // is the bottleneck and loses when several GPUs share one host's memory system; which one it is shows in the clock.
+  mutable std::mutex policy_mutex;
+  mutable double policy_seconds[2] = { 0.0, 0.0 };     // [0] raw only, [1] packing shares the batch; 0 = not measured yet
+  mutable u64 policy_calls = 0;
+
   // Resources of the host-buffer entry points (streams, events, device chunk buffers, pinned staging): created on
   // first use, kept for the life of the handle and handed from call to call, one set per concurrent caller.
   mutable std::mutex pool_mutex;
@@ -915,7 +923,25 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
 
   const int pack_threads = (pack_threads_override >= 0 ? pack_threads_override : hostPackThreads());
   // (below three chunks of 128 k queries there is nothing to share)
-  const bool pack = (pack_threads > 0 && fixed_length > 0 && offsets == nullptr && stats == nullptr && n > (2u << 17));
+  bool pack = (pack_threads > 0 && fixed_length > 0 && offsets == nullptr && stats == nullptr && n > (2u << 17));
+  // No explicit policy: both ways are tried on the first large batches, then the faster one is used, and the other one
+  // is tried again every 32nd batch (the load on the host changes).
+  const char* policy_env = std::getenv("GCSA_B200_HOST_PACK");
+  const bool auto_policy = pack && (policy_env == nullptr || *policy_env == 0 || std::strcmp(policy_env, "auto") == 0);
+  if(auto_policy)
+  {
+    std::lock_guard<std::mutex> lock(index->policy_mutex);
+    u64 call = index->policy_calls++;
+    if(index->policy_seconds[1] == 0.0) { pack = true; }
+    else if(index->policy_seconds[0] == 0.0) { pack = false; }
+    else
+    {
+      bool best = (index->policy_seconds[1] <= index->policy_seconds[0]);
+      pack = (call % 32 == 31 ? !best : best);
+    }
+  }
+  const double policy_t0 = omp_get_wtime();
+  const bool policy_packed = pack;
   // Chunks of >= 128 k queries (4 MB of 32-mers: the link is at its streaming rate), at most ~24 per batch (48 when
   // packing shares it): the H2D engine is the busy resource from the first byte on, so what the pipeline adds to
   // the transfer time is the kernel and the D2H of the LAST chunk -- the smaller the chunks, the smaller that tail.
@@ -1109,6 +1135,14 @@ static int findHost(const gcsa_b200_index* index, const uint8_t* chars, const ui
   if(d_stats) { cudaFree(d_stats); }
   if(rc) { return rc; }
   if(err != cudaSuccess) { return fail(GCSA_B200_ERR_CUDA, std::string("find_host: ") + cudaGetErrorString(err)); }
+  if(auto_policy)
+  {
+    // seconds per query of this batch; a moving average over the batches sent the same way
+    double per_query = (omp_get_wtime() - policy_t0) / (double)n;
+    std::lock_guard<std::mutex> lock(index->policy_mutex);
+    double& slot = index->policy_seconds[policy_packed ? 1 : 0];
+    slot = (slot == 0.0 ? per_query : 0.75 * slot + 0.25 * per_query);
+  }
   return 0;
 }
 

@@ -81,7 +81,8 @@ def test_bench_line_on_the_emulated_engine(monkeypatch, capsys):
     assert line["found"] == line["queries"] == 1_100_000
     assert line["config"]["index"]["fused_table"] is True
     pack = line["e2e"]["host_pack"]
-    assert line["e2e"]["matches_device_leg"] and pack["policy"] == "auto" and pack["chunks"] == 9 and 0 <= pack["packed_chunks"] <= 7
+    assert line["e2e"]["matches_device_leg"] and pack["policy"] == "auto"
+    assert (pack["chunks"] == 9 and 0 <= pack["packed_chunks"] <= 7) or (pack["chunks"] == 5 and pack["packed_chunks"] == 0)   # shared, or raw only
     assert 8 * 1_100_000 <= line["e2e"]["h2d_bytes_per_step"] <= 32 * 1_100_000
     assert line["cpu_baseline"]["parity_on_sample"] and line["cpu_baseline"]["kind"] in ("reference", "port")
     assert line["secondary"]["parity_on_sample"] and line["secondary"]["found"] < 1_100_000 // 2

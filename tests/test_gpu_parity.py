@@ -337,10 +337,10 @@ def test_host_packed_find_equals_byte_path(monkeypatch):
 
 
 def test_host_pack_shares_the_batch_with_the_raw_path(monkeypatch):
-    """The host entry point of find() with packing enabled (the default): a helper thread sends raw chunks from the
-    front of the batch while the caller packs chunks from the back; which chunk goes which way depends on timing, the
-    answers do not -- equal to the unpacked path for every setting, with a chunk that cannot be packed (an N) in the
-    batch, and the share of packed chunks is reported."""
+    """The host entry point of find() with packing enabled: the caller sends raw chunks from the front of the batch while
+    the rest of its OpenMP team packs chunks from the back; which chunk goes which way depends on timing, the answers do
+    not -- equal to the unpacked path for every setting, with a chunk that cannot be packed (an N) in the batch; the share
+    of packed chunks is reported, and without an explicit setting both ways are tried before one is chosen."""
     import ctypes
     from gcsa2_b200 import capi
     L = capi.lib()
@@ -367,11 +367,19 @@ def test_host_pack_shares_the_batch_with_the_raw_path(monkeypatch):
             monkeypatch.setenv("GCSA_B200_HOST_PACK", setting)
         if threads is not None:
             monkeypatch.setenv("GCSA_B200_HOST_PACK_THREADS", threads)
-        for _ in range(2):
+        ways = set()
+        for _ in range(3):
             sp, ep = gpu.find_fixed_batch(chars, length)
             assert (sp == bsp).all() and (ep == bep).all(), (setting, threads)
             L.gcsa_b200_internal_pack_share(ctypes.byref(packed), ctypes.byref(total))
-            assert total.value == 10 and packed.value <= total.value - 2          # the raw path always keeps the reserve
+            if setting in ("auto", None) and total.value == 5:        # the automatic policy tries raw copies only as well
+                assert packed.value == 0
+                ways.add("raw")
+            else:
+                assert total.value == 10 and packed.value <= total.value - 2      # the copy engine is fed raw chunks first
+                ways.add("shared")
+        if setting == "auto":
+            assert ways == {"raw", "shared"}                          # both ways measured before one is chosen
     small = gpu.find_fixed_batch(chars[: 1000 * length], length)      # too small for the two-thread pipeline
     assert (small[0] == bsp[:1000]).all()
 
