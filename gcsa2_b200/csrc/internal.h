@@ -23,6 +23,12 @@ int gcsa_b200_internal_pack_patterns(const uint8_t* chars, uint64_t n, uint64_t 
 int gcsa_b200_internal_pack_range(const uint8_t* chars, uint64_t first, uint64_t last, uint64_t length, const uint8_t* code,
                                   int default_alphabet, uint64_t* out);
 
+/* Measurement hooks of engine.cu (bench.py and the tests read them; not part of the C ABI): the number of batches of
+   this process that took the two-kernel k-mer form of find(), and how many chunks of the last host-buffer find() went
+   over the link packed / in all. */
+unsigned long long gcsa_b200_internal_fast_launches(void);
+void gcsa_b200_internal_pack_share(unsigned long long* packed, unsigned long long* total);
+
 #ifdef __cplusplus
 }
 #endif
