@@ -325,8 +325,9 @@ find_kernel(const DevView v, const u8* __restrict__ chars, const u64* __restrict
 }
 
 /*
-  The first kernel of the two-kernel form of find() for batches of k-mers (one fixed length L, table_k <= L <= 32,
-  default alphabet, a k-mer table): ONE QUERY PER THREAD, no loop.  A thread reads its pattern (consecutive threads,
+  The first kernel of the two-kernel form of find() for batches of k-mers (one fixed length L >= table_k, default
+  alphabet, a k-mer table): ONE QUERY PER THREAD, no loop.  It works on the last 32 characters of a pattern; a longer
+  pattern is continued by the general kernel from where the table and the first jump left it.  A thread reads its pattern (consecutive threads,
   consecutive patterns: the loads coalesce), packs it to 2 bits per character, looks the last table_k characters up in
   the k-mer table and, if the result is one path node and characters remain, takes one jump (fused with the table
   entry, or one more load).  That finishes most k-mers of a large reference (a 32-mer over a 16-mer table: table
@@ -370,10 +371,14 @@ find_fast_kernel(const DevView v, const u8* __restrict__ chars, u32 L, u64 n, u6
       {
         if(PACKED)
         {
-          u64 x = __ldcs((const unsigned long long*)chars + q);
+          // the last min(L, 32) characters of the pattern's words (they straddle two words when L > 32 is not a multiple of 32)
+          const u32 m = (L < 32 ? L : 32), r0 = L - m, sh = (r0 & 31) * 2;
+          const unsigned long long* words = (const unsigned long long*)chars + q * (u64)((L + 31) >> 5) + (r0 >> 5);
+          u64 x = __ldcs(words) >> sh;
+          if(sh != 0 && (r0 & 31) + m > 32) { x |= __ldcs(words + 1) << (64 - sh); }
           u64 t = __brevll(x);
           t = ((t >> 1) & 0x5555555555555555ull) | ((t & 0x5555555555555555ull) << 1);
-          tail[j] = (L < 32 ? t >> (2 * (32 - L)) : t);
+          tail[j] = (m < 32 ? t >> (2 * (32 - m)) : t);
         }
         else
         {
@@ -396,7 +401,7 @@ find_fast_kernel(const DevView v, const u8* __restrict__ chars, u32 L, u64 n, u6
             tail[j] = p3 | (p2 << 16) | (p1 << 32) | (p0 << 48);
             // how many characters, counted from the last one, are bases
             u32 good = (g3 < 8 ? g3 : 8 + (g2 < 8 ? g2 : 8 + (g1 < 8 ? g1 : 8 + g0)));
-            if(good < L) { entry[j] = q | WORK_FRESH; }
+            if(good < (L < 32 ? L : 32)) { entry[j] = q | WORK_FRESH; }       // (characters further to the left are looked at by whoever gets there)
           }
         }
       }

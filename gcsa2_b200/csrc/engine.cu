@@ -781,11 +781,11 @@ static int launchFind(const gcsa_b200_index* index, const u8* d_chars, const u64
   int grid = gridFor(n, index->sm_count, per_sm);
   // idle lanes of a warp are refilled together once this many are idle (16 measured best: DESIGN.md)
   static const int refill_at = []() { const char* e = std::getenv("GCSA_B200_FIND_REFILL"); int r = (e ? std::atoi(e) : 16); return std::min(32, std::max(1, r)); }();
-  // Batches of k-mers (one length between the k-mer table's and 32, the default alphabet): the two-kernel form -- one
+  // Batches of k-mers (one length, at least the k-mer table's, the default alphabet): the two-kernel form -- one
   // probe (or two) per thread for everything, then the general kernel for the work list of what that left unfinished.
   static const bool fast_off = []() { const char* e = std::getenv("GCSA_B200_FIND_FAST"); return (e != nullptr && std::atoi(e) == 0); }();
   const DevView& v = index->view;
-  if(!fast_off && d_offsets == nullptr && fixed_length <= 32 && v.table_k > 0 && fixed_length >= (u64)v.table_k &&
+  if(!fast_off && d_offsets == nullptr && fixed_length <= 255 && v.table_k > 0 && fixed_length >= (u64)v.table_k &&
      (packed || v.default_alphabet != 0) && n >= 4096 && n < (1ull << 47))
   {
     // work list of the general kernel (8 bytes per entry), work list of the quad kernel (16), the two counters

@@ -639,7 +639,7 @@ def test_kmer_batches_two_kernel_form(monkeypatch):
              ("snp", build_index(graph, 16, 3)[0], lambda n, L, s: synth.patterns_from_snp_graph(seq, sites, alt, n, L, seed=s)))
     for name, flat, sampler in cases:
         ora = orc.OracleGCSA(flat)
-        for L in (8, 11, 24, 31, 32):
+        for L in (8, 11, 24, 31, 32, 33, 47, 64, 100):
             n = 6000
             c, o = sampler(n, L, 200 + L)
             c = c.copy()
