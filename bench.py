@@ -425,6 +425,17 @@ def mem_leg(args, rank, world, local, barrier, dist, torch, fixture):
     return out
 
 
+def cfg4_traffic(args, queries):
+    """Recorded DRAM bytes of the find() kernels on the 3 Gbp index (ncu --set full of a 10 M query launch, per query),
+    scaled to `queries`; None for any other configuration."""
+    path = os.path.join(ROOT, "profiles", "traffic_find_cfg2.json")
+    if args.cfg4_mbp != 3000.0 or args.kmer_table_k != 16 or not os.path.exists(path):
+        return None
+    with open(path) as f:
+        entry = json.load(f).get("cfg4_3gbp")
+    return float(entry["dram_bytes_per_launch"]) / float(entry["queries_per_launch"]) * queries if entry else None
+
+
 def cfg4_leg(args, rank, world, local, barrier, dist, torch):
     """BASELINE.json configs[3]: 1 B 32-mers on a 3 Gbp linear-path order-128 index, the batch sharded across the
     GPUs, the index replicated -- STRONG scaling: the job is the same 1 B queries for every N.  Nothing of it touches
@@ -502,7 +513,8 @@ def cfg4_leg(args, rank, world, local, barrier, dist, torch):
         secs = ms_pass / 1000.0
         rank0_queries = sum(min(chunk, total - c * chunk) for c in mine)
         out["roofline"] = {"bound": "hbm", "achieved": per_query * rank0_queries / secs / 1e9, "peak": peak, "unit": "GB/s",
-                           "frac": per_query * rank0_queries / secs / 1e9 / peak, "traffic": None, "kernel": "find_fast_kernel<false,false,4> (+ find_quad_kernel, find_kernel<false,4,false,true> for the work lists)",
+                           "frac": per_query * rank0_queries / secs / 1e9 / peak, "traffic": cfg4_traffic(args, rank0_queries),
+                           "dram_frac": (cfg4_traffic(args, rank0_queries) / secs / 1e9 / peak if cfg4_traffic(args, rank0_queries) else None), "kernel": "find_fast_kernel<false,false,4> (+ find_quad_kernel, find_kernel<false,4,false,true> for the work lists)",
                            "peak_source": peak_src, "probes_per_query": (st["sector_probes"] + st["table_hits"]) / k,
                            "probe_ceiling": PROBE_CEILING, "probe_ceiling_source": PROBE_CEILING_SOURCE,
                            "probe_rate": (st["sector_probes"] + st["table_hits"]) / k * rank0_queries / secs,

@@ -1,5 +1,5 @@
-"""Builds gcsa2_b200/libgcsa2_b200.so in-tree: nvcc for sm_100a (the CUDA translation units; engine.cu includes its
-kernels from csrc/device/*.cuh) + g++ (the host-only sources).
+"""Builds gcsa2_b200/libgcsa2_b200.so in-tree: nvcc for sm_100a (the CUDA translation units; each includes the kernels
+it launches from csrc/device/*.cuh) + g++ (the host-only sources).
 
 The shared library is self-contained (static cudart), so it travels to the GPU box with the
 snapshot and loads on a CPU-only machine too (symbol checks in the CPU test-suite)."""
@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgcsa2_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include", "gcsa2_b200.h")
-DEVICE_SOURCES = ["engine.cu", "linear_builder.cu"]                          # CUDA translation units (nvcc, sm_100a)
+DEVICE_SOURCES = ["engine.cu", "find.cu", "ops.cu", "locate.cu", "lcp.cu", "kmers.cu", "linear_builder.cu"]   # CUDA translation units (nvcc, sm_100a)
 HOST_SOURCES = ["builder.cpp", "gcsa_file.cpp", "kmer_file.cpp", "verify.cpp", "pack.cpp"]      # host-side C++ (g++)
 
 NVCC = os.environ.get("GCSA_B200_NVCC", "nvcc")
@@ -33,14 +33,16 @@ def build(force=False, verbose=False):
     device_o = [src[:-3] + ".o" for src in device_cu]
     host_o = [src[:-4] + ".o" for src in host_cpp]
     headers = [os.path.join(CSRC, "device", f) for f in sorted(os.listdir(os.path.join(CSRC, "device"))) if f.endswith(".cuh")]
-    headers += [INCLUDE, os.path.join(CSRC, "internal.h")]
+    headers += [INCLUDE, os.path.join(CSRC, "internal.h"), os.path.join(CSRC, "engine.h")]
     if not force and not _stale(LIB, device_cu + headers + host_cpp):
         return LIB
     run = lambda cmd: subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL)
-    # only what changed is recompiled (engine.cu takes a minute)
-    for src, obj in zip(device_cu, device_o):
-        if force or _stale(obj, [src] + headers):
-            run([NVCC] + NVCC_FLAGS + ["-c", src, "-o", obj])
+    # only what changed is recompiled, the translation units side by side
+    jobs = [subprocess.Popen([NVCC] + NVCC_FLAGS + ["-c", src, "-o", obj], stdout=None if verbose else subprocess.DEVNULL)
+            for src, obj in zip(device_cu, device_o) if force or _stale(obj, [src] + headers)]
+    failed = [job.args for job in jobs if job.wait() != 0]
+    if failed:
+        raise subprocess.CalledProcessError(1, failed[0])
     for src, obj in zip(host_cpp, host_o):
         if force or _stale(obj, [src] + headers):
             run([CXX] + CXX_FLAGS + ["-c", src, "-o", obj])

@@ -1,5 +1,5 @@
-/* device/find.cuh -- find(): the batched backward-search kernel and the construction of the k-mer table.
-   Part of the single translation unit engine.cu (included there in order); sm_100a only. */
+/* device/find.cuh -- find(): the batched backward-search kernels.
+   Included by find.cu only (its kernels must be defined in one translation unit); sm_100a only. */
 #ifndef GCSA2_B200_DEVICE_FIND_CUH
 #define GCSA2_B200_DEVICE_FIND_CUH
 
@@ -7,45 +7,7 @@
 // Kernels: find
 //------------------------------------------------------------------------------
 
-// Pattern bytes are read through an 8-byte window (one aligned streaming load per 8 characters,
-// evict-first: the pattern stream must not push index lines out of the L2).
-struct CharWindow
-{
-  u64 word; u64 index;
-  __device__ __forceinline__ CharWindow() : word(0), index(~0ull) {}
-  __device__ __forceinline__ u32 get(const u8* chars, u64 pos)
-  {
-    u64 addr = (u64)(chars + pos);
-    u64 wi = addr >> 3;
-    if(wi != index) { word = __ldcs((const unsigned long long*)(wi << 3)); index = wi; }
-    return (u32)((word >> ((addr & 7) * 8)) & 0xFF);
-  }
-};
-
-
-
 struct FindStatsDev { u64 found, total_length, lf_steps, sector_probes, table_hits; };
-
-// Eight pattern bytes of the default alphabet (w: lowest address in the low byte) -> their comp - 1 codes,
-// 2 bits each, the LAST byte in the lowest bits.  *good = how many bytes, counted from the last one, are bases
-// in either case (8 if all); the codes of the others are garbage.
-__device__ __forceinline__ u32 pack8_reversed(u64 w, u32* good)
-{
-  const u64 L7 = 0x7F7F7F7F7F7F7F7Full, H8 = 0x8080808080808080ull;
-  u64 x = w & 0xDFDFDFDFDFDFDFDFull;
-  u64 zA = x ^ 0x4141414141414141ull, zC = x ^ 0x4343434343434343ull, zG = x ^ 0x4747474747474747ull, zT = x ^ 0x5454545454545454ull;
-  // 0x80 in every byte that equals one of the four letters (exact zero-byte test, no carries between bytes)
-  u64 valid = ~(((zA & L7) + L7) | zA | L7) | ~(((zC & L7) + L7) | zC | L7) | ~(((zG & L7) + L7) | zG | L7) | ~(((zT & L7) + L7) | zT | L7);
-  u64 inv = ~valid & H8;
-  *good = (inv == 0 ? 8u : 7u - (u32)((63 - __clzll((long long)inv)) >> 3));
-  u64 t = (w >> 1) & 0x0303030303030303ull;                      // A 0, C 1, T 2, G 3
-  u64 code = t ^ ((t >> 1) & 0x0101010101010101ull);               // A 0, C 1, G 2, T 3
-  u64 y = (code | (code >> 6)) & 0x000F000F000F000Full;
-  y = (y | (y >> 12)) & 0x000000FF000000FFull;
-  y = (y | (y >> 24)) & 0xFFFFull;
-  u32 r = __brev((u32)y) >> 16;                                    // reverse the order of the characters ...
-  return ((r >> 1) & 0x5555u) | ((r & 0x5555u) << 1);              // ... not of the two bits of each
-}
 
 /*
   GCSA::find(begin, end), include/gcsa/gcsa.h:96-110.  One query per lane.  Queries are pulled from a
@@ -601,61 +563,6 @@ find_quad_kernel(const DevView v, u32 L, const ulonglong2* __restrict__ quad_wor
   {
     atomicAdd((ull*)&stats->found, (ull)st_found); atomicAdd((ull*)&stats->total_length, (ull)st_len);
     atomicAdd((ull*)&stats->lf_steps, (ull)st_steps); atomicAdd((ull*)&stats->sector_probes, (ull)st_sectors);
-  }
-}
-
-/*
-  k-mer table.  Entry idx describes the string whose t-th character from the END is comp
-  ((idx >> 2t) & 3) + 1 and holds exactly what find() returns for it, early exit included: an
-  empty result keeps the uncanonicalised pair of the step where the search died, and such a pair
-  always has ep = sp - 1 (rank is monotone), so (sp, length) loses nothing.
-  The table is grown one character at a time: level j+1 is one LF step away from level j.
-*/
-__global__ void __launch_bounds__(256)
-table_init_kernel(const DevView v, ulonglong2* tmp)
-{
-  u32 idx = threadIdx.x;
-  if(idx < 4) { tmp[idx] = make_ulonglong2(v.char_sp[idx + 1], v.char_ep[idx + 1]); }
-}
-
-// level j (4^j entries in tmp[0, 4^j)) -> level j + 1 in place: slot idx | c << 2j
-__global__ void __launch_bounds__(256)
-table_extend_kernel(const DevView v, int j, ulonglong2* tmp)
-{
-  u64 total = 1ull << (2 * j);
-  for(u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x)
-  {
-    ulonglong2 r = tmp[idx];
-    #pragma unroll
-    for(u32 c = 4; c-- > 0; )
-    {
-      u64 sp = r.x, ep = r.y;
-      if(!range_empty(sp, ep)) { lf_range(v, sp, ep, c + 1, sp, ep); }
-      tmp[idx | ((u64)c << (2 * j))] = make_ulonglong2(sp, ep);
-    }
-  }
-}
-
-// last level: level k - 1 in tmp -> packed level k in table (k >= 2); for k == 1 pack tmp itself
-// With table2 != nullptr the fused form is written instead: next to each entry the jump-table entry of its sp when the
-// result is a single path node (find_kernel then takes the first jump without another probe).
-__global__ void __launch_bounds__(256)
-table_final_kernel(const DevView v, int k, const ulonglong2* tmp, u64* table, ulonglong2* table2)
-{
-  u64 total = (k == 1 ? 4 : 1ull << (2 * (k - 1)));
-  for(u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x)
-  {
-    ulonglong2 r = tmp[idx];
-    for(u32 c = 0; c < (k == 1 ? 1u : 4u); c++)
-    {
-      u64 sp = r.x, ep = r.y;
-      if(k > 1 && !range_empty(sp, ep)) { lf_range(v, sp, ep, c + 1, sp, ep); }
-      u64 len = ep + 1 - sp;
-      u64 entry = (len >= TABLE_ESCAPE || sp > M40) ? (TABLE_ESCAPE << 40) : (sp | (len << 40));
-      u64 slot = (k == 1 ? idx : (idx | ((u64)c << (2 * (k - 1)))));
-      if(table2 == nullptr) { table[slot] = entry; }
-      else { table2[slot] = make_ulonglong2(entry, (len == 1 && v.jump != nullptr) ? __ldg(v.jump + sp) : 0ull); }
-    }
   }
 }
 

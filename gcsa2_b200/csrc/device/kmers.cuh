@@ -1,5 +1,5 @@
 /* device/kmers.cuh -- countKMers / compareKMers as breadth-first frontier expansion.
-   Part of the single translation unit engine.cu (included there in order); sm_100a only. */
+   Included by kmers.cu only; sm_100a only. */
 #ifndef GCSA2_B200_DEVICE_KMERS_CUH
 #define GCSA2_B200_DEVICE_KMERS_CUH
 

@@ -1,5 +1,5 @@
 /* device/layout.cuh -- device views of the index (DevView, LcpView) and the rank / select / LF primitives over the fused sectors.
-   Part of the single translation unit engine.cu (included there in order); sm_100a only. */
+   Included by every CUDA translation unit of the engine (device functions only, no kernels); sm_100a only. */
 #ifndef GCSA2_B200_DEVICE_LAYOUT_CUH
 #define GCSA2_B200_DEVICE_LAYOUT_CUH
 
@@ -274,6 +274,61 @@ __device__ __forceinline__ bool bwt_bit(const DevView& v, u64 i, u32 c)
   int slot = sparse_slot(c);
   u64 r = sparse_rank(v.sparse_pos[slot], v.sparse_n[slot], i);
   return (r < v.sparse_n[slot] && v.sparse_pos[slot][r] == i);
+}
+
+//------------------------------------------------------------------------------
+// Shared by several translation units: the single-node step and the packing of pattern characters
+//------------------------------------------------------------------------------
+
+// predecessor of node i by fast character c (0-based) from its fused sector, or false
+__device__ __forceinline__ bool pred_fast(const DevView& v, u64 i, u32 c, u64& pred)
+{
+  u64 b = i / BWT_W; u32 off = (u32)(i - b * BWT_W);
+  ulonglong4 q = ld256(v.bwt + b * 4 + c);
+  bool bit = (off < 64 ? (q.y >> off) & 1 : ((q.x >> 40) >> (off - 64)) & 1);
+  if(!bit) { return false; }
+  u32 j = popc_low88(q.y, (u32)(q.x >> 40), off);
+  pred = (q.z & M40) + popc_low88(q.w, (u32)(q.z >> 40), j + 1);
+  return true;
+}
+
+// Pattern bytes are read through an 8-byte window (one aligned streaming load per 8 characters,
+// evict-first: the pattern stream must not push index lines out of the L2).
+struct CharWindow
+{
+  u64 word; u64 index;
+  __device__ __forceinline__ CharWindow() : word(0), index(~0ull) {}
+  __device__ __forceinline__ u32 get(const u8* chars, u64 pos)
+  {
+    u64 addr = (u64)(chars + pos);
+    u64 wi = addr >> 3;
+    if(wi != index) { word = __ldcs((const unsigned long long*)(wi << 3)); index = wi; }
+    return (u32)((word >> ((addr & 7) * 8)) & 0xFF);
+  }
+};
+
+
+
+
+// Eight pattern bytes of the default alphabet (w: lowest address in the low byte) -> their comp - 1 codes,
+// 2 bits each, the LAST byte in the lowest bits.  *good = how many bytes, counted from the last one, are bases
+// in either case (8 if all); the codes of the others are garbage.
+__device__ __forceinline__ u32 pack8_reversed(u64 w, u32* good)
+{
+  const u64 L7 = 0x7F7F7F7F7F7F7F7Full, H8 = 0x8080808080808080ull;
+  u64 x = w & 0xDFDFDFDFDFDFDFDFull;
+  u64 zA = x ^ 0x4141414141414141ull, zC = x ^ 0x4343434343434343ull, zG = x ^ 0x4747474747474747ull, zT = x ^ 0x5454545454545454ull;
+  // 0x80 in every byte that equals one of the four letters (exact zero-byte test, no carries between bytes)
+  u64 valid = ~(((zA & L7) + L7) | zA | L7) | ~(((zC & L7) + L7) | zC | L7) | ~(((zG & L7) + L7) | zG | L7) | ~(((zT & L7) + L7) | zT | L7);
+  u64 inv = ~valid & H8;
+  *good = (inv == 0 ? 8u : 7u - (u32)((63 - __clzll((long long)inv)) >> 3));
+  u64 t = (w >> 1) & 0x0303030303030303ull;                      // A 0, C 1, T 2, G 3
+  u64 code = t ^ ((t >> 1) & 0x0101010101010101ull);               // A 0, C 1, G 2, T 3
+  u64 y = (code | (code >> 6)) & 0x000F000F000F000Full;
+  y = (y | (y >> 12)) & 0x000000FF000000FFull;
+  y = (y | (y >> 24)) & 0xFFFFull;
+  u32 r = __brev((u32)y) >> 16;                                    // reverse the order of the characters ...
+  return ((r >> 1) & 0x5555u) | ((r & 0x5555u) << 1);              // ... not of the two bits of each
 }
 
 #endif

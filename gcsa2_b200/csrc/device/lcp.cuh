@@ -1,5 +1,5 @@
 /* device/lcp.cuh -- LCPArray: parent, depth, psv / nsv / rmq over the k-ary minimum tree.
-   Part of the single translation unit engine.cu (included there in order); sm_100a only. */
+   Included by lcp.cu only; sm_100a only. */
 #ifndef GCSA2_B200_DEVICE_LCP_CUH
 #define GCSA2_B200_DEVICE_LCP_CUH
 

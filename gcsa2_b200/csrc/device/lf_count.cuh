@@ -1,5 +1,5 @@
 /* device/lf_count.cuh -- LF(range, c), LF(node), LF_fast / LF_all and count() kernels.
-   Part of the single translation unit engine.cu (included there in order); sm_100a only. */
+   Included by ops.cu only; sm_100a only. */
 #ifndef GCSA2_B200_DEVICE_LF_COUNT_CUH
 #define GCSA2_B200_DEVICE_LF_COUNT_CUH
 

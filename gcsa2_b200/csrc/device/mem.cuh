@@ -1,5 +1,5 @@
 /* device/mem.cuh -- MEM-style scan (LF + parent), BASELINE.json configs[4].
-   Part of the single translation unit engine.cu (included there in order); sm_100a only. */
+   Included by lcp.cu only; sm_100a only. */
 #ifndef GCSA2_B200_DEVICE_MEM_CUH
 #define GCSA2_B200_DEVICE_MEM_CUH
 

@@ -1,5 +1,5 @@
 /* device/two_step.cuh -- construction of the two-step blocks (pairs of characters per probe) from the one-step blocks.
-   Part of the single translation unit engine.cu (included there in order); sm_100a only. */
+   Included by engine.cu only (construction kernels); sm_100a only. */
 #ifndef GCSA2_B200_DEVICE_TWO_STEP_CUH
 #define GCSA2_B200_DEVICE_TWO_STEP_CUH
 
@@ -7,17 +7,6 @@
 // Kernels: construction of the two-step blocks from the one-step blocks
 //------------------------------------------------------------------------------
 
-// predecessor of node i by fast character c (0-based) from its fused sector, or false
-__device__ __forceinline__ bool pred_fast(const DevView& v, u64 i, u32 c, u64& pred)
-{
-  u64 b = i / BWT_W; u32 off = (u32)(i - b * BWT_W);
-  ulonglong4 q = ld256(v.bwt + b * 4 + c);
-  bool bit = (off < 64 ? (q.y >> off) & 1 : ((q.x >> 40) >> (off - 64)) & 1);
-  if(!bit) { return false; }
-  u32 j = popc_low88(q.y, (u32)(q.x >> 40), off);
-  pred = (q.z & M40) + popc_low88(q.w, (u32)(q.z >> 40), j + 1);
-  return true;
-}
 
 // 16-bit mask per node: bit c1 * 4 + c2 set iff the 2-path (c1, c2) into the node exists;
 // per block and label the number of set bits.

@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "gcsa2_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libgcsa2_b200_emu.so")
-DEVICE_SOURCES = ["engine.cu", "linear_builder.cu"]       # the first one carries the emulation's out-of-line definitions
+DEVICE_SOURCES = ["engine.cu", "find.cu", "ops.cu", "locate.cu", "lcp.cu", "kmers.cu", "linear_builder.cu"]   # the first one carries the emulation's out-of-line definitions
 HOST_SOURCES = ["builder.cpp", "gcsa_file.cpp", "kmer_file.cpp", "verify.cpp", "pack.cpp"]
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 COLLECTIVES = ("__ballot_sync", "__any_sync", "__all_sync", "__syncwarp", "__syncthreads", "__shfl_sync",
@@ -61,10 +61,12 @@ def _functions(text, qualifier):
 
 
 def inline_device_headers(text):
-    """engine.cu is one translation unit that includes its kernels from csrc/device/*.cuh: paste them in."""
+    """A translation unit includes engine.h and the kernels it launches from csrc/device/*.cuh: paste them in (engine.h
+    first, it includes device/layout.cuh itself)."""
     def paste(m):
         with open(os.path.join(CSRC, m.group(1))) as f:
             return "// ---- %s ----\n%s" % (m.group(1), f.read())
+    text = re.sub(r'#include "(engine\.h)"', paste, text)
     return re.sub(r'#include "(device/[a-z_]+\.cuh)"', paste, text)
 
 
@@ -76,7 +78,7 @@ def translate(text, main=True):
     text = text.replace("#include <cuda_runtime.h>", '#include "cuda_emu.h"')
     text = text.replace("#include <cub/cub.cuh>", "")
     text, n_asm = re.subn(r'asm volatile\("ld\.global\.nc\.v4\.u64[^;]*;[^;]*;', "emu::checkAligned(p, 32); r = *p;", text)
-    assert n_asm == (1 if main else 0), "expected exactly one inline-PTX load (in engine.cu), found %d" % n_asm
+    assert n_asm <= 1, "expected at most one inline-PTX load (ld256 of device/layout.cuh), found %d" % n_asm
     assert "asm" not in re.sub(r"//.*", "", text), "untranslated inline assembly"
 
     # which functions use collectives, directly or through a device function they name
@@ -118,7 +120,7 @@ def build(force=False, verbose=False):
     os.makedirs(OUT, exist_ok=True)
     device_cu = [os.path.join(CSRC, s) for s in DEVICE_SOURCES]
     device = [os.path.join(CSRC, "device", f) for f in sorted(os.listdir(os.path.join(CSRC, "device"))) if f.endswith(".cuh")]
-    sources = device_cu + [os.path.join(CSRC, "internal.h"), os.path.join(HERE, "cuda_emu.h"), os.path.abspath(__file__),
+    sources = device_cu + [os.path.join(CSRC, "internal.h"), os.path.join(CSRC, "engine.h"), os.path.join(HERE, "cuda_emu.h"), os.path.abspath(__file__),
                os.path.join(ROOT, "include", "gcsa2_b200.h")] + device + [os.path.join(CSRC, s) for s in HOST_SOURCES]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in sources):
         return LIB
@@ -129,8 +131,8 @@ def build(force=False, verbose=False):
         stem = os.path.basename(source)[:-3]
         obj = os.path.join(OUT, stem + "_emu.o")
         objs.append(obj)
-        deps = [source, os.path.join(CSRC, "internal.h"), os.path.join(HERE, "cuda_emu.h"), os.path.abspath(__file__),
-                os.path.join(ROOT, "include", "gcsa2_b200.h")] + (device if i == 0 else [])
+        deps = [source, os.path.join(CSRC, "internal.h"), os.path.join(CSRC, "engine.h"), os.path.join(HERE, "cuda_emu.h"), os.path.abspath(__file__),
+                os.path.join(ROOT, "include", "gcsa2_b200.h")] + device
         if not force and os.path.exists(obj) and all(os.path.getmtime(s) <= os.path.getmtime(obj) for s in deps):
             continue
         with open(source) as f:
