@@ -28,7 +28,7 @@ def main():
     ap.add_argument("--kmer-table-k", type=int, default=14)
     ap.add_argument("--out", default="")
     ap.add_argument("--ops", default="count,locate,parent,mem,kmers,compare,verify",
-                    help="comma-separated subset of: count,locate,parent,mem,kmers,compare,verify (find always runs)")
+                    help="comma-separated subset of: count,locate,locate_short,parent,mem,kmers,compare,verify (find always runs)")
     args = ap.parse_args()
 
     import torch
@@ -114,6 +114,29 @@ def main():
       report("locate (sorted distinct positions per range)", "positions/s", got[0], ms, k / secs, ml,
              (offs[:ml + 1] == ooffs).all() and (vals[:k] == ovals).all() and got[0] == total,
              {"positions": got[0], "ranges": n})
+
+    # ---- locate() of short patterns: wide ranges, the general pipeline (segmented sort) instead of the short-range path ----
+    if "locate_short" in ops:
+      for plen, nq in ((12, 2_000_000), (10, 1_000_000), (8, 200_000)):
+          pchars, poffsets = synth.patterns_from_snp_graph(seq, sites, alt, nq, plen, seed=600 + plen)
+          psp, pep = index.find_batch(pchars, poffsets)
+          d_psp = torch.from_numpy(psp.view(np.int64)).cuda(); d_pep = torch.from_numpy(pep.view(np.int64)).cuda()
+          d_pcnt = torch.empty(nq, dtype=torch.int64, device="cuda")
+          index.count_device(d_psp, d_pep, nq, d_pcnt, stream.cuda_stream); torch.cuda.synchronize()
+          ptotal = int(d_pcnt.sum().item())
+          d_poffs = torch.empty(nq + 1, dtype=torch.int64, device="cuda")
+          d_pvals = torch.empty(ptotal + 16, dtype=torch.int64, device="cuda")
+          pgot = [0]
+          def do_locate_short():
+              pgot[0] = index.locate_device(d_psp, d_pep, nq, d_poffs, d_pvals, ptotal + 16, stream.cuda_stream)
+          ms = timed(do_locate_short, steps=3)
+          ml = min(nq, 100_000)
+          ooffs, ovals, secs = ora.locate_batch(psp[:ml], pep[:ml], threads=threads)
+          kk = int(ooffs[ml])
+          poffs = d_poffs.cpu().numpy().view(np.uint64); pvals = d_pvals[:kk].cpu().numpy().view(np.uint64)
+          report("locate of %d-mers (%.1f path nodes per range)" % (plen, float((pep - psp + 1).astype(np.float64).mean())), "positions/s", pgot[0], ms, kk / secs, ml,
+                 (poffs[:ml + 1] == ooffs).all() and (pvals == ovals).all() and pgot[0] == ptotal, {"positions": pgot[0], "ranges": nq})
+          del d_psp, d_pep, d_pcnt, d_poffs, d_pvals
 
     # ---- parent / depth ----
     if "parent" in ops:
