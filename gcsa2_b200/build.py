@@ -10,8 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgcsa2_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include", "gcsa2_b200.h")
-DEVICE_SOURCES = ["engine.cu", "find.cu", "ops.cu", "locate.cu", "lcp.cu", "kmers.cu", "linear_builder.cu"]   # CUDA translation units (nvcc, sm_100a)
-HOST_SOURCES = ["builder.cpp", "gcsa_file.cpp", "kmer_file.cpp", "verify.cpp", "pack.cpp"]      # host-side C++ (g++)
+DEVICE_SOURCES = ["engine.cu", "find.cu", "ops.cu", "locate.cu", "lcp.cu", "kmers.cu", "verify.cu", "linear_builder.cu"]   # CUDA translation units (nvcc, sm_100a)
+HOST_SOURCES = ["builder.cpp", "gcsa_file.cpp", "kmer_file.cpp", "pack.cpp"]      # host-side C++ (g++)
 
 NVCC = os.environ.get("GCSA_B200_NVCC", "nvcc")
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"

@@ -416,6 +416,7 @@ int gcsa_b200_locate_max_host(const gcsa_b200_index* index, const uint64_t* sp, 
   struct Special { std::mt19937_64 rng; std::unordered_set<u64> found; std::vector<u64> result; u64 draws = 0; };
   std::unordered_map<u64, Special> special;
   std::vector<u64> full_sp, full_ep, full_id, rnd_id;
+  full_sp.reserve(n); full_ep.reserve(n); full_id.reserve(n);
   for(u64 i = 0; i < n; i++)
   {
     if(totals[i] == 0) { continue; }
@@ -501,30 +502,27 @@ int gcsa_b200_locate_max_host(const gcsa_b200_index* index, const uint64_t* sp, 
     std::sort(r.begin(), r.end());
   }
   // assemble: plain ranges straight from the full locate, special ones from their state
-  out_offsets[0] = 0;
-  {
-    u64 t = 0;
-    for(u64 i = 0; i < n; i++)
-    {
-      while(t < full_id.size() && full_id[t] < i) { t++; }
-      auto it = special.find(i);
-      u64 size = 0;
-      if(it != special.end()) { size = it->second.result.size(); }
-      else if(t < full_id.size() && full_id[t] == i) { size = full_offs[t + 1] - full_offs[t]; }
-      out_offsets[i + 1] = out_offsets[i] + size;
-    }
-  }
+  // (sizes first, one pass per source; the common case -- no special range at all -- is two parallel loops)
+  std::vector<u64> slot_of(n, ~(u64)0);                                  // position in the full locate, or none
+  #pragma omp parallel for schedule(static)
+  for(u64 t = 0; t < full_id.size(); t++) { slot_of[full_id[t]] = t; }
+  for(u64 i = 0; i <= n; i++) { out_offsets[i] = 0; }
+  #pragma omp parallel for schedule(static)
+  for(u64 t = 0; t < full_id.size(); t++) { out_offsets[full_id[t] + 1] = full_offs[t + 1] - full_offs[t]; }
+  for(auto& entry : special) { out_offsets[entry.first + 1] = entry.second.result.size(); }
+  for(u64 i = 0; i < n; i++) { out_offsets[i + 1] += out_offsets[i]; }
   u64* vals = (u64*)std::malloc(std::max<u64>(out_offsets[n], 1) * sizeof(u64));
+  if(vals == nullptr) { std::free(full_vals); return fail(GCSA_B200_ERR_NOMEM, "locate_max_host: out of host memory"); }
+  #pragma omp parallel for schedule(static)
+  for(u64 t = 0; t < full_id.size(); t++)
   {
-    u64 t = 0;
-    for(u64 i = 0; i < n; i++)
+    u64 i = full_id[t];
+    if(out_offsets[i + 1] - out_offsets[i] == full_offs[t + 1] - full_offs[t])        // (a special range has its own, shorter result)
     {
-      while(t < full_id.size() && full_id[t] < i) { t++; }
-      auto it = special.find(i);
-      if(it != special.end()) { std::copy(it->second.result.begin(), it->second.result.end(), vals + out_offsets[i]); }
-      else if(t < full_id.size() && full_id[t] == i) { std::copy(full_vals + full_offs[t], full_vals + full_offs[t + 1], vals + out_offsets[i]); }
+      std::copy(full_vals + full_offs[t], full_vals + full_offs[t + 1], vals + out_offsets[i]);
     }
   }
+  for(auto& entry : special) { std::copy(entry.second.result.begin(), entry.second.result.end(), vals + out_offsets[entry.first]); }
   std::free(full_vals);
   *values = (uint64_t*)vals;
   return 0;

@@ -18,8 +18,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "gcsa2_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libgcsa2_b200_emu.so")
-DEVICE_SOURCES = ["engine.cu", "find.cu", "ops.cu", "locate.cu", "lcp.cu", "kmers.cu", "linear_builder.cu"]   # the first one carries the emulation's out-of-line definitions
-HOST_SOURCES = ["builder.cpp", "gcsa_file.cpp", "kmer_file.cpp", "verify.cpp", "pack.cpp"]
+DEVICE_SOURCES = ["engine.cu", "find.cu", "ops.cu", "locate.cu", "lcp.cu", "kmers.cu", "verify.cu", "linear_builder.cu"]   # the first one carries the emulation's out-of-line definitions
+HOST_SOURCES = ["builder.cpp", "gcsa_file.cpp", "kmer_file.cpp", "pack.cpp"]
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 COLLECTIVES = ("__ballot_sync", "__any_sync", "__all_sync", "__syncwarp", "__syncthreads", "__shfl_sync",
                "__shfl_down_sync", "__shfl_up_sync", "__shfl_xor_sync")
