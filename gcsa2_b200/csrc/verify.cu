@@ -17,8 +17,9 @@
   Every stage calls the same entry points a caller would (gcsa_b200_find_batch, _parent_batch, _depth_batch,
   _count_batch, _locate_batch: device pointers, one stream), the comparisons are small kernels that count failures per
   stage, and a label that fails a stage is not looked at by the later ones, as in the reference.  Only the last stage
-  goes through the host: locate(range, max_positions) draws with std::mt19937_64 (gcsa_b200_locate_max_host); its
-  inputs and the located values are downloaded for it.  The first version did every stage through the host entry points
+  goes through the host, and only for the labels with more than 10 occurrences: locate(range, max_positions) draws with
+  std::mt19937_64 (gcsa_b200_locate_max_host); for a range with at most max_positions occurrences it is by definition
+  locate(range) (src/gcsa.cpp:860-875), which the stage before has just compared.  The first version did every stage through the host entry points
   and spent its time sorting, building patterns and filtering on the host (20.5 s for the 58 M labels of cfg3; the
   device was busy for a fraction of a second).
 
@@ -220,8 +221,8 @@ vf_select_kernel(const u64* __restrict__ keep_pos, const u64* __restrict__ sp, c
   }
 }
 
-// locate(range) == the distinct start nodes (algorithms.cpp:202-234); random_flag: the size was right, so the random
-// locate is tried as well (the reference tries it after a value mismatch too)
+// locate(range) == the distinct start nodes (algorithms.cpp:202-234); random_flag: the size was right (the reference tries
+// the random locate after a value mismatch too) and the label has more than 10 occurrences
 __global__ void __launch_bounds__(256)
 vf_locate_check_kernel(const u64* __restrict__ ids, u64 n_ids, const u64* __restrict__ loc_offsets, const u64* __restrict__ located,
                        const u64* __restrict__ exp_offsets, const u64* __restrict__ expected, u64* __restrict__ random_flag, ull* __restrict__ counters)
@@ -236,7 +237,10 @@ vf_locate_check_kernel(const u64* __restrict__ ids, u64 n_ids, const u64* __rest
       bool same = (got == want);
       for(u64 j = 0; same && j < want; j++) { same = (located[loc_offsets[i] + j] == expected[exp_offsets[g] + j]); }
       fails += (same ? 0 : 1);
-      flag = (got == want ? 1 : 0);
+      // locate(range, 10) of a range with at most 10 occurrences IS locate(range) (gcsa.cpp:860-875: everything is located,
+      // and nothing is dropped because nothing exceeds max_positions): the reference compares locate() with itself there.
+      // The labels with more occurrences are the ones that draw random numbers; they go through the real entry point.
+      flag = (got == want && want > RANDOM_LOCATE_SIZE ? 1 : 0);
     }
     random_flag[i] = flag;
   }
@@ -457,8 +461,19 @@ extern "C" int gcsa_b200_verify_index_mapped(const gcsa_b200_index* index, const
       CUDA_TRY(cudaGetLastError());
       lap("locate");
 
-      // locate(range, 10) -- algorithms.cpp:236-274.  The random draws are the host's (std::mt19937_64): the ranges and
-      // the located values come down for this stage.
+      // locate(range, 10) -- algorithms.cpp:236-274.  The random draws are the host's (std::mt19937_64): if any label of
+      // the chunk has more than 10 occurrences, the ranges and the located values come down for this stage.
+      VF_RC(scanExclusive(random_flag, random_flag, n_ids + 1, st));
+      u64 n_random = 0;
+      CUDA_TRY(cudaMemcpyAsync(&n_random, random_flag + n_ids, sizeof(u64), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      if(n_random == 0)
+      {
+        for(void* p : { (void*)ids, (void*)a, (void*)b, (void*)loc_offsets, (void*)located, (void*)random_flag }) { buf.release(p); }
+        lap("locate(range, 10): none");
+      }
+      else
+      {
       std::vector<u64> h_a(n_ids), h_b(n_ids), h_offs(n_ids + 1), h_flag(n_ids + 1), h_located(std::max<u64>(needed, 1));
       CUDA_TRY(cudaMemcpyAsync(h_a.data(), a, n_ids * sizeof(u64), cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaMemcpyAsync(h_b.data(), b, n_ids * sizeof(u64), cudaMemcpyDeviceToHost, st));
@@ -469,7 +484,7 @@ extern "C" int gcsa_b200_verify_index_mapped(const gcsa_b200_index* index, const
       for(void* p : { (void*)ids, (void*)a, (void*)b, (void*)loc_offsets, (void*)located, (void*)random_flag }) { buf.release(p); }
       const auto host_start = std::chrono::steady_clock::now();
       std::vector<u64> pick;                                             // positions in ids whose locate() had the right size
-      for(u64 i = 0; i < n_ids; i++) { if(h_flag[i]) { pick.push_back(i); } }
+      for(u64 i = 0; i < n_ids; i++) { if(h_flag[i + 1] != h_flag[i]) { pick.push_back(i); } }       // (h_flag holds the exclusive scan)
       std::vector<u64> ra(pick.size() + 1), rb(pick.size() + 1), rnd_offsets(pick.size() + 1, 0);
       #pragma omp parallel for schedule(static)
       for(u64 i = 0; i < pick.size(); i++) { ra[i] = h_a[pick[i]]; rb[i] = h_b[pick[i]]; }
@@ -497,6 +512,7 @@ extern "C" int gcsa_b200_verify_index_mapped(const gcsa_b200_index* index, const
       report->random_locate_failures += random_fails;
       host_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - host_start).count();
       lap("locate(range, 10)");
+      }
     }
     for(void* p : { (void*)offsets, (void*)chars, (void*)sp, (void*)ep, (void*)alive, (void*)counts, (void*)keep }) { buf.release(p); }
   }

@@ -249,7 +249,9 @@ int gcsa_b200_compare_kmers(const gcsa_b200_index* left, const gcsa_b200_index* 
    include/gcsa/support.h:475-497) is searched with find(); parent() must equal the first different range
    obtained by dropping characters from the right end and depth() must agree; count() must equal the number
    of distinct start nodes; locate() must return exactly those; locate(range, 10) must return min(10, n) of
-   them.  lcp may be NULL (the parent / depth checks are skipped, like `lcp == 0` in the reference).
+   them (checked through gcsa_b200_locate_max_host for the labels with more than 10 start nodes: for the others
+   locate(range, 10) is locate(range) by definition, src/gcsa.cpp:860-875).  Device-resident: the records are
+   uploaded once and sorted, grouped, turned into patterns and compared on the GPU.  lcp may be NULL (the parent / depth checks are skipped, like `lcp == 0` in the reference).
    Returns 0 when the verification ran; the index is correct iff report->failures == 0. */
 typedef struct gcsa_b200_verify_report {
   uint64_t unique;                      /* distinct labels queried */

@@ -32,6 +32,7 @@ def main():
     from gcsa2_b200 import capi
     capi._lib = capi._bind(ctypes.CDLL(build_emu.build()))
     from brute import random_graph
+    from test_builder import flat_equal
     from gcsa2_b200 import GCSA, LCPArray, mem_batch, synth
     from gcsa2_b200.builder import CharGraph, build_index
     from oracle import oracle as orc
@@ -52,7 +53,12 @@ def main():
                 a, b, w = int(rng.integers(0, L - 600)), int(rng.integers(0, L - 600)), int(rng.integers(20, 500))
                 seq[a:a + w] = seq[b:b + w]
             graph = synth.linear_graph(seq)
-            flat, flcp, _ = build_index(graph, 16, int(rng.integers(1, 4)))
+            steps = int(rng.integers(1, 4))
+            flat, flcp, _ = build_index(graph, 16, steps)
+            if rounds % 4 == 0:                                       # the device builder for linear references emits the same arrays
+                from gcsa2_b200.builder import build_linear
+                dflat, dlcp = build_linear(seq, k=16, doubling_steps=steps)
+                assert flat_equal(flat, dflat) == [] and (dlcp.data == flcp.data).all(), ("build_linear", seed, L, steps)
             sampler = lambda n, ln, s: synth.patterns_from_sequence(seq, n, ln, seed=s)
             what = "linear L=%d" % L
         elif kind == 1:                                               # SNP graph
@@ -76,7 +82,7 @@ def main():
             what = "indel graph N=%d" % flat.path_nodes
         N = flat.path_nodes
         opts = dict(kmer_table_k=int(rng.choice([0, 1, 2, 4, 6, 8, 9])), two_step=bool(rng.integers(0, 2)),
-                    walk_table=[None, 0, 1, 2][int(rng.integers(0, 4))], jump_table=bool(rng.integers(0, 4) > 0),
+                    walk_table=[None, 0, 1, 2][int(rng.integers(0, 4))], jump_table=[False, True, True, "wide"][int(rng.integers(0, 4))],
                     fused_table=[None, True, False][int(rng.integers(0, 3))])
         gpu, ora = GCSA(flat, **opts), orc.OracleGCSA(flat)
         glcp, olcp = LCPArray(flcp), orc.OracleLCP(flcp)
@@ -104,6 +110,23 @@ def main():
         sp, ep = gpu.find_batch(chars, offsets)
         osp, oep, _ = ora.find_batch(chars, offsets, threads=4)
         assert (sp == osp).all() and (ep == oep).all(), ("find", tag, np.flatnonzero((sp != osp) | (ep != oep))[:5])
+
+        # a batch of k-mers (one length, at least 4096 of them): the two-kernel form with its work lists
+        if sampler is not None and opts["kmer_table_k"] > 0:
+            os.environ["GCSA_B200_FIND_UNROLL"] = str(int(rng.choice([1, 2, 4])))
+            ln = int(rng.choice([opts["kmer_table_k"], 12, 16, 24, 31, 32, 33, 50, 64, 101]))
+            if ln >= opts["kmer_table_k"]:
+                kc, ko = sampler(4500, ln, int(rng.integers(0, 1 << 30)))
+                kc = kc.copy()
+                for i in range(0, 4500, 3):
+                    r = rng.random()
+                    if r < 0.5:
+                        kc[int(ko[i]) + int(rng.integers(0, ln))] = alphabet[int(rng.integers(0, alphabet.size if r < 0.1 else 16))]
+                    elif r < 0.6:
+                        kc[int(ko[i]):int(ko[i + 1])] = synth.random_patterns(1, ln, seed=int(rng.integers(0, 1 << 30)))[0]
+                ksp0, kep0, _ = ora.find_batch(kc, ko, threads=4)
+                ksp, kep = gpu.find_fixed_batch(kc, ln)
+                assert (ksp == ksp0).all() and (kep == kep0).all(), ("k-mer form", ln, tag, np.flatnonzero((ksp != ksp0) | (kep != kep0))[:5])
 
         # fixed-length batches through the host entry point, with and without host-side 2-bit packing
         if sampler is not None and rounds % 8 == 0:
