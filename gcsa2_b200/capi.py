@@ -82,7 +82,7 @@ SYMBOLS = [
     "gcsa_b200_lf_batch", "gcsa_b200_lf_host", "gcsa_b200_lf_node_batch", "gcsa_b200_lf_node_host",
     "gcsa_b200_lf_multi_batch", "gcsa_b200_lf_multi_host",
     "gcsa_b200_count_batch", "gcsa_b200_count_host",
-    "gcsa_b200_locate_host", "gcsa_b200_locate_into_host", "gcsa_b200_locate_raw_host", "gcsa_b200_locate_batch", "gcsa_b200_locate_max_host", "gcsa_b200_free", "gcsa_b200_count_kmers", "gcsa_b200_compare_kmers", "gcsa_b200_verify_index",
+    "gcsa_b200_locate_host", "gcsa_b200_locate_into_host", "gcsa_b200_locate_raw_host", "gcsa_b200_locate_batch", "gcsa_b200_locate_max_host", "gcsa_b200_free", "gcsa_b200_count_kmers", "gcsa_b200_compare_kmers", "gcsa_b200_compare_kmers_to_files", "gcsa_b200_verify_index",
     "gcsa_b200_lcp_create", "gcsa_b200_lcp_destroy",
     "gcsa_b200_parent_batch", "gcsa_b200_parent_host", "gcsa_b200_depth_batch", "gcsa_b200_depth_host",
     "gcsa_b200_lcp_sv_host", "gcsa_b200_lcp_rmq_host", "gcsa_b200_mem_batch", "gcsa_b200_mem_host",
@@ -147,6 +147,7 @@ def _bind(L):
     L.gcsa_b200_free.argtypes = [vp]; L.gcsa_b200_free.restype = None
     L.gcsa_b200_count_kmers.argtypes = [vp, u64, i32, C.POINTER(u64), C.POINTER(vp)]
     L.gcsa_b200_compare_kmers.argtypes = [vp, vp, u64, i32, vp, C.POINTER(vp), C.POINTER(vp)]
+    L.gcsa_b200_compare_kmers_to_files.argtypes = [vp, vp, u64, i32, C.c_char_p, vp]
     L.gcsa_b200_verify_index.argtypes = [vp, vp, vp, vp, u64, i32, C.POINTER(VerifyReport)]
     L.gcsa_b200_lcp_create.argtypes = [C.POINTER(FlatLcp), i32, C.POINTER(vp)]
     L.gcsa_b200_lcp_destroy.argtypes = [vp]; L.gcsa_b200_lcp_destroy.restype = None

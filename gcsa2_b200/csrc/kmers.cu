@@ -213,3 +213,31 @@ done:
   HOST_EPILOGUE("compare_kmers", rc);
 }
 
+
+/*
+  compareKMers with KMerSearchParameters::output set (include/gcsa/algorithms.h:59-71, src/algorithms.cpp:556-613): the
+  k-mers unique to either index are written to <output>.left / <output>.right as the reference writes them -- raw
+  KMerComparisonState records, 64 bytes each (both ranges, k, the k-mer in three words), in no particular order.
+*/
+int gcsa_b200_compare_kmers_to_files(const gcsa_b200_index* left, const gcsa_b200_index* right, uint64_t k, int include_Ns,
+                                     const char* output, uint64_t* result)
+{
+  if(output == nullptr || *output == 0) { return gcsa_b200_compare_kmers(left, right, k, include_Ns, result, nullptr, nullptr); }
+  const std::string left_name = std::string(output) + ".left", right_name = std::string(output) + ".right";   // KMerSearchParameters::LEFT_EXTENSION / RIGHT_EXTENSION
+  FILE* left_file = std::fopen(left_name.c_str(), "wb");
+  if(left_file == nullptr) { return fail(GCSA_B200_ERR_INVALID, "compare_kmers: cannot open output file " + left_name); }
+  FILE* right_file = std::fopen(right_name.c_str(), "wb");
+  if(right_file == nullptr) { std::fclose(left_file); return fail(GCSA_B200_ERR_INVALID, "compare_kmers: cannot open output file " + right_name); }
+  gcsa_b200_kmer_state *left_kmers = nullptr, *right_kmers = nullptr;
+  int rc = gcsa_b200_compare_kmers(left, right, k, include_Ns, result, &left_kmers, &right_kmers);
+  if(rc == 0)
+  {
+    bool ok = (result[1] == 0 || std::fwrite(left_kmers, sizeof(gcsa_b200_kmer_state), result[1], left_file) == result[1]);
+    ok = ok && (result[2] == 0 || std::fwrite(right_kmers, sizeof(gcsa_b200_kmer_state), result[2], right_file) == result[2]);
+    if(!ok) { rc = fail(GCSA_B200_ERR_INVALID, "compare_kmers: writing the output files failed"); }
+  }
+  std::free(left_kmers); std::free(right_kmers);
+  if(std::fclose(left_file) != 0 && rc == 0) { rc = fail(GCSA_B200_ERR_INVALID, "compare_kmers: closing " + left_name + " failed"); }
+  if(std::fclose(right_file) != 0 && rc == 0) { rc = fail(GCSA_B200_ERR_INVALID, "compare_kmers: closing " + right_name + " failed"); }
+  return rc;
+}

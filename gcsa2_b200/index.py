@@ -232,6 +232,12 @@ class GCSA:
                                                             len(mapping.ids) if mapping is not None else 0, C.byref(rep)))
         return {name: getattr(rep, name) for name, _ in capi.VerifyReport._fields_}
 
+    def compare_kmers_to_files(self, other, k, output, include_Ns=False):
+        """compareKMers with parameters.output = `output`: counts, and the unique kmers in <output>.left / <output>.right."""
+        res = np.zeros(3, dtype=np.uint64)
+        capi.check(capi.lib().gcsa_b200_compare_kmers_to_files(self._h, other._h, int(k), int(bool(include_Ns)), str(output).encode(), res.ctypes.data))
+        return tuple(int(x) for x in res)
+
     def compare_kmers(self, other, k, include_Ns=False, return_kmers=False):
         """compareKMers(left, right, k), src/algorithms.cpp:535-616 -> (shared, left only, right only)
         [, left_kmers, right_kmers as rows of 8 uint64: KMerComparisonState records]."""

@@ -243,6 +243,10 @@ typedef struct gcsa_b200_kmer_state { uint64_t left_sp, left_ep, right_sp, right
    Like gcsa_b200_count_kmers this does not compare k with order() (parameters.force = true). */
 int gcsa_b200_compare_kmers(const gcsa_b200_index* left, const gcsa_b200_index* right, uint64_t k, int include_Ns,
                             uint64_t* result, gcsa_b200_kmer_state** left_kmers, gcsa_b200_kmer_state** right_kmers);
+/* The same with KMerSearchParameters::output set (algorithms.h:59-71): the unique kmers go to <output>.left and
+   <output>.right as the reference writes them (raw 64-byte KMerComparisonState records, src/algorithms.cpp:606-607). */
+int gcsa_b200_compare_kmers_to_files(const gcsa_b200_index* left, const gcsa_b200_index* right, uint64_t k, int include_Ns,
+                                     const char* output, uint64_t* result);
 
 /* verifyIndex(index, lcp, kmers, kmer_length), src/algorithms.cpp:101-295 (declared include/gcsa/algorithms.h:40-55),
    batched: every distinct kmer label of the construction input (keys / from = the KMer records,

@@ -94,6 +94,20 @@ def test_device_compare_kmers(pair):
     assert ga.compare_kmers(ga, 10) == (ga.count_kmers(10), 0, 0)
     with pytest.raises(Exception):
         ga.compare_kmers(gb, 65)
+    # KMerSearchParameters::output: the unique kmers as raw 64-byte records in <output>.left / <output>.right
+    import os
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        base = os.path.join(tmp, "unique")
+        counts, left, right = ga.compare_kmers(gb, 8, return_kmers=True)
+        assert ga.compare_kmers_to_files(gb, 8, base) == counts
+        order = lambda r: r[np.lexsort(r.T[::-1])] if len(r) else r
+        from_left = np.fromfile(base + ".left", dtype=np.uint64).reshape(-1, 8)
+        from_right = np.fromfile(base + ".right", dtype=np.uint64).reshape(-1, 8)
+        assert from_left.shape[0] == counts[1] and from_right.shape[0] == counts[2]
+        assert (order(from_left) == order(left)).all() and (order(from_right) == order(right)).all()
+        with pytest.raises(Exception):
+            ga.compare_kmers_to_files(gb, 8, os.path.join(tmp, "no", "such", "directory", "x"))
     # a graph with bubbles against its own backbone
     seq = synth.random_sequence(50_000, seed=9)
     fg, _, _ = build_index(synth.snp_graph(seq, seed=9, snp_rate=0.02)[0], 16, 2)
