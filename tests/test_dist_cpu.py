@@ -85,3 +85,48 @@ def test_shard_by_length_gives_every_rank_the_same_mix():
             seen.append(ids); totals.append(int(o[-1]))
         assert sorted(np.concatenate(seen).tolist()) == list(range(lengths.size))
         assert max(totals) - min(totals) <= 256 * 2
+
+
+def strong_scaling_worker(rank, world, port, out_dir):
+    """The strong-scaling legs of bench.py (configs[3]: chunks of one job dealt round-robin; configs[4]: patterns dealt in
+    length order) with the CPU oracle standing in for the kernels: the all-reduced counters must be those of the whole job."""
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from gcsa2_b200 import synth
+    from gcsa2_b200.builder import build_index
+    from oracle import oracle as orc
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    seq = synth.counter_sequence(30_000, seed=4)                        # every rank regenerates the same reference
+    graph, sites, alt = synth.snp_graph(seq, seed=3, snp_rate=0.01)
+    flat, flcp, _ = build_index(graph, 16, 2)
+    ora, olcp = orc.OracleGCSA(flat), orc.OracleLCP(flcp)
+    # configs[3]: 7 chunks of 1000 queries (the last one shorter), chunk c belongs to rank c % world
+    total, chunk, length = 6500, 1000, 32
+    t_seq = torch.from_numpy(seq)
+    mine = [c for c in range((total + chunk - 1) // chunk) if c % world == rank]
+    counts = torch.zeros(2, dtype=torch.int64)
+    for c in mine:
+        m = min(chunk, total - c * chunk)
+        chars = synth.device_patterns(t_seq, m, length, seed=4000 + c).numpy()
+        sp, ep, _ = ora.find_batch(chars, np.arange(m + 1, dtype=np.uint64) * np.uint64(length))
+        counts += torch.tensor([m, int(np.count_nonzero(sp <= ep))])
+    dist.all_reduce(counts)
+    # configs[4]: one batch of mixed lengths, dealt in length order
+    all_chars, all_offsets = synth.device_mixed_length_patterns(t_seq, sites, alt, 801, 16, 120, seed=5, error_rate=0.02)
+    my_chars, my_offsets, ids = synth.device_shard_by_length(all_chars, all_offsets, rank, world)
+    offs, vals, _ = orc.mem_batch(ora, olcp, my_chars.numpy(), my_offsets.numpy().astype(np.uint64))
+    mem = torch.tensor([int(ids.numel()), int(offs[-1])], dtype=torch.int64)
+    dist.all_reduce(mem)
+    if rank == 0:
+        whole_offs, _, _ = orc.mem_batch(ora, olcp, all_chars.numpy(), all_offsets.numpy().astype(np.uint64))
+        np.save(os.path.join(out_dir, "strong.npy"), np.array([int(counts[0]), int(counts[1]), int(mem[0]), int(mem[1]), int(whole_offs[-1])]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_strong_scaling_legs(tmp_path):
+    port = free_port()
+    mp.spawn(strong_scaling_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    queries, found, patterns, matches, whole_matches = np.load(os.path.join(str(tmp_path), "strong.npy"))
+    assert queries == 6500 and found == 6500                          # every chunk once, everything sampled from the text occurs
+    assert patterns == 801 and matches == whole_matches and matches > 801
