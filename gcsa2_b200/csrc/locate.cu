@@ -117,6 +117,18 @@ int locateGeneral(const gcsa_b200_index* index, const u64* d_sp, const u64* d_ep
   return rc;
 }
 
+// blocks of each locate_medium_kernel class that one SM holds at once
+struct MediumGrids { int per_sm[3]; };
+MediumGrids mediumGrids()
+{
+  MediumGrids g = { { 8, 3, 2 } };
+  int b = 0;
+  if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, locate_medium_kernel<0>, 128, 0) == cudaSuccess && b > 0) { g.per_sm[0] = b; }
+  if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, locate_medium_kernel<1>, 128, 0) == cudaSuccess && b > 0) { g.per_sm[1] = b; }
+  if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, locate_medium_kernel<2>, 256, 0) == cudaSuccess && b > 0) { g.per_sm[2] = b; }
+  return g;
+}
+
 /*
   locate() of a batch of ranges as a CSR of sorted distinct positions.  With the locate table, short ranges are
   answered by the two register passes above (one thread per range) and only the others go through the general
@@ -139,18 +151,53 @@ int locateDevice(const gcsa_b200_index* index, const u64* d_sp, const u64* d_ep,
   auto alloc = [&](u64 bytes) -> void* { void* p = nullptr; if(engineMallocAsync(&p, std::max<u64>(bytes, 16), st) != cudaSuccess) { return nullptr; } tmp.push_back(p); return p; };
   auto cleanup = [&]() { for(void* p : tmp) { cudaFreeAsync(p, st); } tmp.clear(); if(gvals) { cudaFreeAsync(gvals, st); gvals = nullptr; } };
 
+  const char* med_env = std::getenv("GCSA_B200_LOCATE_MEDIUM");
+  const bool medium = (med_env == nullptr || std::atoi(med_env) != 0);
   u64* cnt = (u64*)alloc((n + 1) * sizeof(u64));
   u64* stash = (u64*)alloc(n * sizeof(u64));
   u64* glist = (u64*)alloc(n * sizeof(u64));
-  ull* d_general = (ull*)alloc(sizeof(ull));
-  if(!cnt || !stash || !glist || !d_general) { cleanup(); return fail(GCSA_B200_ERR_NOMEM, "locate: out of device memory"); }
+  u64* mlist = (u64*)alloc(2 * n * sizeof(u64));
+  ull* d_counters = (ull*)alloc(5 * sizeof(ull));
+  if(!cnt || !stash || !glist || !mlist || !d_counters) { cleanup(); return fail(GCSA_B200_ERR_NOMEM, "locate: out of device memory"); }
   LOC_TRY(cudaMemsetAsync(cnt + n, 0, sizeof(u64), st));
-  LOC_TRY(cudaMemsetAsync(d_general, 0, sizeof(ull), st));
-  locate_small_count_kernel<<<gridFor(n, sm), 256, 0, st>>>(v, d_sp, d_ep, n, cnt, stash, glist, d_general);
-  ull n_general = 0;
-  LOC_TRY(cudaMemcpyAsync(&n_general, d_general, sizeof(ull), cudaMemcpyDeviceToHost, st));
+  LOC_TRY(cudaMemsetAsync(d_counters, 0, 5 * sizeof(ull), st));
+  locate_small_count_kernel<<<gridFor(n, sm), 256, 0, st>>>(v, d_sp, d_ep, n, cnt, stash, glist, mlist, d_counters, medium);
+  ull counters[5] = { 0, 0, 0, 0, 0 };
+  LOC_TRY(cudaMemcpyAsync(counters, d_counters, 5 * sizeof(ull), cudaMemcpyDeviceToHost, st));
   LOC_TRY(cudaStreamSynchronize(st));
-  if(std::getenv("GCSA_B200_LOCATE_DEBUG") != nullptr) { std::fprintf(stderr, "locate: %llu of %llu ranges through the general pipeline\n", n_general, (ull)n); }
+  const u64 n_short = counters[1], n_block = counters[2], n_warp = counters[4];
+  const u64* short_list = mlist; const u64* block_list = mlist + (n - n_block); const u64* warp_list = mlist + n;
+  u64* scratch = nullptr;
+  if(n_short + n_warp + n_block > 0)
+  {
+    // the medium ranges: sorted and deduplicated in registers, a warp or a block per range; the grids are what is
+    // resident at once (the groups stride over their list, so no wave is left partly filled)
+    scratch = (u64*)alloc(counters[3] * sizeof(u64));
+    if(!scratch) { cleanup(); return fail(GCSA_B200_ERR_NOMEM, "locate: out of device memory"); }
+    static const MediumGrids grids = mediumGrids();
+    if(n_short > 0)
+    {
+      u64 blocks = std::min<u64>((n_short + 3) / 4, (u64)sm * grids.per_sm[0]);
+      locate_medium_kernel<0><<<(unsigned)blocks, 128, 0, st>>>(v, d_sp, d_ep, short_list, n_short, cnt, stash, scratch, glist, d_counters);
+    }
+    if(n_warp > 0)
+    {
+      u64 blocks = std::min<u64>((n_warp + 3) / 4, (u64)sm * grids.per_sm[1]);
+      locate_medium_kernel<1><<<(unsigned)blocks, 128, 0, st>>>(v, d_sp, d_ep, warp_list, n_warp, cnt, stash, scratch, glist, d_counters);
+    }
+    if(n_block > 0)
+    {
+      u64 blocks = std::min<u64>(n_block, (u64)sm * grids.per_sm[2]);
+      locate_medium_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(v, d_sp, d_ep, block_list, n_block, cnt, stash, scratch, glist, d_counters);
+    }
+    LOC_TRY(cudaMemcpyAsync(counters, d_counters, sizeof(ull), cudaMemcpyDeviceToHost, st));
+    LOC_TRY(cudaStreamSynchronize(st));
+  }
+  const ull n_general = counters[0];
+  if(std::getenv("GCSA_B200_LOCATE_DEBUG") != nullptr)
+  {
+    std::fprintf(stderr, "locate: of %llu ranges %llu + %llu sorted by a warp, %llu by a block, %llu through the general pipeline\n", (ull)n, (ull)n_short, (ull)n_warp, (ull)n_block, n_general);
+  }
 
   u64* goffs = nullptr;
   if(n_general > 0)
@@ -177,7 +224,14 @@ int locateDevice(const gcsa_b200_index* index, const u64* d_sp, const u64* d_ep,
     *d_values_alloc = (u64*)p; d_values = (u64*)p; capacity = distinct;
   }
   if(d_values == nullptr || capacity < distinct) { rc = GCSA_B200_ERR_CAPACITY; g_last_error = "locate: output capacity too small"; }
-  else if(distinct > 0) { locate_small_fill_kernel<<<gridFor(n, sm), 256, 0, st>>>(v, d_sp, d_ep, n, d_out_offsets, stash, goffs, gvals, d_values); }
+  else if(distinct > 0)
+  {
+    locate_small_fill_kernel<<<gridFor(n, sm), 256, 0, st>>>(v, d_sp, d_ep, n, d_out_offsets, stash, d_values);
+    if(n_short > 0) { locate_copy_kernel<false><<<gridFor(n_short * 32, sm), 256, 0, st>>>(short_list, n_short, stash, d_out_offsets, nullptr, scratch, d_values); }
+    if(n_warp > 0) { locate_copy_kernel<false><<<gridFor(n_warp * 32, sm), 256, 0, st>>>(warp_list, n_warp, stash, d_out_offsets, nullptr, scratch, d_values); }
+    if(n_block > 0) { locate_copy_kernel<false><<<gridFor(n_block * 32, sm), 256, 0, st>>>(block_list, n_block, stash, d_out_offsets, nullptr, scratch, d_values); }
+    if(n_general > 0) { locate_copy_kernel<true><<<gridFor(n_general * 32, sm), 256, 0, st>>>(glist, n_general, stash, d_out_offsets, goffs, gvals, d_values); }
+  }
   LOC_TRY(cudaGetLastError());
   cleanup();
   #undef LOC_TRY

@@ -117,7 +117,7 @@ def main():
 
     # ---- locate() of short patterns: wide ranges, the general pipeline (segmented sort) instead of the short-range path ----
     if "locate_short" in ops:
-      for plen, nq in ((12, 2_000_000), (10, 1_000_000), (8, 200_000)):
+      for plen, nq in ((12, 2_000_000), (10, 1_000_000), (8, 200_000), (7, 50_000), (6, 20_000)):
           pchars, poffsets = synth.patterns_from_snp_graph(seq, sites, alt, nq, plen, seed=600 + plen)
           psp, pep = index.find_batch(pchars, poffsets)
           d_psp = torch.from_numpy(psp.view(np.int64)).cuda(); d_pep = torch.from_numpy(pep.view(np.int64)).cuda()

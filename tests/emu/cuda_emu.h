@@ -190,6 +190,9 @@ static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { emu::release((void*)
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
+// (two blocks per "SM": small grids, so that the grid-stride loops of the kernels sized this way are exercised)
+template<class Kernel>
+static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* blocks, Kernel, int, size_t) { *blocks = 2; return cudaSuccess; }
 
 //------------------------------------------------------------------------------
 // Thread coordinates and the fiber scheduler

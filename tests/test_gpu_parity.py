@@ -471,6 +471,42 @@ def test_locate_short_range_path(monkeypatch):
     assert got == int(ooffs[-1]) and (big.cpu().numpy().view(np.uint64) == ovals).all()
 
 
+def test_locate_medium_range_path(monkeypatch):
+    """locate() of ranges of tens to thousands of path nodes (what a short pattern gives): sorted and deduplicated in
+    shared memory by a warp (up to 1024 nodes) or a block (up to 4096) == the general pipeline == the oracle.  Lengths
+    on both sides of every limit (8 | 9, 32 | 33, 128 | 129, ..., 1024 | 1025, 4096 | 4097), repeats (duplicates inside a range, and
+    nodes with several start positions, which hand the range over to the general pipeline), mixed with short, empty
+    and out-of-range ranges."""
+    seq = synth.random_sequence(60_000, seed=23)
+    seq[20_000:26_000] = seq[1000:7000]                               # a long repeat
+    seq[40_000:40_400] = seq[1200:1600]
+    graph, sites, alt = synth.snp_graph(seq, seed=23, snp_rate=0.02)
+    flat, _, _ = build_index(graph, 16, 2)
+    ora = orc.OracleGCSA(flat)
+    N = flat.path_nodes
+    rng = np.random.default_rng(23)
+    edge = np.array([8, 9, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 2047, 2048, 2049, 4095, 4096, 4097, 5000], dtype=np.uint64)
+    ln = np.concatenate([np.repeat(edge, 3), rng.integers(9, 200, size=300).astype(np.uint64), rng.integers(1, 9, size=200).astype(np.uint64),
+                         rng.integers(200, 4200, size=40).astype(np.uint64)])
+    a = rng.integers(0, N - 5001, size=ln.size).astype(np.uint64)
+    sp = np.concatenate([a, np.array([5, 0, N - 3, 0], dtype=np.uint64)])
+    ep = np.concatenate([a + ln - np.uint64(1), np.array([4, M64, N + 2, N - 1], dtype=np.uint64)])
+    order = rng.permutation(sp.size)
+    sp, ep = sp[order], ep[order]
+    want_offs, want_vals, _ = ora.locate_batch(sp, ep, threads=4)
+    gpu = GCSA(flat, walk_table=1)
+    for medium in ("1", "0"):
+        monkeypatch.setenv("GCSA_B200_LOCATE_MEDIUM", medium)
+        offs, vals = gpu.locate_batch(sp, ep)
+        assert (offs == want_offs).all() and (vals == want_vals).all(), medium
+    monkeypatch.setenv("GCSA_B200_LOCATE_MEDIUM", "1")
+    only = np.flatnonzero((ep - sp >= 8) & (ep - sp < 4096) & (ep < N))       # a batch without short or general ranges
+    w_offs, w_vals, _ = ora.locate_batch(sp[only], ep[only], threads=4)
+    offs, vals = gpu.locate_batch(sp[only], ep[only])
+    assert (offs == w_offs).all() and (vals == w_vals).all()
+    assert (gpu.count_batch(sp[only], ep[only]) >= 0).all()
+
+
 def test_locate_into_host_buffers():
     """gcsa_b200_locate_into_host (caller-owned buffers, chunked pipeline) == gcsa_b200_locate_host; too small a
     buffer is reported with the needed size and complete offsets."""
