@@ -16,8 +16,12 @@
   the offsets computed from the counts.
 */
 // MODE 0: count the matches of each pattern.  MODE 1: write them at out_offsets (exact positions known).
-// MODE 2: count AND write the first `stride` matches of pattern q at scratch slot q * stride (one pass; the
-// few patterns with more matches are redone in MODE 1 over the id list `ids`).
+// MODE 2: count AND write the first matches of pattern q into its scratch slot (one pass; the few patterns with more
+// matches than their slot holds are redone in MODE 1 over the id list `ids`).  A slot grows with the pattern: pattern q of
+// length len, starting at character `begin`, owns (len >> shift) + base entries from (begin >> shift) + q * base
+// (mem_slot_start / mem_slot_size; shift = 63 gives every pattern `base` entries).  The number of matches grows with the
+// length -- one per mismatch, roughly -- so equal slots either overflow for the long patterns, whose second pass was a third
+// of the time of configs[4] (profiles/r02_mem_scan_variants.txt), or waste memory on the short ones.
 // JUMP: singleton ranges advance along the unary backward path of their node with one load (the jump tables of
 // find_kernel): the pattern is kept 2-bit packed, 32 characters at a time, and a path of up to 16 steps is one XOR
 // against it.  A path that the pattern leaves after t characters is followed by t + 1 single steps (the last of
@@ -26,6 +30,9 @@
 // load and a table lookup in front of every step), without the jump-table probes.  Measured slower than the byte
 // loads (34.2 vs 27.6 ms per 4 M patterns, profiles/r02_mem_scan_variants.txt): the bytes hit the L1, the packing costs
 // registers and instructions in a kernel that is short of both; opt-in (GCSA_B200_MEM_PACK=1).
+__device__ __forceinline__ u64 mem_slot_start(u64 begin, u64 q, u64 base, u32 shift) { return (begin >> shift) + q * base; }
+__device__ __forceinline__ u64 mem_slot_size(u64 len, u64 base, u32 shift) { return (len >> shift) + base; }
+
 // A match record (start, length, sp, ep)
 __device__ __forceinline__ void store_match(u64* m, u64 start, u64 length, u64 sp, u64 ep)
 {
@@ -36,7 +43,7 @@ template<int MODE, bool JUMP = false, bool PACK = false, int MIN_BLOCKS = 4>
 __global__ void __launch_bounds__(256, MIN_BLOCKS)
 mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const u64* __restrict__ offsets, u64 char_base,
            u64 n, u64* __restrict__ counts, const u64* __restrict__ out_offsets, u64* __restrict__ matches,
-           const u64* __restrict__ ids, u64 stride, u32 parent_batch)
+           const u64* __restrict__ ids, u64 stride, u32 parent_batch, u32 shift)
 {
   constexpr bool WRITE = (MODE == 1);
   constexpr bool TAIL = (JUMP || PACK);
@@ -101,7 +108,7 @@ mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const
           sp = 0; ep = v.path_nodes - 1; depth = 0; extended = false; emitted = 0;
           if(TAIL) { tail = 0; tail_n = 0; tail_end = pos; skip = 0; next_pack = pos; }
           if(WRITE) { out_at = out_offsets[q]; }
-          if(MODE == 2) { out_at = q * stride; }
+          if(MODE == 2) { out_at = mem_slot_start(begin, q, stride, shift); }
         }
       }
       next += __popc(dead);
@@ -131,7 +138,7 @@ mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const
     {
       if(depth > 0 && extended)
       {
-        if(WRITE || (MODE == 2 && emitted < stride)) { store_match(matches + 4 * (out_at + emitted), 0, depth, sp, ep); }
+        if(WRITE || (MODE == 2 && emitted < mem_slot_size(offsets[q + 1] - offsets[q], stride, shift))) { store_match(matches + 4 * (out_at + emitted), 0, depth, sp, ep); }
         emitted++;
       }
       if(!WRITE) { counts[q] = emitted; }
@@ -180,33 +187,40 @@ mem_kernel(const DevView v, const LcpView l, const u8* __restrict__ chars, const
     if(depth == 0) { pos--; continue; }
     if(extended)
     {
-      if(WRITE || (MODE == 2 && emitted < stride)) { store_match(matches + 4 * (out_at + emitted), pos - begin, depth, sp, ep); }
+      if(WRITE || (MODE == 2 && emitted < mem_slot_size(offsets[q + 1] - offsets[q], stride, shift))) { store_match(matches + 4 * (out_at + emitted), pos - begin, depth, sp, ep); }
       emitted++; extended = false;
     }
     need_parent = true;
   }
 }
 
-// scratch (stride matches per pattern) -> CSR; patterns with more than `stride` matches are listed in `overflow`
+// scratch slots -> CSR, eight lanes per pattern (a match record is 32 bytes: the eight copy 256 contiguous bytes at a
+// time); patterns with more matches than their slot holds are listed in `overflow`
 __global__ void __launch_bounds__(256)
 mem_gather_kernel(const ulonglong4* __restrict__ scratch, const u64* __restrict__ counts, const u64* __restrict__ out_offsets,
-                  u64 n, u64 stride, ulonglong4* __restrict__ matches, u64* __restrict__ overflow, ull* __restrict__ n_overflow)
+                  const u64* __restrict__ offsets, u64 char_base, u64 n, u64 stride, u32 shift,
+                  ulonglong4* __restrict__ matches, u64* __restrict__ overflow, ull* __restrict__ n_overflow)
 {
-  for(u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (u64)gridDim.x * blockDim.x)
+  const u32 sub = threadIdx.x & 7;
+  const u64 groups = ((u64)gridDim.x * blockDim.x) >> 3;
+  for(u64 q = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 3; q < n; q += groups)
   {
-    u64 c = counts[q];
-    if(c > stride) { overflow[atomicAdd(n_overflow, 1ull)] = q; continue; }
-    const ulonglong4* src = scratch + q * stride;
+    u64 c = counts[q], begin = offsets[q] - char_base, len = offsets[q + 1] - offsets[q];
+    if(c > mem_slot_size(len, stride, shift)) { if(sub == 0) { overflow[atomicAdd(n_overflow, 1ull)] = q; } continue; }
+    const ulonglong4* src = scratch + mem_slot_start(begin, q, stride, shift);
     ulonglong4* dst = matches + out_offsets[q];
-    for(u64 e = 0; e < c; e++) { dst[e] = src[e]; }
+    for(u64 e = sub; e < c; e += 8) { dst[e] = src[e]; }
   }
 }
 
 __global__ void __launch_bounds__(256)
-mem_count_overflow_kernel(const u64* __restrict__ counts, u64 n, u64 stride, ull* __restrict__ n_overflow)
+mem_count_overflow_kernel(const u64* __restrict__ counts, const u64* __restrict__ offsets, u64 n, u64 stride, u32 shift, ull* __restrict__ n_overflow)
 {
   ull mine = 0;
-  for(u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (u64)gridDim.x * blockDim.x) { mine += (counts[q] > stride ? 1 : 0); }
+  for(u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (u64)gridDim.x * blockDim.x)
+  {
+    mine += (counts[q] > mem_slot_size(offsets[q + 1] - offsets[q], stride, shift) ? 1 : 0);
+  }
   for(int d = 16; d > 0; d >>= 1) { mine += __shfl_down_sync(0xFFFFFFFFu, mine, d); }
   if((threadIdx.x & 31) == 0 && mine > 0) { atomicAdd(n_overflow, mine); }
 }

@@ -138,12 +138,31 @@ static int memDevice(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, con
   CUDA_TRY(cudaMemsetAsync(d_out_offsets, 0, (n + 1) * sizeof(u64), st));
   if(n == 0 || index->header.path_nodes == 0) { return 0; }
 
-  // scratch: up to 16 matches per pattern, fewer for huge batches, none (two full passes) if even 4 do not fit
+  // Scratch for the one-pass form: pattern q owns (len >> shift) + 4 entries of 32 bytes (device/mem.cuh), with the
+  // smallest shift in 0 .. 2 that a quarter of the free memory holds.  A pattern reports at most one match per
+  // character it consumes, so with shift = 0 (32 bytes per pattern character) no slot can overflow; with 1 or 2 the
+  // overflowing patterns are rare and redone.  Else 16 entries each, fewer for huge batches, and none (two full passes)
+  // if even 4 do not fit.  GCSA_B200_MEM_STRIDE (tests): that many entries each, 0 = two passes; GCSA_B200_MEM_SHIFT
+  // (tests, experiments): that shift.
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
-  u64 stride = std::min<u64>(16, (free_b / 8) / (n * 32));
-  if(const char* e = std::getenv("GCSA_B200_MEM_STRIDE")) { stride = std::min<u64>(stride, (u64)std::atoi(e)); }   // tests: 0 = two passes
-  if(stride < 4 && std::getenv("GCSA_B200_MEM_STRIDE") == nullptr) { stride = 0; }
+  u64 total_chars = 0;
+  CUDA_TRY(cudaMemcpyAsync(&total_chars, d_offsets + n, sizeof(u64), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  u64 stride = 4; u32 shift = 0;
+  if(const char* e = std::getenv("GCSA_B200_MEM_SHIFT")) { shift = (u32)std::min(std::max(std::atoi(e), 0), 2); }
+  auto entriesFor = [&](u32 sh) -> u64 { return (total_chars >> sh) + stride * n + 1; };
+  while(shift < 2 && entriesFor(shift) * 32 > free_b / 4) { shift++; }
+  u64 scratch_entries = entriesFor(shift);
+  const char* stride_env = std::getenv("GCSA_B200_MEM_STRIDE");
+  if(stride_env != nullptr || scratch_entries * 32 > free_b / 4)
+  {
+    shift = 63;
+    stride = std::min<u64>(16, (free_b / 8) / (n * 32));
+    if(stride_env != nullptr) { stride = std::min<u64>(stride, (u64)std::atoi(stride_env)); }
+    else if(stride < 4) { stride = 0; }
+    scratch_entries = n * stride;
+  }
 
   std::vector<void*> tmp;
   auto alloc = [&](u64 bytes) -> void* { void* p = nullptr; if(engineMallocAsync(&p, std::max<u64>(bytes, 16), st) != cudaSuccess) { cudaGetLastError(); return nullptr; } tmp.push_back(p); return p; };
@@ -153,7 +172,7 @@ static int memDevice(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, con
 
   u64* counts = (u64*)alloc((n + 1) * sizeof(u64));
   ull* n_overflow = (ull*)alloc(sizeof(ull));
-  u64* scratch = (stride > 0 ? (u64*)alloc(n * stride * 32) : nullptr);
+  u64* scratch = (stride > 0 ? (u64*)alloc(scratch_entries * 32) : nullptr);
   if(counts == nullptr || n_overflow == nullptr) { cleanup(); return fail(GCSA_B200_ERR_NOMEM, "mem_batch: out of device memory"); }
   if(scratch == nullptr) { stride = 0; }
   MEM_TRY(cudaMemsetAsync(counts, 0, (n + 1) * sizeof(u64), st));
@@ -176,15 +195,15 @@ static int memDevice(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, con
   if(const char* e = std::getenv("GCSA_B200_MEM_JUMP")) { jump = (std::atoi(e) != 0 && index->view.jump != nullptr && index->view.default_alphabet != 0); }
   if(stride > 0)
   {
-    LAUNCH_MEM(2, grid, index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, scratch, nullptr, stride, parent_batch);
+    LAUNCH_MEM(2, grid, index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, scratch, nullptr, stride, parent_batch, shift);
   }
   else
   {
-    LAUNCH_MEM(0, grid, index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, nullptr, nullptr, 0, parent_batch);
+    LAUNCH_MEM(0, grid, index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, counts, nullptr, nullptr, nullptr, 0, parent_batch, shift);
   }
   int rc = scanExclusive(counts, (u64*)d_out_offsets, n + 1, st);
   if(rc) { cleanup(); return rc; }
-  if(stride > 0) { mem_count_overflow_kernel<<<gridFor(n, index->sm_count), 256, 0, st>>>(counts, n, stride, n_overflow); }
+  if(stride > 0 && shift != 0) { mem_count_overflow_kernel<<<gridFor(n, index->sm_count), 256, 0, st>>>(counts, (const u64*)d_offsets, n, stride, shift, n_overflow); }
   u64 total = 0; ull overflowing = 0;
   MEM_TRY(cudaMemcpyAsync(&total, (u64*)d_out_offsets + n, sizeof(u64), cudaMemcpyDeviceToHost, st));
   MEM_TRY(cudaMemcpyAsync(&overflowing, n_overflow, sizeof(ull), cudaMemcpyDeviceToHost, st));
@@ -199,19 +218,19 @@ static int memDevice(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, con
   if(d_matches == nullptr || capacity < total) { cleanup(); return fail(GCSA_B200_ERR_CAPACITY, "mem_batch: output capacity too small"); }
   if(stride == 0)
   {
-    LAUNCH_MEM(1, grid, index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, nullptr, (const u64*)d_out_offsets, (u64*)d_matches, nullptr, 0, parent_batch);
+    LAUNCH_MEM(1, grid, index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, n, nullptr, (const u64*)d_out_offsets, (u64*)d_matches, nullptr, 0, parent_batch, shift);
   }
   else
   {
     u64* overflow = (u64*)alloc(std::max<u64>(overflowing, 1) * sizeof(u64));
     if(overflow == nullptr) { cleanup(); return fail(GCSA_B200_ERR_NOMEM, "mem_batch: out of device memory"); }
     MEM_TRY(cudaMemsetAsync(n_overflow, 0, sizeof(ull), st));
-    mem_gather_kernel<<<gridFor(n, index->sm_count), 256, 0, st>>>((const ulonglong4*)scratch, counts, (const u64*)d_out_offsets, n, stride,
+    mem_gather_kernel<<<gridFor(8 * n, index->sm_count), 256, 0, st>>>((const ulonglong4*)scratch, counts, (const u64*)d_out_offsets, (const u64*)d_offsets, 0, n, stride, shift,
                                                                    (ulonglong4*)d_matches, overflow, n_overflow);
     if(overflowing > 0)
     {
       LAUNCH_MEM(1, gridFor(overflowing, index->sm_count, 4), index->view, lcp->view, d_chars, (const u64*)d_offsets, 0, overflowing,
-                 nullptr, (const u64*)d_out_offsets, (u64*)d_matches, overflow, 0, parent_batch);
+                 nullptr, (const u64*)d_out_offsets, (u64*)d_matches, overflow, 0, parent_batch, shift);
     }
   }
   MEM_TRY(cudaGetLastError());

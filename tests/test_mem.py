@@ -65,7 +65,7 @@ def test_mem_scan_device_matches_definition(monkeypatch):
 @pytest.mark.engine
 def test_mem_scan_scratch_paths(monkeypatch):
     """The one-pass scan (matches staged in a per-pattern scratch slot, overflowing patterns redone), with
-    slots of 16, 4 and 1 matches, and the two-pass fallback: all equal to the definition.  Noisy patterns
+    slots that grow with the pattern (the default), slots of 16, 4 and 1 matches, and the two-pass fallback: all equal to the definition.  Noisy patterns
     (10 % substitutions) so that many patterns have more matches than a slot holds."""
     from gcsa2_b200 import GCSA, LCPArray, mem_batch, mem_device
     import torch
@@ -81,12 +81,18 @@ def test_mem_scan_scratch_paths(monkeypatch):
     counts = np.diff(ooffs.astype(np.int64))
     assert (counts > 16).sum() > 40 and (counts <= 4).sum() > 40
     gpu, glcp = GCSA(flat, kmer_table_k=0), LCPArray(flcp)
-    for stride, jump in (("16", "0"), ("4", "0"), ("1", "0"), ("0", "0"), ("4", "1"), ("0", "1")):
-        monkeypatch.setenv("GCSA_B200_MEM_STRIDE", stride)
+    assert (counts > np.diff(offsets.astype(np.int64)) // 4 + 4).sum() > 10      # ... and more than a slot that grows with the pattern
+    for stride, shift, jump in ((None, None, "0"), (None, "2", "0"), (None, "1", "0"), ("16", None, "0"), ("4", None, "0"), ("1", None, "0"), ("0", None, "0"),
+                                ("4", None, "1"), ("0", None, "1"), (None, "2", "1")):
+        # no stride: slots of (len >> shift) + 4 matches; the default shift is 0 where the memory allows it (no overflow possible)
+        for name, value in (("GCSA_B200_MEM_STRIDE", stride), ("GCSA_B200_MEM_SHIFT", shift)):
+            if value is None: monkeypatch.delenv(name, raising=False)
+            else: monkeypatch.setenv(name, value)
         monkeypatch.setenv("GCSA_B200_MEM_JUMP", jump)
         offs, vals = mem_batch(gpu, glcp, chars, offsets)
-        assert (offs == ooffs).all() and vals.shape == ovals.shape and (vals == ovals).all(), (stride, jump)
-    monkeypatch.delenv("GCSA_B200_MEM_STRIDE")
+        assert (offs == ooffs).all() and vals.shape == ovals.shape and (vals == ovals).all(), (stride, shift, jump)
+    monkeypatch.delenv("GCSA_B200_MEM_STRIDE", raising=False)
+    monkeypatch.delenv("GCSA_B200_MEM_SHIFT", raising=False)
     monkeypatch.delenv("GCSA_B200_MEM_JUMP")
     # device entry point with a caller buffer: too small -> the needed size, then the same answer
     from gcsa2_b200 import capi
