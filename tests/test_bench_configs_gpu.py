@@ -81,4 +81,15 @@ def test_config3_full_size_locate_against_the_reference():
     offsets = np.arange(200_001, dtype=np.uint64) * np.uint64(length)
     csp, cep, _ = checker.find_batch(chars[:200_000 * length], offsets, threads=threads)
     assert (csp == sp[:200_000]).all() and (cep == ep[:200_000]).all()
+    # the ranges of short patterns on the same index (tens to thousands of path nodes each): the register sort by a warp
+    # or a block == the reference's locate() on a sample, count() == the sizes, every range sorted and free of duplicates
+    for plen, nq, sample in ((10, 300_000, 20_000), (8, 60_000, 3_000), (7, 20_000, 1_000), (6, 3_000, 300)):
+        pchars, poffsets = synth.patterns_from_snp_graph(seq, sites, alt, nq, plen, seed=600 + plen)
+        psp, pep = gpu.find_batch(pchars, poffsets)
+        poffs, pvals = gpu.locate_batch(psp, pep)
+        assert (gpu.count_batch(psp, pep) == np.diff(poffs)).all()
+        inner = np.ones(pvals.size, dtype=bool); inner[poffs[:-1][np.diff(poffs) > 0].astype(np.int64)] = False      # not the first of its range
+        assert (pvals[1:][inner[1:]] > pvals[:-1][inner[1:]]).all()
+        roffs, rvals, _ = checker.locate_batch(psp[:sample], pep[:sample], threads=threads)
+        assert (poffs[:sample + 1] == roffs).all() and (pvals[:int(roffs[sample])] == rvals).all(), plen
     gpu.close()
