@@ -10,7 +10,9 @@ LCPArray <-> gcsa::LCPArray  (include/gcsa/lcp.h:90-194): parent, depth, psv/pse
 Everything here is plumbing: the work happens in libgcsa2_b200.so (CUDA, sm_100a).  There is no
 CPU implementation behind these classes; constructing one without a CUDA device raises.
 """
+import atexit
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -41,6 +43,20 @@ def range_length(rng):
     return (int(rng[1]) + 1 - int(rng[0])) & UNKNOWN
 
 
+# Handles still open when the interpreter exits are destroyed before the CUDA context goes away (objects alive at exit are
+# not guaranteed their __del__): device memory is released by the library that allocated it, and leak checkers stay quiet.
+_open_handles = weakref.WeakSet()
+
+
+@atexit.register
+def _close_open_handles():
+    for handle in list(_open_handles):
+        try:
+            handle.close()
+        except Exception:
+            pass
+
+
 class GCSA:
     def __init__(self, flat, device=0, kmer_table_k=0, two_step=None, walk_table=None, jump_table=None, fused_table=None):
         self._h = None
@@ -55,6 +71,7 @@ class GCSA:
         h = C.c_void_p()
         capi.check(L.gcsa_b200_index_create(C.byref(f), int(device), C.byref(opt), C.byref(h)))
         self._h = h
+        _open_handles.add(self)
         self.device = int(device)
         self.char2comp = np.array(flat.char2comp, dtype=np.uint8)
         self.C = np.array(flat.C, dtype=np.uint64)
@@ -384,6 +401,7 @@ class LCPArray:
         self._L = capi.lib()
         capi.check(self._L.gcsa_b200_lcp_create(C.byref(f), int(device), C.byref(h)))
         self._h = h
+        _open_handles.add(self)
         self._size, self._values = int(flat_lcp.size), int(self._offsets[int(flat_lcp.levels)])
         self._branching, self._levels = int(flat_lcp.branching), int(flat_lcp.levels)
 
