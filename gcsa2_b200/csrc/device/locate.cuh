@@ -135,6 +135,7 @@ locate_segments_kernel(const u64* __restrict__ node_off, const u64* __restrict__
 #define LOC_MED_SHORT 128               // nodes a warp sorts with at most 4 values per thread
 #define LOC_MED_WARP 1024               // nodes a warp sorts (32 values per thread)
 #define LOC_MED_BLOCK 4096              // nodes a block of 256 threads sorts (16 values per thread)
+#define LOC_MED_HUGE 16384              // nodes a block of 512 threads sorts (32 values per thread)
 
 // start positions of the nodes [s, s + len), len <= LOC_SMALL, padded with ~0; false if an entry is not direct
 __device__ __forceinline__ bool locate_small_values(const DevView& v, u64 s, u32 len, u64 (&a)[LOC_SMALL])
@@ -167,10 +168,11 @@ __device__ __forceinline__ void locate_small_sort(u64 (&a)[LOC_SMALL])
 
 // Pass 1.  cnt[i] = number of distinct positions of range i (0 for the general ranges, which are appended to
 // glist); stash[i] = the position itself when there is exactly one, LOC_TOP | list slot for a general range.
-// Ranges of LOC_SMALL + 1 .. LOC_MED_BLOCK nodes are appended to `mlist` (2 n entries) instead: those of at most
-// LOC_MED_SHORT nodes from its front, those of more than LOC_MED_WARP from the back of its first half, the others
-// from the front of its second half; they reserve their nodes' worth of the medium scratch: stash[i] = LOC_MED | offset
-// into the scratch.  counters: [0] general ranges, [1] short, [2] block-sized, [3] scratch entries reserved, [4] warp-sized.
+// Ranges of LOC_SMALL + 1 .. LOC_MED_HUGE nodes are appended to `mlist` (2 n entries) instead: those of at most
+// LOC_MED_SHORT nodes from its front, those of LOC_MED_WARP + 1 .. LOC_MED_BLOCK from the back of its first half, those of
+// at most LOC_MED_WARP from the front of its second half, the largest from its back; they reserve their nodes' worth of the
+// medium scratch: stash[i] = LOC_MED | offset into the scratch.  counters: [0] general ranges, [1] short, [2] block-sized,
+// [3] scratch entries reserved, [4] warp-sized, [5] large-block-sized.
 __global__ void __launch_bounds__(256)
 locate_small_count_kernel(const DevView v, const u64* __restrict__ sp, const u64* __restrict__ ep, u64 n,
                           u64* __restrict__ cnt, u64* __restrict__ stash, u64* __restrict__ glist, u64* __restrict__ mlist,
@@ -184,7 +186,7 @@ locate_small_count_kernel(const DevView v, const u64* __restrict__ sp, const u64
     const bool active = (i < n);
     u64 s = (active ? sp[i] : 1), e = (active ? ep[i] : 0);
     u64 c = 0, keep = 0, med_len = 0;
-    u32 kind = 0;                                                    // 1 general, 2 medium (short), 3 medium (block), 4 medium (warp)
+    u32 kind = 0;                                                    // 1 general, 2 medium (short), 3 medium (block), 4 medium (warp), 5 medium (large block)
     if(!(range_empty(s, e) || e >= v.path_nodes))                    // gcsa.cpp:831
     {
       u64 len = e + 1 - s;
@@ -206,12 +208,12 @@ locate_small_count_kernel(const DevView v, const u64* __restrict__ sp, const u64
         }
         else { kind = 1; }
       }
-      else if(medium && len <= LOC_MED_BLOCK) { kind = (len <= LOC_MED_SHORT ? 2 : (len <= LOC_MED_WARP ? 4 : 3)); med_len = len; }
+      else if(medium && len <= LOC_MED_HUGE) { kind = (len <= LOC_MED_SHORT ? 2 : (len <= LOC_MED_WARP ? 4 : (len <= LOC_MED_BLOCK ? 3 : 5))); med_len = len; }
       else { kind = 1; }
     }
     const u32 general = __ballot_sync(0xFFFFFFFFu, kind == 1);
     const u32 by_short = __ballot_sync(0xFFFFFFFFu, kind == 2), by_block = __ballot_sync(0xFFFFFFFFu, kind == 3);
-    const u32 by_warp = __ballot_sync(0xFFFFFFFFu, kind == 4);
+    const u32 by_warp = __ballot_sync(0xFFFFFFFFu, kind == 4), by_huge = __ballot_sync(0xFFFFFFFFu, kind == 5);
     const u32 below = (1u << lane) - 1;
     if(general != 0)
     {
@@ -219,7 +221,7 @@ locate_small_count_kernel(const DevView v, const u64* __restrict__ sp, const u64
       first = __shfl_sync(0xFFFFFFFFu, first, 0);
       if(kind == 1) { u64 slot = first + __popc(general & below); glist[slot] = i; keep = LOC_TOP | slot; }
     }
-    if((by_short | by_warp | by_block) != 0)
+    if((by_short | by_warp | by_block | by_huge) != 0)
     {
       u64 incl = med_len;
       #pragma unroll
@@ -229,11 +231,14 @@ locate_small_count_kernel(const DevView v, const u64* __restrict__ sp, const u64
       u64 first_s = (lane == 0 && by_short != 0 ? atomicAdd(counters + 1, (ull)__popc(by_short)) : 0);
       u64 first_b = (lane == 0 && by_block != 0 ? atomicAdd(counters + 2, (ull)__popc(by_block)) : 0);
       u64 first_w = (lane == 0 && by_warp != 0 ? atomicAdd(counters + 4, (ull)__popc(by_warp)) : 0);
+      u64 first_h = (lane == 0 && by_huge != 0 ? atomicAdd(counters + 5, (ull)__popc(by_huge)) : 0);
+      first_h = __shfl_sync(0xFFFFFFFFu, first_h, 0);
       at = __shfl_sync(0xFFFFFFFFu, at, 0); first_s = __shfl_sync(0xFFFFFFFFu, first_s, 0);
       first_b = __shfl_sync(0xFFFFFFFFu, first_b, 0); first_w = __shfl_sync(0xFFFFFFFFu, first_w, 0);
       if(kind == 2) { mlist[first_s + __popc(by_short & below)] = i; }
       if(kind == 3) { mlist[n - 1 - (first_b + __popc(by_block & below))] = i; }
       if(kind == 4) { mlist[n + first_w + __popc(by_warp & below)] = i; }
+      if(kind == 5) { mlist[2 * n - 1 - (first_h + __popc(by_huge & below))] = i; }
       if(kind >= 2) { keep = LOC_MED | (at + incl - med_len); }
     }
     if(active) { cnt[i] = c; stash[i] = keep; }
@@ -315,17 +320,23 @@ __device__ __forceinline__ void locate_bitonic_stage(u64 (&a)[E], u32 tid, u64* 
   if constexpr (J >= 32u * E)
   {
     // partner in another warp: through shared memory, element r of thread t at [r * T + t] (conflict-free)
+    // (LOC_MED_BLOCK values at a time: the 512-thread class holds four times that)
     constexpr u32 tj = J / E;
+    constexpr int R = ((u32)E * T > LOC_MED_BLOCK ? (int)(LOC_MED_BLOCK / T) : E);
     const bool keep_min = (((tid & tj) == 0) == ((tid & (KK / E)) == 0));
-    __syncthreads();
     #pragma unroll
-    for(int r = 0; r < E; r++) { exchange[r * T + tid] = a[r]; }
-    __syncthreads();
-    #pragma unroll
-    for(int r = 0; r < E; r++)
+    for(int r0 = 0; r0 < E; r0 += R)
     {
-      u64 other = exchange[r * T + (tid ^ tj)];
-      a[r] = (keep_min ? (a[r] < other ? a[r] : other) : (a[r] < other ? other : a[r]));
+      __syncthreads();
+      #pragma unroll
+      for(int r = 0; r < R; r++) { exchange[r * T + tid] = a[r0 + r]; }
+      __syncthreads();
+      #pragma unroll
+      for(int r = 0; r < R; r++)
+      {
+        u64 other = exchange[r * T + (tid ^ tj)];
+        a[r0 + r] = (keep_min ? (a[r0 + r] < other ? a[r0 + r] : other) : (a[r0 + r] < other ? other : a[r0 + r]));
+      }
     }
   }
   else if constexpr (J >= (u32)E)
@@ -440,14 +451,15 @@ __device__ __forceinline__ u32 locate_medium_range(const DevView& v, u64 s, u32 
 
 // CLASS 0: a warp per range of at most LOC_MED_SHORT nodes (few registers, many warps in flight: these are bound by
 // the latency of their loads); CLASS 1: a warp per range of at most LOC_MED_WARP nodes (up to 32 values per thread;
-// bound by the integer pipe); CLASS 2: a block of 256 threads per range of at most LOC_MED_BLOCK nodes.
+// bound by the integer pipe); CLASS 2: a block of 256 threads per range of at most LOC_MED_BLOCK nodes;
+// CLASS 3: a block of 512 threads per range of at most LOC_MED_HUGE nodes (32 values per thread).
 template<int CLASS>
-__global__ void __launch_bounds__(CLASS == 2 ? 256 : 128)
+__global__ void __launch_bounds__(CLASS == 3 ? 512 : (CLASS == 2 ? 256 : 128))
 locate_medium_kernel(const DevView v, const u64* __restrict__ sp, const u64* __restrict__ ep, const u64* __restrict__ mlist, u64 m,
                      u64* __restrict__ cnt, u64* __restrict__ stash, u64* __restrict__ scratch,
                      u64* __restrict__ glist, ull* __restrict__ n_general)
 {
-  constexpr int WARPS = (CLASS == 2 ? 8 : 1);
+  constexpr int WARPS = (CLASS == 3 ? 16 : (CLASS == 2 ? 8 : 1));
   __shared__ u64 exchange[WARPS == 1 ? 1 : LOC_MED_BLOCK];
   __shared__ u32 warp_total[WARPS + 1];
   const u32 tid = (WARPS == 1 ? threadIdx.x & 31 : threadIdx.x);
@@ -473,10 +485,15 @@ locate_medium_kernel(const DevView v, const u64* __restrict__ sp, const u64* __r
       else if(per <= 16) { c = locate_medium_range<16, WARPS>(v, s, len, tid, out, exchange, warp_total); }
       else { c = locate_medium_range<32, WARPS>(v, s, len, tid, out, exchange, warp_total); }
     }
-    else
+    else if(CLASS == 2)
     {
       if(per <= 8) { c = locate_medium_range<8, WARPS>(v, s, len, tid, out, exchange, warp_total); }
       else { c = locate_medium_range<16, WARPS>(v, s, len, tid, out, exchange, warp_total); }
+    }
+    else
+    {
+      if(per <= 16) { c = locate_medium_range<16, WARPS>(v, s, len, tid, out, exchange, warp_total); }
+      else { c = locate_medium_range<32, WARPS>(v, s, len, tid, out, exchange, warp_total); }
     }
     if(tid == 0)
     {

@@ -118,14 +118,15 @@ int locateGeneral(const gcsa_b200_index* index, const u64* d_sp, const u64* d_ep
 }
 
 // blocks of each locate_medium_kernel class that one SM holds at once
-struct MediumGrids { int per_sm[3]; };
+struct MediumGrids { int per_sm[4]; };
 MediumGrids mediumGrids()
 {
-  MediumGrids g = { { 8, 3, 2 } };
+  MediumGrids g = { { 8, 3, 2, 1 } };
   int b = 0;
   if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, locate_medium_kernel<0>, 128, 0) == cudaSuccess && b > 0) { g.per_sm[0] = b; }
   if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, locate_medium_kernel<1>, 128, 0) == cudaSuccess && b > 0) { g.per_sm[1] = b; }
   if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, locate_medium_kernel<2>, 256, 0) == cudaSuccess && b > 0) { g.per_sm[2] = b; }
+  if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, locate_medium_kernel<3>, 512, 0) == cudaSuccess && b > 0) { g.per_sm[3] = b; }
   return g;
 }
 
@@ -157,18 +158,19 @@ int locateDevice(const gcsa_b200_index* index, const u64* d_sp, const u64* d_ep,
   u64* stash = (u64*)alloc(n * sizeof(u64));
   u64* glist = (u64*)alloc(n * sizeof(u64));
   u64* mlist = (u64*)alloc(2 * n * sizeof(u64));
-  ull* d_counters = (ull*)alloc(5 * sizeof(ull));
+  ull* d_counters = (ull*)alloc(6 * sizeof(ull));
   if(!cnt || !stash || !glist || !mlist || !d_counters) { cleanup(); return fail(GCSA_B200_ERR_NOMEM, "locate: out of device memory"); }
   LOC_TRY(cudaMemsetAsync(cnt + n, 0, sizeof(u64), st));
-  LOC_TRY(cudaMemsetAsync(d_counters, 0, 5 * sizeof(ull), st));
+  LOC_TRY(cudaMemsetAsync(d_counters, 0, 6 * sizeof(ull), st));
   locate_small_count_kernel<<<gridFor(n, sm), 256, 0, st>>>(v, d_sp, d_ep, n, cnt, stash, glist, mlist, d_counters, medium);
-  ull counters[5] = { 0, 0, 0, 0, 0 };
-  LOC_TRY(cudaMemcpyAsync(counters, d_counters, 5 * sizeof(ull), cudaMemcpyDeviceToHost, st));
+  ull counters[6] = { 0, 0, 0, 0, 0, 0 };
+  LOC_TRY(cudaMemcpyAsync(counters, d_counters, 6 * sizeof(ull), cudaMemcpyDeviceToHost, st));
   LOC_TRY(cudaStreamSynchronize(st));
-  const u64 n_short = counters[1], n_block = counters[2], n_warp = counters[4];
+  const u64 n_short = counters[1], n_block = counters[2], n_warp = counters[4], n_huge = counters[5];
   const u64* short_list = mlist; const u64* block_list = mlist + (n - n_block); const u64* warp_list = mlist + n;
+  const u64* huge_list = mlist + (2 * n - n_huge);
   u64* scratch = nullptr;
-  if(n_short + n_warp + n_block > 0)
+  if(n_short + n_warp + n_block + n_huge > 0)
   {
     // the medium ranges: sorted and deduplicated in registers, a warp or a block per range; the grids are what is
     // resident at once (the groups stride over their list, so no wave is left partly filled)
@@ -190,13 +192,18 @@ int locateDevice(const gcsa_b200_index* index, const u64* d_sp, const u64* d_ep,
       u64 blocks = std::min<u64>(n_block, (u64)sm * grids.per_sm[2]);
       locate_medium_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(v, d_sp, d_ep, block_list, n_block, cnt, stash, scratch, glist, d_counters);
     }
+    if(n_huge > 0)
+    {
+      u64 blocks = std::min<u64>(n_huge, (u64)sm * grids.per_sm[3]);
+      locate_medium_kernel<3><<<(unsigned)blocks, 512, 0, st>>>(v, d_sp, d_ep, huge_list, n_huge, cnt, stash, scratch, glist, d_counters);
+    }
     LOC_TRY(cudaMemcpyAsync(counters, d_counters, sizeof(ull), cudaMemcpyDeviceToHost, st));
     LOC_TRY(cudaStreamSynchronize(st));
   }
   const ull n_general = counters[0];
   if(std::getenv("GCSA_B200_LOCATE_DEBUG") != nullptr)
   {
-    std::fprintf(stderr, "locate: of %llu ranges %llu + %llu sorted by a warp, %llu by a block, %llu through the general pipeline\n", (ull)n, (ull)n_short, (ull)n_warp, (ull)n_block, n_general);
+    std::fprintf(stderr, "locate: of %llu ranges %llu + %llu sorted by a warp, %llu + %llu by a block, %llu through the general pipeline\n", (ull)n, (ull)n_short, (ull)n_warp, (ull)n_block, (ull)n_huge, n_general);
   }
 
   u64* goffs = nullptr;
@@ -230,6 +237,7 @@ int locateDevice(const gcsa_b200_index* index, const u64* d_sp, const u64* d_ep,
     if(n_short > 0) { locate_copy_kernel<false><<<gridFor(n_short * 32, sm), 256, 0, st>>>(short_list, n_short, stash, d_out_offsets, nullptr, scratch, d_values); }
     if(n_warp > 0) { locate_copy_kernel<false><<<gridFor(n_warp * 32, sm), 256, 0, st>>>(warp_list, n_warp, stash, d_out_offsets, nullptr, scratch, d_values); }
     if(n_block > 0) { locate_copy_kernel<false><<<gridFor(n_block * 32, sm), 256, 0, st>>>(block_list, n_block, stash, d_out_offsets, nullptr, scratch, d_values); }
+    if(n_huge > 0) { locate_copy_kernel<false><<<gridFor(n_huge * 32, sm), 256, 0, st>>>(huge_list, n_huge, stash, d_out_offsets, nullptr, scratch, d_values); }
     if(n_general > 0) { locate_copy_kernel<true><<<gridFor(n_general * 32, sm), 256, 0, st>>>(glist, n_general, stash, d_out_offsets, goffs, gvals, d_values); }
   }
   LOC_TRY(cudaGetLastError());

@@ -473,8 +473,8 @@ def test_locate_short_range_path(monkeypatch):
 
 def test_locate_medium_range_path(monkeypatch):
     """locate() of ranges of tens to thousands of path nodes (what a short pattern gives): sorted and deduplicated in
-    shared memory by a warp (up to 1024 nodes) or a block (up to 4096) == the general pipeline == the oracle.  Lengths
-    on both sides of every limit (8 | 9, 32 | 33, 128 | 129, ..., 1024 | 1025, 4096 | 4097), repeats (duplicates inside a range, and
+    registers by a warp (up to 1024 nodes) or a block (up to 4096, up to 16384) == the general pipeline == the oracle.  Lengths
+    on both sides of every limit (8 | 9, 32 | 33, 128 | 129, ..., 1024 | 1025, 4096 | 4097, 16384 | 16385), repeats (duplicates inside a range, and
     nodes with several start positions, which hand the range over to the general pipeline), mixed with short, empty
     and out-of-range ranges."""
     seq = synth.random_sequence(60_000, seed=23)
@@ -485,10 +485,10 @@ def test_locate_medium_range_path(monkeypatch):
     ora = orc.OracleGCSA(flat)
     N = flat.path_nodes
     rng = np.random.default_rng(23)
-    edge = np.array([8, 9, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 2047, 2048, 2049, 4095, 4096, 4097, 5000], dtype=np.uint64)
+    edge = np.array([8, 9, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 2047, 2048, 2049, 4095, 4096, 4097, 5000, 8191, 8192, 8193, 16383, 16384, 16385, 20000], dtype=np.uint64)
     ln = np.concatenate([np.repeat(edge, 3), rng.integers(9, 200, size=300).astype(np.uint64), rng.integers(1, 9, size=200).astype(np.uint64),
                          rng.integers(200, 4200, size=40).astype(np.uint64)])
-    a = rng.integers(0, N - 5001, size=ln.size).astype(np.uint64)
+    a = rng.integers(0, N - 20001, size=ln.size).astype(np.uint64)
     sp = np.concatenate([a, np.array([5, 0, N - 3, 0], dtype=np.uint64)])
     ep = np.concatenate([a + ln - np.uint64(1), np.array([4, M64, N + 2, N - 1], dtype=np.uint64)])
     order = rng.permutation(sp.size)
@@ -500,7 +500,7 @@ def test_locate_medium_range_path(monkeypatch):
         offs, vals = gpu.locate_batch(sp, ep)
         assert (offs == want_offs).all() and (vals == want_vals).all(), medium
     monkeypatch.setenv("GCSA_B200_LOCATE_MEDIUM", "1")
-    only = np.flatnonzero((ep - sp >= 8) & (ep - sp < 4096) & (ep < N))       # a batch without short or general ranges
+    only = np.flatnonzero((ep - sp >= 8) & (ep - sp < 16384) & (ep < N))      # a batch without short or general ranges
     w_offs, w_vals, _ = ora.locate_batch(sp[only], ep[only], threads=4)
     offs, vals = gpu.locate_batch(sp[only], ep[only])
     assert (offs == w_offs).all() and (vals == w_vals).all()
