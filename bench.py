@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--locate-mbp", type=float, default=50.0, help="backbone length of the SNP-bubble graph of the locate() leg (Mbp)")
     ap.add_argument("--locate-queries", type=int, default=10_000_000, help="64-mers per GPU in the locate() leg")
     ap.add_argument("--host-builder", action="store_true", help="build the cfg2 index with the host builder (builder.cpp, ~55 s) instead of the device builder")
+    ap.add_argument("--no-wide-locate", action="store_true", help="skip locate() of the ranges of short patterns (part of the locate leg)")
     ap.add_argument("--no-mem", action="store_true", help="skip the configs[4] leg (MEM-style scan of mixed-length patterns)")
     ap.add_argument("--mem-patterns", type=int, default=4_000_000, help="patterns of the configs[4] leg, WHOLE JOB (strong scaling)")
     ap.add_argument("--mem-steps", type=int, default=3)
@@ -343,8 +344,57 @@ def locate_leg(args, rank, world, local, barrier, dist, torch, fixture):
         out["cpu_baseline"] = {"value": k / secs, "unit": "positions/s", "cores": threads, "kind": kind,
                                "sample": "locate() of the first %d ranges, %d OpenMP threads (schedule dynamic,256)" % (m, threads), "seconds": secs,
                                "parity_on_sample": bool((offs[:m + 1] == roffs).all() and (vals[:k] == rvals).all())}
+    if rank == 0 and not args.no_wide_locate:
+        out["wide_ranges"] = wide_locate(args, index, fixture, torch)
     index.close()
     return out
+
+
+def wide_locate(args, index, fixture, torch):
+    """locate() of the ranges of SHORT patterns on the configs[2] index (rank 0, device-resident): tens to thousands of path
+    nodes per range, sorted and deduplicated in registers by a warp or a block (locate_medium_kernel) instead of one
+    thread per range.  One line per pattern length, each checked against the CPU engine on a sample."""
+    from gcsa2_b200 import synth
+    seq, sites, alt, flat = fixture["seq"], fixture["sites"], fixture["alt"], fixture["flat"]
+    stream = torch.cuda.current_stream()
+    scale = max(args.locate_queries / 10_000_000.0, 0.0005)
+    lines = []
+    for plen, base_n in ((10, 1_000_000), (8, 200_000), (6, 20_000)):
+        nq = max(int(base_n * scale), 64)
+        pchars, poffsets = synth.patterns_from_snp_graph(seq, sites, alt, nq, plen, seed=600 + plen)
+        psp, pep = index.find_batch(pchars, poffsets)
+        d_sp = torch.from_numpy(psp.view(np.int64)).cuda(); d_ep = torch.from_numpy(pep.view(np.int64)).cuda()
+        d_cnt = torch.empty(nq, dtype=torch.int64, device="cuda")
+        index.count_device(d_sp, d_ep, nq, d_cnt, stream.cuda_stream); torch.cuda.synchronize()
+        total = int(d_cnt.sum().item())
+        d_offs = torch.empty(nq + 1, dtype=torch.int64, device="cuda"); d_vals = torch.empty(total + 16, dtype=torch.int64, device="cuda")
+        got = [0]
+
+        def step():
+            got[0] = index.locate_device(d_sp, d_ep, nq, d_offs, d_vals, total + 16, stream.cuda_stream)
+
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(3):
+            step()
+        e1.record(stream); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        line = {"pattern_length": plen, "ranges": nq, "path_nodes_per_range": float((pep - psp + 1).astype(np.float64).mean()),
+                "positions": got[0], "ms_per_step": ms, "value": got[0] / (ms / 1000.0), "unit": "positions/s"}
+        if not args.no_cpu_baseline:
+            engine, kind, threads = cpu_engine(flat)
+            m = min(nq, max(64, 4_000_000 // max(1, int(line["path_nodes_per_range"]))))
+            roffs, rvals, secs = engine.locate_batch(psp[:m], pep[:m], threads=threads)
+            k = int(roffs[m])
+            line["cpu_baseline"] = {"value": k / secs, "unit": "positions/s", "cores": threads, "kind": kind, "sample": "the first %d ranges" % m,
+                                    "parity_on_sample": bool(got[0] == total and (d_offs[:m + 1].cpu().numpy().view(np.uint64) == roffs).all()
+                                                             and (d_vals[:k].cpu().numpy().view(np.uint64) == rvals).all())}
+        lines.append(line)
+        del d_sp, d_ep, d_cnt, d_offs, d_vals
+    return lines
 
 
 def mem_leg(args, rank, world, local, barrier, dist, torch, fixture):

@@ -98,6 +98,9 @@ def test_bench_line_on_the_emulated_engine(monkeypatch, capsys):
     loc = line["locate"]
     assert "error" not in loc, loc
     assert loc["positions"] >= 40_000 and loc["e2e"]["matches_device_leg"] and loc["cpu_baseline"]["parity_on_sample"]
+    wide = loc["wide_ranges"]
+    assert [w["pattern_length"] for w in wide] == [10, 8, 6] and all(w["cpu_baseline"]["parity_on_sample"] and w["positions"] > 0 for w in wide)
+    assert wide[0]["path_nodes_per_range"] < wide[1]["path_nodes_per_range"] < wide[2]["path_nodes_per_range"]
 
 
 def test_smoke_on_the_emulated_engine(monkeypatch, capsys):
