@@ -33,18 +33,21 @@
 
 thread_local std::string g_last_error;
 
+namespace {
+std::mutex g_pool_mutex;
+cudaMemPool_t g_pools[64] = {};
+}
+
 cudaError_t enginePoolAlloc(void** p, size_t bytes, cudaStream_t stream)
 {
-  static std::mutex mutex;
-  static cudaMemPool_t pools[64] = {};
   int device = 0;
   cudaError_t e = cudaGetDevice(&device);
   if(e != cudaSuccess) { return e; }
   if(device < 0 || device >= 64) { return cudaErrorInvalidValue; }
   cudaMemPool_t pool = nullptr;
   {
-    std::lock_guard<std::mutex> lock(mutex);
-    if(pools[device] == nullptr)
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if(g_pools[device] == nullptr)
     {
       cudaMemPoolProps props;
       std::memset(&props, 0, sizeof(props));
@@ -52,14 +55,53 @@ cudaError_t enginePoolAlloc(void** p, size_t bytes, cudaStream_t stream)
       props.handleTypes = cudaMemHandleTypeNone;
       props.location.type = cudaMemLocationTypeDevice;
       props.location.id = device;
-      e = cudaMemPoolCreate(&pools[device], &props);
-      if(e != cudaSuccess) { pools[device] = nullptr; return e; }
+      e = cudaMemPoolCreate(&g_pools[device], &props);
+      if(e != cudaSuccess) { g_pools[device] = nullptr; return e; }
       uint64_t keep = ~0ull;      // do not hand the memory back to the driver between calls
-      cudaMemPoolSetAttribute(pools[device], cudaMemPoolAttrReleaseThreshold, &keep);
+      cudaMemPoolSetAttribute(g_pools[device], cudaMemPoolAttrReleaseThreshold, &keep);
     }
-    pool = pools[device];
+    pool = g_pools[device];
   }
   return cudaMallocFromPoolAsync(p, bytes, pool, stream);
+}
+
+// Hands the pool's idle memory of the current device back to the driver.  Called where the free memory decides what
+// gets built (index creation sizes its optional tables by it): the scratch of an earlier query batch -- the MEM-style
+// scan keeps up to a quarter of the device -- must not count as used.
+void enginePoolTrim()
+{
+  int device = 0;
+  if(cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= 64) { return; }
+  cudaMemPool_t pool = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    pool = g_pools[device];
+  }
+  if(pool == nullptr) { return; }
+  cudaDeviceSynchronize();
+  cudaMemPoolTrimTo(pool, 0);
+}
+
+// free device memory as a query batch sees it: what the driver reports plus what the pool holds idle
+size_t engineFreeMemory()
+{
+  size_t free_b = 0, total_b = 0;
+  if(cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int device = 0;
+  if(cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= 64) { return free_b; }
+  cudaMemPool_t pool = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    pool = g_pools[device];
+  }
+  if(pool != nullptr)
+  {
+    uint64_t reserved = 0, used = 0;
+    if(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+       cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used) { free_b += (size_t)(reserved - used); }
+    else { cudaGetLastError(); }
+  }
+  return free_b;
 }
 
 namespace {
@@ -200,6 +242,7 @@ int gcsa_b200_index_create(const gcsa_flat_index* host, int device, const gcsa_b
   if(device < 0 || device >= n_dev) { return fail(GCSA_B200_ERR_INVALID, "index_create: bad device ordinal"); }
   DeviceGuard guard(device);
   if(!guard.ok) { return fail(GCSA_B200_ERR_CUDA, "index_create: cudaSetDevice failed"); }
+  enginePoolTrim();           // the optional tables are sized by the free memory: scratch kept from earlier batches is free
 
   if(const char* g = std::getenv("GCSA_B200_L2_FETCH"))
   {

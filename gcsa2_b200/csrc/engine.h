@@ -48,6 +48,8 @@ inline int fail(int code, const std::string& msg) { g_last_error = msg; return c
 //------------------------------------------------------------------------------
 
 cudaError_t enginePoolAlloc(void** p, size_t bytes, cudaStream_t stream);      // engine.cu
+void enginePoolTrim();                                                         // engine.cu: idle pool memory back to the driver
+size_t engineFreeMemory();                                                     // engine.cu: free memory incl. what the pool holds idle
 template<class T> inline cudaError_t engineMallocAsync(T** p, size_t bytes, cudaStream_t stream) { return enginePoolAlloc((void**)p, bytes, stream); }
 
 //------------------------------------------------------------------------------

@@ -144,8 +144,7 @@ static int memDevice(const gcsa_b200_index* index, const gcsa_b200_lcp* lcp, con
   // overflowing patterns are rare and redone.  Else 16 entries each, fewer for huge batches, and none (two full passes)
   // if even 4 do not fit.  GCSA_B200_MEM_STRIDE (tests): that many entries each, 0 = two passes; GCSA_B200_MEM_SHIFT
   // (tests, experiments): that shift.
-  size_t free_b = 0, total_b = 0;
-  cudaMemGetInfo(&free_b, &total_b);
+  size_t free_b = engineFreeMemory();
   u64 total_chars = 0;
   CUDA_TRY(cudaMemcpyAsync(&total_chars, d_offsets + n, sizeof(u64), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));

@@ -70,7 +70,7 @@ enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cuda
 enum { cudaStreamNonBlocking = 1, cudaEventBlockingSync = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0 };
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16, cudaDevAttrMaxPersistingL2CacheSize = 108, cudaDevAttrMaxAccessPolicyWindowSize = 109 };
 enum cudaLimit { cudaLimitMaxL2FetchGranularity = 5, cudaLimitPersistingL2CacheSize = 6 };
-enum cudaMemPoolAttr { cudaMemPoolAttrReleaseThreshold = 4 };
+enum cudaMemPoolAttr { cudaMemPoolAttrReleaseThreshold = 4, cudaMemPoolAttrReservedMemCurrent = 5, cudaMemPoolAttrUsedMemCurrent = 7 };
 
 namespace emu
 {
@@ -157,6 +157,8 @@ static inline cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuc
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* pool, int) { *pool = nullptr; return cudaSuccess; }
 static inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, cudaMemPoolAttr, void*) { return cudaSuccess; }
+static inline cudaError_t cudaMemPoolGetAttribute(cudaMemPool_t, cudaMemPoolAttr, void* value) { *(uint64_t*)value = 0; return cudaSuccess; }
+static inline cudaError_t cudaMemPoolTrimTo(cudaMemPool_t, size_t) { return cudaSuccess; }
 enum { cudaMemAllocationTypePinned = 1, cudaMemHandleTypeNone = 0, cudaMemLocationTypeDevice = 1 };
 struct cudaMemPoolProps { int allocType, handleTypes; struct { int type, id; } location; };
 static inline cudaError_t cudaMemPoolCreate(cudaMemPool_t* pool, const cudaMemPoolProps*) { static int token; *pool = &token; return cudaSuccess; }
