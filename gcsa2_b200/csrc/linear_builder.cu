@@ -34,6 +34,8 @@
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
 
+void enginePoolTrim();      // engine.cu: the engine's idle scratch memory back to the driver
+
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
@@ -446,6 +448,7 @@ int buildLinear(const u8* seq, u64 L, int seq_on_device, u64 node_len, int k, in
   LB_CUDA(cudaGetDevice(&prev_device));
   LB_CUDA(cudaSetDevice(device));
   struct Restore { int d; ~Restore() { cudaSetDevice(d); } } restore = { prev_device };
+  enginePoolTrim();           // construction needs the device's memory: scratch kept from earlier query batches goes back first
   int sm_count = 148;
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
 
