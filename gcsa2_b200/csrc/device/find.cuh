@@ -566,4 +566,237 @@ find_quad_kernel(const DevView v, u32 L, const ulonglong2* __restrict__ quad_wor
   }
 }
 
+
+/*
+  The third kernel of the k-mer form, for patterns longer than the k-mer table plus one long jump (64-mers on a
+  variation graph: find_fast_kernel leaves every one of them with 30+ characters to go): the entries of the work list
+  whose range is one path node are followed to the end of their pattern here -- one jump-table entry (up to jump_k, or 4,
+  backward steps along the node's unary path) or one fused sector (a single step, where the path branches or fewer than
+  four characters are left) per round, U entries per thread with their probes issued together, straight-line and
+  predicated like find_fast_kernel: patterns of one length need about the same number of rounds, so the lanes of a warp
+  stay together, which the refill loop of the general kernel cannot offer (13 of 32 lanes active per instruction on this
+  workload).  What cannot be finished here -- a range of several nodes, a character outside ACGT, and every query that
+  is about to fail (the early-exit pair must come from the single step that fails, include/gcsa/gcsa.h:160) -- goes on to
+  the general kernel through a second work list, with the state reached so far.
+*/
+// the up to 64 characters that end at position `end` (exclusive, > 0) of pattern q, 2 bits each: lo = the last 32 (the
+// LAST one in the lowest bits), hi = the 32 before them; *good = how many, counted from the last, are usable (bases,
+// inside the pattern).  One call serves 48 or more characters of the chain.
+template<bool PACKED>
+__device__ __forceinline__ void chain_window(const u8* __restrict__ chars, u64 q, u32 L, u32 end, u64* lo, u64* hi, u32* good)
+{
+  const u32 m = (end < 64 ? end : 64);
+  *lo = 0; *hi = 0;
+  if(PACKED)
+  {
+    // characters [end - m, end) of the pattern's words (32 per word, the first one in the lowest bits), reversed
+    const unsigned long long* words = (const unsigned long long*)chars + q * (u64)((L + 31) >> 5);
+    #pragma unroll
+    for(int half = 0; half < 2; half++)
+    {
+      const u32 e2 = (half == 0 ? end : (end > 32 ? end - 32 : 0));          // this half covers [e2 - mm, e2)
+      const u32 mm = (e2 < 32 ? e2 : 32);
+      if(mm == 0) { continue; }
+      const u32 r0 = e2 - mm, sh = (r0 & 31) * 2;
+      u64 x = __ldcs(words + (r0 >> 5)) >> sh;
+      if(sh != 0 && (r0 & 31) + mm > 32) { x |= __ldcs(words + (r0 >> 5) + 1) << (64 - sh); }
+      u64 t = __brevll(x);
+      t = ((t >> 1) & 0x5555555555555555ull) | ((t & 0x5555555555555555ull) << 1);
+      t = (mm < 32 ? t >> (2 * (32 - mm)) : t);
+      if(half == 0) { *lo = t; } else { *hi = t; }
+    }
+    *good = m;
+    return;
+  }
+  const u64 last = (u64)chars + q * (u64)L + end;                // one past the last byte of the window
+  if(last - 64 < (u64)chars) { *good = 0; return; }                // would read before the buffer: left to the general kernel
+  const u64 a = last - 64; const u32 sh = (u32)(a & 7) * 8;
+  const unsigned long long* words = (const unsigned long long*)(a - (a & 7));
+  u64 w[9];
+  #pragma unroll
+  for(int i = 0; i < 8; i++) { w[i] = __ldcs(words + i); }
+  w[8] = 0;
+  if(sh != 0)
+  {
+    w[8] = __ldcs(words + 8);
+    #pragma unroll
+    for(int i = 0; i < 8; i++) { w[i] = (w[i] >> sh) | (w[i + 1] << (64 - sh)); }
+  }
+  // w[7] holds the last eight characters; usable characters are counted from there
+  u32 g = 0; bool all = true;
+  u64 packed[2] = { 0, 0 };
+  #pragma unroll
+  for(int i = 7; i >= 0; i--)
+  {
+    u32 gi;
+    u64 p = pack8_reversed(w[i], &gi);
+    packed[(7 - i) >> 2] |= p << (16 * ((7 - i) & 3));
+    if(all) { g += gi; all = (gi == 8); }
+  }
+  *lo = packed[0]; *hi = packed[1];
+  *good = (g < m ? g : m);
+}
+
+template<bool STATS, bool PACKED, int U>
+__global__ void __launch_bounds__(256, U == 4 ? 2 : (U == 2 ? 3 : 4))
+find_chain_kernel(const DevView v, const u8* __restrict__ chars, u32 L, u64* __restrict__ sp_out, u64* __restrict__ ep_out,
+                  const u64* __restrict__ work, const unsigned long long* __restrict__ work_count,
+                  u64* __restrict__ work2, unsigned long long* __restrict__ work2_count, FindStatsDev* stats)
+{
+  const u32 lane = threadIdx.x & 31;
+  const u64 n = *work_count;
+  u64 st_found = 0, st_len = 0, st_steps = 0, st_sectors = 0;
+  const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+  const u64 per_round = 32ull * U;
+  const u64 rounds = (n + n_warps * per_round - 1) / (n_warps * per_round);
+  const bool have_long = (v.jump != nullptr || v.jump_wide != nullptr);
+  for(u64 r = 0; r < rounds; r++)
+  {
+    const u64 base = (r * n_warps + warp) * per_round + lane;
+    // state of the U entries of this thread: node, characters left, the packed window [wend - 64, wend) and how many of its
+    // characters (from the end) are usable; hand != 0: the entry for the second work list
+    u64 q[U], node[U], win[U], win_hi[U], hand[U];
+    u32 rem[U], wend[U], wgood[U];
+    bool active[U], step_next[U], moved[U];
+    #pragma unroll
+    for(int j = 0; j < U; j++)
+    {
+      const u64 at = base + 32ull * j;
+      active[j] = false; step_next[j] = false; moved[j] = false; hand[j] = 0; q[j] = 0; node[j] = 0; win[j] = 0; win_hi[j] = 0; rem[j] = 0; wend[j] = 0; wgood[j] = 0;
+      if(at < n)
+      {
+        const u64 entry = work[at];
+        q[j] = entry & WORK_QUERY_MASK; rem[j] = (u32)((entry >> 48) & 0xFF);
+        if((entry & (WORK_FRESH | WORK_NO_JUMP)) != 0 || rem[j] == 0) { hand[j] = entry; }
+        else
+        {
+          const u64 s = sp_out[q[j]], e = ep_out[q[j]];
+          if(s != e) { hand[j] = entry; }
+          else { node[j] = s; active[j] = true; }
+        }
+      }
+    }
+    while(true)
+    {
+      bool any = false;
+      #pragma unroll
+      for(int j = 0; j < U; j++) { any = any || active[j]; }
+      if(!any) { break; }
+      // ---- windows: at least min(rem, 16) characters in front of the current position, or the entry is handed on ----
+      #pragma unroll
+      for(int j = 0; j < U; j++)
+      {
+        if(active[j])
+        {
+          const u32 need = (rem[j] < 16 ? rem[j] : 16);
+          if(wend[j] < rem[j] || wgood[j] < (wend[j] - rem[j]) + need)
+          {
+            chain_window<PACKED>(chars, q[j], L, rem[j], &win[j], &win_hi[j], &wgood[j]); wend[j] = rem[j];
+            if(wgood[j] < need) { active[j] = false; hand[j] = q[j] | ((u64)rem[j] << 48); }
+          }
+        }
+      }
+      // ---- one probe per entry, all issued before any is used ----
+      u64 px[U], py[U], pz[U], pw[U]; u32 kind[U];                  // kind: 0 none, 1 long jump (8 bytes), 2 wide, 3 short jump, 4 sector
+      #pragma unroll
+      for(int j = 0; j < U; j++)
+      {
+        px[j] = py[j] = pz[j] = pw[j] = 0; kind[j] = 0;
+        if(active[j])
+        {
+          if(!step_next[j] && have_long && rem[j] >= (u32)v.jump_k)
+          {
+            if(v.jump_wide != nullptr) { ulonglong2 e = __ldg(v.jump_wide + node[j]); px[j] = e.x; py[j] = e.y; kind[j] = 2; }
+            else { px[j] = __ldg(v.jump + node[j]); kind[j] = 1; }
+          }
+          else if(!step_next[j] && v.jump_short != nullptr && rem[j] >= 4) { px[j] = __ldg(v.jump_short + node[j]); kind[j] = 3; }
+          else
+          {
+            const u32 off = wend[j] - rem[j];
+            const u32 c = (u32)((off < 32 ? win[j] >> (2 * off) : win_hi[j] >> (2 * (off - 32)))) & 3;
+            const u64 b = node[j] / BWT_W;
+            ulonglong4 s4 = ld256(v.bwt + b * 4 + c);
+            px[j] = s4.x; py[j] = s4.y; pz[j] = s4.z; pw[j] = s4.w; kind[j] = 4;
+          }
+          if(STATS) { st_sectors++; }
+        }
+      }
+      // ---- resolve ----
+      #pragma unroll
+      for(int j = 0; j < U; j++)
+      {
+        if(active[j])
+        {
+          const u32 off = wend[j] - rem[j];
+          if(kind[j] == 4)
+          {
+            const u64 b = node[j] / BWT_W; const u32 o = (u32)(node[j] - b * BWT_W);
+            const bool bit = (o < 64 ? (py[j] >> o) & 1 : ((px[j] >> 40) >> (o - 64)) & 1);
+            if(!bit) { active[j] = false; hand[j] = q[j] | ((u64)rem[j] << 48) | WORK_NO_JUMP; }      // it fails here: the exact pair comes from the general kernel
+            else
+            {
+              const u32 t = popc_low88(py[j], (u32)(px[j] >> 40), o);
+              node[j] = (pz[j] & M40) + popc_low88(pw[j], (u32)(pz[j] >> 40), t + 1);
+              rem[j]--; step_next[j] = false; moved[j] = true;
+              if(STATS) { st_steps++; }
+            }
+          }
+          else
+          {
+            JumpPath path = (kind[j] == 2 ? jump_decode_wide(make_ulonglong2(px[j], py[j])) : jump_decode(px[j], v.jump_tbits));
+            if(path.len >= 2 && path.len <= rem[j])
+            {
+              // the next 32 characters of the pattern from the two window words
+              const u64 ahead = (off == 0 ? win[j] : (off < 32 ? (win[j] >> (2 * off)) | (win_hi[j] << (64 - 2 * off)) : win_hi[j] >> (2 * (off - 32))));
+              if(((ahead ^ path.chars) & ((1ull << (2 * path.len)) - 1)) == 0)
+              {
+                node[j] = path.target; rem[j] -= path.len; moved[j] = true;
+                if(STATS) { st_steps += path.len; }
+              }
+              else { active[j] = false; hand[j] = q[j] | ((u64)rem[j] << 48) | WORK_NO_JUMP; }        // it dies within these steps
+            }
+            else { step_next[j] = true; }                              // the path branches here (or is longer than what is left): one single step
+          }
+          if(active[j] && rem[j] == 0)
+          {
+            active[j] = false;
+            __stcs((unsigned long long*)sp_out + q[j], (unsigned long long)node[j]); __stcs((unsigned long long*)ep_out + q[j], (unsigned long long)node[j]);
+            if(STATS) { st_found++; st_len++; }
+          }
+        }
+      }
+    }
+    // ---- what is left goes to the second work list, with the node reached (one atomic per warp and round) ----
+    u32 todo[U]; u32 total = 0;
+    #pragma unroll
+    for(int j = 0; j < U; j++)
+    {
+      if(hand[j] != 0 && moved[j])
+      {
+        __stcs((unsigned long long*)sp_out + q[j], (unsigned long long)node[j]); __stcs((unsigned long long*)ep_out + q[j], (unsigned long long)node[j]);
+      }
+      todo[j] = __ballot_sync(0xFFFFFFFFu, hand[j] != 0);
+      total += __popc(todo[j]);
+    }
+    if(total != 0)
+    {
+      unsigned long long at = 0;
+      if(lane == 0) { at = atomicAdd(work2_count, (unsigned long long)total); }
+      at = __shfl_sync(0xFFFFFFFFu, at, 0);
+      #pragma unroll
+      for(int j = 0; j < U; j++)
+      {
+        if((todo[j] >> lane) & 1) { work2[at + __popc(todo[j] & ((1u << lane) - 1))] = hand[j]; }
+        at += __popc(todo[j]);
+      }
+    }
+  }
+  if(STATS)
+  {
+    atomicAdd((ull*)&stats->found, (ull)st_found); atomicAdd((ull*)&stats->total_length, (ull)st_len);
+    atomicAdd((ull*)&stats->lf_steps, (ull)st_steps); atomicAdd((ull*)&stats->sector_probes, (ull)st_sectors);
+  }
+}
+
 #endif

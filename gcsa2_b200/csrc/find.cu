@@ -35,19 +35,34 @@ static int launchFind(const gcsa_b200_index* index, const u8* d_chars, const u64
     // work list of the general kernel (8 bytes per entry), work list of the quad kernel (16), the two counters
     const bool use_quads = (v.jump_wide != nullptr || v.jump != nullptr);
     // (the 16-byte entries first: the allocation is aligned, the end of an odd number of 8-byte entries is not)
+    // Patterns with more to go than one long jump after the table: the singleton entries of the work list are followed by
+    // find_chain_kernel, which leaves a second work list to the general kernel (GCSA_B200_FIND_CHAIN=0: straight to it).
+    static const bool chain_off = []() { const char* e = std::getenv("GCSA_B200_FIND_CHAIN"); return (e != nullptr && std::atoi(e) == 0); }();
+    const u64 one_jump = (u64)v.table_k + (use_quads ? (u64)v.jump_k : 0);
+    const bool use_chain = (!chain_off && fixed_length > one_jump);
     u64* buffer = nullptr;
-    CUDA_TRY(engineMallocAsync(&buffer, n * sizeof(u64) * (use_quads ? 3 : 1) + 256, stream));
+    CUDA_TRY(engineMallocAsync(&buffer, n * sizeof(u64) * ((use_quads ? 3 : 1) + (use_chain ? 1 : 0)) + 256, stream));
     ulonglong2* quad_work = (use_quads ? (ulonglong2*)buffer : nullptr);
     u64* work = buffer + (use_quads ? 2 * n : 0);
-    unsigned long long* count = (unsigned long long*)(work + n);
+    u64* work2 = (use_chain ? work + n : nullptr);
+    unsigned long long* count = (unsigned long long*)(work + (use_chain ? 2 * n : n));
     unsigned long long* quad_count = count + 1;
-    cudaError_t e = cudaMemsetAsync(count, 0, 2 * sizeof(unsigned long long), stream);
+    unsigned long long* count2 = count + 2;
+    const u64* last_work = (use_chain ? work2 : work); const unsigned long long* last_count = (use_chain ? count2 : count);
+    cudaError_t e = cudaMemsetAsync(count, 0, 4 * sizeof(unsigned long long), stream);
     if(e == cudaSuccess)
     {
       // queries per thread and round in the first kernel (GCSA_B200_FIND_UNROLL = 1, 2 or 4: measured in DESIGN.md)
       static const int unroll = []() { const char* e = std::getenv("GCSA_B200_FIND_UNROLL"); int u = (e ? std::atoi(e) : 4); return (u == 1 || u == 2 ? u : 4); }();
       int fast_grid = gridFor((n + unroll - 1) / unroll, index->sm_count, 8);
       int slow_grid = gridFor(n, index->sm_count, d_stats ? 1 : 4);
+      // entries per thread and round in the chain kernel (GCSA_B200_CHAIN_UNROLL = 1, 2 or 4)
+      static const int chain_unroll = []() { const char* e = std::getenv("GCSA_B200_CHAIN_UNROLL"); int u = (e ? std::atoi(e) : 1); return (u == 2 || u == 4 ? u : 1); }();
+      int chain_grid = gridFor((n + chain_unroll - 1) / chain_unroll, index->sm_count, chain_unroll == 4 ? 2 : (chain_unroll == 2 ? 3 : 4));
+      #define LAUNCH_CHAIN(S, P) do { \
+        if(chain_unroll == 1) { find_chain_kernel<S, P, 1><<<chain_grid, 256, 0, stream>>>(v, d_chars, L, d_sp, d_ep, work, count, work2, count2, d_stats); } \
+        else if(chain_unroll == 2) { find_chain_kernel<S, P, 2><<<chain_grid, 256, 0, stream>>>(v, d_chars, L, d_sp, d_ep, work, count, work2, count2, d_stats); } \
+        else { find_chain_kernel<S, P, 4><<<chain_grid, 256, 0, stream>>>(v, d_chars, L, d_sp, d_ep, work, count, work2, count2, d_stats); } } while(0)
       const u32 L = (u32)fixed_length;
       #define LAUNCH_FAST(S, P, U) find_fast_kernel<S, P, U><<<fast_grid, 256, 0, stream>>>(v, d_chars, L, n, d_sp, d_ep, work, count, quad_work, quad_count, d_stats)
       #define LAUNCH_FAST_U(S, P) do { if(unroll == 1) { LAUNCH_FAST(S, P, 1); } else if(unroll == 2) { LAUNCH_FAST(S, P, 2); } else { LAUNCH_FAST(S, P, 4); } } while(0)
@@ -55,17 +70,26 @@ static int launchFind(const gcsa_b200_index* index, const u8* d_chars, const u64
       {
         if(packed) { LAUNCH_FAST(true, true, 4); } else { LAUNCH_FAST(true, false, 4); }
         if(use_quads) { find_quad_kernel<true><<<gridFor(n, index->sm_count, 8), 256, 0, stream>>>(v, L, quad_work, quad_count, d_sp, d_ep, work, count, d_stats); }
-        if(packed) { find_kernel<true, 1, true, true><<<slow_grid, 256, 0, stream>>>(v, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, d_stats, refill_at, work, count); }
-        else { find_kernel<true, 1, false, true><<<slow_grid, 256, 0, stream>>>(v, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, d_stats, refill_at, work, count); }
+        if(use_chain)
+        {
+          if(packed) { LAUNCH_CHAIN(true, true); } else { LAUNCH_CHAIN(true, false); }
+        }
+        if(packed) { find_kernel<true, 1, true, true><<<slow_grid, 256, 0, stream>>>(v, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, d_stats, refill_at, last_work, last_count); }
+        else { find_kernel<true, 1, false, true><<<slow_grid, 256, 0, stream>>>(v, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, d_stats, refill_at, last_work, last_count); }
       }
       else
       {
         if(packed) { LAUNCH_FAST_U(false, true); } else { LAUNCH_FAST_U(false, false); }
         if(use_quads) { find_quad_kernel<false><<<gridFor(n, index->sm_count, 8), 256, 0, stream>>>(v, L, quad_work, quad_count, d_sp, d_ep, work, count, nullptr); }
-        if(packed) { find_kernel<false, 4, true, true><<<slow_grid, 256, 0, stream>>>(v, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, nullptr, refill_at, work, count); }
-        else { find_kernel<false, 4, false, true><<<slow_grid, 256, 0, stream>>>(v, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, nullptr, refill_at, work, count); }
+        if(use_chain)
+        {
+          if(packed) { LAUNCH_CHAIN(false, true); } else { LAUNCH_CHAIN(false, false); }
+        }
+        if(packed) { find_kernel<false, 4, true, true><<<slow_grid, 256, 0, stream>>>(v, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, nullptr, refill_at, last_work, last_count); }
+        else { find_kernel<false, 4, false, true><<<slow_grid, 256, 0, stream>>>(v, d_chars, nullptr, 0, fixed_length, n, d_sp, d_ep, nullptr, refill_at, last_work, last_count); }
       }
       #undef LAUNCH_FAST_U
+      #undef LAUNCH_CHAIN
       #undef LAUNCH_FAST
       e = cudaGetLastError();
     }

@@ -660,8 +660,8 @@ def test_custom_alphabet_takes_the_general_path():
 
 
 def test_kmer_batches_two_kernel_form(monkeypatch):
-    """Batches of k-mers (one length <= 32, at least 4096 of them) go through find_fast_kernel + the work list resumed by
-    the general kernel; they must equal the oracle and the single general kernel (GCSA_B200_FIND_FAST=0 is read once
+    """Batches of k-mers (one length, at least 4096 of them) go through find_fast_kernel, find_quad_kernel, find_chain_kernel
+    (patterns longer than the table plus one long jump) + the work list resumed by the general kernel; they must equal the oracle and the single general kernel (GCSA_B200_FIND_FAST=0 is read once
     per process, so the general kernel is reached through the offsets form of the same patterns).  Every table shape:
     fused and plain entries, 8- and 16-byte jump entries, no jump table, two-step blocks; lengths equal to k, between
     k and k + a path, 32; substitutions (a jump that fails on a character), N, lower case, random patterns (misses in
@@ -710,6 +710,9 @@ def test_kmer_batches_two_kernel_form(monkeypatch):
                 assert (gsp == osp).all() and (gep == oep).all(), (name, L, options)
                 ssp, sep, st = gpu.find_batch(c, o, stats=True)
                 assert (ssp == osp).all() and (sep == oep).all() and st["queries"] == n
+                fsp, fep, fst = gpu.find_fixed_batch(c, L, stats=True)   # the counting variants of the k-mer form's kernels
+                assert (fsp == osp).all() and (fep == oep).all() and fst["queries"] == n and fst["found"] == st["found"], (name, L, options, fst, st)
+                assert fst["total_length"] == st["total_length"]
                 gpu.close()
 
 
