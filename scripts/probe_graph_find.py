@@ -39,6 +39,17 @@ def main():
         e1.record(stream); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
         print("kmer_table_k", k, "ms", ms, "queries/s", n / ms * 1e3, "range length mean", float((ep - sp + 1).mean()), flush=True)
+        # the same patterns through the general kernel alone (the offsets form)
+        d_off = torch.arange(n + 1, dtype=torch.int64, device="cuda") * length
+        for _ in range(3):
+            index.find_device(d_chars, d_off, n, d_sp, d_ep, stream.cuda_stream)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(5):
+            index.find_device(d_chars, d_off, n, d_sp, d_ep, stream.cuda_stream)
+        e1.record(stream); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print("kmer_table_k", k, "general kernel alone: ms", ms, "queries/s", n / ms * 1e3, flush=True)
         index.close()
 
 
