@@ -707,6 +707,15 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        # The timed region is a few milliseconds and nvidia-smi reports every 100 ms: the same step keeps the GPU under the
+        # same load (untimed) until two samples are in, and again after the timed steps until one more is, so that the
+        # clocks line describes the load the timed steps ran under.
+        t_load = time.perf_counter()
+        while len(sampler.lines) < 2 and time.perf_counter() - t_load < 2.0:
+            for _ in range(20):
+                step_device()
+            torch.cuda.synchronize()
+    fast_before = fast_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); barrier()
     ev0.record(stream)
@@ -715,9 +724,16 @@ def main():
     ev1.record(stream)
     torch.cuda.synchronize(); barrier()
     ms_total = ev0.elapsed_time(ev1)
+    fast_after = fast_launches()
+    if rank == 0:
+        seen, t_load = len(sampler.lines), time.perf_counter()
+        while len(sampler.lines) <= seen and time.perf_counter() - t_load < 0.5:
+            for _ in range(20):
+                step_device()
+            torch.cuda.synchronize()
     # kernels of this library launched inside the timed region: a batch in the k-mer form is three launches
     # (find_fast_kernel, find_quad_kernel, find_kernel over the work list), any other batch one (find_kernel)
-    fast_steps = int(fast_launches() - fast_before)
+    fast_steps = int(fast_after - fast_before)
     gpu_launches = 3 * fast_steps + (args.steps - fast_steps)
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
