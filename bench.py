@@ -251,11 +251,21 @@ def locate_leg(args, rank, world, local, barrier, dist, torch, fixture):
         m = min(1_000_000, n - q0)
         c, _ = synth.patterns_from_snp_graph(seq, sites, alt, m, length, seed=7000 + 100 * rank + i)
         chars[q0 * length:(q0 + m) * length] = c
-    index = GCSA(flat, device=local, kmer_table_k=min(12, args.kmer_table_k))     # find() is untimed here
+    index = GCSA(flat, device=local, kmer_table_k=min(14, args.kmer_table_k))     # (4^14 entries: most 14-mers of this graph are one path node)
     stream = torch.cuda.current_stream()
     d_chars = torch.from_numpy(chars).cuda()
     d_sp = torch.empty(n, dtype=torch.int64, device="cuda"); d_ep = torch.empty_like(d_sp)
-    index.find_fixed_device(d_chars, length, n, d_sp, d_ep, stream.cuda_stream)
+    # find() of the 64-mers: timed on its own (not part of the locate metric) -- the k-mer form with the chain kernel
+    for _ in range(3):
+        index.find_fixed_device(d_chars, length, n, d_sp, d_ep, stream.cuda_stream)
+    torch.cuda.synchronize(); barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for _ in range(3):
+        index.find_fixed_device(d_chars, length, n, d_sp, d_ep, stream.cuda_stream)
+    f1.record(stream)
+    torch.cuda.synchronize()
+    find_ms = f0.elapsed_time(f1) / 3
     d_cnt = torch.empty(n, dtype=torch.int64, device="cuda")
     index.count_device(d_sp, d_ep, n, d_cnt, stream.cuda_stream)
     torch.cuda.synchronize()
@@ -314,7 +324,10 @@ def locate_leg(args, rank, world, local, barrier, dist, torch, fixture):
            "e2e": {"value": positions / (e2e_ms / 1000.0), "unit": "positions/s", "ms_per_step": e2e_ms,
                    "h2d_bytes_per_step": int(16 * n), "d2h_bytes_per_step": int(8 * (n + 1) + 8 * got[0]),
                    "api": "gcsa_b200_locate_into_host (pinned host buffers, chunked H2D/locate/D2H pipeline)", "matches_device_leg": same},
-           "setup": {"index_build_s": build_s}}
+           "setup": {"index_build_s": build_s},
+           "find": {"ms_per_step": find_ms, "value": n / (find_ms / 1000.0), "unit": "queries/s per GPU (rank 0)",
+                    "note": "find() of the same 64-mers, device-resident, timed separately: find_fast_kernel + find_quad_kernel + find_chain_kernel + "
+                            "find_kernel over the second work list; kmer_table_k = %d" % min(14, args.kmer_table_k)}}
     if rank == 0:
         # SURVEY.md 8(d), locate: per located node one probe of the locate table (64 B), per range 16 B in and 8 B of
         # offsets out, per position 8 B out.  (locate_small_count / fill read the table once per node: every 64-mer of
