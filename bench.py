@@ -326,8 +326,8 @@ def locate_leg(args, rank, world, local, barrier, dist, torch, fixture):
                    "api": "gcsa_b200_locate_into_host (pinned host buffers, chunked H2D/locate/D2H pipeline)", "matches_device_leg": same},
            "setup": {"index_build_s": build_s},
            "find": {"ms_per_step": find_ms, "value": n / (find_ms / 1000.0), "unit": "queries/s per GPU (rank 0)",
-                    "note": "find() of the same 64-mers, device-resident, timed separately: find_fast_kernel + find_quad_kernel + find_chain_kernel + "
-                            "find_kernel over the second work list; kmer_table_k = %d" % min(14, args.kmer_table_k)}}
+                    "note": "find() of the same 64-mers, device-resident, timed separately: find_chain_kernel (table probe, then one jump entry or one "
+                            "sector per round) + find_kernel over its work list; kmer_table_k = %d" % min(14, args.kmer_table_k)}}
     if rank == 0:
         # SURVEY.md 8(d), locate: per located node one probe of the locate table (64 B), per range 16 B in and 8 B of
         # offsets out, per position 8 B out.  (locate_small_count / fill read the table once per node: every 64-mer of

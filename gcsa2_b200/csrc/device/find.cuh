@@ -583,14 +583,15 @@ find_quad_kernel(const DevView v, u32 L, const ulonglong2* __restrict__ quad_wor
 // LAST one in the lowest bits), hi = the 32 before them; *good = how many, counted from the last, are usable (bases,
 // inside the pattern).  One call serves 48 or more characters of the chain.
 template<bool PACKED>
-__device__ __forceinline__ void chain_window(const u8* __restrict__ chars, u64 q, u32 L, u32 end, u64* lo, u64* hi, u32* good)
+__device__ __forceinline__ void chain_window(const u8* __restrict__ chars, u64 origin, u32 end, u64* lo, u64* hi, u32* good)
 {
+  // origin: index of the pattern's first byte (PACKED: of its first 8-byte word)
   const u32 m = (end < 64 ? end : 64);
   *lo = 0; *hi = 0;
   if(PACKED)
   {
     // characters [end - m, end) of the pattern's words (32 per word, the first one in the lowest bits), reversed
-    const unsigned long long* words = (const unsigned long long*)chars + q * (u64)((L + 31) >> 5);
+    const unsigned long long* words = (const unsigned long long*)chars + origin;
     #pragma unroll
     for(int half = 0; half < 2; half++)
     {
@@ -608,7 +609,7 @@ __device__ __forceinline__ void chain_window(const u8* __restrict__ chars, u64 q
     *good = m;
     return;
   }
-  const u64 last = (u64)chars + q * (u64)L + end;                // one past the last byte of the window
+  const u64 last = (u64)chars + origin + end;                    // one past the last byte of the window
   if(last - 64 < (u64)chars) { *good = 0; return; }                // would read before the buffer: left to the general kernel
   const u64 a = last - 64; const u32 sh = (u32)(a & 7) * 8;
   const unsigned long long* words = (const unsigned long long*)(a - (a & 7));
@@ -637,15 +638,19 @@ __device__ __forceinline__ void chain_window(const u8* __restrict__ chars, u64 q
   *good = (g < m ? g : m);
 }
 
-template<bool STATS, bool PACKED, int U>
+// FRESH: no first kernel and no input work list -- the patterns are those of the offsets form (any lengths): each entry
+// starts with the k-mer table probe of its last characters and goes on as above.  Patterns shorter than the table or
+// longer than 255 characters, table escapes and characters outside ACGT go to the general kernel as FRESH entries.
+template<bool STATS, bool PACKED, int U, bool FRESH = false>
 __global__ void __launch_bounds__(256, U == 4 ? 2 : (U == 2 ? 3 : 4))
 find_chain_kernel(const DevView v, const u8* __restrict__ chars, u32 L, u64* __restrict__ sp_out, u64* __restrict__ ep_out,
                   const u64* __restrict__ work, const unsigned long long* __restrict__ work_count,
-                  u64* __restrict__ work2, unsigned long long* __restrict__ work2_count, FindStatsDev* stats)
+                  u64* __restrict__ work2, unsigned long long* __restrict__ work2_count, FindStatsDev* stats,
+                  u32 straggle, const u64* __restrict__ offsets = nullptr, u64 char_base = 0, u64 n_fresh = 0)
 {
   const u32 lane = threadIdx.x & 31;
-  const u64 n = *work_count;
-  u64 st_found = 0, st_len = 0, st_steps = 0, st_sectors = 0;
+  const u64 n = (FRESH ? n_fresh : *work_count);
+  u64 st_found = 0, st_len = 0, st_steps = 0, st_sectors = 0, st_hits = 0;
   const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
   const u64 per_round = 32ull * U;
@@ -656,7 +661,7 @@ find_chain_kernel(const DevView v, const u8* __restrict__ chars, u32 L, u64* __r
     const u64 base = (r * n_warps + warp) * per_round + lane;
     // state of the U entries of this thread: node, characters left, the packed window [wend - 64, wend) and how many of its
     // characters (from the end) are usable; hand != 0: the entry for the second work list
-    u64 q[U], node[U], win[U], win_hi[U], hand[U];
+    u64 q[U], node[U], win[U], win_hi[U], hand[U], origin[U];
     u32 rem[U], wend[U], wgood[U];
     bool active[U], step_next[U], moved[U];
     #pragma unroll
@@ -664,10 +669,80 @@ find_chain_kernel(const DevView v, const u8* __restrict__ chars, u32 L, u64* __r
     {
       const u64 at = base + 32ull * j;
       active[j] = false; step_next[j] = false; moved[j] = false; hand[j] = 0; q[j] = 0; node[j] = 0; win[j] = 0; win_hi[j] = 0; rem[j] = 0; wend[j] = 0; wgood[j] = 0;
-      if(at < n)
+      origin[j] = 0;
+      if(FRESH)
+      {
+        if(at < n)
+        {
+          q[j] = at;
+          // (patterns of one length L without an offsets array: pattern q starts at q * L)
+          const u64 b = (offsets != nullptr ? offsets[at] - char_base : at * (u64)L);
+          const u64 len = (offsets != nullptr ? offsets[at + 1] - offsets[at] : (u64)L);
+          origin[j] = b;
+          const u32 k = (u32)v.table_k;
+          if(len == 0 || v.path_nodes == 0)                                // gcsa.h:99: the empty pattern matches everything
+          {
+            __stcs((unsigned long long*)sp_out + at, 0ull); __stcs((unsigned long long*)ep_out + at, (unsigned long long)(v.path_nodes - 1));
+            if(STATS && v.path_nodes != 0) { st_found++; st_len += v.path_nodes; }
+          }
+          else if(len > 255 || len < k) { hand[j] = at | WORK_FRESH; }
+          else
+          {
+            chain_window<PACKED>(chars, b, (u32)len, &win[j], &win_hi[j], &wgood[j]); wend[j] = (u32)len;
+            if(wgood[j] < k) { hand[j] = at | WORK_FRESH; }
+            else
+            {
+              const u64 idx = win[j] & (k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1));
+              u64 res, fused_jump = 0;
+              if(v.table2 != nullptr) { ulonglong2 both = __ldg(v.table2 + idx); res = both.x; fused_jump = both.y; }
+              else { res = __ldg(v.table + idx); }
+              const u64 cnt = res >> 40;
+              if(STATS) { st_hits++; }
+              if(cnt == TABLE_ESCAPE) { hand[j] = at | WORK_FRESH; }
+              else
+              {
+                const u64 s = res & M40, e = s + cnt - 1;
+                rem[j] = (u32)len - k;
+                if(cnt == 1 && rem[j] > 0)
+                {
+                  node[j] = s; active[j] = true; moved[j] = true;
+                  // fused table: the long jump entry of the node came with the same load -- the first jump costs no probe
+                  if(fused_jump != 0)
+                  {
+                    JumpPath path = jump_decode(fused_jump, v.jump_tbits);
+                    if(path.len >= 2 && path.len <= rem[j] && k + path.len <= wgood[j] && k + path.len <= 32)
+                    {
+                      if((((win[j] >> (2 * k)) ^ path.chars) & ((1ull << (2 * path.len)) - 1)) == 0)
+                      {
+                        node[j] = path.target; rem[j] -= path.len;
+                        if(STATS) { st_steps += path.len; }
+                        if(rem[j] == 0)
+                        {
+                          active[j] = false;
+                          __stcs((unsigned long long*)sp_out + at, (unsigned long long)node[j]); __stcs((unsigned long long*)ep_out + at, (unsigned long long)node[j]);
+                          if(STATS) { st_found++; st_len++; }
+                        }
+                      }
+                      else { active[j] = false; hand[j] = at | ((u64)rem[j] << 48) | WORK_NO_JUMP; }
+                    }
+                  }
+                }
+                else
+                {
+                  __stcs((unsigned long long*)sp_out + at, (unsigned long long)s); __stcs((unsigned long long*)ep_out + at, (unsigned long long)e);
+                  if(cnt >= 2 && rem[j] > 0) { hand[j] = at | ((u64)rem[j] << 48); }
+                  else if(STATS && cnt >= 1) { st_found++; st_len += cnt; }
+                }
+              }
+            }
+          }
+        }
+      }
+      else if(at < n)
       {
         const u64 entry = work[at];
         q[j] = entry & WORK_QUERY_MASK; rem[j] = (u32)((entry >> 48) & 0xFF);
+        origin[j] = (PACKED ? q[j] * (u64)((L + 31) >> 5) : q[j] * (u64)L);
         if((entry & (WORK_FRESH | WORK_NO_JUMP)) != 0 || rem[j] == 0) { hand[j] = entry; }
         else
         {
@@ -682,7 +757,20 @@ find_chain_kernel(const DevView v, const u8* __restrict__ chars, u32 L, u64* __r
       bool any = false;
       #pragma unroll
       for(int j = 0; j < U; j++) { any = any || active[j]; }
-      if(!any) { break; }
+      // (warp-uniform loop: the lanes leave together.)  Once fewer than `straggle` lanes of the warp still have an entry to
+      // follow -- the long patterns of a batch of mixed lengths, the queries that met several branches -- those go on to the
+      // general kernel with what they have reached: its refill loop keeps every lane busy, these rounds would not.
+      const u32 busy = __ballot_sync(0xFFFFFFFFu, any);
+      if(busy == 0) { break; }
+      if((u32)__popc(busy) < straggle)
+      {
+        #pragma unroll
+        for(int j = 0; j < U; j++)
+        {
+          if(active[j]) { active[j] = false; hand[j] = q[j] | ((u64)rem[j] << 48); }
+        }
+        break;
+      }
       // ---- windows: at least min(rem, 16) characters in front of the current position, or the entry is handed on ----
       #pragma unroll
       for(int j = 0; j < U; j++)
@@ -692,7 +780,7 @@ find_chain_kernel(const DevView v, const u8* __restrict__ chars, u32 L, u64* __r
           const u32 need = (rem[j] < 16 ? rem[j] : 16);
           if(wend[j] < rem[j] || wgood[j] < (wend[j] - rem[j]) + need)
           {
-            chain_window<PACKED>(chars, q[j], L, rem[j], &win[j], &win_hi[j], &wgood[j]); wend[j] = rem[j];
+            chain_window<PACKED>(chars, origin[j], rem[j], &win[j], &win_hi[j], &wgood[j]); wend[j] = rem[j];
             if(wgood[j] < need) { active[j] = false; hand[j] = q[j] | ((u64)rem[j] << 48); }
           }
         }
@@ -796,6 +884,7 @@ find_chain_kernel(const DevView v, const u8* __restrict__ chars, u32 L, u64* __r
   {
     atomicAdd((ull*)&stats->found, (ull)st_found); atomicAdd((ull*)&stats->total_length, (ull)st_len);
     atomicAdd((ull*)&stats->lf_steps, (ull)st_steps); atomicAdd((ull*)&stats->sector_probes, (ull)st_sectors);
+    if(FRESH) { atomicAdd((ull*)&stats->table_hits, (ull)st_hits); }
   }
 }
 

@@ -25,10 +25,49 @@ static int launchFind(const gcsa_b200_index* index, const u8* d_chars, const u64
   int grid = gridFor(n, index->sm_count, per_sm);
   // idle lanes of a warp are refilled together once this many are idle (16 measured best: DESIGN.md)
   static const int refill_at = []() { const char* e = std::getenv("GCSA_B200_FIND_REFILL"); int r = (e ? std::atoi(e) : 16); return std::min(32, std::max(1, r)); }();
-  // Batches of k-mers (one length, at least the k-mer table's, the default alphabet): the two-kernel form -- one
-  // probe (or two) per thread for everything, then the general kernel for the work list of what that left unfinished.
+  // chain kernel: a warp hands its last entries on to the general kernel once fewer than this many of its lanes are busy
+  // (off: measured on 64-mers and on mixed lengths 16..256, 4 M queries on a 20 Mbp graph, thresholds 0 / 8 / 16 / 24:
+  // 1.08 / 1.14 / 1.17 / 1.52 ms and 1.04 / 0.99 / 0.94 / 0.96 ms -- what the mixed batch gains the uniform one loses)
+  static const u32 straggle = []() { const char* e = std::getenv("GCSA_B200_CHAIN_STRAGGLE"); int t = (e ? std::atoi(e) : 0); return (u32)std::min(32, std::max(0, t)); }();
   static const bool fast_off = []() { const char* e = std::getenv("GCSA_B200_FIND_FAST"); return (e != nullptr && std::atoi(e) == 0); }();
   const DevView& v = index->view;
+  // Batches of patterns of any lengths (the offsets form), and of one length beyond the k-mer table plus one long jump: the
+  // chain kernel starts every pattern from the k-mer table and follows single path nodes to the end; the general kernel
+  // finishes what that leaves (GCSA_B200_FIND_CHAIN_OFFSETS=0: the general kernel alone, or the k-mer form below).  4 M
+  // 64-mers on the configs[2] graph: 0.95 ms this way, 1.09 ms through the k-mer form, 1.33 ms through the general kernel.
+  static const bool chain_offsets_off = []() { const char* e = std::getenv("GCSA_B200_FIND_CHAIN_OFFSETS"); return (e != nullptr && std::atoi(e) == 0); }();
+  const u64 one_long_jump = (u64)v.table_k + ((v.jump_wide != nullptr || v.jump != nullptr) ? (u64)v.jump_k : 0);
+  const bool long_fixed = (d_offsets == nullptr && fixed_length > one_long_jump && fixed_length <= 255);
+  if(!fast_off && !chain_offsets_off && !packed && (d_offsets != nullptr || long_fixed) && v.table_k > 0 && v.default_alphabet != 0 && n >= 4096 && n < (1ull << 47))
+  {
+    u64* buffer = nullptr;
+    CUDA_TRY(engineMallocAsync(&buffer, n * sizeof(u64) + 256, stream));
+    u64* work = buffer;
+    unsigned long long* count = (unsigned long long*)(work + n);
+    cudaError_t e = cudaMemsetAsync(count, 0, 2 * sizeof(unsigned long long), stream);
+    if(e == cudaSuccess)
+    {
+      int chain_grid = gridFor(n, index->sm_count, 4);
+      int slow_grid = gridFor(n, index->sm_count, d_stats ? 1 : 4);
+      if(d_stats)
+      {
+        find_chain_kernel<true, false, 1, true><<<chain_grid, 256, 0, stream>>>(v, d_chars, (u32)fixed_length, d_sp, d_ep, nullptr, nullptr, work, count, d_stats, straggle, d_offsets, char_base, n);
+        find_kernel<true, 1, false, true><<<slow_grid, 256, 0, stream>>>(v, d_chars, d_offsets, char_base, fixed_length, n, d_sp, d_ep, d_stats, refill_at, work, count);
+      }
+      else
+      {
+        find_chain_kernel<false, false, 1, true><<<chain_grid, 256, 0, stream>>>(v, d_chars, (u32)fixed_length, d_sp, d_ep, nullptr, nullptr, work, count, nullptr, straggle, d_offsets, char_base, n);
+        find_kernel<false, 4, false, true><<<slow_grid, 256, 0, stream>>>(v, d_chars, d_offsets, char_base, fixed_length, n, d_sp, d_ep, nullptr, refill_at, work, count);
+      }
+      e = cudaGetLastError();
+    }
+    cudaFreeAsync(buffer, stream);
+    CUDA_TRY(e);
+    if(long_fixed) { g_fast_launches.fetch_add(1); }
+    return 0;
+  }
+  // Batches of k-mers (one length, at least the k-mer table's, the default alphabet): the two-kernel form -- one
+  // probe (or two) per thread for everything, then the general kernel for the work list of what that left unfinished.
   if(!fast_off && d_offsets == nullptr && fixed_length <= 255 && v.table_k > 0 && fixed_length >= (u64)v.table_k &&
      (packed || v.default_alphabet != 0) && n >= 4096 && n < (1ull << 47))
   {
@@ -60,9 +99,9 @@ static int launchFind(const gcsa_b200_index* index, const u8* d_chars, const u64
       static const int chain_unroll = []() { const char* e = std::getenv("GCSA_B200_CHAIN_UNROLL"); int u = (e ? std::atoi(e) : 1); return (u == 2 || u == 4 ? u : 1); }();
       int chain_grid = gridFor((n + chain_unroll - 1) / chain_unroll, index->sm_count, chain_unroll == 4 ? 2 : (chain_unroll == 2 ? 3 : 4));
       #define LAUNCH_CHAIN(S, P) do { \
-        if(chain_unroll == 1) { find_chain_kernel<S, P, 1><<<chain_grid, 256, 0, stream>>>(v, d_chars, L, d_sp, d_ep, work, count, work2, count2, d_stats); } \
-        else if(chain_unroll == 2) { find_chain_kernel<S, P, 2><<<chain_grid, 256, 0, stream>>>(v, d_chars, L, d_sp, d_ep, work, count, work2, count2, d_stats); } \
-        else { find_chain_kernel<S, P, 4><<<chain_grid, 256, 0, stream>>>(v, d_chars, L, d_sp, d_ep, work, count, work2, count2, d_stats); } } while(0)
+        if(chain_unroll == 1) { find_chain_kernel<S, P, 1><<<chain_grid, 256, 0, stream>>>(v, d_chars, L, d_sp, d_ep, work, count, work2, count2, d_stats, straggle); } \
+        else if(chain_unroll == 2) { find_chain_kernel<S, P, 2><<<chain_grid, 256, 0, stream>>>(v, d_chars, L, d_sp, d_ep, work, count, work2, count2, d_stats, straggle); } \
+        else { find_chain_kernel<S, P, 4><<<chain_grid, 256, 0, stream>>>(v, d_chars, L, d_sp, d_ep, work, count, work2, count2, d_stats, straggle); } } while(0)
       const u32 L = (u32)fixed_length;
       #define LAUNCH_FAST(S, P, U) find_fast_kernel<S, P, U><<<fast_grid, 256, 0, stream>>>(v, d_chars, L, n, d_sp, d_ep, work, count, quad_work, quad_count, d_stats)
       #define LAUNCH_FAST_U(S, P) do { if(unroll == 1) { LAUNCH_FAST(S, P, 1); } else if(unroll == 2) { LAUNCH_FAST(S, P, 2); } else { LAUNCH_FAST(S, P, 4); } } while(0)

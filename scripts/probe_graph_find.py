@@ -50,6 +50,26 @@ def main():
         e1.record(stream); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
         print("kmer_table_k", k, "general kernel alone: ms", ms, "queries/s", n / ms * 1e3, flush=True)
+        # mixed lengths 16..256 (the configs[4] patterns), as generated and sorted by length
+        mc, mo = synth.mixed_length_patterns(seq, sites, alt, 1_000_000, 16, 256, seed=5, error_rate=0.0)
+        lens = np.diff(mo.astype(np.int64))
+        order = np.argsort(lens, kind="stable")
+        sc = np.concatenate([mc[int(mo[i]):int(mo[i + 1])] for i in order]) if os.environ.get("SORTED", "1") != "0" else None
+        for tag, cc, oo in (("mixed 16..256", mc, mo), ("mixed, sorted by length", sc, np.concatenate([[0], np.cumsum(lens[order])]).astype(np.uint64))):
+            if cc is None:
+                continue
+            m = oo.size - 1
+            dc = torch.from_numpy(cc).cuda(); do = torch.from_numpy(oo.view(np.int64)).cuda()
+            ds = torch.empty(m, dtype=torch.int64, device="cuda"); de = torch.empty_like(ds)
+            for _ in range(3):
+                index.find_device(dc, do, m, ds, de, stream.cuda_stream)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            for _ in range(5):
+                index.find_device(dc, do, m, ds, de, stream.cuda_stream)
+            e1.record(stream); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            print("kmer_table_k", k, tag, "ms", ms, "queries/s", m / ms * 1e3, "found", int((ds <= de).sum().item()), flush=True)
         index.close()
 
 
