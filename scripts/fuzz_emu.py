@@ -103,7 +103,7 @@ def main():
                     elif r < 0.4:
                         c[int(o[i]):int(o[i + 1])] |= 0x20
                     pats.append(bytes(c[int(o[i]):int(o[i + 1])]))
-        lengths = rng.integers(0, 40, size=600)
+        lengths = rng.integers(0, 40, size=(600 if rng.random() < 0.5 else 4200))     # (4096 patterns and more: the batch starts in the chain kernel)
         pats += [bytes(alphabet[rng.integers(0, alphabet.size if rng.random() < 0.3 else 16, size=int(ln))]) for ln in lengths]
         chars, offsets = orc.pack_patterns(pats)
 

@@ -716,6 +716,55 @@ def test_kmer_batches_two_kernel_form(monkeypatch):
                 gpu.close()
 
 
+def test_ragged_batches_start_in_the_chain_kernel():
+    """Batches in the offsets form (at least 4096 patterns of any lengths) start in find_chain_kernel's FRESH form -- k-mer table
+    probe, then one jump entry or one sector per round -- and the general kernel finishes its work list: equal to the oracle
+    for empty patterns, patterns shorter than the table, longer than 255 characters (left to the general kernel whole), up
+    to 600 characters, with substitutions, N / $ / # / garbage bytes, lower case and random patterns, on a linear text, a
+    repetitive one and a graph with bubbles, for every table shape; the counting variant agrees on what it found."""
+    rng = np.random.default_rng(61)
+    seq = synth.random_sequence(150_000, seed=61)
+    rep = np.concatenate([np.tile(synth.random_sequence(700, seed=62), 30), synth.random_sequence(20_000, seed=63)])
+    graph, sites, alt = synth.snp_graph(seq, seed=61, snp_rate=0.02)
+    alphabet = np.frombuffer(b"ACGTACGTACGTACGTacgtN$#x", dtype=np.uint8)
+    cases = (("linear", build_index(synth.linear_graph(seq), 16, 3)[0], lambda n, L, s: synth.patterns_from_sequence(seq, n, L, seed=s)),
+             ("repeats", build_index(synth.linear_graph(rep), 16, 3)[0], lambda n, L, s: synth.patterns_from_sequence(rep, n, L, seed=s)),
+             ("snp", build_index(graph, 16, 3)[0], lambda n, L, s: synth.patterns_from_snp_graph(seq, sites, alt, n, L, seed=s)))
+    for name, flat, sampler in cases:
+        ora = orc.OracleGCSA(flat)
+        pats = [b"", b"A", b"N", b"acgt"]
+        for L in (1, 3, 7, 8, 9, 15, 16, 17, 31, 32, 33, 63, 64, 65, 100, 200, 254, 255, 256, 257, 400, 600):
+            n = 260 if L <= 256 else 60
+            c, o = sampler(n, L, 300 + L)
+            c = c.copy()
+            for i in range(n):
+                r = i % 7
+                if r == 1:
+                    p = int(o[i]) + int(rng.integers(0, L)); c[p] = synth.COMP2CHAR[1 + (int(np.where(synth.COMP2CHAR == c[p])[0][0]) % 4)]
+                elif r == 2 and i % 14 == 2:
+                    c[int(o[i]) + int(rng.integers(0, L))] = alphabet[int(rng.integers(16, alphabet.size))]
+                elif r == 3:
+                    c[int(o[i]):int(o[i + 1])] |= 0x20
+                pats.append(bytes(c[int(o[i]):int(o[i + 1])]))
+        pats += [bytes(alphabet[rng.integers(0, 16, size=int(ln))]) for ln in rng.integers(0, 50, size=400)]
+        order = rng.permutation(len(pats))
+        pats = [pats[i] for i in order]
+        assert len(pats) >= 4096
+        chars, offsets = orc.pack_patterns(pats)
+        osp, oep, _ = ora.find_batch(chars, offsets, threads=4)
+        for options in (dict(kmer_table_k=8, jump_table=True, fused_table=True), dict(kmer_table_k=8, jump_table=True, fused_table=False),
+                        dict(kmer_table_k=9, jump_table="wide"), dict(kmer_table_k=6, jump_table=False), dict(kmer_table_k=2, jump_table=True)):
+            gpu = GCSA(flat, **options)
+            sp, ep = gpu.find_batch(chars, offsets)
+            bad = np.flatnonzero((sp != osp) | (ep != oep))
+            assert bad.size == 0, (name, options, bad[:5], [pats[i] for i in bad[:3]])
+            ssp, sep, st = gpu.find_batch(chars, offsets, stats=True)
+            assert (ssp == osp).all() and (sep == oep).all() and st["queries"] == len(pats)
+            hit = ~((osp + np.uint64(1)) > (oep + np.uint64(1)))       # Range::empty, include/gcsa/utils.h:93-101 ((0, -1) is empty)
+            assert st["found"] == int(np.count_nonzero(hit)) and st["total_length"] == int((oep - osp + np.uint64(1))[hit].sum())
+            gpu.close()
+
+
 def test_single_process_multi_gpu_entry_points():
     """gcsa_b200_find_fixed_host_multi / _find_host_multi / _locate_into_host_multi: the batch cut into blocks over several
     handles (here replicas on one device; tests/test_multi_gpu.py runs them on two devices) == the single-handle calls."""
